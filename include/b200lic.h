@@ -1,0 +1,234 @@
+/*
+ * b200lic.h -- flat C ABI of libb200lic.so, the sm_100a (B200) implementation of the RDO-PTQ hot path.
+ *
+ * The reference (Eric-qi/RDO-PTQ) is pure Python/PyTorch and has no FFI; its boundary is the Python
+ * class surface of task-oriented-PTQ/quantization and light-uniform-PTQ/quant_int.  Each entry point
+ * below replaces the ATen/cuDNN calls issued by the cited reference lines ("TO" =
+ * task-oriented-PTQ/quantization, "LU" = light-uniform-PTQ/quant_int; compressai 1.2.4 call sites
+ * are cited through the reference file that reaches them).  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 (unless typed otherwise) owned by the caller; the
+ *    library allocates nothing and keeps no pointer after the call returns;
+ *  - all work is enqueued on `stream` (a cudaStream_t); no call synchronises the host, so every entry
+ *    point is CUDA-graph capturable;
+ *  - activations are NCHW contiguous, conv weights [Cout,Cin,KH,KW], transposed-conv weights
+ *    [Cin,Cout,KH,KW] (PyTorch layouts);
+ *  - return value 0 on success, a negative B200LIC_ERR_* otherwise (never throws, never exits);
+ *    b200lic_last_error_string() describes the last failure of the calling thread;
+ *  - sm_100 only: on any other device every compute entry point returns B200LIC_ERR_ARCH.
+ */
+#ifndef B200LIC_H_
+#define B200LIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200lic_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define B200LIC_API __attribute__((visibility("default")))
+#else
+#define B200LIC_API
+#endif
+
+enum {
+  B200LIC_OK = 0,
+  B200LIC_ERR_ARG = -1,         /* bad shape / null pointer / unsupported combination of flags */
+  B200LIC_ERR_ARCH = -2,        /* current device is not sm_100 */
+  B200LIC_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed (see last_error_string) */
+  B200LIC_ERR_UNSUPPORTED = -4  /* valid request this build has no kernel for */
+};
+
+/* activation fused into a conv epilogue (TO quant_layer.py:128 `activation_function`) */
+enum { B200LIC_ACT_NONE = 0, B200LIC_ACT_RELU = 1, B200LIC_ACT_LEAKY_RELU = 2 };
+
+/* conv engine selection */
+enum {
+  B200LIC_ENGINE_AUTO = 0,   /* tcgen05 when the shape qualifies, else SIMT */
+  B200LIC_ENGINE_SIMT = 1,   /* fp32 CUDA-core implicit GEMM (exact fp32 products) */
+  B200LIC_ENGINE_TC = 2      /* tcgen05 tensor cores, split-bf16 operands, fp32 TMEM accumulation */
+};
+
+B200LIC_API int b200lic_version(void);
+B200LIC_API const char* b200lic_last_error_string(void);
+/* 0 when the current CUDA device is sm_100, B200LIC_ERR_ARCH otherwise. */
+B200LIC_API int b200lic_device_check(void);
+/* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
+B200LIC_API unsigned long long b200lic_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  per-channel weight range + fake-quant.
+ * The tensor is viewed as [outer, ch, inner] with the quantisation channel in the middle:
+ * conv weight -> (1, Cout, Cin*KH*KW); tconv weight -> (Cin, Cout, KH*KW); GDN gamma -> (1, C, C);
+ * per-tensor -> (1, 1, numel).
+ * replaces: TO quantizer.py:233-298 (init_quantization_scale, 'max' / 'max_scale'), LU quantizer.py:192-281.
+ * delta/zp: [ch].  Arithmetic is the reference's: fp64 range -> fp32 delta, zp = rint(rcp(delta) * -min).
+ * ---------------------------------------------------------------------------------------------- */
+B200LIC_API int b200lic_wq_init_minmax(const float* w, int outer, int ch, int inner, int n_bits, int scale_variant,
+                           int symmetric, float* delta, float* zero_point, b200lic_stream_t stream);
+
+/* replaces: TO quantizer.py:175-177 (UniformAffineQuantizer.forward), LU quantizer.py:171-177.
+ * Any of w_dq / codes / codes_u8 may be NULL.  codes are integer-valued fp32 in [0, n_levels-1]. */
+B200LIC_API int b200lic_wq_fake_quant(const float* w, const float* delta, const float* zero_point, int outer, int ch,
+                          int inner, int n_levels, float* w_dq, float* codes, uint8_t* codes_u8,
+                          b200lic_stream_t stream);
+
+/* LU quant_layer.py:121-122: w = (codes_u8 - zp) * delta */
+B200LIC_API int b200lic_wq_dequant_u8(const uint8_t* codes_u8, const float* delta, const float* zero_point, int outer,
+                          int ch, int inner, float* w_dq, b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6  AdaRound (learned hard sigmoid).
+ * replaces: TO quantizer.py:454-466 (init_alpha), :437-452 (forward / get_soft_targets),
+ * autograd of those + layer_opt.py:160-165 (rounding regulariser) + torch.optim.Adam (layer_opt.py:254,307).
+ * ---------------------------------------------------------------------------------------------- */
+B200LIC_API int b200lic_adaround_init_alpha(const float* w, const float* delta, int outer, int ch, int inner,
+                                float* alpha, b200lic_stream_t stream);
+/* soft != 0: x_int = floor(w/d) + h(alpha); else + (alpha >= 0).  codes may be NULL. */
+B200LIC_API int b200lic_adaround_fwd(const float* w, const float* alpha, const float* delta, const float* zero_point,
+                         int outer, int ch, int inner, int n_levels, int soft, float* w_q, float* codes,
+                         b200lic_stream_t stream);
+/* One fused step: d_alpha = grad_scale * d_wq * dWq/dalpha + d(reg)/dalpha; Adam(step) on alpha, m, v
+ * in place.  reg_b <= 0 disables the regulariser (warm-up).  reg_loss (device scalar, may be NULL) is
+ * atomically incremented by reg_weight * sum(1 - |2h-1|^b).  d_alpha_out (may be NULL) receives the
+ * gradient that was applied.  exp_avg == exp_avg_sq == NULL selects gradient-only mode (alpha untouched). */
+B200LIC_API int b200lic_adaround_bwd_adam(const float* w, float* alpha, const float* delta, const float* zero_point,
+                              const float* d_wq, float* exp_avg, float* exp_avg_sq, int outer, int ch,
+                              int inner, int n_levels, int step, float lr, float beta1, float beta2,
+                              float eps, float grad_scale, float reg_weight, float reg_b, float* reg_loss,
+                              float* d_alpha_out, b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8  activation quantisers.
+ * replaces: TO quantizer.py:81-121 (Handle_Parameter/ActQuant: dynamic per-channel, 4-D NCHW),
+ * LU quantizer.py:120-128 (static Q8.8).
+ * ---------------------------------------------------------------------------------------------- */
+/* minmax: [2*C] 32-bit words holding order-preserving keys of the per-channel (min, max) over (N,H,W);
+ * opaque to the caller, must be initialised by b200lic_actq_stats_init before b200lic_actq_stats. */
+B200LIC_API int b200lic_actq_stats_init(float* minmax, int C, b200lic_stream_t stream);
+B200LIC_API int b200lic_actq_stats(const float* x, int N, int C, int HW, float* minmax, b200lic_stream_t stream);
+B200LIC_API int b200lic_actq_apply(const float* x, const float* minmax, int N, int C, int HW, int n_bits, float* out,
+                       float* codes, b200lic_stream_t stream);
+B200LIC_API int b200lic_fixed_point(const float* x, size_t n, int a_l, int a_r, float* out, b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9 / K10  entropy-model likelihoods (compressai 1.2.4 semantics; reference call sites
+ * TO models/nic_cvt.py:297-308, quant_model.py:72-79).
+ * bits (device fp32 scalar, may be NULL) is atomically incremented by sum(-log2(lik)).
+ * ---------------------------------------------------------------------------------------------- */
+/* y_hat = rint(y - mu) + mu; lik = Phi((.5-|y_hat-mu|)/s) - Phi((-.5-|y_hat-mu|)/s), s = max(scale, scale_bound).
+ * means may be NULL (zero-mean).  scales/means may be strided views of one tensor (chunk(2,1)):
+ * element (n,c,i) lives at n*param_batch_stride + c*HW + i. */
+B200LIC_API int b200lic_gaussian_lik_fwd(const float* y, const float* scales, const float* means, int N, int C, int HW,
+                             long long param_batch_stride, float scale_bound, float lik_bound, float* y_hat,
+                             float* lik, float* bits, b200lic_stream_t stream);
+/* rint(y - mu) + mu only (GaussianConditional.quantize "dequantize"); means may be NULL. */
+B200LIC_API int b200lic_round_latent(const float* y, const float* means, size_t n, float* y_hat, b200lic_stream_t stream);
+/* Factorised prior, filters (3,3,3,3).  params: [C][58] = matrices 3+9+9+9+3 (raw, softplus applied inside),
+ * biases 3+3+3+3+1, factors 3+3+3+3 (raw, tanh applied inside).  medians: [C]. */
+B200LIC_API int b200lic_factorized_lik_fwd(const float* z, const float* params, const float* medians, int N, int C, int HW,
+                               float lik_bound, float* z_hat, float* lik, float* bits, b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K11  losses.
+ * replaces: TO quantizer.py:71-79 (lp_loss), losses/losses.py:20-28, test_datasets.py:21-33.
+ * ---------------------------------------------------------------------------------------------- */
+/* loss += scale * sum |pred-tgt|^p ; d_pred (may be NULL) = grad_scale * p*|d|^(p-1)*sign(d). */
+B200LIC_API int b200lic_lp_loss_fwd_bwd(const float* pred, const float* tgt, size_t n, float p, float scale, float grad_scale,
+                            float* loss, float* d_pred, b200lic_stream_t stream);
+/* out[0] += sum (a-b)^2 ; out[1] += sum (clamp(a,0,1)-b)^2 (test_datasets.py:98 clamps before PSNR). */
+B200LIC_API int b200lic_sq_err_sum(const float* a, const float* b, size_t n, float* out, b200lic_stream_t stream);
+/* out[0] += sum -log2(lik) */
+B200LIC_API int b200lic_bits_sum(const float* lik, size_t n, float* out, b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1/K2/K4/K5  convolutions as implicit GEMM.
+ * replaces: F.conv2d TO quant_layer.py:28,123 / LU quant_layer.py:27,128; F.conv_transpose2d
+ * quant_layer.py:36; their autograd (layer_opt.py:298-307, block_opt.py:299-309).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int N, Cin, H, W;         /* input  [N,Cin,H,W]   */
+  int Cout, Ho, Wo;         /* output [N,Cout,Ho,Wo] */
+  int KH, KW, stride, pad;  /* square stride/pad, dilation 1, groups 1 */
+  int act;                  /* B200LIC_ACT_* applied to the output (forward only) */
+  float act_slope;          /* LeakyReLU negative slope */
+  int engine;               /* B200LIC_ENGINE_* */
+  int in_square;            /* forward/wgrad: use x*x instead of x (GDN's 1x1 conv on x^2) */
+  int gdn_mode;             /* forward: 0 plain; 1 out = gdn_x * rsqrt(acc); 2 out = gdn_x * sqrt(acc) */
+  int fixed_point;          /* forward: apply LU Q8.8 round(clamp(v,-128,128)*256)/256 to the output */
+} b200lic_conv_desc;
+
+/* y = act(conv2d(x, w) + bias).  gdn_x (may be NULL unless gdn_mode) is [N,Cout,Ho,Wo]; norm_out (may be NULL)
+ * receives the pre-(r)sqrt accumulator in gdn_mode. */
+B200LIC_API int b200lic_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias,
+                     const float* gdn_x, float* norm_out, float* y, b200lic_stream_t stream);
+/* y = act(conv_transpose2d(x, w) + bias); w is [Cin,Cout,KH,KW]; Ho/Wo carry the output_padding. */
+B200LIC_API int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                       b200lic_stream_t stream);
+/* dw[Cout,Cin,KH,KW] = sum_pixels dy (x) x.  dw is overwritten. */
+B200LIC_API int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
+                       b200lic_stream_t stream);
+/* dw[Cin,Cout,KH,KW] for y = conv_transpose2d(x, w). */
+B200LIC_API int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
+                         b200lic_stream_t stream);
+/* dx[N,Cin,H,W] for y = conv2d(x, w). */
+B200LIC_API int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
+                       b200lic_stream_t stream);
+/* dx[N,Cin,H,W] for y = conv_transpose2d(x, w). */
+B200LIC_API int b200lic_deconv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
+                         b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  GDN / IGDN helpers (compressai GDN via TO quant_layer.py:142-154).
+ * ---------------------------------------------------------------------------------------------- */
+/* NonNegativeParametrizer forward: out = max(p, bound)^2 - pedestal. */
+B200LIC_API int b200lic_gdn_reparam_fwd(const float* p, size_t n, float bound, float pedestal, float* out,
+                            b200lic_stream_t stream);
+/* its backward incl. LowerBound's gate: dp = [(p>=bound)|(g<0)] * g, g = d_out*2*max(p,bound). */
+B200LIC_API int b200lic_gdn_reparam_bwd(const float* p, const float* d_out, size_t n, float bound, float* d_p,
+                            b200lic_stream_t stream);
+/* d_norm = dy * x * dfn(norm), dfn = -0.5*norm^-1.5 (GDN) or 0.5*norm^-0.5 (IGDN);
+ * dx_direct (may be NULL) = dy * fn(norm). */
+B200LIC_API int b200lic_gdn_bwd_prep(const float* x, const float* norm, const float* dy, size_t n, int inverse,
+                         float* d_norm, float* dx_direct, b200lic_stream_t stream);
+/* dx = dx_direct + 2*x*t   (t = gamma^T-contracted d_norm, produced by b200lic_conv_dgrad) */
+B200LIC_API int b200lic_gdn_bwd_finish(const float* x, const float* t, const float* dx_direct, size_t n, float* dx,
+                           b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * small fused elementwise helpers used by the block wrappers (TO quant_block.py:219-328) and the
+ * calibration loop (layer_opt.py:289-292).
+ * ---------------------------------------------------------------------------------------------- */
+/* out = act(a + b) ; b may be NULL */
+B200LIC_API int b200lic_add_act(const float* a, const float* b, size_t n, int act, float slope, float* out,
+                    b200lic_stream_t stream);
+/* d_in = d_out * act'(y) where y is the activation OUTPUT */
+B200LIC_API int b200lic_act_bwd(const float* y, const float* d_out, size_t n, int act, float slope, float* d_in,
+                    b200lic_stream_t stream);
+/* Batch pick + QDrop mix (layer_opt.py:289-292): out[b,:] = keep ? q[idx[b],:] : fp[idx[b],:] for b < rows.
+ * idx (int64, may be NULL = identity).  keep = mask[b,:] != 0 when mask (uint8) is given, else a counter-based
+ * hash RNG(seed, element) < prob. */
+B200LIC_API int b200lic_gather_mix(const float* q, const float* fp, const long long* idx, size_t rows, size_t row_elems,
+                       float prob, unsigned long long seed, const uint8_t* mask, float* out,
+                       b200lic_stream_t stream);
+/* out = a * sigmoid(b) + c   (AttentionBlock tail) */
+B200LIC_API int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out,
+                      b200lic_stream_t stream);
+/* |x| (ScaleHyperprior h_a input) */
+B200LIC_API int b200lic_abs(const float* x, size_t n, float* out, b200lic_stream_t stream);
+/* PixelShuffle(r) with optional fused activation: in [N, C*r*r, H, W] -> out [N, C, H*r, W*r] */
+B200LIC_API int b200lic_pixel_shuffle(const float* x, int N, int C, int H, int W, int r, int act, float slope, float* out,
+                          b200lic_stream_t stream);
+B200LIC_API int b200lic_pixel_unshuffle(const float* dy, int N, int C, int H, int W, int r, float* dx,
+                            b200lic_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LIC_H_ */

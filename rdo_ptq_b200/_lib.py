@@ -1,0 +1,108 @@
+"""ctypes binding of libb200lic.so (the C ABI declared in include/b200lic.h).
+
+There is deliberately no fallback: if the shared library is missing, or the device is not sm_100, every
+op raises.  Build with `python -c "import __graft_entry__ as g; g.build()"` or `make -C rdo_ptq_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200lic.so")
+
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_ARCH", -3: "ERR_CUDA", -4: "ERR_UNSUPPORTED"}
+ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+
+
+class B200LicError(RuntimeError):
+    def __init__(self, fn, code, msg):
+        super().__init__(f"b200lic_{fn} failed: {ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `b200lic_conv_desc`."""
+    _fields_ = [("N", C.c_int), ("Cin", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("Cout", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int),
+                ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+                ("act", C.c_int), ("act_slope", C.c_float), ("engine", C.c_int),
+                ("in_square", C.c_int), ("gdn_mode", C.c_int), ("fixed_point", C.c_int)]
+
+
+_P, _I, _F, _LL, _SZ, _ULL = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_ulonglong
+_D = C.POINTER(ConvDesc)
+
+# name -> argtypes (the trailing stream argument is appended automatically)
+SIGNATURES = {
+    "wq_init_minmax": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "wq_fake_quant": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "wq_dequant_u8": [_P, _P, _P, _I, _I, _I, _P],
+    "adaround_init_alpha": [_P, _P, _I, _I, _I, _P],
+    "adaround_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "adaround_bwd_adam": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _F, _P, _P],
+    "actq_stats_init": [_P, _I],
+    "actq_stats": [_P, _I, _I, _I, _P],
+    "actq_apply": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "fixed_point": [_P, _SZ, _I, _I, _P],
+    "gaussian_lik_fwd": [_P, _P, _P, _I, _I, _I, _LL, _F, _F, _P, _P, _P],
+    "round_latent": [_P, _P, _SZ, _P],
+    "factorized_lik_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
+    "lp_loss_fwd_bwd": [_P, _P, _SZ, _F, _F, _F, _P, _P],
+    "sq_err_sum": [_P, _P, _SZ, _P],
+    "bits_sum": [_P, _SZ, _P],
+    "conv_fwd": [_D, _P, _P, _P, _P, _P, _P],
+    "deconv_fwd": [_D, _P, _P, _P, _P],
+    "conv_wgrad": [_D, _P, _P, _P],
+    "deconv_wgrad": [_D, _P, _P, _P],
+    "conv_dgrad": [_D, _P, _P, _P],
+    "deconv_dgrad": [_D, _P, _P, _P],
+    "gdn_reparam_fwd": [_P, _SZ, _F, _F, _P],
+    "gdn_reparam_bwd": [_P, _P, _SZ, _F, _P],
+    "gdn_bwd_prep": [_P, _P, _P, _SZ, _I, _P, _P],
+    "gdn_bwd_finish": [_P, _P, _P, _SZ, _P],
+    "add_act": [_P, _P, _SZ, _I, _F, _P],
+    "act_bwd": [_P, _P, _SZ, _I, _F, _P],
+    "gather_mix": [_P, _P, _P, _SZ, _SZ, _F, _ULL, _P, _P],
+    "attn_gate": [_P, _P, _P, _SZ, _P],
+    "abs": [_P, _SZ, _P],
+    "pixel_shuffle": [_P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "pixel_unshuffle": [_P, _I, _I, _I, _I, _I, _P],
+}
+PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
+         "launch_count": (C.c_ulonglong, [])}
+
+_lib = None
+
+
+def exported_names():
+    """Every symbol include/b200lic.h declares (checked by the CPU test-suite)."""
+    return ["b200lic_" + n for n in list(SIGNATURES) + list(PLAIN)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built: the sm_100a CUDA library is mandatory (no CPU fallback); "
+                              "run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, "b200lic_" + name)
+            fn.restype, fn.argtypes = C.c_int, list(args) + [C.c_void_p]
+        for name, (res, args) in PLAIN.items():
+            fn = getattr(L, "b200lic_" + name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def call(name, *args, stream=None):
+    """Invoke b200lic_<name>(*args, stream); raise B200LicError on a non-zero return."""
+    L = lib()
+    rc = getattr(L, "b200lic_" + name)(*args, stream)
+    if rc != 0:
+        raise B200LicError(name, rc, L.b200lic_last_error_string().decode())
+
+
+def launch_count():
+    return int(lib().b200lic_launch_count())

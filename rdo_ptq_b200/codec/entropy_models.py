@@ -1,0 +1,94 @@
+"""compressai-style entropy models on libb200lic kernels (K9 Gaussian conditional, K10 factorised prior).
+
+Evaluation-mode semantics of compressai 1.2.4 (`quantize(..., "dequantize")`, likelihood lower bound 1e-9, scale
+lower bound 0.11), reached in the reference from task-oriented-PTQ/models/nic_cvt.py:297-308 and
+quant_model.py:72-79.  Each forward also leaves `last_bits` = sum(-log2 likelihood) (device scalar) so the
+bpp reduction (losses/losses.py:20-23) needs no second pass over the likelihood tensor.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .layers import LowerBound
+
+
+class EntropyBottleneck(nn.Module):
+    def __init__(self, channels, tail_mass=1e-9, init_scale=10, filters=(3, 3, 3, 3), likelihood_bound=1e-9):
+        super().__init__()
+        self.channels, self.filters = int(channels), tuple(int(f) for f in filters)
+        if self.filters != (3, 3, 3, 3):
+            raise NotImplementedError("K10 is specialised for compressai's default filters (3,3,3,3)")
+        self.init_scale, self.tail_mass = float(init_scale), float(tail_mass)
+        self.likelihood_bound = float(likelihood_bound)
+        f = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for i in range(len(self.filters) + 1):
+            init = np.log(np.expm1(1 / scale / f[i + 1]))
+            self.register_parameter(f"_matrix{i:d}", nn.Parameter(torch.full((channels, f[i + 1], f[i]), float(init))))
+            self.register_parameter(f"_bias{i:d}", nn.Parameter(torch.empty(channels, f[i + 1], 1).uniform_(-0.5, 0.5)))
+            if i < len(self.filters):
+                self.register_parameter(f"_factor{i:d}", nn.Parameter(torch.zeros(channels, f[i + 1], 1)))
+        self.quantiles = nn.Parameter(torch.Tensor([-self.init_scale, 0, self.init_scale]).repeat(channels, 1, 1))
+        t = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-t, 0, t]))
+        self.last_bits = None
+
+    def _get_medians(self):
+        return self.quantiles[:, :, 1:2]
+
+    def packed_params(self):
+        """[C,58] = matrices 3+9+9+9+3 | biases 3+3+3+3+1 | factors 3+3+3+3 (layout of b200lic_factorized_lik_fwd)."""
+        C_ = self.channels
+        parts = [getattr(self, f"_matrix{i:d}").detach().reshape(C_, -1) for i in range(5)]
+        parts += [getattr(self, f"_bias{i:d}").detach().reshape(C_, -1) for i in range(5)]
+        parts += [getattr(self, f"_factor{i:d}").detach().reshape(C_, -1) for i in range(4)]
+        return torch.cat(parts, dim=1).contiguous()
+
+    def quantize(self, inputs, mode, means=None):
+        if mode != "dequantize":
+            raise NotImplementedError("only the evaluation-mode quantiser is on the hot path")
+        return ops.round_latent(inputs, means)
+
+    def forward(self, x, training=None):
+        training = self.training if training is None else training
+        if training:
+            raise NotImplementedError("EntropyBottleneck: the additive-noise training path is not on the PTQ hot path "
+                                      "(call .eval(); the reference evaluates under model.eval())")
+        z_hat, lik, bits = ops.factorized_lik(x, self.packed_params(), self._get_medians().detach().reshape(-1),
+                                              self.likelihood_bound)
+        self.last_bits = bits
+        return z_hat, lik
+
+    def loss(self):
+        """aux loss |logits(quantiles) - target| (quant_model.py:72-79).  Parameter-sized (C x 3) host-side helper,
+        not a data-path op; evaluated with plain tensor ops."""
+        import torch.nn.functional as F
+        v = self.quantiles
+        for i in range(5):
+            v = torch.matmul(F.softplus(getattr(self, f"_matrix{i:d}").detach()), v) + getattr(self, f"_bias{i:d}").detach()
+            if i < 4:
+                v = v + torch.tanh(getattr(self, f"_factor{i:d}").detach()) * torch.tanh(v)
+        return torch.abs(v - self.target).sum()
+
+
+class GaussianConditional(nn.Module):
+    def __init__(self, scale_table=None, scale_bound=0.11, tail_mass=1e-9, likelihood_bound=1e-9):
+        super().__init__()
+        self.scale_bound, self.likelihood_bound = float(scale_bound), float(likelihood_bound)
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self.last_bits = None
+
+    def quantize(self, inputs, mode, means=None):
+        if mode != "dequantize":
+            raise NotImplementedError("only the evaluation-mode quantiser is on the hot path")
+        return ops.round_latent(inputs, means)
+
+    def forward(self, inputs, scales, means=None, training=None):
+        training = self.training if training is None else training
+        if training:
+            raise NotImplementedError("GaussianConditional: the additive-noise training path is not on the PTQ hot "
+                                      "path (call .eval())")
+        y_hat, lik, bits = ops.gaussian_lik(inputs, scales, means, self.scale_bound, self.likelihood_bound)
+        self.last_bits = bits
+        return y_hat, lik

@@ -1,0 +1,68 @@
+// libb200lic: error reporting, device gate and launch accounting (include/b200lic.h).
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace b200lic {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+struct DevInfo {
+  int major = -1, minor = -1, sms = 0;
+};
+static DevInfo g_dev[64];
+
+static DevInfo* dev_info() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  DevInfo* d = &g_dev[dev];
+  if (d->major < 0) {
+    int major = 0, minor = 0, sms = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return nullptr;
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    d->minor = minor;
+    d->sms = sms;
+    d->major = major;
+  }
+  return d;
+}
+
+int check_arch() {
+  DevInfo* d = dev_info();
+  if (!d) {
+    set_error("no CUDA device available (cudaGetDevice failed): libb200lic has no CPU fallback");
+    (void)cudaGetLastError();
+    return B200LIC_ERR_ARCH;
+  }
+  if (d->major != 10) {
+    set_error("device is sm_%d%d; libb200lic is built for sm_100a (B200) only", d->major, d->minor);
+    return B200LIC_ERR_ARCH;
+  }
+  return B200LIC_OK;
+}
+
+int num_sms() {
+  DevInfo* d = dev_info();
+  return (d && d->sms > 0) ? d->sms : 148;
+}
+
+}  // namespace b200lic
+
+extern "C" {
+int b200lic_version(void) { return 100; }
+const char* b200lic_last_error_string(void) { return b200lic::g_err; }
+int b200lic_device_check(void) { return b200lic::check_arch(); }
+unsigned long long b200lic_launch_count(void) { return b200lic::g_launches.load(); }
+}

@@ -1,0 +1,95 @@
+// Shared plumbing of libb200lic: error reporting, arch gate, launch accounting, warp/block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/b200lic.h"
+
+namespace b200lic {
+
+void set_error(const char* fmt, ...);
+int check_arch();                       // B200LIC_OK iff current device is sm_100
+void count_launch(int n = 1);
+int num_sms();
+
+#define B200_REQUIRE(cond, ...)                              \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      ::b200lic::set_error(__VA_ARGS__);                     \
+      return B200LIC_ERR_ARG;                                \
+    }                                                        \
+  } while (0)
+
+#define B200_ARCH_GATE()                                     \
+  do {                                                       \
+    int _a = ::b200lic::check_arch();                        \
+    if (_a != B200LIC_OK) return _a;                         \
+  } while (0)
+
+#define B200_LAUNCH_CHECK(name)                                                        \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      ::b200lic::set_error("%s: launch failed: %s", name, cudaGetErrorString(_e));     \
+      return B200LIC_ERR_CUDA;                                                         \
+    }                                                                                  \
+    ::b200lic::count_launch();                                                         \
+  } while (0)
+
+static inline cudaStream_t as_stream(b200lic_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Persistent-style 1-D grid: a multiple of the SM count, capped by the work available.
+static inline int grid_for(size_t work_items, int per_block, int blocks_per_sm = 8) {
+  size_t need = (work_items + per_block - 1) / per_block;
+  size_t cap = (size_t)num_sms() * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = lane < nw ? red[lane] : 0.f;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// Order-preserving float <-> uint key (for atomicMin/atomicMax on floats).
+__device__ __forceinline__ unsigned f2key(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == B200LIC_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == B200LIC_ACT_LEAKY_RELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+}  // namespace b200lic

@@ -1,0 +1,339 @@
+// K11 (loss reductions) and the small fused elementwise helpers around the conv kernels.
+// All HBM-bound: float4 where alignment allows, grid a multiple of the SM count, one atomic per CTA.
+//
+// Reference lines restated: quantizer.py:71-79 (lp_loss), losses/losses.py:20-28, test_datasets.py:21-33,98,
+// quant_block.py:219-328 (residual add / LeakyReLU placement), layer_opt.py:291-292 (QDrop mix),
+// compressai GDN reparametrisation (via quant_layer.py:142-154).
+#include "common.cuh"
+
+namespace b200lic {
+
+// Generic float4-vectorised elementwise launcher: F::apply(a,b,c) -> out, any of b/c may be unused.
+template <typename F>
+__global__ void __launch_bounds__(256) ew_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                  const float* __restrict__ c, float* __restrict__ out, size_t n, F f) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)out) & 15) == 0;
+  if (vec) {
+    const size_t n4 = n >> 2;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i);
+      const float4 bv = b ? __ldg(reinterpret_cast<const float4*>(b) + i) : zero;
+      const float4 cv = c ? __ldg(reinterpret_cast<const float4*>(c) + i) : zero;
+      float4 o;
+      o.x = f(av.x, bv.x, cv.x, 4 * i);
+      o.y = f(av.y, bv.y, cv.y, 4 * i + 1);
+      o.z = f(av.z, bv.z, cv.z, 4 * i + 2);
+      o.w = f(av.w, bv.w, cv.w, 4 * i + 3);
+      reinterpret_cast<float4*>(out)[i] = o;
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) out[i] = f(a[i], b ? b[i] : 0.f, c ? c[i] : 0.f, i);
+  } else {
+    for (size_t i = tid; i < n; i += stride) out[i] = f(a[i], b ? b[i] : 0.f, c ? c[i] : 0.f, i);
+  }
+}
+
+template <typename F>
+static int launch_ew(const char* name, const float* a, const float* b, const float* c, float* out, size_t n, F f,
+                     cudaStream_t s) {
+  if (n == 0) return B200LIC_OK;
+  ew_kernel<F><<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(a, b, c, out, n, f);
+  B200_LAUNCH_CHECK(name);
+  return B200LIC_OK;
+}
+
+struct AddAct {
+  int act;
+  float slope;
+  __device__ float operator()(float a, float b, float, size_t) const { return apply_act(a + b, act, slope); }
+};
+struct ActBwd {  // a = activation output y, b = d_out
+  int act;
+  float slope;
+  __device__ float operator()(float y, float g, float, size_t) const {
+    if (act == B200LIC_ACT_RELU) return y > 0.f ? g : 0.f;
+    if (act == B200LIC_ACT_LEAKY_RELU) return y > 0.f ? g : g * slope;
+    return g;
+  }
+};
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+// Batch pick + QDrop mix in one pass: out[b, :] = keep ? q[idx[b], :] : fp[idx[b], :]
+__global__ void __launch_bounds__(256)
+    gather_mix_kernel(const float* __restrict__ q, const float* __restrict__ fp, const long long* __restrict__ idx,
+                      size_t row, size_t n, float prob, unsigned long long seed, const uint8_t* __restrict__ mask,
+                      float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / row, e = i - b * row;
+    const size_t src = (idx ? (size_t)idx[b] : b) * row + e;
+    bool keep;
+    if (mask) keep = mask[i] != 0;
+    else if (prob >= 1.f) keep = true;
+    else {
+      const unsigned r = (unsigned)(mix64(seed ^ mix64((unsigned long long)i)) >> 40);  // 24 random bits
+      keep = ((float)r * (1.f / 16777216.f)) < prob;
+    }
+    out[i] = keep ? __ldg(q + src) : __ldg(fp + src);
+  }
+}
+struct AttnGate {
+  __device__ float operator()(float a, float b, float c, size_t) const { return a * (1.f / (1.f + expf(-b))) + c; }
+};
+struct Abs {
+  __device__ float operator()(float a, float, float, size_t) const { return fabsf(a); }
+};
+struct ReparamFwd {
+  float bound, pedestal;
+  __device__ float operator()(float p, float, float, size_t) const {
+    const float l = fmaxf(p, bound);
+    return l * l - pedestal;
+  }
+};
+struct ReparamBwd {  // a = p, b = d_out
+  float bound;
+  __device__ float operator()(float p, float g, float, size_t) const {
+    const float gl = g * 2.f * fmaxf(p, bound);
+    return (p >= bound || gl < 0.f) ? gl : 0.f;
+  }
+};
+struct GdnBwdDnorm {  // a = x, b = norm, c = dy
+  int inverse;
+  __device__ float operator()(float x, float nrm, float dy, size_t) const {
+    const float r = rsqrtf(nrm);
+    return inverse ? dy * x * 0.5f * r : dy * x * (-0.5f) * r * r * r;
+  }
+};
+struct GdnBwdDirect {  // a = norm, b = dy
+  int inverse;
+  __device__ float operator()(float nrm, float dy, float, size_t) const {
+    return inverse ? dy * sqrtf(nrm) : dy * rsqrtf(nrm);
+  }
+};
+struct GdnBwdFinish {  // a = x, b = t, c = dx_direct
+  __device__ float operator()(float x, float t, float d, size_t) const { return d + 2.f * x * t; }
+};
+
+// ---- reductions ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lp_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                       size_t n, float p, float scale, float grad_scale,
+                                                       float* __restrict__ loss, float* __restrict__ d_pred) {
+  __shared__ float red[32];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  const bool p2 = (p == 2.f);
+  auto one = [&](float a, float b, float& g) {
+    const float d = a - b;
+    if (p2) {
+      acc += d * d;
+      g = grad_scale * 2.f * d;
+    } else {
+      const float ad = fabsf(d);
+      const float pw = powf(ad, p - 1.f);
+      acc += pw * ad;
+      g = grad_scale * p * pw * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+    }
+  };
+  const bool vec = (((uintptr_t)pred | (uintptr_t)tgt | (uintptr_t)d_pred) & 15) == 0;
+  if (vec) {
+    const size_t n4 = n >> 2;
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(tgt) + i);
+      float4 g;
+      one(a.x, b.x, g.x);
+      one(a.y, b.y, g.y);
+      one(a.z, b.z, g.z);
+      one(a.w, b.w, g.w);
+      if (d_pred) reinterpret_cast<float4*>(d_pred)[i] = g;
+    }
+    for (size_t i = (n4 << 2) + tid; i < n; i += stride) {
+      float g;
+      one(pred[i], tgt[i], g);
+      if (d_pred) d_pred[i] = g;
+    }
+  } else {
+    for (size_t i = tid; i < n; i += stride) {
+      float g;
+      one(pred[i], tgt[i], g);
+      if (d_pred) d_pred[i] = g;
+    }
+  }
+  if (loss) {
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss, scale * tot);
+  }
+}
+
+__global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                                      float* __restrict__ out) {
+  __shared__ float red[32];
+  float s0 = 0.f, s1 = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float av = __ldg(a + i), bv = __ldg(b + i);
+    const float d0 = av - bv, d1 = fminf(fmaxf(av, 0.f), 1.f) - bv;
+    s0 += d0 * d0;
+    s1 += d1 * d1;
+  }
+  const float t0 = block_sum(s0, red);
+  const float t1 = block_sum(s1, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(out, t0);
+    atomicAdd(out + 1, t1);
+  }
+}
+
+__global__ void __launch_bounds__(256) bits_sum_kernel(const float* __restrict__ lik, size_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s -= log2f(__ldg(lik + i));
+  const float t = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
+// ---- pixel shuffle (compressai subpel_conv3x3 tail; quant_layer.py:108-111 adds the LeakyReLU) -------------------
+__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const float* __restrict__ x, int C, int H, int W, int r,
+                                                             size_t n, int act, float slope, int inverse,
+                                                             float* __restrict__ out) {
+  // forward: out[n,c,h*r+i,w*r+j] = act(x[n,c*r*r+i*r+j,h,w]); inverse: dx[...] = dy[...] (same index map)
+  const int Ho = H * r, Wo = W * r;
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(o % Wo);
+    const int ho = (int)((o / Wo) % Ho);
+    const int c = (int)((o / ((size_t)Wo * Ho)) % C);
+    const int b = (int)(o / ((size_t)Wo * Ho * C));
+    const int i = ho % r, j = wo % r, h = ho / r, w = wo / r;
+    const size_t src = (((size_t)b * C * r * r + (size_t)c * r * r + i * r + j) * H + h) * W + w;
+    if (inverse) out[src] = x[o];
+    else out[o] = apply_act(__ldg(x + src), act, slope);
+  }
+}
+
+}  // namespace b200lic
+
+using namespace b200lic;
+
+extern "C" {
+
+int b200lic_lp_loss_fwd_bwd(const float* pred, const float* tgt, size_t n, float p, float scale, float grad_scale,
+                            float* loss, float* d_pred, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(pred && tgt, "lp_loss_fwd_bwd: null pointer");
+  B200_REQUIRE(p >= 1.f, "lp_loss_fwd_bwd: p=%f < 1", p);
+  if (n == 0) return B200LIC_OK;
+  lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, as_stream(stream)>>>(pred, tgt, n, p, scale, grad_scale, loss,
+                                                                             d_pred);
+  B200_LAUNCH_CHECK("lp_loss_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_sq_err_sum(const float* a, const float* b, size_t n, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(a && b && out, "sq_err_sum: null pointer");
+  if (n == 0) return B200LIC_OK;
+  sq_err_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(a, b, n, out);
+  B200_LAUNCH_CHECK("sq_err_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_bits_sum(const float* lik, size_t n, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(lik && out, "bits_sum: null pointer");
+  if (n == 0) return B200LIC_OK;
+  bits_sum_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(lik, n, out);
+  B200_LAUNCH_CHECK("bits_sum_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_gdn_reparam_fwd(const float* p, size_t n, float bound, float pedestal, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(p && out, "gdn_reparam_fwd: null pointer");
+  return launch_ew("gdn_reparam_fwd", p, nullptr, nullptr, out, n, ReparamFwd{bound, pedestal}, as_stream(stream));
+}
+
+int b200lic_gdn_reparam_bwd(const float* p, const float* d_out, size_t n, float bound, float* d_p,
+                            b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(p && d_out && d_p, "gdn_reparam_bwd: null pointer");
+  return launch_ew("gdn_reparam_bwd", p, d_out, nullptr, d_p, n, ReparamBwd{bound}, as_stream(stream));
+}
+
+int b200lic_gdn_bwd_prep(const float* x, const float* norm, const float* dy, size_t n, int inverse, float* d_norm,
+                         float* dx_direct, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && norm && dy && d_norm, "gdn_bwd_prep: null pointer");
+  int rc = launch_ew("gdn_bwd_dnorm", x, norm, dy, d_norm, n, GdnBwdDnorm{inverse}, as_stream(stream));
+  if (rc != B200LIC_OK || !dx_direct) return rc;
+  return launch_ew("gdn_bwd_direct", norm, dy, nullptr, dx_direct, n, GdnBwdDirect{inverse}, as_stream(stream));
+}
+
+int b200lic_gdn_bwd_finish(const float* x, const float* t, const float* dx_direct, size_t n, float* dx,
+                           b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && t && dx_direct && dx, "gdn_bwd_finish: null pointer");
+  return launch_ew("gdn_bwd_finish", x, t, dx_direct, dx, n, GdnBwdFinish{}, as_stream(stream));
+}
+
+int b200lic_add_act(const float* a, const float* b, size_t n, int act, float slope, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(a && out, "add_act: null pointer");
+  return launch_ew("add_act", a, b, nullptr, out, n, AddAct{act, slope}, as_stream(stream));
+}
+
+int b200lic_act_bwd(const float* y, const float* d_out, size_t n, int act, float slope, float* d_in,
+                    b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(y && d_out && d_in, "act_bwd: null pointer");
+  return launch_ew("act_bwd", y, d_out, nullptr, d_in, n, ActBwd{act, slope}, as_stream(stream));
+}
+
+int b200lic_gather_mix(const float* q, const float* fp, const long long* idx, size_t rows, size_t row_elems, float prob,
+                       unsigned long long seed, const uint8_t* mask, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(q && fp && out, "gather_mix: null pointer");
+  const size_t n = rows * row_elems;
+  if (n == 0) return B200LIC_OK;
+  gather_mix_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(q, fp, idx, row_elems, n, prob, seed, mask, out);
+  B200_LAUNCH_CHECK("gather_mix_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(a && b && c && out, "attn_gate: null pointer");
+  return launch_ew("attn_gate", a, b, c, out, n, AttnGate{}, as_stream(stream));
+}
+
+int b200lic_abs(const float* x, size_t n, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && out, "abs: null pointer");
+  return launch_ew("abs", x, nullptr, nullptr, out, n, Abs{}, as_stream(stream));
+}
+
+int b200lic_pixel_shuffle(const float* x, int N, int C, int H, int W, int r, int act, float slope, float* out,
+                          b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && out && N > 0 && C > 0 && H > 0 && W > 0 && r > 0, "pixel_shuffle: bad arguments");
+  const size_t n = (size_t)N * C * H * W * r * r;
+  pixel_shuffle_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, C, H, W, r, n, act, slope, 0, out);
+  B200_LAUNCH_CHECK("pixel_shuffle_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_pixel_unshuffle(const float* dy, int N, int C, int H, int W, int r, float* dx, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(dy && dx && N > 0 && C > 0 && H > 0 && W > 0 && r > 0, "pixel_unshuffle: bad arguments");
+  const size_t n = (size_t)N * C * H * W * r * r;
+  pixel_shuffle_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(dy, C, H, W, r, n, 0, 0.f, 1, dx);
+  B200_LAUNCH_CHECK("pixel_shuffle_kernel(inverse)");
+  return B200LIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+// K7 (per-channel weight range + fake-quant) and K6 (AdaRound fwd / fused bwd + regulariser + Adam).
+// Compiled with -fmad=false: the integer codes are a bit-exact contract, so every fp32 operation is
+// issued exactly as the reference issues it (true division, rint, separate mul/add).
+//
+// Reference arithmetic restated (not translated): task-oriented-PTQ/quantization/quantizer.py
+//   :281-298 range -> (delta, zero_point); :175-177 fake-quant; :437-452 AdaRound forward;
+//   :454-466 alpha init; layer_opt.py:160-165 rounding regulariser; torch.optim.Adam.
+#include "common.cuh"
+
+namespace b200lic {
+
+constexpr float kZeta = 1.1f, kGamma = -0.1f;
+constexpr float kStretch = 1.2f;  // fl32(zeta - gamma) = fl32(1.2000000000000002)
+
+// ---- K7a: one CTA per quantisation channel; tensor viewed as [outer, ch, inner] ---------------------
+__global__ void __launch_bounds__(256) wq_minmax_kernel(const float* __restrict__ w, int outer, int ch, int inner,
+                                                         int n_bits, int scale_variant, int symmetric,
+                                                         float* __restrict__ delta, float* __restrict__ zp) {
+  const int c = blockIdx.x;
+  float mn = INFINITY, mx = -INFINITY;
+  const size_t per_outer = (size_t)ch * inner;
+  const size_t total = (size_t)outer * inner;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const size_t o = i / inner, k = i - o * inner;
+    const float v = __ldg(w + o * per_outer + (size_t)c * inner + k);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  __shared__ float smn[8], smx[8];
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+      mn = fminf(mn, smn[i]);
+      mx = fmaxf(mx, smx[i]);
+    }
+    // float64 range arithmetic on the `.item()` values, then one rounding to fp32 (quantizer.py:282-297)
+    double lo = fmin((double)mn, 0.0), hi = fmax((double)mx, 0.0);
+    if (scale_variant) {
+      lo = lo * (double)(n_bits + 2) / 8.0;
+      hi = hi * (double)(n_bits + 2) / 8.0;
+    }
+    if (symmetric) {
+      const double a = fmax(fabs(lo), hi);
+      lo = lo < 0 ? -a : 0.0;
+      hi = a;
+    }
+    const double levels = (double)((1 << n_bits) - 1);
+    float d = (float)((hi - lo) / levels);
+    d = fmaxf(d, 1e-8f);
+    // (-x_min / delta) on a 0-dim tensor is delta.reciprocal() * (-x_min) in fp32 (Tensor.__rdiv__)
+    const float z = rintf(__fmul_rn(__frcp_rn(d), (float)(-lo)));
+    delta[c] = d;
+    zp[c] = z;
+  }
+}
+
+// ---- K7b: fake-quant -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wq_fake_quant_kernel(const float* __restrict__ w, const float* __restrict__ delta,
+                                                             const float* __restrict__ zp, size_t n, int ch, int inner,
+                                                             float top, float* __restrict__ w_dq,
+                                                             float* __restrict__ codes, uint8_t* __restrict__ codes_u8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / inner) % ch);
+    const float d = __ldg(delta + c), z = __ldg(zp + c);
+    float q = __fadd_rn(rintf(__fdiv_rn(w[i], d)), z);
+    q = fminf(fmaxf(q, 0.f), top);
+    if (codes) codes[i] = q;
+    if (codes_u8) codes_u8[i] = (uint8_t)q;
+    if (w_dq) w_dq[i] = __fmul_rn(__fsub_rn(q, z), d);
+  }
+}
+
+__global__ void __launch_bounds__(256) wq_dequant_u8_kernel(const uint8_t* __restrict__ q, const float* __restrict__ delta,
+                                                             const float* __restrict__ zp, size_t n, int ch, int inner,
+                                                             float* __restrict__ w_dq) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / inner) % ch);
+    w_dq[i] = __fmul_rn(__fsub_rn((float)q[i], __ldg(zp + c)), __ldg(delta + c));
+  }
+}
+
+// ---- K6 ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float a) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-a))); }
+
+__global__ void __launch_bounds__(256) adaround_init_kernel(const float* __restrict__ w, const float* __restrict__ delta,
+                                                             size_t n, int ch, int inner, float* __restrict__ alpha) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / inner) % ch);
+    const float t = __fdiv_rn(w[i], __ldg(delta + c));
+    const float rest = __fsub_rn(t, floorf(t));
+    // -log((zeta-gamma)/(rest-gamma) - 1); scalar/tensor is reciprocal()*scalar in torch
+    const float r = __fmul_rn(__frcp_rn(__fsub_rn(rest, kGamma)), kStretch);
+    alpha[i] = -logf(__fsub_rn(r, 1.f));
+  }
+}
+
+__global__ void __launch_bounds__(256) adaround_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha,
+                                                            const float* __restrict__ delta, const float* __restrict__ zp,
+                                                            size_t n, int ch, int inner, float top, int soft,
+                                                            float* __restrict__ w_q, float* __restrict__ codes) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / inner) % ch);
+    const float d = __ldg(delta + c), z = __ldg(zp + c);
+    const float base = floorf(__fdiv_rn(w[i], d));
+    const float a = alpha[i];
+    float up;
+    if (soft) {
+      const float s = __fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma);
+      up = fminf(fmaxf(s, 0.f), 1.f);
+    } else {
+      up = a >= 0.f ? 1.f : 0.f;
+    }
+    float q = __fadd_rn(__fadd_rn(base, up), z);
+    q = fminf(fmaxf(q, 0.f), top);
+    if (codes) codes[i] = q;
+    if (w_q) w_q[i] = __fmul_rn(__fsub_rn(q, z), d);
+  }
+}
+
+struct AdamArgs {
+  float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps;
+};
+
+__global__ void __launch_bounds__(256)
+    adaround_bwd_adam_kernel(const float* __restrict__ w, float* __restrict__ alpha, const float* __restrict__ delta,
+                             const float* __restrict__ zp, const float* __restrict__ d_wq, float* __restrict__ m,
+                             float* __restrict__ v, size_t n, int ch, int inner, float top, AdamArgs ad,
+                             float grad_scale, float reg_weight, float reg_b, float* __restrict__ reg_loss,
+                             float* __restrict__ d_alpha_out) {
+  __shared__ float red[32];
+  float reg_acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / inner) % ch);
+    const float d = __ldg(delta + c), z = __ldg(zp + c);
+    const float a = alpha[i];
+    const float sg = sigmoidf_(a);
+    const float s = __fadd_rn(__fmul_rn(sg, kStretch), kGamma);
+    const float h = fminf(fmaxf(s, 0.f), 1.f);
+    // autograd of clamp passes the gradient on the closed interval
+    const float dh_da = (s >= 0.f && s <= 1.f) ? kStretch * sg * (1.f - sg) : 0.f;
+    const float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(w[i], d)), h), z);
+    float g = 0.f;
+    if (xi >= 0.f && xi <= top) g = grad_scale * d_wq[i] * d * dh_da;
+    if (reg_b > 0.f) {
+      const float u = fabsf(h - 0.5f) * 2.f;          // |2h-1|
+      const float ub1 = powf(u, reg_b - 1.f);
+      reg_acc += 1.f - ub1 * u;
+      const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
+      g += -reg_weight * reg_b * ub1 * 2.f * sgn * dh_da;
+    }
+    if (d_alpha_out) d_alpha_out[i] = g;
+    if (m == nullptr) continue;  // gradient-only mode (autograd surface); no optimiser state touched
+    const float mi = ad.beta1 * m[i] + (1.f - ad.beta1) * g;
+    const float vi = ad.beta2 * v[i] + (1.f - ad.beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * ad.inv_sqrt_bc2 + ad.eps;
+    alpha[i] = a - ad.lr_over_bc1 * (mi / denom);
+  }
+  if (reg_loss != nullptr && reg_b > 0.f) {
+    const float tot = block_sum(reg_acc, red);
+    if (threadIdx.x == 0) atomicAdd(reg_loss, reg_weight * tot);
+  }
+}
+
+}  // namespace b200lic
+
+using namespace b200lic;
+
+extern "C" {
+
+int b200lic_wq_init_minmax(const float* w, int outer, int ch, int inner, int n_bits, int scale_variant,
+                           int symmetric, float* delta, float* zero_point, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && zero_point, "wq_init_minmax: null pointer");
+  B200_REQUIRE(outer > 0 && ch > 0 && inner > 0, "wq_init_minmax: bad shape (%d,%d,%d)", outer, ch, inner);
+  B200_REQUIRE(n_bits >= 2 && n_bits <= 16, "wq_init_minmax: n_bits=%d outside [2,16]", n_bits);
+  wq_minmax_kernel<<<ch, 256, 0, as_stream(stream)>>>(w, outer, ch, inner, n_bits, scale_variant, symmetric, delta,
+                                                      zero_point);
+  B200_LAUNCH_CHECK("wq_minmax_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_wq_fake_quant(const float* w, const float* delta, const float* zero_point, int outer, int ch, int inner,
+                          int n_levels, float* w_dq, float* codes, uint8_t* codes_u8, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && zero_point, "wq_fake_quant: null pointer");
+  B200_REQUIRE(outer > 0 && ch > 0 && inner > 0 && n_levels >= 2, "wq_fake_quant: bad shape");
+  B200_REQUIRE(!codes_u8 || n_levels <= 256, "wq_fake_quant: uint8 codes need n_levels <= 256");
+  const size_t n = (size_t)outer * ch * inner;
+  wq_fake_quant_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, delta, zero_point, n, ch, inner,
+                                                                        (float)(n_levels - 1), w_dq, codes, codes_u8);
+  B200_LAUNCH_CHECK("wq_fake_quant_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_wq_dequant_u8(const uint8_t* codes_u8, const float* delta, const float* zero_point, int outer, int ch,
+                          int inner, float* w_dq, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(codes_u8 && delta && zero_point && w_dq, "wq_dequant_u8: null pointer");
+  const size_t n = (size_t)outer * ch * inner;
+  wq_dequant_u8_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(codes_u8, delta, zero_point, n, ch, inner, w_dq);
+  B200_LAUNCH_CHECK("wq_dequant_u8_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_adaround_init_alpha(const float* w, const float* delta, int outer, int ch, int inner, float* alpha,
+                                b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && alpha, "adaround_init_alpha: null pointer");
+  const size_t n = (size_t)outer * ch * inner;
+  adaround_init_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, delta, n, ch, inner, alpha);
+  B200_LAUNCH_CHECK("adaround_init_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_adaround_fwd(const float* w, const float* alpha, const float* delta, const float* zero_point, int outer,
+                         int ch, int inner, int n_levels, int soft, float* w_q, float* codes, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && alpha && delta && zero_point, "adaround_fwd: null pointer");
+  const size_t n = (size_t)outer * ch * inner;
+  adaround_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, alpha, delta, zero_point, n, ch, inner,
+                                                                       (float)(n_levels - 1), soft, w_q, codes);
+  B200_LAUNCH_CHECK("adaround_fwd_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_adaround_bwd_adam(const float* w, float* alpha, const float* delta, const float* zero_point,
+                              const float* d_wq, float* exp_avg, float* exp_avg_sq, int outer, int ch, int inner,
+                              int n_levels, int step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                              float reg_weight, float reg_b, float* reg_loss, float* d_alpha_out,
+                              b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && alpha && delta && zero_point && d_wq, "adaround_bwd_adam: null pointer");
+  B200_REQUIRE((exp_avg && exp_avg_sq) || (!exp_avg && !exp_avg_sq && d_alpha_out),
+               "adaround_bwd_adam: pass both Adam moments, or neither together with d_alpha_out (gradient-only)");
+  B200_REQUIRE(step >= 1, "adaround_bwd_adam: step must be >= 1");
+  const size_t n = (size_t)outer * ch * inner;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  AdamArgs ad{(float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps};
+  adaround_bwd_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
+      reg_weight, reg_b, reg_loss, d_alpha_out);
+  B200_LAUNCH_CHECK("adaround_bwd_adam_kernel");
+  return B200LIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""Evaluation entry of the hot path: drop-in for task-oriented-PTQ/test_datasets.py (:21-33 PSNR/bpp, :45-73
+pad/crop, :76-117 Test_kodak) and losses/losses.py (:15-28 RateDistortionLoss, MSE metric), on libb200lic
+reductions (K11).  MS-SSIM is outside the hot path (BASELINE north_star names rate + lambda*MSE).
+
+Images are independent, so `evaluate` shards them round-robin over the ranks of the default process group and
+all-reduces (sum psnr, sum bpp, count): the only collective evaluation needs.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def pad(x, p=2 ** 6):
+    """Centred zero pad to a multiple of p (test_datasets.py:45-58).  Buffer plumbing, not arithmetic."""
+    h, w = x.size(2), x.size(3)
+    H, W = (h + p - 1) // p * p, (w + p - 1) // p * p
+    l, t = (W - w) // 2, (H - h) // 2
+    return F.pad(x, (l, W - w - l, t, H - h - t), mode="constant", value=0)
+
+
+def crop(x, size):
+    """Inverse of `pad` (test_datasets.py:61-73)."""
+    H, W = x.size(2), x.size(3)
+    h, w = size
+    l, t = (W - w) // 2, (H - h) // 2
+    return x[:, :, t:t + h, l:l + w].contiguous()
+
+
+def squared_error_sums(a, b):
+    """Device tensor [sum (a-b)^2, sum (clamp(a,0,1)-b)^2]."""
+    return ops.sq_err_sum(a, b)
+
+
+def compute_psnr(a, b, clamp=False):
+    """-10 log10(mean((a-b)^2)) (test_datasets.py:21-23); `clamp` folds the reference's `rec.clamp_(0,1)` (:98)."""
+    s = squared_error_sums(a, b)
+    return -10 * math.log10(float(s[1 if clamp else 0]) / a.numel())
+
+
+def total_bits(out_net):
+    """sum over likelihood tensors of sum(-log2 lik), as a device scalar (one K11 pass per tensor)."""
+    tot = None
+    for lik in out_net["likelihoods"].values():
+        b = ops.bits_sum(lik)
+        tot = b if tot is None else ops.add_act(tot, b)
+    return tot
+
+
+def compute_bpp(out_net):
+    """test_datasets.py:29-33: bits / pixels of the (padded) x_hat."""
+    n, _, h, w = out_net["x_hat"].shape
+    return float(total_bits(out_net)) / (n * h * w)
+
+
+@torch.no_grad()
+def evaluate(model, images, p=256, shard=True):
+    """Test_kodak (test_datasets.py:76-117) over a list of [1,3,h,w] CUDA tensors.
+    Returns dict(psnr, bpp, count, per_image=[(psnr, bpp), ...] for this rank's images)."""
+    rank, world = (dist.get_rank(), dist.get_world_size()) if (shard and dist.is_initialized()) else (0, 1)
+    per = []
+    for i, x in enumerate(images):
+        if i % world != rank:
+            continue
+        h, w = x.size(2), x.size(3)
+        out = model.forward(pad(x, p))
+        rec = crop(out["x_hat"], (h, w))
+        per.append((compute_psnr(rec, x, clamp=True), compute_bpp(out)))
+    acc = torch.tensor([sum(v[0] for v in per), sum(v[1] for v in per), float(len(per))], dtype=torch.float64,
+                       device=images[0].device)
+    if world > 1:
+        dist.all_reduce(acc)
+    psnr_sum, bpp_sum, cnt = acc.tolist()
+    return dict(psnr=psnr_sum / max(cnt, 1), bpp=bpp_sum / max(cnt, 1), count=int(cnt), per_image=per)
+
+
+class RateDistortionLoss(nn.Module):
+    """losses/losses.py:8-35 with metric='mse': bpp_loss + lmbda * 255^2 * mse (value only: PTQ never back-props it)."""
+
+    def __init__(self, lmbda=1e-2, metric='mse'):
+        super().__init__()
+        if metric != 'mse':
+            raise NotImplementedError("MS-SSIM is outside the hot path")
+        self.lmbda, self.metric = lmbda, metric
+
+    def forward(self, output, target):
+        N, _, H, W = target.size()
+        bpp = float(total_bits(output)) / (N * H * W)
+        mse = float(squared_error_sums(output["x_hat"], target)[0]) / target.numel()
+        return {"bpp_loss": bpp, "mse_loss": mse, "loss": self.lmbda * 255 ** 2 * mse + bpp}

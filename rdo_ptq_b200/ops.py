@@ -1,0 +1,517 @@
+"""Tensor-level entry points over the C ABI (include/b200lic.h) + the autograd glue.
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic op on the hot path is a
+libb200lic kernel enqueued on torch's current CUDA stream.  Tensors must be CUDA fp32; there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC
+
+_ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tc": ENGINE_TC}
+DEFAULT_ENGINE = _ENGINES[os.environ.get("B200LIC_ENGINE", "auto").lower()]
+
+
+def set_default_engine(name: str):
+    global DEFAULT_ENGINE
+    DEFAULT_ENGINE = _ENGINES[name]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c(t, name="tensor"):
+    """Validate a tensor for the ABI: CUDA, fp32 (or uint8), contiguous."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"rdo_ptq_b200: `{name}` must be a CUDA tensor -- the hot path has no CPU fallback")
+    if t.dtype not in (torch.float32, torch.uint8, torch.int32):
+        raise TypeError(f"rdo_ptq_b200: `{name}` must be float32 (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def call(name, *args):
+    _lib.call(name, *args, stream=_stream())
+
+
+def channel_view(shape, axis):
+    """(outer, ch, inner) view of a weight for per-channel quantisation along `axis` (None = per tensor)."""
+    numel = 1
+    for s in shape:
+        numel *= s
+    if axis is None:
+        return 1, 1, numel
+    outer = 1
+    for s in shape[:axis]:
+        outer *= s
+    return outer, shape[axis], numel // (outer * shape[axis])
+
+
+def _bshape(shape, axis, ch):
+    """Broadcast shape the reference gives delta/zero_point (quantizer.py:267-279)."""
+    if axis is None:
+        return ()
+    if len(shape) == 4:
+        s = [1, 1, 1, 1]
+        s[axis] = ch
+        return tuple(s)
+    return (ch, 1)
+
+
+# ------------------------------------------------------------------------------------------------ K7 / K6
+def wq_init_minmax(w, axis, n_bits=8, scale_variant=False, symmetric=False):
+    w = _c(w, "weight")
+    outer, ch, inner = channel_view(w.shape, axis)
+    delta = torch.empty(ch, device=w.device, dtype=torch.float32)
+    zp = torch.empty_like(delta)
+    call("wq_init_minmax", _p(w), outer, ch, inner, n_bits, int(scale_variant), int(symmetric), _p(delta), _p(zp))
+    bs = _bshape(w.shape, axis, ch)
+    return delta.view(bs), zp.view(bs)
+
+
+def wq_fake_quant(w, delta, zp, axis, n_levels, want=("dq",)):
+    w = _c(w, "weight")
+    outer, ch, inner = channel_view(w.shape, axis)
+    dq = torch.empty_like(w) if "dq" in want else None
+    codes = torch.empty_like(w) if "codes" in want else None
+    u8 = torch.empty(w.shape, device=w.device, dtype=torch.uint8) if "u8" in want else None
+    call("wq_fake_quant", _p(w), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))), outer, ch, inner, n_levels,
+         _p(dq), _p(codes), _p(u8))
+    out = {"dq": dq, "codes": codes, "u8": u8}
+    return out[want[0]] if len(want) == 1 else tuple(out[k] for k in want)
+
+
+def wq_dequant_u8(u8, delta, zp, axis):
+    u8 = _c(u8, "codes")
+    outer, ch, inner = channel_view(u8.shape, axis)
+    out = torch.empty(u8.shape, device=u8.device, dtype=torch.float32)
+    call("wq_dequant_u8", _p(u8), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))), outer, ch, inner, _p(out))
+    return out
+
+
+def adaround_init_alpha(w, delta, axis):
+    w = _c(w, "weight")
+    outer, ch, inner = channel_view(w.shape, axis)
+    alpha = torch.empty_like(w)
+    call("adaround_init_alpha", _p(w), _p(_c(delta.reshape(-1))), outer, ch, inner, _p(alpha))
+    return alpha
+
+
+def adaround_fwd(w, alpha, delta, zp, axis, n_levels, soft, want_codes=False, out=None):
+    w, alpha = _c(w, "weight"), _c(alpha, "alpha")
+    outer, ch, inner = channel_view(w.shape, axis)
+    wq = out if out is not None else torch.empty_like(w)
+    codes = torch.empty_like(w) if want_codes else None
+    call("adaround_fwd", _p(w), _p(alpha), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))), outer, ch, inner,
+         n_levels, int(soft), _p(wq), _p(codes))
+    return (wq, codes) if want_codes else wq
+
+
+def adaround_bwd_adam(w, alpha, delta, zp, d_wq, exp_avg, exp_avg_sq, axis, n_levels, step, lr=1e-3, beta1=0.9,
+                      beta2=0.999, eps=1e-8, grad_scale=1.0, reg_weight=0.0, reg_b=0.0, reg_loss=None,
+                      d_alpha_out=None):
+    outer, ch, inner = channel_view(w.shape, axis)
+    call("adaround_bwd_adam", _p(_c(w)), _p(_c(alpha)), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))),
+         _p(_c(d_wq)), _p(exp_avg), _p(exp_avg_sq), outer, ch, inner, n_levels, int(step), lr, beta1, beta2, eps,
+         grad_scale, reg_weight, reg_b, _p(reg_loss), _p(d_alpha_out))
+
+
+# ------------------------------------------------------------------------------------------------ K8
+def act_quant(x, n_bits=8, want_codes=False):
+    """Dynamic per-channel fake-quant of a [N,C,H,W] (or [N,C]) activation; result is detached (quantizer.py:100)."""
+    x = _c(x.detach(), "activation")
+    if x.dim() == 4:
+        N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    elif x.dim() == 2:
+        N, Cc, HW = x.shape[0], x.shape[1], 1
+    else:
+        raise NotImplementedError("act_quant: only NCHW / NC activations are on the hot path")
+    keys = torch.empty(2 * Cc, device=x.device, dtype=torch.int32)
+    out = torch.empty_like(x)
+    codes = torch.empty_like(x) if want_codes else None
+    call("actq_stats_init", _p(keys), Cc)
+    call("actq_stats", _p(x), N, Cc, HW, _p(keys))
+    call("actq_apply", _p(x), _p(keys), N, Cc, HW, n_bits, _p(out), _p(codes))
+    return (out, codes) if want_codes else out
+
+
+def fixed_point(x, a_l=8, a_r=8):
+    x = _c(x, "activation")
+    out = torch.empty_like(x)
+    call("fixed_point", _p(x), x.numel(), a_l, a_r, _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K9 / K10 / K11
+def gaussian_lik(y, scales, means=None, scale_bound=0.11, lik_bound=1e-9, want_lik=True):
+    """Returns (y_hat, lik, bits) with bits = sum(-log2 lik) as a device scalar."""
+    y = _c(y, "y")
+    N, Cc = y.shape[0], y.shape[1]
+    HW = y.numel() // (N * Cc)
+    chw = Cc * HW
+
+    def strided_ok(t):
+        return t.shape == y.shape and t.stride()[1:] == y.stride()[1:] and t.stride(0) >= chw
+
+    if means is not None and not (strided_ok(scales) and strided_ok(means) and scales.stride(0) == means.stride(0)):
+        scales, means = scales.contiguous(), means.contiguous()
+    elif means is None and not strided_ok(scales):
+        scales = scales.contiguous()
+    for t in (scales, means):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError("gaussian_lik: parameters must be CUDA fp32")
+    y_hat = torch.empty_like(y)
+    lik = torch.empty_like(y) if want_lik else None
+    bits = torch.zeros(1, device=y.device, dtype=torch.float32)
+    call("gaussian_lik_fwd", _p(y), _p(scales), _p(means), N, Cc, HW, scales.stride(0) if N > 1 else chw,
+         scale_bound, lik_bound, _p(y_hat), _p(lik), _p(bits))
+    return y_hat, lik, bits
+
+
+def round_latent(y, means=None):
+    y = _c(y, "y")
+    out = torch.empty_like(y)
+    call("round_latent", _p(y), _p(_c(means)), y.numel(), _p(out))
+    return out
+
+
+def factorized_lik(z, packed_params, medians, lik_bound=1e-9, want_lik=True):
+    z = _c(z, "z")
+    N, Cc = z.shape[0], z.shape[1]
+    HW = z.numel() // (N * Cc)
+    z_hat = torch.empty_like(z)
+    lik = torch.empty_like(z) if want_lik else None
+    bits = torch.zeros(1, device=z.device, dtype=torch.float32)
+    call("factorized_lik_fwd", _p(z), _p(_c(packed_params)), _p(_c(medians)), N, Cc, HW, lik_bound, _p(z_hat),
+         _p(lik), _p(bits))
+    return z_hat, lik, bits
+
+
+def lp_loss_fwd_bwd(pred, tgt, p=2.0, scale=1.0, grad_scale=None, loss=None, want_grad=True):
+    """loss += scale * sum|pred-tgt|^p ; returns (loss, d_pred)."""
+    pred, tgt = _c(pred, "pred"), _c(tgt, "tgt")
+    if loss is None:
+        loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+    g = torch.empty_like(pred) if want_grad else None
+    call("lp_loss_fwd_bwd", _p(pred), _p(tgt), pred.numel(), float(p), float(scale),
+         float(scale if grad_scale is None else grad_scale), _p(loss), _p(g))
+    return loss, g
+
+
+def sq_err_sum(a, b):
+    a, b = _c(a), _c(b)
+    out = torch.zeros(2, device=a.device, dtype=torch.float32)
+    call("sq_err_sum", _p(a), _p(b), a.numel(), _p(out))
+    return out
+
+
+def bits_sum(lik):
+    lik = _c(lik)
+    out = torch.zeros(1, device=lik.device, dtype=torch.float32)
+    call("bits_sum", _p(lik), lik.numel(), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def _sq(v, what):
+    a, b = _pair(v)
+    if a != b:
+        raise NotImplementedError(f"rdo_ptq_b200: non-square {what} {v}")
+    return a
+
+
+def conv_desc(x_shape, w_shape, stride, padding, transposed=False, output_padding=0, act=ACT_NONE, slope=0.01,
+              engine=None, in_square=0, gdn_mode=0, fixed_pt=0):
+    N, Cin, H, W = x_shape
+    st, pd = _sq(stride, "stride"), _sq(padding, "padding")
+    KH, KW = w_shape[2], w_shape[3]
+    if transposed:
+        op = _sq(output_padding, "output_padding")
+        if w_shape[0] != Cin:
+            raise ValueError(f"conv_transpose2d: weight {tuple(w_shape)} does not match input channels {Cin}")
+        Cout = w_shape[1]
+        Ho, Wo = (H - 1) * st - 2 * pd + KH + op, (W - 1) * st - 2 * pd + KW + op
+    else:
+        if w_shape[1] != Cin:
+            raise ValueError(f"conv2d: weight {tuple(w_shape)} does not match input channels {Cin}")
+        Cout = w_shape[0]
+        Ho, Wo = (H + 2 * pd - KH) // st + 1, (W + 2 * pd - KW) // st + 1
+    return ConvDesc(N, Cin, H, W, Cout, Ho, Wo, KH, KW, st, pd, act, slope,
+                    DEFAULT_ENGINE if engine is None else engine, in_square, gdn_mode, fixed_pt)
+
+
+def _act_id(module):
+    """Map an absorbed activation module (quant_model.py:51-56) to (act id, slope)."""
+    import torch.nn as nn
+    if module is None or type(module).__name__ == "StraightThrough":
+        return ACT_NONE, 0.0
+    if isinstance(module, nn.LeakyReLU):
+        return ACT_LEAKY_RELU, float(module.negative_slope)
+    if isinstance(module, nn.ReLU):
+        return ACT_RELU, 0.0
+    raise NotImplementedError(f"rdo_ptq_b200: activation {module} is not on the hot path")
+
+
+def conv2d_raw(x, w, bias, d, gdn_x=None, want_norm=False):
+    y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
+    norm = torch.empty_like(y) if want_norm else None
+    call("conv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(gdn_x), _p(norm), _p(y))
+    return (y, norm) if want_norm else y
+
+
+def deconv2d_raw(x, w, bias, d):
+    y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
+    call("deconv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(y))
+    return y
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, act, slope, fixed_pt):
+        x, w, bias = _c(x, "input"), _c(w, "weight"), _c(bias, "bias")
+        d = conv_desc(x.shape, w.shape, stride, padding, act=act, slope=slope, fixed_pt=fixed_pt)
+        y = conv2d_raw(x, w, bias, d)
+        ctx.d, ctx.act, ctx.slope = d, act, slope
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy, "grad")
+        if ctx.act != ACT_NONE:
+            dy = act_bwd(y, dy, ctx.act, ctx.slope)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("conv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx))
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            call("conv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw))
+        return dx, dw, None, None, None, None, None, None
+
+
+class _DeconvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, output_padding, act, slope, fixed_pt):
+        x, w, bias = _c(x, "input"), _c(w, "weight"), _c(bias, "bias")
+        d = conv_desc(x.shape, w.shape, stride, padding, True, output_padding, act=act, slope=slope, fixed_pt=fixed_pt)
+        y = deconv2d_raw(x, w, bias, d)
+        ctx.d, ctx.act, ctx.slope = d, act, slope
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _c(dy, "grad")
+        if ctx.act != ACT_NONE:
+            dy = act_bwd(y, dy, ctx.act, ctx.slope)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("deconv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx))
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            call("deconv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw))
+        return dx, dw, None, None, None, None, None, None, None
+
+
+def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1, act=ACT_NONE, slope=0.01, fixed_pt=0):
+    """Drop-in for F.conv2d on the hot path (dilation 1, groups 1), optional fused activation."""
+    if _sq(dilation, "dilation") != 1 or groups != 1:
+        raise NotImplementedError("rdo_ptq_b200.conv2d: dilation/groups != 1 are not on the hot path")
+    return _ConvFn.apply(x, w, bias, stride, padding, act, slope, fixed_pt)
+
+
+def conv_transpose2d(x, w, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1, act=ACT_NONE,
+                     slope=0.01, fixed_pt=0):
+    """Drop-in for F.conv_transpose2d on the hot path."""
+    if _sq(dilation, "dilation") != 1 or groups != 1:
+        raise NotImplementedError("rdo_ptq_b200.conv_transpose2d: dilation/groups != 1 are not on the hot path")
+    return _DeconvFn.apply(x, w, bias, stride, padding, output_padding, act, slope, fixed_pt)
+
+
+# ------------------------------------------------------------------------------------------------ GDN
+def gdn_reparam(p, bound, pedestal):
+    p = _c(p)
+    out = torch.empty_like(p)
+    call("gdn_reparam_fwd", _p(p), p.numel(), bound, pedestal, _p(out))
+    return out
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, bound, pedestal):
+        p = _c(p)
+        ctx.bound = bound
+        ctx.save_for_backward(p)
+        return gdn_reparam(p, bound, pedestal)
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        g = _c(g)
+        dp = torch.empty_like(p)
+        call("gdn_reparam_bwd", _p(p), _p(g), p.numel(), ctx.bound, _p(dp))
+        return dp, None, None
+
+
+def gdn_desc(x_shape, inverse, want_norm=False):
+    N, Cc, H, W = x_shape
+    return ConvDesc(N, Cc, H, W, Cc, H, W, 1, 1, 1, 0, ACT_NONE, 0.0, DEFAULT_ENGINE, 1, 2 if inverse else 1, 0)
+
+
+class _GdnFn(torch.autograd.Function):
+    """y = x * (beta + gamma . x^2)^(-1/2 | +1/2) with effective (re-parametrised) gamma [C,C], beta [C]."""
+
+    @staticmethod
+    def forward(ctx, x, gamma_eff, beta_eff, inverse):
+        x, gamma_eff, beta_eff = _c(x), _c(gamma_eff), _c(beta_eff)
+        d = gdn_desc(x.shape, inverse)
+        need_bwd = any(ctx.needs_input_grad[:2])
+        res = conv2d_raw(x, gamma_eff, beta_eff, d, gdn_x=x, want_norm=need_bwd)
+        y, norm = res if need_bwd else (res, None)
+        ctx.d, ctx.inverse = d, inverse
+        ctx.save_for_backward(x, gamma_eff, norm)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma_eff, norm = ctx.saved_tensors
+        dy = _c(dy)
+        need_dx = ctx.needs_input_grad[0]
+        d_norm = torch.empty_like(x)
+        dx_direct = torch.empty_like(x) if need_dx else None
+        call("gdn_bwd_prep", _p(x), _p(norm), _p(dy), x.numel(), int(ctx.inverse), _p(d_norm), _p(dx_direct))
+        d = ConvDesc(ctx.d.N, ctx.d.Cin, ctx.d.H, ctx.d.W, ctx.d.Cout, ctx.d.Ho, ctx.d.Wo, 1, 1, 1, 0, ACT_NONE, 0.0,
+                     ctx.d.engine, 1, 0, 0)
+        dx = dgamma = None
+        if ctx.needs_input_grad[1]:
+            dgamma = torch.empty_like(gamma_eff)
+            call("conv_wgrad", C.byref(d), _p(x), _p(d_norm), _p(dgamma))     # in_square: sum d_norm * x^2
+        if need_dx:
+            d.in_square = 0
+            t = torch.empty_like(x)
+            call("conv_dgrad", C.byref(d), _p(d_norm), _p(gamma_eff), _p(t))
+            dx = torch.empty_like(x)
+            call("gdn_bwd_finish", _p(x), _p(t), _p(dx_direct), x.numel(), _p(dx))
+        dbeta = None
+        if ctx.needs_input_grad[2]:
+            dbeta = d_norm.sum(dim=(0, 2, 3))
+        return dx, dgamma, dbeta, None
+
+
+def gdn(x, gamma_eff, beta_eff, inverse):
+    return _GdnFn.apply(x, gamma_eff, beta_eff, bool(inverse))
+
+
+def gdn_reparam_fn(p, bound, pedestal):
+    return _ReparamFn.apply(p, float(bound), float(pedestal))
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def add_act(a, b=None, act=ACT_NONE, slope=0.01):
+    a = _c(a)
+    out = torch.empty_like(a)
+    call("add_act", _p(a), _p(_c(b)), a.numel(), act, slope, _p(out))
+    return out
+
+
+def act_bwd(y, dy, act, slope):
+    out = torch.empty_like(dy)
+    call("act_bwd", _p(_c(y)), _p(_c(dy)), dy.numel(), act, slope, _p(out))
+    return out
+
+
+class _AddActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, act, slope):
+        y = add_act(a, b, act, slope)
+        ctx.act, ctx.slope, ctx.has_b = act, slope, b is not None
+        ctx.save_for_backward(y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        g = act_bwd(y, dy, ctx.act, ctx.slope) if ctx.act != ACT_NONE else dy
+        return g, (g if ctx.has_b else None), None, None
+
+
+def add_act_fn(a, b=None, act=ACT_NONE, slope=0.01):
+    return _AddActFn.apply(a, b, act, slope)
+
+
+def gather_mix(q, fp, idx=None, prob=1.0, seed=0, mask=None, out=None):
+    """Batch pick + QDrop mix: out[b] = keep ? q[idx[b]] : fp[idx[b]]  (layer_opt.py:289-292)."""
+    q, fp = _c(q), _c(fp)
+    rows = q.shape[0] if idx is None else idx.numel()
+    row = q[0].numel()
+    if idx is not None and (idx.dtype != torch.int64 or not idx.is_cuda):
+        raise TypeError("gather_mix: idx must be a CUDA int64 tensor")
+    if mask is not None:
+        mask = mask.to(torch.uint8) if mask.dtype != torch.uint8 else mask
+        if not mask.is_cuda or mask.numel() != rows * row:
+            raise ValueError("gather_mix: mask must be a CUDA tensor with rows*row elements")
+        mask = mask.contiguous()
+    if out is None:
+        out = torch.empty((rows,) + tuple(q.shape[1:]), device=q.device, dtype=torch.float32)
+    call("gather_mix", _p(q), _p(fp), _p(idx), rows, row, float(prob), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(mask),
+         _p(out))
+    return out
+
+
+def attn_gate(a, b, c):
+    a = _c(a)
+    out = torch.empty_like(a)
+    call("attn_gate", _p(a), _p(_c(b)), _p(_c(c)), a.numel(), _p(out))
+    return out
+
+
+def abs_(x):
+    x = _c(x)
+    out = torch.empty_like(x)
+    call("abs", _p(x), x.numel(), _p(out))
+    return out
+
+
+class _PixelShuffleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, r, act, slope):
+        x = _c(x)
+        N, Crr, H, W = x.shape
+        Cc = Crr // (r * r)
+        out = torch.empty((N, Cc, H * r, W * r), device=x.device, dtype=torch.float32)
+        call("pixel_shuffle", _p(x), N, Cc, H, W, r, act, slope, _p(out))
+        ctx.r, ctx.act, ctx.slope, ctx.shape = r, act, slope, (N, Cc, H, W)
+        ctx.save_for_backward(out if act != ACT_NONE else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        if ctx.act != ACT_NONE:
+            dy = act_bwd(y, dy, ctx.act, ctx.slope)
+        N, Cc, H, W = ctx.shape
+        dx = torch.empty((N, Cc * ctx.r * ctx.r, H, W), device=dy.device, dtype=torch.float32)
+        call("pixel_unshuffle", _p(dy), N, Cc, H, W, ctx.r, _p(dx))
+        return dx, None, None, None
+
+
+def pixel_shuffle(x, r, act=ACT_NONE, slope=0.01):
+    return _PixelShuffleFn.apply(x, r, act, slope)

@@ -1,0 +1,116 @@
+"""B200 drop-in for the Cheng2020 part of task-oriented-PTQ/quantization/quant_block.py (:77-102, :219-328, :645-657).
+
+The Lu2022 Swin blocks of that file (QuantNIC/QuantMlp/QuantWindowAttention/...) are outside the hot path
+(SURVEY.md section 2 row 3).  Residual add, LeakyReLU and the block-level dynamic activation quantiser run as
+libb200lic kernels (`add_act`, K8).
+"""
+import torch.nn as nn
+
+from .. import ops
+from ..codec.layers import ResidualBlockWithStride, ResidualBlockUpsample, ResidualBlock, subpel_conv3x3
+from .quant_layer import QuantModule
+from .quantizer import StraightThrough, UniformAffineQuantizer, ActQuantizer
+
+
+class BaseQuantBlock(nn.Module):
+    def __init__(self, act_quant_params: dict = {}):
+        super().__init__()
+        self.use_weight_quant = False
+        self.use_act_quant = False
+        self.trained = False
+        self.act_quantizer = UniformAffineQuantizer(act=True, **act_quant_params)
+        self.activation_function = StraightThrough()
+        self.ignore_reconstruction = False
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for m in self.modules():
+            if isinstance(m, QuantModule):
+                m.set_quant_state(weight_quant, act_quant)
+
+    def _aq(self, t):
+        return self.act_quantizer(t, True) if (self.use_act_quant and self.trained) else t
+
+    def _lrelu(self, t):
+        return ops.add_act_fn(t, None, ops.ACT_LEAKY_RELU, float(self.leaky_relu.negative_slope))
+
+
+class QuantRBWS(BaseQuantBlock):
+    """ResidualBlockWithStride (reference :219-250)."""
+
+    def __init__(self, basic_block: ResidualBlockWithStride, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.conv1 = QuantModule(basic_block.conv1, weight_quant_params, act_quant_params, disable_act_quant=True)
+        self.leaky_relu = basic_block.leaky_relu
+        self.conv2 = QuantModule(basic_block.conv2, weight_quant_params, act_quant_params)
+        self.gdn = QuantModule(basic_block.gdn, weight_quant_params, act_quant_params)
+        self.skip = (QuantModule(basic_block.skip, weight_quant_params, act_quant_params)
+                     if basic_block.skip is not None else None)
+
+    def forward(self, x):
+        out = self._aq(self._lrelu(self.conv1(x)))
+        out = self.gdn(self.conv2(out))
+        out = ops.add_act_fn(out, self.skip(x) if self.skip is not None else x)
+        return self._aq(out)
+
+
+class QuantRBU(BaseQuantBlock):
+    """ResidualBlockUpsample (reference :253-284)."""
+
+    def __init__(self, basic_block: ResidualBlockUpsample, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.subpel_conv = nn.Sequential(
+            QuantModule(basic_block.subpel_conv[0], weight_quant_params, act_quant_params, disable_act_quant=True),
+            basic_block.subpel_conv[1])
+        self.leaky_relu = basic_block.leaky_relu
+        self.conv = QuantModule(basic_block.conv, weight_quant_params, act_quant_params)
+        self.igdn = QuantModule(basic_block.igdn, weight_quant_params, act_quant_params)
+        self.upsample = nn.Sequential(QuantModule(basic_block.upsample[0], weight_quant_params, act_quant_params),
+                                      basic_block.upsample[1])
+
+    def forward(self, x):
+        out = self._aq(self._lrelu(self.subpel_conv(x)))
+        out = self.igdn(self.conv(out))
+        return self._aq(ops.add_act_fn(out, self.upsample(x)))
+
+
+class QuantRB(BaseQuantBlock):
+    """ResidualBlock (reference :286-313)."""
+
+    def __init__(self, basic_block: ResidualBlock, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.conv1 = QuantModule(basic_block.conv1, weight_quant_params, act_quant_params, disable_act_quant=True)
+        self.leaky_relu = basic_block.leaky_relu
+        self.conv2 = QuantModule(basic_block.conv2, weight_quant_params, act_quant_params, disable_act_quant=True)
+        self.skip = (QuantModule(basic_block.skip, weight_quant_params, act_quant_params)
+                     if basic_block.skip is not None else None)
+
+    def forward(self, x):
+        out = self._aq(self._lrelu(self.conv1(x)))
+        out = self._aq(self._lrelu(self.conv2(out)))
+        out = ops.add_act_fn(out, self.skip(x) if self.skip is not None else x)
+        return self._aq(out)
+
+
+class QuantSC(BaseQuantBlock):
+    """subpel_conv3x3 wrapper (reference :315-328).  Unreachable through `specials` in the reference too: the key is
+    a function, the lookup is by type(); kept for API parity."""
+
+    def __init__(self, basic_block, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.subpel_conv = nn.Sequential(
+            QuantModule(basic_block[0], weight_quant_params, act_quant_params, disable_act_quant=True),
+            basic_block[1], nn.LeakyReLU(inplace=True))
+
+    def forward(self, x):
+        out = self.subpel_conv[1](self.subpel_conv[0](x))
+        return ops.add_act_fn(out, None, ops.ACT_LEAKY_RELU, 0.01)
+
+
+specials = {
+    ResidualBlockWithStride: QuantRBWS,
+    ResidualBlockUpsample: QuantRBU,
+    ResidualBlock: QuantRB,
+    subpel_conv3x3: QuantSC,
+}

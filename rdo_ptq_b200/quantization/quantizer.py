@@ -1,0 +1,193 @@
+"""B200 drop-in for task-oriented-PTQ/quantization/quantizer.py.
+
+Same public names and state (`UniformAffineQuantizer.delta/zero_point/n_bits/n_levels/sym/inited`,
+`AdaRoundQuantizer.alpha/soft_targets/get_soft_targets`), but the arithmetic runs in libb200lic
+kernels: K7 (range + fake-quant), K6 (AdaRound) and K8 (dynamic activation quant).  No CPU path.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class StraightThrough(nn.Module):
+    """reference quantizer.py:12-17."""
+
+    def __init__(self, channel_num: int = 1):
+        super().__init__()
+
+    def forward(self, input):
+        return input
+
+
+def round_ste(x: torch.Tensor):
+    """reference quantizer.py:64-68.  Only the calibration surface uses it (never the fused loop)."""
+    return x + (ops.round_latent(x) - x).detach()
+
+
+def lp_loss(pred, tgt, p=2.0, reduction='none'):
+    """reference quantizer.py:71-79, value only (the fused loop uses ops.lp_loss_fwd_bwd for value+grad)."""
+    denom = pred.numel() // pred.shape[1] if reduction == 'none' else pred.numel()
+    loss, _ = ops.lp_loss_fwd_bwd(pred.detach(), tgt.detach(), p=p, scale=1.0 / denom, want_grad=False)
+    return loss.reshape(())
+
+
+def ActQuantizer(x: torch.Tensor, n_bits: int = 8):
+    """reference quantizer.py:99-121: dynamic per-channel fake-quant, detached.  The reference hard-wires 8 bit
+    (`Handle_Parameter(b_w=8)`); `n_bits` is the additive knob BASELINE config 4 (W10A10) needs."""
+    return ops.act_quant(x, n_bits)
+
+
+def ActQuant(x: torch.Tensor):
+    return ActQuantizer(x)
+
+
+class _FakeQuantSTE(torch.autograd.Function):
+    """(clamp(rint(x/d)+zp, 0, L-1) - zp) * d with the straight-through gradient of quantizer.py:175-177."""
+
+    @staticmethod
+    def forward(ctx, x, delta, zp, axis, n_levels):
+        ctx.save_for_backward(x, delta, zp)
+        ctx.n_levels = n_levels
+        return ops.wq_fake_quant(x, delta, zp, axis, n_levels, want=("dq",))
+
+    @staticmethod
+    def backward(ctx, g):          # off the hot path: nothing in RDO-PTQ trains through this quantizer
+        x, delta, zp = ctx.saved_tensors
+        xi = torch.round(x / delta) + zp
+        return g * ((xi >= 0) & (xi <= ctx.n_levels - 1)).to(g.dtype), None, None, None, None
+
+
+class UniformAffineQuantizer(nn.Module):
+    """reference quantizer.py:123-393.  Scale methods: 'max' / 'max_scale' on the GPU (the hot-path default
+    `--init max`); the search-based ones ('mse', 'l1', 'l2', 'gaussian') are not on the hot path."""
+
+    # additive switch: thread n_bits into the activation quantiser (config 4, W10A10); default = reference (8 bit)
+    act_bits_follow_n_bits = False
+
+    def __init__(self, n_bits: int = 8, symmetric: bool = False, channel_wise: bool = False, scale_method: str = 'max',
+                 leaf_param: bool = False, tconv: bool = False, act: bool = False, prob: float = 1.0):
+        super().__init__()
+        self.sym = symmetric
+        assert 2 <= n_bits <= 16, 'bitwidth not supported'      # reference asserts <= 8; lifted for W10A10 (Q6)
+        self.n_bits = n_bits
+        self.n_levels = 2 ** self.n_bits
+        self.delta = None
+        self.zero_point = None
+        self.inited = False
+        self.leaf_param = leaf_param
+        self.channel_wise = channel_wise
+        self.scale_method = scale_method
+        self.tconv = tconv
+        self.act = act
+        self.prob = prob
+        self.is_training = False
+
+    def channel_axis(self, x):
+        """Axis that carries per-channel scales (quantizer.py:237-279); None = per tensor."""
+        if not self.channel_wise or x.dim() == 1:
+            return None
+        return 1 if (self.tconv and x.dim() == 4) else 0
+
+    def forward(self, x: torch.Tensor, act: bool = False):
+        if act:
+            return ActQuantizer(x, self.n_bits if self.act_bits_follow_n_bits else 8)
+        if self.inited is False:
+            if self.leaf_param:
+                return x
+            self.delta, self.zero_point = self.init_quantization_scale(x, self.channel_wise)
+            self.inited = True
+        return _FakeQuantSTE.apply(x, self.delta, self.zero_point, self.channel_axis(x), self.n_levels)
+
+    def codes(self, x):
+        """Integer codes (fp32-valued) of the forward above: the bit-exact contract."""
+        return ops.wq_fake_quant(x.detach(), self.delta, self.zero_point, self.channel_axis(x), self.n_levels,
+                                 want=("codes",))
+
+    def init_quantization_scale(self, x: torch.Tensor, channel_wise: bool = False):
+        if 'max' not in self.scale_method:
+            raise NotImplementedError(f"scale_method {self.scale_method!r}: only 'max'/'max_scale' run on the B200 path")
+        axis = self.channel_axis(x) if channel_wise else None
+        delta, zp = ops.wq_init_minmax(x.detach(), axis, self.n_bits, 'scale' in self.scale_method, self.sym)
+        if channel_wise and x.dim() == 1:
+            delta, zp = delta.view(-1), zp.view(-1)
+        return delta, zp
+
+    def bitwidth_refactor(self, refactored_bit: int):
+        assert 2 <= refactored_bit <= 16, 'bitwidth not supported'
+        self.n_bits = refactored_bit
+        self.n_levels = 2 ** self.n_bits
+
+    def extra_repr(self):
+        return (f'bit={self.n_bits}, scale_method={self.scale_method}, symmetric={self.sym}, '
+                f'channel_wise={self.channel_wise}, leaf_param={self.leaf_param}')
+
+
+class _AdaRoundFn(torch.autograd.Function):
+    """AdaRound forward with gradient to alpha (autograd surface for reference-style training loops;
+    the fused calibration loop bypasses it and calls K6 bwd+Adam directly)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, q):
+        ctx.q = q
+        ctx.save_for_backward(x, alpha)
+        return ops.adaround_fwd(x, alpha, q.delta, q.zero_point, q.axis, q.n_levels, True)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, alpha = ctx.saved_tensors
+        q = ctx.q
+        d_alpha = torch.empty_like(alpha)
+        ops.adaround_bwd_adam(x, alpha, q.delta, q.zero_point, g.contiguous(), None, None, q.axis, q.n_levels, 1,
+                              d_alpha_out=d_alpha)
+        return None, d_alpha, None
+
+
+class AdaRoundQuantizer(nn.Module):
+    """reference quantizer.py:397-470 ('learned_hard_sigmoid')."""
+
+    def __init__(self, uaq: UniformAffineQuantizer, weight_tensor: torch.Tensor, round_mode='learned_round_sigmoid'):
+        super().__init__()
+        self.n_bits = uaq.n_bits
+        self.sym = uaq.sym
+        self.delta = uaq.delta
+        self.zero_point = uaq.zero_point
+        self.n_levels = uaq.n_levels
+        self.axis = uaq.channel_axis(weight_tensor)
+        self.round_mode = round_mode
+        self.alpha = None
+        self.soft_targets = False
+        self.gamma, self.zeta = -0.1, 1.1
+        self.beta = 2 / 3
+        self._leaf = None          # soft-quantised weight materialised by the fused loop (leaf for dWq)
+        self.init_alpha(x=weight_tensor)
+
+    def init_alpha(self, x: torch.Tensor):
+        if self.round_mode != 'learned_hard_sigmoid':
+            raise NotImplementedError
+        self.alpha = nn.Parameter(ops.adaround_init_alpha(x.detach(), self.delta, self.axis))
+
+    def get_soft_targets(self):
+        """h(alpha) = clamp(sigmoid(alpha)*(zeta-gamma)+gamma, 0, 1) (quantizer.py:451-452).  Compatibility
+        surface only: the fused loop evaluates h and the regulariser inside K6."""
+        return torch.clamp(torch.sigmoid(self.alpha) * (self.zeta - self.gamma) + self.gamma, 0, 1)
+
+    def forward(self, x):
+        if self.round_mode != 'learned_hard_sigmoid':
+            raise ValueError('Wrong rounding mode')
+        if self._leaf is not None:
+            return self._leaf
+        if self.soft_targets:
+            if torch.is_grad_enabled() and self.alpha.requires_grad:
+                return _AdaRoundFn.apply(x, self.alpha, self)
+            return ops.adaround_fwd(x.detach(), self.alpha.detach(), self.delta, self.zero_point, self.axis,
+                                    self.n_levels, True)
+        return ops.adaround_fwd(x.detach(), self.alpha.detach(), self.delta, self.zero_point, self.axis, self.n_levels,
+                                False)
+
+    def codes(self, x):
+        return ops.adaround_fwd(x.detach(), self.alpha.detach(), self.delta, self.zero_point, self.axis, self.n_levels,
+                                False, want_codes=True)[1]
+
+    def extra_repr(self):
+        return 'bit={}'.format(self.n_bits)

@@ -1,0 +1,156 @@
+"""Fused AdaRound reconstruction engine shared by `layer_reconstruction` and `block_reconstruction`.
+
+One iteration of the reference loop (layer_opt.py:287-309 / block_opt.py:287-311) is issued as:
+  gather_mix (batch pick + QDrop)  ->  K6 adaround_fwd per QuantModule (soft weight, a leaf tensor)
+  -> unit forward on K1/K2/K3 kernels  ->  K11 lp_loss_fwd_bwd (loss value + dL/dout in one pass)
+  -> wgrad/dgrad kernels (K4/K5, driven by the autograd tape of the unit)  ->  [NCCL all-reduce of dL/dWq]
+  -> K6 adaround_bwd_adam per QuantModule (STE masks + rounding regulariser + Adam in one kernel).
+No `.item()`/`float()` syncs inside the loop; the loss is read back only every `log_every` iterations.
+"""
+import logging
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from .quant_block import BaseQuantBlock
+from .quant_layer import QuantModule
+from .quantizer import AdaRoundQuantizer
+from .utils import LinearTempDecay
+
+
+class DrawPlan:
+    """Source of the per-iteration randomness (layer_opt.py:289-292).  The default draws the batch indices with
+    torch's device generator and the QDrop mask inside the gather_mix kernel (counter-based hash).  Tests pass a plan
+    that replays explicit (idx, mask) pairs so the CPU oracle sees the same draws."""
+
+    def __init__(self, seed: int = 1005):
+        self.seed = seed
+
+    def draw(self, unit_id: int, it: int, n: int, bs: int, shape, prob: float, device):
+        g = torch.Generator(device=device)
+        g.manual_seed(self.seed * 1000003 + unit_id * 100003 + it)
+        idx = torch.randperm(n, generator=g, device=device)[:bs]
+        return idx, None, (self.seed * 2654435761 + unit_id * 40503 + it) & 0xFFFFFFFFFFFF
+
+
+class UnitTrainer:
+    """State of one reconstruction problem: the QuantModules whose alpha is trained, Adam moments, schedules."""
+
+    def __init__(self, unit, iters: int, weight: float, b_range, warmup: float, p: float, task_p: Optional[float],
+                 lr: float = 1e-3, process_group=None):
+        self.unit = unit
+        self.mods: List[QuantModule] = ([unit] if isinstance(unit, QuantModule) else
+                                        [m for _, m in unit.named_modules() if isinstance(m, QuantModule)])
+        self.mods = [m for m in self.mods if m.org_weight is not None]
+        self.iters, self.weight, self.p, self.task_p, self.lr = iters, weight, p, task_p, lr
+        self.loss_start = iters * warmup
+        self.temp_decay = LinearTempDecay(iters, rel_start_decay=warmup, start_b=b_range[0], end_b=b_range[1])
+        self.count = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        for m in self.mods:
+            if not isinstance(m.weight_quantizer, AdaRoundQuantizer):
+                m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid',
+                                                       weight_tensor=m.org_weight.data)
+            m.weight_quantizer.soft_targets = True
+        self.exp_avg = [torch.zeros_like(m.weight_quantizer.alpha.data) for m in self.mods]
+        self.exp_avg_sq = [torch.zeros_like(m.weight_quantizer.alpha.data) for m in self.mods]
+        dev = self.mods[0].weight.device if self.mods else None
+        self.loss_buf = torch.zeros(3, device=dev)      # [rec, task, round] accumulated since the last read
+        self.last = {}
+
+    # -- one iteration ---------------------------------------------------------------------------------------
+    def step(self, cur_inp: torch.Tensor, tgt: torch.Tensor, trace: Optional[dict] = None):
+        self.count += 1
+        b = self.temp_decay(self.count)
+        reg_b = 0.0 if self.count < self.loss_start else float(b)
+        leaves = []
+        for m in self.mods:
+            q = m.weight_quantizer
+            leaf = ops.adaround_fwd(m.weight.data, q.alpha.data, q.delta, q.zero_point, q.axis, q.n_levels, True)
+            leaf.requires_grad_(True)
+            q._leaf = leaf
+            leaves.append(leaf)
+        try:
+            with torch.enable_grad():
+                out = self.unit(cur_inp)
+            # rec + task (with compressai-style names fp_out is the identity, so task == lp(out, tgt, task_p))
+            denom = out.numel() // out.shape[1]
+            rec = self.loss_buf[0:1]
+            if self.task_p is not None and float(self.task_p) == float(self.p):
+                _, d_out = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.p, scale=1.0 / denom, grad_scale=2.0 / denom,
+                                               loss=rec)
+                same = True
+            else:
+                _, d_out = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.p, scale=1.0 / denom, loss=rec)
+                if self.task_p is not None:
+                    _, d2 = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.task_p, scale=1.0 / denom,
+                                                loss=self.loss_buf[1:2])
+                    d_out = ops.add_act(d_out, d2)
+                same = False
+            self._same = same
+            out.backward(d_out)
+        finally:
+            for m in self.mods:
+                m.weight_quantizer._leaf = None
+        grads = [l.grad for l in leaves]
+        if self.world > 1:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+            grads = [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)]
+        for i, m in enumerate(self.mods):
+            q = m.weight_quantizer
+            d_alpha = torch.empty_like(q.alpha.data) if trace is not None else None
+            ops.adaround_bwd_adam(m.weight.data, q.alpha.data, q.delta, q.zero_point, grads[i], self.exp_avg[i],
+                                  self.exp_avg_sq[i], q.axis, q.n_levels, self.count, lr=self.lr,
+                                  grad_scale=1.0 / self.world, reg_weight=self.weight, reg_b=reg_b,
+                                  reg_loss=self.loss_buf[2:3], d_alpha_out=d_alpha)
+            if trace is not None:
+                trace.setdefault("d_alpha", []).append(d_alpha)
+        if trace is not None:
+            trace["out"] = out.detach()
+        return out
+
+    def read_losses(self, since: int):
+        """One device->host read of the accumulated (rec, task, round) sums; returns per-iteration means."""
+        v = (self.loss_buf / max(since, 1)).tolist()
+        self.loss_buf.zero_()
+        rec, task, rnd = v
+        if getattr(self, "_same", False):
+            task = rec
+        self.last = dict(rec=rec, task=task, round=rnd, total=rec + task + rnd)
+        return self.last
+
+    def finish(self):
+        for m in self.mods:
+            m.weight_quantizer.soft_targets = False
+        marks = ([self.unit] if isinstance(self.unit, QuantModule) else
+                 [m for _, m in self.unit.named_modules() if isinstance(m, (QuantModule, BaseQuantBlock))])
+        for m in marks:
+            m.act_quantizer.is_training = False
+            m.trained = True
+
+
+def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_size: int, input_prob: float,
+                       unit_id: int = 0, plan: Optional[DrawPlan] = None, log_every: int = 500, trace=None):
+    """The hot loop: `iters` fused iterations over the cached (quant_in, fp_in) -> fp_out pairs."""
+    plan = plan or DrawPlan()
+    q_in, fp_in = cached_inps[0], (cached_inps[1] if len(cached_inps) > 1 else cached_inps[0])
+    n = q_in.size(0)
+    losses, since = [], 0
+    for it in range(trainer.iters):
+        idx, mask, seed = plan.draw(unit_id, it, n, batch_size, q_in.shape[1:], input_prob, q_in.device)
+        cur_inp = ops.gather_mix(q_in, fp_in, idx, prob=input_prob, seed=seed, mask=mask)
+        tgt = ops.gather_mix(cached_outs, cached_outs, idx, prob=1.0)
+        trainer.step(cur_inp, tgt, trace=trace if (trace is not None and it == 0) else None)
+        since += 1
+        if trainer.count % log_every == 0 or it == trainer.iters - 1:
+            l = trainer.read_losses(since)
+            since = 0
+            losses.append(l)
+            logging.info('Total loss:\t{:.3f} ( task:{:.3f}, rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
+                l["total"], l["task"], l["rec"], l["round"], trainer.temp_decay(trainer.count), trainer.count))
+    trainer.finish()
+    return losses
