@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RDO-PTQ hot path on B200 (contract: see the task brief / DESIGN.md section 6).
+
+Workload (BASELINE.json configs[1]): W8 RDO-PTQ (AdaRound) calibration of Minnen2018 mean-scale (mbt2018-mean,
+N=192, M=320, random init) on synthetic 256x256 calibration patches.  One *step* = one fused AdaRound iteration
+(batch pick + QDrop mix, soft-quantised weight, forward, rec+task loss, wgrad, [all-reduce], STE/regulariser/Adam)
+on EVERY reconstruction unit of the model (20 QuantModules), per-GPU batch 8 (weak scaling: global batch = 8*N).
+metric `calib imgs/s` = units * global_batch / step time  (SURVEY.md 8(d)).
+Secondary: `fwd_mpx_s` = W8A8 evaluation forward (dynamic A8 on) on 768x512 synthetic images, Mpx/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the oracle port of the reference on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH, N_CH, M_CH, GAIN = "mbt2018-mean", 192, 320, 1.2
+PATCH, PER_GPU_BATCH, POOL = 256, 8, 16
+WQ = dict(n_bits=8, channel_wise=True, scale_method="max")
+AQ = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+CALIB = dict(iters=20000, weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf=d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)),
+                    src="measured")
+    return dict(hbm=6650.0, tf=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def layer_macs(session_units, caches):
+    """Algorithmic MACs per sample of each unit's forward (conv Ho*Wo*Cout*Cin*k*k, tconv
+    Hin*Win*Cin*Cout*k*k, GDN H*W*C^2)."""
+    out = {}
+    for name, u in session_units:
+        q_in, _, fp_out = caches[name]
+        if getattr(u, "is_gdn", False):
+            C_, H, W = q_in.shape[1:]
+            out[name] = H * W * C_ * C_
+        elif u.if_tconv:
+            Cin, H, W = q_in.shape[1:]
+            Cout, k = u.weight.shape[1], u.weight.shape[2]
+            out[name] = H * W * Cin * Cout * k * k
+        else:
+            Cout, Ho, Wo = fp_out.shape[1:]
+            Cin, k = u.weight.shape[1], u.weight.shape[2]
+            out[name] = Ho * Wo * Cout * Cin * k * k
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import torch.distributed as dist
+    from rdo_ptq_b200 import codec, synth, ops, _lib, evaluate as E
+    from rdo_ptq_b200.quantization import QuantModel
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.call("actq_stats_init", ops._p(torch.empty(2, dtype=torch.int32, device=dev)), 1, stream=None)  # arch gate early
+
+    def build():
+        torch.manual_seed(1005)
+        m = codec.ARCHS[ARCH](N=N_CH, M=M_CH).eval()
+        synth.init_weights(m, gain=GAIN)
+        m.to(dev)
+        qnn = QuantModel(m, WQ, AQ).eval()
+        return qnn
+
+    cali = synth.calibration_patches(POOL, PATCH, seed=1005 + rank).to(dev)     # each rank: its own shard of the pool
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(session, steps, warmup, probe=None):
+        for _ in range(warmup):
+            session.sweep()
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            session.sweep()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), _lib.launch_count() - l0
+
+    # ---- device-resident run (value) -------------------------------------------------------------------------------
+    qnn = build()
+    sess = CalibrationSession(qnn, cali, batch_size=PER_GPU_BATCH, host_caches=False, **CALIB)
+    n_units = len(sess.units)
+    macs = layer_macs(sess.units, sess.caches)
+    if sampler:
+        sampler.start()
+    ms, launches = timed(sess, args.steps, args.warmup)
+    value = n_units * PER_GPU_BATCH * world * args.steps / (ms / 1e3)
+
+    # ---- dominant kernel roofline: g_a.2 (192->192 5x5 s2 conv) forward, CUDA events on the launching stream ------------
+    top = "g_a.2"
+    u = dict(sess.units)[top]
+    q_in = sess.caches[top][0][:PER_GPU_BATCH].contiguous()
+    w = u.weight_quantizer(u.weight).detach()
+    d = ops.conv_desc(q_in.shape, w.shape, u.fwd_kwargs["stride"], u.fwd_kwargs["padding"])
+    for _ in range(3):
+        ops.conv2d_raw(q_in, w, u.bias.data, d)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    flush = torch.empty(64 * 1024 * 1024, device=dev)       # 256 MB > 126 MB L2
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        ops.conv2d_raw(q_in, w, u.bias.data, d)
+        b.record()
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    flops = 2.0 * macs[top] * PER_GPU_BATCH
+    pk = peaks()
+    roof = {"bound": "tensor", "kernel": "conv_fwd g_a.2 192->192 5x5 s2 @[8,192,128,128]",
+            "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
+            "frac": flops / (k_ms * 1e-3) / 1e12 / pk["tf"], "traffic": None, "peak_source": pk["src"],
+            "ms_per_launch": k_ms}
+    del flush
+
+    # ---- end-to-end run through the public API with HOST-resident caches (e2e) ------------------------------------------
+    del sess
+    torch.cuda.empty_cache()
+    qnn2 = build()
+    sess2 = CalibrationSession(qnn2, cali, batch_size=PER_GPU_BATCH, host_caches=True, **CALIB)
+    for _ in range(max(1, args.warmup // 2)):
+        sess2.sweep()
+        sess2.losses()
+    barrier()
+    sess2.h2d_bytes = 0
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        sess2.sweep()
+        d2h += 4 * 3 * len(sess2.losses())          # loss read-back every step (rec/task/round per unit)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_units * PER_GPU_BATCH * world * args.steps / t.item()
+    e2e = {"value": e2e_value, "unit": "imgs/s", "h2d_bytes_per_step": sess2.h2d_bytes // args.steps,
+           "d2h_bytes_per_step": d2h // args.steps}
+    del sess2
+
+    # ---- secondary metric: W8A8 evaluation forward Mpx/s on 768x512 ---------------------------------------------------
+    fwd = None
+    if rank == 0 and not args.skip_fwd:
+        qnn3 = build()
+        img = synth.synthetic_image(512, 768).to(dev)
+        qnn3.set_quant_state(True, False)
+        with torch.no_grad():
+            qnn3(E.pad(img, 256))
+            for m in qnn3.modules():
+                if hasattr(m, "trained"):
+                    m.trained = True
+            qnn3.set_quant_state(True, True)
+            qnn3.model.g_s[-1].set_quant_state(True, False)
+            for _ in range(2):
+                qnn3(E.pad(img, 256))
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                qnn3(E.pad(img, 256))
+            b.record()
+            torch.cuda.synchronize()
+        fwd = 5 * 512 * 768 / 1e6 / (a.elapsed_time(b) / 1e3)
+
+    clocks = sampler.summary() if sampler else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_baseline(steps=1, batch=PER_GPU_BATCH, units_subset=None)
+    if rank == 0:
+        line = {"metric": "calib imgs/s", "value": value, "unit": "imgs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"RDO-PTQ AdaRound calibration sweep, {ARCH} N={N_CH} M={M_CH} random-init, "
+                                       f"{n_units} units x batch {PER_GPU_BATCH}/GPU of {PATCH}x{PATCH} patches, W8 "
+                                       "per-channel, QDrop 0.5", "per_gpu_batch": PER_GPU_BATCH, "units": n_units,
+                           "l2_policy": "inputs larger than L2 (unit caches total > 126 MB; a different unit each call)",
+                           "engine": os.environ.get("B200LIC_ENGINE", "auto")},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "fwd_mpx_s": fwd, "gflop_per_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e9}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------- CPU arms
+def cpu_baseline(steps=1, batch=PER_GPU_BATCH, units_subset=None, warmup=0):
+    """The oracle port of the reference loop on the host cores (all threads), same model / patches / batch."""
+    from oracle import codec as ocodec, quant_wrap as owrap, calib as ocalib, quantizers as oq
+    from rdo_ptq_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(1005)
+    m = ocodec.ARCHS[ARCH](N=N_CH, M=M_CH).eval()
+    synth.init_weights(m, gain=GAIN)
+    qnn = owrap.QuantModel(m, WQ, AQ).eval()
+    cali = synth.calibration_patches(batch, PATCH)
+    units = [(n, u) for n, u in qnn.model.named_modules() if isinstance(u, owrap.QuantModule) and u.org_weight is not None]
+    store = {}
+    hooks = [u.register_forward_hook(lambda _m, i, o, n=n: store.__setitem__(n, (i[0].detach(), o.detach())))
+             for n, u in units]
+    qnn.set_quant_state(False, False)
+    with torch.no_grad():
+        qnn(cali)
+    fp = dict(store)
+    qnn.set_quant_state(True, False)
+    with torch.no_grad():
+        qnn(cali)
+    qin = {n: v[0] for n, v in store.items()}
+    for h in hooks:
+        h.remove()
+    opts = {}
+    for n, u in units:
+        u.weight_quantizer = oq.AdaRoundQuantizer(u.weight_quantizer, u.org_weight.data)
+        u.weight_quantizer.soft_targets = True
+        u.set_quant_state(True, False)
+        opts[n] = torch.optim.Adam([u.weight_quantizer.alpha])
+    g = torch.Generator().manual_seed(1)
+
+    def sweep():
+        for n, u in units:
+            keep = torch.rand(qin[n].shape, generator=g) < CALIB["input_prob"]
+            cur = torch.where(keep, qin[n], fp[n][0])
+            opts[n].zero_grad()
+            out = u(cur)
+            loss = oq.lp_loss(out, fp[n][1]) + oq.lp_loss(out, fp[n][1])
+            loss.backward()
+            opts[n].step()
+
+    for _ in range(warmup):
+        sweep()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sweep()
+    dt = time.perf_counter() - t0
+    return {"value": len(units) * batch * steps / dt, "unit": "imgs/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{steps} sweep(s) of the same {len(units)}-unit AdaRound iteration at batch {batch} "
+                      f"({PATCH}x{PATCH}), PyTorch-CPU fp32 oracle, {os.cpu_count()} threads",
+            "seconds": dt}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    r = cpu_baseline(steps=steps, warmup=1 if args.warmup > 0 else 0)
+    line = {"impl": "reference", "metric": "calib imgs/s", "value": r["value"], "unit": "imgs/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": 1 if args.warmup > 0 else 0,
+            "ms_per_step": r["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"oracle port of the reference AdaRound sweep on host cores, {ARCH} N={N_CH} "
+                                   f"M={M_CH}, batch {PER_GPU_BATCH} of {PATCH}x{PATCH}"},
+            "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0,
+                                       "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-fwd", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the "
+                         "host-CPU arm)")
+    run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -107,7 +107,8 @@ class LossFunction:
             for m in self.round_modules():
                 h = m.weight_quantizer.get_soft_targets()
                 rnd = rnd + self.weight * (1 - ((h - .5).abs() * 2).pow(b)).sum()
-        self.last = dict(rec=float(rec), task=float(task), round=float(rnd), b=b)
+        self.last = dict(rec=float(rec.detach()), task=float(task.detach()) if torch.is_tensor(task) else task,
+                         round=float(rnd.detach()) if torch.is_tensor(rnd) else rnd, b=b)
         return rnd + rec + task
 
 

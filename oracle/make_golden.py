@@ -73,6 +73,7 @@ def quantizer_vectors():
                     ar = TO.AdaRoundQuantizer(ref, w.clone(), "learned_hard_sigmoid")
                     am = oq.AdaRoundQuantizer(mine, w.clone())
                     _same(ar.alpha.data, am.alpha.data, f"{name}/alpha")
+                    alpha0 = ar.alpha.data.clone()
                     shift = torch.randn(w.shape, generator=g) * 2          # move alpha off its init
                     ar.alpha.data += shift
                     am.alpha.data += shift
@@ -83,7 +84,7 @@ def quantizer_vectors():
                         _same(a.detach(), b.detach(), f"{name}/adaround soft={soft}")
                         out["soft" if soft else "hard"] = a.detach()
                     _same(ar.get_soft_targets().detach(), am.get_soft_targets().detach(), f"{name}/h(alpha)")
-                    G[key].update(alpha0=ar.alpha.data - shift, alpha=ar.alpha.data.clone(), ada_soft=out["soft"],
+                    G[key].update(alpha0=alpha0, alpha=ar.alpha.data.clone(), ada_soft=out["soft"],
                                   ada_hard=out["hard"], h=ar.get_soft_targets().detach())
     # per-tensor (channel_wise=False) and symmetric
     for sym in (False, True):

@@ -1,0 +1,327 @@
+"""GPU parity of every libb200lic kernel against the CPU oracle / the reference-generated golden vectors.
+All calls go through the C ABI (rdo_ptq_b200.ops -> ctypes -> libb200lic.so).
+
+Tolerances: integer / index work (weight codes, activation codes, latent symbols, Q8.8) is BIT-EXACT;
+floating-point kernels are held to the north_star bar of 1e-4 relative (the SIMT engine is ~1e-6)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import quantizers as oq, codec as ocodec
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(dev):
+    from rdo_ptq_b200 import ops as _ops, _lib
+    assert _lib.lib().b200lic_device_check() == 0, _lib.lib().b200lic_last_error_string()
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------- K7 / K6 (bit-exact)
+def test_weight_quant_golden_bit_exact(ops, dev, golden_q):
+    n = 0
+    for key, g in golden_q.items():
+        if not key.startswith("uaq/") or "per_tensor" in key:
+            continue
+        w = g["w"].to(dev)
+        axis = None if w.dim() == 1 else (1 if g["tconv"] else 0)
+        delta, zp = ops.wq_init_minmax(w, axis, g["bits"], "scale" in g["method"], False)
+        assert torch.equal(delta.cpu().reshape(-1), g["delta"].reshape(-1)), key
+        assert torch.equal(zp.cpu().reshape(-1), g["zp"].reshape(-1)), key
+        dq, codes = ops.wq_fake_quant(w, delta, zp, axis, 2 ** g["bits"], want=("dq", "codes"))
+        assert torch.equal(codes.cpu(), g["codes"]) and torch.equal(dq.cpu(), g["dequant"]), key
+        if "alpha" in g:
+            a0 = ops.adaround_init_alpha(w, delta, axis)
+            assert torch.allclose(a0.cpu(), g["alpha0"], rtol=2e-6, atol=2e-6), key       # logf vs Sleef log
+            alpha = g["alpha"].to(dev)
+            hard, hcodes = ops.adaround_fwd(w, alpha, delta, zp, axis, 2 ** g["bits"], False, want_codes=True)
+            assert torch.equal(hard.cpu(), g["ada_hard"]), key                             # integer decision: exact
+            soft = ops.adaround_fwd(w, alpha, delta, zp, axis, 2 ** g["bits"], True)
+            assert torch.allclose(soft.cpu(), g["ada_soft"], rtol=0, atol=2e-7 * float(g["delta"].max()) * 256), key
+        n += 1
+    assert n >= 20
+
+
+def test_weight_quant_large_random_bit_exact(ops, dev):
+    g = torch.Generator().manual_seed(7)
+    for shape, tconv in (((192, 192, 5, 5), False), ((320, 192, 5, 5), True), ((192, 192), False), ((3, 192, 5, 5), True)):
+        w = torch.randn(shape, generator=g) * 0.05
+        q = oq.UniformAffineQuantizer(8, False, True, "max", tconv=tconv)
+        ref = q(w.clone())
+        axis = 1 if (tconv and w.dim() == 4) else 0
+        delta, zp = ops.wq_init_minmax(w.to(dev), axis, 8, False, False)
+        assert torch.equal(delta.cpu(), q.delta) and torch.equal(zp.cpu(), q.zero_point)
+        dq, codes, u8 = ops.wq_fake_quant(w.to(dev), delta, zp, axis, 256, want=("dq", "codes", "u8"))
+        assert torch.equal(dq.cpu(), ref) and torch.equal(codes.cpu(), q.codes(w))
+        assert torch.equal(u8.cpu().float(), q.codes(w))
+        assert torch.equal(ops.wq_dequant_u8(u8, delta, zp, axis).cpu(), ref)
+
+
+def test_adaround_backward_adam_matches_autograd(ops, dev):
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(16, 8, 3, 3, generator=g) * 0.1
+    q = oq.UniformAffineQuantizer(4, False, True, "max")
+    q(w.clone())
+    a = oq.AdaRoundQuantizer(q, w.clone())
+    a.soft_targets = True
+    with torch.no_grad():
+        a.alpha.add_(torch.randn(w.shape, generator=g))
+    alpha0 = a.alpha.data.clone()
+    d_wq = torch.randn(w.shape, generator=g)
+    opt = torch.optim.Adam([a.alpha], foreach=False)
+    m = torch.zeros_like(w).to(dev)
+    v = torch.zeros_like(w).to(dev)
+    alpha = alpha0.clone().to(dev)
+    for step, b in ((1, 0.0), (2, 20.0), (3, 8.5)):
+        opt.zero_grad()
+        loss = (a(w) * d_wq).sum() * 0.5
+        reg_ref = 0.0
+        if b > 0:
+            h = a.get_soft_targets()
+            reg_ref = 0.01 * (1 - ((h - .5).abs() * 2).pow(b)).sum()
+            loss = loss + reg_ref
+        loss.backward()
+        grad_ref = a.alpha.grad.clone()
+        opt.step()
+        reg = torch.zeros(1, device=dev)
+        d_alpha = torch.empty_like(alpha)
+        ops.adaround_bwd_adam(w.to(dev), alpha, q.delta.to(dev), q.zero_point.to(dev), d_wq.to(dev), m, v, 0, 16,
+                              step, grad_scale=0.5, reg_weight=0.01, reg_b=b, reg_loss=reg, d_alpha_out=d_alpha)
+        assert torch.allclose(d_alpha.cpu(), grad_ref, rtol=1e-4, atol=1e-7), step
+        assert torch.allclose(alpha.cpu(), a.alpha.data, rtol=1e-5, atol=2e-6), step
+        if b > 0:
+            assert abs(reg.item() - float(reg_ref)) < 1e-4 * max(1.0, abs(float(reg_ref)))
+
+
+# ------------------------------------------------------------------------------------------- K8 (bit-exact)
+def test_act_quant_golden_and_random_bit_exact(ops, dev, golden_q):
+    for name in ("x4", "x2"):
+        g = golden_q[f"actq/{name}"]
+        assert torch.equal(ops.act_quant(g["x"].to(dev)).cpu(), g["out"]), name
+    gen = torch.Generator().manual_seed(11)
+    for shape in ((2, 7, 33, 17), (1, 192, 64, 96), (3, 5, 1, 1), (1, 3, 100, 91)):
+        x = torch.randn(shape, generator=gen) * torch.rand(1, shape[1], 1, 1, generator=gen) * 10
+        ref, ref_codes = oq.act_quant(x, 8, return_codes=True)
+        out, codes = ops.act_quant(x.to(dev), 8, want_codes=True)
+        assert torch.equal(codes.cpu(), ref_codes) and torch.equal(out.cpu(), ref), shape
+        ref10 = oq.act_quant(x, 10)
+        assert torch.equal(ops.act_quant(x.to(dev), 10).cpu(), ref10), shape
+    # idempotence property on the quantised grid at full size (18.9 M elements = g_a stage-1 map at 512x768)
+    big = torch.randn(1, 192, 256, 384, generator=gen).to(dev)
+    once = ops.act_quant(big)
+    codes_per_ch = torch.stack([once[0, c].unique().numel() * torch.ones(1) for c in (0, 95, 191)])
+    assert (codes_per_ch <= 256).all()
+    twice = ops.act_quant(once)
+    assert (twice - once).abs().max().item() <= 2e-6 * once.abs().max().item()
+
+
+def test_fixed_point_q88_bit_exact(ops, dev, golden_q):
+    g = golden_q["lu"]
+    assert torch.equal(ops.fixed_point(g["x"].to(dev)).cpu(), g["q88"])
+    x = torch.randn(100003) * 100
+    assert torch.equal(ops.fixed_point(x.to(dev)).cpu(), oq.lu_act_quantizer(x))
+
+
+# ------------------------------------------------------------------------------------------- K9 / K10 / K11
+def test_gaussian_likelihood(ops, dev, golden_c):
+    g = golden_c["gc"]
+    yh, lik, bits = ops.gaussian_lik(g["y"].to(dev), g["scales"].to(dev), g["means"].to(dev))
+    assert torch.equal(yh.cpu(), g["y_hat"])                                    # latent symbols: bit-exact
+    assert torch.allclose(lik.cpu(), g["lik"], rtol=1e-4, atol=3e-7)
+    assert abs(bits.item() - (-torch.log2(g["lik"]).sum().item())) < 1e-3 * g["lik"].numel() / 100
+    yh0, lik0, _ = ops.gaussian_lik(g["y"].to(dev), g["scales"].to(dev))
+    assert torch.equal(yh0.cpu(), g["y_hat0"]) and torch.allclose(lik0.cpu(), g["lik0"], rtol=1e-4, atol=3e-7)
+    # strided chunk(2,1) parameters, odd sizes (scalar path) and batch > 1
+    gen = torch.Generator().manual_seed(5)
+    gc = ocodec.GaussianConditional(None).eval()
+    for shape in ((2, 6, 5, 7), (3, 8, 8, 12), (1, 320, 32, 48)):
+        y = torch.randn(shape, generator=gen) * 3
+        gp = torch.randn(shape[0], 2 * shape[1], *shape[2:], generator=gen)
+        sc, mu = gp.chunk(2, 1)
+        ref_yh, ref_lik = gc(y, sc, means=mu)
+        gpd = gp.to(dev)
+        scd, mud = gpd.chunk(2, 1)
+        yh, lik, bits = ops.gaussian_lik(y.to(dev), scd, mud)
+        assert torch.equal(yh.cpu(), ref_yh), shape
+        assert torch.allclose(lik.cpu(), ref_lik, rtol=1e-4, atol=3e-7), shape
+        ref_bits = -torch.log2(ref_lik.double()).sum().item()
+        assert abs(bits.item() - ref_bits) < 1e-4 * ref_bits + 1e-2, shape
+    assert torch.equal(ops.round_latent(y.to(dev), mu.contiguous().to(dev)).cpu(), ref_yh)
+
+
+def test_factorized_likelihood(ops, dev, golden_c):
+    from rdo_ptq_b200.codec import EntropyBottleneck
+    g = golden_c["eb"]
+    eb = EntropyBottleneck(5).eval()
+    eb.load_state_dict(g["state"])
+    eb.to(dev)
+    zh, lik = eb(g["z"].to(dev))
+    assert torch.equal(zh.cpu(), g["z_hat"])                                    # latent symbols: bit-exact
+    assert torch.allclose(lik.cpu(), g["lik"], rtol=2e-4, atol=3e-7)
+    ref_bits = -torch.log2(g["lik"].double()).sum().item()
+    assert abs(eb.last_bits.item() - ref_bits) < 1e-4 * ref_bits + 1e-2
+    # default init at production width, z in Kodak shape
+    torch.manual_seed(0)
+    oe = ocodec.EntropyBottleneck(192).eval()
+    pe = EntropyBottleneck(192).eval()
+    pe.load_state_dict(oe.state_dict())
+    pe.to(dev)
+    z = torch.randn(2, 192, 8, 12) * 4
+    rz, rl = oe(z)
+    gz, gl = pe(z.to(dev))
+    assert torch.equal(gz.cpu(), rz) and torch.allclose(gl.cpu(), rl.detach(), rtol=2e-4, atol=3e-7)
+
+
+def test_lp_loss_and_reductions(ops, dev, golden_q):
+    for p in (2.0, 1.0, 2.4):
+        g = golden_q[f"lp/{p}"]
+        a = g["a"].clone().requires_grad_(True)
+        ref = oq.lp_loss(a, g["b"], p)
+        ref.backward()
+        denom = a.numel() // a.shape[1]
+        loss, grad = ops.lp_loss_fwd_bwd(g["a"].to(dev), g["b"].to(dev), p, scale=1.0 / denom)
+        assert abs(loss.item() - g["loss"].item()) < 1e-5 * abs(g["loss"].item())
+        assert torch.allclose(grad.cpu(), a.grad, rtol=1e-5, atol=1e-7)
+    gen = torch.Generator().manual_seed(2)
+    a, b = torch.rand(1, 3, 512, 768, generator=gen) * 1.2 - 0.1, torch.rand(1, 3, 512, 768, generator=gen)
+    s = ops.sq_err_sum(a.to(dev), b.to(dev)).cpu().double()
+    assert abs(s[0] - ((a - b).double() ** 2).sum()) < 1e-5 * s[0]
+    assert abs(s[1] - ((a.clamp(0, 1) - b).double() ** 2).sum()) < 1e-5 * s[1]
+    lik = torch.rand(100001, generator=gen).clamp_min(1e-9)
+    assert abs(ops.bits_sum(lik.to(dev)).item() - (-torch.log2(lik.double()).sum().item())) < 1e-5 * lik.numel()
+
+
+# ------------------------------------------------------------------------------------------- convolutions
+CONV_CASES = [  # N, Cin, H, W, Cout, k, stride, pad
+    (2, 3, 32, 48, 24, 5, 2, 2), (1, 24, 16, 24, 24, 5, 2, 2), (2, 16, 9, 11, 20, 3, 1, 1), (1, 20, 8, 12, 40, 3, 2, 1),
+    (2, 12, 7, 5, 6, 1, 1, 0), (1, 8, 10, 14, 16, 1, 2, 0), (1, 192, 16, 24, 192, 5, 2, 2), (1, 130, 12, 12, 70, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_bwd(ops, dev, case):
+    N, Cin, H, W, Cout, k, st, pd = case
+    gen = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=gen, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) * 0.1).requires_grad_(True)
+    b = torch.randn(Cout, generator=gen)
+    for act, slope in ((ops.ACT_NONE, 0.0), (ops.ACT_LEAKY_RELU, 0.01), (ops.ACT_RELU, 0.0)):
+        ref = F.conv2d(x, w, b, stride=st, padding=pd)
+        ref = F.leaky_relu(ref, slope) if act == ops.ACT_LEAKY_RELU else (F.relu(ref) if act == ops.ACT_RELU else ref)
+        xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().to(dev).requires_grad_(True)
+        out = ops.conv2d(xd, wd, b.to(dev), st, pd, act=act, slope=slope)
+        assert rel_err(out, ref) < 1e-5, (case, act)
+        dy = torch.randn(ref.shape, generator=gen)
+        gx, gw = torch.autograd.grad(ref, (x, w), dy)
+        out.backward(dy.to(dev))
+        assert rel_err(xd.grad, gx) < 1e-5 and rel_err(wd.grad, gw) < 1e-5, (case, act)
+
+
+DECONV_CASES = [  # N, Cin, H, W, Cout, k, stride, pad, out_pad
+    (2, 24, 8, 12, 16, 5, 2, 2, 1), (1, 16, 16, 24, 3, 5, 2, 2, 1), (1, 12, 5, 7, 10, 3, 2, 1, 1), (2, 8, 6, 6, 8, 3, 1, 1, 0),
+    (1, 192, 8, 12, 192, 5, 2, 2, 1), (1, 6, 4, 5, 4, 5, 2, 2, 0), (1, 4, 3, 3, 5, 4, 3, 1, 2),
+]
+
+
+@pytest.mark.parametrize("case", DECONV_CASES)
+def test_deconv_fwd_bwd(ops, dev, case):
+    N, Cin, H, W, Cout, k, st, pd, op = case
+    gen = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=gen, requires_grad=True)
+    w = (torch.randn(Cin, Cout, k, k, generator=gen) * 0.1).requires_grad_(True)
+    b = torch.randn(Cout, generator=gen)
+    ref = F.leaky_relu(F.conv_transpose2d(x, w, b, stride=st, padding=pd, output_padding=op), 0.01)
+    xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().to(dev).requires_grad_(True)
+    out = ops.conv_transpose2d(xd, wd, b.to(dev), st, pd, op, act=ops.ACT_LEAKY_RELU, slope=0.01)
+    assert out.shape == ref.shape and rel_err(out, ref) < 1e-5, case
+    dy = torch.randn(ref.shape, generator=gen)
+    gx, gw = torch.autograd.grad(ref, (x, w), dy)
+    out.backward(dy.to(dev))
+    assert rel_err(xd.grad, gx) < 1e-5 and rel_err(wd.grad, gw) < 1e-5, case
+
+
+def test_conv_rejects_bad_arguments(ops, dev):
+    from rdo_ptq_b200._lib import B200LicError
+    x = torch.randn(1, 4, 8, 8, device=dev)
+    with pytest.raises(ValueError):
+        ops.conv2d(x, torch.randn(4, 5, 3, 3, device=dev), None, 1, 1)
+    with pytest.raises(NotImplementedError):
+        ops.conv2d(x, torch.randn(4, 4, 3, 3, device=dev), None, 1, 1, dilation=2)
+    with pytest.raises(RuntimeError):
+        ops.conv2d(x.cpu(), torch.randn(4, 4, 3, 3), None, 1, 1)            # no CPU fallback
+    d = ops.conv_desc(x.shape, (4, 4, 3, 3), 1, 1)
+    d.Ho = 99
+    with pytest.raises(B200LicError):
+        ops.conv2d_raw(x, torch.randn(4, 4, 3, 3, device=dev), None, d)
+
+
+def test_conv_linearity_property_full_size(ops, dev):
+    """Size-independent property at BASELINE size (g_a conv1 of mbt2018-mean @512x768): conv(a*x1+x2) = a*conv(x1)+conv(x2)."""
+    gen = torch.Generator().manual_seed(1)
+    x1 = torch.randn(1, 192, 256, 384, generator=gen).to(dev)
+    x2 = torch.randn(1, 192, 256, 384, generator=gen).to(dev)
+    w = (torch.randn(192, 192, 5, 5, generator=gen) * 0.02).to(dev)
+    y1, y2 = ops.conv2d(x1, w, None, 2, 2), ops.conv2d(x2, w, None, 2, 2)
+    y12 = ops.conv2d(x1 * 0.5 + x2, w, None, 2, 2)
+    assert y1.shape == (1, 192, 128, 192)
+    assert rel_err(y12, y1 * 0.5 + y2) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------- GDN
+def test_gdn_fwd_bwd(ops, dev, golden_c):
+    from rdo_ptq_b200.codec import GDN
+    g = golden_c["gdn"]
+    for inverse, key in ((False, "gdn"), (True, "igdn")):
+        ref_mod = ocodec.GDN(6, inverse=inverse)
+        ref_mod.load_state_dict(g["state"])
+        mod = GDN(6, inverse=inverse)
+        mod.load_state_dict(g["state"])
+        mod.to(dev)
+        x = g["x"].clone().requires_grad_(True)
+        ref = ref_mod(x)
+        assert torch.allclose(ref.detach(), golden_c[key]["y"], rtol=1e-6, atol=1e-7)
+        xd = g["x"].to(dev).requires_grad_(True)
+        out = mod(xd)
+        assert rel_err(out, ref) < 1e-5
+        dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9))
+        ref.backward(dy)
+        out.backward(dy.to(dev))
+        assert rel_err(xd.grad, x.grad) < 1e-4
+        assert rel_err(mod.gamma.grad, ref_mod.gamma.grad) < 1e-4
+        assert rel_err(mod.beta.grad, ref_mod.beta.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- elementwise helpers
+def test_elementwise_helpers(ops, dev):
+    gen = torch.Generator().manual_seed(4)
+    a, b, c = (torch.randn(2, 5, 7, 3, generator=gen) for _ in range(3))
+    ad, bd, cd = a.to(dev), b.to(dev), c.to(dev)
+    assert torch.equal(ops.add_act(ad, bd).cpu(), a + b)
+    assert torch.equal(ops.add_act(ad, bd, ops.ACT_LEAKY_RELU, 0.01).cpu(), F.leaky_relu(a + b, 0.01))
+    assert torch.equal(ops.abs_(ad).cpu(), a.abs())
+    assert torch.allclose(ops.attn_gate(ad, bd, cd).cpu(), a * torch.sigmoid(b) + c, rtol=1e-6, atol=1e-6)
+    x = torch.randn(2, 12, 3, 5, generator=gen)
+    assert torch.equal(ops.pixel_shuffle(x.to(dev), 2).cpu(), F.pixel_shuffle(x, 2))
+    xr = x.to(dev).requires_grad_(True)
+    y = ops.pixel_shuffle(xr, 2, ops.ACT_LEAKY_RELU, 0.01)
+    y.backward(torch.ones_like(y))
+    xc = x.clone().requires_grad_(True)
+    F.leaky_relu(F.pixel_shuffle(xc, 2), 0.01).sum().backward()
+    assert torch.equal(xr.grad.cpu(), xc.grad)
+    q, fp = torch.randn(6, 4, 5, generator=gen), torch.randn(6, 4, 5, generator=gen)
+    idx = torch.tensor([4, 0, 3])
+    mask = torch.rand(3, 4, 5, generator=gen) < 0.5
+    out = ops.gather_mix(q.to(dev), fp.to(dev), idx.to(dev), mask=mask.to(dev))
+    assert torch.equal(out.cpu(), torch.where(mask, q[idx], fp[idx]))
+    mixed = ops.gather_mix(q.to(dev), fp.to(dev), idx.to(dev), prob=0.5, seed=123).cpu()
+    assert ((mixed == q[idx]) | (mixed == fp[idx])).all()
+    big_q, big_f = torch.zeros(4, 100000), torch.ones(4, 100000)
+    frac = ops.gather_mix(big_q.to(dev), big_f.to(dev), None, prob=0.5, seed=7).mean().item()
+    assert abs(frac - 0.5) < 0.01

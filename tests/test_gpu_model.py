@@ -1,0 +1,256 @@
+"""GPU parity of the drop-in surface (QuantModel / QuantModule / blocks / reconstruction / evaluation) against the
+CPU oracle on identical seeded weights and synthetic inputs.
+
+Bars (BASELINE.json north_star): integer weight codes bit-exact; per-layer outputs <= 1e-4 relative; end-to-end bpp
+within 1e-3 and PSNR within 0.01 dB."""
+import math
+
+import pytest
+import torch
+
+from oracle import codec as ocodec, quant_wrap as owrap, calib as ocalib, evalpath as oeval, quantizers as oq
+from rdo_ptq_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+WQ = dict(n_bits=8, channel_wise=True, scale_method="max")
+AQ = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def build_pair(arch, kw, gain, dev, wq=WQ, aq=AQ, state=None):
+    """Oracle model on CPU + product model on the GPU with identical parameters, both wrapped in QuantModel after
+    one FP forward (bakes the MaskedConv2d mask)."""
+    from rdo_ptq_b200 import codec, quantization as Q
+    torch.manual_seed(1005)
+    om = ocodec.ARCHS[arch](**kw).eval()
+    if state is None:
+        synth.init_weights(om, gain=gain)
+    else:
+        om.load_state_dict(state)
+    pm = codec.ARCHS[arch](**kw).eval()
+    pm.load_state_dict(om.state_dict())
+    pm.to(dev)
+    return om, pm, Q
+
+
+def per_layer_outputs(model, x, kinds):
+    outs, hooks = [], []
+    for name, m in model.named_modules():
+        if isinstance(m, kinds):
+            hooks.append(m.register_forward_hook(lambda _m, _i, o, name=name: outs.append((name, o.detach()))))
+    with torch.no_grad():
+        res = model(x)
+    for h in hooks:
+        h.remove()
+    return res, outs
+
+
+@pytest.mark.parametrize("arch,kw,gain", [("mbt2018-mean", dict(N=8, M=12), 1.2),
+                                          ("bmshj2018-hyperprior", dict(N=8, M=12), 1.2),
+                                          ("cheng2020-attn", dict(N=12), 0.6)])
+def test_fp_forward_matches_golden(dev, golden_c, arch, kw, gain):
+    g = golden_c[f"model/{arch}"]
+    om, pm, _ = build_pair(arch, g["kw"], gain, dev, state=g["state"])
+    with torch.no_grad():
+        out = pm(g["x"].to(dev))
+    assert rel_err(out["x_hat"], g["x_hat"]) < 1e-4
+    from rdo_ptq_b200 import evaluate as E
+    assert abs(E.compute_bpp(out) - g["bpp"]) < 1e-3
+    assert abs(E.compute_psnr(out["x_hat"], g["x"].to(dev), clamp=True) - g["psnr"]) < 0.01
+
+
+@pytest.mark.parametrize("arch,kw,gain,hw", [("mbt2018-mean", dict(N=32, M=48), 1.2, (128, 192)),
+                                             ("cheng2020-attn", dict(N=24), 0.6, (64, 128))])
+def test_quantized_forward_per_layer_parity(dev, arch, kw, gain, hw):
+    om, pm, Q = build_pair(arch, kw, gain, dev)
+    x = synth.synthetic_image(*hw)
+    with torch.no_grad():
+        om(x), pm(x.to(dev))                                   # FP forward first (Q5)
+    oq_model, pq_model = owrap.QuantModel(om, WQ, AQ).eval(), Q.QuantModel(pm, WQ, AQ).eval()
+    oq_model.set_quant_state(True, False)
+    pq_model.set_quant_state(True, False)
+    ref, ref_layers = per_layer_outputs(oq_model, x, (owrap.QuantModule,))
+    out, layers = per_layer_outputs(pq_model, x.to(dev), (Q.QuantModule,))
+    assert [n for n, _ in layers] == [n for n, _ in ref_layers] and len(layers) > 15
+    # integer weight codes: bit-exact for every wrapped layer
+    omods = dict((n, m) for n, m in oq_model.named_modules() if isinstance(m, owrap.QuantModule))
+    for n, m in pq_model.named_modules():
+        if isinstance(m, Q.QuantModule) and m.weight is not None:
+            o = omods[n]
+            assert torch.equal(m.weight_quantizer.delta.cpu().reshape(-1), o.weight_quantizer.delta.reshape(-1)), n
+            assert torch.equal(m.weight_quantizer.codes(m.weight).cpu(), o.weight_quantizer.codes(o.weight)), n
+    worst = max(rel_err(a, b) for (_, a), (_, b) in zip(layers, ref_layers))
+    assert worst < 1e-4, worst
+    from rdo_ptq_b200 import evaluate as E
+    assert abs(E.compute_bpp(out) - oeval.compute_bpp(ref)) < 1e-3
+    # W8A8: dynamic activation quant switched on for trained layers (main2.py:272-282)
+    for q in (oq_model, pq_model):
+        for m in q.modules():
+            if hasattr(m, "trained"):
+                m.trained = True
+        q.set_quant_state(True, True)
+    ref8, ref8_layers = per_layer_outputs(oq_model, x, (owrap.QuantModule,))
+    out8, layers8 = per_layer_outputs(pq_model, x.to(dev), (Q.QuantModule,))
+    # activation codes flip when a pre-quant value sits on a rounding boundary, so compare in units of one A8 step
+    n_bad = 0
+    for (n, a), (_, b) in zip(layers8, ref8_layers):
+        step = (b.amax() - b.amin()).item() / 255 + 1e-12
+        n_bad += ((a.cpu() - b).abs() > 1.01 * step).sum().item()
+    assert n_bad == 0
+    assert abs(E.compute_bpp(out8) - oeval.compute_bpp(ref8)) < 5e-3
+    p_ref = oeval.compute_psnr(x, ref8["x_hat"].clamp(0, 1))
+    assert abs(E.compute_psnr(out8["x_hat"], x.to(dev), clamp=True) - p_ref) < 0.05
+
+
+def test_evaluate_matches_oracle_end_to_end(dev):
+    """Test_kodak path (pad-256, crop, clamp, PSNR, bpp) on Kodak-shaped synthetic images, W8 weights."""
+    from rdo_ptq_b200 import evaluate as E
+    om, pm, Q = build_pair("mbt2018-mean", dict(N=16, M=24), 1.2, dev)
+    imgs = synth.synthetic_images(2, 200, 300)
+    with torch.no_grad():
+        om(oeval.pad(imgs[0], 256)), pm(E.pad(imgs[0].to(dev), 256))
+    oqm, pqm = owrap.QuantModel(om, WQ, AQ).eval(), Q.QuantModel(pm, WQ, AQ).eval()
+    oqm.set_quant_state(True, False)
+    pqm.set_quant_state(True, False)
+    ps, bs = oeval.evaluate(oqm, imgs)
+    res = E.evaluate(pqm, [i.to(dev) for i in imgs])
+    assert res["count"] == 2
+    assert abs(res["psnr"] - sum(ps) / 2) < 0.01 and abs(res["bpp"] - sum(bs) / 2) < 1e-3
+    rd = E.RateDistortionLoss(lmbda=0.01)(pqm(E.pad(imgs[0].to(dev), 256)), E.pad(imgs[0].to(dev), 256))
+    with torch.no_grad():
+        ref_rd = oeval.rate_distortion_loss(oqm(oeval.pad(imgs[0], 256)), oeval.pad(imgs[0], 256), 0.01)
+    assert abs(rd["loss"] - float(ref_rd["loss"])) < 1e-3 * max(1.0, float(ref_rd["loss"]))
+
+
+def test_lu_uint8_q88_forward_parity(dev):
+    """BASELINE config 1: light-uniform-PTQ rules on Balle2018 (uint8 per-channel weights, Q8.8 activations, GDN fp32)."""
+    from rdo_ptq_b200 import quant_int as LU, evaluate as E
+    om, pm, _ = build_pair("bmshj2018-hyperprior", dict(N=16, M=24), 1.2, dev)
+    x = synth.synthetic_image(128, 192)
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=True)
+    oqm, pqm = owrap.LUQuantModel(om, wq, aq).eval(), LU.QuantModel(pm, wq, aq).eval()
+    oqm.set_quant_state(True, True)
+    pqm.set_quant_state(True, True)
+    ref, ref_layers = per_layer_outputs(oqm, x, (owrap.LUQuantModule,))
+    out, layers = per_layer_outputs(pqm, x.to(dev), (LU.QuantModule,))
+    om_mods = [m for m in oqm.modules() if isinstance(m, owrap.LUQuantModule)]
+    pm_mods = [m for m in pqm.modules() if isinstance(m, LU.QuantModule)]
+    assert len(om_mods) == len(pm_mods) == 14
+    for a, b in zip(pm_mods, om_mods):
+        assert a.weight.dtype == torch.uint8 and torch.equal(a.weight.data.cpu(), b.weight.data)      # bit-exact codes
+    for (n, a), (_, b) in zip(layers, ref_layers):
+        assert ((a.cpu() - b).abs() <= 1.0 / 256 + 1e-6).all(), n        # at most one Q8.8 step on boundary flips
+        assert ((a.cpu() - b).abs() > 0).float().mean() < 0.02, n
+    assert abs(E.compute_bpp(out) - oeval.compute_bpp(ref)) < 5e-3
+
+
+class ReplayPlan:
+    """Feeds the oracle's CPU-drawn (idx, mask) pairs to the CUDA loop."""
+
+    def __init__(self, seed=1005):
+        self.cpu = ocalib.DrawPlan(seed)
+
+    def draw(self, unit_id, it, n, bs, shape, prob, device):
+        idx, keep = self.cpu.draw(unit_id, it, n, bs, shape, prob)
+        return idx.to(device), (None if keep is None else keep.to(device)), 0
+
+
+def _calib_pair(dev, arch, kw, gain, bits=4):
+    wq = dict(n_bits=bits, channel_wise=True, scale_method="max")
+    om, pm, Q = build_pair(arch, kw, gain, dev)
+    cali = synth.calibration_patches(4, 64)
+    with torch.no_grad():
+        om(cali[:1]), pm(cali[:1].to(dev))
+    oqm, pqm = owrap.QuantModel(om, wq, AQ).eval(), Q.QuantModel(pm, wq, AQ).eval()
+    for q, c in ((oqm, cali), (pqm, cali.to(dev))):
+        q.set_quant_state(True, False)
+        with torch.no_grad():
+            q(c[:2])                                            # scale init (main2.py:194-198)
+    return oqm, pqm, Q, cali
+
+
+@pytest.mark.parametrize("layer_path", ["g_a.2", "g_a.1", "g_s.2", "h_s.0"])
+def test_layer_reconstruction_parity(dev, layer_path):
+    """First-iteration dL/dalpha and the alpha trajectory over 30 iterations of one AdaRound problem."""
+    oqm, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+    sub, idx = layer_path.split(".")
+    olayer, player = getattr(oqm.model, sub)[int(idx)], getattr(pqm.model, sub)[int(idx)]
+    kw = dict(batch_size=2, iters=30, weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5)
+    otrace, ptrace = {}, {}
+    ocalib.reconstruct(oqm, olayer, 3, idx, cali, plan=ocalib.DrawPlan(), trace=otrace, **kw)
+
+    class Args:
+        task_loss = 2.0
+    Q.layer_reconstruction(pqm, player, idx, cali.to(dev), asym=True, act_quant=False, opt_mode='mse', args=Args(),
+                           plan=ReplayPlan(), unit_id=3, trace=ptrace, **kw)
+    assert rel_err(ptrace["out"], otrace["out0"]) < 1e-4
+    assert rel_err(ptrace["d_alpha"][0], otrace["grad0"][0]) < 1e-3
+    a_ref, a_gpu = olayer.weight_quantizer.alpha.data, player.weight_quantizer.alpha.data.cpu()
+    assert (a_ref - a_gpu).abs().max().item() < 5e-3               # 30 Adam steps of 1e-3 each: well inside 1 step
+    flips = ((a_ref >= 0) != (a_gpu >= 0)).float().mean().item()
+    assert flips < 1e-3
+    assert player.trained and not player.weight_quantizer.soft_targets
+    # hardened weights: integer codes agree wherever the rounding decision agrees
+    oc, pc = olayer.weight_quantizer.codes(olayer.weight), player.weight_quantizer.codes(player.weight).cpu()
+    assert ((oc != pc).float().mean().item()) <= flips + 1e-9
+
+
+def test_block_reconstruction_parity(dev):
+    """Cheng2020 residual blocks: joint AdaRound over all QuantModules of a block (dgrad through conv, GDN, subpel)."""
+    oqm, pqm, Q, cali = _calib_pair(dev, "cheng2020-attn", dict(N=12), 0.6)
+    kw = dict(batch_size=2, iters=12, weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5)
+
+    class Args:
+        task_loss = 2.0
+    for unit_id, (sub, idx) in enumerate((("g_a", 0), ("g_a", 1), ("g_s", 2))):
+        oblk, pblk = getattr(oqm.model, sub)[idx], getattr(pqm.model, sub)[idx]
+        otrace, ptrace = {}, {}
+        ocalib.reconstruct(oqm, oblk, unit_id, str(idx), cali, plan=ocalib.DrawPlan(), trace=otrace, **kw)
+        Q.block_reconstruction(pqm, pblk, str(idx), cali.to(dev), asym=True, act_quant=False, opt_mode='mse',
+                               args=Args(), plan=ReplayPlan(), unit_id=unit_id, trace=ptrace, **kw)
+        assert rel_err(ptrace["out"], otrace["out0"]) < 1e-4, (sub, idx)
+        assert len(ptrace["d_alpha"]) == len(otrace["grad0"]) >= 3
+        for a, b in zip(ptrace["d_alpha"], otrace["grad0"]):
+            assert rel_err(a, b) < 2e-3, (sub, idx)
+        omods = [m for m in oblk.modules() if isinstance(m, owrap.QuantModule)]
+        pmods = [m for m in pblk.modules() if isinstance(m, Q.QuantModule)]
+        for a, b in zip(pmods, omods):
+            assert (a.weight_quantizer.alpha.data.cpu() - b.weight_quantizer.alpha.data).abs().max().item() < 5e-3
+        assert pblk.trained and all(m.trained for m in pmods)
+
+
+def test_reference_style_autograd_loop_still_works(dev):
+    """Drop-in check: the reference's own loop shape (AdaRoundQuantizer + torch.optim.Adam + err.backward())."""
+    oqm, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=8, M=12), 1.2)
+    layer = pqm.model.g_a[2]
+    (q_in, fp_in), fp_out = Q.save_inp_oup_data(pqm, layer, cali.to(dev), True, False, batch_size=1, input_prob=True)
+    layer.weight_quantizer = Q.AdaRoundQuantizer(uaq=layer.weight_quantizer, round_mode='learned_hard_sigmoid',
+                                                 weight_tensor=layer.org_weight.data)
+    layer.weight_quantizer.soft_targets = True
+    layer.set_quant_state(True, False)
+    opt = torch.optim.Adam([layer.weight_quantizer.alpha])
+    before = Q.lp_loss(layer(q_in), fp_out).item()
+    for _ in range(40):
+        opt.zero_grad()
+        out = layer(q_in)
+        _, g = __import__("rdo_ptq_b200").ops.lp_loss_fwd_bwd(out.detach(), fp_out, 2.0, scale=1.0 / (out.numel() // out.shape[1]))
+        out.backward(g)
+        opt.step()
+    assert Q.lp_loss(layer(q_in), fp_out).item() < before
+
+
+def test_quant_model_pickles(dev, tmp_path):
+    """main2.py:285-290 saves the whole QuantModel object."""
+    oqm, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=8, M=12), 1.2)
+    p = tmp_path / "qnn.pth"
+    torch.save(pqm, p)
+    back = torch.load(p, weights_only=False)
+    x = cali[:1].to(dev)
+    with torch.no_grad():
+        assert torch.equal(back(x)["x_hat"], pqm(x)["x_hat"])

@@ -1,0 +1,80 @@
+"""CPU: host-side logic of the product (graph rewrite, schedules, sharding) incl. the N>1 path on gloo, world_size 2."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+from oracle import quant_wrap as owrap, codec as ocodec
+
+
+def test_product_graph_rewrite_matches_oracle():
+    from rdo_ptq_b200 import codec, quantization as Q
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    for arch, kw in (("mbt2018-mean", dict(N=8, M=12)), ("bmshj2018-hyperprior", dict(N=8, M=12)),
+                     ("cheng2020-attn", dict(N=12))):
+        p = Q.QuantModel(codec.ARCHS[arch](**kw), wq, aq)
+        o = owrap.QuantModel(ocodec.ARCHS[arch](**kw), wq, aq)
+        ps = [(n, type(m).__name__) for n, m in p.named_modules()
+              if isinstance(m, (Q.QuantModule, Q.BaseQuantBlock, Q.StraightThrough))]
+        os_ = [(n, type(m).__name__) for n, m in o.named_modules()
+               if isinstance(m, (owrap.QuantModule, owrap.BaseQuantBlock, owrap.StraightThrough))]
+        assert ps == os_ and len(ps) > 10, arch
+        pa = [type(m.activation_function).__name__ for m in p.modules() if isinstance(m, Q.QuantModule)]
+        oa = [type(m.activation_function).__name__ for m in o.modules() if isinstance(m, owrap.QuantModule)]
+        assert pa == oa
+        assert sorted(p.state_dict().keys()) == sorted(o.state_dict().keys())
+    from rdo_ptq_b200.quantization.session import reconstruction_units
+    p = Q.QuantModel(codec.ARCHS["mbt2018-mean"](N=8, M=12), wq, aq)
+    assert len(reconstruction_units(p)) == 20
+
+
+def test_lu_graph_rewrite_and_schedule():
+    from rdo_ptq_b200 import codec, quant_int as LU, quantization as Q
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=True)
+    m = LU.QuantModel(codec.ScaleHyperprior(8, 12), wq, aq)
+    assert sum(isinstance(x, LU.QuantModule) for x in m.modules()) == 14
+    assert sum(isinstance(x, codec.GDN) for x in m.modules()) == 6            # GDN stays fp32
+    c = LU.QuantCodingModel(codec.ScaleHyperprior(8, 12), wq, aq)
+    assert sum(isinstance(x, LU.QuantModule) for x in c.modules()) == 6       # h_a + h_s only
+    d = Q.LinearTempDecay(20000, rel_start_decay=0.2, start_b=20, end_b=2)
+    assert d(0) == 20 and abs(d(12000) - 11.0) < 1e-9 and d(20000) == 2
+    from rdo_ptq_b200 import evaluate as E
+    x = torch.rand(1, 3, 70, 100)
+    assert torch.equal(E.crop(E.pad(x, 64), (70, 100)), x)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rdo_ptq_b200 import dist as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    idx = D.shard_indices(7)
+    grads = [torch.full((3, 2), float(rank + 1)), torch.full((5,), float(10 * (rank + 1)))]
+    D.allreduce_flat_(grads, average=True)
+    psnr, bpp, cnt = D.reduce_metrics(30.0 * len(idx), 0.5 * len(idx), len(idx))
+    q.put((rank, idx, grads[0][0, 0].item(), grads[1][0].item(), psnr, bpp, cnt))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res[0][1] == [0, 2, 4, 6] and res[1][1] == [1, 3, 5]               # round-robin image shards
+    for r in res:
+        assert r[2] == 1.5 and r[3] == 15.0                                   # mean of the two ranks' gradients
+        assert abs(r[4] - 30.0) < 1e-12 and abs(r[5] - 0.5) < 1e-12 and r[6] == 7

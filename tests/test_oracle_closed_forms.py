@@ -1,0 +1,127 @@
+"""CPU: self-checks of the compressai restatement (oracle.codec) against closed forms -- the reference holds no
+fixture for these pieces ("parity unpinned")."""
+import math
+
+import numpy as np
+import torch
+from scipy import special
+
+from oracle import codec, evalpath, quant_wrap, calib
+from rdo_ptq_b200 import synth
+
+
+def test_gaussian_likelihood_is_a_pmf_and_matches_scipy():
+    gc = codec.GaussianConditional(None).eval()
+    ks = torch.arange(-60, 61, dtype=torch.float32).view(1, 1, -1, 1)
+    for sigma, mu in ((0.11, 0.3), (1.0, -0.2), (4.0, 0.45)):
+        y = ks + mu
+        _, lik = gc(y, torch.full_like(y, sigma), means=torch.full_like(y, mu))
+        assert abs(lik.sum().item() - 1.0) < 1e-4
+        k = ks.flatten().double().numpy()
+        ref = 0.5 * special.erfc(-(0.5 - np.abs(k)) / sigma / math.sqrt(2)) - 0.5 * special.erfc(-(-0.5 - np.abs(k)) / sigma / math.sqrt(2))
+        assert np.allclose(lik.flatten().double().numpy(), np.maximum(ref, 1e-9), atol=2e-7)
+
+
+def test_scale_lower_bound_and_rounding():
+    gc = codec.GaussianConditional(None).eval()
+    y = torch.tensor([[[[0.5, 1.5, 2.5, -0.5]]]])
+    yh, lik = gc(y, torch.full_like(y, 1e-3))
+    assert yh.flatten().tolist() == [0.0, 2.0, 2.0, -0.0]
+    _, lik_b = gc(y, torch.full_like(y, 0.11))
+    assert torch.equal(lik, lik_b)
+
+
+def test_factorized_prior_is_monotone_and_sums_to_one(golden_c):
+    eb = codec.EntropyBottleneck(5).eval()
+    eb.load_state_dict(golden_c["eb"]["state"])
+    v = torch.linspace(-40, 40, 801).view(1, 1, -1).repeat(5, 1, 1)
+    c = eb._logits_cumulative(v)
+    assert (c[:, :, 1:] >= c[:, :, :-1]).all()
+    med = eb._get_medians().detach()
+    ks = torch.arange(-200, 201, dtype=torch.float32).view(1, 1, -1) + med
+    lik = eb._likelihood(ks)
+    assert torch.allclose(lik.sum(-1), torch.ones(5, 1), atol=1e-3)
+
+
+def test_entropy_bottleneck_eval_rounds_around_median(golden_c):
+    g = golden_c["eb"]
+    eb = codec.EntropyBottleneck(5).eval()
+    eb.load_state_dict(g["state"])
+    zh, lik = eb(g["z"])
+    med = eb._get_medians().detach().view(1, 5, 1, 1)
+    assert torch.equal(zh, torch.round(g["z"] - med) + med)
+    assert torch.equal(zh, g["z_hat"]) and torch.allclose(lik, g["lik"], rtol=1e-6, atol=1e-9)
+    assert (lik >= 1e-9).all() and (lik <= 1).all()
+
+
+def test_gdn_igdn_round_trip_on_diagonal_gamma():
+    gdn, igdn = codec.GDN(4), codec.GDN(4, inverse=True)
+    x = torch.randn(2, 4, 5, 5)
+    y = gdn(x)                                   # y = x / sqrt(1 + 0.1 x^2)  =>  x = y / sqrt(1 - 0.1 y^2)
+    assert torch.allclose(y, x / torch.sqrt(1 + 0.1 * x * x), atol=1e-6)
+    assert torch.allclose(igdn(x), x * torch.sqrt(1 + 0.1 * x * x), atol=1e-5)
+    back = y / torch.sqrt(1 - 0.1 * y * y)
+    assert torch.allclose(back, x, atol=1e-4)
+
+
+def test_masked_conv_is_causal():
+    m = codec.MaskedConv2d(2, 3, kernel_size=5, padding=2, bias=False)
+    x = torch.zeros(1, 2, 9, 9)
+    x[0, :, 4, 4] = 1.0
+    y = m(x)
+    assert (m.mask.sum(dim=(2, 3)) == 12).all()
+    assert y[0, :, :4].abs().sum() == 0 and y[0, :, 4, :5].abs().sum() == 0     # nothing above / left / at centre
+    assert y[0, :, 5:7].abs().sum() > 0
+
+
+def test_pad_crop_round_trip_and_bpp():
+    x = torch.rand(1, 3, 70, 100)
+    xp = evalpath.pad(x, 64)
+    assert xp.shape == (1, 3, 128, 128)
+    assert torch.equal(evalpath.crop(xp, (70, 100)), x)
+    out = {"x_hat": xp, "likelihoods": {"y": torch.full((1, 2, 8, 8), 0.5)}}
+    assert abs(evalpath.compute_bpp(out) - 128 / (128 * 128)) < 1e-9
+
+
+def test_golden_models_are_reproducible(golden_c):
+    for arch in ("mbt2018-mean", "bmshj2018-hyperprior", "cheng2020-attn"):
+        g = golden_c[f"model/{arch}"]
+        m = codec.ARCHS[arch](**g["kw"]).eval()
+        m.load_state_dict(g["state"])
+        with torch.no_grad():
+            out = m(g["x"])
+        assert torch.allclose(out["x_hat"], g["x_hat"], rtol=1e-4, atol=1e-5)
+        assert abs(evalpath.compute_bpp(out) - g["bpp"]) < 1e-3
+
+
+def test_quant_model_rewrite_rules():
+    m = codec.Cheng2020Attention(N=12).eval()
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    q = quant_wrap.QuantModel(m, wq, aq)
+    assert isinstance(q.model.g_a[0], quant_wrap.QuantRBWS) and isinstance(q.model.g_s[2], quant_wrap.QuantRBU)
+    assert isinstance(q.model.h_a[1], quant_wrap.StraightThrough)            # LeakyReLU absorbed
+    assert isinstance(q.model.h_a[0].activation_function, torch.nn.LeakyReLU)
+    ps = q.model.g_s[9][1]
+    assert isinstance(ps, quant_wrap.QuantModule) and ps.is_ps                # Q4: wrapped PixelShuffle + LeakyReLU
+    assert isinstance(q.model.context_prediction, quant_wrap.QuantModule)     # Q5: mask dropped by the wrap
+    n_blocks = sum(isinstance(x, quant_wrap.BaseQuantBlock) for x in q.model.modules())
+    assert n_blocks == 13
+
+
+def test_oracle_calibration_reduces_reconstruction_error():
+    torch.manual_seed(0)
+    m = codec.MeanScaleHyperprior(N=8, M=12).eval()
+    synth.init_weights(m, gain=1.2)
+    wq = dict(n_bits=4, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    q = quant_wrap.QuantModel(m, wq, aq)
+    q.eval()
+    cali = synth.calibration_patches(4, 64)
+    q.set_quant_state(True, False)
+    with torch.no_grad():
+        q(cali[:2])
+    layer = q.model.g_a[2]
+    losses = calib.reconstruct(q, layer, 0, "2", cali, batch_size=2, iters=100, weight=0.0, warmup=0.2, input_prob=1.0)
+    assert layer.trained and not layer.weight_quantizer.soft_targets
+    assert sum(losses[-10:]) < sum(losses[:10])
