@@ -136,6 +136,9 @@ def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data
         m.weight_quantizer = AdaRoundQuantizer(m.weight_quantizer, m.org_weight.data)
         m.weight_quantizer.soft_targets = True
     params = [m.weight_quantizer.alpha for m in mods if m.org_weight is not None]
+    if trace is not None:
+        trace["h0_all"] = [m.weight_quantizer.get_soft_targets().detach().clone() for m in mods if m.org_weight is not None]
+        trace["h0"] = trace["h0_all"][0]
     opt = torch.optim.Adam(params)                      # lr 1e-3 (layer_opt.py:254)
     loss_fn = LossFunction(unit, weight, iters, b_range, warmup, p, task_p)
     losses = []

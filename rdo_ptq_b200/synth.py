@@ -56,6 +56,15 @@ def init_weights(model, seed=SEED, gain=1.0):
         if m.bias is not None:
             m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) * 0.05)
     for m in model.modules():
+        if type(m).__name__ == "GDN":
+            # compressai's init (beta=1, gamma=0.1*I) puts every gamma entry exactly on a quantisation grid point
+            # (0 or the row maximum), which makes AdaRound's gradient degenerate; a trained GDN has dense gamma.
+            c = m.beta.numel()
+            gam = 0.1 * torch.eye(c) + 0.04 * torch.rand(c, c, generator=g) / max(1.0, c / 16.0)
+            bet = 1.0 + 0.3 * torch.rand(c, generator=g)
+            m.gamma.copy_(m.gamma_reparam.init(gam))
+            m.beta.copy_(m.beta_reparam.init(bet))
+    for m in model.modules():
         if type(m).__name__ == "EntropyBottleneck":
             for i in range(5):
                 b = getattr(m, f"_bias{i:d}")
