@@ -164,13 +164,21 @@ typedef struct {
   int fixed_point;          /* forward: apply LU Q8.8 round(clamp(v,-128,128)*256)/256 to the output */
 } b200lic_conv_desc;
 
+/* Scratch bytes the tensor-core engine needs for `op` on this shape (operand staging: NHWC split-bf16 activations and
+ * packed weights); 0 when the shape only runs on the SIMT engine.  The caller owns the workspace; with a NULL or
+ * too-small workspace ENGINE_AUTO uses the SIMT engine and ENGINE_TC fails with B200LIC_ERR_UNSUPPORTED. */
+enum { B200LIC_OP_CONV_FWD = 0, B200LIC_OP_DECONV_FWD = 1, B200LIC_OP_CONV_DGRAD = 2, B200LIC_OP_DECONV_DGRAD = 3,
+       B200LIC_OP_CONV_WGRAD = 4, B200LIC_OP_DECONV_WGRAD = 5 };
+B200LIC_API size_t b200lic_conv_workspace_bytes(const b200lic_conv_desc* d, int op);
+
 /* y = act(conv2d(x, w) + bias).  gdn_x (may be NULL unless gdn_mode) is [N,Cout,Ho,Wo]; norm_out (may be NULL)
  * receives the pre-(r)sqrt accumulator in gdn_mode. */
 B200LIC_API int b200lic_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias,
-                     const float* gdn_x, float* norm_out, float* y, b200lic_stream_t stream);
+                     const float* gdn_x, float* norm_out, float* y, void* workspace, size_t workspace_bytes,
+                     b200lic_stream_t stream);
 /* y = act(conv_transpose2d(x, w) + bias); w is [Cin,Cout,KH,KW]; Ho/Wo carry the output_padding. */
 B200LIC_API int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                       b200lic_stream_t stream);
+                       void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
 /* dw[Cout,Cin,KH,KW] = sum_pixels dy (x) x.  dw is overwritten. */
 B200LIC_API int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
                        b200lic_stream_t stream);
@@ -179,10 +187,10 @@ B200LIC_API int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x,
                          b200lic_stream_t stream);
 /* dx[N,Cin,H,W] for y = conv2d(x, w). */
 B200LIC_API int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
-                       b200lic_stream_t stream);
+                       void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
 /* dx[N,Cin,H,W] for y = conv_transpose2d(x, w). */
 B200LIC_API int b200lic_deconv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
-                         b200lic_stream_t stream);
+                         void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  GDN / IGDN helpers (compressai GDN via TO quant_layer.py:142-154).

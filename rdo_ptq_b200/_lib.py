@@ -50,12 +50,12 @@ SIGNATURES = {
     "lp_loss_fwd_bwd": [_P, _P, _SZ, _F, _F, _F, _P, _P],
     "sq_err_sum": [_P, _P, _SZ, _P],
     "bits_sum": [_P, _SZ, _P],
-    "conv_fwd": [_D, _P, _P, _P, _P, _P, _P],
-    "deconv_fwd": [_D, _P, _P, _P, _P],
+    "conv_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _SZ],
+    "deconv_fwd": [_D, _P, _P, _P, _P, _P, _SZ],
     "conv_wgrad": [_D, _P, _P, _P],
     "deconv_wgrad": [_D, _P, _P, _P],
-    "conv_dgrad": [_D, _P, _P, _P],
-    "deconv_dgrad": [_D, _P, _P, _P],
+    "conv_dgrad": [_D, _P, _P, _P, _P, _SZ],
+    "deconv_dgrad": [_D, _P, _P, _P, _P, _SZ],
     "gdn_reparam_fwd": [_P, _SZ, _F, _F, _P],
     "gdn_reparam_bwd": [_P, _P, _SZ, _F, _P],
     "gdn_bwd_prep": [_P, _P, _P, _SZ, _I, _P, _P],
@@ -69,7 +69,8 @@ SIGNATURES = {
     "pixel_unshuffle": [_P, _I, _I, _I, _I, _I, _P],
 }
 PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
-         "launch_count": (C.c_ulonglong, [])}
+         "launch_count": (C.c_ulonglong, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int])}
+OP_CONV_FWD, OP_DECONV_FWD, OP_CONV_DGRAD, OP_DECONV_DGRAD, OP_CONV_WGRAD, OP_DECONV_WGRAD = range(6)
 
 _lib = None
 

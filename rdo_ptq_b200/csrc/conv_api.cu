@@ -10,42 +10,67 @@ int simt_conv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*
 int simt_deconv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, cudaStream_t);
 int simt_conv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, cudaStream_t);
 int simt_deconv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, cudaStream_t);
-// tensor-core engine (conv_tc.cu): returns B200LIC_ERR_UNSUPPORTED when the shape does not qualify
-int tc_conv_fwd(const b200lic_conv_desc*, const float*, const float*, const float*, const float*, float*, float*,
-                cudaStream_t);
+// tensor-core engine (conv_tc.cu): B200LIC_ERR_UNSUPPORTED when the shape / workspace does not qualify
+size_t tc_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
+                          int transposed);
+int tc_conv_fwd(const b200lic_conv_desc*, const float*, const float*, const float*, const float*, float*, float*, void*,
+                size_t, cudaStream_t);
+int tc_deconv_fwd(const b200lic_conv_desc*, const float*, const float*, const float*, float*, void*, size_t,
+                  cudaStream_t);
+int tc_conv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
+int tc_deconv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
 }  // namespace b200lic
 
 using namespace b200lic;
 
+// AUTO: tensor cores when eligible, else SIMT.  TC: tensor cores or an error.  SIMT: exact-fp32 engine.
+#define DISPATCH(tc_call, simt_call)                                     \
+  do {                                                                   \
+    if (d->engine != B200LIC_ENGINE_SIMT) {                              \
+      int _rc = (tc_call);                                               \
+      if (_rc != B200LIC_ERR_UNSUPPORTED || d->engine == B200LIC_ENGINE_TC) return _rc; \
+    }                                                                    \
+    return (simt_call);                                                  \
+  } while (0)
+
 extern "C" {
 
+size_t b200lic_conv_workspace_bytes(const b200lic_conv_desc* d, int op) {
+  if (!d) return 0;
+  switch (op) {
+    case B200LIC_OP_CONV_FWD:
+      return tc_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, 0);
+    case B200LIC_OP_DECONV_FWD:
+      return tc_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, 1);
+    case B200LIC_OP_CONV_DGRAD:
+      return tc_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, 1);
+    case B200LIC_OP_DECONV_DGRAD:
+      return tc_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, 0);
+    default:
+      return 0;
+  }
+}
+
 int b200lic_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, const float* gdn_x,
-                     float* norm_out, float* y, b200lic_stream_t stream) {
+                     float* norm_out, float* y, void* workspace, size_t workspace_bytes, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   int rc = conv_check_desc(d, "conv_fwd", false);
   if (rc != B200LIC_OK) return rc;
   B200_REQUIRE(x && w && y, "conv_fwd: null pointer");
   B200_REQUIRE(!d->gdn_mode || gdn_x, "conv_fwd: gdn_mode needs gdn_x");
-  if (d->engine != B200LIC_ENGINE_SIMT) {
-    rc = tc_conv_fwd(d, x, w, bias, gdn_x, norm_out, y, as_stream(stream));
-    if (rc != B200LIC_ERR_UNSUPPORTED) return rc;
-    if (d->engine == B200LIC_ENGINE_TC) return rc;
-  }
-  return simt_conv_fwd(d, x, w, bias, gdn_x, norm_out, y, as_stream(stream));
+  DISPATCH(tc_conv_fwd(d, x, w, bias, gdn_x, norm_out, y, workspace, workspace_bytes, as_stream(stream)),
+           simt_conv_fwd(d, x, w, bias, gdn_x, norm_out, y, as_stream(stream)));
 }
 
 int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                       b200lic_stream_t stream) {
+                       void* workspace, size_t workspace_bytes, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   int rc = conv_check_desc(d, "deconv_fwd", true);
   if (rc != B200LIC_OK) return rc;
   B200_REQUIRE(x && w && y, "deconv_fwd: null pointer");
   B200_REQUIRE(!d->gdn_mode && !d->in_square, "deconv_fwd: GDN flags are conv-only");
-  if (d->engine == B200LIC_ENGINE_TC) {
-    set_error("deconv_fwd: tensor-core engine not available for this op yet");
-    return B200LIC_ERR_UNSUPPORTED;
-  }
-  return simt_deconv_fwd(d, x, w, bias, y, as_stream(stream));
+  DISPATCH(tc_deconv_fwd(d, x, w, bias, y, workspace, workspace_bytes, as_stream(stream)),
+           simt_deconv_fwd(d, x, w, bias, y, as_stream(stream)));
 }
 
 int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, b200lic_stream_t stream) {
@@ -65,21 +90,24 @@ int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float
   return simt_deconv_wgrad(d, x, dy, dw, as_stream(stream));
 }
 
-int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx, b200lic_stream_t stream) {
+int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,
+                       size_t workspace_bytes, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   int rc = conv_check_desc(d, "conv_dgrad", false);
   if (rc != B200LIC_OK) return rc;
   B200_REQUIRE(dy && w && dx, "conv_dgrad: null pointer");
-  return simt_conv_dgrad(d, dy, w, dx, as_stream(stream));
+  DISPATCH(tc_conv_dgrad(d, dy, w, dx, workspace, workspace_bytes, as_stream(stream)),
+           simt_conv_dgrad(d, dy, w, dx, as_stream(stream)));
 }
 
-int b200lic_deconv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
-                         b200lic_stream_t stream) {
+int b200lic_deconv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,
+                         size_t workspace_bytes, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   int rc = conv_check_desc(d, "deconv_dgrad", true);
   if (rc != B200LIC_OK) return rc;
   B200_REQUIRE(dy && w && dx, "deconv_dgrad: null pointer");
-  return simt_deconv_dgrad(d, dy, w, dx, as_stream(stream));
+  DISPATCH(tc_deconv_dgrad(d, dy, w, dx, workspace, workspace_bytes, as_stream(stream)),
+           simt_deconv_dgrad(d, dy, w, dx, as_stream(stream)));
 }
 
 }  // extern "C"

@@ -265,16 +265,28 @@ def _act_id(module):
     raise NotImplementedError(f"rdo_ptq_b200: activation {module} is not on the hot path")
 
 
+def _workspace(d, op, device):
+    """Scratch for the tensor-core engine (caller-owned, C ABI contract); empty when the engine/shape is SIMT-only."""
+    if d.engine == ENGINE_SIMT:
+        return None, 0
+    n = int(_lib.lib().b200lic_conv_workspace_bytes(C.byref(d), op))
+    if n == 0:
+        return None, 0
+    return torch.empty(n, dtype=torch.uint8, device=device), n
+
+
 def conv2d_raw(x, w, bias, d, gdn_x=None, want_norm=False):
     y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
     norm = torch.empty_like(y) if want_norm else None
-    call("conv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(gdn_x), _p(norm), _p(y))
+    ws, nws = _workspace(d, _lib.OP_CONV_FWD, x.device)
+    call("conv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(gdn_x), _p(norm), _p(y), _p(ws), nws)
     return (y, norm) if want_norm else y
 
 
 def deconv2d_raw(x, w, bias, d):
     y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
-    call("deconv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(y))
+    ws, nws = _workspace(d, _lib.OP_DECONV_FWD, x.device)
+    call("deconv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(y), _p(ws), nws)
     return y
 
 
@@ -297,7 +309,8 @@ class _ConvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("conv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx))
+            ws, nws = _workspace(ctx.d, _lib.OP_CONV_DGRAD, dy.device)
+            call("conv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx), _p(ws), nws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             call("conv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw))
@@ -323,14 +336,15 @@ class _DeconvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("deconv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx))
+            ws, nws = _workspace(ctx.d, _lib.OP_DECONV_DGRAD, dy.device)
+            call("deconv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx), _p(ws), nws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             call("deconv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw))
         return dx, dw, None, None, None, None, None, None, None
 
 
-def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1, act=ACT_NONE, slope=0.01, fixed_pt=0):
+def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1, act=ACT_NONE, slope=0.01, fixed_pt=0):  # noqa
     """Drop-in for F.conv2d on the hot path (dilation 1, groups 1), optional fused activation."""
     if _sq(dilation, "dilation") != 1 or groups != 1:
         raise NotImplementedError("rdo_ptq_b200.conv2d: dilation/groups != 1 are not on the hot path")
@@ -406,7 +420,8 @@ class _GdnFn(torch.autograd.Function):
         if need_dx:
             d.in_square = 0
             t = torch.empty_like(x)
-            call("conv_dgrad", C.byref(d), _p(d_norm), _p(gamma_eff), _p(t))
+            ws, nws = _workspace(d, _lib.OP_CONV_DGRAD, x.device)
+            call("conv_dgrad", C.byref(d), _p(d_norm), _p(gamma_eff), _p(t), _p(ws), nws)
             dx = torch.empty_like(x)
             call("gdn_bwd_finish", _p(x), _p(t), _p(dx_direct), x.numel(), _p(dx))
         dbeta = None
