@@ -181,10 +181,10 @@ B200LIC_API int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, c
                        void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
 /* dw[Cout,Cin,KH,KW] = sum_pixels dy (x) x.  dw is overwritten. */
 B200LIC_API int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
-                       b200lic_stream_t stream);
+                       void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
 /* dw[Cin,Cout,KH,KW] for y = conv_transpose2d(x, w). */
 B200LIC_API int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
-                         b200lic_stream_t stream);
+                         void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
 /* dx[N,Cin,H,W] for y = conv2d(x, w). */
 B200LIC_API int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
                        void* workspace, size_t workspace_bytes, b200lic_stream_t stream);

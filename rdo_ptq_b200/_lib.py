@@ -52,8 +52,8 @@ SIGNATURES = {
     "bits_sum": [_P, _SZ, _P],
     "conv_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _SZ],
     "deconv_fwd": [_D, _P, _P, _P, _P, _P, _SZ],
-    "conv_wgrad": [_D, _P, _P, _P],
-    "deconv_wgrad": [_D, _P, _P, _P],
+    "conv_wgrad": [_D, _P, _P, _P, _P, _SZ],
+    "deconv_wgrad": [_D, _P, _P, _P, _P, _SZ],
     "conv_dgrad": [_D, _P, _P, _P, _P, _SZ],
     "deconv_dgrad": [_D, _P, _P, _P, _P, _SZ],
     "gdn_reparam_fwd": [_P, _SZ, _F, _F, _P],

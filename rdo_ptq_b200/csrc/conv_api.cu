@@ -19,6 +19,10 @@ int tc_deconv_fwd(const b200lic_conv_desc*, const float*, const float*, const fl
                   cudaStream_t);
 int tc_conv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
 int tc_deconv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
+int tc_conv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
+int tc_deconv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
+size_t tc_conv_wgrad_ws(const b200lic_conv_desc*);
+size_t tc_deconv_wgrad_ws(const b200lic_conv_desc*);
 }  // namespace b200lic
 
 using namespace b200lic;
@@ -46,6 +50,10 @@ size_t b200lic_conv_workspace_bytes(const b200lic_conv_desc* d, int op) {
       return tc_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, 1);
     case B200LIC_OP_DECONV_DGRAD:
       return tc_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, 0);
+    case B200LIC_OP_CONV_WGRAD:
+      return tc_conv_wgrad_ws(d);
+    case B200LIC_OP_DECONV_WGRAD:
+      return tc_deconv_wgrad_ws(d);
     default:
       return 0;
   }
@@ -73,21 +81,24 @@ int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* 
            simt_deconv_fwd(d, x, w, bias, y, as_stream(stream)));
 }
 
-int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, b200lic_stream_t stream) {
+int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,
+                       size_t workspace_bytes, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   int rc = conv_check_desc(d, "conv_wgrad", false);
   if (rc != B200LIC_OK) return rc;
   B200_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
-  return simt_conv_wgrad(d, x, dy, dw, as_stream(stream));
+  DISPATCH(tc_conv_wgrad(d, x, dy, dw, workspace, workspace_bytes, as_stream(stream)),
+           simt_conv_wgrad(d, x, dy, dw, as_stream(stream)));
 }
 
-int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
-                         b200lic_stream_t stream) {
+int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,
+                         size_t workspace_bytes, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   int rc = conv_check_desc(d, "deconv_wgrad", true);
   if (rc != B200LIC_OK) return rc;
   B200_REQUIRE(x && dy && dw, "deconv_wgrad: null pointer");
-  return simt_deconv_wgrad(d, x, dy, dw, as_stream(stream));
+  DISPATCH(tc_deconv_wgrad(d, x, dy, dw, workspace, workspace_bytes, as_stream(stream)),
+           simt_deconv_wgrad(d, x, dy, dw, as_stream(stream)));
 }
 
 int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,

@@ -516,6 +516,19 @@ static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int
   return B200LIC_OK;
 }
 
+// shared with conv_tc_wgrad.cu
+int tc_stage_nhwc(const float* x, int N, int C, int HW, int Cpad, int square, void* xh, void* xl, cudaStream_t s) {
+  dim3 grid((HW + 31) / 32, Cpad / 32, N);
+  nhwc_split_kernel<<<grid, 256, 0, s>>>(x, C, HW, Cpad, square, reinterpret_cast<__nv_bfloat16*>(xh),
+                                         reinterpret_cast<__nv_bfloat16*>(xl));
+  B200_LAUNCH_CHECK("nhwc_split_kernel");
+  return B200LIC_OK;
+}
+bool tc_encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box, const cuuint32_t* estr) {
+  return encode_map(m, base, rank, dims, strides_bytes, box, estr);
+}
+
 size_t tc_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
                           int transposed) {
   TcPlan p = make_plan(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed);

@@ -1,0 +1,382 @@
+// tcgen05 tensor-core wgrad for conv / transposed conv (B200LIC_ENGINE_TC).
+//
+//   dW[cs, cb, r, s] = sum_{n,h,w} small[n, cs, h, w] * big[n, cb, h*st - pad + r, w*st - pad + s]
+//   (conv: small = dY, big = x;  transposed conv: small = x, big = dY -- same roles as conv_simt.cu's wgrad)
+//
+// GEMM view per filter tap t:  D_t[cb, cs] = sum_pixels  Big_t[pixel, cb] * Small[pixel, cs]
+// The contraction runs over PIXELS, which are the rows of the NHWC tiles TMA delivers, so both operands are fed to
+// tcgen05.mma as MN-major (channel-contiguous) SWIZZLE_128B tiles: a [64 pixel x 64 channel] bf16 box is exactly one
+// 64-wide MN block with K = 64.  Two (tap, channel-block) boxes stacked 8 KB apart form one M = 128 operand; the small
+// tensor's channel blocks stacked 8 KB apart form N = 64*nb.  A CTA owns NACC = 2 accumulators (4 (tap, cb) boxes) in
+// TMEM and streams the pixel tiles of its split through a 2-stage TMA ring; split-K partial sums are merged with fp32
+// atomics into the zero-initialised dW.  Split-bf16 operands, 3 passes (hi*hi + hi*lo + lo*hi), fp32 accumulation.
+// Replaces cuDNN wgrad under autograd of F.conv2d / F.conv_transpose2d (TO layer_opt.py:298-307).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace b200lic {
+
+int tc_stage_nhwc(const float* x, int N, int C, int HW, int Cpad, int square, void* xh, void* xl, cudaStream_t s);
+bool tc_encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box, const cuuint32_t* estr);
+
+namespace wg {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(addr)
+      : "memory");
+}
+
+// MN-major SWIZZLE_128B descriptor: 64-element (128 B) MN rows, 8 K-rows per 1024 B atom;
+// SBO = next 8-row K group, LBO = next 64-wide MN block.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+}  // namespace wg
+
+constexpr int kWgThreads = 192;
+constexpr int kBoxBytes = 64 * 128;   // 64 pixels x 64 bf16 channels
+constexpr int kNacc = 2;              // accumulators (TMEM) per CTA
+constexpr int kBoxesA = 2 * kNacc;    // (tap, channel-block) boxes per CTA
+
+struct WgGeom {
+  int N;
+  int Cs, Hs, Ws, CsPad;     // small tensor (indexed directly)
+  int Cb, Hb, Wb, CbPad;     // big tensor (gathered)
+  int KH, KW, stride, pad;
+  int BW, BH, BI;            // pixel box: BW*BH*BI == 64
+  int nb_max;                // 64-channel blocks of the small tensor per N tile (<= 4)
+  int tiles_per_split;       // pixel tiles per split
+  int tmem_cols;             // columns per accumulator (power of two >= 64*nb_max)
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                    const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl, WgGeom g,
+                    float* __restrict__ dw) {
+  using namespace wg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int T = g.KH * g.KW;
+  const int cblocks = g.CbPad >> 6;
+  const int TT = T * cblocks;                         // (tap, channel-block) boxes in total
+  const int unit = blockIdx.x;                        // 4 consecutive boxes
+  const int sblocks = g.CsPad >> 6;
+  const int nb0 = blockIdx.y * g.nb_max;              // first 64-block of the small tensor handled here
+  const int nb = min(g.nb_max, sblocks - nb0);
+  const int BN = nb * 64;
+  const int tiles_w = (g.Ws + g.BW - 1) / g.BW, tiles_h = (g.Hs + g.BH - 1) / g.BH, tiles_n = (g.N + g.BI - 1) / g.BI;
+  const int ktiles = tiles_w * tiles_h * tiles_n;
+  const int kt0 = blockIdx.z * g.tiles_per_split;
+  const int kt1 = min(ktiles, kt0 + g.tiles_per_split);
+  if (kt0 >= kt1 || nb <= 0) return;
+  const int nkt = kt1 - kt0;
+
+  constexpr int S = 2;
+  const uint32_t a_bytes = 2u * kBoxesA * kBoxBytes;            // hi + lo
+  const uint32_t b_bytes = 2u * (uint32_t)g.nb_max * kBoxBytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bars = smem_base + S * stage_bytes;
+  const uint32_t full_bar = bars, empty_bar = bars + 8u * S, tmem_full_bar = bars + 16u * S;
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar + 8u * s, 1);
+      mbar_init(empty_bar + 8u * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t total_cols = (uint32_t)(kNacc * g.tmem_cols);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(total_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer =================================================================================================
+    if (lane == 0) {
+      int bt[kBoxesA], bcb[kBoxesA], br[kBoxesA], bs[kBoxesA];
+#pragma unroll
+      for (int j = 0; j < kBoxesA; ++j) {
+        int idx = unit * kBoxesA + j;
+        if (idx >= TT) idx = TT - 1;                   // duplicate of the last box; masked in the epilogue
+        bt[j] = idx / cblocks;
+        bcb[j] = idx - bt[j] * cblocks;
+        br[j] = bt[j] / g.KW;
+        bs[j] = bt[j] - br[j] * g.KW;
+      }
+      const uint32_t tx_bytes = a_bytes + 2u * (uint32_t)nb * kBoxBytes;
+      for (int it = 0; it < nkt; ++it) {
+        const int s = it % S;
+        const uint32_t round = (uint32_t)(it / S);
+        mbar_wait(empty_bar + 8u * s, (round & 1u) ^ 1u);
+        const int kt = kt0 + it;
+        const int tw = kt % tiles_w, th = (kt / tiles_w) % tiles_h, tn = kt / (tiles_w * tiles_h);
+        const int w0 = tw * g.BW, h0 = th * g.BH, n0 = tn * g.BI;
+        const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t fb = full_bar + 8u * s;
+        mbar_expect_tx(fb, tx_bytes);
+#pragma unroll
+        for (int j = 0; j < kBoxesA; ++j) {
+          const int cw = w0 * g.stride - g.pad + bs[j], ch = h0 * g.stride - g.pad + br[j];
+          tma_load_4d(st_base + (uint32_t)j * kBoxBytes, &map_bh, fb, bcb[j] * 64, cw, ch, n0);
+          tma_load_4d(st_base + (uint32_t)(kBoxesA + j) * kBoxBytes, &map_bl, fb, bcb[j] * 64, cw, ch, n0);
+        }
+        for (int j = 0; j < nb; ++j) {
+          tma_load_4d(st_base + a_bytes + (uint32_t)j * kBoxBytes, &map_sh, fb, (nb0 + j) * 64, w0, h0, n0);
+          tma_load_4d(st_base + a_bytes + (uint32_t)(g.nb_max + j) * kBoxBytes, &map_sl, fb, (nb0 + j) * 64, w0, h0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ===================================================================================================
+    if (lane == 0) {
+      // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < nkt; ++it) {
+        const int s = it % S;
+        const uint32_t round = (uint32_t)(it / S);
+        mbar_wait(full_bar + 8u * s, round & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t b_hi = st_base + a_bytes, b_lo = b_hi + (uint32_t)g.nb_max * kBoxBytes;
+#pragma unroll
+        for (int acc = 0; acc < kNacc; ++acc) {
+          const uint32_t a_hi = st_base + (uint32_t)(2 * acc) * kBoxBytes;
+          const uint32_t a_lo = st_base + (uint32_t)(kBoxesA + 2 * acc) * kBoxBytes;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.tmem_cols);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                 // 4 x UMMA_K(16 pixels) = 64; 16 K-rows = 2048 B
+            const uint32_t ko = (uint32_t)k * 2048u;
+            const uint64_t ah = make_mnmajor_sw128_desc(a_hi + ko, kBoxBytes), al = make_mnmajor_sw128_desc(a_lo + ko, kBoxBytes);
+            const uint64_t bh = make_mnmajor_sw128_desc(b_hi + ko, kBoxBytes), bl = make_mnmajor_sw128_desc(b_lo + ko, kBoxBytes);
+            umma_bf16(d_tmem, ah, bh, idesc, (it | k) != 0);
+            umma_bf16(d_tmem, ah, bl, idesc, 1u);
+            umma_bf16(d_tmem, al, bh, idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar + 8u * s);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: TMEM -> atomicAdd into dW[cs][cb][tap] ================================================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                      // accumulator row = box (row / 64), channel (row % 64)
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int acc = 0; acc < kNacc; ++acc) {
+      const int idx = unit * kBoxesA + 2 * acc + (row >> 6);
+      const int t = idx / cblocks, cb = (idx - t * cblocks) * 64 + (row & 63);
+      const bool valid = idx < TT && cb < g.Cb;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.tmem_cols + c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int cs = nb0 * 64 + c0 + j;
+            if (cs < g.Cs) atomicAdd(dw + ((size_t)cs * g.Cb + cb) * T + t, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(total_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct WgPlan {
+  bool ok = false;
+  int CsPad, CbPad, BW, BH, BI, nb_max, n_tiles, units, ktiles, splits, tiles_per_split, tmem_cols;
+  size_t small_bytes, big_bytes, total_bytes, smem_bytes;
+};
+
+static int p2ceil(int v) {
+  int p = 1;
+  while (p < v) p *= 2;
+  return p;
+}
+
+static WgPlan make_wg_plan(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride) {
+  WgPlan p;
+  if (Cs < 16 || Cb < 16 || KH * KW > 64) return p;
+  p.CsPad = (Cs + 63) / 64 * 64;
+  p.CbPad = (Cb + 63) / 64 * 64;
+  p.BW = Ws >= 16 ? 16 : p2ceil(Ws);
+  p.BH = 64 / p.BW;
+  if (p.BH > p2ceil(Hs)) p.BH = p2ceil(Hs);
+  p.BI = 64 / (p.BW * p.BH);
+  if (p.BW * stride > 256 || p.BH * stride > 256 || p.BI > 256) return p;
+  const int sblocks = p.CsPad / 64;
+  p.nb_max = sblocks >= 3 ? 3 : sblocks;          // N <= 192 per MMA
+  if (sblocks == 4) p.nb_max = 2;
+  p.n_tiles = (sblocks + p.nb_max - 1) / p.nb_max;
+  p.tmem_cols = p.nb_max * 64 <= 64 ? 64 : (p.nb_max * 64 <= 128 ? 128 : 256);
+  const int TT = KH * KW * (p.CbPad / 64);
+  p.units = (TT + kBoxesA - 1) / kBoxesA;
+  p.ktiles = ((Ws + p.BW - 1) / p.BW) * ((Hs + p.BH - 1) / p.BH) * ((N + p.BI - 1) / p.BI);
+  const int ctas = p.units * p.n_tiles;
+  int want = (2 * num_sms() + ctas - 1) / ctas;
+  int max_splits = (p.ktiles + 3) / 4;            // >= 4 pixel tiles per split
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  p.tiles_per_split = (p.ktiles + want - 1) / want;
+  p.splits = (p.ktiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  const size_t stage = 2 * (size_t)kBoxesA * kBoxBytes + 2 * (size_t)p.nb_max * kBoxBytes;
+  p.smem_bytes = 2 * stage + 1024 + 256;
+  if (p.smem_bytes > 227 * 1024) return p;
+  p.small_bytes = ((size_t)N * Hs * Ws * p.CsPad * 2 + 1023) / 1024 * 1024;
+  p.big_bytes = ((size_t)N * Hb * Wb * p.CbPad * 2 + 1023) / 1024 * 1024;
+  p.total_bytes = 2 * p.small_bytes + 2 * p.big_bytes + 1024;
+  p.ok = true;
+  return p;
+}
+
+size_t tc_wgrad_workspace_bytes(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride) {
+  WgPlan p = make_wg_plan(N, Cs, Hs, Ws, Cb, Hb, Wb, KH, KW, stride);
+  return p.ok ? p.total_bytes : 0;
+}
+
+// small [N,Cs,Hs,Ws], big [N,Cb,Hb,Wb] (fp32 NCHW) -> dw [Cs][Cb][KH][KW] (overwritten)
+int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
+             const float* small, const float* big, float* dw, void* workspace, size_t workspace_bytes, cudaStream_t s,
+             const char* name) {
+  WgPlan p = make_wg_plan(N, Cs, Hs, Ws, Cb, Hb, Wb, KH, KW, stride);
+  if (!p.ok) {
+    set_error("%s: shape not eligible for the tcgen05 engine", name);
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  if (!workspace || workspace_bytes < p.total_bytes) {
+    set_error("%s: tcgen05 engine needs %zu workspace bytes (got %zu)", name, p.total_bytes, workspace_bytes);
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  void *sh = ws, *sl = ws + p.small_bytes, *bh = ws + 2 * p.small_bytes, *bl = ws + 2 * p.small_bytes + p.big_bytes;
+  int rc = tc_stage_nhwc(small, N, Cs, Hs * Ws, p.CsPad, 0, sh, sl, s);
+  if (rc != B200LIC_OK) return rc;
+  rc = tc_stage_nhwc(big, N, Cb, Hb * Wb, p.CbPad, big_square, bh, bl, s);
+  if (rc != B200LIC_OK) return rc;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cs * Cb * KH * KW, s);
+  if (e != cudaSuccess) {
+    set_error("%s: memset failed: %s", name, cudaGetErrorString(e));
+    return B200LIC_ERR_CUDA;
+  }
+  CUtensorMap mbh, mbl, msh, msl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.CbPad, (cuuint64_t)Wb, (cuuint64_t)Hb, (cuuint64_t)N};
+    cuuint64_t str[3] = {(cuuint64_t)p.CbPad * 2, (cuuint64_t)Wb * p.CbPad * 2, (cuuint64_t)Hb * Wb * p.CbPad * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), (cuuint32_t)p.BI};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    if (!tc_encode_map(&mbh, bh, 4, dims, str, box, es) || !tc_encode_map(&mbl, bl, 4, dims, str, box, es))
+      return B200LIC_ERR_CUDA;
+    cuuint64_t sdims[4] = {(cuuint64_t)p.CsPad, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
+    cuuint64_t sstr[3] = {(cuuint64_t)p.CsPad * 2, (cuuint64_t)Ws * p.CsPad * 2, (cuuint64_t)Hs * Ws * p.CsPad * 2};
+    cuuint32_t sbox[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    cuuint32_t ses[4] = {1, 1, 1, 1};
+    if (!tc_encode_map(&msh, sh, 4, sdims, sstr, sbox, ses) || !tc_encode_map(&msl, sl, 4, sdims, sstr, sbox, ses))
+      return B200LIC_ERR_CUDA;
+  }
+  WgGeom g{N, Cs, Hs, Ws, p.CsPad, Cb, Hb, Wb, p.CbPad, KH, KW, stride, pad, p.BW, p.BH, p.BI, p.nb_max,
+           p.tiles_per_split, p.tmem_cols};
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e2 = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e2 != cudaSuccess) {
+      set_error("%s: cannot raise dynamic shared memory: %s", name, cudaGetErrorString(e2));
+      return B200LIC_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(p.units, p.n_tiles, p.splits);
+  tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mbh, mbl, msh, msl, g, dw);
+  B200_LAUNCH_CHECK(name);
+  return B200LIC_OK;
+}
+
+int tc_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+  return tc_wgrad(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, d->pad, d->in_square, dy, x,
+                  dw, ws, ws_bytes, s, "conv_wgrad(tc)");
+}
+
+int tc_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                    cudaStream_t s) {
+  return tc_wgrad(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0, x, dy, dw, ws,
+                  ws_bytes, s, "deconv_wgrad(tc)");
+}
+
+size_t tc_conv_wgrad_ws(const b200lic_conv_desc* d) {
+  return tc_wgrad_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride);
+}
+size_t tc_deconv_wgrad_ws(const b200lic_conv_desc* d) {
+  return tc_wgrad_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride);
+}
+
+}  // namespace b200lic

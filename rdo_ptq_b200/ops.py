@@ -313,7 +313,8 @@ class _ConvFn(torch.autograd.Function):
             call("conv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx), _p(ws), nws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            call("conv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw))
+            ws, nws = _workspace(ctx.d, _lib.OP_CONV_WGRAD, dy.device)
+            call("conv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw), _p(ws), nws)
         return dx, dw, None, None, None, None, None, None
 
 
@@ -340,7 +341,8 @@ class _DeconvFn(torch.autograd.Function):
             call("deconv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx), _p(ws), nws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            call("deconv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw))
+            ws, nws = _workspace(ctx.d, _lib.OP_DECONV_WGRAD, dy.device)
+            call("deconv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw), _p(ws), nws)
         return dx, dw, None, None, None, None, None, None, None
 
 
@@ -416,7 +418,8 @@ class _GdnFn(torch.autograd.Function):
         dx = dgamma = None
         if ctx.needs_input_grad[1]:
             dgamma = torch.empty_like(gamma_eff)
-            call("conv_wgrad", C.byref(d), _p(x), _p(d_norm), _p(dgamma))     # in_square: sum d_norm * x^2
+            ws, nws = _workspace(d, _lib.OP_CONV_WGRAD, x.device)
+            call("conv_wgrad", C.byref(d), _p(x), _p(d_norm), _p(dgamma), _p(ws), nws)   # in_square: sum d_norm * x^2
         if need_dx:
             d.in_square = 0
             t = torch.empty_like(x)

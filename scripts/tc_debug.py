@@ -77,3 +77,47 @@ if __name__ == "__main__":
         conv_case(8, 192, 32, 32, 320, 5, 2, 2)
         conv_case(8, 192, 64, 64, 192, 1, 1, 0)
         deconv_case(8, 192, 64, 64, 192, 5, 2, 2, 1)
+
+
+def wgrad_case(N, Cin, H, W, Cout, k, st, pd, transposed=False, op=0, cpu_check=False):
+    import ctypes as C
+    from rdo_ptq_b200 import _lib
+    g = torch.Generator().manual_seed(N + Cin + H + Cout + k)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
+    ds = ops.conv_desc(x.shape, wshape, st, pd, transposed, op, engine=ENGINE_SIMT)
+    dt = ops.conv_desc(x.shape, wshape, st, pd, transposed, op, engine=ENGINE_TC)
+    dy = torch.randn(N, Cout, ds.Ho, ds.Wo, generator=g).to(dev)
+    name = "deconv_wgrad" if transposed else "conv_wgrad"
+    opid = _lib.OP_DECONV_WGRAD if transposed else _lib.OP_CONV_WGRAD
+
+    def run(d):
+        dw = torch.empty(wshape, device=dev)
+        ws, nws = ops._workspace(d, opid, dev)
+        ops.call(name, C.byref(d), ops._p(x), ops._p(dy), ops._p(dw), ops._p(ws), nws)
+        return dw
+    a, b = run(ds), run(dt)
+    torch.cuda.synchronize()
+    msg = f"{name} N{N} {Cin}->{Cout} {H}x{W} k{k} s{st}: tc-vs-simt rel {rel(b, a):.2e}"
+    if cpu_check:
+        xc = x.cpu().requires_grad_(False)
+        wc = torch.zeros(wshape, requires_grad=True)
+        y = (F.conv_transpose2d(xc, wc, None, st, pd, op) if transposed else F.conv2d(xc, wc, None, st, pd))
+        y.backward(dy.cpu())
+        msg += f" | tc-vs-cpu {rel(b.cpu(), wc.grad):.2e}"
+    macs = N * (H * W if transposed else ds.Ho * ds.Wo) * Cout * Cin * k * k
+    ts, tt = timeit(lambda: run(ds)), timeit(lambda: run(dt))
+    msg += f" | simt {ts:.3f} ms ({2*macs/ts/1e9:.1f} TF/s) tc {tt:.3f} ms ({2*macs/tt/1e9:.1f} TF/s)"
+    print(msg, flush=True)
+
+
+if __name__ == "__main__":
+    wgrad_case(1, 64, 16, 16, 64, 1, 1, 0, cpu_check=True)
+    wgrad_case(2, 64, 16, 16, 128, 3, 1, 1, cpu_check=True)
+    wgrad_case(2, 48, 20, 28, 80, 3, 2, 1, cpu_check=True)
+    wgrad_case(1, 192, 32, 48, 192, 5, 2, 2, cpu_check=True)
+    wgrad_case(2, 192, 8, 12, 320, 5, 2, 2, True, 1, cpu_check=True)
+    if (sys.argv[1] if len(sys.argv) > 1 else "all") == "all":
+        wgrad_case(8, 192, 128, 128, 192, 5, 2, 2)
+        wgrad_case(8, 192, 64, 64, 192, 5, 2, 2, True, 1)
+        wgrad_case(8, 192, 64, 64, 192, 1, 1, 0)
