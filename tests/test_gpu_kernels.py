@@ -202,49 +202,67 @@ def test_lp_loss_and_reductions(ops, dev, golden_q):
 CONV_CASES = [  # N, Cin, H, W, Cout, k, stride, pad
     (2, 3, 32, 48, 24, 5, 2, 2), (1, 24, 16, 24, 24, 5, 2, 2), (2, 16, 9, 11, 20, 3, 1, 1), (1, 20, 8, 12, 40, 3, 2, 1),
     (2, 12, 7, 5, 6, 1, 1, 0), (1, 8, 10, 14, 16, 1, 2, 0), (1, 192, 16, 24, 192, 5, 2, 2), (1, 130, 12, 12, 70, 3, 1, 1),
+    (3, 64, 5, 3, 320, 3, 1, 1), (5, 32, 4, 4, 640, 5, 2, 2), (1, 96, 33, 17, 48, 3, 2, 1), (2, 320, 8, 12, 192, 5, 2, 2),
 ]
 
 
+ENGINE_BARS = {"simt": 1e-5, "auto": 1e-4}     # exact-fp32 engine / tcgen05 split-bf16 engine (north_star bar 1e-4)
+
+
+@pytest.fixture(params=["simt", "auto"])
+def engine_bar(request, ops):
+    ops.set_default_engine(request.param)
+    yield ENGINE_BARS[request.param]
+    ops.set_default_engine("auto")
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_fwd_bwd(ops, dev, case):
+def test_conv_fwd_bwd(ops, dev, case, engine_bar):
     N, Cin, H, W, Cout, k, st, pd = case
     gen = torch.Generator().manual_seed(sum(case))
     x = torch.randn(N, Cin, H, W, generator=gen, requires_grad=True)
     w = (torch.randn(Cout, Cin, k, k, generator=gen) * 0.1).requires_grad_(True)
     b = torch.randn(Cout, generator=gen)
     for act, slope in ((ops.ACT_NONE, 0.0), (ops.ACT_LEAKY_RELU, 0.01), (ops.ACT_RELU, 0.0)):
-        ref = F.conv2d(x, w, b, stride=st, padding=pd)
-        ref = F.leaky_relu(ref, slope) if act == ops.ACT_LEAKY_RELU else (F.relu(ref) if act == ops.ACT_RELU else ref)
+        pre = F.conv2d(x, w, b, stride=st, padding=pd)
+        ref = F.leaky_relu(pre, slope) if act == ops.ACT_LEAKY_RELU else (F.relu(pre) if act == ops.ACT_RELU else pre)
         xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().to(dev).requires_grad_(True)
         out = ops.conv2d(xd, wd, b.to(dev), st, pd, act=act, slope=slope)
-        assert rel_err(out, ref) < 1e-5, (case, act)
+        assert rel_err(out, ref) < engine_bar, (case, act)
         dy = torch.randn(ref.shape, generator=gen)
-        gx, gw = torch.autograd.grad(ref, (x, w), dy)
+        # the activation derivative is discontinuous at 0: use the GPU's own sign pattern so that an output within one
+        # ulp of 0 cannot turn into a 100x difference of one dy element
+        pos = out.detach().cpu() > 0
+        dy_eff = dy if act == ops.ACT_NONE else torch.where(pos, dy, dy * (slope if act == ops.ACT_LEAKY_RELU else 0.0))
+        gx, gw = torch.autograd.grad(pre, (x, w), dy_eff)
         out.backward(dy.to(dev))
-        assert rel_err(xd.grad, gx) < 1e-5 and rel_err(wd.grad, gw) < 1e-5, (case, act)
+        assert rel_err(xd.grad, gx) < engine_bar and rel_err(wd.grad, gw) < engine_bar, (case, act)
 
 
 DECONV_CASES = [  # N, Cin, H, W, Cout, k, stride, pad, out_pad
     (2, 24, 8, 12, 16, 5, 2, 2, 1), (1, 16, 16, 24, 3, 5, 2, 2, 1), (1, 12, 5, 7, 10, 3, 2, 1, 1), (2, 8, 6, 6, 8, 3, 1, 1, 0),
     (1, 192, 8, 12, 192, 5, 2, 2, 1), (1, 6, 4, 5, 4, 5, 2, 2, 0), (1, 4, 3, 3, 5, 4, 3, 1, 2),
+    (2, 320, 4, 6, 480, 5, 2, 2, 1), (3, 64, 3, 5, 32, 3, 2, 1, 1), (1, 48, 9, 7, 96, 5, 2, 2, 0),
 ]
 
 
 @pytest.mark.parametrize("case", DECONV_CASES)
-def test_deconv_fwd_bwd(ops, dev, case):
+def test_deconv_fwd_bwd(ops, dev, case, engine_bar):
     N, Cin, H, W, Cout, k, st, pd, op = case
     gen = torch.Generator().manual_seed(sum(case))
     x = torch.randn(N, Cin, H, W, generator=gen, requires_grad=True)
     w = (torch.randn(Cin, Cout, k, k, generator=gen) * 0.1).requires_grad_(True)
     b = torch.randn(Cout, generator=gen)
-    ref = F.leaky_relu(F.conv_transpose2d(x, w, b, stride=st, padding=pd, output_padding=op), 0.01)
+    pre = F.conv_transpose2d(x, w, b, stride=st, padding=pd, output_padding=op)
+    ref = F.leaky_relu(pre, 0.01)
     xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().to(dev).requires_grad_(True)
     out = ops.conv_transpose2d(xd, wd, b.to(dev), st, pd, op, act=ops.ACT_LEAKY_RELU, slope=0.01)
-    assert out.shape == ref.shape and rel_err(out, ref) < 1e-5, case
+    assert out.shape == ref.shape and rel_err(out, ref) < engine_bar, case
     dy = torch.randn(ref.shape, generator=gen)
-    gx, gw = torch.autograd.grad(ref, (x, w), dy)
+    dy_eff = torch.where(out.detach().cpu() > 0, dy, dy * 0.01)        # GPU's own sign pattern (see test_conv_fwd_bwd)
+    gx, gw = torch.autograd.grad(pre, (x, w), dy_eff)
     out.backward(dy.to(dev))
-    assert rel_err(xd.grad, gx) < 1e-5 and rel_err(wd.grad, gw) < 1e-5, case
+    assert rel_err(xd.grad, gx) < engine_bar and rel_err(wd.grad, gw) < engine_bar, case
 
 
 def test_conv_rejects_bad_arguments(ops, dev):
@@ -271,7 +289,12 @@ def test_conv_linearity_property_full_size(ops, dev):
     y1, y2 = ops.conv2d(x1, w, None, 2, 2), ops.conv2d(x2, w, None, 2, 2)
     y12 = ops.conv2d(x1 * 0.5 + x2, w, None, 2, 2)
     assert y1.shape == (1, 192, 128, 192)
-    assert rel_err(y12, y1 * 0.5 + y2) < 1e-5
+    assert rel_err(y12, y1 * 0.5 + y2) < 1e-4
+    # and the two engines agree at full size
+    ops.set_default_engine("simt")
+    ys = ops.conv2d(x1, w, None, 2, 2)
+    ops.set_default_engine("auto")
+    assert rel_err(y1, ys) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------- GDN
@@ -296,6 +319,21 @@ def test_gdn_fwd_bwd(ops, dev, golden_c):
         assert rel_err(xd.grad, x.grad) < 1e-4
         assert rel_err(mod.gamma.grad, ref_mod.gamma.grad) < 1e-4
         assert rel_err(mod.beta.grad, ref_mod.beta.grad) < 1e-4
+    # production width (C=192 runs on the tcgen05 engine: x^2 staged as split-bf16, second contraction + rsqrt fused)
+    gen = torch.Generator().manual_seed(12)
+    ref_mod, mod = ocodec.GDN(192), GDN(192)
+    with torch.no_grad():
+        ref_mod.gamma.add_(torch.rand(192, 192, generator=gen) * 0.01)
+    mod.load_state_dict(ref_mod.state_dict())
+    mod.to(dev)
+    x = torch.randn(2, 192, 24, 40, generator=gen) * 2
+    xr, xd = x.clone().requires_grad_(True), x.to(dev).requires_grad_(True)
+    ref, out = ref_mod(xr), mod(xd)
+    assert rel_err(out, ref) < 1e-4
+    dy = torch.randn(ref.shape, generator=gen)
+    ref.backward(dy)
+    out.backward(dy.to(dev))
+    assert rel_err(xd.grad, xr.grad) < 1e-4 and rel_err(mod.gamma.grad, ref_mod.gamma.grad) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------- elementwise helpers
