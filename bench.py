@@ -123,10 +123,10 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     def timed(session, steps, warmup, probe=None):
-        for _ in range(warmup):
+        for _ in range(max(warmup, session.graph_warmup + 1)):      # eager warm-up sweeps + the graph-capture sweep
             session.sweep()
         barrier()
-        l0 = _lib.launch_count()
+        l0 = session.launch_total()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -137,7 +137,7 @@ def run_cuda(args):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), _lib.launch_count() - l0
+        return t.item(), session.launch_total() - l0
 
     # ---- device-resident run (value) -------------------------------------------------------------------------------
     qnn = build()
@@ -179,7 +179,7 @@ def run_cuda(args):
     torch.cuda.empty_cache()
     qnn2 = build()
     sess2 = CalibrationSession(qnn2, cali, batch_size=PER_GPU_BATCH, host_caches=True, **CALIB)
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(3, args.warmup)):          # >= graph_warmup eager sweeps + the capture sweep
         sess2.sweep()
         sess2.losses()
     barrier()
@@ -235,7 +235,8 @@ def run_cuda(args):
                                        f"{n_units} units x batch {PER_GPU_BATCH}/GPU of {PATCH}x{PATCH} patches, W8 "
                                        "per-channel, QDrop 0.5", "per_gpu_batch": PER_GPU_BATCH, "units": n_units,
                            "l2_policy": "inputs larger than L2 (unit caches total > 126 MB; a different unit each call)",
-                           "engine": os.environ.get("B200LIC_ENGINE", "auto")},
+                           "engine": os.environ.get("B200LIC_ENGINE", "auto"),
+                           "launch": "one CUDA graph per unit per iteration (device-resident schedule)"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "fwd_mpx_s": fwd, "gflop_per_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e9}
         print(json.dumps(line))

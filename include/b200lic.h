@@ -225,6 +225,35 @@ B200LIC_API int b200lic_act_bwd(const float* y, const float* d_out, size_t n, in
 B200LIC_API int b200lic_gather_mix(const float* q, const float* fp, const long long* idx, size_t rows, size_t row_elems,
                        float prob, unsigned long long seed, const uint8_t* mask, float* out,
                        b200lic_stream_t stream);
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident calibration schedule: everything that changes from one AdaRound iteration to the
+ * next (layer_opt.py:287-309: iteration counter -> Adam bias corrections, LinearTempDecay(count) of
+ * utils.py:37-54, warm-up gate of layer_opt.py:156-158, the batch pick and the QDrop draw) lives in
+ * DEVICE memory, so one captured CUDA graph of the iteration can be replayed 20 000 times with no
+ * host-side scalar in any kernel argument.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int step;            /* 1-based index of the iteration being executed (0 = before the first tick) */
+  float lr_over_bc1;   /* lr / (1 - beta1^step) */
+  float inv_sqrt_bc2;  /* 1 / sqrt(1 - beta2^step) */
+  float reg_b;         /* LinearTempDecay(step), 0 while step < warmup*iters (regulariser off) */
+} b200lic_calib_sched;
+/* step += 1 and recompute the derived scalars (one thread).  `sched` must be zero-initialised before the
+ * first tick. */
+B200LIC_API int b200lic_calib_sched_tick(b200lic_calib_sched* sched, int iters, double warmup, double b_start, double b_end,
+                             float lr, float beta1, float beta2, b200lic_stream_t stream);
+/* b200lic_adaround_bwd_adam with step / lr / bias corrections / reg_b read from `sched`. */
+B200LIC_API int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, const float* delta, const float* zero_point,
+                                    const float* d_wq, float* exp_avg, float* exp_avg_sq, int outer, int ch,
+                                    int inner, int n_levels, const b200lic_calib_sched* sched, float beta1,
+                                    float beta2, float eps, float grad_scale, float reg_weight, float* reg_loss,
+                                    b200lic_stream_t stream);
+/* b200lic_gather_mix whose batch pick and QDrop seed follow the schedule: k = (sched->step - 1) * units + unit;
+ * idx = idx_table[k % table_rows][0..rows) (idx_table NULL = identity rows); seed = (seed_base + k) mod 2^48. */
+B200LIC_API int b200lic_gather_mix_sched(const float* q, const float* fp, const long long* idx_table, int table_rows,
+                             size_t rows, size_t row_elems, float prob, unsigned long long seed_base, int units,
+                             int unit, const b200lic_calib_sched* sched, float* out, b200lic_stream_t stream);
+
 /* out = a * sigmoid(b) + c   (AttentionBlock tail) */
 B200LIC_API int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out,
                       b200lic_stream_t stream);

@@ -20,6 +20,11 @@ class B200LicError(RuntimeError):
         self.code = code
 
 
+class CalibSched(C.Structure):
+    """Mirror of `b200lic_calib_sched` (lives in device memory; this mirror is for size/offset checks and read-back)."""
+    _fields_ = [("step", C.c_int), ("lr_over_bc1", C.c_float), ("inv_sqrt_bc2", C.c_float), ("reg_b", C.c_float)]
+
+
 class ConvDesc(C.Structure):
     """Mirror of `b200lic_conv_desc`."""
     _fields_ = [("N", C.c_int), ("Cin", C.c_int), ("H", C.c_int), ("W", C.c_int),
@@ -29,7 +34,8 @@ class ConvDesc(C.Structure):
                 ("in_square", C.c_int), ("gdn_mode", C.c_int), ("fixed_point", C.c_int)]
 
 
-_P, _I, _F, _LL, _SZ, _ULL = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_ulonglong
+_P, _I, _F, _LL, _SZ, _ULL, _DBL = (C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_ulonglong,
+                                     C.c_double)
 _D = C.POINTER(ConvDesc)
 
 # name -> argtypes (the trailing stream argument is appended automatically)
@@ -63,6 +69,9 @@ SIGNATURES = {
     "add_act": [_P, _P, _SZ, _I, _F, _P],
     "act_bwd": [_P, _P, _SZ, _I, _F, _P],
     "gather_mix": [_P, _P, _P, _SZ, _SZ, _F, _ULL, _P, _P],
+    "calib_sched_tick": [_P, _I, _DBL, _DBL, _DBL, _F, _F, _F],
+    "adaround_bwd_adam_sched": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F, _F, _F, _P],
+    "gather_mix_sched": [_P, _P, _P, _I, _SZ, _SZ, _F, _ULL, _I, _I, _P, _P],
     "attn_gate": [_P, _P, _P, _SZ, _P],
     "abs": [_P, _SZ, _P],
     "pixel_shuffle": [_P, _I, _I, _I, _I, _I, _I, _F, _P],

@@ -65,22 +65,81 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // 
   return x ^ (x >> 31);
 }
 // Batch pick + QDrop mix in one pass: out[b, :] = keep ? q[idx[b], :] : fp[idx[b], :]
+// keep(i) = mask[i] if a mask is given, else 16 bits of a counter-based hash (one splitmix64 word per 4 elements)
+// compared with prob * 65536.  With a device schedule the batch-pick row and the seed follow sched->step.
+struct GatherSched {
+  const long long* idx_table;   // [table_rows][rows] or nullptr (identity)
+  int table_rows, units, unit;
+  const b200lic_calib_sched* sched;   // nullptr: use idx / seed as given
+};
+
+__device__ __forceinline__ bool qdrop_keep(unsigned long long word, unsigned lane4, unsigned thresh) {
+  return (unsigned)((word >> (16u * lane4)) & 0xFFFFu) < thresh;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
     gather_mix_kernel(const float* __restrict__ q, const float* __restrict__ fp, const long long* __restrict__ idx,
-                      size_t row, size_t n, float prob, unsigned long long seed, const uint8_t* __restrict__ mask,
-                      float* __restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / row, e = i - b * row;
-    const size_t src = (idx ? (size_t)idx[b] : b) * row + e;
-    bool keep;
-    if (mask) keep = mask[i] != 0;
-    else if (prob >= 1.f) keep = true;
-    else {
-      const unsigned r = (unsigned)(mix64(seed ^ mix64((unsigned long long)i)) >> 40);  // 24 random bits
-      keep = ((float)r * (1.f / 16777216.f)) < prob;
-    }
-    out[i] = keep ? __ldg(q + src) : __ldg(fp + src);
+                      size_t rows, size_t row, float prob, unsigned long long seed, const uint8_t* __restrict__ mask,
+                      GatherSched gs, float* __restrict__ out) {
+  if (gs.sched != nullptr) {
+    const unsigned long long k =
+        (unsigned long long)(__ldg(&gs.sched->step) - 1) * (unsigned long long)gs.units + (unsigned long long)gs.unit;
+    idx = gs.idx_table ? gs.idx_table + (size_t)(k % (unsigned long long)gs.table_rows) * rows : nullptr;
+    seed = (seed + k) & 0xFFFFFFFFFFFFull;
   }
+  const unsigned thresh = prob >= 1.f ? 65536u : (unsigned)(fminf(fmaxf(prob, 0.f), 1.f) * 65536.f);
+  const bool all_q = (mask == nullptr && prob >= 1.f);
+  const size_t n = rows * row;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    for (size_t i4 = tid; i4 < (n >> 2); i4 += stride) {
+      const size_t i = i4 << 2;
+      const size_t b = i / row, e = i - b * row;
+      const size_t src = (idx ? (size_t)idx[b] : b) * row + e;
+      const float4 qv = __ldg(reinterpret_cast<const float4*>(q + src));
+      float4 o = qv;
+      if (!all_q) {
+        const float4 fv = __ldg(reinterpret_cast<const float4*>(fp + src));
+        bool k0, k1, k2, k3;
+        if (mask) {
+          const uchar4 mv = *reinterpret_cast<const uchar4*>(mask + i);
+          k0 = mv.x != 0; k1 = mv.y != 0; k2 = mv.z != 0; k3 = mv.w != 0;
+        } else {
+          const unsigned long long word = mix64(seed ^ mix64((unsigned long long)i4));
+          k0 = qdrop_keep(word, 0, thresh); k1 = qdrop_keep(word, 1, thresh);
+          k2 = qdrop_keep(word, 2, thresh); k3 = qdrop_keep(word, 3, thresh);
+        }
+        o.x = k0 ? qv.x : fv.x; o.y = k1 ? qv.y : fv.y; o.z = k2 ? qv.z : fv.z; o.w = k3 ? qv.w : fv.w;
+      }
+      reinterpret_cast<float4*>(out)[i4] = o;
+    }
+  } else {
+    for (size_t i = tid; i < n; i += stride) {
+      const size_t b = i / row, e = i - b * row;
+      const size_t src = (idx ? (size_t)idx[b] : b) * row + e;
+      bool keep;
+      if (mask) keep = mask[i] != 0;
+      else if (all_q) keep = true;
+      else keep = qdrop_keep(mix64(seed ^ mix64((unsigned long long)(i >> 2))), (unsigned)(i & 3), thresh);
+      out[i] = keep ? __ldg(q + src) : __ldg(fp + src);
+    }
+  }
+}
+
+static int launch_gather_mix(const char* name, const float* q, const float* fp, const long long* idx, size_t rows,
+                             size_t row_elems, float prob, unsigned long long seed, const uint8_t* mask,
+                             GatherSched gs, float* out, cudaStream_t s) {
+  const size_t n = rows * row_elems;
+  if (n == 0) return B200LIC_OK;
+  const bool vec = (row_elems & 3) == 0 &&
+                   (((uintptr_t)q | (uintptr_t)fp | (uintptr_t)out | (uintptr_t)mask) & 15) == 0;
+  if (vec)
+    gather_mix_kernel<true><<<grid_for(n / 4, 256, 8), 256, 0, s>>>(q, fp, idx, rows, row_elems, prob, seed, mask, gs, out);
+  else
+    gather_mix_kernel<false><<<grid_for(n, 256, 8), 256, 0, s>>>(q, fp, idx, rows, row_elems, prob, seed, mask, gs, out);
+  B200_LAUNCH_CHECK(name);
+  return B200LIC_OK;
 }
 struct AttnGate {
   __device__ float operator()(float a, float b, float c, size_t) const { return a * (1.f / (1.f + expf(-b))) + c; }
@@ -298,11 +357,19 @@ int b200lic_gather_mix(const float* q, const float* fp, const long long* idx, si
                        unsigned long long seed, const uint8_t* mask, float* out, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   B200_REQUIRE(q && fp && out, "gather_mix: null pointer");
-  const size_t n = rows * row_elems;
-  if (n == 0) return B200LIC_OK;
-  gather_mix_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(q, fp, idx, row_elems, n, prob, seed, mask, out);
-  B200_LAUNCH_CHECK("gather_mix_kernel");
-  return B200LIC_OK;
+  return launch_gather_mix("gather_mix_kernel", q, fp, idx, rows, row_elems, prob, seed, mask,
+                           GatherSched{nullptr, 0, 0, 0, nullptr}, out, as_stream(stream));
+}
+
+int b200lic_gather_mix_sched(const float* q, const float* fp, const long long* idx_table, int table_rows, size_t rows,
+                             size_t row_elems, float prob, unsigned long long seed_base, int units, int unit,
+                             const b200lic_calib_sched* sched, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(q && fp && out && sched, "gather_mix_sched: null pointer");
+  B200_REQUIRE(units >= 1 && unit >= 0 && unit < units, "gather_mix_sched: unit %d outside [0,%d)", unit, units);
+  B200_REQUIRE(!idx_table || table_rows >= 1, "gather_mix_sched: empty index table");
+  return launch_gather_mix("gather_mix_kernel(sched)", q, fp, nullptr, rows, row_elems, prob, seed_base, nullptr,
+                           GatherSched{idx_table, table_rows, units, unit, sched}, out, as_stream(stream));
 }
 
 int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out, b200lic_stream_t stream) {

@@ -132,9 +132,14 @@ __global__ void __launch_bounds__(256)
                              const float* __restrict__ zp, const float* __restrict__ d_wq, float* __restrict__ m,
                              float* __restrict__ v, size_t n, int ch, int inner, float top, AdamArgs ad,
                              float grad_scale, float reg_weight, float reg_b, float* __restrict__ reg_loss,
-                             float* __restrict__ d_alpha_out) {
+                             float* __restrict__ d_alpha_out, const b200lic_calib_sched* __restrict__ sched) {
   __shared__ float red[32];
   float reg_acc = 0.f;
+  if (sched != nullptr) {  // iteration-dependent scalars come from device memory (CUDA-graph replay)
+    ad.lr_over_bc1 = __ldg(&sched->lr_over_bc1);
+    ad.inv_sqrt_bc2 = __ldg(&sched->inv_sqrt_bc2);
+    reg_b = __ldg(&sched->reg_b);
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)((i / inner) % ch);
     const float d = __ldg(delta + c), z = __ldg(zp + c);
@@ -167,6 +172,27 @@ __global__ void __launch_bounds__(256)
     const float tot = block_sum(reg_acc, red);
     if (threadIdx.x == 0) atomicAdd(reg_loss, reg_weight * tot);
   }
+}
+
+// One thread advances the device-resident schedule (same arithmetic as the host path: fp64 bias corrections cast to
+// fp32; LinearTempDecay of utils.py:37-54 evaluated in fp64 like Python does).
+__global__ void calib_sched_tick_kernel(b200lic_calib_sched* s, int iters, double warmup, double b_start, double b_end,
+                                        float lr, float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int step = s->step + 1;
+  s->step = step;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  s->lr_over_bc1 = (float)((double)lr / bc1);
+  s->inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const double start_decay = warmup * (double)iters;
+  double b;
+  if ((double)step < start_decay) {
+    b = 0.0;                                   // layer_opt.py:156-158: no rounding loss during warm-up
+  } else {
+    const double rel = ((double)step - start_decay) / ((double)iters - start_decay);
+    b = b_end + (b_start - b_end) * fmax(0.0, 1.0 - rel);
+  }
+  s->reg_b = (float)b;
 }
 
 }  // namespace b200lic
@@ -246,8 +272,35 @@ int b200lic_adaround_bwd_adam(const float* w, float* alpha, const float* delta, 
   AdamArgs ad{(float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps};
   adaround_bwd_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
       w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
-      reg_weight, reg_b, reg_loss, d_alpha_out);
+      reg_weight, reg_b, reg_loss, d_alpha_out, nullptr);
   B200_LAUNCH_CHECK("adaround_bwd_adam_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_calib_sched_tick(b200lic_calib_sched* sched, int iters, double warmup, double b_start, double b_end, float lr,
+                             float beta1, float beta2, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(sched, "calib_sched_tick: null pointer");
+  B200_REQUIRE(iters >= 1 && warmup >= 0.0 && warmup < 1.0, "calib_sched_tick: bad schedule (iters=%d, warmup=%f)", iters,
+               warmup);
+  calib_sched_tick_kernel<<<1, 32, 0, as_stream(stream)>>>(sched, iters, warmup, b_start, b_end, lr, beta1, beta2);
+  B200_LAUNCH_CHECK("calib_sched_tick_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, const float* delta, const float* zero_point,
+                                    const float* d_wq, float* exp_avg, float* exp_avg_sq, int outer, int ch, int inner,
+                                    int n_levels, const b200lic_calib_sched* sched, float beta1, float beta2, float eps,
+                                    float grad_scale, float reg_weight, float* reg_loss, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && alpha && delta && zero_point && d_wq && exp_avg && exp_avg_sq && sched,
+               "adaround_bwd_adam_sched: null pointer");
+  const size_t n = (size_t)outer * ch * inner;
+  AdamArgs ad{0.f, 0.f, beta1, beta2, eps};
+  adaround_bwd_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
+      reg_weight, 0.f, reg_loss, nullptr, sched);
+  B200_LAUNCH_CHECK("adaround_bwd_adam_kernel(sched)");
   return B200LIC_OK;
 }
 

@@ -30,7 +30,7 @@ def _c(t, name="tensor"):
         return None
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"rdo_ptq_b200: `{name}` must be a CUDA tensor -- the hot path has no CPU fallback")
-    if t.dtype not in (torch.float32, torch.uint8, torch.int32):
+    if t.dtype not in (torch.float32, torch.uint8, torch.int32, torch.int64):
         raise TypeError(f"rdo_ptq_b200: `{name}` must be float32 (got {t.dtype})")
     return t if t.is_contiguous() else t.contiguous()
 
@@ -490,6 +490,47 @@ def gather_mix(q, fp, idx=None, prob=1.0, seed=0, mask=None, out=None):
         out = torch.empty((rows,) + tuple(q.shape[1:]), device=q.device, dtype=torch.float32)
     call("gather_mix", _p(q), _p(fp), _p(idx), rows, row, float(prob), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(mask),
          _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ device schedule
+def new_sched(device):
+    """Zero-initialised `b200lic_calib_sched` in device memory (4 x 32-bit words)."""
+    return torch.zeros(4, dtype=torch.int32, device=device)
+
+
+def sched_tick(sched, iters, warmup, b_start, b_end, lr=1e-3, beta1=0.9, beta2=0.999):
+    call("calib_sched_tick", _p(sched), int(iters), float(warmup), float(b_start), float(b_end), lr, beta1, beta2)
+
+
+def read_sched(sched):
+    """Host copy of the schedule (synchronises): dict(step, lr_over_bc1, inv_sqrt_bc2, reg_b)."""
+    raw = sched.cpu()
+    f = raw.view(torch.float32)
+    return dict(step=int(raw[0]), lr_over_bc1=float(f[1]), inv_sqrt_bc2=float(f[2]), reg_b=float(f[3]))
+
+
+def adaround_bwd_adam_sched(w, alpha, delta, zp, d_wq, exp_avg, exp_avg_sq, axis, n_levels, sched, beta1=0.9,
+                            beta2=0.999, eps=1e-8, grad_scale=1.0, reg_weight=0.0, reg_loss=None):
+    outer, ch, inner = channel_view(w.shape, axis)
+    call("adaround_bwd_adam_sched", _p(_c(w)), _p(_c(alpha)), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))),
+         _p(_c(d_wq)), _p(exp_avg), _p(exp_avg_sq), outer, ch, inner, n_levels, _p(sched), beta1, beta2, eps,
+         grad_scale, reg_weight, _p(reg_loss))
+
+
+def gather_mix_sched(q, fp, idx_table, rows, prob, seed_base, units, unit, sched, out=None):
+    """gather_mix whose batch pick (row `k % table_rows` of the int64 `idx_table`, None = identity) and QDrop seed
+    follow the device schedule: k = (step - 1) * units + unit."""
+    q, fp = _c(q), _c(fp)
+    row = q[0].numel()
+    if idx_table is not None:
+        if idx_table.dtype != torch.int64 or not idx_table.is_cuda or idx_table.dim() != 2 or idx_table.size(1) != rows:
+            raise TypeError("gather_mix_sched: idx_table must be a CUDA int64 [table_rows, rows] tensor")
+        idx_table = idx_table.contiguous()
+    if out is None:
+        out = torch.empty((rows,) + tuple(q.shape[1:]), device=q.device, dtype=torch.float32)
+    call("gather_mix_sched", _p(q), _p(fp), _p(idx_table), 0 if idx_table is None else idx_table.size(0), rows, row,
+         float(prob), int(seed_base) & 0xFFFFFFFFFFFFFFFF, int(units), int(unit), _p(sched), _p(out))
     return out
 
 

@@ -29,7 +29,8 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, block_name: s
                          batch_size: int = 32, iters: int = 20000, weight: float = 0.01, opt_mode: str = 'mse',
                          asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
                          warmup: float = 0.0, input_prob: float = 1.0, act_quant: bool = False, lr: float = 4e-5,
-                         p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None):
+                         p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None,
+                         log_every: int = 500, graph: bool = True, process_group=None):
     if opt_mode != 'mse':
         raise NotImplementedError("only opt_mode='mse' is reachable in the reference (main2.py:225)")
     t0 = time.time()
@@ -46,8 +47,9 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, block_name: s
     org_act_func = None
     if not include_act_func:
         org_act_func, block.activation_function = block.activation_function, StraightThrough()
-    trainer = UnitTrainer(block, iters, weight, b_range, warmup, p, _task_p(args))
-    losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace)
+    trainer = UnitTrainer(block, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group)
+    losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace,
+                                log_every=log_every, graph=graph)
     if org_act_func is not None:
         block.activation_function = org_act_func
     return losses

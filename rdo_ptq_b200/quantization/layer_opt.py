@@ -38,7 +38,8 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
                          batch_size: int = 32, iters: int = 20000, weight: float = 0.001, opt_mode: str = 'mse',
                          asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
                          warmup: float = 0.0, input_prob: float = 1.0, act_quant: bool = False, lr: float = 4e-5,
-                         p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None):
+                         p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None,
+                         log_every: int = 500, graph: bool = True, process_group=None):
     """Same arguments as the reference; `plan` / `unit_id` / `trace` are additive (deterministic replays, tests).
     As in the reference, `lr` is accepted and ignored: Adam runs at its default 1e-3 (layer_opt.py:254)."""
     if opt_mode != 'mse':
@@ -63,8 +64,9 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
         org_act_func, layer.activation_function = layer.activation_function, StraightThrough()
     if layer.org_weight is None:                # PixelShuffle wrapper: nothing to learn (reference :245-246)
         return None
-    trainer = UnitTrainer(layer, iters, weight, b_range, warmup, p, _task_p(args))
-    losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace)
+    trainer = UnitTrainer(layer, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group)
+    losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace,
+                                log_every=log_every, graph=graph)
     if org_act_func is not None:
         layer.activation_function = org_act_func
     return losses

@@ -62,10 +62,14 @@ class UnitTrainer:
         self.last = {}
 
     # -- one iteration ---------------------------------------------------------------------------------------
-    def step(self, cur_inp: torch.Tensor, tgt: torch.Tensor, trace: Optional[dict] = None):
-        self.count += 1
-        b = self.temp_decay(self.count)
-        reg_b = 0.0 if self.count < self.loss_start else float(b)
+    def step(self, cur_inp: torch.Tensor, tgt: torch.Tensor, trace: Optional[dict] = None, sched=None):
+        """One fused iteration.  With `sched` (a device-resident b200lic_calib_sched, already ticked for this
+        iteration) no host scalar that changes between iterations enters a kernel argument, so the call sequence can be
+        captured once as a CUDA graph and replayed (session.py)."""
+        if sched is None:
+            self.count += 1
+            b = self.temp_decay(self.count)
+            reg_b = 0.0 if self.count < self.loss_start else float(b)
         leaves = []
         for m in self.mods:
             q = m.weight_quantizer
@@ -102,6 +106,12 @@ class UnitTrainer:
             grads = [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)]
         for i, m in enumerate(self.mods):
             q = m.weight_quantizer
+            if sched is not None:
+                ops.adaround_bwd_adam_sched(m.weight.data, q.alpha.data, q.delta, q.zero_point, grads[i],
+                                            self.exp_avg[i], self.exp_avg_sq[i], q.axis, q.n_levels, sched,
+                                            grad_scale=1.0 / self.world, reg_weight=self.weight,
+                                            reg_loss=self.loss_buf[2:3])
+                continue
             d_alpha = torch.empty_like(q.alpha.data) if trace is not None else None
             ops.adaround_bwd_adam(m.weight.data, q.alpha.data, q.delta, q.zero_point, grads[i], self.exp_avg[i],
                                   self.exp_avg_sq[i], q.axis, q.n_levels, self.count, lr=self.lr,
@@ -134,23 +144,71 @@ class UnitTrainer:
 
 
 def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_size: int, input_prob: float,
-                       unit_id: int = 0, plan: Optional[DrawPlan] = None, log_every: int = 500, trace=None):
-    """The hot loop: `iters` fused iterations over the cached (quant_in, fp_in) -> fp_out pairs."""
-    plan = plan or DrawPlan()
+                       unit_id: int = 0, plan: Optional[DrawPlan] = None, log_every: int = 500, trace=None,
+                       graph: bool = True, graph_warmup: int = 2):
+    """The hot loop: `iters` fused iterations over the cached (quant_in, fp_in) -> fp_out pairs.
+
+    Default (no explicit `plan`): batch picks are pre-drawn into a device table, the QDrop mask comes from the
+    counter-based hash inside gather_mix, the iteration-dependent scalars live in a device `b200lic_calib_sched`, and
+    after `graph_warmup` eager iterations ONE captured CUDA graph of the whole iteration is replayed -- the reference's
+    ~60 launches + 2 host syncs per iteration (layer_opt.py:287-309) become one graph launch.
+    With an explicit `plan` (tests replaying the oracle's draws) every iteration is issued eagerly."""
     q_in, fp_in = cached_inps[0], (cached_inps[1] if len(cached_inps) > 1 else cached_inps[0])
     n = q_in.size(0)
     losses, since = [], 0
+
+    def log(it):
+        nonlocal since
+        l = trainer.read_losses(since)
+        since = 0
+        losses.append(l)
+        cnt = it + 1
+        logging.info('Total loss:\t{:.3f} ( task:{:.3f}, rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
+            l["total"], l["task"], l["rec"], l["round"], trainer.temp_decay(cnt), cnt))
+
+    if plan is not None:
+        for it in range(trainer.iters):
+            idx, mask, seed = plan.draw(unit_id, it, n, batch_size, q_in.shape[1:], input_prob, q_in.device)
+            cur_inp = ops.gather_mix(q_in, fp_in, idx, prob=input_prob, seed=seed, mask=mask)
+            tgt = ops.gather_mix(cached_outs, cached_outs, idx, prob=1.0)
+            trainer.step(cur_inp, tgt, trace=trace if (trace is not None and it == 0) else None)
+            since += 1
+            if trainer.count % log_every == 0 or it == trainer.iters - 1:
+                log(it)
+        trainer.finish()
+        return losses
+
+    dev = q_in.device
+    seed = DrawPlan().seed
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed * 1000003 + unit_id * 100003)
+    rows = min(trainer.iters, 4096)
+    table = torch.stack([torch.randperm(n, generator=gen, device=dev)[:batch_size] for _ in range(rows)])
+    seed_base = (seed * 2654435761 + unit_id * 40503) & 0xFFFFFFFFFFFF
+    sched = ops.new_sched(dev)
+    tick = (trainer.iters, trainer.loss_start / trainer.iters if trainer.iters else 0.0, trainer.temp_decay.start_b,
+            trainer.temp_decay.end_b, trainer.lr)
+
+    def body():
+        cur_inp = ops.gather_mix_sched(q_in, fp_in, table, batch_size, input_prob, seed_base, 1, 0, sched)
+        tgt = ops.gather_mix_sched(cached_outs, cached_outs, table, batch_size, 1.0, seed_base, 1, 0, sched)
+        trainer.step(cur_inp, tgt, sched=sched)
+
+    g = None
     for it in range(trainer.iters):
-        idx, mask, seed = plan.draw(unit_id, it, n, batch_size, q_in.shape[1:], input_prob, q_in.device)
-        cur_inp = ops.gather_mix(q_in, fp_in, idx, prob=input_prob, seed=seed, mask=mask)
-        tgt = ops.gather_mix(cached_outs, cached_outs, idx, prob=1.0)
-        trainer.step(cur_inp, tgt, trace=trace if (trace is not None and it == 0) else None)
+        ops.sched_tick(sched, *tick)
+        if graph and it >= graph_warmup:
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                kw = {"capture_error_mode": "thread_local"} if trainer.world > 1 else {}
+                with torch.cuda.graph(g, **kw):
+                    body()
+            g.replay()
+        else:
+            body()
+        trainer.count += 1
         since += 1
         if trainer.count % log_every == 0 or it == trainer.iters - 1:
-            l = trainer.read_losses(since)
-            since = 0
-            losses.append(l)
-            logging.info('Total loss:\t{:.3f} ( task:{:.3f}, rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
-                l["total"], l["task"], l["rec"], l["round"], trainer.temp_decay(trainer.count), trainer.count))
+            log(it)
     trainer.finish()
     return losses

@@ -303,3 +303,98 @@ def test_quant_model_pickles(dev, tmp_path):
     x = cali[:1].to(dev)
     with torch.no_grad():
         assert torch.equal(back(x)["x_hat"], pqm(x)["x_hat"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device-resident schedule + CUDA-graph replay of the calibration iteration
+# ---------------------------------------------------------------------------------------------------------------------
+def test_device_schedule_matches_host_formulas(dev):
+    """b200lic_calib_sched_tick reproduces LinearTempDecay (utils.py:37-54), the warm-up gate (layer_opt.py:156-158) and
+    Adam's bias corrections for every step of a short schedule."""
+    from rdo_ptq_b200 import ops
+    from rdo_ptq_b200.quantization import LinearTempDecay
+    iters, warmup, b0, b1, lr = 50, 0.2, 20, 2, 1e-3
+    decay = LinearTempDecay(iters, rel_start_decay=warmup, start_b=b0, end_b=b1)
+    s = ops.new_sched(dev)
+    for step in range(1, iters + 1):
+        ops.sched_tick(s, iters, warmup, b0, b1, lr)
+        got = ops.read_sched(s)
+        assert got["step"] == step
+        want_b = 0.0 if step < iters * warmup else float(decay(step))
+        assert got["reg_b"] == pytest.approx(want_b, rel=1e-6, abs=1e-7)
+        assert got["lr_over_bc1"] == pytest.approx(lr / (1 - 0.9 ** step), rel=1e-6)
+        assert got["inv_sqrt_bc2"] == pytest.approx(1 / math.sqrt(1 - 0.999 ** step), rel=1e-6)
+
+
+def test_gather_mix_sched_follows_the_schedule(dev):
+    from rdo_ptq_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    q, fp = torch.randn(6, 5, 4, 4, generator=g).to(dev), torch.randn(6, 5, 4, 4, generator=g).to(dev)
+    table = torch.stack([torch.randperm(6, generator=g)[:3] for _ in range(7)]).to(dev)
+    s = ops.new_sched(dev)
+    units, seed_base = 4, 12345
+    for step in range(1, 12):
+        ops.sched_tick(s, 100, 0.2, 20, 2)
+        for unit in range(units):
+            k = (step - 1) * units + unit
+            got = ops.gather_mix_sched(q, fp, table, 3, 0.5, seed_base, units, unit, s)
+            want = ops.gather_mix(q, fp, table[k % 7].contiguous(), prob=0.5, seed=(seed_base + k) & 0xFFFFFFFFFFFF)
+            assert torch.equal(got, want)
+            ident = ops.gather_mix_sched(q[:3].contiguous(), fp[:3].contiguous(), None, 3, 1.0, seed_base, units, unit, s)
+            assert torch.equal(ident, q[:3])
+    # the QDrop draw keeps ~prob of the quantised input and every element comes from one of the two sources
+    big_q, big_f = torch.zeros(4, 8, 64, 64, device=dev), torch.ones(4, 8, 64, 64, device=dev)
+    mix = ops.gather_mix(big_q, big_f, None, prob=0.5, seed=7)
+    assert 0.48 < (mix == 0).float().mean().item() < 0.52
+    odd = ops.gather_mix(big_q[:, :, :, :63].contiguous(), big_f[:, :, :, :63].contiguous(), None, prob=0.25, seed=7)
+    assert 0.23 < (odd == 0).float().mean().item() < 0.27          # scalar (non-float4) path
+
+
+@pytest.mark.parametrize("host_caches", [False, True])
+def test_session_graph_replay_matches_eager(dev, host_caches):
+    """The captured-graph sweep must walk the same trajectory as the eagerly issued one (same device schedule, same
+    batch picks and QDrop draws); differences are limited to fp32 atomics ordering in split-K wgrad / loss sums."""
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+
+    def run(graph):
+        _, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+        sess = CalibrationSession(pqm, cali.to(dev), batch_size=2, iters=20, host_caches=host_caches, graph=graph)
+        for _ in range(8):
+            sess.sweep()
+        torch.cuda.synchronize()
+        losses = sess.losses()
+        alphas = {n: [m.weight_quantizer.alpha.data.clone() for m in t.mods] for n, t in sess.trainers.items()}
+        return sess, losses, alphas
+
+    se, le, ae = run(False)
+    sg, lg, ag = run(True)
+    assert ops_step(se) == ops_step(sg) == 8
+    assert len(sg._graphs) == len(sg.units) and sg.replayed_launches > 0
+    assert sg.launch_total() > 0
+    for n in ae:
+        for a, b in zip(ae[n], ag[n]):
+            assert (a - b).abs().max().item() < 2e-3, n         # 8 Adam steps of 1e-3; sign flips of ~0 gradients allowed
+            assert ((a - b).abs() > 1e-5).float().mean().item() < 0.02, n
+        assert lg[n]["rec"] == pytest.approx(le[n]["rec"], rel=1e-3, abs=1e-7), n
+        assert lg[n]["round"] == pytest.approx(le[n]["round"], rel=1e-3, abs=1e-7), n
+
+
+def ops_step(sess):
+    from rdo_ptq_b200 import ops
+    return ops.read_sched(sess.sched)["step"]
+
+
+def test_layer_reconstruction_default_path_uses_graph_and_converges(dev):
+    """Reference entry point with its default (device-drawn) randomness: graph-replayed loop, loss goes down, the unit is
+    hardened afterwards."""
+    _, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+    layer = pqm.model.g_a[2]
+
+    class Args:
+        task_loss = 2.0
+    losses = Q.layer_reconstruction(pqm, layer, "2", cali.to(dev), batch_size=2, iters=120, weight=0.01, b_range=(20, 2),
+                                    warmup=0.2, input_prob=0.5, asym=True, act_quant=False, opt_mode='mse', args=Args(),
+                                    log_every=40)
+    assert len(losses) == 3 and losses[-1]["rec"] < losses[0]["rec"]
+    assert losses[-1]["round"] > 0.0 and losses[0]["round"] == 0.0 or losses[1]["round"] > 0.0
+    assert layer.trained and not layer.weight_quantizer.soft_targets
