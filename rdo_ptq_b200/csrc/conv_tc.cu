@@ -15,6 +15,7 @@
 // Replaces cuDNN under F.conv2d / F.conv_transpose2d (TO quant_layer.py:28,36,123) and their dgrad.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200lic {
@@ -27,31 +28,55 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// x [N,C,HW] fp32 -> xh/xl [N,HW,Cpad] bf16 (pad channels zero).  32x32 smem transpose, coalesced both ways.
+// x [N,C,HW] fp32 -> xh/xl [N,HW,Cpad] bf16 (pad channels zero).  One CTA transposes a 64-channel x 64-pixel tile
+// through shared memory: reads are 256 B contiguous per warp (64 pixels of one channel), writes are one full 128 B
+// NHWC row (64 channels x bf16) per warp for each of the hi and lo slices.
 __global__ void __launch_bounds__(256) nhwc_split_kernel(const float* __restrict__ x, int C, int HW, int Cpad,
                                                           int square, __nv_bfloat16* __restrict__ xh,
                                                           __nv_bfloat16* __restrict__ xl) {
-  __shared__ float t[32][33];
-  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  __shared__ float t[64][65];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
   const float* xn = x + (size_t)n * C * HW;
+  const bool vec2 = (HW & 1) == 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 8 * j, p = p0 + tx;
-    float v = (c < C && p < HW) ? __ldg(xn + (size_t)c * HW + p) : 0.f;
-    if (square) v *= v;
-    t[ty + 8 * j][tx] = v;
+  for (int j = 0; j < 8; ++j) {
+    const int cl = warp + 8 * j, c = c0 + cl, p = p0 + 2 * lane;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < C) {
+      const float* src = xn + (size_t)c * HW + p;
+      if (vec2 && p + 1 < HW) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+        v0 = v.x;
+        v1 = v.y;
+      } else {
+        if (p < HW) v0 = __ldg(src);
+        if (p + 1 < HW) v1 = __ldg(src + 1);
+      }
+    }
+    if (square) {
+      v0 *= v0;
+      v1 *= v1;
+    }
+    t[cl][2 * lane] = v0;
+    t[cl][2 * lane + 1] = v1;
   }
   __syncthreads();
+  if (c0 + 2 * lane >= Cpad) return;               // Cpad is a multiple of 64, so this only trims nothing; kept for safety
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int p = p0 + ty + 8 * j, c = c0 + tx;
-    if (p < HW && c < Cpad) {
-      __nv_bfloat16 h, l;
-      split_bf16(t[tx][ty + 8 * j], h, l);
-      const size_t o = ((size_t)n * HW + p) * Cpad + c;
-      xh[o] = h;
-      xl[o] = l;
+  for (int j = 0; j < 8; ++j) {
+    const int pl = warp + 8 * j, p = p0 + pl;
+    if (p < HW) {
+      const float a = t[2 * lane][pl], b = t[2 * lane + 1][pl];
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(a, ah, al);
+      split_bf16(b, bh, bl);
+      const size_t o = ((size_t)n * HW + p) * Cpad + c0 + 2 * lane;
+      __nv_bfloat162 hv, lv;
+      hv.x = ah; hv.y = bh;
+      lv.x = al; lv.y = bl;
+      *reinterpret_cast<__nv_bfloat162*>(xh + o) = hv;
+      *reinterpret_cast<__nv_bfloat162*>(xl + o) = lv;
     }
   }
 }
@@ -117,6 +142,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// same, for warps that wait through a whole main loop: sleep between probes instead of hammering the barrier
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(256);
+  }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -305,12 +345,27 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const long long pix = (long long)ho * g.Wo + wo;
     const long long plane = (long long)g.Ho * g.Wo;
     if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
+      mbar_wait_backoff(tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     const int co_base = n_tile * g.BN;
+    const long long obase = ((long long)n * g.Cout + co_base) * plane + pix;   // element (n, co_base, ho, wo)
+    const bool gdn = g.gdn_mode != 0 && valid;
+    // GDN operand x for the 16 channels of a chunk: all 16 loads are issued together (and one chunk ahead of their use),
+    // so the epilogue keeps 16-32 requests per thread in flight instead of one dependent round trip per channel.
+    float xn[16];
+    auto load_x = [&](int c0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        xn[j] = (gdn && co_base + c0 + j < g.Cout) ? __ldg(gdn_x + obase + (long long)(c0 + j) * plane) : 0.f;
+    };
+    if (gdn) load_x(0);
     for (int c0 = 0; c0 < g.BN; c0 += 16) {
       uint32_t v[16];
+      float xc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xc[j] = xn[j];
+      if (gdn && c0 + 16 < g.BN) load_x(c0 + 16);
       if (num_kb > 0) {
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -323,12 +378,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int j = 0; j < 16; ++j) {
           const int co = co_base + c0 + j;
           if (co < g.Cout) {
-            const long long idx = ((long long)n * g.Cout + co) * plane + pix;
+            const long long idx = obase + (long long)(c0 + j) * plane;
             float r = __uint_as_float(v[j]) + (bias ? __ldg(bias + co) : 0.f);
             if (g.gdn_mode) {
               if (norm_out) norm_out[idx] = r;
-              const float xv = __ldg(gdn_x + idx);
-              r = g.gdn_mode == 1 ? xv * rsqrtf(r) : xv * sqrtf(r);
+              r = g.gdn_mode == 1 ? xc[j] * rsqrtf(r) : xc[j] * sqrtf(r);
             }
             r = apply_act(r, g.act, g.slope);
             if (g.fixed_point) r = rintf(fminf(fmaxf(r, -128.f), 128.f) * 256.f) * (1.f / 256.f);
@@ -386,7 +440,7 @@ struct TcPlan {
 static TcPlan make_plan(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
                         int transposed) {
   TcPlan p;
-  if (Cin < 16 || Cout < 16) return p;                       // the 3-channel ends of the codec stay on the SIMT engine
+  if (Cin < 1 || Cout < 1) return p;
   const int st = transposed ? stride : 1;
   p.phases = st * st;
   p.Tmax = transposed ? ((KH + st - 1) / st) * ((KW + st - 1) / st) : KH * KW;
@@ -446,6 +500,22 @@ static bool encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* d
   return true;
 }
 
+// second-generation engine (conv_tc2.cu); B200LIC_TC_V1=1 in the environment keeps the first one for A/B runs
+size_t tc2_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
+                           int transposed);
+int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
+               int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
+               int fixed_point, const float* x, const float* w, const float* bias, const float* gdn_x, float* norm_out,
+               float* y, void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name);
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200LIC_TC_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // Generic launcher.  (N,Cin,H,W) gathered tensor, (Cout,Ho,Wo) written tensor, weight strides of the written /
 // gathered channel axes.
 static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
@@ -453,6 +523,9 @@ static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int
                      int fixed_point, const float* x, const float* w, const float* bias, const float* gdn_x,
                      float* norm_out, float* y, void* workspace, size_t workspace_bytes, cudaStream_t s,
                      const char* name) {
+  if (!use_v1())
+    return tc2_launch(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, pad, transposed, s_co, s_ci, act, slope, in_square,
+                      gdn_mode, fixed_point, x, w, bias, gdn_x, norm_out, y, workspace, workspace_bytes, s, name);
   TcPlan p = make_plan(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed);
   if (!p.ok) {
     set_error("%s: shape not eligible for the tcgen05 engine", name);
@@ -471,7 +544,7 @@ static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int
   // 1. stage operands
   {
     const int HW = H * W;
-    dim3 grid((HW + 31) / 32, p.Cpad / 32, N);
+    dim3 grid((HW + 63) / 64, (p.Cpad + 63) / 64, N);
     nhwc_split_kernel<<<grid, 256, 0, s>>>(x, Cin, HW, p.Cpad, in_square, xh, xl);
     B200_LAUNCH_CHECK("nhwc_split_kernel");
     PackGeom pg{Cout, Cin, KH, KW, stride, pad, transposed, p.CoutPad, p.Cpad, p.Tmax, s_co, s_ci};
@@ -518,7 +591,7 @@ static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int
 
 // shared with conv_tc_wgrad.cu
 int tc_stage_nhwc(const float* x, int N, int C, int HW, int Cpad, int square, void* xh, void* xl, cudaStream_t s) {
-  dim3 grid((HW + 31) / 32, Cpad / 32, N);
+  dim3 grid((HW + 63) / 64, (Cpad + 63) / 64, N);
   nhwc_split_kernel<<<grid, 256, 0, s>>>(x, C, HW, Cpad, square, reinterpret_cast<__nv_bfloat16*>(xh),
                                          reinterpret_cast<__nv_bfloat16*>(xl));
   B200_LAUNCH_CHECK("nhwc_split_kernel");
@@ -529,8 +602,36 @@ bool tc_encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims,
   return encode_map(m, base, rank, dims, strides_bytes, box, estr);
 }
 
+int tc_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, int stride, int pad, int transposed, int CoutPad,
+                    int Cpad, int Tmax, int phases, long long s_co, long long s_ci, void* bh, void* bl, cudaStream_t s) {
+  PackGeom pg{Cout, Cin, KH, KW, stride, pad, transposed, CoutPad, Cpad, Tmax, s_co, s_ci};
+  const size_t per_phase = (size_t)CoutPad * Tmax * Cpad;
+  dim3 pgrid((unsigned)((per_phase + 255) / 256 > 1184 ? 1184 : (per_phase + 255) / 256), 1, phases);
+  pack_weights_kernel<<<pgrid, 256, 0, s>>>(pg, w, reinterpret_cast<__nv_bfloat16*>(bh),
+                                            reinterpret_cast<__nv_bfloat16*>(bl));
+  B200_LAUNCH_CHECK("pack_weights_kernel");
+  return B200LIC_OK;
+}
+bool tc_encode_map_ex(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle sw, void* base, int rank,
+                      const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                      const cuuint32_t* estr) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return false;
+  }
+  CUresult r = fn(m, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, box %u x %u)", (int)r, rank, box[0], box[1]);
+    return false;
+  }
+  return true;
+}
+
 size_t tc_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
                           int transposed) {
+  if (!use_v1()) return tc2_workspace_bytes(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed);
   TcPlan p = make_plan(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed);
   return p.ok ? p.total_bytes : 0;
 }

@@ -266,7 +266,7 @@ static int p2ceil(int v) {
 
 static WgPlan make_wg_plan(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride) {
   WgPlan p;
-  if (Cs < 16 || Cb < 16 || KH * KW > 64) return p;
+  if (Cs < 1 || Cb < 1 || KH * KW > 64) return p;
   p.CsPad = (Cs + 63) / 64 * 64;
   p.CbPad = (Cb + 63) / 64 * 64;
   p.BW = Ws >= 16 ? 16 : p2ceil(Ws);

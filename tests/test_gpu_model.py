@@ -322,8 +322,9 @@ def test_device_schedule_matches_host_formulas(dev):
         assert got["step"] == step
         want_b = 0.0 if step < iters * warmup else float(decay(step))
         assert got["reg_b"] == pytest.approx(want_b, rel=1e-6, abs=1e-7)
-        assert got["lr_over_bc1"] == pytest.approx(lr / (1 - 0.9 ** step), rel=1e-6)
-        assert got["inv_sqrt_bc2"] == pytest.approx(1 / math.sqrt(1 - 0.999 ** step), rel=1e-6)
+        be1, be2 = float(torch.tensor(0.9, dtype=torch.float32)), float(torch.tensor(0.999, dtype=torch.float32))
+        assert got["lr_over_bc1"] == pytest.approx(float(torch.tensor(lr, dtype=torch.float32)) / (1 - be1 ** step), rel=1e-6)
+        assert got["inv_sqrt_bc2"] == pytest.approx(1 / math.sqrt(1 - be2 ** step), rel=1e-6)   # betas are fp32 in the ABI
 
 
 def test_gather_mix_sched_follows_the_schedule(dev):
