@@ -59,6 +59,9 @@ B200LIC_API int b200lic_version(void);
 B200LIC_API const char* b200lic_last_error_string(void);
 /* 0 when the current CUDA device is sm_100, B200LIC_ERR_ARCH otherwise. */
 B200LIC_API int b200lic_device_check(void);
+/* Debug aid: with B200LIC_TC_DEBUG=3 in the environment the tensor-core conv kernel records a %globaltimer timeline
+ * (ns) of CTA 0's first work item; this copies up to 128 stamps of the last launch to `out` (synchronises). */
+B200LIC_API int b200lic_debug_timeline(unsigned long long* out, int n);
 /* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
 B200LIC_API unsigned long long b200lic_launch_count(void);
 

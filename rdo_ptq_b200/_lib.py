@@ -78,7 +78,8 @@ SIGNATURES = {
     "pixel_unshuffle": [_P, _I, _I, _I, _I, _I, _P],
 }
 PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
-         "launch_count": (C.c_ulonglong, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int])}
+         "launch_count": (C.c_ulonglong, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
+         "debug_timeline": (C.c_int, [C.c_void_p, C.c_int])}
 OP_CONV_FWD, OP_DECONV_FWD, OP_CONV_DGRAD, OP_DECONV_DGRAD, OP_CONV_WGRAD, OP_DECONV_WGRAD = range(6)
 
 _lib = None

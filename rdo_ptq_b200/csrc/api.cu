@@ -60,7 +60,9 @@ int num_sms() {
 
 }  // namespace b200lic
 
+namespace b200lic { int tc2_debug_timeline(unsigned long long* out, int n); }
 extern "C" {
+int b200lic_debug_timeline(unsigned long long* out, int n) { return b200lic::tc2_debug_timeline(out, n); }
 int b200lic_version(void) { return 100; }
 const char* b200lic_last_error_string(void) { return b200lic::g_err; }
 int b200lic_device_check(void) { return b200lic::check_arch(); }

@@ -98,6 +98,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
       : "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void epi_bar(int id) {  // named barrier over the 4 epilogue warps
   asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
@@ -128,13 +133,13 @@ struct Tc2Geom {
   int gdn_mode, fixed_point;
   int tma_out, has_norm;
   int epi_smem;               // staging tiles are carved out of shared memory (planned TMA epilogue)
+  int x_slots;                // ring slots (one chunk each) for GDN's x operand
+  int chunk;                  // epilogue chunk width in channels (16 or 32)
   int dbg_mode;               // 0 normal; 1 = skip the MMAs; 2 = skip the TMA loads (bottleneck experiments only)
 };
 
 constexpr int kT2Threads = 192;
 constexpr int kA2Bytes = 128 * 64;        // 128 pixel rows x 32 bf16
-constexpr int kChunk = 16;                // epilogue chunk: 16 channels
-constexpr int kStageTile = kChunk * 128 * 4;   // fp32 staging tile of one chunk (8 KB)
 
 struct PhaseGeom {
   int ph, pw, KHp, KWp, Pa, Pb, in_step, tap_step, base_h, base_w, out_step;
@@ -167,7 +172,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                            const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
                            const __grid_constant__ CUtensorMap map_n, Tc2Geom g, const float* __restrict__ bias,
-                           const float* __restrict__ gdn_x, float* __restrict__ norm_out, float* __restrict__ y) {
+                           const float* __restrict__ gdn_x, float* __restrict__ norm_out, float* __restrict__ y,
+                           unsigned long long* __restrict__ dbg) {
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -178,14 +184,16 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   const uint32_t stage_bytes = (uint32_t)g.MT * 2u * kA2Bytes + 2u * b_tile_bytes;
   const uint32_t stage_area = (uint32_t)g.stages * stage_bytes;
   const uint32_t sY = smem_base + stage_area;                    // [2] output staging
-  const uint32_t sX = sY + (g.epi_smem ? 2u * kStageTile : 0u);                     // [2] GDN x operand (gdn_mode)
-  const uint32_t sN = sX + ((g.epi_smem && g.gdn_mode) ? 2u * kStageTile : 0u);      // [2] norm staging (has_norm)
-  const uint32_t bars = sN + ((g.epi_smem && g.has_norm) ? 2u * kStageTile : 0u);
+  const uint32_t ctile = (uint32_t)g.chunk * 512u;                                   // staging tile of one chunk
+  const uint32_t sX = sY + (g.epi_smem ? 2u * ctile : 0u);                          // [x_slots] GDN x operand ring
+  const uint32_t sN = sX + (uint32_t)g.x_slots * ctile;                              // [2] norm staging (has_norm)
+  const uint32_t bars = sN + ((g.epi_smem && g.has_norm) ? 2u * ctile : 0u);
+  const uint32_t sBias = bars + 512u;                                                // [BN] bias of the current n-tile
   const uint32_t full_bar = bars, empty_bar = bars + 8u * g.stages;
   const uint32_t tfull_bar = empty_bar + 8u * g.stages;          // [2] accumulator set complete
   const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (4 warp arrivals)
-  const uint32_t xfull_bar = tempty_bar + 16u;                   // [2] GDN x chunk landed
-  const uint32_t tmem_ptr_addr = xfull_bar + 16u;
+  const uint32_t xfull_bar = tempty_bar + 16u;                   // [x_slots] GDN x chunk landed
+  const uint32_t tmem_ptr_addr = xfull_bar + 8u * (uint32_t)(g.x_slots > 0 ? g.x_slots : 1);
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
 
@@ -197,8 +205,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8u * s, 1);
       mbar_init(tempty_bar + 8u * s, 4);
-      mbar_init(xfull_bar + 8u * s, 1);
     }
+    for (int s = 0; s < g.x_slots; ++s) mbar_init(xfull_bar + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -211,6 +219,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_gen;
+  const bool trace = dbg != nullptr && blockIdx.x == 0;     // B200LIC_TC_DEBUG=3: timeline of CTA 0's first item (ns)
+  if (trace && threadIdx.x == 0) dbg[0] = gtime();
 
   const int cblocks = g.Cpad >> 5;
   const int total_items = g.phases * g.n_tiles * g.m_groups;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       int s = 0;
       uint32_t sphase = 0;
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const int phase = w % g.phases, rest = w / g.phases;
+        const int rest = w / g.phases, phase = (w + rest) % g.phases;   // rotate: a CTA's items cycle through the phases
         const int n_tile = rest % g.n_tiles, mg = rest / g.n_tiles;
         const PhaseGeom q = phase_geom(g, phase);
         const int tiles_w = (q.Pb + g.BW - 1) / g.BW, tiles_h = (q.Pa + g.BH - 1) / g.BH;
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       int set = 0;
       uint32_t set_phase[2] = {0u, 0u};
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-        const int phase = w % g.phases, rest = w / g.phases;
+        const int rest = w / g.phases, phase = (w + rest) % g.phases;   // rotate: a CTA's items cycle through the phases
         const int mg = rest / g.n_tiles;
         const PhaseGeom q = phase_geom(g, phase);
         const int tiles_w = (q.Pb + g.BW - 1) / g.BW, tiles_h = (q.Pa + g.BH - 1) / g.BH;
@@ -296,6 +306,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const uint32_t acc0 = tmem_base + (uint32_t)(set * set_cols);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8u * s, sphase);
+          if (trace && w == 0 && kb == 0) dbg[100] = gtime();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t bb = st_base + (uint32_t)g.MT * 2u * kA2Bytes;
@@ -319,6 +330,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           }
         }
         umma_commit(tfull_bar + 8u * set);        // accumulators of this item complete
+        if (trace && w == 0) dbg[101] = gtime();
         set_phase[set] ^= 1u;
         if (g.acc_sets == 2) set ^= 1;
       }
@@ -330,14 +342,18 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     const int et = (warp - 2) * 32 + lane;                          // 0..127 within the epilogue group
     const int iw = m % g.BW, ih = (m / g.BW) % g.BH, ii = m / (g.BW * g.BH);
     const int hw_box = g.BW * g.BH;
-    const uint32_t st_off = (uint32_t)(ii * kChunk * hw_box + (m % hw_box)) * 4u;   // + j*hw_box*4 per channel
+    const int CH = g.chunk;                                         // channels per chunk: 16 or 32
+    const uint32_t tile_bytes = (uint32_t)CH * 512u;                // one staging tile: CH channels x 128 pixels fp32
+    const uint32_t st_off = (uint32_t)(ii * CH * hw_box + (m % hw_box)) * 4u;   // + j*hw_box*4 per channel
     const long long plane = (long long)g.Ho * g.Wo;
     int set = 0;
     uint32_t set_phase[2] = {0u, 0u};
     uint32_t kk = 0;                        // running chunk counter (staging buffer = kk & 1)
-    uint32_t xk_issued = 0, xk_used = 0;    // GDN x chunks requested / consumed (buffer = k & 1, parity = (k >> 1) & 1)
+    uint32_t xk_issued = 0, xk_used = 0;    // GDN x chunks requested / consumed (slot = k % NX, parity = (k / NX) & 1)
+    const uint32_t NX = (uint32_t)(g.x_slots > 0 ? g.x_slots : 1);
+    int bias_base = -1;                     // n-tile whose bias currently sits in sBias
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
-      const int phase = w % g.phases, rest = w / g.phases;
+      const int rest = w / g.phases, phase = (w + rest) % g.phases;
       const int n_tile = rest % g.n_tiles, mg = rest / g.n_tiles;
       const PhaseGeom q = phase_geom(g, phase);
       const int tiles_w = (q.Pb + g.BW - 1) / g.BW, tiles_h = (q.Pa + g.BH - 1) / g.BH;
@@ -346,14 +362,14 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       if (mg * g.MT >= m_tiles) continue;
       const int num_kb = q.KHp * q.KWp * cblocks;
       const int co_base = n_tile * g.BN;
-      const int n_chunks = g.BN / kChunk;
+      const int n_chunks = g.BN / CH;
       // chunks of this item, in processing order: (tile t, chunk c); count only valid tiles
       int vt = 0;
       for (int t = 0; t < g.MT; ++t) vt += (mg * g.MT + t < m_tiles) ? 1 : 0;
       const uint32_t item_chunks = (uint32_t)(vt * n_chunks);
       auto chunk_coords = [&](uint32_t ci, int& b0, int& a0, int& n0, int& c0) {
         const int t = (int)ci / n_chunks;
-        c0 = ((int)ci - t * n_chunks) * kChunk;
+        c0 = ((int)ci - t * n_chunks) * CH;
         const int mt = mg * g.MT + t;
         const int tw = mt % tiles_w, th = (mt / tiles_w) % tiles_h, tn = mt / (tiles_w * tiles_h);
         b0 = tw * g.BW;
@@ -363,111 +379,162 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       auto request_x = [&](uint32_t ci) {     // one thread: TMA load of GDN's x operand for chunk ci of this item
         int b0, a0, n0, c0;
         chunk_coords(ci, b0, a0, n0, c0);
-        const uint32_t buf = xk_issued & 1u;
-        mbar_expect_tx(xfull_bar + 8u * buf, kStageTile);
-        tma_load_4d(sX + buf * kStageTile, &map_x, xfull_bar + 8u * buf, b0, a0, co_base + c0, n0);
+        const uint32_t buf = xk_issued % NX;
+        mbar_expect_tx(xfull_bar + 8u * buf, tile_bytes);
+        tma_load_4d(sX + buf * tile_bytes, &map_x, xfull_bar + 8u * buf, b0, a0, co_base + c0, n0);
       };
-      if (g.gdn_mode && g.tma_out) {          // prefetch the first two x chunks while the main loop still runs
+      if (g.gdn_mode && g.tma_out) {          // fill the x ring while the main loop still runs
         if (et == 0) {
-          for (uint32_t ci = 0; ci < 2 && ci < item_chunks; ++ci) {
+          for (uint32_t ci = 0; ci < NX && ci < item_chunks; ++ci) {
             request_x(ci);
             ++xk_issued;
           }
         } else {
-          xk_issued += item_chunks < 2 ? item_chunks : 2;
+          xk_issued += item_chunks < NX ? item_chunks : NX;
         }
       }
+      if (bias_base != co_base) {             // per-channel bias of this n-tile -> shared memory (once per n-tile)
+        epi_bar(3);
+        for (int i = et; i < g.BN; i += 128) {
+          const float bv = (bias && co_base + i < g.Cout) ? __ldg(bias + co_base + i) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + (uint32_t)i * 4u), "f"(bv) : "memory");
+        }
+        epi_bar(3);
+        bias_base = co_base;
+      }
+      const bool tr = trace && w == 0 && et == 0;
       if (num_kb > 0) {
         mbar_wait_backoff(tfull_bar + 8u * set, set_phase[set]);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
+      if (tr) dbg[1] = gtime();
       const uint32_t acc0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * set_cols);
       for (uint32_t ci = 0; ci < item_chunks; ++ci) {
         int b0, a0, n0, c0;
         chunk_coords(ci, b0, a0, n0, c0);
         const int t = (int)ci / n_chunks;
-        uint32_t v[16];
-        if (num_kb > 0) {
-          tmem_ld16(acc0 + (uint32_t)(t * g.BN + c0), v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
-        }
+        const uint32_t buf = kk & 1u;
+        uint32_t xb = 0;
         if (g.tma_out) {
-          const uint32_t buf = kk & 1u;
           // the TMA store that read this staging buffer two chunks ago must have finished reading it
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           epi_bar(1);
-          float xv[16];
+          if (tr && ci < 30) dbg[2 + 3 * ci] = gtime();
           if (g.gdn_mode) {
-            const uint32_t xb = xk_used & 1u;
-            mbar_wait(xfull_bar + 8u * xb, (xk_used >> 1) & 1u);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float t0;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(sX + xb * kStageTile + st_off + (uint32_t)(j * hw_box) * 4u));
-              xv[j] = t0;
-            }
+            xb = xk_used % NX;
+            mbar_wait(xfull_bar + 8u * xb, (xk_used / NX) & 1u);
             ++xk_used;
           }
+          if (tr && ci < 30) dbg[3 + 3 * ci] = gtime();
+        }
+        // direct-store addressing (strided / unaligned outputs)
+        const int a = a0 + ih, b = b0 + iw, n = n0 + ii;
+        const bool valid = a < q.Pa && b < q.Pb && n < g.N;
+        const long long obase = ((long long)n * g.Cout + co_base + c0) * plane +
+                                (long long)(a * q.out_step + q.ph) * g.Wo + (b * q.out_step + q.pw);
+        for (int h = 0; h < CH; h += 16) {    // 16-channel halves of the chunk
+          uint32_t v[16];
+          if (num_kb > 0) {
+            tmem_ld16(acc0 + (uint32_t)(t * g.BN + c0 + h), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+          }
+          // Every mode test below is hoisted out of the 16-channel loops: with the tests inside, the unrolled body
+          // compiled to ~100 SASS instructions per channel and the single epilogue warp per scheduler became
+          // instruction-bound (2 us per 16 channels in the r1 timeline).
+          float r[16];
+          const uint32_t bias_addr = sBias + (uint32_t)(c0 + h) * 4u;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = co_base + c0 + j;
-            float r = __uint_as_float(v[j]) + ((bias && co < g.Cout) ? __ldg(bias + co) : 0.f);
-            const uint32_t so = st_off + (uint32_t)(j * hw_box) * 4u;
-            if (g.gdn_mode) {
-              if (g.has_norm) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sN + buf * kStageTile + so), "f"(r) : "memory");
-              r = g.gdn_mode == 1 ? xv[j] * rsqrtf(r) : xv[j] * sqrtf(r);
-            }
-            r = apply_act(r, g.act, g.slope);
-            if (g.fixed_point) r = rintf(fminf(fmaxf(r, -128.f), 128.f) * 256.f) * (1.f / 256.f);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sY + buf * kStageTile + so), "f"(r) : "memory");
+            float bj;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bj) : "r"(bias_addr + (uint32_t)j * 4u));
+            r[j] = __uint_as_float(v[j]) + bj;
           }
+          const uint32_t so0 = st_off + (uint32_t)(h * hw_box) * 4u;
+          const uint32_t sstep = (uint32_t)hw_box * 4u;
+          if (g.tma_out) {
+            if (g.gdn_mode) {
+              float xv[16];
+              const uint32_t xa = sX + xb * tile_bytes + so0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[j]) : "r"(xa + (uint32_t)j * sstep));
+              if (g.has_norm) {
+                const uint32_t na = sN + buf * tile_bytes + so0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(na + (uint32_t)j * sstep), "f"(r[j]) : "memory");
+              }
+              if (g.gdn_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = xv[j] * rsqrtf(r[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = xv[j] * sqrtf(r[j]);
+              }
+            }
+          } else if (g.gdn_mode) {
+            float xv[16];
+            const float* xp = gdn_x + obase + (long long)h * plane;
+            float* np = norm_out ? norm_out + obase + (long long)h * plane : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xv[j] = (valid && co_base + c0 + h + j < g.Cout) ? __ldg(xp + (long long)j * plane) : 0.f;
+            if (np && valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (co_base + c0 + h + j < g.Cout) np[(long long)j * plane] = r[j];
+            }
+            if (g.gdn_mode == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = xv[j] * rsqrtf(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = xv[j] * sqrtf(r[j]);
+            }
+          }
+          if (g.act == B200LIC_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = fmaxf(r[j], 0.f);
+          } else if (g.act == B200LIC_ACT_LEAKY_RELU) {
+            const float sl = g.slope;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * sl;
+          }
+          if (g.fixed_point) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = rintf(fminf(fmaxf(r[j], -128.f), 128.f) * 256.f) * (1.f / 256.f);
+          }
+          if (g.tma_out) {
+            const uint32_t ya = sY + buf * tile_bytes + so0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ya + (uint32_t)j * sstep), "f"(r[j]) : "memory");
+          } else if (valid) {
+            float* yp = y + obase + (long long)h * plane;
+            const int lim = g.Cout - (co_base + c0 + h);     // channels of this half that exist
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < lim) yp[(long long)j * plane] = r[j];
+          }
+        }
+        if (g.tma_out) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           epi_bar(2);
           if (et == 0) {
-            tma_store_4d(&map_y, sY + buf * kStageTile, b0, a0, co_base + c0, n0);
-            if (g.has_norm) tma_store_4d(&map_n, sN + buf * kStageTile, b0, a0, co_base + c0, n0);
+            tma_store_4d(&map_y, sY + buf * tile_bytes, b0, a0, co_base + c0, n0);
+            if (g.has_norm) tma_store_4d(&map_n, sN + buf * tile_bytes, b0, a0, co_base + c0, n0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (g.gdn_mode) {                    // the x buffer just consumed is free: request chunk ci + 2
-            if (ci + 2 < item_chunks) {
-              if (et == 0) request_x(ci + 2);
+          if (tr && ci < 30) dbg[4 + 3 * ci] = gtime();
+          if (g.gdn_mode) {                    // the x slot just consumed is free: request chunk ci + NX
+            if (ci + NX < item_chunks) {
+              if (et == 0) request_x(ci + NX);
               ++xk_issued;
             }
           }
           ++kk;
-        } else {
-          // strided / unaligned outputs: straight from registers (a warp covers 2 rows of 16 pixels per channel)
-          const int a = a0 + ih, b = b0 + iw, n = n0 + ii;
-          if (a < q.Pa && b < q.Pb && n < g.N) {
-            const int ho = a * q.out_step + q.ph, wo = b * q.out_step + q.pw;
-            const long long obase = ((long long)n * g.Cout + co_base + c0) * plane + (long long)ho * g.Wo + wo;
-            float xv[16];
-            if (g.gdn_mode) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                xv[j] = (co_base + c0 + j < g.Cout) ? __ldg(gdn_x + obase + (long long)j * plane) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = co_base + c0 + j;
-              if (co < g.Cout) {
-                const long long idx = obase + (long long)j * plane;
-                float r = __uint_as_float(v[j]) + (bias ? __ldg(bias + co) : 0.f);
-                if (g.gdn_mode) {
-                  if (norm_out) norm_out[idx] = r;
-                  r = g.gdn_mode == 1 ? xv[j] * rsqrtf(r) : xv[j] * sqrtf(r);
-                }
-                r = apply_act(r, g.act, g.slope);
-                if (g.fixed_point) r = rintf(fminf(fmaxf(r, -128.f), 128.f) * 256.f) * (1.f / 256.f);
-                y[idx] = r;
-              }
-            }
-          }
         }
       }
+      if (tr) dbg[99] = gtime();
       if (num_kb > 0) {
         // this warp has read everything it needs from the accumulator set: hand it back to the MMA issuer
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -490,6 +557,15 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
+static unsigned long long* g_dbg_buf = nullptr;      // B200LIC_TC_DEBUG=3 timeline of the last launch (debug aid only)
+int tc2_debug_timeline(unsigned long long* out, int n) {
+  if (!g_dbg_buf || n < 1) return 0;
+  if (n > 128) n = 128;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_dbg_buf, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return n;
+}
+
 static int pow2_ceil2(int v) {
   int p = 1;
   while (p < v) p *= 2;
@@ -499,7 +575,7 @@ static int pow2_ceil2(int v) {
 struct Tc2Plan {
   bool ok = false;
   int Cpad, CoutPad, Tmax, phases, BN, n_tiles, BW, BH, BI, MT, m_tiles, m_groups, stages, acc_sets, tmem_cols;
-  int tma_out, epi_smem;
+  int tma_out, epi_smem, x_slots, chunk;
   size_t x_bytes, b_bytes, total_bytes, smem_bytes;
 };
 
@@ -528,8 +604,21 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   }
   p.n_tiles = p.CoutPad / p.BN;
   const int Pa = (Ho + st - 1) / st, Pb = (Wo + st - 1) / st;  // largest phase
-  p.BW = Pb >= 16 ? 16 : pow2_ceil2(Pb);
+  // Pixel box: as wide as divides the row (up to 128 pixels), so that the NCHW side of the tile (epilogue stores, GDN's
+  // x operand) moves in 256-512 B contiguous rows instead of 64 B pieces; falls back to 16-wide boxes for ragged widths.
   const int es = transposed ? 1 : stride;
+  static int bw_cap = -1;
+  if (bw_cap < 0) {
+    const char* e = getenv("B200LIC_TC_BW");
+    bw_cap = e ? atoi(e) : 128;
+    if (bw_cap < 16) bw_cap = 16;
+  }
+  p.BW = Pb >= 16 ? 16 : pow2_ceil2(Pb);
+  for (int bw = 128; bw > 16; bw >>= 1)
+    if (bw <= bw_cap && Pb % bw == 0 && bw * es <= 256) {
+      p.BW = bw;
+      break;
+    }
   if (p.BW * es > 256) return p;
   p.BH = 128 / p.BW;
   if (p.BH > pow2_ceil2(Pa)) p.BH = pow2_ceil2(Pa);
@@ -549,12 +638,25 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   p.tma_out = (!transposed && (Wo % 4) == 0) ? 1 : 0;
   p.epi_smem = p.tma_out;
   const size_t stage = (size_t)p.MT * 2 * kA2Bytes + 2 * (size_t)p.BN * 64;
-  const size_t epi = p.tma_out ? (size_t)(2 + (gdn_mode ? 2 : 0) + ((gdn_mode && has_norm) ? 2 : 0)) * kStageTile : 0;
-  const size_t avail = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - epi;
-  p.stages = (int)(avail / stage);
-  if (p.stages > 8) p.stages = 8;
-  if (p.stages < 2) return p;
-  p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512;
+  p.chunk = (p.BN % 32 == 0) ? 32 : 16;
+  const size_t ctile = (size_t)p.chunk * 512;
+  size_t epi = p.tma_out ? (size_t)(2 + ((gdn_mode && has_norm) ? 2 : 0)) * ctile : 0;
+  const size_t avail = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 1024 /*bias*/;
+  p.x_slots = 0;
+  if (gdn_mode && p.tma_out) {
+    // GDN is bound by the x / y / norm streams, not by its short K loop: two operand stages, and every remaining
+    // kilobyte becomes x-operand ring slots so ~100 KB of loads are in flight per SM
+    if (avail < 2 * stage + epi + 2 * ctile) return p;
+    p.stages = 2;
+    p.x_slots = (int)((avail - 2 * stage - epi) / ctile);
+    if (p.x_slots > 16) p.x_slots = 16;
+    epi += (size_t)p.x_slots * ctile;
+  } else {
+    if (avail < epi + 2 * stage) return p;
+    p.stages = (int)((avail - epi) / stage);
+    if (p.stages > 8) p.stages = 8;
+  }
+  p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 1024;
   p.x_bytes = ((size_t)N * H * W * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.b_bytes = ((size_t)p.phases * p.CoutPad * p.Tmax * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.total_bytes = 2 * p.x_bytes + 2 * p.b_bytes + 1024;
@@ -622,7 +724,7 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
     // fp32 NCHW output-shaped tensors: (W, H, C, N), box = one staging chunk
     cuuint64_t odims[4] = {(cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)Cout, (cuuint64_t)N};
     cuuint64_t ostr[3] = {(cuuint64_t)Wo * 4, (cuuint64_t)Wo * Ho * 4, (cuuint64_t)Wo * Ho * Cout * 4};
-    cuuint32_t obox[4] = {(cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)kChunk, (cuuint32_t)p.BI};
+    cuuint32_t obox[4] = {(cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.chunk, (cuuint32_t)p.BI};
     cuuint32_t oes[4] = {1, 1, 1, 1};
     if (p.tma_out) {
       if (!tc_encode_map_ex(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, y, 4, odims, ostr, obox, oes))
@@ -649,7 +751,7 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
             p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, act, slope, gdn_mode, fixed_point,
-            p.tma_out, has_norm, p.epi_smem, dbg_mode};
+            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, dbg_mode};
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc2_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -659,11 +761,17 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
     }
     attr_set = true;
   }
+  unsigned long long* dbg = nullptr;
+  if (dbg_mode == 3) {
+    if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 128 * sizeof(unsigned long long));
+    cudaMemsetAsync(g_dbg_buf, 0, 128 * sizeof(unsigned long long), s);
+    dbg = g_dbg_buf;
+  }
   const long long items = (long long)p.phases * p.n_tiles * p.m_groups;
   const int sms = num_sms();
   const int grid = (int)(items < sms ? items : sms);
   tc2_gather_gemm_kernel<<<grid, kT2Threads, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, gdn_x, norm_out,
-                                                                y);
+                                                                y, dbg);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

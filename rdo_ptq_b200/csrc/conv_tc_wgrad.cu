@@ -283,7 +283,8 @@ static WgPlan make_wg_plan(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb
   p.units = (TT + kBoxesA - 1) / kBoxesA;
   p.ktiles = ((Ws + p.BW - 1) / p.BW) * ((Hs + p.BH - 1) / p.BH) * ((N + p.BI - 1) / p.BI);
   const int ctas = p.units * p.n_tiles;
-  int want = (2 * num_sms() + ctas - 1) / ctas;
+  // split-K so that the grid fills two rounds of the SMs without spilling into a third, nearly empty one
+  int want = (2 * num_sms()) / ctas;
   int max_splits = (p.ktiles + 3) / 4;            // >= 4 pixel tiles per split
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
