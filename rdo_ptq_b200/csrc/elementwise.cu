@@ -234,12 +234,25 @@ __global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a
                                                       float* __restrict__ out) {
   __shared__ float red[32];
   float s0 = 0.f, s1 = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float av = __ldg(a + i), bv = __ldg(b + i);
+  auto one = [&](float av, float bv) {
     const float d0 = av - bv, d1 = fminf(fmaxf(av, 0.f), 1.f) - bv;
     s0 += d0 * d0;
     s1 += d1 * d1;
+  };
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t done = 0;
+  if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+    const size_t n4 = n >> 2;
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i), bv = __ldg(reinterpret_cast<const float4*>(b) + i);
+      one(av.x, bv.x);
+      one(av.y, bv.y);
+      one(av.z, bv.z);
+      one(av.w, bv.w);
+    }
+    done = n4 << 2;
   }
+  for (size_t i = done + tid; i < n; i += stride) one(__ldg(a + i), __ldg(b + i));
   const float t0 = block_sum(s0, red);
   const float t1 = block_sum(s1, red);
   if (threadIdx.x == 0) {
@@ -251,8 +264,17 @@ __global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a
 __global__ void __launch_bounds__(256) bits_sum_kernel(const float* __restrict__ lik, size_t n, float* __restrict__ out) {
   __shared__ float red[32];
   float s = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    s -= log2f(__ldg(lik + i));
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t done = 0;
+  if ((((uintptr_t)lik) & 15) == 0) {
+    const size_t n4 = n >> 2;
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(lik) + i);
+      s -= log2f(v.x) + log2f(v.y) + log2f(v.z) + log2f(v.w);
+    }
+    done = n4 << 2;
+  }
+  for (size_t i = done + tid; i < n; i += stride) s -= log2f(__ldg(lik + i));
   const float t = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(out, t);
 }
@@ -287,7 +309,7 @@ int b200lic_lp_loss_fwd_bwd(const float* pred, const float* tgt, size_t n, float
   B200_REQUIRE(pred && tgt, "lp_loss_fwd_bwd: null pointer");
   B200_REQUIRE(p >= 1.f, "lp_loss_fwd_bwd: p=%f < 1", p);
   if (n == 0) return B200LIC_OK;
-  lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, as_stream(stream)>>>(pred, tgt, n, p, scale, grad_scale, loss,
+  lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(pred, tgt, n, p, scale, grad_scale, loss,
                                                                              d_pred);
   B200_LAUNCH_CHECK("lp_loss_kernel");
   return B200LIC_OK;
@@ -297,7 +319,7 @@ int b200lic_sq_err_sum(const float* a, const float* b, size_t n, float* out, b20
   B200_ARCH_GATE();
   B200_REQUIRE(a && b && out, "sq_err_sum: null pointer");
   if (n == 0) return B200LIC_OK;
-  sq_err_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(a, b, n, out);
+  sq_err_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(a, b, n, out);
   B200_LAUNCH_CHECK("sq_err_kernel");
   return B200LIC_OK;
 }
@@ -306,7 +328,7 @@ int b200lic_bits_sum(const float* lik, size_t n, float* out, b200lic_stream_t st
   B200_ARCH_GATE();
   B200_REQUIRE(lik && out, "bits_sum: null pointer");
   if (n == 0) return B200LIC_OK;
-  bits_sum_kernel<<<grid_for(n, 256, 4), 256, 0, as_stream(stream)>>>(lik, n, out);
+  bits_sum_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(lik, n, out);
   B200_LAUNCH_CHECK("bits_sum_kernel");
   return B200LIC_OK;
 }

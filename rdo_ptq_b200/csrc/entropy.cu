@@ -143,6 +143,11 @@ __device__ __forceinline__ float factorized_one(const FactorizedParams& P, float
   return fmaxf(fabsf(sigm(sgn * up) - sigm(sgn * lo)), lik_bound);
 }
 
+// out-of-table symbols: kept out of line so the streaming loop stays at ~40 registers (4+ CTAs per SM)
+__device__ __noinline__ float factorized_rare(const FactorizedParams* P, float zh, float lik_bound) {
+  return factorized_one(*P, zh, lik_bound);
+}
+
 // The latent symbols of a channel are med + k for a few dozen integers k, so the 58-parameter CDF network is evaluated
 // once per (channel, k) into a shared-memory table (|k| <= kTabR) and the element loop is two table reads: the kernel
 // streams z at HBM speed instead of spending ~300 instructions per element.  Symbols outside the table (rare) take the
@@ -150,7 +155,7 @@ __device__ __forceinline__ float factorized_one(const FactorizedParams& P, float
 constexpr int kTabR = 96;
 constexpr int kTabN = 2 * kTabR + 1;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     factorized_lik_kernel(const float* __restrict__ z, const float* __restrict__ params,
                           const float* __restrict__ medians, int N, int C, int HW, int splits, float lik_bound,
                           float* __restrict__ z_hat, float* __restrict__ lik, float* __restrict__ bits_out) {
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(256)
   const float med = __ldg(medians + c);
   for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
     const float zh = __fadd_rn((float)(j - kTabR), med);
-    const float l = factorized_one(P, zh, lik_bound);
+    const float l = factorized_rare(&P, zh, lik_bound);
     t_lik[j] = l;
     t_bits[j] = -log2f(l);
   }
@@ -185,27 +190,44 @@ __global__ void __launch_bounds__(256)
       l = t_lik[j];
       bits += t_bits[j];
     } else {
-      l = factorized_one(P, zh, lik_bound);
+      l = factorized_rare(&P, zh, lik_bound);
       bits -= log2f(l);
     }
   };
-  for (int n = split; n < N; n += splits) {
-    const size_t base = ((size_t)n * C + c) * HW;
-    if (vec) {
-      const float4* z4 = reinterpret_cast<const float4*>(z + base);
-      float4* o4 = reinterpret_cast<float4*>(z_hat + base);
-      float4* l4 = lik ? reinterpret_cast<float4*>(lik + base) : nullptr;
-      for (int i = threadIdx.x; i < (HW >> 2); i += blockDim.x) {
-        const float4 zv = __ldg(z4 + i);
-        float4 o, l;
-        one(zv.x, o.x, l.x);
-        one(zv.y, o.y, l.y);
-        one(zv.z, o.z, l.z);
-        one(zv.w, o.w, l.w);
-        o4[i] = o;
-        if (l4) l4[i] = l;
+  // the CTA's planes n = split, split + splits, ... are walked as one flat float4 index space, four independent
+  // requests per thread in flight (planes of z are small: one float4 per thread per plane would be latency-bound)
+  const int my_planes = (N - split + splits - 1) / splits;
+  if (vec) {
+    const int q4 = HW >> 2;
+    const long long total = (long long)my_planes * q4;
+    for (long long i0 = threadIdx.x; i0 < total; i0 += 4LL * blockDim.x) {
+      float4 zv[4];
+      size_t off[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        ok[u] = i < total;
+        const long long pl = ok[u] ? i / q4 : 0;
+        const int e = ok[u] ? (int)(i - pl * q4) : 0;
+        off[u] = (((size_t)(split + pl * splits) * C + c) * HW) / 4 + e;
+        if (ok[u]) zv[u] = __ldg(reinterpret_cast<const float4*>(z) + off[u]);
       }
-    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float4 o, l;
+        one(zv[u].x, o.x, l.x);
+        one(zv[u].y, o.y, l.y);
+        one(zv[u].z, o.z, l.z);
+        one(zv[u].w, o.w, l.w);
+        reinterpret_cast<float4*>(z_hat)[off[u]] = o;
+        if (lik) reinterpret_cast<float4*>(lik)[off[u]] = l;
+      }
+    }
+  } else {
+    for (int n = split; n < N; n += splits) {
+      const size_t base = ((size_t)n * C + c) * HW;
       for (int i = threadIdx.x; i < HW; i += blockDim.x) {
         float o, l;
         one(__ldg(z + base + i), o, l);

@@ -5,6 +5,7 @@
 // Reference arithmetic restated (not translated): task-oriented-PTQ/quantization/quantizer.py
 //   :281-298 range -> (delta, zero_point); :175-177 fake-quant; :437-452 AdaRound forward;
 //   :454-466 alpha init; layer_opt.py:160-165 rounding regulariser; torch.optim.Adam.
+#include <initializer_list>
 #include "common.cuh"
 
 namespace b200lic {
@@ -100,26 +101,57 @@ __global__ void __launch_bounds__(256) adaround_init_kernel(const float* __restr
   }
 }
 
+// float4 helpers: 4 consecutive elements share a quantisation channel when inner % 4 == 0
+template <bool VEC>
+struct Pack {
+  float v[VEC ? 4 : 1];
+};
+template <bool VEC>
+__device__ __forceinline__ Pack<VEC> ldp(const float* p, size_t i) {
+  Pack<VEC> r;
+  if (VEC) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[VEC ? 2 : 0] = t.z; r.v[VEC ? 3 : 0] = t.w;
+  } else {
+    r.v[0] = __ldg(p + i);
+  }
+  return r;
+}
+template <bool VEC>
+__device__ __forceinline__ void stp(float* p, size_t i, const Pack<VEC>& r) {
+  if (VEC) *reinterpret_cast<float4*>(p + i) = make_float4(r.v[0], r.v[1], r.v[VEC ? 2 : 0], r.v[VEC ? 3 : 0]);
+  else p[i] = r.v[0];
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) adaround_fwd_kernel(const float* __restrict__ w, const float* __restrict__ alpha,
                                                             const float* __restrict__ delta, const float* __restrict__ zp,
                                                             size_t n, int ch, int inner, float top, int soft,
                                                             float* __restrict__ w_q, float* __restrict__ codes) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  constexpr int E = VEC ? 4 : 1;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * E; i < n; i += (size_t)gridDim.x * blockDim.x * E) {
     const int c = (int)((i / inner) % ch);
     const float d = __ldg(delta + c), z = __ldg(zp + c);
-    const float base = floorf(__fdiv_rn(w[i], d));
-    const float a = alpha[i];
-    float up;
-    if (soft) {
-      const float s = __fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma);
-      up = fminf(fmaxf(s, 0.f), 1.f);
-    } else {
-      up = a >= 0.f ? 1.f : 0.f;
+    const Pack<VEC> wv = ldp<VEC>(w, i), av = ldp<VEC>(alpha, i);
+    Pack<VEC> qv, dq;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float base = floorf(__fdiv_rn(wv.v[e], d));
+      const float a = av.v[e];
+      float up;
+      if (soft) {
+        const float s = __fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma);
+        up = fminf(fmaxf(s, 0.f), 1.f);
+      } else {
+        up = a >= 0.f ? 1.f : 0.f;
+      }
+      float q = __fadd_rn(__fadd_rn(base, up), z);
+      q = fminf(fmaxf(q, 0.f), top);
+      qv.v[e] = q;
+      dq.v[e] = __fmul_rn(__fsub_rn(q, z), d);
     }
-    float q = __fadd_rn(__fadd_rn(base, up), z);
-    q = fminf(fmaxf(q, 0.f), top);
-    if (codes) codes[i] = q;
-    if (w_q) w_q[i] = __fmul_rn(__fsub_rn(q, z), d);
+    if (codes) stp<VEC>(codes, i, qv);
+    if (w_q) stp<VEC>(w_q, i, dq);
   }
 }
 
@@ -127,6 +159,7 @@ struct AdamArgs {
   float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps;
 };
 
+template <bool VEC>
 __global__ void __launch_bounds__(256)
     adaround_bwd_adam_kernel(const float* __restrict__ w, float* __restrict__ alpha, const float* __restrict__ delta,
                              const float* __restrict__ zp, const float* __restrict__ d_wq, float* __restrict__ m,
@@ -134,44 +167,68 @@ __global__ void __launch_bounds__(256)
                              float grad_scale, float reg_weight, float reg_b, float* __restrict__ reg_loss,
                              float* __restrict__ d_alpha_out, const b200lic_calib_sched* __restrict__ sched) {
   __shared__ float red[32];
+  constexpr int E = VEC ? 4 : 1;
   float reg_acc = 0.f;
   if (sched != nullptr) {  // iteration-dependent scalars come from device memory (CUDA-graph replay)
     ad.lr_over_bc1 = __ldg(&sched->lr_over_bc1);
     ad.inv_sqrt_bc2 = __ldg(&sched->inv_sqrt_bc2);
     reg_b = __ldg(&sched->reg_b);
   }
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * E; i < n; i += (size_t)gridDim.x * blockDim.x * E) {
     const int c = (int)((i / inner) % ch);
     const float d = __ldg(delta + c), z = __ldg(zp + c);
-    const float a = alpha[i];
-    const float sg = sigmoidf_(a);
-    const float s = __fadd_rn(__fmul_rn(sg, kStretch), kGamma);
-    const float h = fminf(fmaxf(s, 0.f), 1.f);
-    // autograd of clamp passes the gradient on the closed interval
-    const float dh_da = (s >= 0.f && s <= 1.f) ? kStretch * sg * (1.f - sg) : 0.f;
-    const float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(w[i], d)), h), z);
-    float g = 0.f;
-    if (xi >= 0.f && xi <= top) g = grad_scale * d_wq[i] * d * dh_da;
-    if (reg_b > 0.f) {
-      const float u = fabsf(h - 0.5f) * 2.f;          // |2h-1|
-      const float ub1 = powf(u, reg_b - 1.f);
-      reg_acc += 1.f - ub1 * u;
-      const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
-      g += -reg_weight * reg_b * ub1 * 2.f * sgn * dh_da;
+    const Pack<VEC> wv = ldp<VEC>(w, i), av = ldp<VEC>(alpha, i), gv = ldp<VEC>(d_wq, i);
+    Pack<VEC> mv, vv, ga, an;
+    if (m != nullptr) {
+      mv = ldp<VEC>(m, i);
+      vv = ldp<VEC>(v, i);
     }
-    if (d_alpha_out) d_alpha_out[i] = g;
-    if (m == nullptr) continue;  // gradient-only mode (autograd surface); no optimiser state touched
-    const float mi = ad.beta1 * m[i] + (1.f - ad.beta1) * g;
-    const float vi = ad.beta2 * v[i] + (1.f - ad.beta2) * g * g;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) * ad.inv_sqrt_bc2 + ad.eps;
-    alpha[i] = a - ad.lr_over_bc1 * (mi / denom);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float a = av.v[e];
+      const float sg = sigmoidf_(a);
+      const float s = __fadd_rn(__fmul_rn(sg, kStretch), kGamma);
+      const float h = fminf(fmaxf(s, 0.f), 1.f);
+      // autograd of clamp passes the gradient on the closed interval
+      const float dh_da = (s >= 0.f && s <= 1.f) ? kStretch * sg * (1.f - sg) : 0.f;
+      const float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(wv.v[e], d)), h), z);
+      float g = 0.f;
+      if (xi >= 0.f && xi <= top) g = grad_scale * gv.v[e] * d * dh_da;
+      if (reg_b > 0.f) {
+        const float u = fabsf(h - 0.5f) * 2.f;          // |2h-1|
+        const float ub1 = powf(u, reg_b - 1.f);
+        reg_acc += 1.f - ub1 * u;
+        const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
+        g += -reg_weight * reg_b * ub1 * 2.f * sgn * dh_da;
+      }
+      ga.v[e] = g;
+      if (m != nullptr) {
+        const float mi = ad.beta1 * mv.v[e] + (1.f - ad.beta1) * g;
+        const float vi = ad.beta2 * vv.v[e] + (1.f - ad.beta2) * g * g;
+        mv.v[e] = mi;
+        vv.v[e] = vi;
+        const float denom = sqrtf(vi) * ad.inv_sqrt_bc2 + ad.eps;
+        an.v[e] = a - ad.lr_over_bc1 * (mi / denom);
+      }
+    }
+    if (d_alpha_out) stp<VEC>(d_alpha_out, i, ga);
+    if (m != nullptr) {  // else: gradient-only mode (autograd surface); no optimiser state touched
+      stp<VEC>(m, i, mv);
+      stp<VEC>(v, i, vv);
+      stp<VEC>(alpha, i, an);
+    }
   }
   if (reg_loss != nullptr && reg_b > 0.f) {
     const float tot = block_sum(reg_acc, red);
     if (threadIdx.x == 0) atomicAdd(reg_loss, reg_weight * tot);
   }
+}
+
+static inline bool vec4_ok(size_t n, int inner, std::initializer_list<const void*> ptrs) {
+  if ((inner & 3) != 0 || (n & 3) != 0) return false;
+  for (const void* p : ptrs)
+    if (p && (((uintptr_t)p) & 15)) return false;
+  return true;
 }
 
 // One thread advances the device-resident schedule (same arithmetic as the host path: fp64 bias corrections cast to
@@ -251,8 +308,12 @@ int b200lic_adaround_fwd(const float* w, const float* alpha, const float* delta,
   B200_ARCH_GATE();
   B200_REQUIRE(w && alpha && delta && zero_point, "adaround_fwd: null pointer");
   const size_t n = (size_t)outer * ch * inner;
-  adaround_fwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, alpha, delta, zero_point, n, ch, inner,
-                                                                       (float)(n_levels - 1), soft, w_q, codes);
+  if (vec4_ok(n, inner, {w, alpha, w_q, codes}))
+    adaround_fwd_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        w, alpha, delta, zero_point, n, ch, inner, (float)(n_levels - 1), soft, w_q, codes);
+  else
+    adaround_fwd_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        w, alpha, delta, zero_point, n, ch, inner, (float)(n_levels - 1), soft, w_q, codes);
   B200_LAUNCH_CHECK("adaround_fwd_kernel");
   return B200LIC_OK;
 }
@@ -270,9 +331,14 @@ int b200lic_adaround_bwd_adam(const float* w, float* alpha, const float* delta, 
   const size_t n = (size_t)outer * ch * inner;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   AdamArgs ad{(float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps};
-  adaround_bwd_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-      w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
-      reg_weight, reg_b, reg_loss, d_alpha_out, nullptr);
+  if (vec4_ok(n, inner, {w, alpha, d_wq, exp_avg, exp_avg_sq, d_alpha_out}))
+    adaround_bwd_adam_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
+        reg_weight, reg_b, reg_loss, d_alpha_out, nullptr);
+  else
+    adaround_bwd_adam_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
+        reg_weight, reg_b, reg_loss, d_alpha_out, nullptr);
   B200_LAUNCH_CHECK("adaround_bwd_adam_kernel");
   return B200LIC_OK;
 }
@@ -297,9 +363,14 @@ int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, const float* d
                "adaround_bwd_adam_sched: null pointer");
   const size_t n = (size_t)outer * ch * inner;
   AdamArgs ad{0.f, 0.f, beta1, beta2, eps};
-  adaround_bwd_adam_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-      w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
-      reg_weight, 0.f, reg_loss, nullptr, sched);
+  if (vec4_ok(n, inner, {w, alpha, d_wq, exp_avg, exp_avg_sq}))
+    adaround_bwd_adam_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
+        reg_weight, 0.f, reg_loss, nullptr, sched);
+  else
+    adaround_bwd_adam_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
+        reg_weight, 0.f, reg_loss, nullptr, sched);
   B200_LAUNCH_CHECK("adaround_bwd_adam_kernel(sched)");
   return B200LIC_OK;
 }

@@ -66,10 +66,14 @@ class UnitTrainer:
         """One fused iteration.  With `sched` (a device-resident b200lic_calib_sched, already ticked for this
         iteration) no host scalar that changes between iterations enters a kernel argument, so the call sequence can be
         captured once as a CUDA graph and replayed (session.py)."""
-        if sched is None:
-            self.count += 1
-            b = self.temp_decay(self.count)
-            reg_b = 0.0 if self.count < self.loss_start else float(b)
+        out, grads = self.step_compute(cur_inp, tgt)
+        self.step_update(grads, trace=trace, sched=sched)
+        if trace is not None:
+            trace["out"] = out.detach()
+        return out
+
+    def step_compute(self, cur_inp: torch.Tensor, tgt: torch.Tensor):
+        """Soft weights -> unit forward -> loss value + dL/dout -> wgrad/dgrad.  Returns (out, [dL/dWq per module])."""
         leaves = []
         for m in self.mods:
             q = m.weight_quantizer
@@ -100,10 +104,21 @@ class UnitTrainer:
             for m in self.mods:
                 m.weight_quantizer._leaf = None
         grads = [l.grad for l in leaves]
-        if self.world > 1:
+        if self.world > 1:          # one flat bucket per unit for the all-reduce of step_update
             flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
             grads = [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)]
+            self._flat = flat
+        return out, grads
+
+    def step_update(self, grads, trace: Optional[dict] = None, sched=None):
+        """[NCCL all-reduce of the unit's dL/dWq bucket] -> STE masks + rounding regulariser + Adam on alpha.  Touches
+        only this unit's state, so a session may run it on a side stream under the next unit's step_compute."""
+        if sched is None:
+            self.count += 1
+            b = self.temp_decay(self.count)
+            reg_b = 0.0 if self.count < self.loss_start else float(b)
+        if self.world > 1:
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
         for i, m in enumerate(self.mods):
             q = m.weight_quantizer
             if sched is not None:
@@ -119,9 +134,6 @@ class UnitTrainer:
                                   reg_loss=self.loss_buf[2:3], d_alpha_out=d_alpha)
             if trace is not None:
                 trace.setdefault("d_alpha", []).append(d_alpha)
-        if trace is not None:
-            trace["out"] = out.detach()
-        return out
 
     def read_losses(self, since: int):
         """One device->host read of the accumulated (rec, task, round) sums; returns per-iteration means."""

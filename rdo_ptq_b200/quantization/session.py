@@ -26,6 +26,25 @@ from .recon import UnitTrainer
 PERM_ROWS = 4096
 
 
+def unit_macs(u, cache):
+    """Algorithmic MACs per sample of a unit's forward: conv Ho*Wo*Cout*Cin*k*k, transposed conv
+    Hin*Win*Cin*Cout*k*k, GDN H*W*C^2; blocks: sum over their QuantModules is approximated by the first rule on the
+    block's input/output (only used to balance streams)."""
+    q_in, _, fp_out = cache
+    w = getattr(u, "weight", None)
+    if getattr(u, "is_gdn", False):
+        C_, H, W = q_in.shape[1:]
+        return H * W * C_ * C_
+    if w is None or w.dim() != 4:
+        return float(sum(m.weight.numel() for m in u.modules() if getattr(m, "weight", None) is not None)) * \
+            fp_out.shape[2] * fp_out.shape[3]
+    if getattr(u, "if_tconv", False):
+        Cin, H, W = q_in.shape[1:]
+        return H * W * Cin * w.shape[1] * w.shape[2] * w.shape[3]
+    Cout, Ho, Wo = fp_out.shape[1:]
+    return Ho * Wo * Cout * w.shape[1] * w.shape[2] * w.shape[3]
+
+
 def reconstruction_units(qnn: QuantModel):
     """Units in `recon_model` order (main2.py:227-253): QuantModules and BaseQuantBlocks, depth first, blocks opaque."""
     units = []
@@ -82,7 +101,8 @@ class CalibrationSession:
     def __init__(self, qnn: QuantModel, cali: torch.Tensor, batch_size: int = 8, iters: int = 20000,
                  weight: float = 0.01, b_range=(20, 2), warmup: float = 0.2, input_prob: float = 0.5, p: float = 2.0,
                  task_p: float = 2.0, host_caches: bool = False, seed: int = 1005, graph: bool = True,
-                 graph_warmup: int = 2, lr: float = 1e-3, process_group=None):
+                 graph_warmup: int = 2, lr: float = 1e-3, process_group=None, overlap_update: bool = True,
+                 n_streams: int = 3):
         self.qnn, self.batch_size, self.input_prob, self.seed = qnn, batch_size, input_prob, seed
         self.units = reconstruction_units(qnn)
         self.host = host_caches
@@ -106,7 +126,25 @@ class CalibrationSession:
         self.sched = ops.new_sched(dev)
         self._tick = (iters, warmup, b_range[0], b_range[1], lr)
         self.use_graph, self.graph_warmup = graph, graph_warmup
-        self._graphs, self._graph_launches, self._pool, self._captured_launches = {}, {}, None, 0
+        self._graphs, self._graph_launches, self._captured_launches = {}, {}, 0
+        self._tail_graphs, self._tail_launches, self._grads = {}, {}, {}
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # multi-GPU: the all-reduce + Adam tail of each unit runs on ONE side stream (same collective order on every
+        # rank) under the compute of the following units
+        self._side = torch.cuda.Stream(device=dev) if (self.world > 1 and graph and overlap_update) else None
+        # Units are independent problems, and most of them (hyperprior layers, 32x32 / 16x16 stages) launch
+        # 1-64 CTAs: their graphs are spread over `n_streams` streams (longest-processing-time-first by a cost estimate)
+        # so the small units fill the SMs the large ones leave idle.  Each stream owns its graph memory pool.
+        self.n_streams = max(1, n_streams if graph else 1)
+        self._streams = [None] + [torch.cuda.Stream(device=dev) for _ in range(self.n_streams - 1)]   # None = caller's
+        self._pools = [None] * self.n_streams
+        cost = {n: 120.0 + 6.0 * unit_macs(u, self.caches[n]) * batch_size / 8e8 for n, u in self.units}   # ~us
+        load = [0.0] * self.n_streams
+        self._sid = {}
+        for n in sorted(cost, key=cost.get, reverse=True):
+            k = min(range(self.n_streams), key=load.__getitem__)
+            self._sid[n] = k
+            load[k] += cost[n]
         self._since = 0
         self.h2d_bytes = 0
         self.replayed_launches = 0           # kernels launched by graph replays (not seen by the library's host counter)
@@ -120,8 +158,9 @@ class CalibrationSession:
                 self._ready[n] = torch.cuda.Event()
                 self._consumed[n] = None
 
-    # -- one unit, one iteration: the capturable body -----------------------------------------------------------------
-    def _body(self, j, name):
+    # -- one unit, one iteration: the capturable bodies ---------------------------------------------------------------
+    def _compute(self, j, name):
+        """pick + QDrop -> soft weights -> forward -> loss -> wgrad; leaves the unit's dL/dWq in self._grads[name]."""
         U, bs = len(self.units), self.batch_size
         if self.host:
             qi, fi, tgt = self._stage[name]
@@ -131,7 +170,15 @@ class CalibrationSession:
             cur = ops.gather_mix_sched(q_in, fp_in, self._perm_dev, bs, self.input_prob, self.seed_base, U, j,
                                        self.sched)
             tgt = ops.gather_mix_sched(fp_out, fp_out, self._perm_dev, bs, 1.0, self.seed_base, U, j, self.sched)
-        self.trainers[name].step(cur, tgt, sched=self.sched)
+        _, self._grads[name] = self.trainers[name].step_compute(cur, tgt)
+
+    def _update(self, j, name):
+        """[all-reduce] -> STE / regulariser / Adam for the unit (reads self._grads[name])."""
+        self.trainers[name].step_update(self._grads[name], sched=self.sched)
+
+    def _body(self, j, name):
+        self._compute(j, name)
+        self._update(j, name)
 
     def _upload(self, j, name):
         """Host-cache mode: copy this iteration's batch rows of (quant_in, fp_in, fp_out) from pinned host memory into
@@ -148,41 +195,74 @@ class CalibrationSession:
             self._ready[name].record(self._copy_stream)
 
     def _capture(self, j, name):
+        """Capture the unit's iteration on its stream.  Single GPU: one graph.  Multi-GPU: a compute graph and an update
+        graph (side stream) so the all-reduce + Adam tail overlaps the compute of the following units."""
         n0 = _lib.launch_count()
-        g = torch.cuda.CUDAGraph()
-        kw = dict(pool=self._pool) if self._pool is not None else {}
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        sid = self._sid[name]
+        kw = dict(pool=self._pools[sid]) if self._pools[sid] is not None else {}
+        if self._streams[sid] is not None:
+            kw["stream"] = self._streams[sid]
+        if self.world > 1:
             kw["capture_error_mode"] = "thread_local"      # NCCL's watchdog thread polls events during capture
+        g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, **kw):
-            self._body(j, name)
-        if self._pool is None:
-            self._pool = g.pool()
+            if self._side is None:
+                self._body(j, name)
+            else:
+                self._compute(j, name)
+        if self._pools[sid] is None:
+            self._pools[sid] = g.pool()
+        n1 = _lib.launch_count()
+        if self._side is not None:
+            gt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gt, stream=self._side, capture_error_mode="thread_local"):   # no allocations: own pool
+                self._update(j, name)
+            self._tail_graphs[name] = gt
+            self._tail_launches[name] = _lib.launch_count() - n1
         self._graphs[name] = g
-        self._graph_launches[name] = _lib.launch_count() - n0
-        self._captured_launches += self._graph_launches[name]      # counted by the library while capturing, not executed
+        self._graph_launches[name] = n1 - n0
+        self._captured_launches += _lib.launch_count() - n0         # counted by the library while capturing, not executed
 
     def sweep(self, only=None):
         """One AdaRound iteration (fwd + loss + bwd(alpha) + Adam [+ all-reduce]) on every unit."""
-        cur_stream = torch.cuda.current_stream()
+        main = torch.cuda.current_stream()
         ops.sched_tick(self.sched, *self._tick)
         graphed = self.use_graph and self.it >= self.graph_warmup
+        if graphed:
+            for st in self._streams[1:]:
+                st.wait_stream(main)               # the schedule has been advanced
+        used = set()
         for j, (n, _) in enumerate(self.units):
             if only is not None and n not in only:
                 continue
+            st = (self._streams[self._sid[n]] if graphed else None) or main
             if self.host:
                 self._upload(j, n)
-                cur_stream.wait_event(self._ready[n])
+                st.wait_event(self._ready[n])
             if graphed:
                 if n not in self._graphs:
+                    torch.cuda.synchronize()       # capture starts from a quiet device (other streams are mid-sweep)
                     self._capture(j, n)
-                self._graphs[n].replay()
+                with torch.cuda.stream(st):
+                    self._graphs[n].replay()
+                used.add(st)
                 self.replayed_launches += self._graph_launches[n]
+                if self._side is not None:
+                    self._side.wait_stream(st)
+                    with torch.cuda.stream(self._side):
+                        self._tail_graphs[n].replay()
+                    self.replayed_launches += self._tail_launches[n]
             else:
                 self._body(j, n)
             if self.host:
                 ev = torch.cuda.Event()
-                ev.record(cur_stream)
+                ev.record(st)
                 self._consumed[n] = ev
+        for st in used:                            # join: the sweep is complete on the caller's stream
+            if st is not main:
+                main.wait_stream(st)
+        if self._side is not None and graphed:
+            main.wait_stream(self._side)
         self.it += 1
         self._since += 1
 
