@@ -257,6 +257,15 @@ B200LIC_API int b200lic_gather_mix_sched(const float* q, const float* fp, const 
                              size_t rows, size_t row_elems, float prob, unsigned long long seed_base, int units,
                              int unit, const b200lic_calib_sched* sched, float* out, b200lic_stream_t stream);
 
+/* b200lic_lp_loss_fwd_bwd against a target batch picked from a cache: row b of pred [rows, row_elems] is compared
+ * with tgt_cache[idx_table[k % table_rows][b]], k = (sched->step - 1) * units + unit -- the same pick
+ * b200lic_gather_mix_sched makes for the input, so the target batch (layer_opt.py:290 `cur_out = cached_outs[idx]`)
+ * is never materialised. */
+B200LIC_API int b200lic_lp_loss_fwd_bwd_sched(const float* pred, const float* tgt_cache, const long long* idx_table,
+                                  int table_rows, size_t rows, size_t row_elems, int units, int unit,
+                                  const b200lic_calib_sched* sched, float p, float scale, float grad_scale,
+                                  float* loss, float* d_pred, b200lic_stream_t stream);
+
 /* out = a * sigmoid(b) + c   (AttentionBlock tail) */
 B200LIC_API int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out,
                       b200lic_stream_t stream);

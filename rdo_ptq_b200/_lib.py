@@ -54,6 +54,7 @@ SIGNATURES = {
     "round_latent": [_P, _P, _SZ, _P],
     "factorized_lik_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
     "lp_loss_fwd_bwd": [_P, _P, _SZ, _F, _F, _F, _P, _P],
+    "lp_loss_fwd_bwd_sched": [_P, _P, _P, _I, _SZ, _SZ, _I, _I, _P, _F, _F, _F, _P, _P],
     "sq_err_sum": [_P, _P, _SZ, _P],
     "bits_sum": [_P, _SZ, _P],
     "conv_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _SZ],

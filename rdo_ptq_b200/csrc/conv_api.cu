@@ -21,6 +21,8 @@ int tc_conv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, 
 int tc_deconv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
 int tc_conv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
 int tc_deconv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
+size_t tc_conv_fwd_ws(const b200lic_conv_desc*);
+size_t tc_deconv_fwd_ws(const b200lic_conv_desc*);
 size_t tc_conv_wgrad_ws(const b200lic_conv_desc*);
 size_t tc_deconv_wgrad_ws(const b200lic_conv_desc*);
 }  // namespace b200lic
@@ -43,9 +45,9 @@ size_t b200lic_conv_workspace_bytes(const b200lic_conv_desc* d, int op) {
   if (!d) return 0;
   switch (op) {
     case B200LIC_OP_CONV_FWD:
-      return tc_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, 0);
+      return tc_conv_fwd_ws(d);
     case B200LIC_OP_DECONV_FWD:
-      return tc_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, 1);
+      return tc_deconv_fwd_ws(d);
     case B200LIC_OP_CONV_DGRAD:
       return tc_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, 1);
     case B200LIC_OP_DECONV_DGRAD:

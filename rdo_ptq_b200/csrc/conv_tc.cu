@@ -636,8 +636,26 @@ size_t tc_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   return p.ok ? p.total_bytes : 0;
 }
 
+size_t smallc_conv_fwd_ws(const b200lic_conv_desc* d);
+size_t smallc_deconv_fwd_ws(const b200lic_conv_desc* d);
+int smallc_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* ws,
+                    size_t ws_bytes, cudaStream_t s);
+int smallc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* ws,
+                      size_t ws_bytes, cudaStream_t s);
+size_t tc_conv_fwd_ws(const b200lic_conv_desc* d) {
+  if (!use_v1())
+    if (const size_t n = smallc_conv_fwd_ws(d)) return n;
+  return tc_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, 0);
+}
+size_t tc_deconv_fwd_ws(const b200lic_conv_desc* d) {
+  if (!use_v1())
+    if (const size_t n = smallc_deconv_fwd_ws(d)) return n;
+  return tc_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, 1);
+}
+
 int tc_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, const float* gdn_x,
                 float* norm_out, float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!use_v1() && smallc_conv_fwd_ws(d) != 0) return smallc_conv_fwd(d, x, w, bias, y, ws, ws_bytes, s);
   return tc_launch(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0,
                    (long long)d->Cin * d->KH * d->KW, (long long)d->KH * d->KW, d->act, d->act_slope, d->in_square,
                    d->gdn_mode, d->fixed_point, x, w, bias, gdn_x, norm_out, y, ws, ws_bytes, s, "conv_fwd(tc)");
@@ -645,6 +663,7 @@ int tc_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, cons
 
 int tc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* ws,
                   size_t ws_bytes, cudaStream_t s) {
+  if (!use_v1() && smallc_deconv_fwd_ws(d) != 0) return smallc_deconv_fwd(d, x, w, bias, y, ws, ws_bytes, s);
   return tc_launch(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 1,
                    (long long)d->KH * d->KW, (long long)d->Cout * d->KH * d->KW, d->act, d->act_slope, 0, 0,
                    d->fixed_point, x, w, bias, nullptr, nullptr, y, ws, ws_bytes, s, "deconv_fwd(tc)");

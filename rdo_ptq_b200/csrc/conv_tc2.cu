@@ -696,8 +696,11 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
   void* bl = ws + 2 * p.x_bytes + p.b_bytes;
 
   // 1. stage operands
-  int rc = tc_stage_nhwc(x, N, Cin, H * W, p.Cpad, in_square, xh, xl, s);
-  if (rc != B200LIC_OK) return rc;
+  int rc = B200LIC_OK;
+  if (x != nullptr) {            // nullptr: the caller staged the activation operand at the head of the workspace
+    rc = tc_stage_nhwc(x, N, Cin, H * W, p.Cpad, in_square, xh, xl, s);
+    if (rc != B200LIC_OK) return rc;
+  }
   rc = tc_pack_weights(w, Cout, Cin, KH, KW, stride, pad, transposed, p.CoutPad, p.Cpad, p.Tmax, p.phases, s_co, s_ci, bh,
                        bl, s);
   if (rc != B200LIC_OK) return rc;

@@ -322,8 +322,10 @@ int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int 
   void *sh = ws, *sl = ws + p.small_bytes, *bh = ws + 2 * p.small_bytes, *bl = ws + 2 * p.small_bytes + p.big_bytes;
   int rc = tc_stage_nhwc(small, N, Cs, Hs * Ws, p.CsPad, 0, sh, sl, s);
   if (rc != B200LIC_OK) return rc;
-  rc = tc_stage_nhwc(big, N, Cb, Hb * Wb, p.CbPad, big_square, bh, bl, s);
-  if (rc != B200LIC_OK) return rc;
+  if (big != nullptr) {          // nullptr: the caller staged the gathered operand in its workspace slot (conv_tc_smallc.cu)
+    rc = tc_stage_nhwc(big, N, Cb, Hb * Wb, p.CbPad, big_square, bh, bl, s);
+    if (rc != B200LIC_OK) return rc;
+  }
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cs * Cb * KH * KW, s);
   if (e != cudaSuccess) {
     set_error("%s: memset failed: %s", name, cudaGetErrorString(e));
@@ -361,22 +363,33 @@ int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int 
   return B200LIC_OK;
 }
 
+size_t smallc_conv_wgrad_ws(const b200lic_conv_desc* d);
+size_t smallc_deconv_wgrad_ws(const b200lic_conv_desc* d);
+int smallc_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                      cudaStream_t s);
+int smallc_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                        cudaStream_t s);
+
 int tc_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t s) {
+  if (smallc_conv_wgrad_ws(d) != 0) return smallc_conv_wgrad(d, x, dy, dw, ws, ws_bytes, s);
   return tc_wgrad(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, d->pad, d->in_square, dy, x,
                   dw, ws, ws_bytes, s, "conv_wgrad(tc)");
 }
 
 int tc_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
+  if (smallc_deconv_wgrad_ws(d) != 0) return smallc_deconv_wgrad(d, x, dy, dw, ws, ws_bytes, s);
   return tc_wgrad(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0, x, dy, dw, ws,
                   ws_bytes, s, "deconv_wgrad(tc)");
 }
 
 size_t tc_conv_wgrad_ws(const b200lic_conv_desc* d) {
+  if (const size_t n = smallc_conv_wgrad_ws(d)) return n;
   return tc_wgrad_workspace_bytes(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride);
 }
 size_t tc_deconv_wgrad_ws(const b200lic_conv_desc* d) {
+  if (const size_t n = smallc_deconv_wgrad_ws(d)) return n;
   return tc_wgrad_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride);
 }
 

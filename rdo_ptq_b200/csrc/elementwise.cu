@@ -179,13 +179,27 @@ struct GdnBwdFinish {  // a = x, b = t, c = dx_direct
 };
 
 // ---- reductions ----------------------------------------------------------------------------------------------
+struct LossPick {               // target rows picked from a cache by the device schedule (nullptr table: plain tgt)
+  const long long* idx_table;
+  int table_rows, units, unit;
+  size_t rows, row;
+  const b200lic_calib_sched* sched;
+};
+
 __global__ void __launch_bounds__(256) lp_loss_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
                                                        size_t n, float p, float scale, float grad_scale,
-                                                       float* __restrict__ loss, float* __restrict__ d_pred) {
+                                                       float* __restrict__ loss, float* __restrict__ d_pred,
+                                                       LossPick pk) {
   __shared__ float red[32];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float acc = 0.f;
+  const long long* idx = nullptr;
+  if (pk.idx_table != nullptr) {
+    const unsigned long long k =
+        (unsigned long long)(__ldg(&pk.sched->step) - 1) * (unsigned long long)pk.units + (unsigned long long)pk.unit;
+    idx = pk.idx_table + (size_t)(k % (unsigned long long)pk.table_rows) * pk.rows;
+  }
   const bool p2 = (p == 2.f);
   auto one = [&](float a, float b, float& g) {
     const float d = a - b;
@@ -199,6 +213,25 @@ __global__ void __launch_bounds__(256) lp_loss_kernel(const float* __restrict__ 
       g = grad_scale * p * pw * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
     }
   };
+  if (idx != nullptr) {           // picked target rows; row % 4 == 0 and 16-byte alignment are checked by the host
+    const size_t n4 = n >> 2;
+    for (size_t i = tid; i < n4; i += stride) {
+      const size_t e0 = i << 2, b_ = e0 / pk.row, e = e0 - b_ * pk.row;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(tgt + (size_t)idx[b_] * pk.row + e));
+      float4 g;
+      one(a.x, b.x, g.x);
+      one(a.y, b.y, g.y);
+      one(a.z, b.z, g.z);
+      one(a.w, b.w, g.w);
+      if (d_pred) reinterpret_cast<float4*>(d_pred)[i] = g;
+    }
+    if (loss) {
+      const float tot = block_sum(acc, red);
+      if (threadIdx.x == 0) atomicAdd(loss, scale * tot);
+    }
+    return;
+  }
   const bool vec = (((uintptr_t)pred | (uintptr_t)tgt | (uintptr_t)d_pred) & 15) == 0;
   if (vec) {
     const size_t n4 = n >> 2;
@@ -310,8 +343,27 @@ int b200lic_lp_loss_fwd_bwd(const float* pred, const float* tgt, size_t n, float
   B200_REQUIRE(p >= 1.f, "lp_loss_fwd_bwd: p=%f < 1", p);
   if (n == 0) return B200LIC_OK;
   lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(pred, tgt, n, p, scale, grad_scale, loss,
-                                                                             d_pred);
+                                                                             d_pred, LossPick{nullptr, 0, 0, 0, 0, 0, nullptr});
   B200_LAUNCH_CHECK("lp_loss_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_lp_loss_fwd_bwd_sched(const float* pred, const float* tgt_cache, const long long* idx_table, int table_rows,
+                                  size_t rows, size_t row_elems, int units, int unit, const b200lic_calib_sched* sched,
+                                  float p, float scale, float grad_scale, float* loss, float* d_pred,
+                                  b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(pred && tgt_cache && idx_table && sched, "lp_loss_fwd_bwd_sched: null pointer");
+  B200_REQUIRE(p >= 1.f, "lp_loss_fwd_bwd_sched: p=%f < 1", p);
+  B200_REQUIRE(table_rows >= 1 && units >= 1 && unit >= 0 && unit < units, "lp_loss_fwd_bwd_sched: bad pick arguments");
+  B200_REQUIRE((row_elems & 3) == 0 && (((uintptr_t)pred | (uintptr_t)tgt_cache | (uintptr_t)d_pred) & 15) == 0,
+               "lp_loss_fwd_bwd_sched: rows must be a multiple of 4 elements and 16-byte aligned");
+  const size_t n = rows * row_elems;
+  if (n == 0) return B200LIC_OK;
+  lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(
+      pred, tgt_cache, n, p, scale, grad_scale, loss, d_pred,
+      LossPick{idx_table, table_rows, units, unit, rows, row_elems, sched});
+  B200_LAUNCH_CHECK("lp_loss_kernel(sched)");
   return B200LIC_OK;
 }
 

@@ -196,14 +196,24 @@ def factorized_lik(z, packed_params, medians, lik_bound=1e-9, want_lik=True):
     return z_hat, lik, bits
 
 
-def lp_loss_fwd_bwd(pred, tgt, p=2.0, scale=1.0, grad_scale=None, loss=None, want_grad=True):
-    """loss += scale * sum|pred-tgt|^p ; returns (loss, d_pred)."""
+def lp_loss_fwd_bwd(pred, tgt, p=2.0, scale=1.0, grad_scale=None, loss=None, want_grad=True, pick=None):
+    """loss += scale * sum|pred-tgt|^p ; returns (loss, d_pred).
+    pick = (idx_table, units, unit, sched): `tgt` is a [samples, ...] cache and row b of `pred` is compared with
+    tgt[idx_table[k % rows][b]], k = (sched.step - 1) * units + unit (the pick gather_mix_sched makes)."""
     pred, tgt = _c(pred, "pred"), _c(tgt, "tgt")
     if loss is None:
         loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
     g = torch.empty_like(pred) if want_grad else None
-    call("lp_loss_fwd_bwd", _p(pred), _p(tgt), pred.numel(), float(p), float(scale),
-         float(scale if grad_scale is None else grad_scale), _p(loss), _p(g))
+    gs = float(scale if grad_scale is None else grad_scale)
+    if pick is None:
+        call("lp_loss_fwd_bwd", _p(pred), _p(tgt), pred.numel(), float(p), float(scale), gs, _p(loss), _p(g))
+    else:
+        idx_table, units, unit, sched = pick
+        rows, row = pred.shape[0], pred[0].numel()
+        if idx_table.dtype != torch.int64 or idx_table.dim() != 2 or idx_table.size(1) != rows or tgt[0].numel() != row:
+            raise ValueError("lp_loss_fwd_bwd: pick table / target cache do not match the prediction batch")
+        call("lp_loss_fwd_bwd_sched", _p(pred), _p(tgt), _p(idx_table.contiguous()), idx_table.size(0), rows, row,
+             int(units), int(unit), _p(sched), float(p), float(scale), gs, _p(loss), _p(g))
     return loss, g
 
 

@@ -55,6 +55,12 @@ class UnitTrainer:
                 m.weight_quantizer = AdaRoundQuantizer(uaq=m.weight_quantizer, round_mode='learned_hard_sigmoid',
                                                        weight_tensor=m.org_weight.data)
             m.weight_quantizer.soft_targets = True
+        # Only alpha is optimised (layer_opt.py:253-254); the fused loop never needs autograd gradients of the unit's own
+        # parameters (bias, GDN beta, un-quantised weights), so they are frozen for the duration: no dbeta reduction, no
+        # reparametrisation backward.  finish() restores the flags.
+        self._frozen = [p for p in unit.parameters() if p.requires_grad]
+        for p in self._frozen:
+            p.requires_grad_(False)
         self.exp_avg = [torch.zeros_like(m.weight_quantizer.alpha.data) for m in self.mods]
         self.exp_avg_sq = [torch.zeros_like(m.weight_quantizer.alpha.data) for m in self.mods]
         dev = self.mods[0].weight.device if self.mods else None
@@ -72,8 +78,10 @@ class UnitTrainer:
             trace["out"] = out.detach()
         return out
 
-    def step_compute(self, cur_inp: torch.Tensor, tgt: torch.Tensor):
-        """Soft weights -> unit forward -> loss value + dL/dout -> wgrad/dgrad.  Returns (out, [dL/dWq per module])."""
+    def step_compute(self, cur_inp: torch.Tensor, tgt, tgt_pick=None):
+        """Soft weights -> unit forward -> loss value + dL/dout -> wgrad/dgrad.  Returns (out, [dL/dWq per module]).
+        `tgt` is the target batch, or (with `tgt_pick = (idx_table, units, unit, sched)`) the whole cached-output tensor
+        whose rows the loss kernel picks itself, so the target batch is never materialised."""
         leaves = []
         for m in self.mods:
             q = m.weight_quantizer
@@ -89,9 +97,11 @@ class UnitTrainer:
             rec = self.loss_buf[0:1]
             if self.task_p is not None and float(self.task_p) == float(self.p):
                 _, d_out = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.p, scale=1.0 / denom, grad_scale=2.0 / denom,
-                                               loss=rec)
+                                               loss=rec, pick=tgt_pick)
                 same = True
             else:
+                if tgt_pick is not None:
+                    raise NotImplementedError("picked targets are only wired for task_p == p (the reference default)")
                 _, d_out = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.p, scale=1.0 / denom, loss=rec)
                 if self.task_p is not None:
                     _, d2 = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.task_p, scale=1.0 / denom,
@@ -146,6 +156,9 @@ class UnitTrainer:
         return self.last
 
     def finish(self):
+        for p in self._frozen:
+            p.requires_grad_(True)
+        self._frozen = []
         for m in self.mods:
             m.weight_quantizer.soft_targets = False
         marks = ([self.unit] if isinstance(self.unit, QuantModule) else

@@ -169,6 +169,11 @@ class CalibrationSession:
             q_in, fp_in, fp_out = self.caches[name]
             cur = ops.gather_mix_sched(q_in, fp_in, self._perm_dev, bs, self.input_prob, self.seed_base, U, j,
                                        self.sched)
+            t = self.trainers[name]
+            if t.task_p is not None and float(t.task_p) == float(t.p):
+                # the loss kernel reads the target rows straight from the cache (same pick as the input rows)
+                _, self._grads[name] = t.step_compute(cur, fp_out, tgt_pick=(self._perm_dev, U, j, self.sched))
+                return
             tgt = ops.gather_mix_sched(fp_out, fp_out, self._perm_dev, bs, 1.0, self.seed_base, U, j, self.sched)
         _, self._grads[name] = self.trainers[name].step_compute(cur, tgt)
 
