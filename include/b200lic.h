@@ -188,6 +188,16 @@ B200LIC_API int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, c
 /* dw[Cin,Cout,KH,KW] for y = conv_transpose2d(x, w). */
 B200LIC_API int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
                          void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
+/* Staged-operand reuse between forward and weight gradient.  The tensor-core forward leaves a split-bf16 NHWC copy of
+ * x in its workspace; when that copy is directly consumable by the wgrad engine (x_hi / x_lo come back non-NULL) the
+ * caller may keep the forward workspace alive and call b200lic_conv_wgrad_staged instead of b200lic_conv_wgrad /
+ * b200lic_deconv_wgrad, which skips re-staging x (one read + one write of the activation per iteration).
+ * `op` is B200LIC_OP_CONV_FWD or B200LIC_OP_DECONV_FWD; `d` must be the descriptor of the forward call. */
+B200LIC_API int b200lic_conv_staged_view(const b200lic_conv_desc* d, int op, void* fwd_workspace, size_t workspace_bytes,
+                             void** x_hi, void** x_lo);
+B200LIC_API int b200lic_conv_wgrad_staged(const b200lic_conv_desc* d, int transposed, const void* x_hi, const void* x_lo,
+                              const float* dy, float* dw, void* workspace, size_t workspace_bytes,
+                              b200lic_stream_t stream);
 /* dx[N,Cin,H,W] for y = conv2d(x, w). */
 B200LIC_API int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx,
                        void* workspace, size_t workspace_bytes, b200lic_stream_t stream);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "deconv_fwd": [_D, _P, _P, _P, _P, _P, _SZ],
     "conv_wgrad": [_D, _P, _P, _P, _P, _SZ],
     "deconv_wgrad": [_D, _P, _P, _P, _P, _SZ],
+    "conv_wgrad_staged": [_D, _I, _P, _P, _P, _P, _P, _SZ],
     "conv_dgrad": [_D, _P, _P, _P, _P, _SZ],
     "deconv_dgrad": [_D, _P, _P, _P, _P, _SZ],
     "gdn_reparam_fwd": [_P, _SZ, _F, _F, _P],
@@ -80,7 +81,9 @@ SIGNATURES = {
 }
 PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
          "launch_count": (C.c_ulonglong, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
-         "debug_timeline": (C.c_int, [C.c_void_p, C.c_int])}
+         "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+         "conv_staged_view": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p)])}
 OP_CONV_FWD, OP_DECONV_FWD, OP_CONV_DGRAD, OP_DECONV_DGRAD, OP_CONV_WGRAD, OP_DECONV_WGRAD = range(6)
 
 _lib = None

@@ -21,6 +21,10 @@ int tc_conv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, 
 int tc_deconv_dgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
 int tc_conv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
 int tc_deconv_wgrad(const b200lic_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t);
+bool tc_staged_view(const b200lic_conv_desc* d, int transposed, void* fwd_ws, size_t ws_bytes, void** hi, void** lo);
+int tc_conv_wgrad_pre(const b200lic_conv_desc*, const void*, const void*, const float*, float*, void*, size_t, cudaStream_t);
+int tc_deconv_wgrad_pre(const b200lic_conv_desc*, const void*, const void*, const float*, float*, void*, size_t,
+                        cudaStream_t);
 size_t tc_conv_fwd_ws(const b200lic_conv_desc*);
 size_t tc_deconv_fwd_ws(const b200lic_conv_desc*);
 size_t tc_conv_wgrad_ws(const b200lic_conv_desc*);
@@ -101,6 +105,28 @@ int b200lic_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float
   B200_REQUIRE(x && dy && dw, "deconv_wgrad: null pointer");
   DISPATCH(tc_deconv_wgrad(d, x, dy, dw, workspace, workspace_bytes, as_stream(stream)),
            simt_deconv_wgrad(d, x, dy, dw, as_stream(stream)));
+}
+
+int b200lic_conv_staged_view(const b200lic_conv_desc* d, int op, void* fwd_workspace, size_t workspace_bytes,
+                             void** x_hi, void** x_lo) {
+  B200_REQUIRE(d && x_hi && x_lo, "conv_staged_view: null pointer");
+  B200_REQUIRE(op == B200LIC_OP_CONV_FWD || op == B200LIC_OP_DECONV_FWD, "conv_staged_view: op must be a forward op");
+  *x_hi = *x_lo = nullptr;
+  if (d->engine == B200LIC_ENGINE_SIMT) return B200LIC_OK;
+  tc_staged_view(d, op == B200LIC_OP_DECONV_FWD, fwd_workspace, workspace_bytes, x_hi, x_lo);
+  return B200LIC_OK;
+}
+
+int b200lic_conv_wgrad_staged(const b200lic_conv_desc* d, int transposed, const void* x_hi, const void* x_lo,
+                              const float* dy, float* dw, void* workspace, size_t workspace_bytes,
+                              b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  int rc = conv_check_desc(d, "conv_wgrad_staged", transposed != 0);
+  if (rc != B200LIC_OK) return rc;
+  B200_REQUIRE(x_hi && x_lo && dy && dw, "conv_wgrad_staged: null pointer");
+  B200_REQUIRE(d->engine != B200LIC_ENGINE_SIMT, "conv_wgrad_staged: staged operands belong to the tensor-core engine");
+  return transposed ? tc_deconv_wgrad_pre(d, x_hi, x_lo, dy, dw, workspace, workspace_bytes, as_stream(stream))
+                    : tc_conv_wgrad_pre(d, x_hi, x_lo, dy, dw, workspace, workspace_bytes, as_stream(stream));
 }
 
 int b200lic_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,

@@ -642,6 +642,22 @@ int smallc_conv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, 
                     size_t ws_bytes, cudaStream_t s);
 int smallc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* ws,
                       size_t ws_bytes, cudaStream_t s);
+// Where the forward call left the split-bf16 NHWC copy of x inside its workspace, if the wgrad engine can consume it
+// as is (channels a multiple of 64, generic tap-by-tap path of the second-generation engine).
+bool tc_staged_view(const b200lic_conv_desc* d, int transposed, void* fwd_ws, size_t ws_bytes, void** hi, void** lo) {
+  *hi = *lo = nullptr;
+  if (use_v1() || !fwd_ws || (d->Cin % 64) != 0) return false;
+  if ((transposed ? smallc_deconv_fwd_ws(d) : smallc_conv_fwd_ws(d)) != 0) return false;
+  const size_t need = tc2_workspace_bytes(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride,
+                                          transposed);
+  if (need == 0 || ws_bytes < need) return false;
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)fwd_ws + 1023) & ~(uintptr_t)1023);
+  const size_t x_bytes = ((size_t)d->N * d->H * d->W * d->Cin * 2 + 1023) / 1024 * 1024;
+  *hi = base;
+  *lo = base + x_bytes;
+  return true;
+}
+
 size_t tc_conv_fwd_ws(const b200lic_conv_desc* d) {
   if (!use_v1())
     if (const size_t n = smallc_conv_fwd_ws(d)) return n;

@@ -306,9 +306,20 @@ size_t tc_wgrad_workspace_bytes(int N, int Cs, int Hs, int Ws, int Cb, int Hb, i
 }
 
 // small [N,Cs,Hs,Ws], big [N,Cb,Hb,Wb] (fp32 NCHW) -> dw [Cs][Cb][KH][KW] (overwritten)
+// Pre-staged operands: `small` / `big` may be nullptr when the matching split-bf16 NHWC operand already exists, either in
+// this workspace's own slot (conv_tc_smallc.cu) or, with small_pre / big_pre, in a forward workspace (staged view).
+int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
+                const float* small, const float* big, const void* const* small_pre, const void* const* big_pre, float* dw,
+                void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name);
 int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
              const float* small, const float* big, float* dw, void* workspace, size_t workspace_bytes, cudaStream_t s,
              const char* name) {
+  return tc_wgrad_ex(N, Cs, Hs, Ws, Cb, Hb, Wb, KH, KW, stride, pad, big_square, small, big, nullptr, nullptr, dw,
+                     workspace, workspace_bytes, s, name);
+}
+int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
+                const float* small, const float* big, const void* const* small_pre, const void* const* big_pre, float* dw,
+                void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name) {
   WgPlan p = make_wg_plan(N, Cs, Hs, Ws, Cb, Hb, Wb, KH, KW, stride);
   if (!p.ok) {
     set_error("%s: shape not eligible for the tcgen05 engine", name);
@@ -320,9 +331,18 @@ int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int 
   }
   uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   void *sh = ws, *sl = ws + p.small_bytes, *bh = ws + 2 * p.small_bytes, *bl = ws + 2 * p.small_bytes + p.big_bytes;
-  int rc = tc_stage_nhwc(small, N, Cs, Hs * Ws, p.CsPad, 0, sh, sl, s);
-  if (rc != B200LIC_OK) return rc;
-  if (big != nullptr) {          // nullptr: the caller staged the gathered operand in its workspace slot (conv_tc_smallc.cu)
+  int rc = B200LIC_OK;
+  if (small_pre) {
+    sh = const_cast<void*>(small_pre[0]);
+    sl = const_cast<void*>(small_pre[1]);
+  } else if (small != nullptr) {
+    rc = tc_stage_nhwc(small, N, Cs, Hs * Ws, p.CsPad, 0, sh, sl, s);
+    if (rc != B200LIC_OK) return rc;
+  }
+  if (big_pre) {
+    bh = const_cast<void*>(big_pre[0]);
+    bl = const_cast<void*>(big_pre[1]);
+  } else if (big != nullptr) {   // nullptr: the caller staged the gathered operand in its workspace slot (conv_tc_smallc.cu)
     rc = tc_stage_nhwc(big, N, Cb, Hb * Wb, p.CbPad, big_square, bh, bl, s);
     if (rc != B200LIC_OK) return rc;
   }
@@ -382,6 +402,20 @@ int tc_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy,
   if (smallc_deconv_wgrad_ws(d) != 0) return smallc_deconv_wgrad(d, x, dy, dw, ws, ws_bytes, s);
   return tc_wgrad(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0, x, dy, dw, ws,
                   ws_bytes, s, "deconv_wgrad(tc)");
+}
+
+// x already staged by the forward call (b200lic_conv_staged_view): skip its NHWC split
+int tc_conv_wgrad_pre(const b200lic_conv_desc* d, const void* x_hi, const void* x_lo, const float* dy, float* dw, void* ws,
+                      size_t ws_bytes, cudaStream_t s) {
+  const void* pre[2] = {x_hi, x_lo};
+  return tc_wgrad_ex(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, d->pad, d->in_square, dy,
+                     nullptr, nullptr, pre, dw, ws, ws_bytes, s, "conv_wgrad(tc, staged x)");
+}
+int tc_deconv_wgrad_pre(const b200lic_conv_desc* d, const void* x_hi, const void* x_lo, const float* dy, float* dw,
+                        void* ws, size_t ws_bytes, cudaStream_t s) {
+  const void* pre[2] = {x_hi, x_lo};
+  return tc_wgrad_ex(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0, nullptr, dy, pre,
+                     nullptr, dw, ws, ws_bytes, s, "deconv_wgrad(tc, staged x)");
 }
 
 size_t tc_conv_wgrad_ws(const b200lic_conv_desc* d) {

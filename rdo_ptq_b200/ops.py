@@ -285,19 +285,44 @@ def _workspace(d, op, device):
     return torch.empty(n, dtype=torch.uint8, device=device), n
 
 
-def conv2d_raw(x, w, bias, d, gdn_x=None, want_norm=False):
+def conv2d_raw(x, w, bias, d, gdn_x=None, want_norm=False, want_ws=False):
     y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
     norm = torch.empty_like(y) if want_norm else None
     ws, nws = _workspace(d, _lib.OP_CONV_FWD, x.device)
     call("conv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(gdn_x), _p(norm), _p(y), _p(ws), nws)
-    return (y, norm) if want_norm else y
+    out = (y, norm) if want_norm else y
+    return (out, (ws, nws)) if want_ws else out
 
 
-def deconv2d_raw(x, w, bias, d):
+def deconv2d_raw(x, w, bias, d, want_ws=False):
     y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
     ws, nws = _workspace(d, _lib.OP_DECONV_FWD, x.device)
     call("deconv_fwd", C.byref(d), _p(x), _p(w), _p(bias), _p(y), _p(ws), nws)
-    return y
+    return (y, (ws, nws)) if want_ws else y
+
+
+def _staged_x(d, op, fwd_ws):
+    """(x_hi, x_lo) device pointers of the split-bf16 NHWC copy of x the forward call left in its workspace, or None
+    when the wgrad engine cannot consume it (b200lic_conv_staged_view)."""
+    ws, nws = fwd_ws
+    if ws is None:
+        return None
+    hi, lo = C.c_void_p(), C.c_void_p()
+    rc = _lib.lib().b200lic_conv_staged_view(C.byref(d), op, _p(ws), nws, C.byref(hi), C.byref(lo))
+    if rc != 0 or not hi.value:
+        return None
+    return hi, lo
+
+
+def _wgrad(d, transposed, x, dy, dw, fwd_ws):
+    """dW through the tensor-core engine, reusing the forward's staged copy of x when there is one."""
+    op = _lib.OP_DECONV_WGRAD if transposed else _lib.OP_CONV_WGRAD
+    ws, nws = _workspace(d, op, dy.device)
+    st = _staged_x(d, _lib.OP_DECONV_FWD if transposed else _lib.OP_CONV_FWD, fwd_ws) if ws is not None else None
+    if st is not None:
+        call("conv_wgrad_staged", C.byref(d), int(transposed), st[0], st[1], _p(dy), _p(dw), _p(ws), nws)
+    else:
+        call("deconv_wgrad" if transposed else "conv_wgrad", C.byref(d), _p(x), _p(dy), _p(dw), _p(ws), nws)
 
 
 class _ConvFn(torch.autograd.Function):
@@ -305,7 +330,9 @@ class _ConvFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, stride, padding, act, slope, fixed_pt):
         x, w, bias = _c(x, "input"), _c(w, "weight"), _c(bias, "bias")
         d = conv_desc(x.shape, w.shape, stride, padding, act=act, slope=slope, fixed_pt=fixed_pt)
-        y = conv2d_raw(x, w, bias, d)
+        need_dw = ctx.needs_input_grad[1]
+        res = conv2d_raw(x, w, bias, d, want_ws=need_dw)
+        y, ctx.fwd_ws = res if need_dw else (res, (None, 0))
         ctx.d, ctx.act, ctx.slope = d, act, slope
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
         return y
@@ -323,8 +350,8 @@ class _ConvFn(torch.autograd.Function):
             call("conv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx), _p(ws), nws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            ws, nws = _workspace(ctx.d, _lib.OP_CONV_WGRAD, dy.device)
-            call("conv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw), _p(ws), nws)
+            _wgrad(ctx.d, False, x, dy, dw, ctx.fwd_ws)
+        ctx.fwd_ws = (None, 0)
         return dx, dw, None, None, None, None, None, None
 
 
@@ -333,7 +360,9 @@ class _DeconvFn(torch.autograd.Function):
     def forward(ctx, x, w, bias, stride, padding, output_padding, act, slope, fixed_pt):
         x, w, bias = _c(x, "input"), _c(w, "weight"), _c(bias, "bias")
         d = conv_desc(x.shape, w.shape, stride, padding, True, output_padding, act=act, slope=slope, fixed_pt=fixed_pt)
-        y = deconv2d_raw(x, w, bias, d)
+        need_dw = ctx.needs_input_grad[1]
+        res = deconv2d_raw(x, w, bias, d, want_ws=need_dw)
+        y, ctx.fwd_ws = res if need_dw else (res, (None, 0))
         ctx.d, ctx.act, ctx.slope = d, act, slope
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
         return y
@@ -351,8 +380,8 @@ class _DeconvFn(torch.autograd.Function):
             call("deconv_dgrad", C.byref(ctx.d), _p(dy), _p(w), _p(dx), _p(ws), nws)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
-            ws, nws = _workspace(ctx.d, _lib.OP_DECONV_WGRAD, dy.device)
-            call("deconv_wgrad", C.byref(ctx.d), _p(x), _p(dy), _p(dw), _p(ws), nws)
+            _wgrad(ctx.d, True, x, dy, dw, ctx.fwd_ws)
+        ctx.fwd_ws = (None, 0)
         return dx, dw, None, None, None, None, None, None, None
 
 
@@ -409,8 +438,10 @@ class _GdnFn(torch.autograd.Function):
         x, gamma_eff, beta_eff = _c(x), _c(gamma_eff), _c(beta_eff)
         d = gdn_desc(x.shape, inverse)
         need_bwd = any(ctx.needs_input_grad[:2])
-        res = conv2d_raw(x, gamma_eff, beta_eff, d, gdn_x=x, want_norm=need_bwd)
+        res, ctx.fwd_ws = conv2d_raw(x, gamma_eff, beta_eff, d, gdn_x=x, want_norm=need_bwd, want_ws=True)
         y, norm = res if need_bwd else (res, None)
+        if not ctx.needs_input_grad[1]:
+            ctx.fwd_ws = (None, 0)
         ctx.d, ctx.inverse = d, inverse
         ctx.save_for_backward(x, gamma_eff, norm)
         return y
@@ -428,8 +459,8 @@ class _GdnFn(torch.autograd.Function):
         dx = dgamma = None
         if ctx.needs_input_grad[1]:
             dgamma = torch.empty_like(gamma_eff)
-            ws, nws = _workspace(d, _lib.OP_CONV_WGRAD, x.device)
-            call("conv_wgrad", C.byref(d), _p(x), _p(d_norm), _p(dgamma), _p(ws), nws)   # in_square: sum d_norm * x^2
+            _wgrad(d, False, x, d_norm, dgamma, ctx.fwd_ws)                              # in_square: sum d_norm * x^2
+            ctx.fwd_ws = (None, 0)
         if need_dx:
             d.in_square = 0
             t = torch.empty_like(x)
