@@ -34,34 +34,48 @@ static inline size_t align1k(size_t v) { return (v + 1023) / 1024 * 1024; }
 
 // out[n, p = (ho, wo), k = (c, r, s)] = x[n, c, ho*st - pad + r, wo*st - pad + s] (0 outside / for k >= C*KH*KW),
 // written as split-bf16 hi / lo rows of Cpad channels.  One thread = one bf16x2 pair: writes are fully coalesced,
-// reads hit the (tiny) 3-channel tensor in L1/L2.
+// reads hit the (tiny) 3-channel tensor in L1/L2; the k -> (c, r, s) decode comes from a shared-memory table so the
+// inner loop has one integer division (pixel -> row, column).
+constexpr int kFoldMaxK = 256;
 __global__ void __launch_bounds__(256)
     im2col_split_kernel(const float* __restrict__ x, int C, int H, int W, int KH, int KW, int st, int pad, int Ho, int Wo,
                         int Cpad, size_t pairs_per_image, __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl) {
+  __shared__ int s_off[kFoldMaxK];     // c*H*W + r*W + s, or -1 for padding channels
+  __shared__ short s_r[kFoldMaxK], s_s[kFoldMaxK];
   const int n = blockIdx.y;
   const int KK = KH * KW, Kreal = C * KK, half = Cpad >> 1;
+  for (int k = threadIdx.x; k < Cpad; k += blockDim.x) {
+    if (k < Kreal) {
+      const int c = k / KK, rs = k - c * KK, r = rs / KW, s_ = rs - r * KW;
+      s_off[k] = (c * H + r) * W + s_;
+      s_r[k] = (short)r;
+      s_s[k] = (short)s_;
+    } else {
+      s_off[k] = -1;
+      s_r[k] = s_s[k] = 0;
+    }
+  }
+  __syncthreads();
   const float* xn = x + (size_t)n * C * H * W;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs_per_image; t += (size_t)gridDim.x * blockDim.x) {
     const int p = (int)(t / half), kp = (int)(t - (size_t)p * half);
     const int ho = p / Wo, wo = p - ho * Wo;
+    const int h0 = ho * st - pad, w0 = wo * st - pad;
+    const int base = h0 * W + w0;
     float v[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int k = 2 * kp + e;
-      float val = 0.f;
-      if (k < Kreal) {
-        const int c = k / KK, rs = k - c * KK, r = rs / KW, s_ = rs - r * KW;
-        const int hi = ho * st - pad + r, wi = wo * st - pad + s_;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = __ldg(xn + ((size_t)c * H + hi) * W + wi);
-      }
-      v[e] = val;
+      const int off = s_off[k];
+      const int hi = h0 + s_r[k], wi = w0 + s_s[k];
+      v[e] = (off >= 0 && hi >= 0 && hi < H && wi >= 0 && wi < W) ? __ldg(xn + base + off) : 0.f;
     }
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[0] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
+    const __nv_bfloat16 h0b = __float2bfloat16_rn(v[0]), h1b = __float2bfloat16_rn(v[1]);
+    const __nv_bfloat16 l0b = __float2bfloat16_rn(v[0] - __bfloat162float(h0b));
+    const __nv_bfloat16 l1b = __float2bfloat16_rn(v[1] - __bfloat162float(h1b));
     __nv_bfloat162 hv, lv;
-    hv.x = h0; hv.y = h1;
-    lv.x = l0; lv.y = l1;
+    hv.x = h0b; hv.y = h1b;
+    lv.x = l0b; lv.y = l1b;
     const size_t o = ((size_t)n * Ho * Wo + p) * Cpad + 2 * kp;
     *reinterpret_cast<__nv_bfloat162*>(xh + o) = hv;
     *reinterpret_cast<__nv_bfloat162*>(xl + o) = lv;
@@ -79,37 +93,59 @@ static int stage_im2col(const float* x, int N, int C, int H, int W, int KH, int 
 }
 
 // y[n, co, ho, wo] = act(bias[co] + sum over taps (r, s) that hit (ho, wo) of col[n, (co, r, s), h, w]),
-// h = (ho + pad - r) / st, w = (wo + pad - s) / st.
+// h = (ho + pad - r) / st, w = (wo + pad - s) / st.  One thread owns the st x st output block (a, b) -> (st*a + i, st*b + j):
+// every tap is read exactly once per block and reads are contiguous along b.
+constexpr int kMaxSt = 4;
 __global__ void __launch_bounds__(256)
     col2im_kernel(const float* __restrict__ col, const float* __restrict__ bias, int Cout, int H, int W, int KH, int KW,
-                  int st, int pad, int Ho, int Wo, size_t n_out, int act, float slope, int fixed_point,
+                  int st, int pad, int Ho, int Wo, int Ab, int Bb, size_t n_blocks, int act, float slope, int fixed_point,
                   float* __restrict__ y) {
   const int KK = KH * KW;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
-    const int wo = (int)(i % Wo);
-    const size_t t1 = i / Wo;
-    const int ho = (int)(t1 % Ho);
-    const size_t t2 = t1 / Ho;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_blocks; t += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(t % Bb);
+    const size_t t1 = t / Bb;
+    const int a = (int)(t1 % Ab);
+    const size_t t2 = t1 / Ab;
     const int co = (int)(t2 % Cout);
     const size_t n = t2 / Cout;
     const float* cn = col + (n * Cout + co) * (size_t)KK * H * W;
-    float acc = bias ? __ldg(bias + co) : 0.f;
-    for (int r = (ho + pad) % st; r < KH; r += st) {
-      const int hh = ho + pad - r;
-      if (hh < 0) break;
-      const int h = hh / st;
-      if (h >= H) continue;
-      for (int s_ = (wo + pad) % st; s_ < KW; s_ += st) {
-        const int ww = wo + pad - s_;
-        if (ww < 0) break;
-        const int w = ww / st;
-        if (w >= W) continue;
-        acc += __ldg(cn + ((size_t)(r * KW + s_) * H + h) * W + w);
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+    float acc[kMaxSt][kMaxSt];
+#pragma unroll
+    for (int i = 0; i < kMaxSt; ++i)
+#pragma unroll
+      for (int j = 0; j < kMaxSt; ++j) acc[i][j] = bv;
+    for (int r = 0; r < KH; ++r) {
+      // output row st*a + i receives tap r from input row h with st*h - pad + r = st*a + i
+      const int i = ((r - pad) % st + st) % st;
+      const int h = a - (r - pad - i) / st;
+      if (h < 0 || h >= H) continue;
+      for (int s_ = 0; s_ < KW; ++s_) {
+        const int j = ((s_ - pad) % st + st) % st;
+        const int w = b - (s_ - pad - j) / st;
+        if (w < 0 || w >= W) continue;
+        const float v = __ldg(cn + ((size_t)(r * KW + s_) * H + h) * W + w);
+#pragma unroll
+        for (int ii = 0; ii < kMaxSt; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < kMaxSt; ++jj)
+            if (ii == i && jj == j) acc[ii][jj] += v;
       }
     }
-    acc = apply_act(acc, act, slope);
-    if (fixed_point) acc = rintf(fminf(fmaxf(acc, -128.f), 128.f) * 256.f) * (1.f / 256.f);
-    y[i] = acc;
+    float* yn = y + (n * Cout + co) * (size_t)Ho * Wo;
+#pragma unroll
+    for (int i = 0; i < kMaxSt; ++i) {
+      const int ho = st * a + i;
+      if (i >= st || ho >= Ho) continue;
+#pragma unroll
+      for (int j = 0; j < kMaxSt; ++j) {
+        const int wo = st * b + j;
+        if (j >= st || wo >= Wo) continue;
+        float v = apply_act(acc[i][j], act, slope);
+        if (fixed_point) v = rintf(fminf(fmaxf(v, -128.f), 128.f) * 256.f) * (1.f / 256.f);
+        yn[(size_t)ho * Wo + wo] = v;
+      }
+    }
   }
 }
 
@@ -120,7 +156,7 @@ static inline bool fold_conv(const b200lic_conv_desc* d) {      // fold taps int
 }
 static inline bool fold_deconv(const b200lic_conv_desc* d) {    // fold taps into the OUTPUT channel axis
   const int KK = d->KH * d->KW;
-  return KK > 1 && d->Cout * KK <= kSmallK && !d->in_square && !d->gdn_mode;
+  return KK > 1 && d->Cout * KK <= kSmallK && d->stride <= kMaxSt && !d->in_square && !d->gdn_mode;
 }
 
 // ---- conv forward ---------------------------------------------------------------------------------------------------
@@ -198,9 +234,11 @@ int smallc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w
   int rc = tc2_launch(d->N, d->Cin, d->H, d->W, Cc, d->H, d->W, 1, 1, 1, 0, 0, 1LL, (long long)Cc, B200LIC_ACT_NONE, 0.f, 0,
                       0, 0, x, w, nullptr, nullptr, nullptr, col, base, inner, s, "deconv_fwd(tc, folded taps)");
   if (rc != B200LIC_OK) return rc;
-  const size_t n_out = (size_t)d->N * d->Cout * d->Ho * d->Wo;
-  col2im_kernel<<<grid_for(n_out, 256, 8), 256, 0, s>>>(col, bias, d->Cout, d->H, d->W, d->KH, d->KW, d->stride, d->pad,
-                                                        d->Ho, d->Wo, n_out, d->act, d->act_slope, d->fixed_point, y);
+  const int Ab = (d->Ho + d->stride - 1) / d->stride, Bb = (d->Wo + d->stride - 1) / d->stride;
+  const size_t n_blocks = (size_t)d->N * d->Cout * Ab * Bb;
+  col2im_kernel<<<grid_for(n_blocks, 256, 8), 256, 0, s>>>(col, bias, d->Cout, d->H, d->W, d->KH, d->KW, d->stride, d->pad,
+                                                           d->Ho, d->Wo, Ab, Bb, n_blocks, d->act, d->act_slope,
+                                                           d->fixed_point, y);
   B200_LAUNCH_CHECK("col2im_kernel");
   return B200LIC_OK;
 }

@@ -54,3 +54,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(d, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(d, f)
+
+
+def test_calib_sched_mirror_matches_header():
+    """The device-resident schedule struct: ctypes mirror == header field order, 16 bytes."""
+    import ctypes
+    import re
+    from rdo_ptq_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "b200lic.h")).read()
+    body = re.search(r"typedef struct \{([^}]*)\} b200lic_calib_sched;", src).group(1)
+    fields = re.findall(r"\b(?:int|float)\s+(\w+)\s*;", body)
+    assert fields == [f[0] for f in _lib.CalibSched._fields_]
+    assert ctypes.sizeof(_lib.CalibSched) == 16

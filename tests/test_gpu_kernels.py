@@ -363,3 +363,75 @@ def test_elementwise_helpers(ops, dev):
     big_q, big_f = torch.zeros(4, 100000), torch.ones(4, 100000)
     frac = ops.gather_mix(big_q.to(dev), big_f.to(dev), None, prob=0.5, seed=7).mean().item()
     assert abs(frac - 0.5) < 0.01
+
+
+# ------------------------------------------------------------------------------------------- full-size properties
+def test_small_channel_layers_full_size_cross_engine(ops, dev):
+    """The 3-channel ends of the codec at BASELINE size (768x512): folded-tap tensor-core path vs the exact-fp32 SIMT
+    engine, forward and weight gradient, for conv 3->192 5x5 s2 and transposed conv 192->3 5x5 s2."""
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(1, 3, 512, 768, generator=gen).to(dev)
+    w = (torch.randn(192, 3, 5, 5, generator=gen) * 0.1).to(dev)
+    b = torch.randn(192, generator=gen).to(dev)
+    res = {}
+    for eng in ("simt", "auto"):
+        ops.set_default_engine(eng)
+        xd, wd = x.clone().requires_grad_(False), w.clone().requires_grad_(True)
+        y = ops.conv2d(xd, wd, b, 2, 2)
+        y.backward(torch.ones_like(y) * 1e-3 + y.detach() * 1e-3)
+        res[eng] = (y.detach(), wd.grad.clone())
+    ops.set_default_engine("auto")
+    assert res["auto"][0].shape == (1, 192, 256, 384)
+    assert rel_err(res["auto"][0], res["simt"][0]) < 1e-4 and rel_err(res["auto"][1], res["simt"][1]) < 1e-4
+    z = torch.randn(1, 192, 256, 384, generator=gen).to(dev)
+    wt = (torch.randn(192, 3, 5, 5, generator=gen) * 0.05).to(dev)
+    bt = torch.randn(3, generator=gen).to(dev)
+    for eng in ("simt", "auto"):
+        ops.set_default_engine(eng)
+        wd = wt.clone().requires_grad_(True)
+        y = ops.conv_transpose2d(z, wd, bt, 2, 2, 1)
+        y.backward(y.detach() * 1e-3)
+        res[eng] = (y.detach(), wd.grad.clone())
+    ops.set_default_engine("auto")
+    assert res["auto"][0].shape == (1, 3, 512, 768)
+    assert rel_err(res["auto"][0], res["simt"][0]) < 1e-4 and rel_err(res["auto"][1], res["simt"][1]) < 1e-4
+
+
+def test_gdn_igdn_round_trip_full_size(ops, dev):
+    """IGDN(GDN(x)) with a diagonal gamma is the identity up to the norm mismatch: with gamma = g*I, beta = b,
+    gdn(x) = x / sqrt(b + g x^2) and igdn(y) = y * sqrt(b + g y^2); check both closed forms at [1,192,256,384]."""
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(1, 192, 256, 384, generator=gen).to(dev)
+    gam = (0.1 * torch.eye(192)).to(dev)
+    bet = torch.ones(192).to(dev)
+    y = ops.gdn(x, gam, bet, False)
+    assert rel_err(y, x / torch.sqrt(1 + 0.1 * x * x)) < 1e-5
+    xr = ops.gdn(y, gam, bet, True)
+    assert rel_err(xr, y * torch.sqrt(1 + 0.1 * y * y)) < 1e-5
+
+
+def test_entropy_kernels_full_size_properties(ops, dev):
+    """2K-shape latents (BASELINE config 5): the Gaussian likelihoods of all symbols of a pixel sum to 1, bits equal
+    the sum of -log2(lik), and the factorised kernel's table path equals its direct path bit for bit."""
+    gen = torch.Generator().manual_seed(13)
+    y = (torch.randn(1, 320, 96, 128, generator=gen) * 4).to(dev)
+    sc = (torch.rand(1, 320, 96, 128, generator=gen) * 3 + 0.05).to(dev)
+    mu = torch.randn(1, 320, 96, 128, generator=gen).to(dev)
+    yh, lik, bits = ops.gaussian_lik(y, sc, mu)
+    assert torch.equal(yh, torch.round(y - mu) + mu)
+    assert abs(bits.item() - (-torch.log2(lik.double()).sum().item())) < 1e-5 * lik.numel()
+    tot = torch.zeros_like(lik[..., :8, :8])                  # sum over the integer grid on a patch
+    for k in range(-60, 61):
+        _, l, _ = ops.gaussian_lik((mu + k)[..., :8, :8].contiguous(), sc[..., :8, :8].contiguous(),
+                                   mu[..., :8, :8].contiguous(), lik_bound=0.0)
+        tot += l
+    assert (tot - 1).abs().max().item() < 2e-5
+    from rdo_ptq_b200.codec import EntropyBottleneck
+    torch.manual_seed(3)
+    eb = EntropyBottleneck(192).eval().to(dev)
+    z = (torch.randn(2, 192, 24, 32, generator=gen) * 3).to(dev)
+    z[0, :, 0, 0] = 500.0                                       # far outside the symbol table: direct path
+    zh, l1 = eb(z)
+    zh2, l2 = eb(z[:, :, :23, :31].contiguous())                # odd plane size: scalar path
+    assert torch.equal(l1[:, :, :23, :31], l2) and torch.equal(zh[:, :, :23, :31], zh2)
+    assert (l1 >= 1e-9).all() and (l1 <= 1).all()

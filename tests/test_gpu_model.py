@@ -399,3 +399,28 @@ def test_layer_reconstruction_default_path_uses_graph_and_converges(dev):
     assert len(losses) == 3 and losses[-1]["rec"] < losses[0]["rec"]
     assert losses[-1]["round"] > 0.0 and losses[0]["round"] == 0.0 or losses[1]["round"] > 0.0
     assert layer.trained and not layer.weight_quantizer.soft_targets
+
+
+def test_graphed_evaluation_forward_equals_eager(dev):
+    """evaluate.GraphedForward replays the W8A8 forward as one CUDA graph: same x_hat / likelihoods / bits as eager."""
+    from rdo_ptq_b200 import evaluate as E
+    _, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2, bits=8)
+    for m in pqm.modules():
+        if hasattr(m, "trained"):
+            m.trained = True
+    pqm.set_quant_state(True, True)
+    imgs = [i.to(dev) for i in synth.synthetic_images(3, 128, 192)]
+    gf = E.GraphedForward(pqm)
+    for k, img in enumerate(imgs):
+        xp = E.pad(img, 64)
+        with torch.no_grad():
+            ref = pqm(xp)
+            ref_bits = E.total_bits(ref).item()
+        out, bits = gf(xp)                                        # call 0 eager, call 1 captures, call 2 replays
+        assert torch.equal(out["x_hat"], ref["x_hat"]), k
+        assert torch.equal(out["likelihoods"]["y"], ref["likelihoods"]["y"]), k
+        assert abs(bits.item() - ref_bits) < 1e-3 * abs(ref_bits) + 1e-3, k
+    assert len(gf.cache) == 1
+    res_g = E.evaluate(pqm, imgs, p=64, graph=True)
+    res_e = E.evaluate(pqm, imgs, p=64, graph=False)
+    assert abs(res_g["psnr"] - res_e["psnr"]) < 1e-6 and abs(res_g["bpp"] - res_e["bpp"]) < 1e-6
