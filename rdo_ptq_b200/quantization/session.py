@@ -95,6 +95,17 @@ def cache_all_units(qnn: QuantModel, cali: torch.Tensor, units, batch: int = 8, 
     return out
 
 
+class _FixedWeight(torch.nn.Module):
+    """Stand-in weight quantiser that returns a precomputed (nearest-rounded) weight: used by the streaming forwards."""
+
+    def __init__(self, w):
+        super().__init__()
+        self.w = w
+
+    def forward(self, _x):
+        return self.w
+
+
 class CalibrationSession:
     """All units' AdaRound problems side by side; `sweep()` = one fused iteration on every unit."""
 
@@ -105,18 +116,33 @@ class CalibrationSession:
                  n_streams: int = 3):
         self.qnn, self.batch_size, self.input_prob, self.seed = qnn, batch_size, input_prob, seed
         self.units = reconstruction_units(qnn)
-        self.host = host_caches
-        self.caches = cache_all_units(qnn, cali, self.units, batch=batch_size, to_host=host_caches)
+        dev = next(qnn.parameters()).device
+        self.dev = dev
+        # host_caches: False = caches in HBM; True = caches in pinned host memory, batch rows copied every iteration;
+        # "stream" = nothing cached: the calibration IMAGES stay in pinned host memory, each iteration copies its batch
+        # of images (6 MB for 8 patches) and recomputes every unit's (quant_in, fp_in, fp_out) on the device with two
+        # captured forwards (all-FP, and all weights nearest-rounded: the same definition the cached modes use).
+        self.stream = (host_caches == "stream")
+        self.host = bool(host_caches)
+        if self.stream:
+            self._cali_host = cali.detach().cpu().contiguous().pin_memory()
+            self._img = torch.empty((batch_size,) + tuple(cali.shape[1:]), device=dev)
+            self._img.copy_(self._cali_host[:batch_size])
+            self.caches = self._stream_setup()
+        else:
+            self.caches = cache_all_units(qnn, cali, self.units, batch=batch_size, to_host=bool(host_caches))
         qnn.set_quant_state(False, False)
         self.trainers = {}
         for n, u in self.units:
             u.set_quant_state(True, False)
             self.trainers[n] = UnitTrainer(u, iters, weight, b_range, warmup, p, task_p, lr=lr,
                                            process_group=process_group)
+        # all units' (rec, task, round) accumulators live in one [U, 3] buffer: one device->host read per report
+        self._loss_all = torch.zeros(len(self.units), 3, device=dev)
+        for i, (n, _) in enumerate(self.units):
+            self.trainers[n].loss_buf = self._loss_all[i]
         self.n_samples = cali.size(0)
         self.it = 0
-        dev = next(qnn.parameters()).device
-        self.dev = dev
         g = torch.Generator().manual_seed(seed)
         # pre-drawn batch picks (randperm rows), resident on the device: no host RNG inside the timed loop
         self._perm = torch.stack([torch.randperm(self.n_samples, generator=g)[:batch_size] for _ in range(PERM_ROWS)])
@@ -148,7 +174,11 @@ class CalibrationSession:
         self._since = 0
         self.h2d_bytes = 0
         self.replayed_launches = 0           # kernels launched by graph replays (not seen by the library's host counter)
-        if self.host:
+        if self.stream:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = self.caches                       # the hooked tensors of the streaming forwards (batch rows)
+            self._img_ready, self._img_used, self._fwd_graph, self._fwd_launches = torch.cuda.Event(), None, None, 0
+        elif self.host:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._stage, self._ready, self._consumed = {}, {}, {}
             for n, _ in self.units:
@@ -157,6 +187,97 @@ class CalibrationSession:
                                        (q_in, fp_in, fp_out))
                 self._ready[n] = torch.cuda.Event()
                 self._consumed[n] = None
+
+    # -- streaming mode: recompute the units' inputs / targets from the batch of images ------------------------------
+    def _stream_setup(self):
+        """Scale initialisation (main2.py:194-198), nearest-rounded weights frozen per QuantModule, and one eager
+        streaming forward so that self._stage_bufs exist (shapes, cost estimates)."""
+        qnn = self.qnn
+        qnn.eval()
+        qnn.set_quant_state(True, False)
+        with torch.no_grad():
+            qnn(self._img)                                   # first forward initialises every weight quantiser
+        self._fixed_w = {}
+        self._fwd_stream = torch.cuda.Stream(device=self.dev)
+        for m in qnn.modules():
+            if isinstance(m, QuantModule) and m.org_weight is not None:
+                with torch.no_grad():
+                    self._fixed_w[m] = m.weight_quantizer(m.weight).detach().clone()
+        return self._stream_forward()
+
+    @torch.no_grad()
+    def _stream_forward(self):
+        """All-FP pass (fp_in, fp_out of every unit) + pass with every weight nearest-rounded (quant_in) on self._img.
+        Returns {unit: (quant_in, fp_in, fp_out)}; tensors of block units are cloned (blocks may run in-place ops)."""
+        qnn, store = self.qnn, {n: [None, None, None] for n, _ in self.units}
+
+        def run(slot_in, slot_out):
+            hooks = []
+            for n, m in self.units:
+                clone = isinstance(m, BaseQuantBlock)
+
+                def hook(_m, inp, out, n=n, clone=clone):
+                    store[n][slot_in] = inp[0].detach().clone() if clone else inp[0].detach()
+                    if slot_out is not None:
+                        store[n][slot_out] = out.detach().clone() if clone else out.detach()
+                hooks.append(m.register_forward_hook(hook))
+            qnn(self._img)
+            for h in hooks:
+                h.remove()
+
+        states = [(m, m.use_weight_quant, m.use_act_quant) for m in qnn.modules()
+                  if isinstance(m, (QuantModule, BaseQuantBlock))]
+        # the two passes are independent: the quantised one runs on a forked stream (also inside graph capture), so the
+        # many 1-64 CTA layers of one pass fill the SMs the other leaves idle
+        cur = torch.cuda.current_stream()
+        fork = self._fwd_stream
+        fork.wait_stream(cur)
+        qnn.set_quant_state(False, False)
+        run(1, 2)
+        swapped = []
+        for m, w in self._fixed_w.items():                  # nearest-rounded weights, whatever quantiser is installed
+            swapped.append((m, m.weight_quantizer))
+            m.weight_quantizer = _FixedWeight(w)
+        qnn.set_quant_state(True, False)
+        with torch.cuda.stream(fork):
+            run(0, None)
+        cur.wait_stream(fork)
+        for m, q in swapped:
+            m.weight_quantizer = q
+        for m, w_, a_ in states:
+            m.use_weight_quant, m.use_act_quant = w_, a_
+        return {n: tuple(v) for n, v in store.items()}
+
+    def _stream_step(self, main):
+        """Copy this iteration's batch of images host->device (copy stream) and replay the two streaming forwards."""
+        idx = self._perm[self.it % PERM_ROWS].tolist()
+        with torch.cuda.stream(self._copy_stream):
+            if self._img_used is not None:
+                self._copy_stream.wait_event(self._img_used)
+            for b, i in enumerate(idx):
+                self._img[b].copy_(self._cali_host[i], non_blocking=True)
+            self.h2d_bytes += 4 * self._img.numel()
+            self._img_ready.record(self._copy_stream)
+        main.wait_event(self._img_ready)
+        if self.use_graph and self.it >= self.graph_warmup:
+            if self._fwd_graph is None:
+                torch.cuda.synchronize()
+                n0 = _lib.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._stage = self._stream_forward()
+                self._fwd_graph = g
+                self._fwd_launches = _lib.launch_count() - n0
+                self._captured_launches += self._fwd_launches
+                self._graphs.clear()                         # unit graphs must read the captured forward's buffers
+                self._tail_graphs.clear()
+            self._fwd_graph.replay()
+            self.replayed_launches += self._fwd_launches
+        else:
+            self._stage = self._stream_forward()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._img_used = ev
 
     # -- one unit, one iteration: the capturable bodies ---------------------------------------------------------------
     def _compute(self, j, name):
@@ -233,6 +354,8 @@ class CalibrationSession:
         main = torch.cuda.current_stream()
         ops.sched_tick(self.sched, *self._tick)
         graphed = self.use_graph and self.it >= self.graph_warmup
+        if self.stream:
+            self._stream_step(main)
         if graphed:
             for st in self._streams[1:]:
                 st.wait_stream(main)               # the schedule has been advanced
@@ -241,7 +364,7 @@ class CalibrationSession:
             if only is not None and n not in only:
                 continue
             st = (self._streams[self._sid[n]] if graphed else None) or main
-            if self.host:
+            if self.host and not self.stream:
                 self._upload(j, n)
                 st.wait_event(self._ready[n])
             if graphed:
@@ -259,7 +382,7 @@ class CalibrationSession:
                     self.replayed_launches += self._tail_launches[n]
             else:
                 self._body(j, n)
-            if self.host:
+            if self.host and not self.stream:
                 ev = torch.cuda.Event()
                 ev.record(st)
                 self._consumed[n] = ev
@@ -276,7 +399,15 @@ class CalibrationSession:
         return _lib.launch_count() + self.replayed_launches - self._captured_launches
 
     def losses(self):
-        out = {n: t.read_losses(max(self._since, 1)) for n, t in self.trainers.items()}
+        """Per-unit mean (rec, task, round, total) since the last call: ONE device->host copy of the [U, 3] buffer."""
+        vals = (self._loss_all / max(self._since, 1)).tolist()
+        self._loss_all.zero_()
+        out = {}
+        for (n, _), (rec, task, rnd) in zip(self.units, vals):
+            t = self.trainers[n]
+            if getattr(t, "_same", False):
+                task = rec
+            t.last = out[n] = dict(rec=rec, task=task, round=rnd, total=rec + task + rnd)
         self._since = 0
         return out
 

@@ -424,3 +424,30 @@ def test_graphed_evaluation_forward_equals_eager(dev):
     res_g = E.evaluate(pqm, imgs, p=64, graph=True)
     res_e = E.evaluate(pqm, imgs, p=64, graph=False)
     assert abs(res_g["psnr"] - res_e["psnr"]) < 1e-6 and abs(res_g["bpp"] - res_e["bpp"]) < 1e-6
+
+
+def test_streaming_session_matches_cached_session(dev):
+    """host_caches="stream" recomputes every unit's (quant_in, fp_in, fp_out) from the batch images with two captured
+    forwards; with a pool of exactly one batch the tensors must equal the cached ones and the sweeps must agree."""
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+
+    def run(mode):
+        _, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+        cal = cali[:2]                                              # pool == batch: every pick is a permutation of it
+        sess = CalibrationSession(pqm, cal if mode == "stream" else cal.to(dev), batch_size=2, iters=20,
+                                  host_caches=mode, input_prob=1.0, n_streams=2)
+        return sess
+
+    ss, sc = run("stream"), run(False)
+    for n in sc.caches:                                            # streamed tensors == cached tensors (same 2 samples)
+        for a, b in zip(ss.caches[n], sc.caches[n]):
+            assert torch.allclose(a, b, rtol=0, atol=0) or rel_err(a, b) < 1e-6, n
+    for _ in range(6):
+        ss.sweep()
+        sc.sweep()
+    torch.cuda.synchronize()
+    ls, lc = ss.losses(), sc.losses()
+    assert ss.h2d_bytes == 6 * 4 * 2 * 3 * 64 * 64 and ss._fwd_graph is not None
+    for n in lc:
+        # the batch is the whole pool in both runs, only its row order differs: the mean loss is order-independent
+        assert ls[n]["rec"] == pytest.approx(lc[n]["rec"], rel=2e-3, abs=1e-7), n
