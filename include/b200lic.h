@@ -107,6 +107,18 @@ B200LIC_API int b200lic_adaround_bwd_adam(const float* w, float* alpha, const fl
                               float eps, float grad_scale, float reg_weight, float reg_b, float* reg_loss,
                               float* d_alpha_out, b200lic_stream_t stream);
 
+/* Learned step size (LSQ-style): d loss / d delta[ch] from dL/dWq, i.e. the autograd of the fake-quant expression with
+ * delta as the leaf -- the option the reference keeps as commented-out code (TO quantizer.py:166-168,
+ * layer_opt.py:259-265, block_opt.py:254-266).
+ *   alpha == NULL (nearest, quantizer.py:175-177): d_delta[c] = grad_scale * sum d_wq * ((x_q - zp) - in_range * w/delta)
+ *   alpha != NULL (AdaRound, quantizer.py:437-449; soft selects h(alpha) or alpha >= 0): sum d_wq * (x_q - zp)
+ * d_delta may be NULL when the Adam moments exp_avg / exp_avg_sq ([ch], with step >= 1) are given: delta is then
+ * updated in place (clamped at 1e-8 like quantizer.py:292); zero_point stays fixed. */
+B200LIC_API int b200lic_lsq_delta_grad(const float* w, const float* alpha, float* delta, const float* zero_point,
+                           const float* d_wq, int outer, int ch, int inner, int n_levels, int soft, float grad_scale,
+                           float* d_delta, float* exp_avg, float* exp_avg_sq, int step, float lr, float beta1,
+                           float beta2, float eps, b200lic_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K8  activation quantisers.
  * replaces: TO quantizer.py:81-121 (Handle_Parameter/ActQuant: dynamic per-channel, 4-D NCHW),
@@ -137,6 +149,26 @@ B200LIC_API int b200lic_round_latent(const float* y, const float* means, size_t 
  * biases 3+3+3+3+1, factors 3+3+3+3 (raw, tanh applied inside).  medians: [C]. */
 B200LIC_API int b200lic_factorized_lik_fwd(const float* z, const float* params, const float* medians, int N, int C, int HW,
                                float lik_bound, float* z_hat, float* lik, float* bits, b200lic_stream_t stream);
+
+/* Backward of the two likelihood kernels for the rate term of RateDistortionLoss (TO losses/losses.py:20-28; the
+ * R + lambda*D task criterion the reference keeps commented out at layer_opt.py:146-148).
+ * Upstream gradient per element: g = g_lik[i] (may be NULL) + *g_bits (device scalar, may be NULL) * d(-log2 lik)/dlik;
+ * g_yhat / g_zhat (may be NULL) is the gradient arriving at the rounded latent.  LowerBound semantics of compressai:
+ * a gradient passes a bound iff value >= bound or the gradient is negative.
+ * ste == 0: compressai autograd (torch.round has zero gradient): d_y = 0, d_means = g_yhat, d_scales live.
+ * ste != 0: straight-through rounding (round_ste, TO quantizer.py:64-68, applied to y at layer_opt.py:69):
+ *           d_y = g_yhat + g*dlik/dv, d_means = -g*dlik/dv (v = y_hat - mu).
+ * d_scales / d_means use grad_batch_stride (so they can be the two halves of one [N,2C,H,W] gradient tensor);
+ * d_y may be NULL. */
+B200LIC_API int b200lic_gaussian_lik_bwd(const float* y_hat, const float* scales, const float* means, const float* g_lik,
+                             const float* g_bits, const float* g_yhat, int N, int C, int HW,
+                             long long param_batch_stride, long long grad_batch_stride, float scale_bound,
+                             float lik_bound, int ste, float* d_y, float* d_scales, float* d_means,
+                             b200lic_stream_t stream);
+/* d_z of the factorised prior (parameters are frozen in PTQ).  ste == 0 writes zeros. */
+B200LIC_API int b200lic_factorized_lik_bwd(const float* z_hat, const float* params, const float* medians,
+                               const float* g_lik, const float* g_bits, const float* g_zhat, int N, int C, int HW,
+                               float lik_bound, int ste, float* d_z, b200lic_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K11  losses.

@@ -112,9 +112,40 @@ class LossFunction:
         return rnd + rec + task
 
 
+class RDTask:
+    """The R + lambda*D task criterion the reference keeps commented out (layer_opt.py:146-148:
+    `criterion = RateDistortionLoss(...); task_loss = criterion(quant_net_out, cali_data)['loss']`), made runnable:
+    quant_net_out = the codec's forward continued from the unit's output through the not-yet-trained modules (the role
+    of fp_out, layer_opt.py:45-75, whose round_ste on y becomes straight-through rounding of both latents), and
+    losses.py:15-28 (MSE metric) on it.  `unit_path` is the unit's path inside the codec, e.g. "g_a.2"."""
+
+    def __init__(self, qnn: QuantModel, unit_path: str, cali_data, lmbda: float):
+        from .evalpath import rate_distortion_loss
+        self.rd = rate_distortion_loss
+        codec = qnn.model
+        coder, _, rest = unit_path.partition(".")
+        k = int(rest.split(".")[0])
+        self.codec, self.coder, self.lmbda = codec, coder, lmbda
+        self.tail = list(getattr(codec, coder).children())[k + 1:]
+        codec.entropy_bottleneck.ste_round = codec.gaussian_conditional.ste_round = True
+        with torch.no_grad():
+            y, z = codec.latents(cali_data)
+        self.ctx = {"x": cali_data, "y": y, "z": z}
+
+    def __call__(self, out, idx):
+        v = out
+        for m in self.tail:
+            v = m(v)
+        o = self.codec.forward_from(self.coder, v, {k: t[idx] for k, t in self.ctx.items()})
+        return self.rd(o, self.ctx["x"][idx], self.lmbda)["loss"]
+
+    def close(self):
+        self.codec.entropy_bottleneck.ste_round = self.codec.gaussian_conditional.ste_round = False
+
+
 def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data, batch_size=4, iters=20000,
                 weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5, act_quant=False, p=2.0, task_p=2.0,
-                plan: DrawPlan = None, trace=None):
+                plan: DrawPlan = None, trace=None, rd_task: RDTask = None):
     """layer_reconstruction (layer_opt.py:175-319) / block_reconstruction (block_opt.py:176-323).
     For compressai-style models `find_unquantized_module` returns [] so fp_out is the identity
     and the task term equals lp_loss(out_quant, fp_out, task_p)."""
@@ -149,13 +180,19 @@ def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data
             cur = torch.where(keep, cur, fp_in[idx])
         opt.zero_grad()
         out = unit(cur)
-        err = loss_fn(out, fp_out[idx], out, fp_out[idx])
+        if rd_task is not None:                         # task = R + lambda*D instead of lp(out, fp_out, task_p)
+            err = loss_fn(out, fp_out[idx], None, None)
+            task = rd_task(out, idx)
+            loss_fn.last["task"] = float(task.detach())
+            err = err + task
+        else:
+            err = loss_fn(out, fp_out[idx], out, fp_out[idx])
         err.backward()
         if trace is not None and it == 0:
             trace["grad0"] = [p_.grad.detach().clone() for p_ in params]
             trace["out0"] = out.detach().clone()
         opt.step()
-        losses.append(float(err))
+        losses.append(float(err.detach()))
     for m in mods:
         if m.org_weight is not None:
             m.weight_quantizer.soft_targets = False

@@ -74,14 +74,16 @@ def f_gdn(x, gamma, beta, inverse, gamma_reparam, beta_reparam):
 
 
 # ---------------------------------------------------------------------------- entropy models (a16, a17)
-def quantize_latent(inputs, mode, means=None):
-    """compressai EntropyModel.quantize (the reference carries a copy at TO quantizer.py:19-48)."""
+def quantize_latent(inputs, mode, means=None, ste=False):
+    """compressai EntropyModel.quantize (the reference carries a copy at TO quantizer.py:19-48).
+    `ste` (extension, not compressai): round_ste of TO quantizer.py:64-68 instead of torch.round -- the straight-through
+    rounding the reference applies to y in fp_out (layer_opt.py:69); forward values are identical."""
     if mode == "noise":
         return inputs + torch.empty_like(inputs).uniform_(-0.5, 0.5)
     out = inputs.clone()
     if means is not None:
         out -= means
-    out = torch.round(out)
+    out = (torch.round(out) - out).detach() + out if ste else torch.round(out)
     if mode == "dequantize":
         if means is not None:
             out += means
@@ -108,6 +110,11 @@ class EntropyBottleneck(nn.Module):
         self.quantiles = nn.Parameter(q.repeat(channels, 1, 1))
         t = np.log(2 / self.tail_mass - 1)
         self.register_buffer("target", torch.Tensor([-t, 0, t]))
+        self.ste_round = False
+
+    def likelihood_lower_bound(self, lik):
+        """compressai's LowerBound on the likelihood (applied functionally: no extra state_dict key)."""
+        return _LowerBoundFn.apply(lik, lik.new_tensor([self.likelihood_bound]))
 
     def _get_medians(self):
         return self.quantiles[:, :, 1:2]
@@ -134,15 +141,15 @@ class EntropyBottleneck(nn.Module):
         return torch.abs(self._logits_cumulative(self.quantiles, True) - self.target).sum()
 
     def quantize(self, inputs, mode, means=None):
-        return quantize_latent(inputs, mode, means)
+        return quantize_latent(inputs, mode, means, self.ste_round)
 
     def forward(self, x, training=None):
         training = self.training if training is None else training
         xp = x.transpose(0, 1).contiguous()
         shape = xp.shape
         v = xp.reshape(shape[0], 1, -1)
-        out = quantize_latent(v, "noise" if training else "dequantize", self._get_medians())
-        lik = torch.clamp_min(self._likelihood(out), self.likelihood_bound)
+        out = quantize_latent(v, "noise" if training else "dequantize", self._get_medians(), self.ste_round)
+        lik = self.likelihood_lower_bound(self._likelihood(out))
         out = out.reshape(shape).transpose(0, 1).contiguous()
         lik = lik.reshape(shape).transpose(0, 1).contiguous()
         return out, lik
@@ -153,9 +160,13 @@ class GaussianConditional(nn.Module):
         super().__init__()
         self.likelihood_bound = float(likelihood_bound)
         self.lower_bound_scale = LowerBound(scale_bound)
+        self.ste_round = False
+
+    def likelihood_lower_bound(self, lik):
+        return _LowerBoundFn.apply(lik, lik.new_tensor([self.likelihood_bound]))
 
     def quantize(self, inputs, mode, means=None):
-        return quantize_latent(inputs, mode, means)
+        return quantize_latent(inputs, mode, means, self.ste_round)
 
     @staticmethod
     def _standardized_cumulative(t):
@@ -168,8 +179,8 @@ class GaussianConditional(nn.Module):
 
     def forward(self, inputs, scales, means=None, training=None):
         training = self.training if training is None else training
-        out = quantize_latent(inputs, "noise" if training else "dequantize", means)
-        lik = torch.clamp_min(self._likelihood(out, scales, means), self.likelihood_bound)
+        out = quantize_latent(inputs, "noise" if training else "dequantize", means, self.ste_round)
+        lik = self.likelihood_lower_bound(self._likelihood(out, scales, means))
         return out, lik
 
 
@@ -294,6 +305,29 @@ class ScaleHyperprior(nn.Module):
         y_hat, y_lik = self.gaussian_conditional(y, scales)
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
+    # -- tail of the forward from one sub-network's output: what the (commented-out) R + lambda*D task criterion of
+    #    layer_opt.py:146-148 needs; restates the same graph as forward() --------------------------------------------
+    def _hyper_in(self, y):
+        return torch.abs(y)
+
+    def _gauss(self, y, params):
+        return self.gaussian_conditional(y, params, training=False)
+
+    def latents(self, x):
+        y = self.g_a(x)
+        return y, self.h_a(self._hyper_in(y))
+
+    def forward_from(self, coder, value, ctx=None):
+        ctx = ctx or {}
+        y = value if coder == "g_a" else ctx["y"]
+        z = self.h_a(self._hyper_in(y)) if coder == "g_a" else (value if coder == "h_a" else ctx["z"])
+        z_hat, z_lik = self.entropy_bottleneck(z, training=False)     # evaluation-mode rounding, whatever .training says
+        params = value if coder == "h_s" else self.h_s(z_hat)
+        y_hat, y_lik = self._gauss(y, params)
+        x_hat = value if coder == "g_s" else self.g_s(y_hat)
+        bits = -torch.log2(y_lik).sum() - torch.log2(z_lik).sum()
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "bits": bits}
+
 
 class MeanScaleHyperprior(ScaleHyperprior):
     """mbt2018-mean (BASELINE config 2)."""
@@ -312,6 +346,13 @@ class MeanScaleHyperprior(ScaleHyperprior):
         scales, means = self.h_s(z_hat).chunk(2, 1)
         y_hat, y_lik = self.gaussian_conditional(y, scales, means=means)
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+    def _hyper_in(self, y):
+        return y
+
+    def _gauss(self, y, params):
+        scales, means = params.chunk(2, 1)
+        return self.gaussian_conditional(y, scales, means=means, training=False)
 
 
 class Cheng2020Attention(nn.Module):

@@ -33,6 +33,9 @@ class EntropyBottleneck(nn.Module):
         t = np.log(2 / self.tail_mass - 1)
         self.register_buffer("target", torch.Tensor([-t, 0, t]))
         self.last_bits = None
+        # additive switch for the R + lambda*D task criterion: straight-through latent rounding (round_ste,
+        # quantizer.py:64-68) instead of compressai's zero-gradient torch.round; forward values are identical
+        self.ste_round = False
 
     def _get_medians(self):
         return self.quantiles[:, :, 1:2]
@@ -48,6 +51,8 @@ class EntropyBottleneck(nn.Module):
     def quantize(self, inputs, mode, means=None):
         if mode != "dequantize":
             raise NotImplementedError("only the evaluation-mode quantiser is on the hot path")
+        if self.ste_round and torch.is_grad_enabled() and inputs.requires_grad:
+            return ops.round_latent_ste(inputs, means)
         return ops.round_latent(inputs, means)
 
     def forward(self, x, training=None):
@@ -55,8 +60,12 @@ class EntropyBottleneck(nn.Module):
         if training:
             raise NotImplementedError("EntropyBottleneck: the additive-noise training path is not on the PTQ hot path "
                                       "(call .eval(); the reference evaluates under model.eval())")
-        z_hat, lik, bits = ops.factorized_lik(x, self.packed_params(), self._get_medians().detach().reshape(-1),
-                                              self.likelihood_bound)
+        if torch.is_grad_enabled() and x.requires_grad:
+            z_hat, lik, bits = ops.factorized_lik_fn(x, self.packed_params(), self._get_medians().detach().reshape(-1),
+                                                     self.likelihood_bound, self.ste_round)
+        else:
+            z_hat, lik, bits = ops.factorized_lik(x, self.packed_params(), self._get_medians().detach().reshape(-1),
+                                                  self.likelihood_bound)
         self.last_bits = bits
         return z_hat, lik
 
@@ -78,10 +87,13 @@ class GaussianConditional(nn.Module):
         self.scale_bound, self.likelihood_bound = float(scale_bound), float(likelihood_bound)
         self.lower_bound_scale = LowerBound(scale_bound)
         self.last_bits = None
+        self.ste_round = False           # see EntropyBottleneck.ste_round
 
     def quantize(self, inputs, mode, means=None):
         if mode != "dequantize":
             raise NotImplementedError("only the evaluation-mode quantiser is on the hot path")
+        if self.ste_round and torch.is_grad_enabled() and inputs.requires_grad:
+            return ops.round_latent_ste(inputs, means)
         return ops.round_latent(inputs, means)
 
     def forward(self, inputs, scales, means=None, training=None):
@@ -89,6 +101,11 @@ class GaussianConditional(nn.Module):
         if training:
             raise NotImplementedError("GaussianConditional: the additive-noise training path is not on the PTQ hot "
                                       "path (call .eval())")
-        y_hat, lik, bits = ops.gaussian_lik(inputs, scales, means, self.scale_bound, self.likelihood_bound)
+        if torch.is_grad_enabled() and (inputs.requires_grad or scales.requires_grad or
+                                        (means is not None and means.requires_grad)):
+            y_hat, lik, bits = ops.gaussian_lik_fn(inputs, scales, means, self.scale_bound, self.likelihood_bound,
+                                                   self.ste_round)
+        else:
+            y_hat, lik, bits = ops.gaussian_lik(inputs, scales, means, self.scale_bound, self.likelihood_bound)
         self.last_bits = bits
         return y_hat, lik

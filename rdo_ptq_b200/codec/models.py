@@ -34,6 +34,35 @@ class ScaleHyperprior(nn.Module):
         y_hat, y_lik = self.gaussian_conditional(y, scales)
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
+    # -- tail of the forward from the output of one sub-network (R + lambda*D task criterion of the calibration) -------
+    def _hyper_in(self, y):
+        return ops.abs_fn(y)
+
+    def _gauss(self, y, params):
+        return self.gaussian_conditional(y, params, training=False)
+
+    def latents(self, x):
+        """(y, z) of an image batch: the upstream context `forward_from` needs for units in h_a / h_s / g_s."""
+        y = self.g_a(x)
+        return y, self.h_a(self._hyper_in(y))
+
+    def forward_from(self, coder, value, ctx=None):
+        """Continue the forward with `value` standing in for the OUTPUT of sub-network `coder` ('g_a': y, 'h_a': z,
+        'h_s': the Gaussian parameters, 'g_s': x_hat); whatever lies upstream comes from ctx['y'] / ctx['z'].
+        Returns the usual dict plus 'bits' = sum(-log2 likelihood) over y and z as a (differentiable) device scalar."""
+        ctx = ctx or {}
+        if coder not in ("g_a", "h_a", "h_s", "g_s"):
+            raise NotImplementedError(f"forward_from: no tail defined after {coder!r}")
+        y = value if coder == "g_a" else ctx["y"]
+        z = self.h_a(self._hyper_in(y)) if coder == "g_a" else (value if coder == "h_a" else ctx["z"])
+        z_hat, z_lik = self.entropy_bottleneck(z, training=False)     # evaluation-mode rounding, whatever .training says
+        bits_z = self.entropy_bottleneck.last_bits
+        params = value if coder == "h_s" else self.h_s(z_hat)
+        y_hat, y_lik = self._gauss(y, params)
+        bits = ops.add_act_fn(self.gaussian_conditional.last_bits, bits_z)
+        x_hat = value if coder == "g_s" else self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "bits": bits}
+
 
 class MeanScaleHyperprior(ScaleHyperprior):
     def __init__(self, N=128, M=192):
@@ -50,6 +79,13 @@ class MeanScaleHyperprior(ScaleHyperprior):
         scales, means = self.h_s(z_hat).chunk(2, 1)           # strided views; K9 reads them in place
         y_hat, y_lik = self.gaussian_conditional(y, scales, means=means)
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
+
+    def _hyper_in(self, y):
+        return y
+
+    def _gauss(self, y, params):
+        scales, means = params.chunk(2, 1)
+        return self.gaussian_conditional(y, scales, means=means, training=False)
 
 
 class Cheng2020Attention(nn.Module):

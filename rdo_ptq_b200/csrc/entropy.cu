@@ -242,6 +242,167 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
+
+// ---- K9 backward -------------------------------------------------------------------------------------------
+// Gradient of the Gaussian-conditional likelihood (compressai autograd of GaussianConditional.forward in eval mode,
+// reached from nic_cvt.py:300-308) for the rate term of RateDistortionLoss (losses/losses.py:20-28).
+//   v = y_hat - mu, a = |v|, s = LowerBound(scale, 0.11), lik = LowerBound(Phi((.5-a)/s) - Phi((-.5-a)/s), 1e-9)
+//   dlik/da = (phi(u_lo) - phi(u_up)) / s,  dlik/ds = (phi(u_lo) u_lo - phi(u_up) u_up) / s,  u = (+-.5 - a)/s
+// upstream: g = g_lik[i] + g_bits * d(-log2 lik)/dlik.  LowerBound passes a gradient iff x >= bound or g < 0.
+// ste == 0: torch.round has zero gradient, so only d_scales (and d_means = g_yhat through the "+ means") are non-zero.
+// ste != 0: latent rounding is straight-through (round_ste of quantizer.py:64-68, as layer_opt.py:69 applies to y):
+//           d_y = g_yhat + g dlik/dv, d_means = -g dlik/dv.
+constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
+constexpr float kInvLn2 = 1.44269504088896340736f;
+
+__device__ __forceinline__ void gauss_bwd_one(float yh, float mu, float sc, float g_lik, float g_bits, float g_yh,
+                                              float scale_bound, float lik_bound, int ste, float& d_y, float& d_s,
+                                              float& d_m) {
+  const float v = __fsub_rn(yh, mu);
+  const float a = fabsf(v);
+  const float s = fmaxf(sc, scale_bound);
+  const float rs = __fdividef(1.f, s);
+  const float inv = kInvSqrt2 * rs;
+  const float u1 = (a - 0.5f) * inv, u2 = (a + 0.5f) * inv;            // same operands as the forward kernel
+  const float e1 = erfc_pos(fabsf(u1)), e2 = erfc_pos(u2);
+  const float E1 = u1 < 0.f ? 2.f - e1 : e1;
+  const float lik_raw = 0.5f * (E1 - e2);
+  const float lik = fmaxf(lik_raw, lik_bound);
+  float g = g_lik - g_bits * kInvLn2 * __fdividef(1.f, lik);
+  if (!(lik_raw >= lik_bound || g < 0.f)) g = 0.f;
+  const float up = (0.5f - a) * rs, lo = (-0.5f - a) * rs;
+  const float p_up = kInvSqrt2Pi * __expf(-0.5f * up * up), p_lo = kInvSqrt2Pi * __expf(-0.5f * lo * lo);
+  const float dl_da = (p_lo - p_up) * rs;
+  const float dl_ds = (p_lo * lo - p_up * up) * rs;
+  float ds = g * dl_ds;
+  if (!(sc >= scale_bound || ds < 0.f)) ds = 0.f;
+  d_s = ds;
+  const float sgn = v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f);
+  const float dv = g * dl_da * sgn;
+  if (ste) {
+    d_y = g_yh + dv;
+    d_m = -dv;
+  } else {
+    d_y = 0.f;
+    d_m = g_yh;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    gaussian_lik_bwd_kernel(const float* __restrict__ y_hat, const float* __restrict__ scales,
+                            const float* __restrict__ means, const float* __restrict__ g_lik,
+                            const float* __restrict__ g_bits, const float* __restrict__ g_yhat, int CHW, int chunks,
+                            long long pstride, long long gstride, float scale_bound, float lik_bound, int ste,
+                            float* __restrict__ d_y, float* __restrict__ d_scales, float* __restrict__ d_means) {
+  const int chunk = blockIdx.x % chunks, n = blockIdx.x / chunks;
+  const size_t ybase = (size_t)n * CHW, pbase = (size_t)n * (size_t)pstride, gbase = (size_t)n * (size_t)gstride;
+  const int beg = chunk * kChunkG, end = min(CHW, beg + kChunkG);
+  const float gb = g_bits ? __ldg(g_bits) : 0.f;
+  for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    const float mu = means ? __ldg(means + pbase + i) : 0.f;
+    float dy, ds, dm;
+    gauss_bwd_one(__ldg(y_hat + ybase + i), mu, __ldg(scales + pbase + i), g_lik ? __ldg(g_lik + ybase + i) : 0.f, gb,
+                  g_yhat ? __ldg(g_yhat + ybase + i) : 0.f, scale_bound, lik_bound, ste, dy, ds, dm);
+    if (d_y) d_y[ybase + i] = dy;
+    d_scales[gbase + i] = ds;
+    if (d_means) d_means[gbase + i] = dm;
+  }
+}
+
+// ---- K10 backward ------------------------------------------------------------------------------------------
+// d lik / d z_hat of the factorised prior by forward-mode differentiation of the per-channel cumulative network
+// (parameters are frozen during PTQ: only the latent receives a gradient, and only under straight-through rounding --
+// with torch.round the gradient of EntropyBottleneck.forward w.r.t. z is identically zero).
+__device__ __forceinline__ void logits_cumulative_jvp(const FactorizedParams& P, float v, float& c, float& dc) {
+  float l[3], d[3], t[3], td[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float u = P.m[k] * v + P.b[k];
+    const float th = tanhf(u);
+    l[k] = u + P.f[k] * th;
+    d[k] = P.m[k] * (1.f + P.f[k] * (1.f - th * th));
+  }
+#pragma unroll
+  for (int layer = 1; layer <= 3; ++layer) {
+    const float* M = P.m + 3 + 9 * (layer - 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float u = M[3 * k] * l[0] + M[3 * k + 1] * l[1] + M[3 * k + 2] * l[2] + P.b[3 * layer + k];
+      const float du = M[3 * k] * d[0] + M[3 * k + 1] * d[1] + M[3 * k + 2] * d[2];
+      const float th = tanhf(u);
+      t[k] = u + P.f[3 * layer + k] * th;
+      td[k] = du * (1.f + P.f[3 * layer + k] * (1.f - th * th));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      l[k] = t[k];
+      d[k] = td[k];
+    }
+  }
+  c = P.m[30] * l[0] + P.m[31] * l[1] + P.m[32] * l[2] + P.b[12];
+  dc = P.m[30] * d[0] + P.m[31] * d[1] + P.m[32] * d[2];
+}
+
+// returns raw (un-bounded) likelihood and its derivative w.r.t. the symbol value
+__device__ __noinline__ void factorized_grad_one(const FactorizedParams* P, float zh, float* lik_raw, float* dlik) {
+  float lo, dlo, up, dup;
+  logits_cumulative_jvp(*P, zh - 0.5f, lo, dlo);
+  logits_cumulative_jvp(*P, zh + 0.5f, up, dup);
+  const float sum = lo + up;
+  const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+  const float su = sigm(sgn * up), sl = sigm(sgn * lo);
+  const float diff = su - sl;
+  const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+  *lik_raw = fabsf(diff);
+  *dlik = sd * sgn * (su * (1.f - su) * dup - sl * (1.f - sl) * dlo);
+}
+
+__global__ void __launch_bounds__(256)
+    factorized_lik_bwd_kernel(const float* __restrict__ z_hat, const float* __restrict__ params,
+                              const float* __restrict__ medians, const float* __restrict__ g_lik,
+                              const float* __restrict__ g_bits, const float* __restrict__ g_zhat, int N, int C, int HW,
+                              int splits, float lik_bound, int ste, float* __restrict__ d_z) {
+  __shared__ FactorizedParams P;
+  __shared__ float t_lik[kTabN], t_dl[kTabN];
+  const int c = blockIdx.x % C, split = blockIdx.x / C;
+  if (threadIdx.x < 58) {
+    const float raw = __ldg(params + (size_t)c * 58 + threadIdx.x);
+    float v = raw;
+    if (threadIdx.x < 33) v = softplusf_(raw);
+    else if (threadIdx.x >= 46) v = tanhf(raw);
+    reinterpret_cast<float*>(&P)[threadIdx.x] = v;
+  }
+  __syncthreads();
+  const float med = __ldg(medians + c);
+  if (ste) {
+    for (int j = threadIdx.x; j < kTabN; j += blockDim.x)
+      factorized_grad_one(&P, __fadd_rn((float)(j - kTabR), med), &t_lik[j], &t_dl[j]);
+  }
+  __syncthreads();
+  const float gb = g_bits ? __ldg(g_bits) : 0.f;
+  for (int n = split; n < N; n += splits) {
+    const size_t base = ((size_t)n * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float out = 0.f;
+      if (ste) {
+        const float zh = __ldg(z_hat + base + i);
+        const float k = rintf(__fsub_rn(zh, med));
+        float lr, dl;
+        if (fabsf(k) <= (float)kTabR) {
+          lr = t_lik[(int)k + kTabR];
+          dl = t_dl[(int)k + kTabR];
+        } else {
+          factorized_grad_one(&P, zh, &lr, &dl);
+        }
+        float g = (g_lik ? __ldg(g_lik + base + i) : 0.f) - gb * kInvLn2 * __fdividef(1.f, fmaxf(lr, lik_bound));
+        if (!(lr >= lik_bound || g < 0.f)) g = 0.f;
+        out = g * dl + (g_zhat ? __ldg(g_zhat + base + i) : 0.f);
+      }
+      d_z[base + i] = out;
+    }
+  }
+}
+
 }  // namespace b200lic
 
 using namespace b200lic;
@@ -285,6 +446,41 @@ int b200lic_factorized_lik_fwd(const float* z, const float* params, const float*
   factorized_lik_kernel<<<(unsigned)(C * splits), 256, 0, as_stream(stream)>>>(z, params, medians, N, C, HW, splits,
                                                                                lik_bound, z_hat, lik, bits);
   B200_LAUNCH_CHECK("factorized_lik_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_gaussian_lik_bwd(const float* y_hat, const float* scales, const float* means, const float* g_lik,
+                             const float* g_bits, const float* g_yhat, int N, int C, int HW,
+                             long long param_batch_stride, long long grad_batch_stride, float scale_bound,
+                             float lik_bound, int ste, float* d_y, float* d_scales, float* d_means,
+                             b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(y_hat && scales && d_scales, "gaussian_lik_bwd: null pointer");
+  B200_REQUIRE(N > 0 && C > 0 && HW > 0, "gaussian_lik_bwd: bad shape (%d,%d,%d)", N, C, HW);
+  B200_REQUIRE(!means == !d_means, "gaussian_lik_bwd: means and d_means go together");
+  const long long chw = (long long)C * HW;
+  B200_REQUIRE(chw < 2147483647LL, "gaussian_lik_bwd: sample too large");
+  B200_REQUIRE(param_batch_stride >= chw && grad_batch_stride >= chw, "gaussian_lik_bwd: batch stride < C*HW");
+  const int chunks = (int)((chw + kChunkG - 1) / kChunkG);
+  gaussian_lik_bwd_kernel<<<(unsigned)(N * chunks), 256, 0, as_stream(stream)>>>(
+      y_hat, scales, means, g_lik, g_bits, g_yhat, (int)chw, chunks, param_batch_stride, grad_batch_stride, scale_bound,
+      lik_bound, ste, d_y, d_scales, d_means);
+  B200_LAUNCH_CHECK("gaussian_lik_bwd_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_factorized_lik_bwd(const float* z_hat, const float* params, const float* medians, const float* g_lik,
+                               const float* g_bits, const float* g_zhat, int N, int C, int HW, float lik_bound, int ste,
+                               float* d_z, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(z_hat && params && medians && d_z, "factorized_lik_bwd: null pointer");
+  B200_REQUIRE(N > 0 && C > 0 && HW > 0, "factorized_lik_bwd: bad shape (%d,%d,%d)", N, C, HW);
+  int splits = (4 * num_sms() + C - 1) / C;
+  if (splits > N) splits = N;
+  if (splits < 1) splits = 1;
+  factorized_lik_bwd_kernel<<<(unsigned)(C * splits), 256, 0, as_stream(stream)>>>(
+      z_hat, params, medians, g_lik, g_bits, g_zhat, N, C, HW, splits, lik_bound, ste, d_z);
+  B200_LAUNCH_CHECK("factorized_lik_bwd_kernel");
   return B200LIC_OK;
 }
 

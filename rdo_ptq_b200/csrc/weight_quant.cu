@@ -224,6 +224,60 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- learned step size (LSQ) ------------------------------------------------------------------------------
+// d loss / d delta[c] by the autograd of the fake-quant expressions with delta as the leaf (the reference keeps this
+// option as commented-out code: quantizer.py:166-168, layer_opt.py:259-265, block_opt.py:254-266):
+//   nearest (quantizer.py:175-177, x_int = round_ste(w/d) + zp):   d out/d d = (x_q - zp) - [0 <= x_int <= top] * w/d
+//   AdaRound (quantizer.py:437-449, x_int = floor(w/d) + h + zp):   d out/d d = (x_q - zp)        (floor: zero gradient)
+// One CTA per quantisation channel, fixed-order block reduction (deterministic), optional fused Adam step on delta.
+__global__ void __launch_bounds__(256)
+    lsq_delta_grad_kernel(const float* __restrict__ w, const float* __restrict__ alpha, float* __restrict__ delta,
+                          const float* __restrict__ zp, const float* __restrict__ d_wq, int outer, int ch, int inner,
+                          float top, int soft, float grad_scale, float* __restrict__ d_delta, float* __restrict__ m,
+                          float* __restrict__ v, AdamArgs ad) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  const float d = delta[c], z = __ldg(zp + c);
+  const size_t per_outer = (size_t)ch * inner, total = (size_t)outer * inner;
+  float acc = 0.f;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const size_t o = i / inner, k = i - o * inner;
+    const size_t e = o * per_outer + (size_t)c * inner + k;
+    const float t = __fdiv_rn(__ldg(w + e), d);
+    float term;
+    if (alpha == nullptr) {
+      const float xi = __fadd_rn(rintf(t), z);
+      const float xq = fminf(fmaxf(xi, 0.f), top);
+      term = __fsub_rn(xq, z);
+      if (xi >= 0.f && xi <= top) term = __fsub_rn(term, t);
+    } else {
+      const float a = __ldg(alpha + e);
+      float up;
+      if (soft) {
+        const float sg = __fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma);
+        up = fminf(fmaxf(sg, 0.f), 1.f);
+      } else {
+        up = a >= 0.f ? 1.f : 0.f;
+      }
+      const float xq = fminf(fmaxf(__fadd_rn(__fadd_rn(floorf(t), up), z), 0.f), top);
+      term = __fsub_rn(xq, z);
+    }
+    acc += __ldg(d_wq + e) * term;
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float g = grad_scale * tot;
+    if (d_delta) d_delta[c] = g;
+    if (m != nullptr) {
+      const float mi = ad.beta1 * m[c] + (1.f - ad.beta1) * g;
+      const float vi = ad.beta2 * v[c] + (1.f - ad.beta2) * g * g;
+      m[c] = mi;
+      v[c] = vi;
+      delta[c] = fmaxf(d - ad.lr_over_bc1 * (mi / (sqrtf(vi) * ad.inv_sqrt_bc2 + ad.eps)), 1e-8f);
+    }
+  }
+}
+
 static inline bool vec4_ok(size_t n, int inner, std::initializer_list<const void*> ptrs) {
   if ((inner & 3) != 0 || (n & 3) != 0) return false;
   for (const void* p : ptrs)
@@ -372,6 +426,28 @@ int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, const float* d
         w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
         reg_weight, 0.f, reg_loss, nullptr, sched);
   B200_LAUNCH_CHECK("adaround_bwd_adam_kernel(sched)");
+  return B200LIC_OK;
+}
+
+int b200lic_lsq_delta_grad(const float* w, const float* alpha, float* delta, const float* zero_point, const float* d_wq,
+                           int outer, int ch, int inner, int n_levels, int soft, float grad_scale, float* d_delta,
+                           float* exp_avg, float* exp_avg_sq, int step, float lr, float beta1, float beta2, float eps,
+                           b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && zero_point && d_wq, "lsq_delta_grad: null pointer");
+  B200_REQUIRE(outer > 0 && ch > 0 && inner > 0 && n_levels >= 2, "lsq_delta_grad: bad shape");
+  B200_REQUIRE((exp_avg && exp_avg_sq && step >= 1) || (!exp_avg && !exp_avg_sq && d_delta),
+               "lsq_delta_grad: pass both Adam moments and step >= 1, or neither together with d_delta");
+  AdamArgs ad{0.f, 0.f, beta1, beta2, eps};
+  if (exp_avg) {
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    ad.lr_over_bc1 = (float)((double)lr / bc1);
+    ad.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  }
+  lsq_delta_grad_kernel<<<ch, 256, 0, as_stream(stream)>>>(w, alpha, delta, zero_point, d_wq, outer, ch, inner,
+                                                           (float)(n_levels - 1), soft, grad_scale, d_delta, exp_avg,
+                                                           exp_avg_sq, ad);
+  B200_LAUNCH_CHECK("lsq_delta_grad_kernel");
   return B200LIC_OK;
 }
 

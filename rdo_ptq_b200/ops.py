@@ -196,6 +196,146 @@ def factorized_lik(z, packed_params, medians, lik_bound=1e-9, want_lik=True):
     return z_hat, lik, bits
 
 
+def _param_views(y, scales, means):
+    """scales / means may be the two halves of one [N,2C,H,W] tensor (chunk(2,1)): keep them strided when the rows of a
+    sample are contiguous, else materialise.  Returns (scales, means, param_batch_stride)."""
+    chw = y[0].numel()
+
+    def strided_ok(t):
+        return t.shape == y.shape and t.stride()[1:] == y.stride()[1:] and t.stride(0) >= chw
+
+    if means is not None and not (strided_ok(scales) and strided_ok(means) and scales.stride(0) == means.stride(0)):
+        scales, means = scales.contiguous(), means.contiguous()
+    elif means is None and not strided_ok(scales):
+        scales = scales.contiguous()
+    return scales, means, (scales.stride(0) if y.shape[0] > 1 else chw)
+
+
+class _GaussianLikFn(torch.autograd.Function):
+    """K9 with its backward (b200lic_gaussian_lik_bwd).  `ste`: straight-through latent rounding (round_ste) instead of
+    compressai's zero-gradient torch.round."""
+
+    @staticmethod
+    def forward(ctx, y, scales, means, scale_bound, lik_bound, ste):
+        y_hat, lik, bits = gaussian_lik(y, scales, means, scale_bound, lik_bound)
+        ctx.save_for_backward(y_hat, scales, means if means is not None else y_hat.new_empty(0))
+        ctx.cfg = (float(scale_bound), float(lik_bound), bool(ste), means is not None)
+        ctx.set_materialize_grads(False)
+        return y_hat, lik, bits
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik, g_bits):
+        y_hat, scales, means = ctx.saved_tensors
+        scale_bound, lik_bound, ste, has_means = ctx.cfg
+        means = means if has_means else None
+        scales, means, pstride = _param_views(y_hat, scales.detach(), None if means is None else means.detach())
+        N, Cc = y_hat.shape[0], y_hat.shape[1]
+        HW = y_hat.numel() // (N * Cc)
+        d_y = torch.empty_like(y_hat) if ctx.needs_input_grad[0] else None
+        d_s = torch.empty_like(y_hat)
+        d_m = torch.empty_like(y_hat) if has_means else None
+        g_yhat = None if g_yhat is None else _c(g_yhat)
+        g_lik = None if g_lik is None else _c(g_lik)
+        g_bits = None if g_bits is None else _c(g_bits.reshape(1))
+        call("gaussian_lik_bwd", _p(y_hat), _p(scales), _p(means), _p(g_lik), _p(g_bits), _p(g_yhat), N, Cc, HW,
+             pstride, Cc * HW, scale_bound, lik_bound, int(ste), _p(d_y), _p(d_s), _p(d_m))
+        return d_y, d_s, (d_m if ctx.needs_input_grad[2] else None), None, None, None
+
+
+def gaussian_lik_fn(y, scales, means=None, scale_bound=0.11, lik_bound=1e-9, ste=False):
+    """Differentiable (y_hat, lik, bits)."""
+    return _GaussianLikFn.apply(y, scales, means, scale_bound, lik_bound, ste)
+
+
+class _FactorizedLikFn(torch.autograd.Function):
+    """K10 with its latent gradient (b200lic_factorized_lik_bwd); the prior's parameters are frozen in PTQ."""
+
+    @staticmethod
+    def forward(ctx, z, packed_params, medians, lik_bound, ste):
+        z_hat, lik, bits = factorized_lik(z, packed_params, medians, lik_bound)
+        ctx.save_for_backward(z_hat, packed_params, medians)
+        ctx.cfg = (float(lik_bound), bool(ste))
+        ctx.set_materialize_grads(False)
+        return z_hat, lik, bits
+
+    @staticmethod
+    def backward(ctx, g_zhat, g_lik, g_bits):
+        z_hat, packed, med = ctx.saved_tensors
+        lik_bound, ste = ctx.cfg
+        N, Cc = z_hat.shape[0], z_hat.shape[1]
+        HW = z_hat.numel() // (N * Cc)
+        d_z = torch.empty_like(z_hat)
+        g_zhat = None if g_zhat is None else _c(g_zhat)
+        g_lik = None if g_lik is None else _c(g_lik)
+        g_bits = None if g_bits is None else _c(g_bits.reshape(1))
+        call("factorized_lik_bwd", _p(z_hat), _p(_c(packed)), _p(_c(med)), _p(g_lik), _p(g_bits), _p(g_zhat), N, Cc, HW,
+             lik_bound, int(ste), _p(d_z))
+        return d_z, None, None, None, None
+
+
+def factorized_lik_fn(z, packed_params, medians, lik_bound=1e-9, ste=False):
+    return _FactorizedLikFn.apply(z, packed_params, medians, lik_bound, ste)
+
+
+class _RoundLatentSTE(torch.autograd.Function):
+    """rint(y - mu) + mu with the straight-through gradient of round_ste (quantizer.py:64-68): d/dy = 1, d/dmu = 0."""
+
+    @staticmethod
+    def forward(ctx, y, means):
+        return round_latent(y, means)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def round_latent_ste(y, means=None):
+    return _RoundLatentSTE.apply(y, means)
+
+
+class _RDLossFn(torch.autograd.Function):
+    """RateDistortionLoss (losses/losses.py:20-28, MSE metric): loss = lmbda*255^2*mean((x_hat-x)^2) + bits/pixels.
+    One K11 pass yields the distortion value and its gradient; bits come from the likelihood kernels' reductions."""
+
+    @staticmethod
+    def forward(ctx, x_hat, target, bits, lmbda, pixels):
+        k = float(lmbda) * 255.0 ** 2 / x_hat.numel()
+        dist, g = lp_loss_fwd_bwd(x_hat, target, 2.0, scale=k, grad_scale=k)     # kernel applies p*|d|^(p-1)
+        ctx.save_for_backward(g)
+        ctx.inv_px = 1.0 / float(pixels)
+        return add_act(dist, bits.reshape(1) * ctx.inv_px).reshape(())
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (g,) = ctx.saved_tensors
+        return g * g_out, None, (g_out * ctx.inv_px).reshape(1), None, None
+
+
+def rd_loss(x_hat, target, bits, lmbda=1e-2, pixels=None):
+    """Differentiable R + lambda*D; `bits` = device scalar sum of -log2 likelihoods."""
+    N, _, H, W = target.shape
+    return _RDLossFn.apply(x_hat, target, bits, lmbda, N * H * W if pixels is None else pixels)
+
+
+def lsq_delta_grad(w, delta, zp, d_wq, axis, n_levels, alpha=None, soft=True, grad_scale=1.0, adam=None):
+    """Per-channel d loss / d delta from dL/dWq (learned step size).  adam = (exp_avg, exp_avg_sq, step, lr) updates
+    delta in place; returns d_delta ([ch], always written)."""
+    w, d_wq = _c(w, "w"), _c(d_wq, "d_wq")
+    outer, ch, inner = channel_view(w.shape, axis)
+    dflat = delta.view(-1)
+    if not dflat.is_contiguous() or dflat.numel() != ch:
+        raise ValueError("lsq_delta_grad: delta must hold one contiguous value per quantisation channel")
+    d_delta = torch.empty(ch, device=w.device, dtype=torch.float32)
+    m = v = None
+    step, lr = 0, 0.0
+    if adam is not None:
+        m, v, step, lr = adam
+    call("lsq_delta_grad", _p(w), _p(None if alpha is None else _c(alpha)), _p(dflat), _p(_c(zp.view(-1))), _p(d_wq),
+         outer, ch, inner, int(n_levels), int(bool(soft)), float(grad_scale), _p(d_delta), _p(m), _p(v), int(step),
+         float(lr), 0.9, 0.999, 1e-8)
+    return d_delta
+
+
 def lp_loss_fwd_bwd(pred, tgt, p=2.0, scale=1.0, grad_scale=None, loss=None, want_grad=True, pick=None):
     """loss += scale * sum|pred-tgt|^p ; returns (loss, d_pred).
     pick = (idx_table, units, unit, sched): `tgt` is a [samples, ...] cache and row b of `pred` is compared with
@@ -483,9 +623,10 @@ def gdn_reparam_fn(p, bound, pedestal):
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
-def add_act(a, b=None, act=ACT_NONE, slope=0.01):
+def add_act(a, b=None, act=ACT_NONE, slope=0.01, out=None):
     a = _c(a)
-    out = torch.empty_like(a)
+    if out is None:
+        out = torch.empty_like(a)
     call("add_act", _p(a), _p(_c(b)), a.numel(), act, slope, _p(out))
     return out
 
@@ -587,6 +728,25 @@ def abs_(x):
     out = torch.empty_like(x)
     call("abs", _p(x), x.numel(), _p(out))
     return out
+
+
+class _AbsFn(torch.autograd.Function):
+    """|x| with gradient sign(x)*g (the LeakyReLU-derivative kernel with slope -1; differs from torch.abs only at
+    exactly 0, where torch returns 0)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return abs_(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return act_bwd(x, g, ACT_LEAKY_RELU, -1.0)
+
+
+def abs_fn(x):
+    return _AbsFn.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else abs_(x)
 
 
 class _PixelShuffleFn(torch.autograd.Function):

@@ -10,7 +10,7 @@ from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule
 from .quant_model import QuantModel
 from .quantizer import StraightThrough
-from .recon import DrawPlan, UnitTrainer, run_reconstruction
+from .recon import DrawPlan, RDTask, UnitTrainer, run_reconstruction
 from .utils import save_inp_oup_data, set_mode
 
 
@@ -31,7 +31,23 @@ def find_unquantized_module(model: torch.nn.Module, _name_: str = "g_a", module_
 
 
 def _task_p(args, default=2.0):
-    return float(getattr(args, "task_loss", default)) if args is not None else default
+    v = getattr(args, "task_loss", default) if args is not None else default
+    return default if v == "rd" else float(v)
+
+
+def _rd_task(model, unit_path, cali_data, args, task, lmbda):
+    """`task='rd'` (or args.task_loss == 'rd'): the R + lambda*D task criterion (recon.RDTask); lambda from `lmbda` or
+    args.lmbda (main2.py's --lmbda)."""
+    if task is None and args is not None and getattr(args, "task_loss", None) == "rd":
+        task = "rd"
+    if task != "rd":
+        return None
+    if unit_path is None:
+        raise ValueError("task='rd' needs unit_path (the unit's path inside the codec, e.g. 'g_a.2')")
+    lm = lmbda if lmbda is not None else getattr(args, "lmbda", None)
+    if lm is None:
+        raise ValueError("task='rd' needs lmbda (or args.lmbda)")
+    return RDTask(model, unit_path, cali_data, lm)
 
 
 def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str, cali_data: torch.Tensor,
@@ -39,8 +55,11 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
                          asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
                          warmup: float = 0.0, input_prob: float = 1.0, act_quant: bool = False, lr: float = 4e-5,
                          p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None,
-                         log_every: int = 500, graph: bool = True, process_group=None):
-    """Same arguments as the reference; `plan` / `unit_id` / `trace` are additive (deterministic replays, tests).
+                         log_every: int = 500, graph: bool = True, process_group=None, task: str = None,
+                         lmbda: float = None, unit_path: str = None):
+    """Same arguments as the reference; `plan` / `unit_id` / `trace` are additive (deterministic replays, tests), and
+    so is `task='rd'` with `lmbda` / `unit_path`: the R + lambda*D task criterion instead of the reference's live
+    lp_loss(quant_out, fp_out, args.task_loss).
     As in the reference, `lr` is accepted and ignored: Adam runs at its default 1e-3 (layer_opt.py:254)."""
     if opt_mode != 'mse':
         raise NotImplementedError("only opt_mode='mse' is reachable in the reference (main2.py:225)")
@@ -64,7 +83,9 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
         org_act_func, layer.activation_function = layer.activation_function, StraightThrough()
     if layer.org_weight is None:                # PixelShuffle wrapper: nothing to learn (reference :245-246)
         return None
-    trainer = UnitTrainer(layer, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group)
+    rd = _rd_task(model, unit_path, cali_data, args, task, lmbda)
+    trainer = UnitTrainer(layer, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group,
+                          rd_task=rd)
     losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace,
                                 log_every=log_every, graph=graph)
     if org_act_func is not None:

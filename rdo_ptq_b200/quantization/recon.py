@@ -35,12 +35,50 @@ class DrawPlan:
         return idx, None, (self.seed * 2654435761 + unit_id * 40503 + it) & 0xFFFFFFFFFFFF
 
 
+class RDTask:
+    """Task criterion R + lambda*D (BASELINE north_star; the reference keeps it commented out at layer_opt.py:146-148 /
+    block_opt.py:145-147): the codec's forward is continued from the unit's output through the not-yet-trained modules
+    (the role of `fp_out`, layer_opt.py:45-75) and RateDistortionLoss (losses/losses.py:15-28, MSE metric) is evaluated
+    on it.  Both latents are rounded straight-through (round_ste, which fp_out applies to y at layer_opt.py:69), so the
+    rate term back-propagates through the likelihood kernels (b200lic_gaussian_lik_bwd / _factorized_lik_bwd) and the
+    distortion term through the dgrad kernels.  `unit_path` is the unit's path inside the codec, e.g. "g_a.2"."""
+
+    def __init__(self, qnn, unit_path: str, cali_data: torch.Tensor, lmbda: float, batch: int = 8):
+        codec = qnn.model
+        coder, _, rest = unit_path.partition(".")
+        if coder not in ("g_a", "h_a", "h_s", "g_s") or not hasattr(codec, "forward_from"):
+            raise NotImplementedError(f"RDTask: no forward tail defined after {unit_path!r}")
+        k = int(rest.split(".")[0])
+        self.codec, self.coder, self.lmbda = codec, coder, float(lmbda)
+        self.tail = list(getattr(codec, coder).children())[k + 1:]
+        codec.entropy_bottleneck.ste_round = codec.gaussian_conditional.ste_round = True
+        ys, zs = [], []
+        with torch.no_grad():
+            for i in range(0, cali_data.size(0), batch):
+                y, z = codec.latents(cali_data[i:i + batch])
+                ys.append(y)
+                zs.append(z)
+        self.ctx = {"x": cali_data, "y": torch.cat(ys), "z": torch.cat(zs)}
+
+    def __call__(self, out: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        v = out
+        for m in self.tail:
+            v = m(v)
+        ctx = {k: t[idx] for k, t in self.ctx.items()}          # batch rows: buffer plumbing
+        o = self.codec.forward_from(self.coder, v, ctx)
+        return ops.rd_loss(o["x_hat"], ctx["x"], o["bits"], self.lmbda)
+
+    def close(self):
+        self.codec.entropy_bottleneck.ste_round = self.codec.gaussian_conditional.ste_round = False
+
+
 class UnitTrainer:
     """State of one reconstruction problem: the QuantModules whose alpha is trained, Adam moments, schedules."""
 
     def __init__(self, unit, iters: int, weight: float, b_range, warmup: float, p: float, task_p: Optional[float],
-                 lr: float = 1e-3, process_group=None):
+                 lr: float = 1e-3, process_group=None, rd_task: Optional[RDTask] = None):
         self.unit = unit
+        self.rd_task = rd_task
         self.mods: List[QuantModule] = ([unit] if isinstance(unit, QuantModule) else
                                         [m for _, m in unit.named_modules() if isinstance(m, QuantModule)])
         self.mods = [m for m in self.mods if m.org_weight is not None]
@@ -68,17 +106,18 @@ class UnitTrainer:
         self.last = {}
 
     # -- one iteration ---------------------------------------------------------------------------------------
-    def step(self, cur_inp: torch.Tensor, tgt: torch.Tensor, trace: Optional[dict] = None, sched=None):
+    def step(self, cur_inp: torch.Tensor, tgt: torch.Tensor, trace: Optional[dict] = None, sched=None, idx=None):
         """One fused iteration.  With `sched` (a device-resident b200lic_calib_sched, already ticked for this
         iteration) no host scalar that changes between iterations enters a kernel argument, so the call sequence can be
-        captured once as a CUDA graph and replayed (session.py)."""
-        out, grads = self.step_compute(cur_inp, tgt)
+        captured once as a CUDA graph and replayed (session.py).  `idx` = the batch pick (the R + lambda*D task needs
+        the images and upstream latents of the same samples)."""
+        out, grads = self.step_compute(cur_inp, tgt, idx=idx)
         self.step_update(grads, trace=trace, sched=sched)
         if trace is not None:
             trace["out"] = out.detach()
         return out
 
-    def step_compute(self, cur_inp: torch.Tensor, tgt, tgt_pick=None):
+    def step_compute(self, cur_inp: torch.Tensor, tgt, tgt_pick=None, idx=None):
         """Soft weights -> unit forward -> loss value + dL/dout -> wgrad/dgrad.  Returns (out, [dL/dWq per module]).
         `tgt` is the target batch, or (with `tgt_pick = (idx_table, units, unit, sched)`) the whole cached-output tensor
         whose rows the loss kernel picks itself, so the target batch is never materialised."""
@@ -95,7 +134,15 @@ class UnitTrainer:
             # rec + task (with compressai-style names fp_out is the identity, so task == lp(out, tgt, task_p))
             denom = out.numel() // out.shape[1]
             rec = self.loss_buf[0:1]
-            if self.task_p is not None and float(self.task_p) == float(self.p):
+            if self.rd_task is not None:
+                # rec gradient from the loss kernel, task gradient by autograd through the codec's tail
+                _, d_out = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.p, scale=1.0 / denom, loss=rec)
+                task = self.rd_task(out, idx)
+                (g_task,) = torch.autograd.grad(task, out, retain_graph=True)
+                ops.add_act(self.loss_buf[1:2], task.detach().reshape(1), out=self.loss_buf[1:2])
+                d_out = ops.add_act(d_out, g_task)
+                same = False
+            elif self.task_p is not None and float(self.task_p) == float(self.p):
                 _, d_out = ops.lp_loss_fwd_bwd(out.detach(), tgt, self.p, scale=1.0 / denom, grad_scale=2.0 / denom,
                                                loss=rec, pick=tgt_pick)
                 same = True
@@ -166,6 +213,8 @@ class UnitTrainer:
         for m in marks:
             m.act_quantizer.is_training = False
             m.trained = True
+        if self.rd_task is not None:
+            self.rd_task.close()
 
 
 def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_size: int, input_prob: float,
@@ -191,18 +240,22 @@ def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_siz
         logging.info('Total loss:\t{:.3f} ( task:{:.3f}, rec:{:.3f}, round:{:.3f})\tb={:.2f}\tcount={}'.format(
             l["total"], l["task"], l["rec"], l["round"], trainer.temp_decay(cnt), cnt))
 
+    if plan is None and trainer.rd_task is not None:
+        plan = DrawPlan()                       # the rate-distortion tail is issued eagerly (autograd through the codec)
     if plan is not None:
         for it in range(trainer.iters):
             idx, mask, seed = plan.draw(unit_id, it, n, batch_size, q_in.shape[1:], input_prob, q_in.device)
             cur_inp = ops.gather_mix(q_in, fp_in, idx, prob=input_prob, seed=seed, mask=mask)
             tgt = ops.gather_mix(cached_outs, cached_outs, idx, prob=1.0)
-            trainer.step(cur_inp, tgt, trace=trace if (trace is not None and it == 0) else None)
+            trainer.step(cur_inp, tgt, trace=trace if (trace is not None and it == 0) else None, idx=idx)
             since += 1
             if trainer.count % log_every == 0 or it == trainer.iters - 1:
                 log(it)
         trainer.finish()
         return losses
 
+    if trainer.rd_task is not None:
+        raise NotImplementedError("the R + lambda*D task runs on the explicit-plan (eager) path")
     dev = q_in.device
     seed = DrawPlan().seed
     gen = torch.Generator(device=dev)

@@ -125,3 +125,41 @@ def test_oracle_calibration_reduces_reconstruction_error():
     losses = calib.reconstruct(q, layer, 0, "2", cali, batch_size=2, iters=100, weight=0.0, warmup=0.2, input_prob=1.0)
     assert layer.trained and not layer.weight_quantizer.soft_targets
     assert sum(losses[-10:]) < sum(losses[:10])
+
+
+def test_oracle_rate_gradients_match_finite_differences():
+    """The autograd the GPU backward kernels are checked against: d(-log2 lik)/d(scale) of the Gaussian conditional and
+    d(-log2 lik)/dz of the factorised prior under straight-through rounding, against central differences in fp64."""
+    torch.manual_seed(0)
+    gc = codec.GaussianConditional(None).eval().double()
+    y = torch.tensor([[[[0.3, -2.2, 4.1, 0.0]]]], dtype=torch.float64)
+    mu = torch.tensor([[[[0.1, 0.4, -0.3, 0.2]]]], dtype=torch.float64)
+    sc = torch.tensor([[[[0.5, 1.3, 2.0, 0.3]]]], dtype=torch.float64, requires_grad=True)
+
+    def bits(s):
+        return (-torch.log2(gc(y, s, means=mu)[1])).sum()
+    bits(sc).backward()
+    eps = 1e-6
+    for i in range(4):
+        d = torch.zeros_like(sc)
+        d[..., i] = eps
+        fd = (bits(sc.detach() + d) - bits(sc.detach() - d)) / (2 * eps)
+        assert abs(fd.item() - sc.grad[..., i].item()) < 1e-6 * max(1.0, abs(fd.item()))
+    eb = codec.EntropyBottleneck(3).eval().double()
+    with torch.no_grad():
+        for i in range(4):
+            getattr(eb, f"_factor{i}").normal_(0, 0.5)
+    eb.ste_round = True
+    z = (torch.randn(1, 3, 2, 2, dtype=torch.float64) * 3).requires_grad_(True)
+    (-torch.log2(eb(z)[1])).sum().backward()
+    # straight-through rounding: the gradient w.r.t. z equals the derivative of -log2 lik(v) at the SYMBOL v = z_hat
+    zh = eb(z)[0].detach()
+
+    def bits_at(v):
+        vv = v.transpose(0, 1).reshape(3, 1, -1)
+        return (-torch.log2(eb._likelihood(vv))).sum()
+    for idx in [(0, 0, 0, 0), (0, 1, 1, 0), (0, 2, 1, 1)]:
+        d = torch.zeros_like(zh)
+        d[idx] = eps
+        fd = (bits_at(zh + d) - bits_at(zh - d)) / (2 * eps)
+        assert abs(fd.item() - z.grad[idx].item()) < 1e-5 * max(1.0, abs(fd.item()))
