@@ -293,6 +293,12 @@ B200LIC_API int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, co
                                     int inner, int n_levels, const b200lic_calib_sched* sched, float beta1,
                                     float beta2, float eps, float grad_scale, float reg_weight, float* reg_loss,
                                     b200lic_stream_t stream);
+/* b200lic_lsq_delta_grad with the Adam step on delta driven by the schedule: lr = lr_scale * (the schedule's lr). */
+B200LIC_API int b200lic_lsq_delta_grad_sched(const float* w, const float* alpha, float* delta, const float* zero_point,
+                                 const float* d_wq, int outer, int ch, int inner, int n_levels, int soft,
+                                 float grad_scale, float* d_delta, float* exp_avg, float* exp_avg_sq,
+                                 const b200lic_calib_sched* sched, float lr_scale, float beta1, float beta2, float eps,
+                                 b200lic_stream_t stream);
 /* b200lic_gather_mix whose batch pick and QDrop seed follow the schedule: k = (sched->step - 1) * units + unit;
  * idx = idx_table[k % table_rows][0..rows) (idx_table NULL = identity rows); seed = (seed_base + k) mod 2^48. */
 B200LIC_API int b200lic_gather_mix_sched(const float* q, const float* fp, const long long* idx_table, int table_rows,

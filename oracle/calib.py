@@ -145,7 +145,8 @@ class RDTask:
 
 def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data, batch_size=4, iters=20000,
                 weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5, act_quant=False, p=2.0, task_p=2.0,
-                plan: DrawPlan = None, trace=None, rd_task: RDTask = None):
+                plan: DrawPlan = None, trace=None, rd_task: RDTask = None, learn_delta=False,
+                delta_lr_scale=0.1):
     """layer_reconstruction (layer_opt.py:175-319) / block_reconstruction (block_opt.py:176-323).
     For compressai-style models `find_unquantized_module` returns [] so fp_out is the identity
     and the task term equals lp_loss(out_quant, fp_out, task_p)."""
@@ -171,6 +172,15 @@ def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data
         trace["h0_all"] = [m.weight_quantizer.get_soft_targets().detach().clone() for m in mods if m.org_weight is not None]
         trace["h0"] = trace["h0_all"][0]
     opt = torch.optim.Adam(params)                      # lr 1e-3 (layer_opt.py:254)
+    deltas = []
+    if learn_delta:
+        # the option the reference keeps commented out (layer_opt.py:259-265): delta becomes a leaf with its own Adam
+        # group; autograd of quantizer.py:437-449 supplies d loss / d delta (floor() has zero gradient)
+        for m in mods:
+            if m.org_weight is not None:
+                m.weight_quantizer.delta = nn.Parameter(m.weight_quantizer.delta.detach().clone())
+                deltas.append(m.weight_quantizer.delta)
+        opt = torch.optim.Adam([{"params": params}, {"params": deltas, "lr": 1e-3 * delta_lr_scale}])
     loss_fn = LossFunction(unit, weight, iters, b_range, warmup, p, task_p)
     losses = []
     for it in range(iters):
@@ -191,7 +201,10 @@ def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data
         if trace is not None and it == 0:
             trace["grad0"] = [p_.grad.detach().clone() for p_ in params]
             trace["out0"] = out.detach().clone()
+            trace["d_delta0"] = [d.grad.detach().clone().reshape(-1) for d in deltas]
         opt.step()
+        for d in deltas:
+            d.data.clamp_(min=1e-8)
         losses.append(float(err.detach()))
     for m in mods:
         if m.org_weight is not None:

@@ -56,6 +56,7 @@ SIGNATURES = {
     "gaussian_lik_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _LL, _F, _F, _I, _P, _P, _P],
     "factorized_lik_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     "lsq_delta_grad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _F, _F, _F, _F],
+    "lsq_delta_grad_sched": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _F, _F, _F, _F],
     "lp_loss_fwd_bwd": [_P, _P, _SZ, _F, _F, _F, _P, _P],
     "lp_loss_fwd_bwd_sched": [_P, _P, _P, _I, _SZ, _SZ, _I, _I, _P, _F, _F, _F, _P, _P],
     "sq_err_sum": [_P, _P, _SZ, _P],

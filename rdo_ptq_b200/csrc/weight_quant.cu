@@ -234,9 +234,14 @@ __global__ void __launch_bounds__(256)
     lsq_delta_grad_kernel(const float* __restrict__ w, const float* __restrict__ alpha, float* __restrict__ delta,
                           const float* __restrict__ zp, const float* __restrict__ d_wq, int outer, int ch, int inner,
                           float top, int soft, float grad_scale, float* __restrict__ d_delta, float* __restrict__ m,
-                          float* __restrict__ v, AdamArgs ad) {
+                          float* __restrict__ v, AdamArgs ad, const b200lic_calib_sched* __restrict__ sched,
+                          float lr_scale) {
   __shared__ float red[32];
   const int c = blockIdx.x;
+  if (sched != nullptr) {  // CUDA-graph replay: bias corrections of this iteration come from device memory
+    ad.lr_over_bc1 = lr_scale * __ldg(&sched->lr_over_bc1);
+    ad.inv_sqrt_bc2 = __ldg(&sched->inv_sqrt_bc2);
+  }
   const float d = delta[c], z = __ldg(zp + c);
   const size_t per_outer = (size_t)ch * inner, total = (size_t)outer * inner;
   float acc = 0.f;
@@ -446,8 +451,24 @@ int b200lic_lsq_delta_grad(const float* w, const float* alpha, float* delta, con
   }
   lsq_delta_grad_kernel<<<ch, 256, 0, as_stream(stream)>>>(w, alpha, delta, zero_point, d_wq, outer, ch, inner,
                                                            (float)(n_levels - 1), soft, grad_scale, d_delta, exp_avg,
-                                                           exp_avg_sq, ad);
+                                                           exp_avg_sq, ad, nullptr, 1.f);
   B200_LAUNCH_CHECK("lsq_delta_grad_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_lsq_delta_grad_sched(const float* w, const float* alpha, float* delta, const float* zero_point,
+                                 const float* d_wq, int outer, int ch, int inner, int n_levels, int soft,
+                                 float grad_scale, float* d_delta, float* exp_avg, float* exp_avg_sq,
+                                 const b200lic_calib_sched* sched, float lr_scale, float beta1, float beta2, float eps,
+                                 b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && zero_point && d_wq && exp_avg && exp_avg_sq && sched, "lsq_delta_grad_sched: null pointer");
+  B200_REQUIRE(outer > 0 && ch > 0 && inner > 0 && n_levels >= 2, "lsq_delta_grad_sched: bad shape");
+  AdamArgs ad{0.f, 0.f, beta1, beta2, eps};
+  lsq_delta_grad_kernel<<<ch, 256, 0, as_stream(stream)>>>(w, alpha, delta, zero_point, d_wq, outer, ch, inner,
+                                                           (float)(n_levels - 1), soft, grad_scale, d_delta, exp_avg,
+                                                           exp_avg_sq, ad, sched, lr_scale);
+  B200_LAUNCH_CHECK("lsq_delta_grad_kernel(sched)");
   return B200LIC_OK;
 }
 

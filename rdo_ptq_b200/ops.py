@@ -317,9 +317,11 @@ def rd_loss(x_hat, target, bits, lmbda=1e-2, pixels=None):
     return _RDLossFn.apply(x_hat, target, bits, lmbda, N * H * W if pixels is None else pixels)
 
 
-def lsq_delta_grad(w, delta, zp, d_wq, axis, n_levels, alpha=None, soft=True, grad_scale=1.0, adam=None):
+def lsq_delta_grad(w, delta, zp, d_wq, axis, n_levels, alpha=None, soft=True, grad_scale=1.0, adam=None, sched=None,
+                   lr_scale=1.0):
     """Per-channel d loss / d delta from dL/dWq (learned step size).  adam = (exp_avg, exp_avg_sq, step, lr) updates
-    delta in place; returns d_delta ([ch], always written)."""
+    delta in place; with `sched` (device-resident schedule) adam = (exp_avg, exp_avg_sq) and lr = lr_scale * the
+    schedule's.  Returns d_delta ([ch], always written)."""
     w, d_wq = _c(w, "w"), _c(d_wq, "d_wq")
     outer, ch, inner = channel_view(w.shape, axis)
     dflat = delta.view(-1)
@@ -328,6 +330,12 @@ def lsq_delta_grad(w, delta, zp, d_wq, axis, n_levels, alpha=None, soft=True, gr
     d_delta = torch.empty(ch, device=w.device, dtype=torch.float32)
     m = v = None
     step, lr = 0, 0.0
+    if sched is not None:
+        m, v = adam[0], adam[1]
+        call("lsq_delta_grad_sched", _p(w), _p(None if alpha is None else _c(alpha)), _p(dflat), _p(_c(zp.view(-1))),
+             _p(d_wq), outer, ch, inner, int(n_levels), int(bool(soft)), float(grad_scale), _p(d_delta), _p(m), _p(v),
+             _p(sched), float(lr_scale), 0.9, 0.999, 1e-8)
+        return d_delta
     if adam is not None:
         m, v, step, lr = adam
     call("lsq_delta_grad", _p(w), _p(None if alpha is None else _c(alpha)), _p(dflat), _p(_c(zp.view(-1))), _p(d_wq),

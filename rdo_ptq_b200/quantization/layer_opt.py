@@ -56,7 +56,7 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
                          warmup: float = 0.0, input_prob: float = 1.0, act_quant: bool = False, lr: float = 4e-5,
                          p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None,
                          log_every: int = 500, graph: bool = True, process_group=None, task: str = None,
-                         lmbda: float = None, unit_path: str = None):
+                         lmbda: float = None, unit_path: str = None, learn_delta: bool = False):
     """Same arguments as the reference; `plan` / `unit_id` / `trace` are additive (deterministic replays, tests), and
     so is `task='rd'` with `lmbda` / `unit_path`: the R + lambda*D task criterion instead of the reference's live
     lp_loss(quant_out, fp_out, args.task_loss).
@@ -85,7 +85,7 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
         return None
     rd = _rd_task(model, unit_path, cali_data, args, task, lmbda)
     trainer = UnitTrainer(layer, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group,
-                          rd_task=rd)
+                          rd_task=rd, learn_delta=learn_delta)
     losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace,
                                 log_every=log_every, graph=graph)
     if org_act_func is not None:

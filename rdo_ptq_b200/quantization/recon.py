@@ -76,9 +76,13 @@ class UnitTrainer:
     """State of one reconstruction problem: the QuantModules whose alpha is trained, Adam moments, schedules."""
 
     def __init__(self, unit, iters: int, weight: float, b_range, warmup: float, p: float, task_p: Optional[float],
-                 lr: float = 1e-3, process_group=None, rd_task: Optional[RDTask] = None):
+                 lr: float = 1e-3, process_group=None, rd_task: Optional[RDTask] = None, learn_delta: bool = False,
+                 delta_lr_scale: float = 0.1):
         self.unit = unit
         self.rd_task = rd_task
+        # learned per-channel step sizes (LSQ-style; the reference keeps the option as commented-out code,
+        # layer_opt.py:259-265, SURVEY Q7): delta gets its own fused Adam at delta_lr_scale * lr, zero_point stays fixed
+        self.learn_delta, self.delta_lr_scale = learn_delta, delta_lr_scale
         self.mods: List[QuantModule] = ([unit] if isinstance(unit, QuantModule) else
                                         [m for _, m in unit.named_modules() if isinstance(m, QuantModule)])
         self.mods = [m for m in self.mods if m.org_weight is not None]
@@ -101,6 +105,11 @@ class UnitTrainer:
             p.requires_grad_(False)
         self.exp_avg = [torch.zeros_like(m.weight_quantizer.alpha.data) for m in self.mods]
         self.exp_avg_sq = [torch.zeros_like(m.weight_quantizer.alpha.data) for m in self.mods]
+        if learn_delta:
+            for m in self.mods:        # own storage: the AdaRound quantiser shares delta with the quantiser it wraps
+                m.weight_quantizer.delta = m.weight_quantizer.delta.clone().contiguous()
+            self.d_exp_avg = [torch.zeros(m.weight_quantizer.delta.numel(), device=m.weight.device) for m in self.mods]
+            self.d_exp_avg_sq = [torch.zeros_like(t) for t in self.d_exp_avg]
         dev = self.mods[0].weight.device if self.mods else None
         self.loss_buf = torch.zeros(3, device=dev)      # [rec, task, round] accumulated since the last read
         self.last = {}
@@ -178,6 +187,19 @@ class UnitTrainer:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
         for i, m in enumerate(self.mods):
             q = m.weight_quantizer
+            if self.learn_delta:        # before the alpha step: both gradients belong to the same (alpha, delta) point
+                if sched is not None:
+                    ops.lsq_delta_grad(m.weight.data, q.delta, q.zero_point, grads[i], q.axis, q.n_levels,
+                                       alpha=q.alpha.data, soft=True, grad_scale=1.0 / self.world,
+                                       adam=(self.d_exp_avg[i], self.d_exp_avg_sq[i]), sched=sched,
+                                       lr_scale=self.delta_lr_scale)
+                else:
+                    d_delta = ops.lsq_delta_grad(m.weight.data, q.delta, q.zero_point, grads[i], q.axis, q.n_levels,
+                                                 alpha=q.alpha.data, soft=True, grad_scale=1.0 / self.world,
+                                                 adam=(self.d_exp_avg[i], self.d_exp_avg_sq[i], self.count,
+                                                       self.lr * self.delta_lr_scale))
+                    if trace is not None:
+                        trace.setdefault("d_delta", []).append(d_delta)
             if sched is not None:
                 ops.adaround_bwd_adam_sched(m.weight.data, q.alpha.data, q.delta, q.zero_point, grads[i],
                                             self.exp_avg[i], self.exp_avg_sq[i], q.axis, q.n_levels, sched,

@@ -113,7 +113,7 @@ class CalibrationSession:
                  weight: float = 0.01, b_range=(20, 2), warmup: float = 0.2, input_prob: float = 0.5, p: float = 2.0,
                  task_p: float = 2.0, host_caches: bool = False, seed: int = 1005, graph: bool = True,
                  graph_warmup: int = 2, lr: float = 1e-3, process_group=None, overlap_update: bool = True,
-                 n_streams: int = 3):
+                 n_streams: int = 3, learn_delta: bool = False):
         self.qnn, self.batch_size, self.input_prob, self.seed = qnn, batch_size, input_prob, seed
         self.units = reconstruction_units(qnn)
         dev = next(qnn.parameters()).device
@@ -136,7 +136,7 @@ class CalibrationSession:
         for n, u in self.units:
             u.set_quant_state(True, False)
             self.trainers[n] = UnitTrainer(u, iters, weight, b_range, warmup, p, task_p, lr=lr,
-                                           process_group=process_group)
+                                           process_group=process_group, learn_delta=learn_delta)
         # all units' (rec, task, round) accumulators live in one [U, 3] buffer: one device->host read per report
         self._loss_all = torch.zeros(len(self.units), 3, device=dev)
         for i, (n, _) in enumerate(self.units):

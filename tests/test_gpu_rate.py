@@ -211,3 +211,52 @@ def test_layer_reconstruction_with_rd_task(dev, layer_path):
     a_ref, a_gpu = olayer.weight_quantizer.alpha.data, player.weight_quantizer.alpha.data.cpu()
     assert (a_ref - a_gpu)[inner].abs().max().item() < 5e-3
     assert not pqm.model.entropy_bottleneck.ste_round and not pqm.model.gaussian_conditional.ste_round
+
+
+@pytest.mark.parametrize("layer_path", ["g_a.2", "g_s.2"])
+def test_layer_reconstruction_with_learned_step_size(dev, layer_path):
+    """AdaRound + learned per-channel delta (the option the reference keeps commented out, layer_opt.py:259-265):
+    first-iteration d loss / d delta and the delta / alpha trajectories against the oracle loop."""
+    oqm, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+    sub, idx = layer_path.split(".")
+    olayer, player = getattr(oqm.model, sub)[int(idx)], getattr(pqm.model, sub)[int(idx)]
+    kw = dict(batch_size=2, iters=12, weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5)
+    otrace, ptrace = {}, {}
+    ocalib.reconstruct(oqm, olayer, 3, idx, cali, plan=ocalib.DrawPlan(), trace=otrace, learn_delta=True, **kw)
+
+    class Args:
+        task_loss = 2.0
+    delta_before = player.weight_quantizer.delta.clone()
+    Q.layer_reconstruction(pqm, player, idx, cali.to(dev), asym=True, act_quant=False, opt_mode='mse', args=Args(),
+                           plan=ReplayPlan(), unit_id=3, trace=ptrace, learn_delta=True, **kw)
+    assert rel_err(ptrace["d_delta"][0], otrace["d_delta0"][0]) < 1e-3
+    d_ref = olayer.weight_quantizer.delta.detach().reshape(-1)
+    d_gpu = player.weight_quantizer.delta.reshape(-1).cpu()
+    moved = (d_gpu - delta_before.reshape(-1).cpu()).abs().max().item()
+    assert moved > 0.0                                                     # delta was actually trained
+    # Adam moves delta by ~lr_delta = 1e-4 per step whatever the gradient's size, and floor(w/delta) makes the loss
+    # piecewise in delta: a channel whose tiny gradient flips sign once ends two steps apart.  Bar: every channel within
+    # two steps, the typical channel within a hundredth of a step.
+    diff = (d_gpu - d_ref).abs()
+    assert diff.max().item() < 2.5e-4 and diff.median().item() < 1e-6, (diff.max().item(), diff.median().item())
+    h0 = otrace["h0"]
+    inner = (h0 > 1e-4) & (h0 < 1 - 1e-4)
+    a_ref, a_gpu = olayer.weight_quantizer.alpha.data, player.weight_quantizer.alpha.data.cpu()
+    assert (a_ref - a_gpu)[inner].abs().max().item() < 5e-3
+
+
+def test_session_with_learned_step_size_graph_matches_eager(dev):
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+
+    def run(graph):
+        _, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+        sess = CalibrationSession(pqm, cali.to(dev), batch_size=2, iters=20, graph=graph, learn_delta=True)
+        for _ in range(6):
+            sess.sweep()
+        torch.cuda.synchronize()
+        return {n: [m.weight_quantizer.delta.clone() for m in t.mods] for n, t in sess.trainers.items()}
+
+    de, dg = run(False), run(True)
+    for n in de:
+        for a, b in zip(de[n], dg[n]):
+            assert rel_err(b, a) < 1e-4, n
