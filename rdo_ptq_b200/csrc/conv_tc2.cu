@@ -66,6 +66,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -98,6 +105,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
       : "r"(addr)
       : "memory");
 }
+// One lane of a converged warp, chosen by the hardware: unlike `lane == 0`, a branch on elect.sync tells the compiler
+// that exactly one thread is active, so TMA / tcgen05 operands go straight to uniform registers (with `lane == 0` every
+// UTMALDG / UTCHMMA was wrapped in a ~20-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY loop that paced the K loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -118,6 +138,35 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   return d;
 }
 
+// The MMAs of one K block as straight-line code.  The single issuing thread is a dependent scalar instruction stream:
+// with run-time loop bounds (pixel tiles, chains) and descriptors rebuilt per MMA it spent ~190 cycles per tcgen05.mma
+// -- twice the tensor pipe's own 96 cycles at N = 192 and the whole cost at small N (profiles/README.md r1d: the
+// MMA-only K loop took 580 ns per K block whether N was 16 or 192).  Here everything that depends on the stage is one
+// 64-bit add per descriptor (shared-memory descriptors advance by bytes >> 4) and the accumulator addresses are
+// computed once per work item.
+//   a0: descriptor of pixel tile 0's hi slice in this stage (lo = + kA2Bytes >> 4, next tile = + 2 * kA2Bytes >> 4)
+//   b0: descriptor of the weight hi slice in this stage (lo = + b_lo_off)
+//   acc[mt * CHAINS + chain]: TMEM address of each accumulator tile
+template <int MT, int CHAINS>
+__device__ __forceinline__ void issue_kblock(uint64_t a0, uint64_t b0, uint64_t b_lo_off, const uint32_t* acc,
+                                             uint32_t idesc, bool first) {
+  constexpr uint64_t kALo = (128 * 64) >> 4, kATile = (2 * 128 * 64) >> 4;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {            // 2 x UMMA_K(16) = 32 channels; +32 B per step inside the 64 B swizzle row
+    const uint64_t o = (uint64_t)(k * 2);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) { // hi*hi, hi*lo, lo*hi
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {    // consecutive MMAs never target the same accumulator tile
+        const uint64_t ad = a0 + (uint64_t)mt * kATile + (pass == 2 ? kALo : 0) + o;
+        const uint64_t bd = b0 + (pass == 1 ? b_lo_off : 0) + o;
+        const uint32_t accum = (first && k == 0 && pass < CHAINS) ? 0u : 1u;
+        umma_bf16(acc[mt * CHAINS + (pass % CHAINS)], ad, bd, idesc, accum);
+      }
+    }
+  }
+}
+
 }  // namespace v2
 
 struct Tc2Geom {
@@ -128,6 +177,7 @@ struct Tc2Geom {
   int BN, n_tiles;            // output-channel tile and their count
   int MT, m_groups, phases;   // pixel tiles per work item, groups of the largest phase, sub-pixel phases
   int stages, acc_sets, tmem_cols;
+  int chains;                 // independent accumulator chains per pixel tile (summed in the epilogue)
   int act;
   float slope;
   int gdn_mode, fixed_point;
@@ -224,11 +274,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 
   const int cblocks = g.Cpad >> 5;
   const int total_items = g.phases * g.n_tiles * g.m_groups;
-  const int set_cols = g.MT * g.BN;
+  const int set_cols = g.MT * g.chains * g.BN;
 
   if (warp == 0) {
     // ===== TMA producer ===============================================================================================
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ah)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bh)) : "memory");
       int s = 0;
@@ -251,10 +301,9 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           hb[t] = th * g.BH * q.in_step + q.base_h;
           nb[t] = tn * g.BI;
         }
+        int cb = 0, i = 0, j = 0;          // channel block, tap row, tap column of K block kb (no divisions in the loop)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8u * s, sphase ^ 1u);
-          const int t = kb / cblocks, cb = kb - t * cblocks;
-          const int i = t / q.KWp, j = t - i * q.KWp;
           const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t fb = full_bar + 8u * s;
           if (g.dbg_mode == 2) {
@@ -266,30 +315,46 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             continue;
           }
           mbar_expect_tx(fb, stage_bytes);
+          // One TMA instruction per operand tile PAIR: the hi and lo slices are two slabs of one workspace, so a tensor
+          // map with an outermost dimension of extent 2 (stride = slab bytes) lands [hi tile | lo tile] in consecutive
+          // shared memory -- the layout the MMA descriptors already expect.  The TMA unit's cost here is per
+          // instruction, not per byte (scripts/probes/tma_probe.cu on B200: ~113 ns per 128-row box, ~135 ns per
+          // 256-row box, whatever the row length), and with four / six instructions per K block the producer, not the
+          // tensor pipe, paced the main loop (profiles/README.md, r1d).
           for (int mt = 0; mt < g.MT; ++mt) {
             const int cw = wb[mt] + j * q.tap_step, ch = hb[mt] + i * q.tap_step;
-            tma_load_4d(st_base + (uint32_t)(2 * mt) * kA2Bytes, &map_ah, fb, cb * 32, cw, ch, nb[mt]);
-            tma_load_4d(st_base + (uint32_t)(2 * mt + 1) * kA2Bytes, &map_al, fb, cb * 32, cw, ch, nb[mt]);
+            tma_load_5d(st_base + (uint32_t)(2 * mt) * kA2Bytes, &map_ah, fb, cb * 32, cw, ch, nb[mt], 0);
           }
           const uint32_t bb = st_base + (uint32_t)g.MT * 2u * kA2Bytes;
-          tma_load_3d(bb, &map_bh, fb, kb * 32, n_tile * g.BN, phase);
-          tma_load_3d(bb + b_tile_bytes, &map_bl, fb, kb * 32, n_tile * g.BN, phase);
+          tma_load_4d(bb, &map_bh, fb, kb * 32, n_tile * g.BN, phase, 0);
           if (++s == g.stages) {
             s = 0;
             sphase ^= 1u;
+          }
+          if (++cb == cblocks) {
+            cb = 0;
+            if (++j == q.KWp) {
+              j = 0;
+              ++i;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====================================================================================
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((128u >> 4) << 24);
       int s = 0;
       uint32_t sphase = 0;
       int set = 0;
       uint32_t set_phase[2] = {0u, 0u};
+      // stage-0 descriptors; stage s adds s * (stage_bytes >> 4) to the address field (all stages sit below 256 KB)
+      const uint64_t a_desc0 = make_kmajor_sw64_desc(smem_base);
+      const uint64_t b_desc0 = make_kmajor_sw64_desc(smem_base + (uint32_t)g.MT * 2u * kA2Bytes);
+      const uint64_t b_lo_off = (uint64_t)(b_tile_bytes >> 4);
+      const int variant = (g.MT - 1) * 3 + (g.chains - 1);
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
         const int rest = w / g.phases, phase = (w + rest) % g.phases;   // rotate: a CTA's items cycle through the phases
         const int mg = rest / g.n_tiles;
@@ -304,23 +369,24 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         mbar_wait(tempty_bar + 8u * set, set_phase[set] ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc0 = tmem_base + (uint32_t)(set * set_cols);
+        uint32_t accs[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) accs[i] = acc0 + (uint32_t)(i * g.BN);    // tile i = mt * chains + chain
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8u * s, sphase);
           if (trace && w == 0 && kb == 0) dbg[100] = gtime();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
-          const uint32_t bb = st_base + (uint32_t)g.MT * 2u * kA2Bytes;
-          const uint64_t bh = make_kmajor_sw64_desc(bb), bl = make_kmajor_sw64_desc(bb + b_tile_bytes);
-          for (int mt = 0; mt < g.MT && g.dbg_mode != 1; ++mt) {
-            const uint64_t ah = make_kmajor_sw64_desc(st_base + (uint32_t)(2 * mt) * kA2Bytes);
-            const uint64_t al = make_kmajor_sw64_desc(st_base + (uint32_t)(2 * mt + 1) * kA2Bytes);
-            const uint32_t d = acc0 + (uint32_t)(mt * g.BN);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {  // 2 x UMMA_K(16) = 32; +32 B per step inside the 64 B swizzle row
-              const uint64_t o = (uint64_t)(k * 2);
-              umma_bf16(d, ah + o, bh + o, idesc, (kb | k) != 0);
-              umma_bf16(d, ah + o, bl + o, idesc, 1u);
-              umma_bf16(d, al + o, bh + o, idesc, 1u);
+          if (g.dbg_mode != 1) {
+            const uint64_t sd = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
+            const uint64_t a0 = a_desc0 + sd, b0 = b_desc0 + sd;
+            const bool first = kb == 0;
+            switch (variant) {               // uniform branch; each arm is straight-line code
+              case 0: issue_kblock<1, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
+              case 1: issue_kblock<1, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
+              case 2: issue_kblock<1, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
+              case 3: issue_kblock<2, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
+              case 4: issue_kblock<2, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
+              default: issue_kblock<2, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
             }
           }
           umma_commit(empty_bar + 8u * s);        // frees the smem stage when these MMAs retire
@@ -435,8 +501,15 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         for (int h = 0; h < CH; h += 16) {    // 16-channel halves of the chunk
           uint32_t v[16];
           if (num_kb > 0) {
-            tmem_ld16(acc0 + (uint32_t)(t * g.BN + c0 + h), v);
+            tmem_ld16(acc0 + (uint32_t)(t * g.chains * g.BN + c0 + h), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int ch = 1; ch < g.chains; ++ch) {      // partial sums of the other accumulator chains
+              uint32_t u[16];
+              tmem_ld16(acc0 + (uint32_t)((t * g.chains + ch) * g.BN + c0 + h), u);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0u;
@@ -575,7 +648,7 @@ static int pow2_ceil2(int v) {
 struct Tc2Plan {
   bool ok = false;
   int Cpad, CoutPad, Tmax, phases, BN, n_tiles, BW, BH, BI, MT, m_tiles, m_groups, stages, acc_sets, tmem_cols;
-  int tma_out, epi_smem, x_slots, chunk;
+  int tma_out, epi_smem, x_slots, chunk, chains;
   size_t x_bytes, b_bytes, total_bytes, smem_bytes;
 };
 
@@ -590,19 +663,18 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   if (p.Tmax < 1 || p.Tmax > 64) return p;
   p.Cpad = (Cin + 31) / 32 * 32;
   const int c16 = (Cout + 15) / 16 * 16;
-  p.BN = 0;
+  int bn_max = 0;
   for (int bn = 256; bn >= 16; bn -= 16)
     if (c16 % bn == 0) {
-      p.BN = bn;
+      bn_max = bn;
       break;
     }
-  if (c16 > 256 && p.BN < 96) {                              // awkward factorisation: pad to a multiple of 128 instead
-    p.BN = 128;
+  if (c16 > 256 && bn_max < 96) {                            // awkward factorisation: pad to a multiple of 128 instead
+    bn_max = 128;
     p.CoutPad = (Cout + 127) / 128 * 128;
   } else {
     p.CoutPad = c16;
   }
-  p.n_tiles = p.CoutPad / p.BN;
   const int Pa = (Ho + st - 1) / st, Pb = (Wo + st - 1) / st;  // largest phase
   // Pixel box: as wide as divides the row (up to 128 pixels), so that the NCHW side of the tile (epilogue stores, GDN's
   // x operand) moves in 256-512 B contiguous rows instead of 64 B pieces; falls back to 16-wide boxes for ragged widths.
@@ -626,13 +698,62 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   p.BI = 128 / (p.BW * p.BH);
   if (p.BI > 256) return p;
   p.m_tiles = ((Pb + p.BW - 1) / p.BW) * ((Pa + p.BH - 1) / p.BH) * ((N + p.BI - 1) / p.BI);
-  // two pixel tiles share each weight stage when there is enough work to keep every SM busy anyway
+  // Output-channel tile.  The widest tile (fewest weight re-reads) is right when the pixel tiles alone fill the chip; a
+  // layer with few pixel tiles (hyperprior stages, batch-1 evaluation: 1-64 tiles, profiles/r1d_launches_fwd_*.csv)
+  // left most SMs idle while a handful of CTAs walked the whole K loop at the single-SM MMA rate.  Narrower tiles
+  // spread the same K loop over more SMs: cost per K block of one CTA = max(six MMAs, the two TMA instructions that
+  // fill the stage, the same bytes of all active CTAs at the L2 rate); pick the divisor of the padded channel count
+  // that minimises waves x cost.
   const int sms = num_sms();
+  {
+    double best = 1e300;
+    p.BN = bn_max;
+    const char* e_bn = getenv("B200LIC_TC_BN");            // experiments only: cap the tile width
+    const int bn_cap = e_bn ? atoi(e_bn) : 0;
+    for (int bn = bn_max; bn >= 16; bn -= 16) {
+      if (p.CoutPad % bn) continue;
+      if (bn_cap > 0) {
+        if (bn <= bn_cap || bn == 16) {
+          p.BN = bn;
+          break;
+        }
+        continue;
+      }
+      const long long items = (long long)p.m_tiles * (p.CoutPad / bn) * p.phases;
+      const long long waves = (items + sms - 1) / sms;
+      const double active = (double)(items < sms ? items : sms);
+      // constants measured on B200 with scripts/bn_sweep.py / tc_timeline.py (profiles/README.md r1d)
+      const double t_mma = 6.0 * 62.0 * bn / 192.0;                       // ns per K block: 6 MMAs, 62 ns each at N = 192
+      const double bytes = 2.0 * kA2Bytes + 128.0 * bn;
+      const double t_fill = 225.0 + 0.36 * bn;                            // two TMA instructions (~135 ns + ~90 ns + rows)
+      const double t_l2 = active * bytes / 12000.0;                       // ~12 TB/s of L2 -> shared memory chip-wide
+      double t = t_mma > t_fill ? t_mma : t_fill;
+      if (t_l2 > t) t = t_l2;
+      const double cost = (double)waves * (t + 2.0);                      // +2 ns: ties go to the wider tile
+      if (cost < best) {
+        best = cost;
+        p.BN = bn;
+      }
+    }
+  }
+  p.n_tiles = p.CoutPad / p.BN;
+  // two pixel tiles share each weight stage when there is enough work to keep every SM busy anyway
   const long long items1 = (long long)p.m_tiles * p.n_tiles * p.phases;
   p.MT = (items1 >= (long long)(2 * sms * 3) / 4 && 2 * p.BN <= 512) ? 2 : 1;
   p.m_groups = (p.m_tiles + p.MT - 1) / p.MT;
-  p.acc_sets = (2 * p.MT * p.BN <= 512) ? 2 : 1;
-  p.tmem_cols = pow2_ceil2(p.acc_sets * p.MT * p.BN);
+  // accumulator chains per tile: as many (up to the three passes) as TMEM holds next to double buffering
+  p.chains = 1;
+  {
+    const char* e_ch = getenv("B200LIC_TC_CHAINS");          // experiments only
+    const int want = e_ch ? atoi(e_ch) : 1;   // measured: extra chains buy nothing once the issue stream is lean
+    for (int c = 3; c >= 1; --c)
+      if (c <= want && p.MT * c * p.BN <= 512) {
+        p.chains = c;
+        break;
+      }
+  }
+  p.acc_sets = (2 * p.MT * p.chains * p.BN <= 512) ? 2 : 1;
+  p.tmem_cols = pow2_ceil2(p.acc_sets * p.MT * p.chains * p.BN);
   if (p.tmem_cols < 32) p.tmem_cols = 32;
   // conv-type outputs with 16-byte aligned rows leave by TMA store
   p.tma_out = (!transposed && (Wo % 4) == 0) ? 1 : 0;
@@ -709,21 +830,23 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
   CUtensorMap mah, mal, mbh, mbl, my, mx, mn;
   {
     const int es = transposed ? 1 : stride;
-    cuuint64_t dims[4] = {(cuuint64_t)p.Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)p.Cpad * 2, (cuuint64_t)W * p.Cpad * 2, (cuuint64_t)H * W * p.Cpad * 2};
-    cuuint32_t box[4] = {32, (cuuint32_t)(p.BW * es), (cuuint32_t)(p.BH * es), (cuuint32_t)p.BI};
-    cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
-    if (!tc_encode_map_ex(&mah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, xh, 4, dims, strides, box, estr) ||
-        !tc_encode_map_ex(&mal, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, xl, 4, dims, strides, box, estr))
+    // outermost dimension (extent 2) = the hi / lo slab of the workspace: one box fetches both slices of a tile
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, 2};
+    cuuint64_t strides[4] = {(cuuint64_t)p.Cpad * 2, (cuuint64_t)W * p.Cpad * 2, (cuuint64_t)H * W * p.Cpad * 2,
+                             (cuuint64_t)p.x_bytes};
+    cuuint32_t box[5] = {32, (cuuint32_t)(p.BW * es), (cuuint32_t)(p.BH * es), (cuuint32_t)p.BI, 2};
+    cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
+    if (!tc_encode_map_ex(&mah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, xh, 5, dims, strides, box, estr))
       return B200LIC_ERR_CUDA;
+    mal = mah;
     const cuuint64_t Kmax = (cuuint64_t)p.Tmax * p.Cpad;
-    cuuint64_t bdims[3] = {Kmax, (cuuint64_t)p.CoutPad, (cuuint64_t)p.phases};
-    cuuint64_t bstrides[2] = {Kmax * 2, Kmax * 2 * (cuuint64_t)p.CoutPad};
-    cuuint32_t bbox[3] = {32, (cuuint32_t)p.BN, 1};
-    cuuint32_t bestr[3] = {1, 1, 1};
-    if (!tc_encode_map_ex(&mbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bh, 3, bdims, bstrides, bbox, bestr) ||
-        !tc_encode_map_ex(&mbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bl, 3, bdims, bstrides, bbox, bestr))
+    cuuint64_t bdims[4] = {Kmax, (cuuint64_t)p.CoutPad, (cuuint64_t)p.phases, 2};
+    cuuint64_t bstrides[3] = {Kmax * 2, Kmax * 2 * (cuuint64_t)p.CoutPad, (cuuint64_t)p.b_bytes};
+    cuuint32_t bbox[4] = {32, (cuuint32_t)p.BN, 1, 2};
+    cuuint32_t bestr[4] = {1, 1, 1, 1};
+    if (!tc_encode_map_ex(&mbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bh, 4, bdims, bstrides, bbox, bestr))
       return B200LIC_ERR_CUDA;
+    mbl = mbh;
     // fp32 NCHW output-shaped tensors: (W, H, C, N), box = one staging chunk
     cuuint64_t odims[4] = {(cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)Cout, (cuuint64_t)N};
     cuuint64_t ostr[3] = {(cuuint64_t)Wo * 4, (cuuint64_t)Wo * Ho * 4, (cuuint64_t)Wo * Ho * Cout * 4};
@@ -753,7 +876,7 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
     dbg_mode = e ? atoi(e) : 0;
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
-            p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, act, slope, gdn_mode, fixed_point,
+            p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, p.chains, act, slope, gdn_mode, fixed_point,
             p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, dbg_mode};
   static bool attr_set = false;
   if (!attr_set) {
@@ -765,7 +888,8 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
     attr_set = true;
   }
   unsigned long long* dbg = nullptr;
-  if (dbg_mode == 3) {
+  static const bool timeline = getenv("B200LIC_TC_TIMELINE") != nullptr;   // timeline together with modes 1 / 2
+  if (dbg_mode == 3 || timeline) {
     if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 128 * sizeof(unsigned long long));
     cudaMemsetAsync(g_dbg_buf, 0, 128 * sizeof(unsigned long long), s);
     dbg = g_dbg_buf;

@@ -49,6 +49,24 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// one lane of a converged warp (see conv_tc2.cu: with `lane == 0` every UTMALDG / UTCHMMA is wrapped in an ELECT loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -101,8 +119,7 @@ struct WgGeom {
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-    tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                    const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl, WgGeom g,
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_s, WgGeom g,
                     float* __restrict__ dw) {
   using namespace wg;
   extern __shared__ uint8_t smem_raw[];
@@ -154,24 +171,27 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 
   if (warp == 0) {
     // ===== TMA producer =================================================================================================
-    if (lane == 0) {
-      int bt[kBoxesA], bcb[kBoxesA], br[kBoxesA], bs[kBoxesA];
+    // Shared-memory stage: A region = kBoxesA x [hi box | lo box], B region = nb_max x [hi box | lo box].  One TMA
+    // instruction fetches the hi and the lo slice of a box (outermost tensor-map dimension = the two slabs of the
+    // staged operand): the TMA unit's cost is per instruction (~115-135 ns, scripts/probes/tma_probe.cu), and fourteen
+    // single-slice loads per pixel tile paced this loop.
+    if (elect_one()) {
+      int bcb[kBoxesA], br[kBoxesA], bs[kBoxesA];
 #pragma unroll
       for (int j = 0; j < kBoxesA; ++j) {
         int idx = unit * kBoxesA + j;
         if (idx >= TT) idx = TT - 1;                   // duplicate of the last box; masked in the epilogue
-        bt[j] = idx / cblocks;
-        bcb[j] = idx - bt[j] * cblocks;
-        br[j] = bt[j] / g.KW;
-        bs[j] = bt[j] - br[j] * g.KW;
+        const int bt = idx / cblocks;
+        bcb[j] = idx - bt * cblocks;
+        br[j] = bt / g.KW;
+        bs[j] = bt - br[j] * g.KW;
       }
       const uint32_t tx_bytes = a_bytes + 2u * (uint32_t)nb * kBoxBytes;
+      int tw = kt0 % tiles_w, th = (kt0 / tiles_w) % tiles_h, tn = kt0 / (tiles_w * tiles_h);
+      int s = 0;
+      uint32_t sphase = 0;
       for (int it = 0; it < nkt; ++it) {
-        const int s = it % S;
-        const uint32_t round = (uint32_t)(it / S);
-        mbar_wait(empty_bar + 8u * s, (round & 1u) ^ 1u);
-        const int kt = kt0 + it;
-        const int tw = kt % tiles_w, th = (kt / tiles_w) % tiles_h, tn = kt / (tiles_w * tiles_h);
+        mbar_wait(empty_bar + 8u * s, sphase ^ 1u);
         const int w0 = tw * g.BW, h0 = th * g.BH, n0 = tn * g.BI;
         const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
         const uint32_t fb = full_bar + 8u * s;
@@ -179,44 +199,60 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 #pragma unroll
         for (int j = 0; j < kBoxesA; ++j) {
           const int cw = w0 * g.stride - g.pad + bs[j], ch = h0 * g.stride - g.pad + br[j];
-          tma_load_4d(st_base + (uint32_t)j * kBoxBytes, &map_bh, fb, bcb[j] * 64, cw, ch, n0);
-          tma_load_4d(st_base + (uint32_t)(kBoxesA + j) * kBoxBytes, &map_bl, fb, bcb[j] * 64, cw, ch, n0);
+          tma_load_5d(st_base + (uint32_t)(2 * j) * kBoxBytes, &map_b, fb, bcb[j] * 64, cw, ch, n0, 0);
         }
-        for (int j = 0; j < nb; ++j) {
-          tma_load_4d(st_base + a_bytes + (uint32_t)j * kBoxBytes, &map_sh, fb, (nb0 + j) * 64, w0, h0, n0);
-          tma_load_4d(st_base + a_bytes + (uint32_t)(g.nb_max + j) * kBoxBytes, &map_sl, fb, (nb0 + j) * 64, w0, h0, n0);
+        for (int j = 0; j < nb; ++j)
+          tma_load_5d(st_base + a_bytes + (uint32_t)(2 * j) * kBoxBytes, &map_s, fb, (nb0 + j) * 64, w0, h0, n0, 0);
+        if (++s == S) {
+          s = 0;
+          sphase ^= 1u;
+        }
+        if (++tw == tiles_w) {
+          tw = 0;
+          if (++th == tiles_h) {
+            th = 0;
+            ++tn;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer ===================================================================================================
-    if (lane == 0) {
+    if (elect_one()) {
       // D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+      // Stage-0 descriptors; everything else is a compile-time offset or one add per stage (descriptor address fields
+      // count 16-byte units), so the 24 MMAs of a pixel tile are straight-line code.  Consecutive 64-wide MN blocks of
+      // one slice are 2 boxes apart (LBO), the lo slice of a box follows its hi slice.
+      const uint64_t a_d0 = make_mnmajor_sw128_desc(smem_base, 2u * kBoxBytes);
+      const uint64_t b_d0 = make_mnmajor_sw128_desc(smem_base + a_bytes, 2u * kBoxBytes);
+      constexpr uint64_t kLo = kBoxBytes >> 4, kAcc = (4u * kBoxBytes) >> 4, kStep = 2048u >> 4;
+      const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)g.tmem_cols;
+      int s = 0;
+      uint32_t sphase = 0;
       for (int it = 0; it < nkt; ++it) {
-        const int s = it % S;
-        const uint32_t round = (uint32_t)(it / S);
-        mbar_wait(full_bar + 8u * s, round & 1u);
+        mbar_wait(full_bar + 8u * s, sphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t b_hi = st_base + a_bytes, b_lo = b_hi + (uint32_t)g.nb_max * kBoxBytes;
+        const uint64_t sd = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
+        const uint64_t a0 = a_d0 + sd, b0 = b_d0 + sd;
 #pragma unroll
-        for (int acc = 0; acc < kNacc; ++acc) {
-          const uint32_t a_hi = st_base + (uint32_t)(2 * acc) * kBoxBytes;
-          const uint32_t a_lo = st_base + (uint32_t)(kBoxesA + 2 * acc) * kBoxBytes;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.tmem_cols);
+        for (int k = 0; k < 4; ++k) {                   // 4 x UMMA_K(16 pixels) = 64; 16 K-rows = 2048 B
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                 // 4 x UMMA_K(16 pixels) = 64; 16 K-rows = 2048 B
-            const uint32_t ko = (uint32_t)k * 2048u;
-            const uint64_t ah = make_mnmajor_sw128_desc(a_hi + ko, kBoxBytes), al = make_mnmajor_sw128_desc(a_lo + ko, kBoxBytes);
-            const uint64_t bh = make_mnmajor_sw128_desc(b_hi + ko, kBoxBytes), bl = make_mnmajor_sw128_desc(b_lo + ko, kBoxBytes);
-            umma_bf16(d_tmem, ah, bh, idesc, (it | k) != 0);
-            umma_bf16(d_tmem, ah, bl, idesc, 1u);
-            umma_bf16(d_tmem, al, bh, idesc, 1u);
+          for (int pass = 0; pass < 3; ++pass) {        // hi*hi, hi*lo, lo*hi
+#pragma unroll
+            for (int acc = 0; acc < kNacc; ++acc) {     // alternate the two accumulators
+              const uint64_t ad = a0 + (uint64_t)acc * kAcc + (pass == 2 ? kLo : 0) + (uint64_t)k * kStep;
+              const uint64_t bd = b0 + (pass == 1 ? kLo : 0) + (uint64_t)k * kStep;
+              umma_bf16(acc == 0 ? d0 : d1, ad, bd, idesc, (it != 0 || k != 0 || pass != 0) ? 1u : 0u);
+            }
           }
         }
         umma_commit(empty_bar + 8u * s);
+        if (++s == S) {
+          s = 0;
+          sphase ^= 1u;
+        }
       }
       umma_commit(tmem_full_bar);
     }
@@ -351,20 +387,26 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
     set_error("%s: memset failed: %s", name, cudaGetErrorString(e));
     return B200LIC_ERR_CUDA;
   }
-  CUtensorMap mbh, mbl, msh, msl;
+  // hi and lo slabs of each operand as the outermost dimension of one 5-D map (one TMA instruction per box pair)
+  const long long big_slab = (const uint8_t*)bl - (const uint8_t*)bh, small_slab = (const uint8_t*)sl - (const uint8_t*)sh;
+  if (big_slab <= 0 || small_slab <= 0 || (big_slab & 15) || (small_slab & 15)) {
+    set_error("%s: staged hi/lo slabs must be ascending and 16-byte aligned", name);
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  CUtensorMap mb, ms;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p.CbPad, (cuuint64_t)Wb, (cuuint64_t)Hb, (cuuint64_t)N};
-    cuuint64_t str[3] = {(cuuint64_t)p.CbPad * 2, (cuuint64_t)Wb * p.CbPad * 2, (cuuint64_t)Hb * Wb * p.CbPad * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), (cuuint32_t)p.BI};
-    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    if (!tc_encode_map(&mbh, bh, 4, dims, str, box, es) || !tc_encode_map(&mbl, bl, 4, dims, str, box, es))
-      return B200LIC_ERR_CUDA;
-    cuuint64_t sdims[4] = {(cuuint64_t)p.CsPad, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N};
-    cuuint64_t sstr[3] = {(cuuint64_t)p.CsPad * 2, (cuuint64_t)Ws * p.CsPad * 2, (cuuint64_t)Hs * Ws * p.CsPad * 2};
-    cuuint32_t sbox[4] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
-    cuuint32_t ses[4] = {1, 1, 1, 1};
-    if (!tc_encode_map(&msh, sh, 4, sdims, sstr, sbox, ses) || !tc_encode_map(&msl, sl, 4, sdims, sstr, sbox, ses))
-      return B200LIC_ERR_CUDA;
+    cuuint64_t dims[5] = {(cuuint64_t)p.CbPad, (cuuint64_t)Wb, (cuuint64_t)Hb, (cuuint64_t)N, 2};
+    cuuint64_t str[4] = {(cuuint64_t)p.CbPad * 2, (cuuint64_t)Wb * p.CbPad * 2, (cuuint64_t)Hb * Wb * p.CbPad * 2,
+                         (cuuint64_t)big_slab};
+    cuuint32_t box[5] = {64, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), (cuuint32_t)p.BI, 2};
+    cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
+    if (!tc_encode_map(&mb, bh, 5, dims, str, box, es)) return B200LIC_ERR_CUDA;
+    cuuint64_t sdims[5] = {(cuuint64_t)p.CsPad, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N, 2};
+    cuuint64_t sstr[4] = {(cuuint64_t)p.CsPad * 2, (cuuint64_t)Ws * p.CsPad * 2, (cuuint64_t)Hs * Ws * p.CsPad * 2,
+                          (cuuint64_t)small_slab};
+    cuuint32_t sbox[5] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI, 2};
+    cuuint32_t ses[5] = {1, 1, 1, 1, 1};
+    if (!tc_encode_map(&ms, sh, 5, sdims, sstr, sbox, ses)) return B200LIC_ERR_CUDA;
   }
   WgGeom g{N, Cs, Hs, Ws, p.CsPad, Cb, Hb, Wb, p.CbPad, KH, KW, stride, pad, p.BW, p.BH, p.BI, p.nb_max,
            p.tiles_per_split, p.tmem_cols};
@@ -378,7 +420,7 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
     attr_set = true;
   }
   dim3 grid(p.units, p.n_tiles, p.splits);
-  tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mbh, mbl, msh, msl, g, dw);
+  tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mb, ms, g, dw);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

@@ -19,6 +19,12 @@ elif what == "conv":
     b = torch.randn(192, generator=g).to(dev)
     d = ops.conv_desc(x.shape, w.shape, 2, 2)
     fn = lambda: ops.conv2d_raw(x, w, b, d)
+elif what == "small":          # h_a.4 at batch 1 (768x512 image): one pixel tile, 150 K blocks -- the latency regime
+    x = torch.randn(1, 192, 16, 24, generator=g).to(dev)
+    w = (torch.randn(192, 192, 5, 5, generator=g) * 0.05).to(dev)
+    b = torch.randn(192, generator=g).to(dev)
+    d = ops.conv_desc(x.shape, w.shape, 2, 2)
+    fn = lambda: ops.conv2d_raw(x, w, b, d)
 else:
     x = torch.randn(B, 192, 64, 64, generator=g).to(dev)
     w = (torch.randn(192, 192, 5, 5, generator=g) * 0.05).to(dev)
