@@ -157,15 +157,22 @@ def run_cuda(args):
     d = ops.conv_desc(q_in.shape, w.shape, u.fwd_kwargs["stride"], u.fwd_kwargs["padding"])
     for _ in range(3):
         ops.conv2d_raw(q_in, w, u.bias.data, d)
+    torch.cuda.synchronize()
+    # the launch (operand staging + GEMM, three kernels) is replayed from a CUDA graph, as the calibration loop issues
+    # it: issued eagerly from Python the three launches are host-bound (~65 us each) and the events would time the host
+    kg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(kg):
+        ops.conv2d_raw(q_in, w, u.bias.data, d)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
     flush = torch.empty(64 * 1024 * 1024, device=dev)       # 256 MB > 126 MB L2
     for a, b in evs:
         flush.zero_()
         a.record()
-        ops.conv2d_raw(q_in, w, u.bias.data, d)
+        kg.replay()
         b.record()
     torch.cuda.synchronize()
     k_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    del kg
     flops = 2.0 * macs[top] * PER_GPU_BATCH
     pk = peaks()
     roof = {"bound": "tensor", "kernel": "conv_fwd g_a.2 192->192 5x5 s2 @[8,192,128,128]",

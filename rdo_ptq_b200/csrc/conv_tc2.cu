@@ -740,6 +740,17 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   // two pixel tiles share each weight stage when there is enough work to keep every SM busy anyway
   const long long items1 = (long long)p.m_tiles * p.n_tiles * p.phases;
   p.MT = (items1 >= (long long)(2 * sms * 3) / 4 && 2 * p.BN <= 512) ? 2 : 1;
+  if (p.MT == 2 && 4 * p.BN > 512) {
+    // two tiles of this width leave no room to double-buffer the accumulators, so every item's epilogue would run
+    // with the tensor pipe idle: worth it only when a CTA gets a single item anyway (measured, scripts/bn_sweep.py --mt:
+    // transposed conv 192->192 @64x64x8 236 -> 182 us with one tile per item, conv 192->192 @128x128x8 184 vs 191 us)
+    const long long items2 = (long long)((p.m_tiles + 1) / 2) * p.n_tiles * p.phases;
+    if (items2 > sms) p.MT = 1;
+  }
+  {
+    const char* e_mt = getenv("B200LIC_TC_MT");              // experiments only
+    if (e_mt && atoi(e_mt) == 1) p.MT = 1;
+  }
   p.m_groups = (p.m_tiles + p.MT - 1) / p.MT;
   // accumulator chains per tile: as many (up to the three passes) as TMEM holds next to double buffering
   p.chains = 1;

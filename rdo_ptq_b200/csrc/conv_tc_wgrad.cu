@@ -120,7 +120,7 @@ struct WgGeom {
 
 __global__ void __launch_bounds__(kWgThreads, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_s, WgGeom g,
-                    float* __restrict__ dw) {
+                    float* __restrict__ part) {
   using namespace wg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -257,15 +257,20 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       umma_commit(tmem_full_bar);
     }
   } else {
-    // ===== epilogue: TMEM -> atomicAdd into dW[cs][cb][tap] ================================================================
+    // ===== epilogue: TMEM -> this split's slab of partial sums, part[split][tap][cs][cb] ===================================
+    // Plain stores, lanes along cb (128 B per warp instruction); wgrad_reduce_kernel sums the slabs into dW[cs][cb][tap].
+    // (The first version added every split's tile into dW with one fp32 atomic per element: 14 M scattered L2 atomics
+    // for the 192x192 5x5 layer, ~70 us of its 175 us, and a summation order that changed from run to run.)
     const int q = warp & 3;
     const int row = q * 32 + lane;                      // accumulator row = box (row / 64), channel (row % 64)
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* slab = part + (size_t)blockIdx.z * T * g.Cs * g.Cb;
     for (int acc = 0; acc < kNacc; ++acc) {
       const int idx = unit * kBoxesA + 2 * acc + (row >> 6);
       const int t = idx / cblocks, cb = (idx - t * cblocks) * 64 + (row & 63);
       const bool valid = idx < TT && cb < g.Cb;
+      float* dst = slab + ((size_t)t * g.Cs) * g.Cb + cb;
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * g.tmem_cols + c0), v);
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int cs = nb0 * 64 + c0 + j;
-            if (cs < g.Cs) atomicAdd(dw + ((size_t)cs * g.Cb + cb) * T + t, __uint_as_float(v[j]));
+            if (cs < g.Cs) dst[(size_t)cs * g.Cb] = __uint_as_float(v[j]);
           }
         }
       }
@@ -287,11 +292,33 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   }
 }
 
+// dW[cs][cb][tap] = sum over splits of part[split][tap][cs][cb]; fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int splits, int T, int Cs, int Cb,
+                                                            float* __restrict__ dw) {
+  const size_t per = (size_t)T * Cs * Cb;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four loads in flight; the order of additions is fixed
+    int z = 0;
+    for (; z + 3 < splits; z += 4) {
+      a0 += __ldg(part + (size_t)z * per + i);
+      a1 += __ldg(part + (size_t)(z + 1) * per + i);
+      a2 += __ldg(part + (size_t)(z + 2) * per + i);
+      a3 += __ldg(part + (size_t)(z + 3) * per + i);
+    }
+    for (; z < splits; ++z) a0 += __ldg(part + (size_t)z * per + i);
+    const float acc = (a0 + a1) + (a2 + a3);
+    const int cb = (int)(i % Cb);
+    const size_t r = i / Cb;
+    const int cs = (int)(r % Cs), t = (int)(r / Cs);
+    dw[((size_t)cs * Cb + cb) * T + t] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 struct WgPlan {
   bool ok = false;
   int CsPad, CbPad, BW, BH, BI, nb_max, n_tiles, units, ktiles, splits, tiles_per_split, tmem_cols;
-  size_t small_bytes, big_bytes, total_bytes, smem_bytes;
+  size_t small_bytes, big_bytes, part_bytes, total_bytes, smem_bytes;
 };
 
 static int p2ceil(int v) {
@@ -331,7 +358,8 @@ static WgPlan make_wg_plan(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb
   if (p.smem_bytes > 227 * 1024) return p;
   p.small_bytes = ((size_t)N * Hs * Ws * p.CsPad * 2 + 1023) / 1024 * 1024;
   p.big_bytes = ((size_t)N * Hb * Wb * p.CbPad * 2 + 1023) / 1024 * 1024;
-  p.total_bytes = 2 * p.small_bytes + 2 * p.big_bytes + 1024;
+  p.part_bytes = ((size_t)p.splits * KH * KW * Cs * Cb * sizeof(float) + 1023) / 1024 * 1024;   // per-split partial dW
+  p.total_bytes = 2 * p.small_bytes + 2 * p.big_bytes + p.part_bytes + 1024;
   p.ok = true;
   return p;
 }
@@ -382,11 +410,7 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
     rc = tc_stage_nhwc(big, N, Cb, Hb * Wb, p.CbPad, big_square, bh, bl, s);
     if (rc != B200LIC_OK) return rc;
   }
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cs * Cb * KH * KW, s);
-  if (e != cudaSuccess) {
-    set_error("%s: memset failed: %s", name, cudaGetErrorString(e));
-    return B200LIC_ERR_CUDA;
-  }
+  float* part = reinterpret_cast<float*>(ws + 2 * p.small_bytes + 2 * p.big_bytes);
   // hi and lo slabs of each operand as the outermost dimension of one 5-D map (one TMA instruction per box pair)
   const long long big_slab = (const uint8_t*)bl - (const uint8_t*)bh, small_slab = (const uint8_t*)sl - (const uint8_t*)sh;
   if (big_slab <= 0 || small_slab <= 0 || (big_slab & 15) || (small_slab & 15)) {
@@ -420,8 +444,11 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
     attr_set = true;
   }
   dim3 grid(p.units, p.n_tiles, p.splits);
-  tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mb, ms, g, dw);
+  tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mb, ms, g, part);
   B200_LAUNCH_CHECK(name);
+  const size_t per = (size_t)KH * KW * Cs * Cb;
+  wgrad_reduce_kernel<<<grid_for(per, 256), 256, 0, s>>>(part, p.splits, KH * KW, Cs, Cb, dw);
+  B200_LAUNCH_CHECK("wgrad_reduce_kernel");
   return B200LIC_OK;
 }
 

@@ -21,7 +21,9 @@ CASES = [  # name, N, Cin, H, W, Cout, k, stride, transposed
     ("g_a.4 b8p", 8, 192, 64, 64, 192, 5, 2, False), ("g_a.6 b8p", 8, 192, 32, 32, 320, 5, 2, False),
     ("h_a.0 b8p", 8, 320, 16, 16, 192, 3, 1, False), ("h_a.2 b8p", 8, 192, 16, 16, 192, 5, 2, False),
     ("h_s.4 b8p", 8, 480, 16, 16, 640, 3, 1, False), ("g_s.0 b8p", 8, 320, 16, 16, 192, 5, 2, True),
-    ("g_a.2 b8p", 8, 192, 128, 128, 192, 5, 2, False),
+    ("g_a.2 b8p", 8, 192, 128, 128, 192, 5, 2, False), ("g_s.4 b8p", 8, 192, 64, 64, 192, 5, 2, True),
+    ("g_s.2 b8p", 8, 192, 32, 32, 192, 5, 2, True), ("g_a.2 2K", 1, 192, 768, 1024, 192, 5, 2, False),
+    ("g_s.4 2K", 1, 192, 384, 512, 192, 5, 2, True), ("g_a.4 2K", 1, 192, 384, 512, 192, 5, 2, False),
 ]
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 for name, N, Cin, H, W, Cout, k, st, tr in CASES:
@@ -32,8 +34,8 @@ for name, N, Cin, H, W, Cout, k, st, tr in CASES:
     fn = (lambda: ops.deconv2d_raw(x, w, b, d)) if tr else (lambda: ops.conv2d_raw(x, w, b, d))
     row = {"case": name}
     ref = None
-    VAR = "B200LIC_TC_CHAINS" if "--chains" in sys.argv else "B200LIC_TC_BN"
-    for cap in ((0, 1, 2, 3) if VAR.endswith("CHAINS") else (0, 256, 96, 64, 48, 32, 16)):
+    VAR = "B200LIC_TC_CHAINS" if "--chains" in sys.argv else ("B200LIC_TC_MT" if "--mt" in sys.argv else "B200LIC_TC_BN")
+    for cap in ((0, 1, 2, 3) if VAR.endswith("CHAINS") else ((0, 1) if VAR.endswith("MT") else (0, 256, 96, 64, 48, 32, 16))):
         os.environ[VAR] = str(cap)
         if cap == 0:
             os.environ.pop(VAR)
