@@ -107,6 +107,13 @@ B200LIC_API int b200lic_adaround_bwd_adam(const float* w, float* alpha, const fl
                               float eps, float grad_scale, float reg_weight, float reg_b, float* reg_loss,
                               float* d_alpha_out, b200lic_stream_t stream);
 
+/* Integer weights n = code - zero_point (integer-valued fp32, |n| <= n_levels - 1): the weight operand of
+ * b200lic_conv_fwd_wq / b200lic_deconv_fwd_wq.  alpha == NULL: nearest rounding (TO quantizer.py:175-177); alpha given:
+ * hardened AdaRound, floor(w/d) + (alpha >= 0) (quantizer.py:437-449 with soft_targets False).  Same arithmetic as
+ * b200lic_wq_fake_quant / b200lic_adaround_fwd, so n * delta equals their dequantised weight bit for bit. */
+B200LIC_API int b200lic_wq_int_weights(const float* w, const float* alpha, const float* delta, const float* zero_point,
+                           int outer, int ch, int inner, int n_levels, float* w_int, b200lic_stream_t stream);
+
 /* Learned step size (LSQ-style): d loss / d delta[ch] from dL/dWq, i.e. the autograd of the fake-quant expression with
  * delta as the leaf -- the option the reference keeps as commented-out code (TO quantizer.py:166-168,
  * layer_opt.py:259-265, block_opt.py:254-266).
@@ -214,6 +221,17 @@ B200LIC_API int b200lic_conv_fwd(const b200lic_conv_desc* d, const float* x, con
 /* y = act(conv_transpose2d(x, w) + bias); w is [Cin,Cout,KH,KW]; Ho/Wo carry the output_padding. */
 B200LIC_API int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                        void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
+/* Forward of a layer whose weight is HARD-quantised per OUTPUT channel (evaluation, TO quant_layer.py:113-123 with
+ * the quantiser of quantizer.py:175-177 or a hardened AdaRound): y = act(conv(x, w_int) * w_scale[co] + bias[co]), where
+ * w_int = code - zero_point (b200lic_wq_int_weights, n_levels <= 256 so that |n| <= 255 is exact in bf16) and
+ * w_scale = delta per output channel.  Equal to b200lic_conv_fwd on the dequantised weight up to fp32 rounding, with
+ * two tensor-core passes per product instead of three (the weight has no lo slice).  Tensor-core engine only; returns
+ * B200LIC_ERR_UNSUPPORTED for shapes that run on the folded-tap path (3-channel layers): call b200lic_conv_fwd there. */
+B200LIC_API int b200lic_conv_fwd_wq(const b200lic_conv_desc* d, const float* x, const float* w_int, const float* w_scale,
+                        const float* bias, float* y, void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
+B200LIC_API int b200lic_deconv_fwd_wq(const b200lic_conv_desc* d, const float* x, const float* w_int, const float* w_scale,
+                          const float* bias, float* y, void* workspace, size_t workspace_bytes,
+                          b200lic_stream_t stream);
 /* dw[Cout,Cin,KH,KW] = sum_pixels dy (x) x.  dw is overwritten. */
 B200LIC_API int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw,
                        void* workspace, size_t workspace_bytes, b200lic_stream_t stream);

@@ -63,6 +63,9 @@ SIGNATURES = {
     "bits_sum": [_P, _SZ, _P],
     "conv_fwd": [_D, _P, _P, _P, _P, _P, _P, _P, _SZ],
     "deconv_fwd": [_D, _P, _P, _P, _P, _P, _SZ],
+    "conv_fwd_wq": [_D, _P, _P, _P, _P, _P, _P, _SZ],
+    "deconv_fwd_wq": [_D, _P, _P, _P, _P, _P, _P, _SZ],
+    "wq_int_weights": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "conv_wgrad": [_D, _P, _P, _P, _P, _SZ],
     "deconv_wgrad": [_D, _P, _P, _P, _P, _SZ],
     "conv_wgrad_staged": [_D, _I, _P, _P, _P, _P, _P, _SZ],

@@ -25,6 +25,10 @@ bool tc_staged_view(const b200lic_conv_desc* d, int transposed, void* fwd_ws, si
 int tc_conv_wgrad_pre(const b200lic_conv_desc*, const void*, const void*, const float*, float*, void*, size_t, cudaStream_t);
 int tc_deconv_wgrad_pre(const b200lic_conv_desc*, const void*, const void*, const float*, float*, void*, size_t,
                         cudaStream_t);
+int tc_conv_fwd_wq(const b200lic_conv_desc*, const float*, const float*, const float*, const float*, float*, void*, size_t,
+                   cudaStream_t);
+int tc_deconv_fwd_wq(const b200lic_conv_desc*, const float*, const float*, const float*, const float*, float*, void*,
+                     size_t, cudaStream_t);
 size_t tc_conv_fwd_ws(const b200lic_conv_desc*);
 size_t tc_deconv_fwd_ws(const b200lic_conv_desc*);
 size_t tc_conv_wgrad_ws(const b200lic_conv_desc*);
@@ -85,6 +89,35 @@ int b200lic_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* 
   B200_REQUIRE(!d->gdn_mode && !d->in_square, "deconv_fwd: GDN flags are conv-only");
   DISPATCH(tc_deconv_fwd(d, x, w, bias, y, workspace, workspace_bytes, as_stream(stream)),
            simt_deconv_fwd(d, x, w, bias, y, as_stream(stream)));
+}
+
+int b200lic_conv_fwd_wq(const b200lic_conv_desc* d, const float* x, const float* w_int, const float* w_scale,
+                        const float* bias, float* y, void* workspace, size_t workspace_bytes, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  int rc = conv_check_desc(d, "conv_fwd_wq", false);
+  if (rc != B200LIC_OK) return rc;
+  B200_REQUIRE(x && w_int && w_scale && y, "conv_fwd_wq: null pointer");
+  B200_REQUIRE(!d->gdn_mode && !d->in_square, "conv_fwd_wq: GDN flags are not supported");
+  if (d->engine == B200LIC_ENGINE_SIMT) {
+    set_error("conv_fwd_wq: tensor-core engine only");
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  return tc_conv_fwd_wq(d, x, w_int, w_scale, bias, y, workspace, workspace_bytes, as_stream(stream));
+}
+
+int b200lic_deconv_fwd_wq(const b200lic_conv_desc* d, const float* x, const float* w_int, const float* w_scale,
+                          const float* bias, float* y, void* workspace, size_t workspace_bytes,
+                          b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  int rc = conv_check_desc(d, "deconv_fwd_wq", true);
+  if (rc != B200LIC_OK) return rc;
+  B200_REQUIRE(x && w_int && w_scale && y, "deconv_fwd_wq: null pointer");
+  B200_REQUIRE(!d->gdn_mode && !d->in_square, "deconv_fwd_wq: GDN flags are conv-only");
+  if (d->engine == B200LIC_ENGINE_SIMT) {
+    set_error("deconv_fwd_wq: tensor-core engine only");
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  return tc_deconv_fwd_wq(d, x, w_int, w_scale, bias, y, workspace, workspace_bytes, as_stream(stream));
 }
 
 int b200lic_conv_wgrad(const b200lic_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,

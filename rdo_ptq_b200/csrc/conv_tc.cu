@@ -685,6 +685,35 @@ int tc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w, co
                    d->fixed_point, x, w, bias, nullptr, nullptr, y, ws, ws_bytes, s, "deconv_fwd(tc)");
 }
 
+int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
+                  int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
+                  int fixed_point, const float* x, const float* w, const float* w_scale, const float* bias,
+                  const float* gdn_x, float* norm_out, float* y, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                  const char* name);
+// integer-valued weights + per-output-channel scale (two MMA passes); the folded-tap path of the 3-channel layers keeps
+// the three-pass engine (its scale would have to be expanded per folded column)
+int tc_conv_fwd_wq(const b200lic_conv_desc* d, const float* x, const float* w_int, const float* w_scale, const float* bias,
+                   float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (use_v1() || smallc_conv_fwd_ws(d) != 0) {
+    set_error("conv_fwd_wq: shape runs on the folded-tap path");
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  return tc2_launch_wq(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0,
+                       (long long)d->Cin * d->KH * d->KW, (long long)d->KH * d->KW, d->act, d->act_slope, 0, 0,
+                       d->fixed_point, x, w_int, w_scale, bias, nullptr, nullptr, y, ws, ws_bytes, s, "conv_fwd_wq(tc)");
+}
+int tc_deconv_fwd_wq(const b200lic_conv_desc* d, const float* x, const float* w_int, const float* w_scale,
+                     const float* bias, float* y, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (use_v1() || smallc_deconv_fwd_ws(d) != 0) {
+    set_error("deconv_fwd_wq: shape runs on the folded-tap path");
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  return tc2_launch_wq(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 1,
+                       (long long)d->KH * d->KW, (long long)d->Cout * d->KH * d->KW, d->act, d->act_slope, 0, 0,
+                       d->fixed_point, x, w_int, w_scale, bias, nullptr, nullptr, y, ws, ws_bytes, s,
+                       "deconv_fwd_wq(tc)");
+}
+
 int tc_conv_dgrad(const b200lic_conv_desc* d, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes,
                   cudaStream_t s) {
   return tc_launch(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, d->pad, 1,

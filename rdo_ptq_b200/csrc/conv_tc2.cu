@@ -147,7 +147,9 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
 //   a0: descriptor of pixel tile 0's hi slice in this stage (lo = + kA2Bytes >> 4, next tile = + 2 * kA2Bytes >> 4)
 //   b0: descriptor of the weight hi slice in this stage (lo = + b_lo_off)
 //   acc[mt * CHAINS + chain]: TMEM address of each accumulator tile
-template <int MT, int CHAINS>
+//   EXACT: the weight operand is exactly representable in bf16 (integer codes minus zero point, |n| <= 256), so its
+//          lo slice is zero and the hi*lo pass is skipped: two passes per product instead of three.
+template <int MT, int CHAINS, bool EXACT = false>
 __device__ __forceinline__ void issue_kblock(uint64_t a0, uint64_t b0, uint64_t b_lo_off, const uint32_t* acc,
                                              uint32_t idesc, bool first) {
   constexpr uint64_t kALo = (128 * 64) >> 4, kATile = (2 * 128 * 64) >> 4;
@@ -156,6 +158,7 @@ __device__ __forceinline__ void issue_kblock(uint64_t a0, uint64_t b0, uint64_t 
     const uint64_t o = (uint64_t)(k * 2);
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) { // hi*hi, hi*lo, lo*hi
+      if (EXACT && pass == 1) continue;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {    // consecutive MMAs never target the same accumulator tile
         const uint64_t ad = a0 + (uint64_t)mt * kATile + (pass == 2 ? kALo : 0) + o;
@@ -178,6 +181,7 @@ struct Tc2Geom {
   int MT, m_groups, phases;   // pixel tiles per work item, groups of the largest phase, sub-pixel phases
   int stages, acc_sets, tmem_cols;
   int chains;                 // independent accumulator chains per pixel tile (summed in the epilogue)
+  int w_exact;                // weights are bf16-exact integers: B lo slice not loaded, 2 passes, per-channel scale in the epilogue
   int act;
   float slope;
   int gdn_mode, fixed_point;
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                            const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
                            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
                            const __grid_constant__ CUtensorMap map_n, Tc2Geom g, const float* __restrict__ bias,
-                           const float* __restrict__ gdn_x, float* __restrict__ norm_out, float* __restrict__ y,
-                           unsigned long long* __restrict__ dbg) {
+                           const float* __restrict__ w_scale, const float* __restrict__ gdn_x,
+                           float* __restrict__ norm_out, float* __restrict__ y, unsigned long long* __restrict__ dbg) {
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   const uint32_t sN = sX + (uint32_t)g.x_slots * ctile;                              // [2] norm staging (has_norm)
   const uint32_t bars = sN + ((g.epi_smem && g.has_norm) ? 2u * ctile : 0u);
   const uint32_t sBias = bars + 512u;                                                // [BN] bias of the current n-tile
+  const uint32_t sScale = sBias + 1024u;                                             // [BN] weight scale (w_exact)
   const uint32_t full_bar = bars, empty_bar = bars + 8u * g.stages;
   const uint32_t tfull_bar = empty_bar + 8u * g.stages;          // [2] accumulator set complete
   const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (4 warp arrivals)
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             }
             continue;
           }
-          mbar_expect_tx(fb, stage_bytes);
+          mbar_expect_tx(fb, g.w_exact ? stage_bytes - b_tile_bytes : stage_bytes);
           // One TMA instruction per operand tile PAIR: the hi and lo slices are two slabs of one workspace, so a tensor
           // map with an outermost dimension of extent 2 (stride = slab bytes) lands [hi tile | lo tile] in consecutive
           // shared memory -- the layout the MMA descriptors already expect.  The TMA unit's cost here is per
@@ -326,7 +331,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             tma_load_5d(st_base + (uint32_t)(2 * mt) * kA2Bytes, &map_ah, fb, cb * 32, cw, ch, nb[mt], 0);
           }
           const uint32_t bb = st_base + (uint32_t)g.MT * 2u * kA2Bytes;
-          tma_load_4d(bb, &map_bh, fb, kb * 32, n_tile * g.BN, phase, 0);
+          if (g.w_exact) tma_load_4d(bb, &map_bl, fb, kb * 32, n_tile * g.BN, phase, 0);    // hi slab only
+          else tma_load_4d(bb, &map_bh, fb, kb * 32, n_tile * g.BN, phase, 0);
           if (++s == g.stages) {
             s = 0;
             sphase ^= 1u;
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       const uint64_t a_desc0 = make_kmajor_sw64_desc(smem_base);
       const uint64_t b_desc0 = make_kmajor_sw64_desc(smem_base + (uint32_t)g.MT * 2u * kA2Bytes);
       const uint64_t b_lo_off = (uint64_t)(b_tile_bytes >> 4);
-      const int variant = (g.MT - 1) * 3 + (g.chains - 1);
+      const int variant = g.w_exact ? 6 + (g.MT - 1) : (g.MT - 1) * 3 + (g.chains - 1);
       for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
         const int rest = w / g.phases, phase = (w + rest) % g.phases;   // rotate: a CTA's items cycle through the phases
         const int mg = rest / g.n_tiles;
@@ -381,6 +387,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             const uint64_t a0 = a_desc0 + sd, b0 = b_desc0 + sd;
             const bool first = kb == 0;
             switch (variant) {               // uniform branch; each arm is straight-line code
+              case 6: issue_kblock<1, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+              case 7: issue_kblock<2, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
               case 0: issue_kblock<1, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
               case 1: issue_kblock<1, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
               case 2: issue_kblock<1, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
@@ -464,6 +472,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         for (int i = et; i < g.BN; i += 128) {
           const float bv = (bias && co_base + i < g.Cout) ? __ldg(bias + co_base + i) : 0.f;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + (uint32_t)i * 4u), "f"(bv) : "memory");
+          if (g.w_exact) {
+            const float sv = (co_base + i < g.Cout) ? __ldg(w_scale + co_base + i) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sScale + (uint32_t)i * 4u), "f"(sv) : "memory");
+          }
         }
         epi_bar(3);
         bias_base = co_base;
@@ -519,11 +531,21 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           // instruction-bound (2 us per 16 channels in the r1 timeline).
           float r[16];
           const uint32_t bias_addr = sBias + (uint32_t)(c0 + h) * 4u;
+          if (g.w_exact) {                     // accumulator holds sum x * n: y = acc * delta[co] + bias[co]
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float bj;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bj) : "r"(bias_addr + (uint32_t)j * 4u));
-            r[j] = __uint_as_float(v[j]) + bj;
+            for (int j = 0; j < 16; ++j) {
+              float bj, sj;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bj) : "r"(bias_addr + (uint32_t)j * 4u));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sj) : "r"(bias_addr + 1024u + (uint32_t)j * 4u));
+              r[j] = fmaf(__uint_as_float(v[j]), sj, bj);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float bj;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bj) : "r"(bias_addr + (uint32_t)j * 4u));
+              r[j] = __uint_as_float(v[j]) + bj;
+            }
           }
           const uint32_t so0 = st_off + (uint32_t)(h * hw_box) * 4u;
           const uint32_t sstep = (uint32_t)hw_box * 4u;
@@ -773,7 +795,7 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   p.chunk = (p.BN % 32 == 0) ? 32 : 16;
   const size_t ctile = (size_t)p.chunk * 512;
   size_t epi = p.tma_out ? (size_t)(2 + ((gdn_mode && has_norm) ? 2 : 0)) * ctile : 0;
-  const size_t avail = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 1024 /*bias*/;
+  const size_t avail = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 2048 /*bias, weight scale*/;
   p.x_slots = 0;
   if (gdn_mode && p.tma_out) {
     // GDN is bound by the x / y / norm streams, not by its short K loop: two operand stages, and every remaining
@@ -788,7 +810,7 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
     p.stages = (int)((avail - epi) / stage);
     if (p.stages > 8) p.stages = 8;
   }
-  p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 1024;
+  p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 2048;
   p.x_bytes = ((size_t)N * H * W * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.b_bytes = ((size_t)p.phases * p.CoutPad * p.Tmax * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.total_bytes = 2 * p.x_bytes + 2 * p.b_bytes + 1024;
@@ -804,10 +826,29 @@ size_t tc2_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int W
 
 // Generic launcher.  (N,Cin,H,W) gathered tensor, (Cout,Ho,Wo) written tensor, weight strides of the written /
 // gathered channel axes.
+int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
+                  int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
+                  int fixed_point, const float* x, const float* w, const float* w_scale, const float* bias,
+                  const float* gdn_x, float* norm_out, float* y, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                  const char* name);
 int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
                int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
                int fixed_point, const float* x, const float* w, const float* bias, const float* gdn_x, float* norm_out,
                float* y, void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name) {
+  return tc2_launch_wq(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, pad, transposed, s_co, s_ci, act, slope, in_square,
+                       gdn_mode, fixed_point, x, w, nullptr, bias, gdn_x, norm_out, y, workspace, workspace_bytes, s, name);
+}
+// w_scale != nullptr: `w` holds bf16-exact integers (codes minus zero point) and w_scale[Cout] the per-output-channel
+// step size: y = act(conv(x, w) * w_scale + bias) with two MMA passes per product.
+int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
+                  int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
+                  int fixed_point, const float* x, const float* w, const float* w_scale, const float* bias,
+                  const float* gdn_x, float* norm_out, float* y, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                  const char* name) {
+  if (w_scale && gdn_mode) {
+    set_error("%s: integer-weight mode does not combine with gdn_mode", name);
+    return B200LIC_ERR_ARG;
+  }
   const int has_norm = (gdn_mode && norm_out) ? 1 : 0;
   Tc2Plan p = make_plan2(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed, gdn_mode, has_norm);
   if (!p.ok) {
@@ -858,6 +899,11 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
     if (!tc_encode_map_ex(&mbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bh, 4, bdims, bstrides, bbox, bestr))
       return B200LIC_ERR_CUDA;
     mbl = mbh;
+    if (w_scale) {                              // hi slab only
+      cuuint32_t bbox1[4] = {32, (cuuint32_t)p.BN, 1, 1};
+      if (!tc_encode_map_ex(&mbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bh, 4, bdims, bstrides, bbox1, bestr))
+        return B200LIC_ERR_CUDA;
+    }
     // fp32 NCHW output-shaped tensors: (W, H, C, N), box = one staging chunk
     cuuint64_t odims[4] = {(cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)Cout, (cuuint64_t)N};
     cuuint64_t ostr[3] = {(cuuint64_t)Wo * 4, (cuuint64_t)Wo * Ho * 4, (cuuint64_t)Wo * Ho * Cout * 4};
@@ -887,7 +933,7 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
     dbg_mode = e ? atoi(e) : 0;
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
-            p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, p.chains, act, slope, gdn_mode, fixed_point,
+            p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, w_scale ? 1 : p.chains, w_scale ? 1 : 0, act, slope, gdn_mode, fixed_point,
             p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, dbg_mode};
   static bool attr_set = false;
   if (!attr_set) {
@@ -908,8 +954,8 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
   const long long items = (long long)p.phases * p.n_tiles * p.m_groups;
   const int sms = num_sms();
   const int grid = (int)(items < sms ? items : sms);
-  tc2_gather_gemm_kernel<<<grid, kT2Threads, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, gdn_x, norm_out,
-                                                                y, dbg);
+  tc2_gather_gemm_kernel<<<grid, kT2Threads, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
+                                                                norm_out, y, dbg);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

@@ -224,6 +224,23 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- integer weights n = code - zero_point (the operand of the two-pass forward, b200lic_conv_fwd_wq) ----------------
+__global__ void __launch_bounds__(256) wq_int_weights_kernel(const float* __restrict__ w, const float* __restrict__ alpha,
+                                                              const float* __restrict__ delta, const float* __restrict__ zp,
+                                                              size_t n, int ch, int inner, float top,
+                                                              float* __restrict__ w_int) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / inner) % ch);
+    const float d = __ldg(delta + c), z = __ldg(zp + c);
+    const float t = __fdiv_rn(w[i], d);
+    float q;
+    if (alpha == nullptr) q = __fadd_rn(rintf(t), z);                                     // quantizer.py:175
+    else q = __fadd_rn(__fadd_rn(floorf(t), __ldg(alpha + i) >= 0.f ? 1.f : 0.f), z);     // quantizer.py:437-449, hard
+    q = fminf(fmaxf(q, 0.f), top);
+    w_int[i] = __fsub_rn(q, z);
+  }
+}
+
 // ---- learned step size (LSQ) ------------------------------------------------------------------------------
 // d loss / d delta[c] by the autograd of the fake-quant expressions with delta as the leaf (the reference keeps this
 // option as commented-out code: quantizer.py:166-168, layer_opt.py:259-265, block_opt.py:254-266):
@@ -431,6 +448,18 @@ int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, const float* d
         w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
         reg_weight, 0.f, reg_loss, nullptr, sched);
   B200_LAUNCH_CHECK("adaround_bwd_adam_kernel(sched)");
+  return B200LIC_OK;
+}
+
+int b200lic_wq_int_weights(const float* w, const float* alpha, const float* delta, const float* zero_point, int outer,
+                           int ch, int inner, int n_levels, float* w_int, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && zero_point && w_int, "wq_int_weights: null pointer");
+  B200_REQUIRE(outer > 0 && ch > 0 && inner > 0 && n_levels >= 2, "wq_int_weights: bad shape");
+  const size_t n = (size_t)outer * ch * inner;
+  wq_int_weights_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(w, alpha, delta, zero_point, n, ch, inner,
+                                                                         (float)(n_levels - 1), w_int);
+  B200_LAUNCH_CHECK("wq_int_weights_kernel");
   return B200LIC_OK;
 }
 

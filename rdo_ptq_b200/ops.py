@@ -533,6 +533,40 @@ class _DeconvFn(torch.autograd.Function):
         return dx, dw, None, None, None, None, None, None, None
 
 
+def wq_int_weights(w, delta, zp, axis, n_levels, alpha=None):
+    """n = code - zero_point (integer-valued fp32): nearest rounding, or hardened AdaRound when `alpha` is given."""
+    w = _c(w, "weight")
+    outer, ch, inner = channel_view(w.shape, axis)
+    out = torch.empty_like(w)
+    call("wq_int_weights", _p(w), _p(None if alpha is None else _c(alpha)), _p(_c(delta.reshape(-1))),
+         _p(_c(zp.reshape(-1))), outer, ch, inner, int(n_levels), _p(out))
+    return out
+
+
+def conv_wq(x, w_int, w_scale, bias=None, stride=1, padding=0, output_padding=0, dilation=1, groups=1, transposed=False,
+            act=ACT_NONE, slope=0.01, fixed_pt=0):
+    """Inference-only forward with integer-valued weights and a per-output-channel scale (two tensor-core passes):
+    act(conv(x, w_int) * w_scale + bias).  Returns None when the shape has no two-pass kernel (the caller then runs the
+    regular op on the dequantised weight)."""
+    if _sq(dilation, "dilation") != 1 or groups != 1:
+        return None
+    x, w_int, w_scale, bias = _c(x, "input"), _c(w_int, "weight"), _c(w_scale, "scale"), _c(bias, "bias")
+    d = conv_desc(x.shape, w_int.shape, stride, padding, transposed, output_padding, act=act, slope=slope,
+                  fixed_pt=fixed_pt)
+    ws, nws = _workspace(d, _lib.OP_DECONV_FWD if transposed else _lib.OP_CONV_FWD, x.device)
+    if ws is None:
+        return None
+    y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=x.device, dtype=torch.float32)
+    try:
+        call("deconv_fwd_wq" if transposed else "conv_fwd_wq", C.byref(d), _p(x), _p(w_int), _p(w_scale), _p(bias),
+             _p(y), _p(ws), nws)
+    except _lib.B200LicError as e:
+        if e.code == -4:                 # B200LIC_ERR_UNSUPPORTED: folded-tap layers keep the three-pass engine
+            return None
+        raise
+    return y
+
+
 def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1, act=ACT_NONE, slope=0.01, fixed_pt=0):  # noqa
     """Drop-in for F.conv2d on the hot path (dilation 1, groups 1), optional fused activation."""
     if _sq(dilation, "dilation") != 1 or groups != 1:

@@ -75,11 +75,23 @@ class QuantModule(nn.Module):
         act, slope = ops._act_id(self.activation_function)
         if self.is_ps:
             return ops.pixel_shuffle(input, self.fwd_kwargs, act, slope)
-        if self.use_weight_quant:
+        out = None
+        if self.use_weight_quant and not self.is_gdn and not torch.is_grad_enabled():
+            # hard-quantised weight, no gradient wanted (evaluation): integer weights + per-channel scale in the conv
+            # epilogue, two tensor-core passes instead of three (b200lic_conv_fwd_wq); same value up to fp32 rounding
+            iw = getattr(self.weight_quantizer, "int_weights", lambda _w: None)(self.weight)
+            if iw is not None:
+                out = ops.conv_wq(input, iw[0], iw[1], self.bias, transposed=self.if_tconv, act=act, slope=slope,
+                                  **self.fwd_kwargs)
+        if out is not None:
+            weight = bias = None
+        elif self.use_weight_quant:
             weight, bias = self.weight_quantizer(self.weight), self.bias
         else:
             weight, bias = self.org_weight, self.org_bias
-        if self.is_gdn:
+        if out is not None:
+            pass
+        elif self.is_gdn:
             out = self.fwd_func(input, weight, bias, **self.fwd_kwargs)
             if act != ops.ACT_NONE:
                 out = ops.add_act_fn(out, None, act, slope)

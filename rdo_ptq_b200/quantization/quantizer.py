@@ -104,6 +104,13 @@ class UniformAffineQuantizer(nn.Module):
         return ops.wq_fake_quant(x.detach(), self.delta, self.zero_point, self.channel_axis(x), self.n_levels,
                                  want=("codes",))
 
+    def int_weights(self, x):
+        """(code - zero_point, delta per output channel) of a conv / transposed-conv weight, or None when the two-pass
+        integer-weight forward does not apply (not initialised, more than 256 levels: |n| must be exact in bf16)."""
+        if not self.inited or self.n_levels > 256 or x.dim() != 4 or self.delta is None:
+            return None
+        return _int_weights(x, self.delta, self.zero_point, self.channel_axis(x), self.n_levels, self.tconv, None)
+
     def init_quantization_scale(self, x: torch.Tensor, channel_wise: bool = False):
         if 'max' not in self.scale_method:
             raise NotImplementedError(f"scale_method {self.scale_method!r}: only 'max'/'max_scale' run on the B200 path")
@@ -121,6 +128,17 @@ class UniformAffineQuantizer(nn.Module):
     def extra_repr(self):
         return (f'bit={self.n_bits}, scale_method={self.scale_method}, symmetric={self.sym}, '
                 f'channel_wise={self.channel_wise}, leaf_param={self.leaf_param}')
+
+
+def _int_weights(x, delta, zp, axis, n_levels, tconv, alpha):
+    cout = x.shape[1] if tconv else x.shape[0]
+    if axis is not None and axis != (1 if tconv else 0):
+        return None                                   # scale not along the output channels
+    n = ops.wq_int_weights(x.detach(), delta, zp, axis, n_levels, alpha)
+    scale = delta.reshape(-1)
+    if scale.numel() == 1:
+        scale = scale.expand(cout)
+    return n, scale.contiguous()
 
 
 class _AdaRoundFn(torch.autograd.Function):
@@ -154,6 +172,7 @@ class AdaRoundQuantizer(nn.Module):
         self.zero_point = uaq.zero_point
         self.n_levels = uaq.n_levels
         self.axis = uaq.channel_axis(weight_tensor)
+        self.tconv = uaq.tconv
         self.round_mode = round_mode
         self.alpha = None
         self.soft_targets = False
@@ -188,6 +207,13 @@ class AdaRoundQuantizer(nn.Module):
     def codes(self, x):
         return ops.adaround_fwd(x.detach(), self.alpha.detach(), self.delta, self.zero_point, self.axis, self.n_levels,
                                 False, want_codes=True)[1]
+
+    def int_weights(self, x):
+        """See UniformAffineQuantizer.int_weights; only the hardened quantiser has integer weights."""
+        if self.soft_targets or self._leaf is not None or self.n_levels > 256 or x.dim() != 4:
+            return None
+        return _int_weights(x, self.delta, self.zero_point, self.axis, self.n_levels, getattr(self, "tconv", False),
+                            self.alpha.detach())
 
     def extra_repr(self):
         return 'bit={}'.format(self.n_bits)

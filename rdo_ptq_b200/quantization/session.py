@@ -98,12 +98,15 @@ def cache_all_units(qnn: QuantModel, cali: torch.Tensor, units, batch: int = 8, 
 class _FixedWeight(torch.nn.Module):
     """Stand-in weight quantiser that returns a precomputed (nearest-rounded) weight: used by the streaming forwards."""
 
-    def __init__(self, w):
+    def __init__(self, w, iw=None):
         super().__init__()
-        self.w = w
+        self.w, self.iw = w, iw
 
     def forward(self, _x):
         return self.w
+
+    def int_weights(self, _x):
+        return self.iw
 
 
 class CalibrationSession:
@@ -202,7 +205,9 @@ class CalibrationSession:
         for m in qnn.modules():
             if isinstance(m, QuantModule) and m.org_weight is not None:
                 with torch.no_grad():
-                    self._fixed_w[m] = m.weight_quantizer(m.weight).detach().clone()
+                    q = m.weight_quantizer
+                    iw = None if m.is_gdn else getattr(q, "int_weights", lambda _w: None)(m.weight)
+                    self._fixed_w[m] = (q(m.weight).detach().clone(), iw)
         return self._stream_forward()
 
     @torch.no_grad()
@@ -237,7 +242,7 @@ class CalibrationSession:
         swapped = []
         for m, w in self._fixed_w.items():                  # nearest-rounded weights, whatever quantiser is installed
             swapped.append((m, m.weight_quantizer))
-            m.weight_quantizer = _FixedWeight(w)
+            m.weight_quantizer = _FixedWeight(*w)
         qnn.set_quant_state(True, False)
         with torch.cuda.stream(fork):
             run(0, None)

@@ -435,3 +435,44 @@ def test_entropy_kernels_full_size_properties(ops, dev):
     zh2, l2 = eb(z[:, :, :23, :31].contiguous())                # odd plane size: scalar path
     assert torch.equal(l1[:, :, :23, :31], l2) and torch.equal(zh[:, :, :23, :31], zh2)
     assert (l1 >= 1e-9).all() and (l1 <= 1).all()
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("shape", [(2, 32, 24, 40, 48, 5, 2), (1, 192, 32, 48, 192, 3, 1), (3, 64, 17, 23, 96, 5, 2)])
+def test_integer_weight_forward_matches_dequantised_forward(ops, dev, shape, transposed):
+    """b200lic_wq_int_weights is bit-exact (code - zero_point of the reference quantiser), and the two-pass forward on
+    (n, delta) equals the reference's conv on the dequantised weight (n * delta) within the 1e-4 per-layer bar."""
+    N, Cin, H, W, Cout, k, st = shape
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(N, Cin, H, W, generator=gen)
+    w = torch.randn((Cin, Cout, k, k) if transposed else (Cout, Cin, k, k), generator=gen) * 0.05
+    b = torch.randn(Cout, generator=gen)
+    uq = oq.UniformAffineQuantizer(n_bits=8, channel_wise=True, scale_method="max", tconv=transposed)
+    w_dq = uq(w)
+    axis = oq.channel_axis(w.shape, transposed)
+    n_ref = torch.clamp(torch.round(w / uq.delta) + uq.zero_point, 0, uq.n_levels - 1) - uq.zero_point
+    n = ops.wq_int_weights(w.to(dev), uq.delta.to(dev), uq.zero_point.to(dev), axis, uq.n_levels)
+    assert torch.equal(n.cpu(), n_ref)
+    assert torch.equal((n.cpu() * uq.delta), w_dq)
+    if transposed:
+        ref = F.leaky_relu(F.conv_transpose2d(x, w_dq, b, stride=st, padding=k // 2, output_padding=st - 1), 0.01)
+    else:
+        ref = F.leaky_relu(F.conv2d(x, w_dq, b, stride=st, padding=k // 2), 0.01)
+    y = ops.conv_wq(x.to(dev), n, uq.delta.reshape(-1).to(dev), b.to(dev), stride=st, padding=k // 2,
+                    output_padding=st - 1 if transposed else 0, transposed=transposed, act=ops.ACT_LEAKY_RELU, slope=0.01)
+    assert y is not None
+    assert rel_err(y, ref) < 1e-5, rel_err(y, ref)
+    # hardened AdaRound codes: floor(w/d) + (alpha >= 0)
+    ar = oq.AdaRoundQuantizer(uq, w)
+    with torch.no_grad():
+        ar.alpha.add_(torch.randn(ar.alpha.shape, generator=gen))
+    ar.soft_targets = False
+    n2 = ops.wq_int_weights(w.to(dev), uq.delta.to(dev), uq.zero_point.to(dev), axis, uq.n_levels,
+                            alpha=ar.alpha.detach().to(dev))
+    assert torch.equal(n2.cpu() * uq.delta, ar(w).detach())
+
+
+def test_integer_weight_forward_declines_folded_tap_layers(ops, dev):
+    x = torch.randn(1, 3, 32, 32).to(dev)
+    n = torch.randint(-100, 100, (16, 3, 5, 5)).float().to(dev)
+    assert ops.conv_wq(x, n, torch.ones(16, device=dev), None, stride=2, padding=2) is None
