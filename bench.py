@@ -103,6 +103,8 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: with NCCL_DEBUG=VERSION/INFO NCCL prints its banner on stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200LIC_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     _lib.call("actq_stats_init", ops._p(torch.empty(2, dtype=torch.int32, device=dev)), 1, stream=None)  # arch gate early
 

@@ -137,6 +137,11 @@ B200LIC_API int b200lic_actq_stats_init(float* minmax, int C, b200lic_stream_t s
 B200LIC_API int b200lic_actq_stats(const float* x, int N, int C, int HW, float* minmax, b200lic_stream_t stream);
 B200LIC_API int b200lic_actq_apply(const float* x, const float* minmax, int N, int C, int HW, int n_bits, float* out,
                        float* codes, b200lic_stream_t stream);
+/* The three calls above in one launch (no minmax buffer): one thread-block cluster per channel keeps the channel's
+ * elements in (distributed) shared memory between the min/max reduction and the quantisation, so the activation is read
+ * from HBM once.  Bit-identical to stats_init + stats + apply. */
+B200LIC_API int b200lic_actq_fused(const float* x, int N, int C, int HW, int n_bits, float* out, float* codes,
+                       b200lic_stream_t stream);
 B200LIC_API int b200lic_fixed_point(const float* x, size_t n, int a_l, int a_r, float* out, b200lic_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -49,6 +49,7 @@ SIGNATURES = {
     "actq_stats_init": [_P, _I],
     "actq_stats": [_P, _I, _I, _I, _P],
     "actq_apply": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "actq_fused": [_P, _I, _I, _I, _I, _P, _P],
     "fixed_point": [_P, _SZ, _I, _I, _P],
     "gaussian_lik_fwd": [_P, _P, _P, _I, _I, _I, _LL, _F, _F, _P, _P, _P],
     "round_latent": [_P, _P, _SZ, _P],

@@ -101,6 +101,115 @@ __global__ void __launch_bounds__(256) actq_apply_kernel(const float* __restrict
   }
 }
 
+// ---- K8 fused: statistics + apply in ONE launch, one thread-block cluster per channel ---------------------------------
+// The three-launch form (init, min/max with global atomics, apply) reads the activation twice from HBM (12 B/elem) and
+// costs three launch latencies per layer -- the dominant share of the W8A8 evaluation forward's non-GEMM time
+// (profiles/README.md r1d: 27 % of the Cheng2020 forward).  Here the CTAs of a cluster split the (N, H*W) elements of a
+// channel, keep their slice in shared memory while reducing it, exchange the per-CTA (min, max) through distributed
+// shared memory, and quantise the slice they still hold: 8 B/elem, no atomics, no initialisation pass.  Slices that
+// do not fit in shared memory are re-read from global memory (L2) in the second pass.  Arithmetic is actq_one(), so
+// codes and outputs are bit-identical to the three-launch path.
+constexpr int kFuseThreads = 512;
+constexpr int kFuseKeepBytes = 160 * 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_peer_f32(const float* local, uint32_t rank) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t pa;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pa) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(pa));
+  return v;
+}
+
+__global__ void __launch_bounds__(kFuseThreads, 1)
+    actq_cluster_kernel(const float* __restrict__ x, int N, int C, int HW, int S, int ps, int keep, float L,
+                        float* __restrict__ out, float* __restrict__ codes) {
+  extern __shared__ float4 kept4[];
+  float* kept = reinterpret_cast<float*>(kept4);
+  __shared__ float s_mn[kFuseThreads / 32], s_mx[kFuseThreads / 32];
+  __shared__ float s_stat[2];
+  const uint32_t rank = cluster_ctarank();
+  const int c = blockIdx.x / S;
+  // CTA `rank` owns elements [beg, end) of EVERY plane (n, c): no index division anywhere in the loops
+  const int beg = (int)rank * ps, end = min(HW, beg + ps);
+  const bool vec = (HW & 3) == 0 && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)codes) & 15) == 0;   // ps % 4 == 0
+  float mn = INFINITY, mx = -INFINITY;
+  for (int n = 0; n < N; ++n) {
+    const float* p = x + ((size_t)n * C + c) * HW;
+    if (vec) {
+      float4* k4 = kept4 + (size_t)n * (ps >> 2);
+      for (int i = beg + 4 * (int)threadIdx.x; i < end; i += 4 * kFuseThreads) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
+        if (keep) k4[(i - beg) >> 2] = v;
+        mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+        mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+      }
+    } else {
+      float* k1 = kept + (size_t)n * ps;
+      for (int i = beg + (int)threadIdx.x; i < end; i += kFuseThreads) {
+        const float v = __ldg(p + i);
+        if (keep) k1[i - beg] = v;
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+      }
+    }
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) {
+    s_mn[threadIdx.x >> 5] = mn;
+    s_mx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < kFuseThreads / 32; ++i) {
+      mn = fminf(mn, s_mn[i]);
+      mx = fmaxf(mx, s_mx[i]);
+    }
+    s_stat[0] = mn;
+    s_stat[1] = mx;
+  }
+  cluster_sync_all();                              // every CTA's (min, max) is visible cluster-wide
+  float gmn = INFINITY, gmx = -INFINITY;
+  for (int r = 0; r < S; ++r) {
+    gmn = fminf(gmn, ld_peer_f32(&s_stat[0], (uint32_t)r));
+    gmx = fmaxf(gmx, ld_peer_f32(&s_stat[1], (uint32_t)r));
+  }
+  const float m = gmn, rr = fmaxf(__fsub_rn(gmx, gmn), 1e-6f);
+  for (int n = 0; n < N; ++n) {
+    const size_t base = ((size_t)n * C + c) * HW;
+    if (vec) {
+      const float4* k4 = kept4 + (size_t)n * (ps >> 2);
+      for (int i = beg + 4 * (int)threadIdx.x; i < end; i += 4 * kFuseThreads) {
+        const float4 v = keep ? k4[(i - beg) >> 2] : __ldg(reinterpret_cast<const float4*>(x + base + i));
+        float4 o, q;
+        o.x = actq_one(v.x, m, rr, L, &q.x);
+        o.y = actq_one(v.y, m, rr, L, &q.y);
+        o.z = actq_one(v.z, m, rr, L, &q.z);
+        o.w = actq_one(v.w, m, rr, L, &q.w);
+        *reinterpret_cast<float4*>(out + base + i) = o;
+        if (codes) *reinterpret_cast<float4*>(codes + base + i) = q;
+      }
+    } else {
+      const float* k1 = kept + (size_t)n * ps;
+      for (int i = beg + (int)threadIdx.x; i < end; i += kFuseThreads) {
+        float q;
+        out[base + i] = actq_one(keep ? k1[i - beg] : __ldg(x + base + i), m, rr, L, &q);
+        if (codes) codes[base + i] = q;
+      }
+    }
+  }
+  cluster_sync_all();                              // no CTA leaves while a peer may still read its s_stat
+}
+
 __global__ void __launch_bounds__(256) fixed_point_kernel(const float* __restrict__ x, size_t n, float lo, float hi,
                                                            float mult, float* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -162,6 +271,50 @@ int b200lic_actq_apply(const float* x, const float* minmax, int N, int C, int HW
   actq_apply_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
       x, reinterpret_cast<const unsigned*>(minmax), C, HW, chunks, (float)((1 << n_bits) - 1), out, codes);
   B200_LAUNCH_CHECK("actq_apply_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_actq_fused(const float* x, int N, int C, int HW, int n_bits, float* out, float* codes,
+                       b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && out && N > 0 && C > 0 && HW > 0, "actq_fused: bad arguments");
+  B200_REQUIRE(n_bits >= 2 && n_bits <= 16, "actq_fused: n_bits=%d outside [2,16]", n_bits);
+  const long long bytes = (long long)N * HW * 4;
+  // cluster size: enough CTAs to keep the channel's elements in shared memory, and enough to occupy the chip
+  int S = 1;
+  while (S < 8 && bytes > (long long)S * kFuseKeepBytes) S *= 2;
+  while (S < 8 && (long long)C * S < 2LL * num_sms() && HW / (2 * S) >= 2048) S *= 2;
+  const int ps = ((HW + S - 1) / S + 3) / 4 * 4;              // elements of every plane owned by one CTA
+  const int keep = (long long)N * ps * 4 <= (long long)kFuseKeepBytes ? 1 : 0;
+  const size_t smem = keep ? (size_t)N * ps * 4 : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(actq_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuseKeepBytes);
+    if (e != cudaSuccess) {
+      set_error("actq_fused: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+      return B200LIC_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(C * S), 1, 1);
+  cfg.blockDim = dim3(kFuseThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)S;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, actq_cluster_kernel, x, N, C, HW, S, ps, keep, (float)((1 << n_bits) - 1), out,
+                                     codes);
+  if (e != cudaSuccess) {
+    set_error("actq_fused: launch failed: %s", cudaGetErrorString(e));
+    return B200LIC_ERR_CUDA;
+  }
+  B200_LAUNCH_CHECK("actq_cluster_kernel");
   return B200LIC_OK;
 }
 

@@ -126,6 +126,13 @@ def adaround_bwd_adam(w, alpha, delta, zp, d_wq, exp_avg, exp_avg_sq, axis, n_le
 
 
 # ------------------------------------------------------------------------------------------------ K8
+# One cluster launch (b200lic_actq_fused) instead of stats_init + stats + apply; both paths are bit-identical.  Measured
+# (scripts/actq_time.py): the cluster kernel wins on single-image activations up to ~75 MB (launch latency, one HBM
+# read), the three-launch path on batches and on 2K-size tensors (more CTAs in flight), so the wrapper picks by shape.
+ACTQ_FUSED = True
+ACTQ_FUSED_MAX_BYTES = 80 * 1000 * 1000
+
+
 def act_quant(x, n_bits=8, want_codes=False):
     """Dynamic per-channel fake-quant of a [N,C,H,W] (or [N,C]) activation; result is detached (quantizer.py:100)."""
     x = _c(x.detach(), "activation")
@@ -135,9 +142,12 @@ def act_quant(x, n_bits=8, want_codes=False):
         N, Cc, HW = x.shape[0], x.shape[1], 1
     else:
         raise NotImplementedError("act_quant: only NCHW / NC activations are on the hot path")
-    keys = torch.empty(2 * Cc, device=x.device, dtype=torch.int32)
     out = torch.empty_like(x)
     codes = torch.empty_like(x) if want_codes else None
+    if ACTQ_FUSED and (ACTQ_FUSED == "always" or (N == 1 and 4 * x.numel() <= ACTQ_FUSED_MAX_BYTES)):
+        call("actq_fused", _p(x), N, Cc, HW, n_bits, _p(out), _p(codes))
+        return (out, codes) if want_codes else out
+    keys = torch.empty(2 * Cc, device=x.device, dtype=torch.int32)
     call("actq_stats_init", _p(keys), Cc)
     call("actq_stats", _p(x), N, Cc, HW, _p(keys))
     call("actq_apply", _p(x), _p(keys), N, Cc, HW, n_bits, _p(out), _p(codes))

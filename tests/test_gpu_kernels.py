@@ -476,3 +476,32 @@ def test_integer_weight_forward_declines_folded_tap_layers(ops, dev):
     x = torch.randn(1, 3, 32, 32).to(dev)
     n = torch.randint(-100, 100, (16, 3, 5, 5)).float().to(dev)
     assert ops.conv_wq(x, n, torch.ones(16, device=dev), None, stride=2, padding=2) is None
+
+
+@pytest.mark.parametrize("shape", [(1, 192, 32, 48), (8, 192, 64, 64), (1, 5, 7, 9), (3, 320, 1, 1), (2, 3, 512, 768),
+                                   (1, 192, 256, 384), (1, 24, 768, 1024)])
+def test_fused_activation_quant_is_bit_identical_to_the_three_launch_path(ops, dev, shape):
+    """b200lic_actq_fused (one cluster launch; slices kept in shared memory, or re-read when they do not fit) against
+    stats_init + stats + apply and against the oracle's per-channel loop: outputs and integer codes bit for bit."""
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(shape, generator=gen) * torch.rand(1, shape[1], 1, 1, generator=gen) * 5
+    xd = x.to(dev)
+    ops.ACTQ_FUSED = "always"
+    yf, cf = ops.act_quant(xd, 8, want_codes=True)
+    ops.ACTQ_FUSED = False
+    try:
+        y3, c3 = ops.act_quant(xd, 8, want_codes=True)
+    finally:
+        ops.ACTQ_FUSED = True
+    assert torch.equal(yf, y3) and torch.equal(cf, c3)
+    if x.numel() <= 4_000_000:
+        ref, codes = oq.act_quant(x, 8, return_codes=True)
+        assert torch.equal(yf.cpu(), ref) and torch.equal(cf.cpu(), codes)
+    x2 = x[:, :, :, : max(1, shape[3] - 1)].contiguous().to(dev)          # ragged rows: scalar path
+    ops.ACTQ_FUSED = False
+    y3 = ops.act_quant(x2, 8)
+    ops.ACTQ_FUSED = "always"
+    try:
+        assert torch.equal(ops.act_quant(x2, 8), y3)
+    finally:
+        ops.ACTQ_FUSED = True
