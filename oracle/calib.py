@@ -143,6 +143,31 @@ class RDTask:
         self.codec.entropy_bottleneck.ste_round = self.codec.gaussian_conditional.ste_round = False
 
 
+class CoderTask:
+    """layer_opt.py:45-75 (fp_out), :219-224 (fp_net_out) and :296-299 (quant_net_out) with `module_list` = the later,
+    untrained modules of the unit's own sub-network taken by position (what `find_unquantized_module` intends; for
+    compressai child names its string test never matches)."""
+
+    def __init__(self, qnn: QuantModel, unit_path: str, fp_unit_out, p=2.0):
+        coder, _, rest = unit_path.partition(".")
+        k = int(rest.split(".")[0])
+        self.tail = list(getattr(qnn.model, coder).children())[k + 1:]
+        self.round, self.p = coder == "g_a", p
+        with torch.no_grad():
+            self.target = self._run(fp_unit_out)
+
+    def _run(self, v):
+        for m in self.tail:
+            v = m(v)
+        return round_ste(v) if self.round else v         # layer_opt.py:67-70
+
+    def __call__(self, out, idx):
+        return lp_loss(self._run(out), self.target[idx], p=self.p)
+
+    def close(self):
+        pass
+
+
 def reconstruct(model: QuantModel, unit, unit_id: int, unit_name: str, cali_data, batch_size=4, iters=20000,
                 weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5, act_quant=False, p=2.0, task_p=2.0,
                 plan: DrawPlan = None, trace=None, rd_task: RDTask = None, learn_delta=False,

@@ -96,7 +96,7 @@ class BaseQuantBlock(nn.Module):
                 m.set_quant_state(weight_quant, act_quant)
 
     def _aq(self, t):
-        return act_quant(t) if (self.use_act_quant and self.trained) else t
+        return self.act_quantizer(t, True) if (self.use_act_quant and self.trained) else t
 
 
 class QuantRBWS(BaseQuantBlock):

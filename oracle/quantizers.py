@@ -116,6 +116,10 @@ class UniformAffineQuantizer(nn.Module):
     ('max', 'max_scale', 'mse') are carried.  `n_bits` up to 16 is accepted (Q6: the reference
     asserts <= 8, config 4 needs 10)."""
 
+    # Extension switch (not in the reference, SURVEY Q6): thread n_bits into the dynamic activation quantiser, which the
+    # reference hard-wires to 8 bit (quantizer.py:81-121); BASELINE config 4 (W10A10) sets it.  Default = reference.
+    act_bits_follow_n_bits = False
+
     def __init__(self, n_bits=8, symmetric=False, channel_wise=False, scale_method="max",
                  leaf_param=False, tconv=False, act=False, prob=1.0):
         super().__init__()
@@ -172,7 +176,7 @@ class UniformAffineQuantizer(nn.Module):
     def forward(self, x: torch.Tensor, act: bool = False):
         """:156-184."""
         if act:
-            return act_quant(x)
+            return act_quant(x, self.n_bits if self.act_bits_follow_n_bits else 8)
         if not self.inited:
             if self.leaf_param:
                 return x

@@ -303,6 +303,25 @@ def round_latent_ste(y, means=None):
     return _RoundLatentSTE.apply(y, means)
 
 
+class _LpLossFn(torch.autograd.Function):
+    """scale * sum |pred - tgt|^p with its gradient w.r.t. pred, both from one K11 pass."""
+
+    @staticmethod
+    def forward(ctx, pred, tgt, p, scale):
+        val, g = lp_loss_fwd_bwd(pred, tgt, p, scale=scale, grad_scale=scale)
+        ctx.save_for_backward(g)
+        return val.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (g,) = ctx.saved_tensors
+        return g * g_out, None, None, None
+
+
+def lp_loss_fn(pred, tgt, p=2.0, scale=1.0):
+    return _LpLossFn.apply(pred, tgt, float(p), float(scale))
+
+
 class _RDLossFn(torch.autograd.Function):
     """RateDistortionLoss (losses/losses.py:20-28, MSE metric): loss = lmbda*255^2*mean((x_hat-x)^2) + bits/pixels.
     One K11 pass yields the distortion value and its gradient; bits come from the likelihood kernels' reductions."""

@@ -10,7 +10,7 @@ from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule
 from .quant_model import QuantModel
 from .quantizer import StraightThrough
-from .recon import DrawPlan, RDTask, UnitTrainer, run_reconstruction
+from .recon import CoderTask, DrawPlan, RDTask, UnitTrainer, run_reconstruction
 from .utils import save_inp_oup_data, set_mode
 
 
@@ -35,11 +35,16 @@ def _task_p(args, default=2.0):
     return default if v == "rd" else float(v)
 
 
-def _rd_task(model, unit_path, cali_data, args, task, lmbda):
+def _rd_task(model, unit_path, cali_data, args, task, lmbda, fp_unit_out=None):
     """`task='rd'` (or args.task_loss == 'rd'): the R + lambda*D task criterion (recon.RDTask); lambda from `lmbda` or
-    args.lmbda (main2.py's --lmbda)."""
+    args.lmbda (main2.py's --lmbda).  `task='coder'`: the reference's fp_out tail by the unit's real position
+    (recon.CoderTask)."""
     if task is None and args is not None and getattr(args, "task_loss", None) == "rd":
         task = "rd"
+    if task == "coder":
+        if unit_path is None:
+            raise ValueError("task='coder' needs unit_path (the unit's path inside the codec, e.g. 'g_a.2')")
+        return CoderTask(model, unit_path, fp_unit_out, _task_p(args))
     if task != "rd":
         return None
     if unit_path is None:
@@ -83,7 +88,7 @@ def layer_reconstruction(model: QuantModel, layer: QuantModule, layer_name: str,
         org_act_func, layer.activation_function = layer.activation_function, StraightThrough()
     if layer.org_weight is None:                # PixelShuffle wrapper: nothing to learn (reference :245-246)
         return None
-    rd = _rd_task(model, unit_path, cali_data, args, task, lmbda)
+    rd = _rd_task(model, unit_path, cali_data, args, task, lmbda, cached_outs)
     trainer = UnitTrainer(layer, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group,
                           rd_task=rd, learn_delta=learn_delta)
     losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace,

@@ -72,6 +72,40 @@ class RDTask:
         self.codec.entropy_bottleneck.ste_round = self.codec.gaussian_conditional.ste_round = False
 
 
+class CoderTask:
+    """The task term the reference computes when `find_unquantized_module` finds later modules (layer_opt.py:45-75,
+    219-224, 296-299): the unit's output is pushed through the not-yet-trained modules of the SAME sub-network in FP32
+    (plus round_ste when that sub-network is g_a) and compared with the same tail applied to the FP unit output:
+    task = lp_loss(tail(out_quant), tail(out_fp), p=args.task_loss).  With compressai's "0", "1", ... child names the
+    reference's name test never fires and the tail is empty; `task="coder"` applies the intended rule by
+    the unit's real position (`unit_path`, e.g. "g_a.2")."""
+
+    def __init__(self, qnn, unit_path: str, fp_unit_out: torch.Tensor, p: float = 2.0, batch: int = 8):
+        coder, _, rest = unit_path.partition(".")
+        k = int(rest.split(".")[0])
+        self.tail = list(getattr(qnn.model, coder).children())[k + 1:]
+        self.round, self.p = coder == "g_a", float(p)
+        outs = []
+        with torch.no_grad():
+            for i in range(0, fp_unit_out.size(0), batch):
+                outs.append(self._run(fp_unit_out[i:i + batch]))
+        self.target = torch.cat(outs)
+
+    def _run(self, v):
+        for m in self.tail:
+            v = m(v)
+        if self.round:
+            v = ops.round_latent_ste(v) if (torch.is_grad_enabled() and v.requires_grad) else ops.round_latent(v)
+        return v
+
+    def __call__(self, out: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        v = self._run(out)
+        return ops.lp_loss_fn(v, self.target[idx], self.p, 1.0 / (v.numel() // v.shape[1]))
+
+    def close(self):
+        pass
+
+
 class UnitTrainer:
     """State of one reconstruction problem: the QuantModules whose alpha is trained, Adam moments, schedules."""
 

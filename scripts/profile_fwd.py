@@ -51,10 +51,13 @@ def main():
     ap.add_argument("--hw", action="append")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--eager", action="store_true")
+    ap.add_argument("--bits", type=int, default=8, help="W/A bit width (10 = BASELINE config 4, W10A10)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     for arch in args.arch or ["mbt2018-mean"]:
-        qnn = build(arch, dev)
+        from rdo_ptq_b200.quantization.quantizer import UniformAffineQuantizer
+        UniformAffineQuantizer.act_bits_follow_n_bits = args.bits != 8
+        qnn = build(arch, dev, args.bits)
         first = True
         for hw in args.hw or ["512x768"]:
             h, w = (int(v) for v in hw.split("x"))
@@ -84,7 +87,7 @@ def main():
                 b.record()
                 torch.cuda.synchronize()
             ms = a.elapsed_time(b) / args.reps
-            print(json.dumps({"arch": arch, "hw": hw, "padded": list(x.shape[2:]), "ms_per_image": ms,
+            print(json.dumps({"arch": arch, "bits": args.bits, "hw": hw, "padded": list(x.shape[2:]), "ms_per_image": ms,
                               "mpx_s": h * w / 1e6 / (ms / 1e3)}))
 
 

@@ -451,3 +451,57 @@ def test_streaming_session_matches_cached_session(dev):
     for n in lc:
         # the batch is the whole pool in both runs, only its row order differs: the mean loss is order-independent
         assert ls[n]["rec"] == pytest.approx(lc[n]["rec"], rel=2e-3, abs=1e-7), n
+
+
+def test_w10a10_cheng2020_forward_parity(dev):
+    """BASELINE config 4: Cheng2020-attention at W10A10.  The reference asserts n_bits <= 8 and hard-wires 8-bit
+    activations; both sides lift that through the same additive switch.  10-bit weight codes bit-exact,
+    per-layer outputs within 1e-4, activation codes on the 1023-level grid, bpp / PSNR against the oracle."""
+    from rdo_ptq_b200 import evaluate as E
+    from rdo_ptq_b200.quantization.quantizer import UniformAffineQuantizer as PUAQ
+    wq = dict(n_bits=10, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=10, channel_wise=True, scale_method="max", leaf_param=False)
+    om, pm, Q = build_pair("cheng2020-attn", dict(N=24), 0.6, dev)
+    x = synth.synthetic_image(64, 128)
+    with torch.no_grad():
+        om(x), pm(x.to(dev))
+    oq.UniformAffineQuantizer.act_bits_follow_n_bits = PUAQ.act_bits_follow_n_bits = True
+    try:
+        oqm, pqm = owrap.QuantModel(om, wq, aq).eval(), Q.QuantModel(pm, wq, aq).eval()
+        for q in (oqm, pqm):
+            q.set_quant_state(True, False)
+        ref, ref_rows = per_layer_io(oqm, x, (owrap.QuantModule,))
+        with torch.no_grad():
+            pqm(x.to(dev))
+        pmods = dict((n, m) for n, m in pqm.named_modules() if isinstance(m, Q.QuantModule))
+        omods = dict((n, m) for n, m in oqm.named_modules() if isinstance(m, owrap.QuantModule))
+        top = 0.0
+        for n, m in pmods.items():
+            if m.weight is not None:
+                codes = m.weight_quantizer.codes(m.weight).cpu()
+                assert torch.equal(codes, omods[n].weight_quantizer.codes(omods[n].weight)), n
+                top = max(top, codes.max().item())
+        assert 255 < top <= 1023                                   # the 10-bit grid is really in use
+
+        def chk(name, a, b):
+            assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
+        layer_local_parity(ref_rows, pmods, dev, chk)
+        for q in (oqm, pqm):
+            for m in q.modules():
+                if hasattr(m, "trained"):
+                    m.trained = True
+            q.set_quant_state(True, True)
+        ref10, rows10 = per_layer_io(oqm, x, (owrap.QuantModule,))
+        with torch.no_grad():
+            out10 = pqm(x.to(dev))
+
+        def chk10(name, a, b):
+            step = (b.amax() - b.amin()).item() / 1023 + 1e-12
+            assert ((a - b).abs() <= 1.01 * step).all(), name
+        layer_local_parity(rows10, pmods, dev, chk10)
+        bpp_ref, bpp = oeval.compute_bpp(ref10), E.compute_bpp(out10)
+        p_ref = oeval.compute_psnr(x, ref10["x_hat"].clamp(0, 1))
+        p = E.compute_psnr(out10["x_hat"], x.to(dev), clamp=True)
+        assert abs(bpp - bpp_ref) < 0.01 * bpp_ref + 1e-3 and abs(p - p_ref) < 0.1
+    finally:
+        oq.UniformAffineQuantizer.act_bits_follow_n_bits = PUAQ.act_bits_follow_n_bits = False

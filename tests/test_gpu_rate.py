@@ -260,3 +260,31 @@ def test_session_with_learned_step_size_graph_matches_eager(dev):
     for n in de:
         for a, b in zip(de[n], dg[n]):
             assert rel_err(b, a) < 1e-4, n
+
+
+@pytest.mark.parametrize("layer_path", ["g_a.2", "g_s.2", "h_s.0"])
+def test_layer_reconstruction_with_coder_task(dev, layer_path):
+    """task = lp_loss(tail(out_quant), tail(out_fp)) over the later modules of the unit's own sub-network (+ round_ste
+    for g_a): the reference's fp_out rule (layer_opt.py:45-75) applied by position."""
+    oqm, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+    sub, idx = layer_path.split(".")
+    olayer, player = getattr(oqm.model, sub)[int(idx)], getattr(pqm.model, sub)[int(idx)]
+    kw = dict(batch_size=2, iters=12, weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5)
+    otrace, ptrace = {}, {}
+    # the oracle's target needs the FP unit outputs: the same cache `reconstruct` builds
+    (_, _), fp_out = ocalib.save_inp_oup_data(oqm, olayer, cali, False, False)
+    oqm.set_quant_state(False, False)
+    otask = ocalib.CoderTask(oqm, layer_path, fp_out, 2.0)
+    olosses = ocalib.reconstruct(oqm, olayer, 3, idx, cali, plan=ocalib.DrawPlan(), trace=otrace, rd_task=otask, **kw)
+
+    class Args:
+        task_loss = 2.0
+    plosses = Q.layer_reconstruction(pqm, player, idx, cali.to(dev), asym=True, act_quant=False, opt_mode='mse',
+                                     args=Args(), plan=ReplayPlan(), unit_id=3, trace=ptrace, task="coder",
+                                     unit_path=layer_path, log_every=1, **kw)
+    h0 = otrace["h0"]
+    inner = (h0 > 1e-4) & (h0 < 1 - 1e-4)
+    assert rel_err(ptrace["d_alpha"][0].cpu()[inner], otrace["grad0"][0][inner]) < 1e-3
+    assert abs(plosses[0]["total"] - olosses[0]) < 1e-3 * abs(olosses[0]) + 1e-7, (plosses[0], olosses[0])
+    a_ref, a_gpu = olayer.weight_quantizer.alpha.data, player.weight_quantizer.alpha.data.cpu()
+    assert (a_ref - a_gpu)[inner].abs().max().item() < 5e-3
