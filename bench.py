@@ -143,7 +143,8 @@ def run_cuda(args):
 
     # ---- device-resident run (value) -------------------------------------------------------------------------------
     qnn = build()
-    sess = CalibrationSession(qnn, cali, batch_size=PER_GPU_BATCH, host_caches=False, **CALIB)
+    skw = json.loads(os.environ.get("B200LIC_SESSION_KW", "{}"))       # experiments: n_streams, overlap_update, ...
+    sess = CalibrationSession(qnn, cali, batch_size=PER_GPU_BATCH, host_caches=False, **CALIB, **skw)
     n_units = len(sess.units)
     macs = layer_macs(sess.units, sess.caches)
     if sampler:
@@ -226,31 +227,43 @@ def run_cuda(args):
     e2e_cached = e2e_run(True)
     e2e_cached["mode"] = "host-resident activation caches: batch rows of every unit H2D each step (PCIe-bound)"
 
-    # ---- secondary metric: W8A8 evaluation forward Mpx/s on 768x512 ---------------------------------------------------
-    fwd = None
-    if rank == 0 and not args.skip_fwd:
+    # ---- secondary metric: W8A8 evaluation forward Mpx/s (BASELINE metric's second half) -------------------------------
+    # Images are independent, so evaluation shards them over the ranks: every rank runs its own image and
+    # the aggregate is world * pixels / max-over-ranks time.  768x512 (Kodak shape, configs 1/4) and 2K CLIC shape
+    # (1365x2048 padded to 1536x2048, config 5; Mpx/s counts the unpadded pixels).
+    fwd, fwd_2k = None, None
+    if not args.skip_fwd:
         qnn3 = build()
-        img = synth.synthetic_image(512, 768).to(dev)
-        qnn3.set_quant_state(True, False)
-        with torch.no_grad():
-            qnn3(E.pad(img, 256))
-            for m in qnn3.modules():
-                if hasattr(m, "trained"):
-                    m.trained = True
-            qnn3.set_quant_state(True, True)
-            qnn3.model.g_s[-1].set_quant_state(True, False)
-            gf = E.GraphedForward(qnn3)
+        res = {}
+        for tag, (h, w_) in (("768x512", (512, 768)), ("2k", (1365, 2048))):
+            img = synth.synthetic_image(h, w_, seed=1005 + rank).to(dev)
             xp = E.pad(img, 256)
-            for _ in range(3):                 # eager pass, capture pass, first replay
-                gf(xp)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(5):
-                gf(xp)
-            b.record()
-            torch.cuda.synchronize()
-        fwd = 5 * 512 * 768 / 1e6 / (a.elapsed_time(b) / 1e3)
+            with torch.no_grad():
+                if not res:
+                    qnn3.set_quant_state(True, False)
+                    qnn3(xp)
+                    for m in qnn3.modules():
+                        if hasattr(m, "trained"):
+                            m.trained = True
+                    qnn3.set_quant_state(True, True)
+                    qnn3.model.g_s[-1].set_quant_state(True, False)
+                    gf = E.GraphedForward(qnn3)
+                for _ in range(3):                 # eager pass, capture pass, first replay
+                    gf(xp)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    gf(xp)
+                b.record()
+                barrier()
+            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[tag] = world * 5 * h * w_ / 1e6 / (t.item() / 1e3)
+        fwd, fwd_2k = res["768x512"], res["2k"]
+        del qnn3, gf
+        torch.cuda.empty_cache()
 
     clocks = sampler.summary() if sampler else None
     cpu = None
@@ -267,7 +280,7 @@ def run_cuda(args):
                            "engine": os.environ.get("B200LIC_ENGINE", "auto"),
                            "launch": "one CUDA graph per unit per iteration (device-resident schedule)"},
                 "e2e": e2e, "e2e_host_caches": e2e_cached, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "fwd_mpx_s": fwd, "gflop_per_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e9}
+                "fwd_mpx_s": fwd, "fwd_mpx_s_2k": fwd_2k, "gflop_per_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e9}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
