@@ -31,6 +31,12 @@ AQ = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
 CALIB = dict(iters=20000, weight=0.01, b_range=(20, 2), warmup=0.2, input_prob=0.5)
 
 
+def workload_name(n_units):
+    """The same string in both arms' `config.workload` (BASELINE.json configs[1])."""
+    return (f"RDO-PTQ AdaRound calibration sweep, {ARCH} N={N_CH} M={M_CH} random-init, {n_units} units x batch "
+            f"{PER_GPU_BATCH}/GPU of {PATCH}x{PATCH} patches, W8 per-channel, QDrop 0.5")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -273,9 +279,7 @@ def run_cuda(args):
         line = {"metric": "calib imgs/s", "value": value, "unit": "imgs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"RDO-PTQ AdaRound calibration sweep, {ARCH} N={N_CH} M={M_CH} random-init, "
-                                       f"{n_units} units x batch {PER_GPU_BATCH}/GPU of {PATCH}x{PATCH} patches, W8 "
-                                       "per-channel, QDrop 0.5", "per_gpu_batch": PER_GPU_BATCH, "units": n_units,
+                "config": {"workload": workload_name(n_units), "per_gpu_batch": PER_GPU_BATCH, "units": n_units,
                            "l2_policy": "inputs larger than L2 (unit caches total > 126 MB; a different unit each call)",
                            "engine": os.environ.get("B200LIC_ENGINE", "auto"),
                            "launch": "one CUDA graph per unit per iteration (device-resident schedule)"},
@@ -336,6 +340,7 @@ def cpu_baseline(steps=1, batch=PER_GPU_BATCH, units_subset=None, warmup=0):
         sweep()
     dt = time.perf_counter() - t0
     return {"value": len(units) * batch * steps / dt, "unit": "imgs/s", "cores": os.cpu_count(), "kind": "port",
+            "units": len(units),
             "sample": f"{steps} sweep(s) of the same {len(units)}-unit AdaRound iteration at batch {batch} "
                       f"({PATCH}x{PATCH}), PyTorch-CPU fp32 oracle, {os.cpu_count()} threads",
             "seconds": dt}
@@ -344,14 +349,16 @@ def cpu_baseline(steps=1, batch=PER_GPU_BATCH, units_subset=None, warmup=0):
 def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    r = cpu_baseline(steps=steps, warmup=1 if args.warmup > 0 else 0)
+    steps = max(1, min(args.steps, 20))          # one sweep is 1.5-4.5 s on 8-16 host cores: K = 20 stays within minutes
+    warm = max(0, min(args.warmup, 3))
+    r = cpu_baseline(steps=steps, warmup=warm)
     line = {"impl": "reference", "metric": "calib imgs/s", "value": r["value"], "unit": "imgs/s",
-            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": 1 if args.warmup > 0 else 0,
+            "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": warm,
             "ms_per_step": r["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"oracle port of the reference AdaRound sweep on host cores, {ARCH} N={N_CH} "
-                                   f"M={M_CH}, batch {PER_GPU_BATCH} of {PATCH}x{PATCH}"},
+            "config": {"workload": workload_name(r["units"]), "per_gpu_batch": PER_GPU_BATCH, "units": r["units"],
+                       "arm": "oracle port of the reference loop (PyTorch-CPU fp32) on the host cores; a step is one "
+                              "sweep of the same units at the same batch"},
             "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0,
                                        "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
