@@ -76,6 +76,16 @@ B200LIC_API unsigned long long b200lic_launch_count(void);
 B200LIC_API int b200lic_wq_init_minmax(const float* w, int outer, int ch, int inner, int n_bits, int scale_variant,
                            int symmetric, float* delta, float* zero_point, b200lic_stream_t stream);
 
+/* Search-based and moment-based ranges of the same tensor view.
+ * replaces: TO quantizer.py:300-316 ('mse': 10 shrink steps of 0.05, score mean|x-xq|^3.5), :339-370 ('l1', 'l2'),
+ * :318-336 ('gaussian': mean -+ 6*var), LU quantizer.py:265-280 ('mse': 80 steps of 0.01, p = 2).
+ * Candidate i uses (max, min) * fp32(1 - i*shrink); the first candidate with the strictly smallest score wins.
+ * The candidates' fake-quant runs in the reference's fp32 order; scores are accumulated in fp64. */
+enum { B200LIC_SCALE_MSE = 1, B200LIC_SCALE_L1 = 2, B200LIC_SCALE_L2 = 3, B200LIC_SCALE_GAUSSIAN = 4 };
+B200LIC_API int b200lic_wq_init_search(const float* w, int outer, int ch, int inner, int n_bits, int method,
+                           int n_steps, double shrink, float p, int symmetric, float* delta, float* zero_point,
+                           b200lic_stream_t stream);
+
 /* replaces: TO quantizer.py:175-177 (UniformAffineQuantizer.forward), LU quantizer.py:171-177.
  * Any of w_dq / codes / codes_u8 may be NULL.  codes are integer-valued fp32 in [0, n_levels-1]. */
 B200LIC_API int b200lic_wq_fake_quant(const float* w, const float* delta, const float* zero_point, int outer, int ch,

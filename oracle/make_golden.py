@@ -116,6 +116,39 @@ def quantizer_vectors():
         _same(TO.lp_loss(a, b, p), oq.lp_loss(a, b, p), f"lp_loss p={p}")
         G[f"lp/{p}"] = dict(a=a, b=b, loss=TO.lp_loss(a, b, p))
     _same(TO.round_ste(a * 3), oq.round_ste(a * 3), "round_ste")
+    # search- / moment-based ranges (TO quantizer.py:300-370; LU :265-278).  Own generator: the cases above keep their
+    # draws.  Gaussian and heavy-tailed slices at 8 / 4 / 3 bits, so that the searches stop at many different candidates.
+    g2 = torch.Generator().manual_seed(2005)
+
+    def heavy(*shape):
+        return torch.randn(*shape, generator=g2) * 0.1 * torch.exp(torch.randn(*shape, generator=g2))
+
+    scases = {"conv": (torch.randn(12, 8, 5, 5, generator=g2) * 0.1, False), "tconv": (heavy(8, 12, 5, 5), True),
+              "gamma": (heavy(9, 9).abs(), False), "vec": (heavy(33), False)}
+    picks = set()
+    for name, (w, tconv) in scases.items():
+        for bits in (8, 4, 3):
+            for method, sym in (("mse", False), ("l1", False), ("l2", False), ("gaussian", False), ("gaussian", True)):
+                ref = TO.UniformAffineQuantizer(bits, sym, True, method, tconv=tconv)
+                mine = oq.UniformAffineQuantizer(bits, sym, True, method, tconv=tconv)
+                r, m = ref(w.clone()), mine(w.clone())
+                _same(ref.delta, mine.delta, f"{name}/{method}/delta")
+                _same(ref.zero_point, mine.zero_point, f"{name}/{method}/zp")
+                _same(r, m, f"{name}/{method}/dequant")
+                G[f"uaq_search/{name}/b{bits}/{method}/sym{int(sym)}"] = dict(
+                    w=w, tconv=tconv, bits=bits, method=method, sym=sym, delta=ref.delta, zp=ref.zero_point, dequant=r)
+                if method in ("mse", "l1", "l2") and w.dim() > 1:
+                    full = (w.amax(dim=(0, 2, 3) if tconv else tuple(range(1, w.dim()))) -
+                            w.amin(dim=(0, 2, 3) if tconv else tuple(range(1, w.dim())))) / (2 ** bits - 1)
+                    picks.update(torch.round((1 - ref.delta.flatten() / full) / 0.05).int().tolist())
+    assert len(picks) > 5, f"the shrink search always picked the same candidates {picks}: weak vectors"
+    w = heavy(6, 4, 3, 3)
+    ref, mine = LU.UniformAffineQuantizer(8, False, True, "mse"), oq.LUUniformAffineQuantizer(8, False, True, "mse")
+    (rc, rd), (mc, md) = ref(w.clone()), mine(w.clone())
+    _same(rc, mc, "lu mse codes")
+    _same(rd, md, "lu mse delta")
+    _same(ref.zero_point, mine.zero_point, "lu mse zp")
+    G["lu_mse"] = dict(w=w, codes=rc, delta=rd, zp=ref.zero_point)
     return G
 
 

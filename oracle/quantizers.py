@@ -112,8 +112,8 @@ def minmax_scale(x_min: float, x_max: float, n_levels: int, n_bits: int, method:
 
 
 class UniformAffineQuantizer(nn.Module):
-    """TO quantizer.py:123-393 (weights) restated; only the scale methods the hot path uses
-    ('max', 'max_scale', 'mse') are carried.  `n_bits` up to 16 is accepted (Q6: the reference
+    """TO quantizer.py:123-393 (weights) restated; scale methods 'max', 'max_scale', 'mse', 'l1', 'l2',
+    'gaussian' (all the reference has).  `n_bits` up to 16 is accepted (Q6: the reference
     asserts <= 8, config 4 needs 10)."""
 
     # Extension switch (not in the reference, SURVEY Q6): thread n_bits into the dynamic activation quantiser, which the
@@ -137,20 +137,34 @@ class UniformAffineQuantizer(nn.Module):
         if "max" in self.scale_method:
             return minmax_scale(t.min().item(), t.max().item(), self.n_levels, self.n_bits,
                                 self.scale_method, self.sym)
-        if self.scale_method == "mse":                    # :300-316
-            best, out = 1e10, None
-            hi, lo = t.max(), t.min()
-            eps = torch.tensor(1e-8)
-            for i in range(10):
-                nh, nl = hi * (1.0 - i * 0.05), lo * (1.0 - i * 0.05)
-                d = torch.max((nh - nl) / (2 ** self.n_bits - 1), eps)
-                z = (-nl / d).round()
-                tq = (torch.clamp(torch.round(t / d) + z, 0, self.n_levels - 1) - z) * d
-                score = lp_loss(t, tq, p=3.5, reduction="all")
-                if score < best:
-                    best, out = score, (float(d), float(z))
-            return out
+        if self.scale_method in ("mse", "l1", "l2"):      # :300-316, :339-370
+            score_fn = {"mse": lambda a, b: lp_loss(a, b, p=3.5, reduction="all"),
+                        "l1": torch.nn.functional.l1_loss, "l2": torch.nn.functional.mse_loss}[self.scale_method]
+            return self._shrink_search(t, 10, 0.05, score_fn)
+        if self.scale_method == "gaussian":               # :318-336 (mean -+ 6 * unbiased variance, fp32 tensors)
+            mu, var = torch.mean(t), torch.var(t)
+            lo, hi = torch.clamp_max(mu - 6 * var, 0), torch.clamp_min(mu + 6 * var, 0)
+            if self.sym:
+                a = torch.max(lo.abs(), hi)
+                lo, hi = (-a if lo < 0 else torch.zeros(())), a
+            d = torch.max((hi - lo) / (self.n_levels - 1), torch.tensor(1e-8))
+            return float(d), float((-lo / d).round())
         raise NotImplementedError(self.scale_method)
+
+    def _shrink_search(self, t, steps, shrink, score_fn):
+        """:300-316 / LU quantizer.py:265-278: shrink (max, min) step by step, keep the first strictly best score."""
+        best, out = 1e10, None
+        hi, lo = t.max(), t.min()
+        eps = torch.tensor(1e-8)
+        for i in range(steps):
+            nh, nl = hi * (1.0 - i * shrink), lo * (1.0 - i * shrink)
+            d = torch.max((nh - nl) / (2 ** self.n_bits - 1), eps)
+            z = (-nl / d).round()
+            tq = (torch.clamp(torch.round(t / d) + z, 0, self.n_levels - 1) - z) * d      # :375-382
+            score = score_fn(t, tq)
+            if score < best:
+                best, out = score, (float(d), float(z))
+        return out
 
     def init_quantization_scale(self, x: torch.Tensor, channel_wise: bool = False):
         """:233-298.  Returns (delta, zero_point) shaped for broadcasting against x."""
@@ -222,6 +236,11 @@ class AdaRoundQuantizer(nn.Module):
 
 class LUUniformAffineQuantizer(UniformAffineQuantizer):
     """LU quantizer.py:130-183: forward returns (codes, delta); leaf_param => static Q8.8."""
+
+    def _slice_scale(self, t):
+        if self.scale_method == "mse":                    # LU :265-278: 80 steps of 1 %, lp_loss p=2 ('none')
+            return self._shrink_search(t, 80, 0.01, lambda a, b: lp_loss(a, b))
+        return super()._slice_scale(t)
 
     def forward(self, x, act=False):
         if not self.inited:

@@ -41,6 +41,7 @@ _D = C.POINTER(ConvDesc)
 # name -> argtypes (the trailing stream argument is appended automatically)
 SIGNATURES = {
     "wq_init_minmax": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "wq_init_search": [_P, _I, _I, _I, _I, _I, _I, _DBL, _F, _I, _P, _P],
     "wq_fake_quant": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "wq_dequant_u8": [_P, _P, _P, _I, _I, _I, _P],
     "adaround_init_alpha": [_P, _P, _I, _I, _I, _P],

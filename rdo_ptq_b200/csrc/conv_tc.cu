@@ -35,7 +35,10 @@ __global__ void __launch_bounds__(256) nhwc_split_kernel(const float* __restrict
                                                           int square, __nv_bfloat16* __restrict__ xh,
                                                           __nv_bfloat16* __restrict__ xl) {
   __shared__ float t[64][65];
-  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  // channel block fastest: the CTAs that complete one NHWC row (Cpad * 2 bytes) are co-resident, so the 128-byte pieces
+  // they write merge into full rows in L2 instead of reaching DRAM one third of a row at a time
+  const int cblk = (Cpad + 63) >> 6;
+  const int n = blockIdx.z, c0 = (int)(blockIdx.x % cblk) * 64, p0 = (int)(blockIdx.x / cblk) * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
   const float* xn = x + (size_t)n * C * HW;
   const bool vec2 = (HW & 1) == 0;
@@ -544,7 +547,7 @@ static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int
   // 1. stage operands
   {
     const int HW = H * W;
-    dim3 grid((HW + 63) / 64, (p.Cpad + 63) / 64, N);
+    dim3 grid(((p.Cpad + 63) / 64) * ((HW + 63) / 64), 1, N);
     nhwc_split_kernel<<<grid, 256, 0, s>>>(x, Cin, HW, p.Cpad, in_square, xh, xl);
     B200_LAUNCH_CHECK("nhwc_split_kernel");
     PackGeom pg{Cout, Cin, KH, KW, stride, pad, transposed, p.CoutPad, p.Cpad, p.Tmax, s_co, s_ci};
@@ -591,7 +594,7 @@ static int tc_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int
 
 // shared with conv_tc_wgrad.cu
 int tc_stage_nhwc(const float* x, int N, int C, int HW, int Cpad, int square, void* xh, void* xl, cudaStream_t s) {
-  dim3 grid((HW + 63) / 64, (Cpad + 63) / 64, N);
+  dim3 grid(((Cpad + 63) / 64) * ((HW + 63) / 64), 1, N);
   nhwc_split_kernel<<<grid, 256, 0, s>>>(x, C, HW, Cpad, square, reinterpret_cast<__nv_bfloat16*>(xh),
                                          reinterpret_cast<__nv_bfloat16*>(xl));
   B200_LAUNCH_CHECK("nhwc_split_kernel");

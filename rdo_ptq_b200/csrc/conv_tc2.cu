@@ -123,8 +123,8 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void epi_bar(int id) {  // named barrier over the 4 epilogue warps
-  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+__device__ __forceinline__ void epi_bar(int id) {  // named barrier over the 8 epilogue warps
+  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
 }
 
 // K-major SWIZZLE_64B operand tile: rows of 64 B (32 bf16), 8-row groups of 512 B.
@@ -192,7 +192,7 @@ struct Tc2Geom {
   int dbg_mode;               // 0 normal; 1 = skip the MMAs; 2 = skip the TMA loads (bottleneck experiments only)
 };
 
-constexpr int kT2Threads = 192;
+constexpr int kT2Threads = 320;        // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kA2Bytes = 128 * 64;        // 128 pixel rows x 32 bf16
 
 struct PhaseGeom {
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   const uint32_t sScale = sBias + 1024u;                                             // [BN] weight scale (w_exact)
   const uint32_t full_bar = bars, empty_bar = bars + 8u * g.stages;
   const uint32_t tfull_bar = empty_bar + 8u * g.stages;          // [2] accumulator set complete
-  const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (4 warp arrivals)
+  const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (8 warp arrivals)
   const uint32_t xfull_bar = tempty_bar + 16u;                   // [x_slots] GDN x chunk landed
   const uint32_t tmem_ptr_addr = xfull_bar + 8u * (uint32_t)(g.x_slots > 0 ? g.x_slots : 1);
   volatile uint32_t* tmem_ptr_gen =
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8u * s, 1);
-      mbar_init(tempty_bar + 8u * s, 4);
+      mbar_init(tempty_bar + 8u * s, 8);
     }
     for (int s = 0; s < g.x_slots; ++s) mbar_init(xfull_bar + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -410,10 +410,15 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =========================================================
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4 =========================================================
+    // Two warps per lane quarter (w and w + 4), each taking one 16-channel half of every 32-channel chunk.  With one
+    // warp per scheduler the epilogue was latency-bound: the fine-grained timeline (profiles/README.md r1f) showed
+    // ~9 cycles per instruction -- tcgen05.ld 0.13 us, 16 bias adds 0.1 us, 16 x (ld.shared, rsqrt, mul) 0.36 us,
+    // 16 st.shared 0.1 us per half, 1.4 us per chunk -- with nothing else resident on the scheduler to fill the stalls.
     const int q4 = warp & 3;
+    const int grp = (warp - 2) >> 2;                                // which half of a chunk this warp handles
     const int m = q4 * 32 + lane;                                   // row of the tile = pixel
-    const int et = (warp - 2) * 32 + lane;                          // 0..127 within the epilogue group
+    const int et = (warp - 2) * 32 + lane;                          // 0..255 within the epilogue group
     const int iw = m % g.BW, ih = (m / g.BW) % g.BH, ii = m / (g.BW * g.BH);
     const int hw_box = g.BW * g.BH;
     const int CH = g.chunk;                                         // channels per chunk: 16 or 32
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       }
       if (bias_base != co_base) {             // per-channel bias of this n-tile -> shared memory (once per n-tile)
         epi_bar(3);
-        for (int i = et; i < g.BN; i += 128) {
+        for (int i = et; i < g.BN; i += 256) {
           const float bv = (bias && co_base + i < g.Cout) ? __ldg(bias + co_base + i) : 0.f;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + (uint32_t)i * 4u), "f"(bv) : "memory");
           if (g.w_exact) {
@@ -510,11 +515,13 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const bool valid = a < q.Pa && b < q.Pb && n < g.N;
         const long long obase = ((long long)n * g.Cout + co_base + c0) * plane +
                                 (long long)(a * q.out_step + q.ph) * g.Wo + (b * q.out_step + q.pw);
-        for (int h = 0; h < CH; h += 16) {    // 16-channel halves of the chunk
+        for (int h = grp * 16; h < CH; h += 32) {    // this warp's 16-channel half of the chunk
           uint32_t v[16];
+          const bool trh = tr && ci == 1;       // fine-grained stamps of one steady-state chunk (debug timeline only)
           if (num_kb > 0) {
             tmem_ld16(acc0 + (uint32_t)(t * g.chains * g.BN + c0 + h), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (trh) dbg[110 + (h >> 4) * 4] = gtime();
             for (int ch = 1; ch < g.chains; ++ch) {      // partial sums of the other accumulator chains
               uint32_t u[16];
               tmem_ld16(acc0 + (uint32_t)((t * g.chains + ch) * g.BN + c0 + h), u);
@@ -549,6 +556,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           }
           const uint32_t so0 = st_off + (uint32_t)(h * hw_box) * 4u;
           const uint32_t sstep = (uint32_t)hw_box * 4u;
+          if (trh) dbg[111 + (h >> 4) * 4] = gtime();
           if (g.tma_out) {
             if (g.gdn_mode) {
               float xv[16];
@@ -599,10 +607,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = rintf(fminf(fmaxf(r[j], -128.f), 128.f) * 256.f) * (1.f / 256.f);
           }
+          if (trh) dbg[112 + (h >> 4) * 4] = gtime();
           if (g.tma_out) {
             const uint32_t ya = sY + buf * tile_bytes + so0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ya + (uint32_t)j * sstep), "f"(r[j]) : "memory");
+            if (trh) dbg[113 + (h >> 4) * 4] = gtime();
           } else if (valid) {
             float* yp = y + obase + (long long)h * plane;
             const int lim = g.Cout - (co_base + c0 + h);     // channels of this half that exist
@@ -613,7 +623,9 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         }
         if (g.tma_out) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (tr && ci == 1) dbg[118] = gtime();
           epi_bar(2);
+          if (tr && ci == 1) dbg[119] = gtime();
           if (et == 0) {
             tma_store_4d(&map_y, sY + buf * tile_bytes, b0, a0, co_base + c0, n0);
             if (g.has_norm) tma_store_4d(&map_n, sN + buf * tile_bytes, b0, a0, co_base + c0, n0);

@@ -157,82 +157,100 @@ constexpr int kTabN = 2 * kTabR + 1;
 
 __global__ void __launch_bounds__(256, 3)
     factorized_lik_kernel(const float* __restrict__ z, const float* __restrict__ params,
-                          const float* __restrict__ medians, int N, int C, int HW, int splits, float lik_bound,
+                          const float* __restrict__ medians, int N, int C, int HW, float lik_bound,
                           float* __restrict__ z_hat, float* __restrict__ lik, float* __restrict__ bits_out) {
   __shared__ FactorizedParams P;
   __shared__ float red[32];
   __shared__ float t_lik[kTabN], t_bits[kTabN];
-  const int c = blockIdx.x % C, split = blockIdx.x / C;
-  if (threadIdx.x < 58) {
-    const float raw = __ldg(params + (size_t)c * 58 + threadIdx.x);
-    float* dst = reinterpret_cast<float*>(&P);
-    float v = raw;
-    if (threadIdx.x < 33) v = softplusf_(raw);
-    else if (threadIdx.x >= 46) v = tanhf(raw);
-    dst[threadIdx.x] = v;
-  }
-  __syncthreads();
-  const float med = __ldg(medians + c);
-  for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
-    const float zh = __fadd_rn((float)(j - kTabR), med);
-    const float l = factorized_rare(&P, zh, lik_bound);
-    t_lik[j] = l;
-    t_bits[j] = -log2f(l);
-  }
-  __syncthreads();
-  float bits = 0.f;
+  // The N*C planes, ordered channel-major, are cut into gridDim.x equal contiguous ranges (grid = resident CTAs: one
+  // wave, every CTA the same bytes +- one plane).  A CTA's range covers at most a few channels; the symbol table is
+  // rebuilt when the channel changes.  The first version launched C * splits CTAs of unequal residency (1.7 waves at
+  // C = 192) and reached 46 % of the HBM peak (profiles/README.md r1c).
+  const long long planes = (long long)N * C;
+  const long long p_begin = planes * blockIdx.x / gridDim.x, p_end = planes * (blockIdx.x + 1) / gridDim.x;
   const bool vec = (HW & 3) == 0 && (((uintptr_t)z | (uintptr_t)z_hat | (uintptr_t)lik) & 15) == 0;
-  auto one = [&](float zv, float& zh, float& l) {
-    const float k = rintf(__fsub_rn(zv, med));
-    zh = __fadd_rn(k, med);
-    if (fabsf(k) <= (float)kTabR) {
-      const int j = (int)k + kTabR;
-      l = t_lik[j];
-      bits += t_bits[j];
+  const int q4 = HW >> 2;
+  float bits = 0.f;
+  long long pp = p_begin;
+  while (pp < p_end) {
+    const int c = (int)(pp / N), n0 = (int)(pp - (long long)c * N);
+    const int n1 = (int)((long long)n0 + (p_end - pp) < (long long)N ? (long long)n0 + (p_end - pp) : (long long)N);
+    pp += n1 - n0;
+    {   // the first planes of the segment start their way from DRAM to L2 while the table is built
+      const int lines = (HW * 4 + 127) >> 7, pre = (n1 - n0) < 24 ? (n1 - n0) : 24;
+      for (int i = threadIdx.x; i < pre * lines; i += blockDim.x) {
+        const int pl = i / lines, ln = i - pl * lines;
+        const char* a = reinterpret_cast<const char*>(z + ((size_t)(n0 + pl) * C + c) * HW) + (size_t)ln * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+      }
+    }
+    __syncthreads();                       // the previous segment's table is no longer read
+    if (threadIdx.x < 58) {
+      const float raw = __ldg(params + (size_t)c * 58 + threadIdx.x);
+      float* dst = reinterpret_cast<float*>(&P);
+      float v = raw;
+      if (threadIdx.x < 33) v = softplusf_(raw);
+      else if (threadIdx.x >= 46) v = tanhf(raw);
+      dst[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const float med = __ldg(medians + c);
+    for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
+      const float zh = __fadd_rn((float)(j - kTabR), med);
+      const float l = factorized_rare(&P, zh, lik_bound);
+      t_lik[j] = l;
+      t_bits[j] = -log2f(l);
+    }
+    __syncthreads();
+    auto one = [&](float zv, float& zh, float& l) {
+      const float k = rintf(__fsub_rn(zv, med));
+      zh = __fadd_rn(k, med);
+      if (fabsf(k) <= (float)kTabR) {
+        const int j = (int)k + kTabR;
+        l = t_lik[j];
+        bits += t_bits[j];
+      } else {
+        l = factorized_rare(&P, zh, lik_bound);
+        bits -= log2f(l);
+      }
+    };
+    if (vec) {
+      // planes n0..n1-1 of channel c as one flat float4 index space, four independent requests per thread in flight
+      // (32-bit float4 offsets: the host checks numel < 2^34)
+      const unsigned total = (unsigned)(n1 - n0) * (unsigned)q4, row4 = (unsigned)C * (unsigned)q4;
+      const unsigned base4 = (unsigned)n0 * row4 + (unsigned)c * (unsigned)q4;
+      const float4* z4 = reinterpret_cast<const float4*>(z);
+      for (unsigned i0 = threadIdx.x; i0 < total; i0 += 4u * blockDim.x) {
+        float4 zv[4];
+        unsigned off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned i = i0 + (unsigned)u * blockDim.x;
+          const unsigned pl = i / (unsigned)q4;
+          off[u] = base4 + pl * row4 + (i - pl * (unsigned)q4);
+          if (i < total) zv[u] = __ldg(z4 + off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + (unsigned)u * blockDim.x >= total) break;
+          float4 o, l;
+          one(zv[u].x, o.x, l.x);
+          one(zv[u].y, o.y, l.y);
+          one(zv[u].z, o.z, l.z);
+          one(zv[u].w, o.w, l.w);
+          reinterpret_cast<float4*>(z_hat)[off[u]] = o;
+          if (lik) reinterpret_cast<float4*>(lik)[off[u]] = l;
+        }
+      }
     } else {
-      l = factorized_rare(&P, zh, lik_bound);
-      bits -= log2f(l);
-    }
-  };
-  // the CTA's planes n = split, split + splits, ... are walked as one flat float4 index space, four independent
-  // requests per thread in flight (planes of z are small: one float4 per thread per plane would be latency-bound)
-  const int my_planes = (N - split + splits - 1) / splits;
-  if (vec) {
-    const int q4 = HW >> 2;
-    const long long total = (long long)my_planes * q4;
-    for (long long i0 = threadIdx.x; i0 < total; i0 += 4LL * blockDim.x) {
-      float4 zv[4];
-      size_t off[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long i = i0 + (long long)u * blockDim.x;
-        ok[u] = i < total;
-        const long long pl = ok[u] ? i / q4 : 0;
-        const int e = ok[u] ? (int)(i - pl * q4) : 0;
-        off[u] = (((size_t)(split + pl * splits) * C + c) * HW) / 4 + e;
-        if (ok[u]) zv[u] = __ldg(reinterpret_cast<const float4*>(z) + off[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (!ok[u]) continue;
-        float4 o, l;
-        one(zv[u].x, o.x, l.x);
-        one(zv[u].y, o.y, l.y);
-        one(zv[u].z, o.z, l.z);
-        one(zv[u].w, o.w, l.w);
-        reinterpret_cast<float4*>(z_hat)[off[u]] = o;
-        if (lik) reinterpret_cast<float4*>(lik)[off[u]] = l;
-      }
-    }
-  } else {
-    for (int n = split; n < N; n += splits) {
-      const size_t base = ((size_t)n * C + c) * HW;
-      for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-        float o, l;
-        one(__ldg(z + base + i), o, l);
-        z_hat[base + i] = o;
-        if (lik) lik[base + i] = l;
+      for (int n = n0; n < n1; ++n) {
+        const size_t base = ((size_t)n * C + c) * HW;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+          float o, l;
+          one(__ldg(z + base + i), o, l);
+          z_hat[base + i] = o;
+          if (lik) lik[base + i] = l;
+        }
       }
     }
   }
@@ -439,12 +457,13 @@ int b200lic_factorized_lik_fwd(const float* z, const float* params, const float*
   B200_ARCH_GATE();
   B200_REQUIRE(z && params && medians && z_hat, "factorized_lik_fwd: null pointer");
   B200_REQUIRE(N > 0 && C > 0 && HW > 0, "factorized_lik_fwd: bad shape (%d,%d,%d)", N, C, HW);
-  // one CTA per (channel, batch split): the symbol table is built once and reused over the CTA's planes
-  int splits = (4 * num_sms() + C - 1) / C;
-  if (splits > N) splits = N;
-  if (splits < 1) splits = 1;
-  factorized_lik_kernel<<<(unsigned)(C * splits), 256, 0, as_stream(stream)>>>(z, params, medians, N, C, HW, splits,
-                                                                               lik_bound, z_hat, lik, bits);
+  B200_REQUIRE((long long)N * C * HW < (1LL << 34), "factorized_lik_fwd: tensor too large (%d,%d,%d)", N, C, HW);
+  // one resident wave: 3 CTAs per SM, each takes an equal contiguous share of the N*C planes (channel-major)
+  long long grid = 3LL * num_sms();
+  const long long planes = (long long)N * C;
+  if (grid > planes) grid = planes;
+  factorized_lik_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(z, params, medians, N, C, HW, lik_bound, z_hat,
+                                                                       lik, bits);
   B200_LAUNCH_CHECK("factorized_lik_kernel");
   return B200LIC_OK;
 }

@@ -61,6 +61,142 @@ __global__ void __launch_bounds__(256) wq_minmax_kernel(const float* __restrict_
   }
 }
 
+// ---- K7c: search-based / moment-based ranges (quantizer.py:300-370; LU quantizer.py:265-280) ---------------------
+// One CTA per quantisation channel.  'mse' / 'l1' / 'l2': the slice's (min, max) are shrunk in n_steps steps of
+// `shrink`; every candidate range is scored by mean |x - fake_quant(x)|^p and the first strictly best candidate wins
+// (the reference's `if score < best_score`).  The fake-quant of a candidate is issued in the reference's fp32 order
+// (quantizer.py:375-382); scores are accumulated in fp64 (the reference's fp32 mean differs in the last bits only,
+// which matters for exact ties alone).  'gaussian': range = mean -+ 6 * var(unbiased) (:318-336).
+struct CandRange { float d, z; };
+
+__device__ __forceinline__ CandRange cand_range(float mx, float mn, float f, float levels) {
+  const float nh = __fmul_rn(mx, f), nl = __fmul_rn(mn, f);
+  CandRange r;
+  r.d = fmaxf(__fdiv_rn(__fsub_rn(nh, nl), levels), 1e-8f);
+  r.z = rintf(__fdiv_rn(-nl, r.d));
+  return r;
+}
+
+__device__ __forceinline__ double block_sum_f64(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];   // fixed order, every thread gets the total
+  return t;
+}
+
+constexpr int kSearchChunk = 8;
+
+__global__ void __launch_bounds__(256) wq_search_kernel(const float* __restrict__ w, int outer, int ch, int inner,
+                                                         int n_bits, int method, int n_steps, double shrink, float p,
+                                                         int symmetric, float* __restrict__ delta,
+                                                         float* __restrict__ zp) {
+  const int c = blockIdx.x;
+  const size_t per_outer = (size_t)ch * inner;
+  const size_t total = (size_t)outer * inner;
+  const float* base = w + (size_t)c * inner;
+  const float levels = (float)((1 << n_bits) - 1);
+  __shared__ float smn[8], smx[8];
+  __shared__ double red[8];
+
+  if (method == B200LIC_SCALE_GAUSSIAN) {
+    double s = 0.0;
+    for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+      const size_t o = i / inner, k = i - o * inner;
+      s += (double)__ldg(base + o * per_outer + k);
+    }
+    const double mean = block_sum_f64(s, red) / (double)total;
+    double q = 0.0;
+    for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+      const size_t o = i / inner, k = i - o * inner;
+      const double e = (double)__ldg(base + o * per_outer + k) - mean;
+      q += e * e;
+    }
+    const double var = block_sum_f64(q, red) / (double)(total - 1);
+    if (threadIdx.x == 0) {
+      const float mu = (float)mean, six = __fmul_rn(6.f, (float)var);
+      float lo = fminf(__fsub_rn(mu, six), 0.f), hi = fmaxf(__fadd_rn(mu, six), 0.f);
+      if (symmetric) {
+        const float a = fmaxf(fabsf(lo), hi);
+        lo = lo < 0.f ? -a : 0.f;
+        hi = a;
+      }
+      const float d = fmaxf(__fdiv_rn(__fsub_rn(hi, lo), levels), 1e-8f);
+      delta[c] = d;
+      zp[c] = rintf(__fdiv_rn(-lo, d));
+    }
+    return;
+  }
+
+  float mn = INFINITY, mx = -INFINITY;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const size_t o = i / inner, k = i - o * inner;
+    const float v = __ldg(base + o * per_outer + k);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) {
+    smn[threadIdx.x >> 5] = mn;
+    smx[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  mn = smn[0];
+  mx = smx[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+    mn = fminf(mn, smn[i]);
+    mx = fmaxf(mx, smx[i]);
+  }
+  const float top = (float)((1 << n_bits) - 1);
+  double best = 1e10;
+  float best_d = 0.f, best_z = 0.f;
+  bool found = false;
+  for (int s0 = 0; s0 < n_steps; s0 += kSearchChunk) {
+    CandRange cr[kSearchChunk];
+    double acc[kSearchChunk];
+#pragma unroll
+    for (int j = 0; j < kSearchChunk; ++j) {
+      // `1.0 - i * shrink` is a Python float (fp64) cast to fp32 when it meets the fp32 tensor
+      cr[j] = cand_range(mx, mn, (float)(1.0 - (double)(s0 + j) * shrink), levels);
+      acc[j] = 0.0;
+    }
+    for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+      const size_t o = i / inner, k = i - o * inner;
+      const float v = __ldg(base + o * per_outer + k);
+#pragma unroll
+      for (int j = 0; j < kSearchChunk; ++j) {
+        float q = __fadd_rn(rintf(__fdiv_rn(v, cr[j].d)), cr[j].z);
+        q = fminf(fmaxf(q, 0.f), top);
+        const double e = (double)fabsf(__fsub_rn(v, __fmul_rn(__fsub_rn(q, cr[j].z), cr[j].d)));
+        if (method == B200LIC_SCALE_L1) acc[j] += e;
+        else if (method == B200LIC_SCALE_L2 || p == 2.f) acc[j] += e * e;
+        else if (p == 3.5f) acc[j] += e * e * e * sqrt(e);
+        else acc[j] += pow(e, (double)p);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kSearchChunk; ++j) {
+      const double score = block_sum_f64(acc[j], red) / (double)total;
+      if (s0 + j < n_steps && score < best) {
+        best = score;
+        best_d = cr[j].d;
+        best_z = cr[j].z;
+        found = true;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    // the reference leaves delta unset (and fails) when no candidate scores below 1e10; report NaN instead
+    delta[c] = found ? best_d : __int_as_float(0x7fc00000);
+    zp[c] = found ? best_z : __int_as_float(0x7fc00000);
+  }
+}
+
 // ---- K7b: fake-quant -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wq_fake_quant_kernel(const float* __restrict__ w, const float* __restrict__ delta,
                                                              const float* __restrict__ zp, size_t n, int ch, int inner,
@@ -343,6 +479,22 @@ int b200lic_wq_init_minmax(const float* w, int outer, int ch, int inner, int n_b
   wq_minmax_kernel<<<ch, 256, 0, as_stream(stream)>>>(w, outer, ch, inner, n_bits, scale_variant, symmetric, delta,
                                                       zero_point);
   B200_LAUNCH_CHECK("wq_minmax_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_wq_init_search(const float* w, int outer, int ch, int inner, int n_bits, int method, int n_steps,
+                           double shrink, float p, int symmetric, float* delta, float* zero_point,
+                           b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(w && delta && zero_point, "wq_init_search: null pointer");
+  B200_REQUIRE(outer > 0 && ch > 0 && inner > 0, "wq_init_search: bad shape (%d,%d,%d)", outer, ch, inner);
+  B200_REQUIRE(n_bits >= 2 && n_bits <= 16, "wq_init_search: n_bits=%d outside [2,16]", n_bits);
+  B200_REQUIRE(method >= B200LIC_SCALE_MSE && method <= B200LIC_SCALE_GAUSSIAN, "wq_init_search: method %d", method);
+  B200_REQUIRE(method == B200LIC_SCALE_GAUSSIAN || (n_steps >= 1 && n_steps <= 1024 && shrink > 0.0 && p > 0.f),
+               "wq_init_search: n_steps=%d shrink=%g p=%g", n_steps, shrink, (double)p);
+  wq_search_kernel<<<ch, 256, 0, as_stream(stream)>>>(w, outer, ch, inner, n_bits, method, n_steps, shrink, p,
+                                                      symmetric, delta, zero_point);
+  B200_LAUNCH_CHECK("wq_search_kernel");
   return B200LIC_OK;
 }
 

@@ -78,6 +78,21 @@ def wq_init_minmax(w, axis, n_bits=8, scale_variant=False, symmetric=False):
     return delta.view(bs), zp.view(bs)
 
 
+SCALE_METHODS = {"mse": 1, "l1": 2, "l2": 3, "gaussian": 4}
+
+
+def wq_init_search(w, axis, n_bits=8, method="mse", n_steps=10, shrink=0.05, p=3.5, symmetric=False):
+    """Search-based ('mse' / 'l1' / 'l2') and moment-based ('gaussian') ranges: quantizer.py:300-370."""
+    w = _c(w, "weight")
+    outer, ch, inner = channel_view(w.shape, axis)
+    delta = torch.empty(ch, device=w.device, dtype=torch.float32)
+    zp = torch.empty_like(delta)
+    call("wq_init_search", _p(w), outer, ch, inner, n_bits, SCALE_METHODS[method], n_steps, shrink, p, int(symmetric),
+         _p(delta), _p(zp))
+    bs = _bshape(w.shape, axis, ch)
+    return delta.view(bs), zp.view(bs)
+
+
 def wq_fake_quant(w, delta, zp, axis, n_levels, want=("dq",)):
     w = _c(w, "weight")
     outer, ch, inner = channel_view(w.shape, axis)

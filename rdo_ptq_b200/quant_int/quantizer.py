@@ -32,10 +32,14 @@ class UniformAffineQuantizer(nn.Module):
         if self.inited is False:
             if self.leaf_param:                       # activations: never initialised => always Q8.8 (SURVEY a3')
                 return ActQuantizer(x, a_l=8, a_r=8)
-            if 'max' not in self.scale_method:
-                raise NotImplementedError("only 'max'-type scale init runs on the B200 path")
-            self.delta, self.zero_point = ops.wq_init_minmax(x.detach(), self.channel_axis(x), self.n_bits,
-                                                             'scale' in self.scale_method, self.sym)
+            if 'max' in self.scale_method:
+                self.delta, self.zero_point = ops.wq_init_minmax(x.detach(), self.channel_axis(x), self.n_bits,
+                                                                 'scale' in self.scale_method, self.sym)
+            elif self.scale_method == 'mse':          # reference :265-278: 80 shrink steps of 1 %, squared-error score
+                self.delta, self.zero_point = ops.wq_init_search(x.detach(), self.channel_axis(x), self.n_bits, 'mse',
+                                                                 80, 0.01, 2.0, self.sym)
+            else:
+                raise NotImplementedError(self.scale_method)                 # as the reference, :279-280
             self.inited = True
         codes = ops.wq_fake_quant(x.detach(), self.delta, self.zero_point, self.channel_axis(x), self.n_levels,
                                   want=("codes",))

@@ -59,8 +59,8 @@ class _FakeQuantSTE(torch.autograd.Function):
 
 
 class UniformAffineQuantizer(nn.Module):
-    """reference quantizer.py:123-393.  Scale methods: 'max' / 'max_scale' on the GPU (the hot-path default
-    `--init max`); the search-based ones ('mse', 'l1', 'l2', 'gaussian') are not on the hot path."""
+    """reference quantizer.py:123-393.  Scale methods: 'max' / 'max_scale' (the default `--init max`, K7a) and the
+    search- / moment-based 'mse', 'l1', 'l2', 'gaussian' (quantizer.py:300-370, K7c), all per channel on the GPU."""
 
     # additive switch: thread n_bits into the activation quantiser (config 4, W10A10); default = reference (8 bit)
     act_bits_follow_n_bits = False
@@ -112,10 +112,13 @@ class UniformAffineQuantizer(nn.Module):
         return _int_weights(x, self.delta, self.zero_point, self.channel_axis(x), self.n_levels, self.tconv, None)
 
     def init_quantization_scale(self, x: torch.Tensor, channel_wise: bool = False):
-        if 'max' not in self.scale_method:
-            raise NotImplementedError(f"scale_method {self.scale_method!r}: only 'max'/'max_scale' run on the B200 path")
         axis = self.channel_axis(x) if channel_wise else None
-        delta, zp = ops.wq_init_minmax(x.detach(), axis, self.n_bits, 'scale' in self.scale_method, self.sym)
+        if 'max' in self.scale_method:
+            delta, zp = ops.wq_init_minmax(x.detach(), axis, self.n_bits, 'scale' in self.scale_method, self.sym)
+        elif self.scale_method in ops.SCALE_METHODS:      # 10 shrink steps of 5 %, L3.5 / L1 / L2 score; mean -+ 6 var
+            delta, zp = ops.wq_init_search(x.detach(), axis, self.n_bits, self.scale_method, 10, 0.05, 3.5, self.sym)
+        else:
+            raise NotImplementedError(f"scale_method {self.scale_method!r}")        # as quantizer.py:372
         if channel_wise and x.dim() == 1:
             delta, zp = delta.view(-1), zp.view(-1)
         return delta, zp

@@ -2,6 +2,7 @@
 
   ncu --set full --clock-control none --import-source on -o gpurun_out/prof python scripts/profile_kernels.py --reps 1
   python scripts/profile_kernels.py --reps 20 --time        # CUDA-event timings + roofline fractions (no profiler)
+  python scripts/profile_kernels.py --reps 20 --time --graph   # the same from a CUDA-graph replay of each case
 """
 import argparse
 import ctypes as C
@@ -26,6 +27,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="time a CUDA-graph replay of each case (device time of its kernels: no host launch gaps)")
     ap.add_argument("--only", default="")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
@@ -113,12 +116,19 @@ def main():
             continue
         for _ in range(3):
             fn()
+        run = fn
+        if args.graph:
+            torch.cuda.synchronize()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                fn()
+            run = cg.replay
         ts = []
         for _ in range(args.reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            fn()
+            run()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -133,7 +143,8 @@ def main():
         print(json.dumps(rows[-1]))
     if args.time:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "kernel_times.json"), "w"), indent=1)
+        name = "kernel_times_graph.json" if args.graph else "kernel_times.json"
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
 
 
 if __name__ == "__main__":

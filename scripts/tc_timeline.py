@@ -46,3 +46,10 @@ for ci in range(30):
     if a == 0:
         break
     print(f" chunk {ci:2d}: staging free {(a - t0) / 1e3:8.2f}  x landed {(b_ - t0) / 1e3:8.2f}  store issued {(c - t0) / 1e3:8.2f}")
+if t[110]:
+    names = ["tmem ld done", "bias added", "math done", "staged"]
+    print(" chunk 1 in detail (us after its x landed):")
+    base = t[3 + 3]
+    for h in range(2):
+        print("  half", h, " ".join(f"{names[k]} {(t[110 + 4 * h + k] - base) / 1e3:6.2f}" for k in range(4) if t[110 + 4 * h + k]))
+    print(f"  proxy fence done {(t[118] - base) / 1e3:6.2f}  barrier passed {(t[119] - base) / 1e3:6.2f}")

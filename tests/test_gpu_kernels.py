@@ -49,6 +49,55 @@ def test_weight_quant_golden_bit_exact(ops, dev, golden_q):
     assert n >= 20
 
 
+def test_search_and_moment_ranges_golden(ops, dev, golden_q):
+    """K7c against the reference's own outputs for 'mse' / 'l1' / 'l2' (argmin over the shrink candidates: the winning
+    (delta, zero_point) must be the reference's bit for bit) and 'gaussian' (mean / variance are fp64 sums here and
+    torch's fp32 cascade in the reference: delta within 2 ulp, hence tolerance 3e-7 relative)."""
+    n = 0
+    for key, g in golden_q.items():
+        if not key.startswith("uaq_search/"):
+            continue
+        w = g["w"].to(dev)
+        axis = None if w.dim() == 1 else (1 if g["tconv"] else 0)
+        delta, zp = ops.wq_init_search(w, axis, g["bits"], g["method"], 10, 0.05, 3.5, g["sym"])
+        d, z = delta.cpu().reshape(-1), zp.cpu().reshape(-1)
+        if g["method"] == "gaussian":
+            assert torch.allclose(d, g["delta"].reshape(-1), rtol=3e-7, atol=0), key
+            assert (z - g["zp"].reshape(-1)).abs().max() <= 1, key
+        else:
+            assert torch.equal(d, g["delta"].reshape(-1)) and torch.equal(z, g["zp"].reshape(-1)), key
+            dq = ops.wq_fake_quant(w, delta, zp, axis, 2 ** g["bits"], want=("dq",))
+            assert torch.equal(dq.cpu(), g["dequant"]), key
+        n += 1
+    assert n >= 60
+
+
+def test_search_ranges_through_the_quantiser_classes(dev, golden_q):
+    """The drop-in classes with scale_method != 'max' at layer sizes, against the oracle (itself pinned to the reference
+    by the golden vectors): TO 'mse' at 4 and 8 bit on conv / transposed-conv weights, LU's 80-step 'mse'."""
+    from rdo_ptq_b200.quantization.quantizer import UniformAffineQuantizer as PQ
+    from rdo_ptq_b200.quant_int.quantizer import UniformAffineQuantizer as PLU
+    g = torch.Generator().manual_seed(11)
+    for shape, tconv, bits, method in (((192, 192, 5, 5), False, 4, "mse"), ((320, 192, 5, 5), True, 8, "mse"),
+                                       ((192, 96, 3, 3), False, 3, "l2"), ((192, 192), False, 4, "l1")):
+        w = torch.randn(shape, generator=g) * 0.05
+        oqz = oq.UniformAffineQuantizer(bits, False, True, method, tconv=tconv)
+        ref = oqz(w.clone())
+        pq = PQ(bits, False, True, method, tconv=tconv)
+        out = pq(w.to(dev))
+        assert pq.delta.shape == oqz.delta.shape
+        assert torch.equal(pq.delta.cpu(), oqz.delta) and torch.equal(pq.zero_point.cpu(), oqz.zero_point), (shape, method)
+        assert torch.equal(out.cpu(), ref), (shape, method)
+    w = torch.randn(48, 32, 3, 3, generator=g) * 0.05
+    oqz, plu = oq.LUUniformAffineQuantizer(8, False, True, "mse"), PLU(8, False, True, "mse")
+    (rc, rd), (pc, pd) = oqz(w.clone()), plu(w.to(dev))
+    assert torch.equal(pc.cpu(), rc) and torch.equal(pd.cpu(), rd) and torch.equal(plu.zero_point.cpu(), oqz.zero_point)
+    g = golden_q["lu_mse"]
+    plu = PLU(8, False, True, "mse")
+    pc, pd = plu(g["w"].to(dev))
+    assert torch.equal(pc.cpu(), g["codes"]) and torch.equal(pd.cpu(), g["delta"])
+
+
 def test_weight_quant_large_random_bit_exact(ops, dev):
     g = torch.Generator().manual_seed(7)
     for shape, tconv in (((192, 192, 5, 5), False), ((320, 192, 5, 5), True), ((192, 192), False), ((3, 192, 5, 5), True)):

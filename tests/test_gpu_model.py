@@ -505,3 +505,96 @@ def test_w10a10_cheng2020_forward_parity(dev):
         assert abs(bpp - bpp_ref) < 0.01 * bpp_ref + 1e-3 and abs(p - p_ref) < 0.1
     finally:
         oq.UniformAffineQuantizer.act_bits_follow_n_bits = PUAQ.act_bits_follow_n_bits = False
+
+
+def test_main2_whole_model_calibration_matches_oracle(dev):
+    """The calibration entry point (main2.py:145-290): QuantModel -> 8-bit head/stem -> range init -> depth-first
+    recon_model walk (every unit sees the hardened units before it) -> W4 test -> W4A8 test, against the oracle's
+    restatement of the same walk on the same draws.  4-bit weights so that rounding decisions matter."""
+    from rdo_ptq_b200 import main2
+    argv = ["--arch", "Minnen2018", "--n_bits_w", "4", "--channel_wise", "--batch_size", "2", "--num_samples", "4",
+            "--iters_w", "12", "--test_before_calibration"]
+    args = main2.parse_args(argv)
+    om, pm, Q = build_pair("mbt2018-mean", dict(N=16, M=24), 1.2, dev)
+    cali = synth.calibration_patches(4, 64)
+    imgs = synth.synthetic_images(2, 100, 150)
+    # oracle side, statement by statement
+    with torch.no_grad():
+        om(cali[:1])
+    wq = {'n_bits': 4, 'channel_wise': True, 'scale_method': 'max'}
+    aq = {'n_bits': 8, 'channel_wise': True, 'scale_method': 'max', 'leaf_param': False}
+    oqm = owrap.QuantModel(om, wq, aq).eval()
+    oqm.set_first_last_layer_to_8bit()
+    oqm.disable_network_output_quantization()
+    oqm.set_quant_state(True, False)
+    with torch.no_grad():
+        oqm(cali[:2])
+    oqm.model.g_s[-1].set_quant_state(True, False)
+    otr = ocalib.recon_model(oqm, cali, batch_size=2, iters=12, weight=0.01, b_range=(20, 2), warmup=0.2,
+                             input_prob=0.5, plan=ocalib.DrawPlan())
+    oqm.set_quant_state(True, False)
+    ps_w, bs_w = oeval.evaluate(oqm, imgs)
+    oqm.set_quant_state(True, True)
+    oqm.model.g_s[-1].set_quant_state(True, False)
+    ps_wa, bs_wa = oeval.evaluate(oqm, imgs)
+    # product side: the entry point
+    pqm, rep = main2.optimize_model(args, model=pm, cali_data=cali, test_images=imgs, device=dev, plan=ReplayPlan())
+    assert list(rep["losses"]) == list(otr) and len(otr) == 20
+    omods = [m for m in oqm.modules() if isinstance(m, owrap.QuantModule) and m.org_weight is not None]
+    pmods = [m for m in pqm.modules() if isinstance(m, Q.QuantModule) and m.org_weight is not None]
+    assert len(omods) == len(pmods) == 20 and all(m.trained for m in pmods)
+    assert pmods[0].weight_quantizer.n_bits == 8 and pmods[1].weight_quantizer.n_bits == 4
+    diff = tot = 0
+    for a, b in zip(pmods, omods):
+        assert torch.equal(a.weight_quantizer.delta.cpu().reshape(-1), b.weight_quantizer.delta.reshape(-1))
+        ca, cb = a.weight_quantizer.codes(a.weight).cpu(), b.weight_quantizer.codes(b.weight)
+        diff += (ca != cb).sum().item()
+        tot += ca.numel()
+    print(f"main2 walk: {diff}/{tot} hardened 4-bit codes differ; W4 bpp {rep['w_opt']['bpp']:.5f} vs "
+          f"{sum(bs_w) / 2:.5f}, psnr {rep['w_opt']['psnr']:.4f} vs {sum(ps_w) / 2:.4f}; W4A8 bpp "
+          f"{rep['wa_opt']['bpp']:.5f} vs {sum(bs_wa) / 2:.5f}, psnr {rep['wa_opt']['psnr']:.4f} vs {sum(ps_wa) / 2:.4f}")
+    assert diff / tot < 2e-3                   # alpha within float noise of 0 after 12 steps: isolated decisions only
+    # hardened units, layer by layer on the oracle's own inputs: the per-layer bar (1e-4)
+    oqm.set_quant_state(True, False)
+    pqm.set_quant_state(True, False)
+    _, rows = per_layer_io(oqm, oeval.pad(imgs[0], 256), (owrap.QuantModule,))
+    pm_by_name = dict((n, m) for n, m in pqm.named_modules() if isinstance(m, Q.QuantModule))
+
+    def chk(name, a, b):
+        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
+    layer_local_parity(rows, pm_by_name, dev, chk)
+    # End to end this random-init 4-bit codec is chaotic (PSNR ~ 6 dB): one latent symbol that rounds the other way
+    # changes every mean / scale after it, so the metrics of two correct implementations agree to a few percent only
+    # (the W8 end-to-end bars of 1e-3 bpp / 0.01 dB are checked in test_quantized_forward_per_layer_parity).
+    assert abs(rep["w_opt"]["bpp"] - sum(bs_w) / 2) < 0.06 * sum(bs_w) / 2
+    assert abs(rep["w_opt"]["psnr"] - sum(ps_w) / 2) < 0.2
+    assert abs(rep["wa_opt"]["bpp"] - sum(bs_wa) / 2) < 0.06 * sum(bs_wa) / 2
+    assert abs(rep["wa_opt"]["psnr"] - sum(ps_wa) / 2) < 0.2
+    assert "fp32" in rep and "w_nearest" in rep
+
+
+@pytest.mark.parametrize("init", ["mse", "gaussian"])
+def test_main2_default_path_with_search_init(dev, init):
+    """Entry point with its own (device-drawn, graph-replayed) randomness and a search-based --init."""
+    from rdo_ptq_b200 import main2
+    args = main2.parse_args(["--arch", "mbt2018-mean", "--N", "8", "--M", "12", "--n_bits_w", "4", "--channel_wise",
+                             "--batch_size", "2", "--num_samples", "4", "--iters_w", "24", "--patch", "64", "--init",
+                             init, "--test_hw", "64x96", "--n_test", "1"])
+    qnn, rep = main2.optimize_model(args, device=dev)
+    assert len(rep["losses"]) == 20 and all(len(v) >= 1 for v in rep["losses"].values())
+    assert math.isfinite(rep["wa_opt"]["bpp"]) and math.isfinite(rep["wa_opt"]["psnr"])
+    assert all(m.weight_quantizer.scale_method == init if hasattr(m.weight_quantizer, "scale_method") else True
+               for m in qnn.modules() if hasattr(m, "weight_quantizer"))
+
+
+def test_lu_quantize_entry_point(dev, tmp_path):
+    """light-uniform-PTQ/quantize.py flow (config 1): uint8 weights materialised by one forward, INT8 state dict saved."""
+    from rdo_ptq_b200 import quantize as lu_entry, quant_int as LU
+    p = tmp_path / "INT8.pth"
+    args = lu_entry.parse_args(["--N", "8", "--M", "12", "--hw", "64x96", "--n_test", "2", "--save", str(p)])
+    qnn, rep = lu_entry.quantize_int8(args, device=dev)
+    mods = [m for m in qnn.modules() if isinstance(m, LU.QuantModule)]
+    assert len(mods) == 14 and all(m.weight.dtype == torch.uint8 for m in mods)
+    assert abs(rep["int8"]["psnr"] - rep["fp32"]["psnr"]) < 1.0 and rep["int8"]["bpp"] > 0
+    sd = torch.load(p, weights_only=False)
+    assert any(v.dtype == torch.uint8 for v in sd.values())
