@@ -169,8 +169,18 @@ B200LIC_API int b200lic_gaussian_lik_fwd(const float* y, const float* scales, co
 B200LIC_API int b200lic_round_latent(const float* y, const float* means, size_t n, float* y_hat, b200lic_stream_t stream);
 /* Factorised prior, filters (3,3,3,3).  params: [C][58] = matrices 3+9+9+9+3 (raw, softplus applied inside),
  * biases 3+3+3+3+1, factors 3+3+3+3 (raw, tanh applied inside).  medians: [C]. */
-B200LIC_API int b200lic_factorized_lik_fwd(const float* z, const float* params, const float* medians, int N, int C, int HW,
-                               float lik_bound, float* z_hat, float* lik, float* bits, b200lic_stream_t stream);
+/* `table` (may be NULL) = the per-channel symbol tables written by b200lic_factorized_table for the same params /
+ * medians / lik_bound; with NULL every CTA rebuilds its channel's table (same values, ~3 us per CTA). */
+B200LIC_API int b200lic_factorized_lik_fwd(const float* z, const float* params, const float* medians, const float* table,
+                               int N, int C, int HW, float lik_bound, float* z_hat, float* lik, float* bits,
+                               b200lic_stream_t stream);
+/* Symbol tables of the factorised prior: table[c][0][k + R] = likelihood of the symbol medians[c] + k and
+ * table[c][1][k + R] = -log2 of it for |k| <= R; b200lic_factorized_table_floats() = floats per channel (2 * (2R + 1)).
+ * They depend on the prior's parameters only, which PTQ never trains (compressai EntropyBottleneck reached from TO
+ * models/nic_cvt.py:297): build once per model, reuse for every forward. */
+B200LIC_API int b200lic_factorized_table_floats(void);
+B200LIC_API int b200lic_factorized_table(const float* params, const float* medians, int C, float lik_bound, float* table,
+                             b200lic_stream_t stream);
 
 /* Backward of the two likelihood kernels for the rate term of RateDistortionLoss (TO losses/losses.py:20-28; the
  * R + lambda*D task criterion the reference keeps commented out at layer_opt.py:146-148).

@@ -54,7 +54,8 @@ SIGNATURES = {
     "fixed_point": [_P, _SZ, _I, _I, _P],
     "gaussian_lik_fwd": [_P, _P, _P, _I, _I, _I, _LL, _F, _F, _P, _P, _P],
     "round_latent": [_P, _P, _SZ, _P],
-    "factorized_lik_fwd": [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
+    "factorized_lik_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
+    "factorized_table": [_P, _P, _I, _F, _P],
     "gaussian_lik_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _LL, _LL, _F, _F, _I, _P, _P, _P],
     "factorized_lik_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     "lsq_delta_grad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _I, _F, _F, _F, _F],
@@ -89,7 +90,7 @@ SIGNATURES = {
     "pixel_unshuffle": [_P, _I, _I, _I, _I, _I, _P],
 }
 PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
-         "launch_count": (C.c_ulonglong, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
+         "launch_count": (C.c_ulonglong, []), "factorized_table_floats": (C.c_int, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
          "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
          "conv_staged_view": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p)])}

@@ -36,6 +36,23 @@ class EntropyBottleneck(nn.Module):
         # additive switch for the R + lambda*D task criterion: straight-through latent rounding (round_ste,
         # quantizer.py:64-68) instead of compressai's zero-gradient torch.round; forward values are identical
         self.ste_round = False
+        self._prior_cache = None         # (key, packed params, medians, symbol tables): see _prior()
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_prior_cache"] = None     # derived from the parameters; rebuilt on first use after un-pickling
+        return state
+
+    def _prior(self):
+        """Packed parameters, medians and per-channel symbol tables (b200lic_factorized_table) of the prior.  PTQ never
+        trains the prior, so they are built once and reused by every forward; the key (storage address and in-place
+        version of every parameter) rebuilds them after load_state_dict / .to() / an optimiser step."""
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters()) + (self.likelihood_bound,)
+        if self._prior_cache is None or self._prior_cache[0] != key:
+            packed = self.packed_params()
+            med = self._get_medians().detach().reshape(-1).contiguous()
+            self._prior_cache = (key, packed, med, ops.factorized_table(packed, med, self.likelihood_bound))
+        return self._prior_cache[1:]
 
     def _get_medians(self):
         return self.quantiles[:, :, 1:2]
@@ -60,12 +77,11 @@ class EntropyBottleneck(nn.Module):
         if training:
             raise NotImplementedError("EntropyBottleneck: the additive-noise training path is not on the PTQ hot path "
                                       "(call .eval(); the reference evaluates under model.eval())")
+        packed, med, table = self._prior()
         if torch.is_grad_enabled() and x.requires_grad:
-            z_hat, lik, bits = ops.factorized_lik_fn(x, self.packed_params(), self._get_medians().detach().reshape(-1),
-                                                     self.likelihood_bound, self.ste_round)
+            z_hat, lik, bits = ops.factorized_lik_fn(x, packed, med, self.likelihood_bound, self.ste_round, table)
         else:
-            z_hat, lik, bits = ops.factorized_lik(x, self.packed_params(), self._get_medians().detach().reshape(-1),
-                                                  self.likelihood_bound)
+            z_hat, lik, bits = ops.factorized_lik(x, packed, med, self.likelihood_bound, table=table)
         self.last_bits = bits
         return z_hat, lik
 

@@ -29,7 +29,19 @@ __global__ void __launch_bounds__(256) actq_stats_kernel(const float* __restrict
   float mn = INFINITY, mx = -INFINITY;
   if ((HW & 3) == 0 && ((uintptr_t)x & 15) == 0) {
     const float4* p4 = reinterpret_cast<const float4*>(p);
-    for (int i = (beg >> 2) + threadIdx.x; i < (end >> 2); i += blockDim.x) {
+    const int e4 = end >> 2, bd = blockDim.x;
+    int i = (beg >> 2) + threadIdx.x;
+    for (; i + 3 * bd < e4; i += 4 * bd) {           // four independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p4 + i + u * bd);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        mn = fminf(fminf(mn, v[u].x), fminf(v[u].y, fminf(v[u].z, v[u].w)));
+        mx = fmaxf(fmaxf(mx, v[u].x), fmaxf(v[u].y, fmaxf(v[u].z, v[u].w)));
+      }
+    }
+    for (; i < e4; i += bd) {
       const float4 v = __ldg(p4 + i);
       mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
       mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
@@ -82,8 +94,8 @@ __global__ void __launch_bounds__(256) actq_apply_kernel(const float* __restrict
     const float4* p4 = reinterpret_cast<const float4*>(x + base);
     float4* o4 = reinterpret_cast<float4*>(out + base);
     float4* c4 = codes ? reinterpret_cast<float4*>(codes + base) : nullptr;
-    for (int i = (beg >> 2) + threadIdx.x; i < (end >> 2); i += blockDim.x) {
-      const float4 v = __ldg(p4 + i);
+    const int e4 = end >> 2, bd = blockDim.x;
+    auto quant4 = [&](int i, const float4& v) {
       float4 o, q;
       o.x = actq_one(v.x, m, r, L, &q.x);
       o.y = actq_one(v.y, m, r, L, &q.y);
@@ -91,7 +103,16 @@ __global__ void __launch_bounds__(256) actq_apply_kernel(const float* __restrict
       o.w = actq_one(v.w, m, r, L, &q.w);
       o4[i] = o;
       if (c4) c4[i] = q;
+    };
+    int i = (beg >> 2) + threadIdx.x;
+    for (; i + 3 * bd < e4; i += 4 * bd) {           // four independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p4 + i + u * bd);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) quant4(i + u * bd, v[u]);
     }
+    for (; i < e4; i += bd) quant4(i, __ldg(p4 + i));
   } else {
     for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
       float q;

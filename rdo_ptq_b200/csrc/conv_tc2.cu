@@ -105,6 +105,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
       : "r"(addr)
       : "memory");
 }
+// tcgen05.wait::ld with the loaded registers as in/out operands: every use of v is ordered after the wait even when the
+// load was issued long before (the epilogue overlaps the TMEM read with its shared-memory loads).
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 // One lane of a converged warp, chosen by the hardware: unlike `lane == 0`, a branch on elect.sync tells the compiler
 // that exactly one thread is active, so TMA / tcgen05 operands go straight to uniform registers (with `lane == 0` every
 // UTMALDG / UTCHMMA was wrapped in a ~20-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY loop that paced the K loop).
@@ -518,14 +527,37 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         for (int h = grp * 16; h < CH; h += 32) {    // this warp's 16-channel half of the chunk
           uint32_t v[16];
           const bool trh = tr && ci == 1;       // fine-grained stamps of one steady-state chunk (debug timeline only)
+          // Issue order: TMEM read (asynchronous), then every shared-memory operand of this half (bias, weight scale,
+          // GDN's x), then the wait -- the three latencies overlap instead of adding up.
+          if (num_kb > 0) tmem_ld16(acc0 + (uint32_t)(t * g.chains * g.BN + c0 + h), v);
+          float bj[16], sj[16], xv[16];
+          const uint32_t bias_addr = sBias + (uint32_t)(c0 + h) * 4u;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(bj[j]), "=f"(bj[j + 1]), "=f"(bj[j + 2]), "=f"(bj[j + 3])
+                         : "r"(bias_addr + (uint32_t)j * 4u));
+          if (g.w_exact) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(sj[j]), "=f"(sj[j + 1]), "=f"(sj[j + 2]), "=f"(sj[j + 3])
+                           : "r"(bias_addr + 1024u + (uint32_t)j * 4u));
+          }
+          const uint32_t so0 = st_off + (uint32_t)(h * hw_box) * 4u;
+          const uint32_t sstep = (uint32_t)hw_box * 4u;
+          if (g.tma_out && g.gdn_mode) {
+            const uint32_t xa = sX + xb * tile_bytes + so0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[j]) : "r"(xa + (uint32_t)j * sstep));
+          }
           if (num_kb > 0) {
-            tmem_ld16(acc0 + (uint32_t)(t * g.chains * g.BN + c0 + h), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_wait_ld16(v);
             if (trh) dbg[110 + (h >> 4) * 4] = gtime();
             for (int ch = 1; ch < g.chains; ++ch) {      // partial sums of the other accumulator chains
               uint32_t u[16];
               tmem_ld16(acc0 + (uint32_t)((t * g.chains + ch) * g.BN + c0 + h), u);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              tmem_wait_ld16(u);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             }
@@ -537,32 +569,16 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           // compiled to ~100 SASS instructions per channel and the single epilogue warp per scheduler became
           // instruction-bound (2 us per 16 channels in the r1 timeline).
           float r[16];
-          const uint32_t bias_addr = sBias + (uint32_t)(c0 + h) * 4u;
           if (g.w_exact) {                     // accumulator holds sum x * n: y = acc * delta[co] + bias[co]
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float bj, sj;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bj) : "r"(bias_addr + (uint32_t)j * 4u));
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sj) : "r"(bias_addr + 1024u + (uint32_t)j * 4u));
-              r[j] = fmaf(__uint_as_float(v[j]), sj, bj);
-            }
+            for (int j = 0; j < 16; ++j) r[j] = fmaf(__uint_as_float(v[j]), sj[j], bj[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float bj;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bj) : "r"(bias_addr + (uint32_t)j * 4u));
-              r[j] = __uint_as_float(v[j]) + bj;
-            }
+            for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(v[j]) + bj[j];
           }
-          const uint32_t so0 = st_off + (uint32_t)(h * hw_box) * 4u;
-          const uint32_t sstep = (uint32_t)hw_box * 4u;
           if (trh) dbg[111 + (h >> 4) * 4] = gtime();
           if (g.tma_out) {
             if (g.gdn_mode) {
-              float xv[16];
-              const uint32_t xa = sX + xb * tile_bytes + so0;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[j]) : "r"(xa + (uint32_t)j * sstep));
               if (g.has_norm) {
                 const uint32_t na = sN + buf * tile_bytes + so0;
 #pragma unroll

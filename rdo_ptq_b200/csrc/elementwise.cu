@@ -215,10 +215,30 @@ __global__ void __launch_bounds__(256) lp_loss_kernel(const float* __restrict__ 
   };
   if (idx != nullptr) {           // picked target rows; row % 4 == 0 and 16-byte alignment are checked by the host
     const size_t n4 = n >> 2;
-    for (size_t i = tid; i < n4; i += stride) {
+    auto tgt4 = [&](size_t i) {
       const size_t e0 = i << 2, b_ = e0 / pk.row, e = e0 - b_ * pk.row;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(tgt + (size_t)idx[b_] * pk.row + e));
+      return __ldg(reinterpret_cast<const float4*>(tgt + (size_t)idx[b_] * pk.row + e));
+    };
+    size_t i = tid;
+    for (; i + stride < n4; i += 2 * stride) {        // two independent float4 pairs in flight per thread
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(pred) + i), b0 = tgt4(i);
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(pred) + i + stride), b1 = tgt4(i + stride);
+      float4 g0, g1;
+      one(a0.x, b0.x, g0.x);
+      one(a0.y, b0.y, g0.y);
+      one(a0.z, b0.z, g0.z);
+      one(a0.w, b0.w, g0.w);
+      one(a1.x, b1.x, g1.x);
+      one(a1.y, b1.y, g1.y);
+      one(a1.z, b1.z, g1.z);
+      one(a1.w, b1.w, g1.w);
+      if (d_pred) {
+        reinterpret_cast<float4*>(d_pred)[i] = g0;
+        reinterpret_cast<float4*>(d_pred)[i + stride] = g1;
+      }
+    }
+    for (; i < n4; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i), b = tgt4(i);
       float4 g;
       one(a.x, b.x, g.x);
       one(a.y, b.y, g.y);
@@ -235,9 +255,27 @@ __global__ void __launch_bounds__(256) lp_loss_kernel(const float* __restrict__ 
   const bool vec = (((uintptr_t)pred | (uintptr_t)tgt | (uintptr_t)d_pred) & 15) == 0;
   if (vec) {
     const size_t n4 = n >> 2;
-    for (size_t i = tid; i < n4; i += stride) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(pred) + i);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(tgt) + i);
+    const float4* p4 = reinterpret_cast<const float4*>(pred);
+    const float4* t4 = reinterpret_cast<const float4*>(tgt);
+    size_t i = tid;
+    for (; i + stride < n4; i += 2 * stride) {        // two independent float4 pairs in flight per thread
+      const float4 a0 = __ldg(p4 + i), b0 = __ldg(t4 + i), a1 = __ldg(p4 + i + stride), b1 = __ldg(t4 + i + stride);
+      float4 g0, g1;
+      one(a0.x, b0.x, g0.x);
+      one(a0.y, b0.y, g0.y);
+      one(a0.z, b0.z, g0.z);
+      one(a0.w, b0.w, g0.w);
+      one(a1.x, b1.x, g1.x);
+      one(a1.y, b1.y, g1.y);
+      one(a1.z, b1.z, g1.z);
+      one(a1.w, b1.w, g1.w);
+      if (d_pred) {
+        reinterpret_cast<float4*>(d_pred)[i] = g0;
+        reinterpret_cast<float4*>(d_pred)[i + stride] = g1;
+      }
+    }
+    for (; i < n4; i += stride) {
+      const float4 a = __ldg(p4 + i), b = __ldg(t4 + i);
       float4 g;
       one(a.x, b.x, g.x);
       one(a.y, b.y, g.y);
@@ -276,8 +314,26 @@ __global__ void __launch_bounds__(256) sq_err_kernel(const float* __restrict__ a
   size_t done = 0;
   if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
     const size_t n4 = n >> 2;
-    for (size_t i = tid; i < n4; i += stride) {
-      const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i), bv = __ldg(reinterpret_cast<const float4*>(b) + i);
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    size_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {    // eight independent 16-byte loads in flight per thread
+      float4 av[4], bv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        av[u] = __ldg(a4 + i + u * stride);
+        bv[u] = __ldg(b4 + i + u * stride);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        one(av[u].x, bv[u].x);
+        one(av[u].y, bv[u].y);
+        one(av[u].z, bv[u].z);
+        one(av[u].w, bv[u].w);
+      }
+    }
+    for (; i < n4; i += stride) {
+      const float4 av = __ldg(a4 + i), bv = __ldg(b4 + i);
       one(av.x, bv.x);
       one(av.y, bv.y);
       one(av.z, bv.z);
@@ -301,8 +357,17 @@ __global__ void __launch_bounds__(256) bits_sum_kernel(const float* __restrict__
   size_t done = 0;
   if ((((uintptr_t)lik) & 15) == 0) {
     const size_t n4 = n >> 2;
-    for (size_t i = tid; i < n4; i += stride) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(lik) + i);
+    const float4* l4 = reinterpret_cast<const float4*>(lik);
+    size_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {    // four independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(l4 + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s -= log2f(v[u].x) + log2f(v[u].y) + log2f(v[u].z) + log2f(v[u].w);
+    }
+    for (; i < n4; i += stride) {
+      const float4 v = __ldg(l4 + i);
       s -= log2f(v.x) + log2f(v.y) + log2f(v.z) + log2f(v.w);
     }
     done = n4 << 2;
@@ -342,7 +407,7 @@ int b200lic_lp_loss_fwd_bwd(const float* pred, const float* tgt, size_t n, float
   B200_REQUIRE(pred && tgt, "lp_loss_fwd_bwd: null pointer");
   B200_REQUIRE(p >= 1.f, "lp_loss_fwd_bwd: p=%f < 1", p);
   if (n == 0) return B200LIC_OK;
-  lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(pred, tgt, n, p, scale, grad_scale, loss,
+  lp_loss_kernel<<<grid_for(n / 8 + 1, 256, 4), 256, 0, as_stream(stream)>>>(pred, tgt, n, p, scale, grad_scale, loss,
                                                                              d_pred, LossPick{nullptr, 0, 0, 0, 0, 0, nullptr});
   B200_LAUNCH_CHECK("lp_loss_kernel");
   return B200LIC_OK;
@@ -360,7 +425,7 @@ int b200lic_lp_loss_fwd_bwd_sched(const float* pred, const float* tgt_cache, con
                "lp_loss_fwd_bwd_sched: rows must be a multiple of 4 elements and 16-byte aligned");
   const size_t n = rows * row_elems;
   if (n == 0) return B200LIC_OK;
-  lp_loss_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(
+  lp_loss_kernel<<<grid_for(n / 8 + 1, 256, 4), 256, 0, as_stream(stream)>>>(
       pred, tgt_cache, n, p, scale, grad_scale, loss, d_pred,
       LossPick{idx_table, table_rows, units, unit, rows, row_elems, sched});
   B200_LAUNCH_CHECK("lp_loss_kernel(sched)");
@@ -371,7 +436,7 @@ int b200lic_sq_err_sum(const float* a, const float* b, size_t n, float* out, b20
   B200_ARCH_GATE();
   B200_REQUIRE(a && b && out, "sq_err_sum: null pointer");
   if (n == 0) return B200LIC_OK;
-  sq_err_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, as_stream(stream)>>>(a, b, n, out);
+  sq_err_kernel<<<grid_for(n / 16 + 1, 256, 4), 256, 0, as_stream(stream)>>>(a, b, n, out);   // 60 registers: 4 CTAs/SM resident
   B200_LAUNCH_CHECK("sq_err_kernel");
   return B200LIC_OK;
 }

@@ -155,19 +155,28 @@ __device__ __noinline__ float factorized_rare(const FactorizedParams* P, float z
 constexpr int kTabR = 96;
 constexpr int kTabN = 2 * kTabR + 1;
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
     factorized_lik_kernel(const float* __restrict__ z, const float* __restrict__ params,
-                          const float* __restrict__ medians, int N, int C, int HW, float lik_bound,
-                          float* __restrict__ z_hat, float* __restrict__ lik, float* __restrict__ bits_out) {
+                          const float* __restrict__ medians, const float* __restrict__ table, int N, int C, int HW,
+                          int per_ch, float lik_bound, float* __restrict__ z_hat, float* __restrict__ lik,
+                          float* __restrict__ bits_out) {
   __shared__ FactorizedParams P;
   __shared__ float red[32];
   __shared__ float t_lik[kTabN], t_bits[kTabN];
-  // The N*C planes, ordered channel-major, are cut into gridDim.x equal contiguous ranges (grid = resident CTAs: one
-  // wave, every CTA the same bytes +- one plane).  A CTA's range covers at most a few channels; the symbol table is
-  // rebuilt when the channel changes.  The first version launched C * splits CTAs of unequal residency (1.7 waves at
-  // C = 192) and reached 46 % of the HBM peak (profiles/README.md r1c).
+  // One resident wave, every CTA the same bytes.  per_ch > 0: gridDim.x = C * per_ch, CTA (c, r) takes the r-th share of
+  // channel c's N planes (one symbol table per CTA).  per_ch == 0 (more channels than CTA slots): the N*C planes,
+  // channel-major, are cut into gridDim.x equal contiguous ranges and the table changes with the channel.  The first
+  // version launched C * splits CTAs of unequal residency (1.7 waves at C = 192): 46 % of the HBM peak (r1c).
   const long long planes = (long long)N * C;
-  const long long p_begin = planes * blockIdx.x / gridDim.x, p_end = planes * (blockIdx.x + 1) / gridDim.x;
+  long long p_begin, p_end;
+  if (per_ch > 0) {
+    const int c = blockIdx.x / per_ch, r = blockIdx.x - c * per_ch;
+    p_begin = (long long)c * N + (long long)N * r / per_ch;
+    p_end = (long long)c * N + (long long)N * (r + 1) / per_ch;
+  } else {
+    p_begin = planes * blockIdx.x / gridDim.x;
+    p_end = planes * (blockIdx.x + 1) / gridDim.x;
+  }
   const bool vec = (HW & 3) == 0 && (((uintptr_t)z | (uintptr_t)z_hat | (uintptr_t)lik) & 15) == 0;
   const int q4 = HW >> 2;
   float bits = 0.f;
@@ -185,7 +194,15 @@ __global__ void __launch_bounds__(256, 3)
       }
     }
     __syncthreads();                       // the previous segment's table is no longer read
-    if (threadIdx.x < 58) {
+    const float med = __ldg(medians + c);
+    if (table != nullptr) {                // tables prepared by b200lic_factorized_table (a function of the parameters)
+      const float* tc = table + (size_t)c * (2 * kTabN);
+      for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
+        t_lik[j] = __ldg(tc + j);
+        t_bits[j] = __ldg(tc + kTabN + j);
+      }
+    }
+    if (threadIdx.x < 58) {                // the direct path (fix-up pass) needs the reparametrised network either way
       const float raw = __ldg(params + (size_t)c * 58 + threadIdx.x);
       float* dst = reinterpret_cast<float*>(&P);
       float v = raw;
@@ -194,31 +211,32 @@ __global__ void __launch_bounds__(256, 3)
       dst[threadIdx.x] = v;
     }
     __syncthreads();
-    const float med = __ldg(medians + c);
-    for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
-      const float zh = __fadd_rn((float)(j - kTabR), med);
-      const float l = factorized_rare(&P, zh, lik_bound);
-      t_lik[j] = l;
-      t_bits[j] = -log2f(l);
+    if (table == nullptr) {
+      for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
+        const float zh = __fadd_rn((float)(j - kTabR), med);
+        const float l = factorized_rare(&P, zh, lik_bound);
+        t_lik[j] = l;
+        t_bits[j] = -log2f(l);
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    // Streaming pass: table symbols only.  A symbol outside the table (|k| > kTabR: rare) gets its z_hat here and
+    // its likelihood in the fix-up pass below, so the hot loop carries no call and stays under 64 registers: four CTAs
+    // (64 KB of loads in flight) per SM instead of three.
+    bool rare = false;
     auto one = [&](float zv, float& zh, float& l) {
       const float k = rintf(__fsub_rn(zv, med));
       zh = __fadd_rn(k, med);
-      if (fabsf(k) <= (float)kTabR) {
-        const int j = (int)k + kTabR;
-        l = t_lik[j];
-        bits += t_bits[j];
-      } else {
-        l = factorized_rare(&P, zh, lik_bound);
-        bits -= log2f(l);
-      }
+      const bool in = fabsf(k) <= (float)kTabR;
+      const int j = in ? (int)k + kTabR : 0;
+      l = t_lik[j];
+      bits += in ? t_bits[j] : 0.f;
+      rare |= !in;
     };
+    const unsigned total = (unsigned)(n1 - n0) * (unsigned)q4, row4 = (unsigned)C * (unsigned)q4;
+    const unsigned base4 = (unsigned)n0 * row4 + (unsigned)c * (unsigned)q4;      // float4 units; host checks numel < 2^34
     if (vec) {
       // planes n0..n1-1 of channel c as one flat float4 index space, four independent requests per thread in flight
-      // (32-bit float4 offsets: the host checks numel < 2^34)
-      const unsigned total = (unsigned)(n1 - n0) * (unsigned)q4, row4 = (unsigned)C * (unsigned)q4;
-      const unsigned base4 = (unsigned)n0 * row4 + (unsigned)c * (unsigned)q4;
       const float4* z4 = reinterpret_cast<const float4*>(z);
       for (unsigned i0 = threadIdx.x; i0 < total; i0 += 4u * blockDim.x) {
         float4 zv[4];
@@ -253,6 +271,19 @@ __global__ void __launch_bounds__(256, 3)
         }
       }
     }
+    if (__syncthreads_or(rare ? 1 : 0)) {
+      // fix-up pass (some symbol of this segment lies outside the table): direct evaluation of those symbols only
+      for (int n = n0; n < n1; ++n) {
+        const size_t base = ((size_t)n * C + c) * HW;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+          const float k = rintf(__fsub_rn(__ldg(z + base + i), med));
+          if (fabsf(k) <= (float)kTabR) continue;
+          const float l = factorized_rare(&P, __fadd_rn(k, med), lik_bound);
+          bits -= log2f(l);
+          if (lik) lik[base + i] = l;
+        }
+      }
+    }
   }
   if (bits_out) {
     const float tot = block_sum(bits, red);
@@ -260,6 +291,33 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
+
+// Symbol tables of every channel: table[c][0][k + R] = likelihood of the symbol median[c] + k, table[c][1][k + R] =
+// -log2 of it, |k| <= R = kTabR.  A function of the prior's parameters only (frozen in PTQ), so callers build it once
+// per model; the same expressions on the same operands as the in-kernel build, hence identical values.
+__global__ void __launch_bounds__(256) factorized_table_kernel(const float* __restrict__ params,
+                                                                const float* __restrict__ medians, float lik_bound,
+                                                                float* __restrict__ table) {
+  __shared__ FactorizedParams P;
+  const int c = blockIdx.x;
+  if (threadIdx.x < 58) {
+    const float raw = __ldg(params + (size_t)c * 58 + threadIdx.x);
+    float* dst = reinterpret_cast<float*>(&P);
+    float v = raw;
+    if (threadIdx.x < 33) v = softplusf_(raw);
+    else if (threadIdx.x >= 46) v = tanhf(raw);
+    dst[threadIdx.x] = v;
+  }
+  __syncthreads();
+  const float med = __ldg(medians + c);
+  float* tc = table + (size_t)c * (2 * kTabN);
+  for (int j = threadIdx.x; j < kTabN; j += blockDim.x) {
+    const float zh = __fadd_rn((float)(j - kTabR), med);
+    const float l = factorized_rare(&P, zh, lik_bound);
+    tc[j] = l;
+    tc[kTabN + j] = -log2f(l);
+  }
+}
 
 // ---- K9 backward -------------------------------------------------------------------------------------------
 // Gradient of the Gaussian-conditional likelihood (compressai autograd of GaussianConditional.forward in eval mode,
@@ -452,18 +510,32 @@ int b200lic_round_latent(const float* y, const float* means, size_t n, float* y_
   return B200LIC_OK;
 }
 
-int b200lic_factorized_lik_fwd(const float* z, const float* params, const float* medians, int N, int C, int HW,
-                               float lik_bound, float* z_hat, float* lik, float* bits, b200lic_stream_t stream) {
+int b200lic_factorized_table_floats(void) { return 2 * kTabN; }
+
+int b200lic_factorized_table(const float* params, const float* medians, int C, float lik_bound, float* table,
+                             b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(params && medians && table, "factorized_table: null pointer");
+  B200_REQUIRE(C > 0, "factorized_table: C=%d", C);
+  factorized_table_kernel<<<(unsigned)C, 256, 0, as_stream(stream)>>>(params, medians, lik_bound, table);
+  B200_LAUNCH_CHECK("factorized_table_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_factorized_lik_fwd(const float* z, const float* params, const float* medians, const float* table, int N,
+                               int C, int HW, float lik_bound, float* z_hat, float* lik, float* bits,
+                               b200lic_stream_t stream) {
   B200_ARCH_GATE();
   B200_REQUIRE(z && params && medians && z_hat, "factorized_lik_fwd: null pointer");
   B200_REQUIRE(N > 0 && C > 0 && HW > 0, "factorized_lik_fwd: bad shape (%d,%d,%d)", N, C, HW);
   B200_REQUIRE((long long)N * C * HW < (1LL << 34), "factorized_lik_fwd: tensor too large (%d,%d,%d)", N, C, HW);
-  // one resident wave: 3 CTAs per SM, each takes an equal contiguous share of the N*C planes (channel-major)
-  long long grid = 3LL * num_sms();
-  const long long planes = (long long)N * C;
-  if (grid > planes) grid = planes;
-  factorized_lik_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(z, params, medians, N, C, HW, lik_bound, z_hat,
-                                                                       lik, bits);
+  // one resident wave of 4 CTAs per SM: whole shares of a channel per CTA when the channels are fewer than the slots
+  const long long slots = 4LL * num_sms(), planes = (long long)N * C;
+  int per_ch = (int)(slots / C);
+  if (per_ch > N) per_ch = N;
+  long long grid = per_ch > 0 ? (long long)C * per_ch : (slots < planes ? slots : planes);
+  factorized_lik_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(z, params, medians, table, N, C, HW, per_ch,
+                                                                       lik_bound, z_hat, lik, bits);
   B200_LAUNCH_CHECK("factorized_lik_kernel");
   return B200LIC_OK;
 }

@@ -209,15 +209,25 @@ def round_latent(y, means=None):
     return out
 
 
-def factorized_lik(z, packed_params, medians, lik_bound=1e-9, want_lik=True):
+def factorized_table(packed_params, medians, lik_bound=1e-9):
+    """Per-channel symbol tables of the factorised prior (b200lic_factorized_table): [C, 2, 2R+1]."""
+    packed_params, medians = _c(packed_params), _c(medians)
+    Cc = packed_params.shape[0]
+    per = int(_lib.lib().b200lic_factorized_table_floats())
+    table = torch.empty(Cc, 2, per // 2, device=packed_params.device, dtype=torch.float32)
+    call("factorized_table", _p(packed_params), _p(medians), Cc, lik_bound, _p(table))
+    return table
+
+
+def factorized_lik(z, packed_params, medians, lik_bound=1e-9, want_lik=True, table=None):
     z = _c(z, "z")
     N, Cc = z.shape[0], z.shape[1]
     HW = z.numel() // (N * Cc)
     z_hat = torch.empty_like(z)
     lik = torch.empty_like(z) if want_lik else None
     bits = torch.zeros(1, device=z.device, dtype=torch.float32)
-    call("factorized_lik_fwd", _p(z), _p(_c(packed_params)), _p(_c(medians)), N, Cc, HW, lik_bound, _p(z_hat),
-         _p(lik), _p(bits))
+    call("factorized_lik_fwd", _p(z), _p(_c(packed_params)), _p(_c(medians)), _p(table), N, Cc, HW, lik_bound,
+         _p(z_hat), _p(lik), _p(bits))
     return z_hat, lik, bits
 
 
@@ -276,8 +286,8 @@ class _FactorizedLikFn(torch.autograd.Function):
     """K10 with its latent gradient (b200lic_factorized_lik_bwd); the prior's parameters are frozen in PTQ."""
 
     @staticmethod
-    def forward(ctx, z, packed_params, medians, lik_bound, ste):
-        z_hat, lik, bits = factorized_lik(z, packed_params, medians, lik_bound)
+    def forward(ctx, z, packed_params, medians, lik_bound, ste, table=None):
+        z_hat, lik, bits = factorized_lik(z, packed_params, medians, lik_bound, table=table)
         ctx.save_for_backward(z_hat, packed_params, medians)
         ctx.cfg = (float(lik_bound), bool(ste))
         ctx.set_materialize_grads(False)
@@ -295,11 +305,11 @@ class _FactorizedLikFn(torch.autograd.Function):
         g_bits = None if g_bits is None else _c(g_bits.reshape(1))
         call("factorized_lik_bwd", _p(z_hat), _p(_c(packed)), _p(_c(med)), _p(g_lik), _p(g_bits), _p(g_zhat), N, Cc, HW,
              lik_bound, int(ste), _p(d_z))
-        return d_z, None, None, None, None
+        return d_z, None, None, None, None, None
 
 
-def factorized_lik_fn(z, packed_params, medians, lik_bound=1e-9, ste=False):
-    return _FactorizedLikFn.apply(z, packed_params, medians, lik_bound, ste)
+def factorized_lik_fn(z, packed_params, medians, lik_bound=1e-9, ste=False, table=None):
+    return _FactorizedLikFn.apply(z, packed_params, medians, lik_bound, ste, table)
 
 
 class _RoundLatentSTE(torch.autograd.Function):

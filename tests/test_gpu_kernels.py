@@ -228,6 +228,48 @@ def test_factorized_likelihood(ops, dev, golden_c):
     assert torch.equal(gz.cpu(), rz) and torch.allclose(gl.cpu(), rl.detach(), rtol=2e-4, atol=3e-7)
 
 
+def test_factorized_tables_work_split_and_rare_symbols(ops, dev):
+    """K10 variants agree bit for bit: prebuilt symbol tables (b200lic_factorized_table) vs tables built inside the
+    kernel; per-channel CTA shares (C < CTA slots) vs contiguous plane ranges (C > slots); symbols outside the table
+    (|k| > 96, fix-up pass) vs the oracle; the module's table cache follows its parameters."""
+    from rdo_ptq_b200.codec import EntropyBottleneck
+    torch.manual_seed(3)
+    for C, N, hw in ((7, 5, (6, 10)), (192, 9, (8, 12)), (700, 2, (3, 5))):        # 700 channels > 4 x 148 CTA slots
+        oe, pe = ocodec.EntropyBottleneck(C).eval(), EntropyBottleneck(C).eval()
+        with torch.no_grad():
+            for i in range(4):
+                getattr(oe, f"_factor{i}").uniform_(-0.5, 0.5)
+            oe.quantiles[:, 0, 1].uniform_(-1, 1)
+        pe.load_state_dict(oe.state_dict())
+        pe.to(dev)
+        z = torch.randn(N, C, *hw) * 6
+        z.view(-1)[::97] *= 40                                                     # symbols far outside the table
+        assert (z.abs() > 100).any()
+        rz, rl = oe(z)
+        packed, med = pe.packed_params(), pe._get_medians().detach().reshape(-1).contiguous()
+        table = ops.factorized_table(packed, med, 1e-9)
+        assert table.shape == (C, 2, 193)
+        a = ops.factorized_lik(z.to(dev), packed, med, 1e-9)
+        b = ops.factorized_lik(z.to(dev), packed, med, 1e-9, table=table)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert abs(a[2].item() - b[2].item()) <= 1e-5 * abs(a[2].item())
+        assert torch.equal(a[0].cpu(), rz)
+        assert torch.allclose(a[1].cpu(), rl.detach(), rtol=2e-4, atol=3e-7)
+        ref_bits = -torch.log2(rl.detach().double()).sum().item()
+        assert abs(b[2].item() - ref_bits) < 1e-4 * ref_bits
+        gz, gl = pe(z.to(dev))                                                     # module path (cached tables)
+        assert torch.equal(gz, a[0]) and torch.equal(gl, a[1])
+    key0 = pe._prior_cache[0]
+    pe(z.to(dev))
+    assert pe._prior_cache[0] == key0                                              # reused
+    with torch.no_grad():
+        pe._bias0.add_(0.25)
+        oe._bias0.add_(0.25)
+    gz, gl = pe(z.to(dev))
+    assert pe._prior_cache[0] != key0                                              # rebuilt after an in-place update
+    assert torch.allclose(gl.cpu(), oe(z)[1].detach(), rtol=2e-4, atol=3e-7)
+
+
 def test_lp_loss_and_reductions(ops, dev, golden_q):
     for p in (2.0, 1.0, 2.4):
         g = golden_q[f"lp/{p}"]
