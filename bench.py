@@ -188,11 +188,12 @@ def run_cuda(args):
             "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s",
             "frac": flops / (k_ms * 1e-3) / 1e12 / pk["tf"],
             # dram__bytes_read.sum + dram__bytes_write.sum of tc2_gather_gemm_kernel on this shape, from the committed
-            # `ncu --set full` capture profiles/r1c_ncu_full_raw.csv (123.3 MB + 4.6 MB); algorithmic operand bytes are
+            # `ncu --set full` capture profiles/r1f_ncu_full_raw.csv (123.0 MB + 4.4 MB); algorithmic operand bytes are
             # 100.7 MB (split-bf16 x) + 3.7 MB (packed weights) + 25.2 MB (y, still in L2 when the kernel ends)
-            "traffic": 127.9e6, "peak_source": pk["src"], "ms_per_launch": k_ms,
+            "traffic": 127.4e6, "peak_source": pk["src"], "ms_per_launch": k_ms,
             "note": "launch = NHWC split + weight pack + tcgen05 GEMM; 3 bf16 MMA passes per product (fp32-accurate "
-                    "split), so frac <= 1/3; ncu tensor-pipe active 69-71 % avg / 80-82 % max SM on the GEMM kernel"}
+                    "split), so frac <= 1/3; ncu tensor-pipe active 68-72 % avg / 79-84 % max SM on the GEMM kernel "
+                    "(profiles/r1d_, r1f_ncu_full_raw.csv)"}
     del flush
 
     # ---- end-to-end runs through the public API with HOST buffers (e2e) ----------------------------------------------

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200lic.so")
+# B200LIC_LIB: another build of the SAME library (A/B experiments on kernel variants); never a different implementation
+LIB_PATH = os.environ.get("B200LIC_LIB") or os.path.join(_HERE, "lib", "libb200lic.so")
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_ARCH", -3: "ERR_CUDA", -4: "ERR_UNSUPPORTED"}
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2

@@ -132,8 +132,8 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void epi_bar(int id) {  // named barrier over the 8 epilogue warps
-  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
+__device__ __forceinline__ void epi_bar(int id, int threads) {  // named barrier over the 4 or 8 epilogue warps
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // K-major SWIZZLE_64B operand tile: rows of 64 B (32 bf16), 8-row groups of 512 B.
@@ -198,10 +198,11 @@ struct Tc2Geom {
   int epi_smem;               // staging tiles are carved out of shared memory (planned TMA epilogue)
   int x_slots;                // ring slots (one chunk each) for GDN's x operand
   int chunk;                  // epilogue chunk width in channels (16 or 32)
+  int epi_warps;              // 4, or 8 (two warps per TMEM lane quarter) when the epilogue outweighs the K loop
   int dbg_mode;               // 0 normal; 1 = skip the MMAs; 2 = skip the TMA loads (bottleneck experiments only)
 };
 
-constexpr int kT2Threads = 320;        // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kT2Threads = 320;        // TMA warp, MMA warp, up to 8 epilogue warps (launched: 64 + 32 * epi_warps)
 constexpr int kA2Bytes = 128 * 64;        // 128 pixel rows x 32 bf16
 
 struct PhaseGeom {
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   const uint32_t sScale = sBias + 1024u;                                             // [BN] weight scale (w_exact)
   const uint32_t full_bar = bars, empty_bar = bars + 8u * g.stages;
   const uint32_t tfull_bar = empty_bar + 8u * g.stages;          // [2] accumulator set complete
-  const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (8 warp arrivals)
+  const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (one arrival per epilogue warp)
   const uint32_t xfull_bar = tempty_bar + 16u;                   // [x_slots] GDN x chunk landed
   const uint32_t tmem_ptr_addr = xfull_bar + 8u * (uint32_t)(g.x_slots > 0 ? g.x_slots : 1);
   volatile uint32_t* tmem_ptr_gen =
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8u * s, 1);
-      mbar_init(tempty_bar + 8u * s, 8);
+      mbar_init(tempty_bar + 8u * s, (uint32_t)g.epi_warps);
     }
     for (int s = 0; s < g.x_slots; ++s) mbar_init(xfull_bar + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -424,8 +425,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     // warp per scheduler the epilogue was latency-bound: the fine-grained timeline (profiles/README.md r1f) showed
     // ~9 cycles per instruction -- tcgen05.ld 0.13 us, 16 bias adds 0.1 us, 16 x (ld.shared, rsqrt, mul) 0.36 us,
     // 16 st.shared 0.1 us per half, 1.4 us per chunk -- with nothing else resident on the scheduler to fill the stalls.
+    // Four warps (one per quarter, both halves each) when the K loop hides the epilogue anyway: the wide form costs the
+    // calibration sweep 1 % (fewer registers / issue slots left for the MMA thread and for co-resident kernels).
     const int q4 = warp & 3;
-    const int grp = (warp - 2) >> 2;                                // which half of a chunk this warp handles
+    const int epi_threads = g.epi_warps * 32;
+    const int h_step = g.epi_warps == 8 ? 32 : 16;
+    const int grp = (warp - 2) >> 2;                                // which half of a chunk this warp handles (8 warps)
     const int m = q4 * 32 + lane;                                   // row of the tile = pixel
     const int et = (warp - 2) * 32 + lane;                          // 0..255 within the epilogue group
     const int iw = m % g.BW, ih = (m / g.BW) % g.BH, ii = m / (g.BW * g.BH);
@@ -482,8 +487,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         }
       }
       if (bias_base != co_base) {             // per-channel bias of this n-tile -> shared memory (once per n-tile)
-        epi_bar(3);
-        for (int i = et; i < g.BN; i += 256) {
+        epi_bar(3, epi_threads);
+        for (int i = et; i < g.BN; i += epi_threads) {
           const float bv = (bias && co_base + i < g.Cout) ? __ldg(bias + co_base + i) : 0.f;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sBias + (uint32_t)i * 4u), "f"(bv) : "memory");
           if (g.w_exact) {
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(sScale + (uint32_t)i * 4u), "f"(sv) : "memory");
           }
         }
-        epi_bar(3);
+        epi_bar(3, epi_threads);
         bias_base = co_base;
       }
       const bool tr = trace && w == 0 && et == 0;
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         if (g.tma_out) {
           // the TMA store that read this staging buffer two chunks ago must have finished reading it
           if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          epi_bar(1);
+          epi_bar(1, epi_threads);
           if (tr && ci < 30) dbg[2 + 3 * ci] = gtime();
           if (g.gdn_mode) {
             xb = xk_used % NX;
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const bool valid = a < q.Pa && b < q.Pb && n < g.N;
         const long long obase = ((long long)n * g.Cout + co_base + c0) * plane +
                                 (long long)(a * q.out_step + q.ph) * g.Wo + (b * q.out_step + q.pw);
-        for (int h = grp * 16; h < CH; h += 32) {    // this warp's 16-channel half of the chunk
+        for (int h = grp * 16; h < CH; h += h_step) {    // this warp's 16-channel half (or both halves) of the chunk
           uint32_t v[16];
           const bool trh = tr && ci == 1;       // fine-grained stamps of one steady-state chunk (debug timeline only)
           // Issue order: TMEM read (asynchronous), then every shared-memory operand of this half (bias, weight scale,
@@ -640,7 +645,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         if (g.tma_out) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           if (tr && ci == 1) dbg[118] = gtime();
-          epi_bar(2);
+          epi_bar(2, epi_threads);
           if (tr && ci == 1) dbg[119] = gtime();
           if (et == 0) {
             tma_store_4d(&map_y, sY + buf * tile_bytes, b0, a0, co_base + c0, n0);
@@ -698,7 +703,7 @@ static int pow2_ceil2(int v) {
 struct Tc2Plan {
   bool ok = false;
   int Cpad, CoutPad, Tmax, phases, BN, n_tiles, BW, BH, BI, MT, m_tiles, m_groups, stages, acc_sets, tmem_cols;
-  int tma_out, epi_smem, x_slots, chunk, chains;
+  int tma_out, epi_smem, x_slots, chunk, chains, epi_warps;
   size_t x_bytes, b_bytes, total_bytes, smem_bytes;
 };
 
@@ -838,6 +843,17 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
     p.stages = (int)((avail - epi) / stage);
     if (p.stages > 8) p.stages = 8;
   }
+  {
+    // Epilogue width.  Estimated per work item (constants from the timelines in profiles/README.md, microseconds):
+    // K loop = K blocks x MT x 6 MMAs x 63 ns x BN/192; epilogue with four warps = MT x BN/32 chunks x (2.1 GDN, 1.1
+    // TMA-store, 1.6 direct-store).  Eight warps when the epilogue is not hidden behind the next item's K loop.
+    const double taps = transposed ? (double)(KH * KW) / p.phases : (double)(KH * KW);
+    const double t_k = taps * (p.Cpad / 32) * p.MT * 6.0 * 0.063 * p.BN / 192.0;
+    const double t_e = p.MT * (p.BN / 32.0) * (gdn_mode ? 2.1 : (p.tma_out ? 1.1 : 1.6));
+    p.epi_warps = (p.chunk == 32 && t_e > 0.4 * t_k) ? 8 : 4;
+    const char* e_ew = getenv("B200LIC_TC_EPI");             // experiments only
+    if (e_ew && (atoi(e_ew) == 4 || atoi(e_ew) == 8)) p.epi_warps = atoi(e_ew);
+  }
   p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 2048;
   p.x_bytes = ((size_t)N * H * W * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.b_bytes = ((size_t)p.phases * p.CoutPad * p.Tmax * p.Cpad * 2 + 1023) / 1024 * 1024;
@@ -962,7 +978,7 @@ int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
             p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, w_scale ? 1 : p.chains, w_scale ? 1 : 0, act, slope, gdn_mode, fixed_point,
-            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, dbg_mode};
+            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode};
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc2_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -982,7 +998,7 @@ int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   const long long items = (long long)p.phases * p.n_tiles * p.m_groups;
   const int sms = num_sms();
   const int grid = (int)(items < sms ? items : sms);
-  tc2_gather_gemm_kernel<<<grid, kT2Threads, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
+  tc2_gather_gemm_kernel<<<grid, 64 + 32 * p.epi_warps, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
                                                                 norm_out, y, dbg);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
