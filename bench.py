@@ -276,6 +276,8 @@ def run_cuda(args):
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_baseline(steps=1, batch=PER_GPU_BATCH, units_subset=None)
+        if not args.skip_fwd:
+            cpu.update(cpu_fwd_baseline())
     if rank == 0:
         line = {"metric": "calib imgs/s", "value": value, "unit": "imgs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -347,12 +349,48 @@ def cpu_baseline(steps=1, batch=PER_GPU_BATCH, units_subset=None, warmup=0):
             "seconds": dt}
 
 
+def cpu_fwd_baseline(h=512, w=768, reps=1):
+    """Second half of the metric on the host cores: the oracle's W8A8 evaluation forward (dynamic A8 on) of one
+    768x512 image, once with the activation quantiser as the reference ships it (Python loop over the channels,
+    quantizer.py:99-117: "verbatim") and once with the vectorised equivalent (same arithmetic; SURVEY 8(d) asks for
+    both so the speed-up is not inflated by interpreter overhead)."""
+    from oracle import codec as ocodec, quant_wrap as owrap, quantizers as oq
+    from rdo_ptq_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(1005)
+    m = ocodec.ARCHS[ARCH](N=N_CH, M=M_CH).eval()
+    synth.init_weights(m, gain=GAIN)
+    qnn = owrap.QuantModel(m, WQ, AQ).eval()
+    x = synth.synthetic_image(h, w)
+    out = {}
+    with torch.no_grad():
+        qnn.set_quant_state(True, False)
+        qnn(x)                                              # weight ranges
+        for mod in qnn.modules():
+            if hasattr(mod, "trained"):
+                mod.trained = True
+        qnn.set_quant_state(True, True)
+        qnn.model.g_s[-1].set_quant_state(True, False)
+        for tag, loop in (("vectorised", False), ("verbatim", True)):
+            oq.UniformAffineQuantizer.act_verbatim_loop = loop
+            try:
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    qnn(x)
+                out[tag] = reps * h * w / 1e6 / (time.perf_counter() - t0)
+            finally:
+                oq.UniformAffineQuantizer.act_verbatim_loop = False
+    return {"fwd_mpx_s_verbatim": out["verbatim"], "fwd_mpx_s_vectorised": out["vectorised"],
+            "fwd_sample": f"{reps} W8A8 forward(s) of one {w}x{h} image, {ARCH} N={N_CH}, oracle on {os.cpu_count()} threads"}
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", 0)) != 0:
         return
     steps = max(1, min(args.steps, 20))          # one sweep is 1.5-4.5 s on 8-16 host cores: K = 20 stays within minutes
     warm = max(0, min(args.warmup, 3))
     r = cpu_baseline(steps=steps, warmup=warm)
+    r.update(cpu_fwd_baseline())
     line = {"impl": "reference", "metric": "calib imgs/s", "value": r["value"], "unit": "imgs/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": warm,
             "ms_per_step": r["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -361,7 +399,8 @@ def run_reference(args):
                        "arm": "oracle port of the reference loop (PyTorch-CPU fp32) on the host cores; a step is one "
                               "sweep of the same units at the same batch"},
             "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0,
-                                       "d2h_bytes_per_step": 0}}
+                                       "d2h_bytes_per_step": 0},
+            "fwd_mpx_s": r["fwd_mpx_s_verbatim"]}
     print(json.dumps(line))
 
 

@@ -119,6 +119,9 @@ class UniformAffineQuantizer(nn.Module):
     # Extension switch (not in the reference): thread n_bits into the dynamic activation quantiser, which the
     # reference hard-wires to 8 bit (quantizer.py:81-121); BASELINE config 4 (W10A10) sets it.  Default = reference.
     act_bits_follow_n_bits = False
+    # CPU-baseline switch: run the dynamic activation quantiser as the reference ships it (a Python loop over the
+    # channels, quantizer.py:99-117) instead of the vectorised equivalent; the two are bit-identical (make_golden.py)
+    act_verbatim_loop = False
 
     def __init__(self, n_bits=8, symmetric=False, channel_wise=False, scale_method="max",
                  leaf_param=False, tconv=False, act=False, prob=1.0):
@@ -190,7 +193,8 @@ class UniformAffineQuantizer(nn.Module):
     def forward(self, x: torch.Tensor, act: bool = False):
         """:156-184."""
         if act:
-            return act_quant(x, self.n_bits if self.act_bits_follow_n_bits else 8)
+            fn = act_quant_loop if self.act_verbatim_loop else act_quant
+            return fn(x, self.n_bits if self.act_bits_follow_n_bits else 8)
         if not self.inited:
             if self.leaf_param:
                 return x
