@@ -78,3 +78,39 @@ def test_two_rank_gloo_sharding_and_gradient_allreduce():
     for r in res:
         assert r[2] == 1.5 and r[3] == 15.0                                   # mean of the two ranks' gradients
         assert abs(r[4] - 30.0) < 1e-12 and abs(r[5] - 0.5) < 1e-12 and r[6] == 7
+
+
+def test_entry_point_flags_and_walk_order(monkeypatch):
+    """main2.py drop-in: the reference's flag defaults (main2.py:20-60) and the depth-first recon_model walk
+    (main2.py:227-250) visiting the units in the oracle's order, layers -> layer_reconstruction, blocks ->
+    block_reconstruction, with the walk position as unit_id; quantize.py drop-in: its defaults (quantize.py:27-48)."""
+    from oracle import calib as ocalib
+    from rdo_ptq_b200 import codec, main2, quantize as lu_entry, quantization as Q
+    a = main2.parse_args([])
+    assert (a.seed, a.batch_size, a.n_bits_w, a.n_bits_a, a.iters_w, a.num_samples) == (1005, 4, 8, 8, 20000, 12)
+    assert (a.weight, a.b_start, a.b_end, a.warmup, a.input_prob, a.lr, a.init, a.task_loss) == \
+        (0.01, 20, 2, 0.2, 0.5, 4e-5, "max", 2.0)
+    assert not a.channel_wise and not a.act_quant and not a.disable_8bit_head_stem
+    assert main2.parse_args(["--task_loss", "rd"]).task_loss == "rd"
+    b = lu_entry.parse_args([])
+    assert (b.seed, b.n_bits_w, b.n_bits_a, b.type, b.init) == (1005, 8, 16, "INT8", "max")
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    for arch, kw in (("mbt2018-mean", dict(N=8, M=12)), ("cheng2020-attn", dict(N=12))):
+        p = Q.QuantModel(codec.ARCHS[arch](**kw), wq, aq)
+        o = owrap.QuantModel(ocodec.ARCHS[arch](**kw), wq, aq)
+        seen, oseen = [], []
+        monkeypatch.setattr(main2, "layer_reconstruction",
+                            lambda qnn, m, name, unit_id=0, **k: seen.append(("layer", name, unit_id, k["iters"])))
+        monkeypatch.setattr(main2, "block_reconstruction",
+                            lambda qnn, m, name, unit_id=0, **k: seen.append(("block", name, unit_id, k["iters"])))
+        monkeypatch.setattr(ocalib, "reconstruct", lambda qnn, m, uid, name, cali, **k: oseen.append(
+            ("block" if isinstance(m, owrap.BaseQuantBlock) else "layer", name, uid, k["iters"])))
+        traces = main2.recon_model(p, iters=7)
+        otraces = ocalib.recon_model(o, None, iters=7)
+        assert seen == oseen and list(traces) == list(otraces) and len(seen) >= 20, arch
+        assert [s[2] for s in seen] == sorted(s[2] for s in seen)                  # unit ids follow the walk
+        if arch == "cheng2020-attn":
+            assert any(k == "block" for k, *_ in seen) and any(k == "layer" for k, *_ in seen)
+    # the image output layer the reference patches by hand (main2.py:256-263)
+    assert main2.output_layer(p, True) is p.model.g_s[-1][0]
