@@ -114,3 +114,29 @@ def test_entry_point_flags_and_walk_order(monkeypatch):
             assert any(k == "block" for k, *_ in seen) and any(k == "layer" for k, *_ in seen)
     # the image output layer the reference patches by hand (main2.py:256-263)
     assert main2.output_layer(p, True) is p.model.g_s[-1][0]
+
+
+def test_bench_reference_arm_json_contract(monkeypatch, capsys):
+    """`bench.py --impl reference` (the host-CPU arm): one JSON line with the contract's keys, the calibration baseline
+    and both forward baselines (verbatim per-channel loop / vectorised).  Shrunk codec so it runs in seconds."""
+    import argparse
+    import json
+    import bench
+    monkeypatch.setattr(bench, "N_CH", 8)
+    monkeypatch.setattr(bench, "M_CH", 12)
+    monkeypatch.setattr(bench, "PATCH", 64)
+    monkeypatch.setenv("RANK", "0")
+    bench.run_reference(argparse.Namespace(steps=1, warmup=0))
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "fwd_mpx_s"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "calib imgs/s" and line["value"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["units"] == 20
+    assert cb["fwd_mpx_s_verbatim"] > 0 and cb["fwd_mpx_s_vectorised"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("RDO-PTQ AdaRound calibration sweep")
+    monkeypatch.setenv("RANK", "1")                       # other ranks exit without work or output
+    bench.run_reference(argparse.Namespace(steps=1, warmup=0))
+    assert capsys.readouterr().out == ""
