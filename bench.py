@@ -208,16 +208,20 @@ def run_cuda(args):
         qnn2 = build()
         sess2 = CalibrationSession(qnn2, cali.cpu() if mode == "stream" else cali, batch_size=PER_GPU_BATCH,
                                    host_caches=mode, **CALIB)
+        # loss read-back every step (rec/task/round per unit): a non-blocking copy into pinned memory whose values are
+        # consumed one step later, so the host queues step k+1 while step k runs (B200LIC_E2E_LAG=0: blocking read)
+        lag = os.environ.get("B200LIC_E2E_LAG", "1") != "0"
         for _ in range(max(3, args.warmup)):          # >= graph_warmup eager sweeps + the capture sweep
             sess2.sweep()
-            sess2.losses()
+            sess2.losses(lag=lag)
         barrier()
         sess2.h2d_bytes = 0
         t0 = time.perf_counter()
         d2h = 0
         for _ in range(args.steps):
             sess2.sweep()
-            d2h += 4 * 3 * len(sess2.losses())          # loss read-back every step (rec/task/round per unit)
+            sess2.losses(lag=lag)
+            d2h += 4 * 3 * n_units
         barrier()
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)

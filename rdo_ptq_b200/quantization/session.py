@@ -142,6 +142,7 @@ class CalibrationSession:
                                            process_group=process_group, learn_delta=learn_delta)
         # all units' (rec, task, round) accumulators live in one [U, 3] buffer: one device->host read per report
         self._loss_all = torch.zeros(len(self.units), 3, device=dev)
+        self._loss_host = None                           # pinned double buffer of losses(lag=True)
         for i, (n, _) in enumerate(self.units):
             self.trainers[n].loss_buf = self._loss_all[i]
         self.n_samples = cali.size(0)
@@ -419,17 +420,42 @@ class CalibrationSession:
         """Library kernel launches so far, including those inside graph replays."""
         return _lib.launch_count() + self.replayed_launches - self._captured_launches
 
-    def losses(self):
-        """Per-unit mean (rec, task, round, total) since the last call: ONE device->host copy of the [U, 3] buffer."""
-        vals = (self._loss_all / max(self._since, 1)).tolist()
+    def losses(self, lag: bool = False):
+        """Per-unit mean (rec, task, round, total) since the last call: ONE device->host copy of the [U, 3] buffer.
+
+        `lag=True`: the copy goes to pinned host memory without blocking and the call returns the values of the PREVIOUS
+        call's window (empty dict the first time), so a loop that logs every step never drains the device queue: the
+        host enqueues step k+1 while step k runs (a blocking read left the GPU idle for the ~0.3 ms of launch work at
+        the start of every step)."""
+        if not lag:
+            vals = (self._loss_all / max(self._since, 1)).tolist()
+            self._loss_all.zero_()
+            self._since = 0
+            return self._loss_dict(vals)
+        if self._loss_host is None:
+            self._loss_host = [torch.empty(self._loss_all.shape, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_ev, self._loss_k = [None, None], 0
+        k = self._loss_k
+        snap = self._loss_all / max(self._since, 1)
+        self._loss_host[k % 2].copy_(snap, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._loss_ev[k % 2] = ev
         self._loss_all.zero_()
+        self._since = 0
+        self._loss_k = k + 1
+        if k == 0:
+            return {}
+        self._loss_ev[(k - 1) % 2].synchronize()
+        return self._loss_dict(self._loss_host[(k - 1) % 2].tolist())
+
+    def _loss_dict(self, vals):
         out = {}
         for (n, _), (rec, task, rnd) in zip(self.units, vals):
             t = self.trainers[n]
             if getattr(t, "_same", False):
                 task = rec
             t.last = out[n] = dict(rec=rec, task=task, round=rnd, total=rec + task + rnd)
-        self._since = 0
         return out
 
     def finish(self):

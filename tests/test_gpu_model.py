@@ -598,3 +598,24 @@ def test_lu_quantize_entry_point(dev, tmp_path):
     assert abs(rep["int8"]["psnr"] - rep["fp32"]["psnr"]) < 1.0 and rep["int8"]["bpp"] > 0
     sd = torch.load(p, weights_only=False)
     assert any(v.dtype == torch.uint8 for v in sd.values())
+
+
+def test_lagged_loss_readback_returns_the_previous_window(dev):
+    """CalibrationSession.losses(lag=True): non-blocking copy into pinned memory, values of the previous call's window."""
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+
+    def make():
+        _, pqm, Q, cali = _calib_pair(dev, "mbt2018-mean", dict(N=16, M=24), 1.2)
+        return CalibrationSession(pqm, cali.to(dev), batch_size=2, iters=20)
+    a, b = make(), make()
+    ref, got = [], []
+    for _ in range(5):
+        a.sweep()
+        ref.append(a.losses())
+        b.sweep()
+        got.append(b.losses(lag=True))
+    assert got[0] == {}
+    for k in range(1, 5):
+        for n in ref[k - 1]:
+            assert got[k][n]["rec"] == pytest.approx(ref[k - 1][n]["rec"], rel=1e-6, abs=1e-12), (k, n)
+            assert got[k][n]["round"] == pytest.approx(ref[k - 1][n]["round"], rel=1e-6, abs=1e-12), (k, n)
