@@ -618,5 +618,6 @@ def test_lagged_loss_readback_returns_the_previous_window(dev):
     assert got[0] == {}
     for k in range(1, 5):
         for n in ref[k - 1]:
-            assert got[k][n]["rec"] == pytest.approx(ref[k - 1][n]["rec"], rel=1e-6, abs=1e-12), (k, n)
-            assert got[k][n]["round"] == pytest.approx(ref[k - 1][n]["round"], rel=1e-6, abs=1e-12), (k, n)
+            # (block partial sums meet in fp32 atomics: the order, hence the last bits, can differ between two runs)
+            assert got[k][n]["rec"] == pytest.approx(ref[k - 1][n]["rec"], rel=1e-4, abs=1e-9), (k, n)
+            assert got[k][n]["round"] == pytest.approx(ref[k - 1][n]["round"], rel=1e-4, abs=1e-9), (k, n)
