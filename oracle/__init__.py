@@ -18,6 +18,15 @@ Pinning status
   `light-uniform-PTQ/quant_int/quantizer.py`, imported from /root/reference by
   `oracle/make_golden.py` (they depend on torch only); the comparison is bit-exact and
   the resulting vectors are committed under `tests/golden/`.
+* wrappers and the calibration loop (`oracle.quant_wrap`, `oracle.calib`): PINNED against the
+  reference's own `task-oriented-PTQ/quantization` and `light-uniform-PTQ/quant_int` packages.
+  `oracle/_ref_shim.py` registers stand-ins for compressai / timm / pytorch_msssim (mapped to
+  `oracle.codec`) in `sys.modules`, imports the UNMODIFIED reference files and
+  `oracle/make_golden.py::wrap_vectors` asserts bit-exact agreement for the `QuantModel` rewrite,
+  FP / W8 / W8A8 / W4-with-8-bit-head forwards of the three codecs (per wrapped module),
+  `save_inp_oup_data`, `LossFunction`, `layer_reconstruction` / `block_reconstruction` walks
+  (alpha and hardened weights of every unit) and LU's `QuantModel`; the reference's outputs are
+  committed as `tests/golden/wrap_ref.pt`.
 * compressai pieces (`oracle.codec`): the reference ships no tests or golden
   vectors for them and compressai is not installable here, so they
   are restated from the published 1.2.4 semantics and checked against closed forms

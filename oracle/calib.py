@@ -4,6 +4,9 @@ Follows /root/reference/task-oriented-PTQ/quantization/{layer_opt.py,block_opt.p
 `recon_model` walk of main2.py:227-264.  The only deviation: the per-iteration randomness
 (`torch.randperm` batch pick and the QDrop mask, layer_opt.py:289-292) is drawn from an explicit
 `DrawPlan` so the CUDA path can replay the identical draws.
+PINNED: `oracle/make_golden.py::wrap_vectors` runs the reference's own loops on CPU (through `oracle/_ref_shim.py`, which
+serves their `torch.randperm` / `torch.rand_like` calls from the same `DrawPlan`) and asserts bit-exact alpha and
+hardened weights for every unit of a mbt2018-mean walk and of the first 14 cheng2020-attn units.
 """
 import torch
 import torch.nn as nn

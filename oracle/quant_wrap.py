@@ -1,9 +1,10 @@
 """Oracle restatement of the reference's quant-module wrappers (test infrastructure, CPU fp32).
 
 TO = /root/reference/task-oriented-PTQ/quantization, LU = /root/reference/light-uniform-PTQ/quant_int.
-These files cannot be imported from /root/reference (they import compressai/timm), so they are
-restated here over `oracle.codec`; the quantizer arithmetic they call is the pinned
-`oracle.quantizers`.
+The reference files import compressai/timm, so they are restated here over `oracle.codec`; the quantizer arithmetic
+they call is the pinned `oracle.quantizers`.  PINNED: `oracle/make_golden.py::wrap_vectors` imports the unmodified
+reference packages through `oracle/_ref_shim.py` and asserts that every class below reproduces them bit for bit
+(`tests/golden/wrap_ref.pt`, `tests/test_oracle_wrap_golden.py`).
 """
 import torch
 import torch.nn as nn

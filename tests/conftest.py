@@ -25,6 +25,12 @@ def golden_c():
 
 
 @pytest.fixture(scope="session")
+def golden_w():
+    """Outputs of the reference's OWN quantization / quant_int packages (oracle/make_golden.py::wrap_vectors)."""
+    return torch.load(os.path.join(GOLDEN, "wrap_ref.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
 def dev():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
