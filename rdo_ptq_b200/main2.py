@@ -93,7 +93,9 @@ def recon_model(qnn: QuantModel, module: nn.Module = None, _counter=None, _prefi
             else:
                 logging.info('Reconstruction for {} {}'.format(kind, name))
                 fn = layer_reconstruction if isinstance(m, QuantModule) else block_reconstruction
-                traces[full] = fn(qnn, m, name, unit_id=counter[0], **kwargs)
+                # the unit's path inside the codec ("g_a.2"): what the R + lambda*D / coder task criteria continue from
+                path = full[len("model."):] if full.startswith("model.") else full
+                traces[full] = fn(qnn, m, name, unit_id=counter[0], unit_path=path, **kwargs)
             counter[0] += 1
         else:
             traces.update(recon_model(qnn, m, counter, full, **kwargs))
@@ -142,7 +144,8 @@ def optimize_model(args, model=None, cali_data=None, test_images=None, device="c
         test('w_nearest', qnn)
     kwargs = dict(cali_data=cali_data, batch_size=args.batch_size, iters=args.iters_w, weight=args.weight,
                   input_prob=args.input_prob, lr=args.lr, asym=True, b_range=(args.b_start, args.b_end),
-                  warmup=args.warmup, act_quant=args.act_quant, opt_mode='mse', config=None, args=args, graph=graph)
+                  warmup=args.warmup, act_quant=args.act_quant, opt_mode='mse', config=None, args=args, graph=graph,
+                  lmbda=args.lmbda)
     if plan is not None:
         kwargs['plan'] = plan
     qnn.set_quant_state(weight_quant=True, act_quant=args.act_quant)

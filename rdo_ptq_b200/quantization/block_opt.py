@@ -6,7 +6,7 @@ import time
 
 import torch
 
-from .layer_opt import find_unquantized_module, _task_p
+from .layer_opt import find_unquantized_module, _task_p, _rd_task
 from .quant_block import BaseQuantBlock
 from .quant_layer import QuantModule
 from .quant_model import QuantModel
@@ -30,7 +30,10 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, block_name: s
                          asym: bool = False, include_act_func: bool = True, b_range: tuple = (20, 2),
                          warmup: float = 0.0, input_prob: float = 1.0, act_quant: bool = False, lr: float = 4e-5,
                          p: float = 2.0, config=None, args=None, plan: DrawPlan = None, unit_id: int = 0, trace=None,
-                         log_every: int = 500, graph: bool = True, process_group=None):
+                         log_every: int = 500, graph: bool = True, process_group=None, task: str = None,
+                         lmbda: float = None, unit_path: str = None):
+    """Same arguments as the reference; `plan` / `unit_id` / `trace` / `task` / `lmbda` / `unit_path` are additive, as in
+    `layer_reconstruction`."""
     if opt_mode != 'mse':
         raise NotImplementedError("only opt_mode='mse' is reachable in the reference (main2.py:225)")
     t0 = time.time()
@@ -47,7 +50,9 @@ def block_reconstruction(model: QuantModel, block: BaseQuantBlock, block_name: s
     org_act_func = None
     if not include_act_func:
         org_act_func, block.activation_function = block.activation_function, StraightThrough()
-    trainer = UnitTrainer(block, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group)
+    rd = _rd_task(model, unit_path, cali_data, args, task, lmbda, cached_outs)
+    trainer = UnitTrainer(block, iters, weight, b_range, warmup, p, _task_p(args), process_group=process_group,
+                          rd_task=rd)
     losses = run_reconstruction(trainer, cached_inps, cached_outs, batch_size, input_prob, unit_id, plan, trace=trace,
                                 log_every=log_every, graph=graph)
     if org_act_func is not None:

@@ -41,6 +41,12 @@ def _rd_task(model, unit_path, cali_data, args, task, lmbda, fp_unit_out=None):
     (recon.CoderTask)."""
     if task is None and args is not None and getattr(args, "task_loss", None) == "rd":
         task = "rd"
+    if task in ("rd", "coder") and unit_path is not None:
+        coder, _, rest = unit_path.partition(".")
+        if coder not in ("g_a", "h_a", "h_s", "g_s") or not rest.isdigit():
+            # a unit nested inside a composite child (e.g. the convolutions of Cheng2020's attention blocks): the codec's
+            # forward cannot be continued from its output by position
+            raise NotImplementedError(f"task={task!r}: {unit_path!r} is not a direct child of g_a / h_a / h_s / g_s")
     if task == "coder":
         if unit_path is None:
             raise ValueError("task='coder' needs unit_path (the unit's path inside the codec, e.g. 'g_a.2')")

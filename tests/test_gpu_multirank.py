@@ -1,0 +1,94 @@
+"""GPU, world size 2 (NCCL): the data-parallel calibration step on hardware.  Skipped on a single-GPU box
+(run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multirank.py -m gpu`).
+
+SURVEY 8(e): each rank draws its sub-batch from its own shard of the calibration pool, the unit's dL/dWq bucket is
+all-reduced (sum) once per iteration and every rank applies the identical fused Adam step with grad_scale = 1/world, so
+  * alpha (and the Adam moments) stay BIT-identical across ranks, and
+  * 2 ranks x batch 4 take the same steps as 1 rank x batch 8 on the union of the shards (lp_loss is a mean over
+    samples, quantizer.py:76), up to fp32 summation order."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+WQ = dict(n_bits=4, channel_wise=True, scale_method="max")
+AQ = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+ITERS, PATHS = 10, ("g_a.2", "g_a.1", "g_s.0")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(dev, cali, batch, process_group=None):
+    """10 graph-replayed AdaRound iterations on three units (conv, GDN, transposed conv); returns their alphas."""
+    from rdo_ptq_b200 import codec, synth, quantization as Q
+    torch.manual_seed(1005)
+    m = codec.ARCHS["mbt2018-mean"](N=16, M=24).eval()
+    synth.init_weights(m, gain=1.2)
+    m.to(dev)
+    q = Q.QuantModel(m, WQ, AQ).eval()
+    q.set_quant_state(True, False)
+    with torch.no_grad():
+        q(synth.calibration_patches(2, 64).to(dev))            # identical scale init on every rank
+
+    class Args:
+        task_loss = 2.0
+    out = {}
+    for uid, path in enumerate(PATHS):
+        sub, idx = path.split(".")
+        layer = getattr(q.model, sub)[int(idx)]
+        Q.layer_reconstruction(q, layer, idx, cali, batch_size=batch, iters=ITERS, weight=0.01, b_range=(20, 2),
+                               warmup=0.2, input_prob=1.0, asym=True, act_quant=False, opt_mode="mse", args=Args(),
+                               unit_id=uid, process_group=process_group)
+        out[path] = layer.weight_quantizer.alpha.data.clone()
+    return out
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rdo_ptq_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pool = synth.calibration_patches(8, 64)
+    alphas = _run(dev, pool[rank::world].contiguous().to(dev), 8 // world)
+    same = True
+    for path, a in alphas.items():
+        parts = [torch.empty_like(a) for _ in range(world)]
+        dist.all_gather(parts, a)
+        same &= all(torch.equal(parts[0], p) for p in parts[1:])
+    if rank == 0:
+        q.put((same, {k: v.cpu() for k, v in alphas.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_keep_alpha_bit_identical_and_match_one_rank():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from rdo_ptq_b200 import synth
+    dev = torch.device("cuda", 0)
+    ref = {k: v.cpu() for k, v in _run(dev, synth.calibration_patches(8, 64).to(dev), 8).items()}
+    torch.cuda.synchronize()
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    same, got = q.get(timeout=600)
+    [p.join(timeout=120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert same, "alpha differs between the ranks after 10 all-reduced steps"
+    for path in PATHS:
+        d = (got[path] - ref[path]).abs()
+        moved = (ref[path] - got[path]).abs().max().item()
+        print(f"{path}: max |alpha(2x4) - alpha(1x8)| = {moved:.2e}, mean {d.mean().item():.2e}")
+        # Adam divides by sqrt(v): an element whose gradient is float noise can step the other way; all others agree
+        assert d.mean().item() < 2e-5 and (d > 1e-3).float().mean().item() < 1e-3, path

@@ -3,6 +3,8 @@ step-size gradient (b200lic_lsq_delta_grad), the differentiable R + lambda*D los
 of the calibration loop, each against torch autograd of the CPU oracle on the same seeded inputs.
 
 Tolerance: 1e-4 relative (norm) on floating-point gradients, stated per assertion."""
+import math
+
 import pytest
 import torch
 
@@ -288,3 +290,24 @@ def test_layer_reconstruction_with_coder_task(dev, layer_path):
     assert abs(plosses[0]["total"] - olosses[0]) < 1e-3 * abs(olosses[0]) + 1e-7, (plosses[0], olosses[0])
     a_ref, a_gpu = olayer.weight_quantizer.alpha.data, player.weight_quantizer.alpha.data.cpu()
     assert (a_ref - a_gpu)[inner].abs().max().item() < 5e-3
+
+
+def test_main2_entry_point_with_rd_task_loss(dev):
+    """`main2.py --task_loss rd` end to end: recon_model hands every unit its path inside the codec and
+    --lmbda, so each of the 20 layer problems runs with task = R + lambda*D; a unit nested inside a composite child
+    (no positional tail) raises instead of silently falling back to the lp task."""
+    from rdo_ptq_b200 import main2
+    from rdo_ptq_b200.quantization import layer_opt
+    args = main2.parse_args(["--arch", "mbt2018-mean", "--N", "8", "--M", "12", "--n_bits_w", "4", "--channel_wise",
+                             "--batch_size", "2", "--num_samples", "4", "--iters_w", "6", "--patch", "64",
+                             "--task_loss", "rd", "--lmbda", "0.01", "--test_hw", "64x96", "--n_test", "1"])
+    assert args.task_loss == "rd"
+    qnn, rep = main2.optimize_model(args, device=dev)
+    assert len(rep["losses"]) == 20
+    for name, recs in rep["losses"].items():
+        assert recs and recs[-1]["task"] > 0 and math.isfinite(recs[-1]["total"]), name
+        # the task term is a rate-distortion value (bits per pixel + lambda * 255^2 * MSE), not a copy of rec
+        assert recs[-1]["task"] != recs[-1]["rec"], name
+    assert math.isfinite(rep["wa_opt"]["bpp"])
+    with pytest.raises(NotImplementedError):
+        layer_opt._rd_task(qnn, "g_a.3.conv_a.0", None, args, None, 0.01)

@@ -1,0 +1,241 @@
+"""GPU parity against (1) the REFERENCE's own outputs (tests/golden/wrap_ref.pt, produced by running the unmodified
+task-oriented-PTQ/quantization and light-uniform-PTQ/quant_int packages, oracle/make_golden.py::wrap_vectors) and
+(2) the pinned oracle at BASELINE.json's full sizes (N=192 / M=320 codecs, 768x512 and padded-2K images).
+
+Bars (north_star): integer weight codes bit-exact; per-layer outputs <= 1e-4 relative on the same inputs; end-to-end
+bpp within 1e-3 and PSNR within 0.01 dB.  The W8A8 end-to-end bars are asserted under the exact-fp32 SIMT engine; under
+the tcgen05 split-bf16 engine (conv outputs differ from fp32 by ~1e-6 relative) the share of activation codes that
+land on the neighbouring level is asserted and recorded, and the end-to-end metrics are recorded
+(gpurun_out/parity_full_size.jsonl -> profiles/)."""
+import copy
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import calib as ocalib, make_golden as MG, parity as P
+from rdo_ptq_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(row):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_full_size.jsonl"), "a") as f:
+        f.write(json.dumps(row) + "\n")
+
+
+def _product_model(case, dev):
+    from rdo_ptq_b200 import codec
+    fp, x = MG.build_fp_model(case["arch"], case["kw"], case["gain"])
+    pm = codec.ARCHS[case["arch"]](**case["kw"]).eval()
+    pm.load_state_dict(fp.state_dict())
+    pm.to(dev)
+    with torch.no_grad():
+        pm(x.to(dev))                                           # bakes the MaskedConv2d mask like the reference run (Q5)
+    return pm, x
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (1) the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arch", ["mbt2018-mean", "bmshj2018-hyperprior", "cheng2020-attn"])
+@pytest.mark.parametrize("tag", ["w8", "w4"])
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+def test_quant_model_forward_against_reference_outputs(dev, golden_w, arch, tag, engine):
+    from rdo_ptq_b200 import ops, quantization as Q, evaluate as E
+    case = golden_w[f"model/{arch}/{tag}"]
+    prev = ops.DEFAULT_ENGINE
+    ops.set_default_engine(engine)
+    try:
+        pm, x = _product_model(case, dev)
+        q = Q.QuantModel(pm, case["wq"], MG.AQ8, is_cheng=case["is_cheng"]).eval()
+        kinds = (Q.QuantModule, Q.BaseQuantBlock)
+        if case["head8"]:
+            q.set_first_last_layer_to_8bit()
+        q.disable_network_output_quantization()
+        assert MG._structure(q, *kinds) == case["structure"]          # same names, classes, absorbed activations, flags
+        assert [(n, m.weight_quantizer.n_bits, m.act_quantizer.n_bits, m.disable_act_quant)
+                for n, m in q.named_modules() if isinstance(m, Q.QuantModule)] == case["n_bits"]
+        xg = x.to(dev)
+        for state in ("fp", "w", "wa"):
+            if state == "wa":
+                MG._mark_trained(q, kinds)
+            q.set_quant_state(state != "fp", state == "wa")
+            if state == "wa":
+                MG._output_layer(q, case["is_cheng"]).set_quant_state(True, False)
+            out, layers = MG._layer_outputs(q, xg, kinds)
+            ref = case[state]
+            d_bpp = E.compute_bpp(out) - ref["bpp"]
+            d_psnr = E.compute_psnr(out["x_hat"], xg, clamp=True) - ref["psnr"]
+            if state != "wa":
+                # no rounding cascade without activation quantisers: every module output of the end-to-end run
+                assert P.rel_err(out["x_hat"], ref["x_hat"]) < 2e-4, (state, P.rel_err(out["x_hat"], ref["x_hat"]))
+                for k, v in ref["layers"].items():
+                    assert P.rel_err(layers[k], v) < 2e-4, (state, k, P.rel_err(layers[k], v))
+                assert abs(d_bpp) < 1e-3 and abs(d_psnr) < 0.01, (state, d_bpp, d_psnr)
+            elif engine == "simt":
+                assert abs(d_bpp) < 1e-3 and abs(d_psnr) < 0.01, (state, d_bpp, d_psnr)
+            else:
+                assert abs(d_bpp) < 0.01 * ref["bpp"] + 1e-3 and abs(d_psnr) < 0.1, (state, d_bpp, d_psnr)
+        for n, m in q.named_modules():
+            if isinstance(m, Q.QuantModule) and m.weight is not None:
+                assert torch.equal(m.weight_quantizer.codes(m.weight).cpu(), case["codes"][n]), n
+    finally:
+        ops.DEFAULT_ENGINE = prev
+
+
+def test_lu_model_against_reference_outputs(dev, golden_w):
+    from rdo_ptq_b200 import quant_int as LU, evaluate as E
+    g = golden_w["lu_model"]
+    pm, x = _product_model(g, dev)
+    q = LU.QuantModel(pm, MG.WQ8, g["aq"]).eval()
+    q.set_quant_state(True, True)
+    q.disable_network_output_quantization()
+    with torch.no_grad():
+        out = q(x.to(dev))
+    mods = {n: m for n, m in q.named_modules() if isinstance(m, LU.QuantModule)}
+    assert list(mods) == list(g["weights_u8"])
+    for n, m in mods.items():
+        assert m.weight.dtype == torch.uint8 and torch.equal(m.weight.data.cpu(), g["weights_u8"][n]), n
+    # Q8.8 grid: outputs agree except where a pre-quant value sits on a rounding boundary (one grid step = 1/256)
+    d = (out["x_hat"].cpu() - g["x_hat"]).abs()
+    assert (d > 1e-4).float().mean().item() < 0.02 and d.max().item() < 0.05
+    assert abs(E.compute_bpp(out) - g["bpp"]) < 1e-3 + 0.01 * g["bpp"]
+    assert abs(E.compute_psnr(out["x_hat"], x.to(dev), clamp=True) - g["psnr"]) < 0.1
+    qc = LU.QuantCodingModel(_product_model(g, dev)[0], MG.WQ8, g["aq"])
+    assert [n for n, m in qc.named_modules() if isinstance(m, LU.QuantModule)] == g["coding_modules"]
+
+
+class _Replay:
+    """The oracle's CPU-drawn (idx, QDrop mask) pairs for the CUDA loop: the draws the reference's loop consumed."""
+
+    def __init__(self, seed):
+        self.cpu = ocalib.DrawPlan(seed)
+
+    def draw(self, unit_id, it, n, bs, shape, prob, device):
+        idx, keep = self.cpu.draw(unit_id, it, n, bs, shape, prob)
+        return idx.to(device), (None if keep is None else keep.to(device)), 0
+
+
+@pytest.mark.parametrize("arch", ["mbt2018-mean", "cheng2020-attn"])
+def test_calibration_walk_against_reference_outputs(dev, golden_w, arch):
+    """layer_reconstruction / block_reconstruction in main2.py's walk order, 24 iterations per unit with the draws the
+    reference's loop consumed: alpha and the hardened weights of every unit against the REFERENCE's."""
+    from rdo_ptq_b200 import quantization as Q
+    walk = golden_w[f"walk/{arch}"]
+    c = walk["calib"]
+    pm, x = _product_model(walk, dev)
+    cali = synth.calibration_patches(c["n_samples"], c["patch"])
+    assert cali.double().sum() == walk["cali_sum"]
+    cali = cali.to(dev)
+    q = Q.QuantModel(pm, walk["wq"], MG.AQ8, is_cheng=walk["is_cheng"]).eval()
+    q.set_first_last_layer_to_8bit()
+    q.disable_network_output_quantization()
+    q.set_quant_state(True, False)
+    with torch.no_grad():
+        q(cali[:c["batch_size"]])
+    MG._output_layer(q, walk["is_cheng"]).set_quant_state(True, False)
+    units = []
+
+    def collect(module, prefix):
+        for name, m in module.named_children():
+            full = f"{prefix}.{name}" if prefix else name
+            if isinstance(m, (Q.QuantModule, Q.BaseQuantBlock)):
+                units.append((full, name, m))
+            else:
+                collect(m, full)
+    collect(q, "")
+    assert [u[0] for u in units] == walk["units"]
+
+    class Args:
+        task_loss, lmbda, arch = 2.0, 0.01, "Cheng2020" if walk["is_cheng"] else "Minnen2018"
+    kw = dict(batch_size=c["batch_size"], iters=c["iters"], weight=c["weight"], b_range=c["b_range"], warmup=c["warmup"],
+              input_prob=c["input_prob"], asym=True, act_quant=False, opt_mode="mse", args=Args())
+    plan = _Replay(walk["seed"])
+    diff = tot = seen = 0
+    worst_alpha = 0.0
+    for uid, (full, name, m) in enumerate(units):
+        if walk["limit"] is not None and uid >= walk["limit"]:
+            break
+        if full in walk["caches"]:
+            (qi, fi), fo = Q.save_inp_oup_data(q, m, cali, True, False, batch_size=1, input_prob=True)
+            ref = walk["caches"][full]
+            for a, b in ((qi, ref["quant_in"]), (fi, ref["fp_in"]), (fo, ref["fp_out"])):
+                assert P.rel_err(a, b) < 2e-4, (full, P.rel_err(a, b))
+        fn = Q.block_reconstruction if isinstance(m, Q.BaseQuantBlock) else Q.layer_reconstruction
+        fn(q, m, name, cali, plan=plan, unit_id=uid, **kw)
+        for n, mm in m.named_modules():
+            if isinstance(mm, Q.QuantModule) and mm.org_weight is not None:
+                key = f"{full}.{n}" if n else full
+                a_ref = walk["alpha"][key]
+                a = mm.weight_quantizer.alpha.data.cpu()
+                # elements that start exactly on the clamp boundary of h(alpha) have a coin-flip gradient gate in the
+                # reference itself (rest == 0); parity is defined on the interior
+                inner = a_ref.abs() < 8.0
+                worst_alpha = max(worst_alpha, (a - a_ref)[inner].abs().max().item())
+                hard = mm.weight_quantizer(mm.weight).detach().cpu()
+                diff += (hard != walk["hard"][key]).sum().item()
+                tot += hard.numel()
+                seen += 1
+                assert mm.trained and not mm.weight_quantizer.soft_targets
+    assert seen == len(walk["alpha"])
+    print(f"walk {arch}: {diff}/{tot} hardened weights differ from the reference's, worst |d alpha| {worst_alpha:.2e}")
+    _record(dict(test="walk_vs_reference", arch=arch, hardened_differ=diff, hardened_total=tot, worst_d_alpha=worst_alpha))
+    assert worst_alpha < 5e-3                      # 24 Adam steps of 1e-3: well inside one step
+    assert diff / tot < 2e-3                       # only decisions whose alpha sits within float noise of 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (2) BASELINE sizes against the pinned oracle
+# ---------------------------------------------------------------------------------------------------------------------
+FULL = [
+    # (id, arch, kw, gain, hw, wq / aq overrides, lu, follow_bits)
+    ("mbt2018-mean N192 768x512 W8A8", "mbt2018-mean", dict(N=192, M=320), 1.2, (512, 768), None, None, False, False),
+    ("bmshj2018 N128 768x512 LU W8+Q8.8", "bmshj2018-hyperprior", dict(N=128, M=192), 1.2, (512, 768), None,
+     dict(n_bits=8, channel_wise=False, scale_method="max", leaf_param=True), True, False),
+    ("cheng2020-attn N192 768x512 W8A8", "cheng2020-attn", dict(N=192), 0.6, (512, 768), None, None, False, False),
+    ("cheng2020-attn N192 768x512 W10A10", "cheng2020-attn", dict(N=192), 0.6, (512, 768),
+     dict(n_bits=10, channel_wise=True, scale_method="max"),
+     dict(n_bits=10, channel_wise=True, scale_method="max", leaf_param=False), False, True),
+    ("mbt2018-mean N192 2K W8A8", "mbt2018-mean", dict(N=192, M=320), 1.2, (1365, 2048), None, None, False, False),
+]
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c[0] for c in FULL])
+def test_full_size_parity_tensor_core_engine(dev, case):
+    """BASELINE configs 1-5 at their stated sizes on the tcgen05 engine: codes bit-exact, every layer within 1e-4 on
+    the oracle's inputs, W-only end-to-end within the strict bars, A8 flip rate small; W+A end-to-end recorded."""
+    name, arch, kw, gain, hw, wq, aq, lu, follow = case
+    r = P.compare_forward(arch, kw, gain, hw, dev, wq=wq, aq=aq, lu=lu, follow_bits=follow, engine="auto")
+    r["case"] = name
+    _record(r)
+    print(json.dumps(r))
+    assert r["codes_equal"]
+    if lu:
+        assert r["q88_off_grid_rate"] < 1e-3
+        assert abs(r["d_bpp_wa"]) < 0.01 * r["bpp_ref"] + 1e-3 and abs(r["d_psnr_wa"]) < 0.1
+        return
+    assert r["worst_layer_rel_err"] < 1e-4, (r["worst_layer"], r["worst_layer_rel_err"])
+    assert abs(r["d_bpp_w"]) < 1e-3 and abs(r["d_psnr_w"]) < 0.01
+    assert r["a8_flip_rate"] < 1e-4
+    assert abs(r["d_bpp_wa"]) < 0.01 * r["bpp_ref_wa"] + 1e-3 and abs(r["d_psnr_wa"]) < 0.1
+
+
+@pytest.mark.parametrize("case", [FULL[0], FULL[2]], ids=[FULL[0][0], FULL[2][0]])
+def test_full_size_w8a8_strict_bars_exact_engine(dev, case):
+    """The same comparison on the exact-fp32 SIMT engine.  If the W+A end-to-end deltas of the tensor-core engine come
+    from activation codes flipping at rounding boundaries under ~1e-6 conv differences (and cascading through the
+    dynamic ranges), the engine whose conv outputs match fp32 to the last bits must meet the strict bars: 1e-3 bpp,
+    0.01 dB."""
+    name, arch, kw, gain, hw, wq, aq, lu, follow = case
+    r = P.compare_forward(arch, kw, gain, hw, dev, wq=wq, aq=aq, lu=lu, follow_bits=follow, engine="simt",
+                          layer_checks=False)
+    r["case"] = name + " (SIMT engine)"
+    _record(r)
+    print(json.dumps(r))
+    assert r["codes_equal"]
+    assert abs(r["d_bpp_w"]) < 1e-3 and abs(r["d_psnr_w"]) < 0.01
+    assert abs(r["d_bpp_wa"]) < 1e-3 and abs(r["d_psnr_wa"]) < 0.01, (r["d_bpp_wa"], r["d_psnr_wa"])
