@@ -147,6 +147,11 @@ B200LIC_API int b200lic_actq_stats_init(float* minmax, int C, b200lic_stream_t s
 B200LIC_API int b200lic_actq_stats(const float* x, int N, int C, int HW, float* minmax, b200lic_stream_t stream);
 B200LIC_API int b200lic_actq_apply(const float* x, const float* minmax, int N, int C, int HW, int n_bits, float* out,
                        float* codes, b200lic_stream_t stream);
+/* b200lic_actq_apply fused with the staging of the NEXT layer's tensor-core operand: the quantised activation (same codes
+ * as b200lic_actq_apply, bit for bit) is written as the split-bf16 NHWC operand [N,HW,cpad] (x*x when square != 0, for a
+ * GDN consumer) into the slot b200lic_conv_x_slot reports; `out` (may be NULL) also receives it as fp32 NCHW. */
+B200LIC_API int b200lic_actq_apply_stage(const float* x, const float* minmax, int N, int C, int HW, int n_bits, int square,
+                             void* x_hi, void* x_lo, int cpad, float* out, b200lic_stream_t stream);
 /* The three calls above in one launch (no minmax buffer): one thread-block cluster per channel keeps the channel's
  * elements in (distributed) shared memory between the min/max reduction and the quantisation, so the activation is read
  * from HBM once.  Bit-identical to stats_init + stats + apply. */
@@ -356,6 +361,79 @@ B200LIC_API int b200lic_lp_loss_fwd_bwd_sched(const float* pred, const float* tg
                                   int table_rows, size_t rows, size_t row_elems, int units, int unit,
                                   const b200lic_calib_sched* sched, float p, float scale, float grad_scale,
                                   float* loss, float* d_pred, b200lic_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prepared operands: the fused form of the reference's QuantModule.forward (TO quant_layer.py:107-134: weight
+ * quantiser -> conv -> activation) and of one AdaRound iteration (layer_opt.py:287-309), in which the kernels that
+ * already hold the values in registers emit the tensor-core operands directly, so the two staging kernels (NHWC
+ * split of the activation, weight pack) in front of every GEMM disappear:
+ *   batch pick + QDrop mix (layer_opt.py:289-292)            -> activation operand   b200lic_stage_mix_sched
+ *   weight quantiser (quantizer.py:175-177 / :437-449)        -> weight operand       b200lic_quant_pack_weights
+ *   lp_loss value + gradient (quantizer.py:71-79)             -> dY operand of wgrad  b200lic_lp_loss_stage_sched
+ *   split-K sum of dW -> STE masks + regulariser + Adam        (layer_opt.py:160-165,298-307) b200lic_conv_wgrad_adam_sched
+ * A frozen layer's weight operand is built once and kept by the caller (the reference re-quantises every weight on
+ * every forward).  Tensor-core engine, generic (tap-by-tap) path only: for the folded-tap 3-channel layers and the
+ * SIMT engine the size / slot queries return 0 / NULL and the compute calls B200LIC_ERR_UNSUPPORTED -- use the plain
+ * entry points there.
+ * ---------------------------------------------------------------------------------------------- */
+/* Bytes of the packed weight operand of a forward op (B200LIC_OP_CONV_FWD / _DECONV_FWD); depends on the layer only
+ * (Cin, Cout, KH, KW, stride), not on N / H / W.  `packed` buffers must be 128-byte aligned. */
+B200LIC_API size_t b200lic_conv_packed_weight_bytes(const b200lic_conv_desc* d, int op);
+/* fp32 weight ([Cout,Cin,KH,KW], or [Cin,Cout,KH,KW] for the transposed op) -> packed operand. */
+B200LIC_API int b200lic_conv_pack_weights(const b200lic_conv_desc* d, int op, const float* w, void* packed,
+                              size_t packed_bytes, b200lic_stream_t stream);
+/* Weight quantiser fused with the packing.  alpha == NULL: nearest rounding (b200lic_wq_fake_quant); alpha given:
+ * AdaRound with soft / hard targets (b200lic_adaround_fwd).  The channel view (outer, ch, inner) is the one of K6/K7.
+ * integer_mode != 0 packs n = code - zero_point (the operand of the two-pass forward: pass delta per output channel as
+ * w_scale to b200lic_conv_fwd_packed; needs n_levels <= 256).  w_q (may be NULL) also receives the fp32 weight that was
+ * packed (needed when a dgrad will re-pack it transposed).  Values are bit-identical to the un-fused kernels. */
+B200LIC_API int b200lic_quant_pack_weights(const b200lic_conv_desc* d, int op, const float* w, const float* alpha,
+                               const float* delta, const float* zero_point, int outer, int ch, int inner, int n_levels,
+                               int soft, int integer_mode, void* packed, size_t packed_bytes, float* w_q,
+                               b200lic_stream_t stream);
+/* b200lic_conv_fwd / b200lic_deconv_fwd / b200lic_conv_fwd_wq with a prepared weight operand.  x == NULL: the
+ * activation operand is already staged in the workspace slot b200lic_conv_x_slot reports.  w_scale (may be NULL)
+ * selects the two-pass integer-weight form. */
+B200LIC_API int b200lic_conv_fwd_packed(const b200lic_conv_desc* d, int op, const float* x, const void* packed_w,
+                            const float* w_scale, const float* bias, const float* gdn_x, float* norm_out, float* y,
+                            void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
+/* Where a forward workspace expects the staged activation operand ([N,H,W,cpad] bf16 hi and lo; x*x for in_square),
+ * and where a weight-gradient workspace (B200LIC_OP_CONV_WGRAD / _DECONV_WGRAD) expects the staged dY
+ * ([N,Ho,Wo,cpad]).  NULL / 0 when the shape stages differently. */
+B200LIC_API int b200lic_conv_x_slot(const b200lic_conv_desc* d, int op, void* workspace, size_t workspace_bytes,
+                        void** x_hi, void** x_lo, int* cpad);
+B200LIC_API int b200lic_conv_dy_slot(const b200lic_conv_desc* d, int op, void* workspace, size_t workspace_bytes,
+                         void** dy_hi, void** dy_lo, int* cpad);
+/* b200lic_gather_mix_sched whose result leaves as the staged activation operand (split-bf16 NHWC, channels zero-padded
+ * to cpad; x*x when square != 0) instead of fp32 NCHW; `out` (may be NULL) additionally receives the fp32 batch.  Same
+ * picks and QDrop draws as b200lic_gather_mix_sched.  sched == NULL: identity rows, seed_base as the seed. */
+B200LIC_API int b200lic_stage_mix_sched(const float* q, const float* fp, const long long* idx_table, int table_rows, int rows,
+                            int C, int HW, float prob, unsigned long long seed_base, int units, int unit,
+                            const b200lic_calib_sched* sched, int square, void* x_hi, void* x_lo, int cpad, float* out,
+                            b200lic_stream_t stream);
+/* b200lic_lp_loss_fwd_bwd_sched whose gradient leaves as the staged dY operand of the weight-gradient GEMM; d_pred (may
+ * be NULL) additionally receives it as fp32 NCHW.  idx_table == NULL: tgt_cache is the target batch itself.  `act` is
+ * the activation fused into the layer that produced `pred`: its derivative (b200lic_act_bwd, on the activation output)
+ * is applied to the gradient, which is then the one the weight gradient needs. */
+B200LIC_API int b200lic_lp_loss_stage_sched(const float* pred, const float* tgt_cache, const long long* idx_table,
+                                int table_rows, int rows, int C, int HW, int units, int unit,
+                                const b200lic_calib_sched* sched, float p, float scale, float grad_scale, int act,
+                                float act_slope, float* loss, void* dy_hi, void* dy_lo, int cpad, float* d_pred,
+                                b200lic_stream_t stream);
+/* b200lic_conv_wgrad_staged for an x operand staged with channel pitch x_cpad (the cpad b200lic_conv_x_slot reports:
+ * any multiple of 32 >= Cin); dy == NULL: dY is already staged in the slot b200lic_conv_dy_slot reports. */
+B200LIC_API int b200lic_conv_wgrad_prepared(const b200lic_conv_desc* d, int transposed, const void* x_hi, const void* x_lo,
+                                int x_cpad, const float* dy, float* dw, void* workspace, size_t workspace_bytes,
+                                b200lic_stream_t stream);
+/* The weight gradient with its tail fused: the per-split partial sums are reduced (fixed order) straight into
+ * b200lic_adaround_bwd_adam_sched's arithmetic -- dW never exists in memory unless dw_out (may be NULL) asks for it.
+ * Bit-identical to b200lic_conv_wgrad_staged followed by b200lic_adaround_bwd_adam_sched. */
+B200LIC_API int b200lic_conv_wgrad_adam_sched(const b200lic_conv_desc* d, int transposed, const void* x_hi, const void* x_lo,
+                                  int x_cpad, const float* dy, void* workspace, size_t workspace_bytes, const float* w, float* alpha,
+                                  const float* delta, const float* zero_point, float* exp_avg, float* exp_avg_sq,
+                                  int outer, int ch, int inner, int n_levels, const b200lic_calib_sched* sched,
+                                  float beta1, float beta2, float eps, float grad_scale, float reg_weight,
+                                  float* reg_loss, float* dw_out, b200lic_stream_t stream);
 
 /* out = a * sigmoid(b) + c   (AttentionBlock tail) */
 B200LIC_API int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out,

@@ -36,7 +36,7 @@ def _rows(model, x, kinds):
 
 
 def compare_forward(arch, kw, gain, hw, dev, wq=None, aq=None, lu=False, follow_bits=False, engine=None, pad=256,
-                    layer_checks=True):
+                    layer_checks=True, self_noise=False):
     """Builds the oracle codec (CPU) and the product codec (CUDA) with identical seeded random-init parameters, wraps both
     (TO rules, or LU rules with `lu=True`), and compares
 
@@ -44,6 +44,7 @@ def compare_forward(arch, kw, gain, hw, dev, wq=None, aq=None, lu=False, follow_
       * W-only forward: every layer fed the ORACLE's input                                 -> `worst_layer_rel_err`
       * W-only and W+A end-to-end bpp / PSNR                                               -> `d_bpp_*`, `d_psnr_*`
       * W+A forward, layer-local: share of activation codes that differ (boundary flips)   -> `a8_flip_rate`
+      * `self_noise`: the oracle against itself with the other CPU conv backend            -> `ref_self_noise_*`
 
     `engine`: "simt" (exact fp32 CUDA engine), "tc" / "auto" (tcgen05 split-bf16 engine) or None (leave as is)."""
     from rdo_ptq_b200 import codec, ops, quantization as Q, quant_int as LU, synth, evaluate as E
@@ -148,6 +149,16 @@ def compare_forward(arch, kw, gain, hw, dev, wq=None, aq=None, lu=False, follow_
                 tot += d.numel()
         res["a8_flip_rate"] = flips / max(tot, 1)
         res["d_bpp_wa"], res["d_psnr_wa"], res["bpp_ref_wa"], res["psnr_ref_wa"] = metrics(ref8, out8)
+        if self_noise:
+            # The reference against ITSELF: the same PyTorch-CPU arithmetic through the other convolution backend (oneDNN
+            # off).  Conv outputs then differ in the last bits (summation order), activation codes flip where a value
+            # sits on a rounding boundary, the flips move the dynamic per-channel ranges and the latent rounding, and
+            # the end-to-end metrics move: this is the reproducibility floor of the W+A forward on this model.
+            with torch.backends.mkldnn.flags(enabled=False), torch.no_grad():
+                alt = oqm(xp)
+            res["ref_self_noise_bpp"] = abs(oeval.compute_bpp(alt) - res["bpp_ref_wa"])
+            res["ref_self_noise_psnr"] = abs(oeval.compute_psnr(x, oeval.crop(alt["x_hat"], hw).clamp(0, 1)) -
+                                             res["psnr_ref_wa"])
         yo_, yp_ = ref8["likelihoods"]["y"], out8["likelihoods"]["y"].cpu()
         res["latent_lik_mismatch"] = ((yo_ - yp_).abs() > 1e-3 * yo_.abs() + 1e-6).float().mean().item()
         res["seconds"] = time.perf_counter() - t0

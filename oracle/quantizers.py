@@ -178,7 +178,7 @@ class UniformAffineQuantizer(nn.Module):
             d, z = torch.tensor(d, dtype=x.dtype), torch.tensor(z, dtype=x.dtype)
             if channel_wise:                                # 1-D: .view(-1) (:274-276)
                 d, z = d.view(-1), z.view(-1)
-            return d, z
+            return d.to(x.device), z.to(x.device)            # (`type_as(x)` in the reference also moves to x's device)
         n = x.shape[ax]
         d = torch.empty(n, dtype=x.dtype)
         z = torch.empty(n, dtype=x.dtype)
@@ -188,7 +188,7 @@ class UniformAffineQuantizer(nn.Module):
         shape[ax] = n
         if x.dim() != 4:                                    # :277-279 2-D/3-D -> [n,1]
             shape = [n, 1]
-        return d.view(shape), z.view(shape)
+        return d.view(shape).to(x.device), z.view(shape).to(x.device)
 
     def forward(self, x: torch.Tensor, act: bool = False):
         """:156-184."""

@@ -52,6 +52,7 @@ SIGNATURES = {
     "actq_stats": [_P, _I, _I, _I, _P],
     "actq_apply": [_P, _P, _I, _I, _I, _I, _P, _P],
     "actq_fused": [_P, _I, _I, _I, _I, _P, _P],
+    "actq_apply_stage": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "fixed_point": [_P, _SZ, _I, _I, _P],
     "gaussian_lik_fwd": [_P, _P, _P, _I, _I, _I, _LL, _F, _F, _P, _P, _P],
     "round_latent": [_P, _P, _SZ, _P],
@@ -85,6 +86,14 @@ SIGNATURES = {
     "calib_sched_tick": [_P, _I, _DBL, _DBL, _DBL, _F, _F, _F],
     "adaround_bwd_adam_sched": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F, _F, _F, _P],
     "gather_mix_sched": [_P, _P, _P, _I, _SZ, _SZ, _F, _ULL, _I, _I, _P, _P],
+    "conv_pack_weights": [_D, _I, _P, _P, _SZ],
+    "quant_pack_weights": [_D, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _P],
+    "conv_fwd_packed": [_D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ],
+    "stage_mix_sched": [_P, _P, _P, _I, _I, _I, _I, _F, _ULL, _I, _I, _P, _I, _P, _P, _I, _P],
+    "lp_loss_stage_sched": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _I, _F, _P, _P, _P, _I, _P],
+    "conv_wgrad_prepared": [_D, _I, _P, _P, _I, _P, _P, _P, _SZ],
+    "conv_wgrad_adam_sched": [_D, _I, _P, _P, _I, _P, _P, _SZ, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F,
+                              _F, _F, _P, _P],
     "attn_gate": [_P, _P, _P, _SZ, _P],
     "abs": [_P, _SZ, _P],
     "pixel_shuffle": [_P, _I, _I, _I, _I, _I, _I, _F, _P],
@@ -94,7 +103,12 @@ PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "devic
          "launch_count": (C.c_ulonglong, []), "factorized_table_floats": (C.c_int, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
          "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
          "conv_staged_view": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
-                                        C.POINTER(C.c_void_p)])}
+                                        C.POINTER(C.c_void_p)]),
+         "conv_packed_weight_bytes": (C.c_size_t, [_D, C.c_int]),
+         "conv_x_slot": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_int)]),
+         "conv_dy_slot": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_int)])}
 OP_CONV_FWD, OP_DECONV_FWD, OP_CONV_DGRAD, OP_DECONV_DGRAD, OP_CONV_WGRAD, OP_DECONV_WGRAD = range(6)
 
 _lib = None

@@ -4,6 +4,7 @@
 // Reference arithmetic restated: task-oriented-PTQ/quantization/quantizer.py:81-117 -- per channel c over
 // (N,H,W): m = min, r = max(max - m, 1e-6), q = rint(clamp((x-m)/r, -1, 1) * L), out = (q/L)*r + m;
 // light-uniform-PTQ/quant_int/quantizer.py:120-128 -- static Q(a_l).(a_r) fixed point.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace b200lic {
@@ -255,6 +256,71 @@ __global__ void __launch_bounds__(256) fixed_point_kernel(const float* __restric
   }
 }
 
+// ---- K8 apply fused with the consumer's operand staging ---------------------------------------------------------------
+// The quantised activation's next reader on the evaluation path is the following layer's tensor-core GEMM, whose operand
+// is the split-bf16 NHWC copy of it (conv_tc.cu nhwc_split_kernel).  actq_apply + nhwc_split read the tensor twice and
+// write it twice (16 B/elem); here one pass quantises (actq_one: same codes, bit for bit) and writes the staged operand
+// (x, or x*x for a GDN consumer) -- and, only when someone needs it (GDN's epilogue), the fp32 quantised tensor.
+__global__ void __launch_bounds__(256)
+    actq_apply_stage_kernel(const float* __restrict__ x, const unsigned* __restrict__ keys, int C, int HW, int cpad, float L,
+                            int square, __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl,
+                            float* __restrict__ out) {
+  __shared__ float t[64][65];
+  const int cblk = (cpad + 63) >> 6;
+  const int n = blockIdx.z, c0 = (int)(blockIdx.x % cblk) * 64, p0 = (int)(blockIdx.x / cblk) * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t img = (size_t)n * C * HW;
+  const bool vec2 = (HW & 1) == 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cl = warp + 8 * j, c = c0 + cl, p = p0 + 2 * lane;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < C && p < HW) {
+      const float m = key2f(keys[2 * c]);
+      const float r = fmaxf(__fsub_rn(key2f(keys[2 * c + 1]), m), 1e-6f);
+      const size_t e = img + (size_t)c * HW + p;
+      const bool has1 = p + 1 < HW;
+      if (vec2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(x + e));
+        v0 = actq_one(v.x, m, r, L, nullptr);
+        v1 = actq_one(v.y, m, r, L, nullptr);
+        if (out) *reinterpret_cast<float2*>(out + e) = make_float2(v0, v1);
+      } else {
+        v0 = actq_one(__ldg(x + e), m, r, L, nullptr);
+        if (has1) v1 = actq_one(__ldg(x + e + 1), m, r, L, nullptr);
+        if (out) {
+          out[e] = v0;
+          if (has1) out[e + 1] = v1;
+        }
+      }
+    }
+    if (square) {
+      v0 = __fmul_rn(v0, v0);
+      v1 = __fmul_rn(v1, v1);
+    }
+    t[cl][2 * lane] = v0;
+    t[cl][2 * lane + 1] = v1;
+  }
+  __syncthreads();
+  if (c0 + 2 * lane >= cpad) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int pl = warp + 8 * j, p = p0 + pl;
+    if (p < HW) {
+      const float a = t[2 * lane][pl], b = t[2 * lane + 1][pl];
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      __nv_bfloat162 hv, lv;
+      hv.x = ah;
+      hv.y = bh;
+      lv.x = __float2bfloat16_rn(__fsub_rn(a, __bfloat162float(ah)));
+      lv.y = __float2bfloat16_rn(__fsub_rn(b, __bfloat162float(bh)));
+      const size_t o = ((size_t)n * HW + p) * cpad + c0 + 2 * lane;
+      *reinterpret_cast<__nv_bfloat162*>(xh + o) = hv;
+      *reinterpret_cast<__nv_bfloat162*>(xl + o) = lv;
+    }
+  }
+}
+
 }  // namespace b200lic
 
 using namespace b200lic;
@@ -278,6 +344,21 @@ int b200lic_actq_stats(const float* x, int N, int C, int HW, float* minmax, b200
   actq_stats_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, C, HW, chunks,
                                                                       reinterpret_cast<unsigned*>(minmax));
   B200_LAUNCH_CHECK("actq_stats_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_actq_apply_stage(const float* x, const float* minmax, int N, int C, int HW, int n_bits, int square,
+                             void* x_hi, void* x_lo, int cpad, float* out, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && minmax && x_hi && x_lo && N > 0 && N <= 65535 && C > 0 && HW > 0, "actq_apply_stage: bad arguments");
+  B200_REQUIRE(n_bits >= 2 && n_bits <= 16, "actq_apply_stage: n_bits=%d outside [2,16]", n_bits);
+  B200_REQUIRE(cpad >= C && (cpad % 32) == 0, "actq_apply_stage: cpad=%d for %d channels", cpad, C);
+  B200_REQUIRE(((((uintptr_t)x) | ((uintptr_t)out)) & 7) == 0, "actq_apply_stage: 8-byte alignment");
+  dim3 grid((unsigned)(((cpad + 63) / 64) * ((HW + 63) / 64)), 1, (unsigned)N);
+  actq_apply_stage_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<const unsigned*>(minmax), C, HW, cpad, (float)((1 << n_bits) - 1), square,
+      reinterpret_cast<__nv_bfloat16*>(x_hi), reinterpret_cast<__nv_bfloat16*>(x_lo), out);
+  B200_LAUNCH_CHECK("actq_apply_stage_kernel");
   return B200LIC_OK;
 }
 

@@ -707,6 +707,28 @@ struct Tc2Plan {
   size_t x_bytes, b_bytes, total_bytes, smem_bytes;
 };
 
+// Layout of the packed weight operand: [phase][CoutPad][Tmax * Cpad] bf16, hi slab then lo slab (b_bytes each).  It
+// depends on the layer only (not on N / H / W), so a packed operand can be kept across calls while the weights are frozen.
+bool tc2_weight_layout(int Cin, int Cout, int KH, int KW, int stride, int transposed, int* Cpad, int* CoutPad, int* Tmax,
+                       int* phases, size_t* b_bytes) {
+  if (Cin < 1 || Cout < 1) return false;
+  const int st = transposed ? stride : 1;
+  *phases = st * st;
+  *Tmax = transposed ? ((KH + st - 1) / st) * ((KW + st - 1) / st) : KH * KW;
+  if (*Tmax < 1 || *Tmax > 64) return false;
+  *Cpad = (Cin + 31) / 32 * 32;
+  const int c16 = (Cout + 15) / 16 * 16;
+  int bn_max = 0;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (c16 % bn == 0) {
+      bn_max = bn;
+      break;
+    }
+  *CoutPad = (c16 > 256 && bn_max < 96) ? (Cout + 127) / 128 * 128 : c16;
+  *b_bytes = ((size_t)*phases * *CoutPad * *Tmax * *Cpad * 2 + 1023) / 1024 * 1024;
+  return true;
+}
+
 // written tensor [N,Cout,Ho,Wo]; gathered tensor [N,Cin,H,W]
 static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
                           int transposed, int gdn_mode, int has_norm) {
@@ -857,6 +879,13 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 2048;
   p.x_bytes = ((size_t)N * H * W * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.b_bytes = ((size_t)p.phases * p.CoutPad * p.Tmax * p.Cpad * 2 + 1023) / 1024 * 1024;
+  {
+    int c_, co_, t_, ph_;
+    size_t bb_;
+    if (!tc2_weight_layout(Cin, Cout, KH, KW, stride, transposed, &c_, &co_, &t_, &ph_, &bb_) || c_ != p.Cpad ||
+        co_ != p.CoutPad || t_ != p.Tmax || ph_ != p.phases || bb_ != p.b_bytes)
+      return p;                                   // never: both follow the same rules (keeps them from drifting apart)
+  }
   p.total_bytes = 2 * p.x_bytes + 2 * p.b_bytes + 1024;
   p.ok = true;
   return p;
@@ -884,11 +913,28 @@ int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, i
 }
 // w_scale != nullptr: `w` holds bf16-exact integers (codes minus zero point) and w_scale[Cout] the per-output-channel
 // step size: y = act(conv(x, w) * w_scale + bias) with two MMA passes per product.
+int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
+                  int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
+                  int fixed_point, const float* x, const float* w, const void* packed_w, const float* w_scale,
+                  const float* bias, const float* gdn_x, float* norm_out, float* y, void* workspace,
+                  size_t workspace_bytes, cudaStream_t s, const char* name);
 int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
                   int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
                   int fixed_point, const float* x, const float* w, const float* w_scale, const float* bias,
                   const float* gdn_x, float* norm_out, float* y, void* workspace, size_t workspace_bytes, cudaStream_t s,
                   const char* name) {
+  return tc2_launch_ex(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, pad, transposed, s_co, s_ci, act, slope, in_square,
+                       gdn_mode, fixed_point, x, w, nullptr, w_scale, bias, gdn_x, norm_out, y, workspace,
+                       workspace_bytes, s, name);
+}
+// packed_w != nullptr: the weight operand was prepared by the caller in tc2_weight_layout form (hi slab, lo slab) --
+// `w` is ignored and no packing kernel runs.  x == nullptr: the activation operand is already staged at the head of the
+// workspace (split-bf16 NHWC, channels padded to 32).
+int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
+                  int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
+                  int fixed_point, const float* x, const float* w, const void* packed_w, const float* w_scale,
+                  const float* bias, const float* gdn_x, float* norm_out, float* y, void* workspace,
+                  size_t workspace_bytes, cudaStream_t s, const char* name) {
   if (w_scale && gdn_mode) {
     set_error("%s: integer-weight mode does not combine with gdn_mode", name);
     return B200LIC_ERR_ARG;
@@ -918,9 +964,18 @@ int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
     rc = tc_stage_nhwc(x, N, Cin, H * W, p.Cpad, in_square, xh, xl, s);
     if (rc != B200LIC_OK) return rc;
   }
-  rc = tc_pack_weights(w, Cout, Cin, KH, KW, stride, pad, transposed, p.CoutPad, p.Cpad, p.Tmax, p.phases, s_co, s_ci, bh,
-                       bl, s);
-  if (rc != B200LIC_OK) return rc;
+  if (packed_w != nullptr) {
+    if (((uintptr_t)packed_w) & 127) {
+      set_error("%s: packed weight operand must be 128-byte aligned", name);
+      return B200LIC_ERR_ARG;
+    }
+    bh = const_cast<void*>(packed_w);
+    bl = reinterpret_cast<uint8_t*>(bh) + p.b_bytes;
+  } else {
+    rc = tc_pack_weights(w, Cout, Cin, KH, KW, stride, pad, transposed, p.CoutPad, p.Cpad, p.Tmax, p.phases, s_co, s_ci,
+                         bh, bl, s);
+    if (rc != B200LIC_OK) return rc;
+  }
 
   // 2. tensor maps
   CUtensorMap mah, mal, mbh, mbl, my, mx, mn;
@@ -1002,6 +1057,19 @@ int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
                                                                 norm_out, y, dbg);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
+}
+
+// Where the forward workspace keeps the staged activation operand: [N,H,W,Cpad] bf16 hi at the (1 KB aligned) head, lo
+// x_bytes behind it.
+bool tc2_x_slot(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int transposed,
+                void* workspace, size_t workspace_bytes, void** hi, void** lo, int* cpad) {
+  Tc2Plan p = make_plan2(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed, 0, 0);
+  if (!p.ok || !workspace || workspace_bytes < p.total_bytes) return false;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  *hi = ws;
+  *lo = ws + p.x_bytes;
+  *cpad = p.Cpad;
+  return true;
 }
 
 }  // namespace b200lic

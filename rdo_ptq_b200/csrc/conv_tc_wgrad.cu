@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "prepared.cuh"
 
 namespace b200lic {
 
@@ -369,12 +370,19 @@ size_t tc_wgrad_workspace_bytes(int N, int Cs, int Hs, int Ws, int Cb, int Hb, i
   return p.ok ? p.total_bytes : 0;
 }
 
+// Fused tail (weight_quant.cu): instead of writing dW, the per-split slabs are summed (same fixed order as
+// wgrad_reduce_kernel) straight into the AdaRound backward + Adam step of the layer's alpha.
+size_t smallc_conv_wgrad_ws(const b200lic_conv_desc* d);
+size_t smallc_deconv_wgrad_ws(const b200lic_conv_desc* d);
+int launch_wgrad_reduce_adam(const float* part, int splits, int T, int Cs, int Cb, const WgTail* tail, cudaStream_t s);
+
 // small [N,Cs,Hs,Ws], big [N,Cb,Hb,Wb] (fp32 NCHW) -> dw [Cs][Cb][KH][KW] (overwritten)
 // Pre-staged operands: `small` / `big` may be nullptr when the matching split-bf16 NHWC operand already exists, either in
 // this workspace's own slot (conv_tc_smallc.cu) or, with small_pre / big_pre, in a forward workspace (staged view).
 int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
                 const float* small, const float* big, const void* const* small_pre, const void* const* big_pre, float* dw,
-                void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name);
+                void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name, const WgTail* tail = nullptr,
+                int pre_pitch = 0);
 int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
              const float* small, const float* big, float* dw, void* workspace, size_t workspace_bytes, cudaStream_t s,
              const char* name) {
@@ -383,7 +391,11 @@ int tc_wgrad(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int 
 }
 int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, int KW, int stride, int pad, int big_square,
                 const float* small, const float* big, const void* const* small_pre, const void* const* big_pre, float* dw,
-                void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name) {
+                void* workspace, size_t workspace_bytes, cudaStream_t s, const char* name, const WgTail* tail,
+                int pre_pitch) {
+  // pre_pitch: channel pitch of a PRE-staged operand when it is not this engine's own padding (a forward workspace pads
+  // channels to 32, this engine to 64): the tensor map then describes the real extent and TMA zero-fills the rest of the
+  // last 64-channel box
   WgPlan p = make_wg_plan(N, Cs, Hs, Ws, Cb, Hb, Wb, KH, KW, stride);
   if (!p.ok) {
     set_error("%s: shape not eligible for the tcgen05 engine", name);
@@ -419,15 +431,15 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
   }
   CUtensorMap mb, ms;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)p.CbPad, (cuuint64_t)Wb, (cuuint64_t)Hb, (cuuint64_t)N, 2};
-    cuuint64_t str[4] = {(cuuint64_t)p.CbPad * 2, (cuuint64_t)Wb * p.CbPad * 2, (cuuint64_t)Hb * Wb * p.CbPad * 2,
-                         (cuuint64_t)big_slab};
+    const cuuint64_t bp = (big_pre && pre_pitch > 0) ? (cuuint64_t)pre_pitch : (cuuint64_t)p.CbPad;
+    const cuuint64_t sp = (small_pre && pre_pitch > 0) ? (cuuint64_t)pre_pitch : (cuuint64_t)p.CsPad;
+    cuuint64_t dims[5] = {bp, (cuuint64_t)Wb, (cuuint64_t)Hb, (cuuint64_t)N, 2};
+    cuuint64_t str[4] = {bp * 2, (cuuint64_t)Wb * bp * 2, (cuuint64_t)Hb * Wb * bp * 2, (cuuint64_t)big_slab};
     cuuint32_t box[5] = {64, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), (cuuint32_t)p.BI, 2};
     cuuint32_t es[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
     if (!tc_encode_map(&mb, bh, 5, dims, str, box, es)) return B200LIC_ERR_CUDA;
-    cuuint64_t sdims[5] = {(cuuint64_t)p.CsPad, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N, 2};
-    cuuint64_t sstr[4] = {(cuuint64_t)p.CsPad * 2, (cuuint64_t)Ws * p.CsPad * 2, (cuuint64_t)Hs * Ws * p.CsPad * 2,
-                          (cuuint64_t)small_slab};
+    cuuint64_t sdims[5] = {sp, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)N, 2};
+    cuuint64_t sstr[4] = {sp * 2, (cuuint64_t)Ws * sp * 2, (cuuint64_t)Hs * Ws * sp * 2, (cuuint64_t)small_slab};
     cuuint32_t sbox[5] = {64, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI, 2};
     cuuint32_t ses[5] = {1, 1, 1, 1, 1};
     if (!tc_encode_map(&ms, sh, 5, sdims, sstr, sbox, ses)) return B200LIC_ERR_CUDA;
@@ -446,10 +458,52 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
   dim3 grid(p.units, p.n_tiles, p.splits);
   tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mb, ms, g, part);
   B200_LAUNCH_CHECK(name);
+  if (tail != nullptr) return launch_wgrad_reduce_adam(part, p.splits, KH * KW, Cs, Cb, tail, s);
   const size_t per = (size_t)KH * KW * Cs * Cb;
   wgrad_reduce_kernel<<<grid_for(per, 256), 256, 0, s>>>(part, p.splits, KH * KW, Cs, Cb, dw);
   B200_LAUNCH_CHECK("wgrad_reduce_kernel");
   return B200LIC_OK;
+}
+
+// Slot of the weight-gradient workspace that holds the split-bf16 NHWC copy of dy ([N,Ho,Wo,cpad], channels padded to
+// 64): the `small` operand of a conv wgrad, the `big` (gathered) operand of a transposed-conv wgrad.
+bool tc_wgrad_dy_slot(const b200lic_conv_desc* d, int transposed, void* workspace, size_t workspace_bytes, void** hi,
+                      void** lo, int* cpad) {
+  if ((transposed ? smallc_deconv_wgrad_ws(d) : smallc_conv_wgrad_ws(d)) != 0) return false;
+  WgPlan p = transposed ? make_wg_plan(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride)
+                        : make_wg_plan(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride);
+  if (!p.ok || !workspace || workspace_bytes < p.total_bytes) return false;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  if (transposed) {
+    *hi = ws + 2 * p.small_bytes;
+    *lo = ws + 2 * p.small_bytes + p.big_bytes;
+    *cpad = p.CbPad;
+  } else {
+    *hi = ws;
+    *lo = ws + p.small_bytes;
+    *cpad = p.CsPad;
+  }
+  return true;
+}
+
+// x staged by the forward call, dy either fp32 (staged here) or nullptr (already staged in the dy slot), and the
+// AdaRound backward + Adam fused behind the split-K reduction when `tail` is given.
+int tc_wgrad_prepared(const b200lic_conv_desc* d, int transposed, const void* x_hi, const void* x_lo, int x_pitch,
+                      const float* dy, float* dw, void* ws, size_t ws_bytes, const WgTail* tail, cudaStream_t s) {
+  if (x_pitch < d->Cin || (x_pitch % 32) != 0) {
+    set_error("conv_wgrad (prepared operands): staged x has channel pitch %d for %d channels", x_pitch, d->Cin);
+    return B200LIC_ERR_ARG;
+  }
+  if ((transposed ? smallc_deconv_wgrad_ws(d) : smallc_conv_wgrad_ws(d)) != 0) {
+    set_error("conv_wgrad (prepared operands): shape runs on the folded-tap path");
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  const void* pre[2] = {x_hi, x_lo};
+  if (transposed)
+    return tc_wgrad_ex(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0, nullptr, dy,
+                       pre, nullptr, dw, ws, ws_bytes, s, "deconv_wgrad(tc, prepared)", tail, x_pitch);
+  return tc_wgrad_ex(d->N, d->Cout, d->Ho, d->Wo, d->Cin, d->H, d->W, d->KH, d->KW, d->stride, d->pad, d->in_square, dy,
+                     nullptr, nullptr, pre, dw, ws, ws_bytes, s, "conv_wgrad(tc, prepared)", tail, x_pitch);
 }
 
 size_t smallc_conv_wgrad_ws(const b200lic_conv_desc* d);

@@ -6,7 +6,9 @@
 //   :281-298 range -> (delta, zero_point); :175-177 fake-quant; :437-452 AdaRound forward;
 //   :454-466 alpha init; layer_opt.py:160-165 rounding regulariser; torch.optim.Adam.
 #include <initializer_list>
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "prepared.cuh"
 
 namespace b200lic {
 
@@ -295,6 +297,37 @@ struct AdamArgs {
   float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps;
 };
 
+// d loss / d alpha of one element: STE masks of the clamp and of the hard sigmoid (autograd of quantizer.py:437-452) on
+// the upstream dL/dWq, plus the gradient of the rounding regulariser (layer_opt.py:160-165); reg_acc accumulates its value.
+__device__ __forceinline__ float adaround_grad(float w, float a, float d, float z, float top, float d_wq, float grad_scale,
+                                               float reg_weight, float reg_b, float& reg_acc) {
+  const float sg = sigmoidf_(a);
+  const float s = __fadd_rn(__fmul_rn(sg, kStretch), kGamma);
+  const float h = fminf(fmaxf(s, 0.f), 1.f);
+  // autograd of clamp passes the gradient on the closed interval
+  const float dh_da = (s >= 0.f && s <= 1.f) ? kStretch * sg * (1.f - sg) : 0.f;
+  const float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(w, d)), h), z);
+  float g = 0.f;
+  if (xi >= 0.f && xi <= top) g = grad_scale * d_wq * d * dh_da;
+  if (reg_b > 0.f) {
+    const float u = fabsf(h - 0.5f) * 2.f;          // |2h-1|
+    const float ub1 = powf(u, reg_b - 1.f);
+    reg_acc += 1.f - ub1 * u;
+    const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
+    g += -reg_weight * reg_b * ub1 * 2.f * sgn * dh_da;
+  }
+  return g;
+}
+// torch.optim.Adam (layer_opt.py:254,307) on one element; bias corrections pre-folded into `ad`.
+__device__ __forceinline__ void adam_step(float a, float g, const AdamArgs& ad, float& m, float& v, float& a_new) {
+  const float mi = ad.beta1 * m + (1.f - ad.beta1) * g;
+  const float vi = ad.beta2 * v + (1.f - ad.beta2) * g * g;
+  m = mi;
+  v = vi;
+  const float denom = sqrtf(vi) * ad.inv_sqrt_bc2 + ad.eps;
+  a_new = a - ad.lr_over_bc1 * (mi / denom);
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
     adaround_bwd_adam_kernel(const float* __restrict__ w, float* __restrict__ alpha, const float* __restrict__ delta,
@@ -321,31 +354,9 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const float a = av.v[e];
-      const float sg = sigmoidf_(a);
-      const float s = __fadd_rn(__fmul_rn(sg, kStretch), kGamma);
-      const float h = fminf(fmaxf(s, 0.f), 1.f);
-      // autograd of clamp passes the gradient on the closed interval
-      const float dh_da = (s >= 0.f && s <= 1.f) ? kStretch * sg * (1.f - sg) : 0.f;
-      const float xi = __fadd_rn(__fadd_rn(floorf(__fdiv_rn(wv.v[e], d)), h), z);
-      float g = 0.f;
-      if (xi >= 0.f && xi <= top) g = grad_scale * gv.v[e] * d * dh_da;
-      if (reg_b > 0.f) {
-        const float u = fabsf(h - 0.5f) * 2.f;          // |2h-1|
-        const float ub1 = powf(u, reg_b - 1.f);
-        reg_acc += 1.f - ub1 * u;
-        const float sgn = (h > 0.5f) ? 1.f : ((h < 0.5f) ? -1.f : 0.f);
-        g += -reg_weight * reg_b * ub1 * 2.f * sgn * dh_da;
-      }
+      const float g = adaround_grad(wv.v[e], av.v[e], d, z, top, gv.v[e], grad_scale, reg_weight, reg_b, reg_acc);
       ga.v[e] = g;
-      if (m != nullptr) {
-        const float mi = ad.beta1 * mv.v[e] + (1.f - ad.beta1) * g;
-        const float vi = ad.beta2 * vv.v[e] + (1.f - ad.beta2) * g * g;
-        mv.v[e] = mi;
-        vv.v[e] = vi;
-        const float denom = sqrtf(vi) * ad.inv_sqrt_bc2 + ad.eps;
-        an.v[e] = a - ad.lr_over_bc1 * (mi / denom);
-      }
+      if (m != nullptr) adam_step(av.v[e], g, ad, mv.v[e], vv.v[e], an.v[e]);
     }
     if (d_alpha_out) stp<VEC>(d_alpha_out, i, ga);
     if (m != nullptr) {  // else: gradient-only mode (autograd surface); no optimiser state touched
@@ -358,6 +369,145 @@ __global__ void __launch_bounds__(256)
     const float tot = block_sum(reg_acc, red);
     if (threadIdx.x == 0) atomicAdd(reg_loss, reg_weight * tot);
   }
+}
+
+// ---- fused weight-gradient tail: split-K slab sum -> STE masks -> regulariser -> Adam --------------------------------------
+// part[split][tap][cs][cb] are the per-split partial weight gradients of tc_wgrad_kernel (conv_tc_wgrad.cu).  One CTA owns
+// 32 consecutive `cb` of one `cs`: phase 1 reads the slabs in their own order (128 B rows) and sums the splits in the
+// fixed order of wgrad_reduce_kernel, phase 2 walks the same 32*T weights in WEIGHT order ([cs][cb][tap], contiguous), so
+// w / alpha / m / v move in full lines.  Bit-identical to wgrad_reduce_kernel + adaround_bwd_adam_kernel.
+constexpr int kTailCb = 32;
+__global__ void __launch_bounds__(256)
+    wgrad_reduce_adam_kernel(const float* __restrict__ part, int splits, int T, int Cs, int Cb, WgTail t, AdamArgs ad) {
+  extern __shared__ float tile[];                 // [kTailCb][T]
+  __shared__ float red[32];
+  const int cbb = (Cb + kTailCb - 1) / kTailCb;
+  const int cs = blockIdx.x / cbb, cb0 = (blockIdx.x % cbb) * kTailCb;
+  const int ncb = min(kTailCb, Cb - cb0);
+  const size_t per = (size_t)T * Cs * Cb;
+  float reg_b = 0.f;
+  if (t.sched != nullptr) {
+    ad.lr_over_bc1 = __ldg(&t.sched->lr_over_bc1);
+    ad.inv_sqrt_bc2 = __ldg(&t.sched->inv_sqrt_bc2);
+    reg_b = __ldg(&t.sched->reg_b);
+  }
+  for (int e = threadIdx.x; e < kTailCb * T; e += blockDim.x) {
+    const int tap = e / kTailCb, cbl = e - tap * kTailCb;
+    float acc = 0.f;
+    if (cbl < ncb) {
+      const float* p = part + ((size_t)tap * Cs + cs) * Cb + cb0 + cbl;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int z = 0;
+      for (; z + 3 < splits; z += 4) {
+        a0 += __ldg(p + (size_t)z * per);
+        a1 += __ldg(p + (size_t)(z + 1) * per);
+        a2 += __ldg(p + (size_t)(z + 2) * per);
+        a3 += __ldg(p + (size_t)(z + 3) * per);
+      }
+      for (; z < splits; ++z) a0 += __ldg(p + (size_t)z * per);
+      acc = (a0 + a1) + (a2 + a3);
+    }
+    tile[cbl * T + tap] = acc;
+  }
+  __syncthreads();
+  float reg_acc = 0.f;
+  const size_t base = ((size_t)cs * Cb + cb0) * T;
+  for (int e = threadIdx.x; e < ncb * T; e += blockDim.x) {
+    const size_t i = base + e;
+    const int c = (int)((i / t.inner) % t.ch);
+    const float d = __ldg(t.delta + c), z = __ldg(t.zp + c);
+    const float dwq = tile[e];
+    if (t.dw_out) t.dw_out[i] = dwq;
+    const float a = t.alpha[i];
+    const float g = adaround_grad(__ldg(t.w + i), a, d, z, t.top, dwq, t.grad_scale, t.reg_weight, reg_b, reg_acc);
+    float mi = t.m[i], vi = t.v[i], an;
+    adam_step(a, g, ad, mi, vi, an);
+    t.m[i] = mi;
+    t.v[i] = vi;
+    t.alpha[i] = an;
+  }
+  if (t.reg_loss != nullptr && reg_b > 0.f) {
+    const float tot = block_sum(reg_acc, red);
+    if (threadIdx.x == 0) atomicAdd(t.reg_loss, t.reg_weight * tot);
+  }
+}
+
+int launch_wgrad_reduce_adam(const float* part, int splits, int T, int Cs, int Cb, const WgTail* tail, cudaStream_t s) {
+  AdamArgs ad{0.f, 0.f, tail->beta1, tail->beta2, tail->eps};
+  const int cbb = (Cb + kTailCb - 1) / kTailCb;
+  const size_t smem = (size_t)kTailCb * T * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("wgrad_reduce_adam: %d taps exceed the tile", T);
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  wgrad_reduce_adam_kernel<<<Cs * cbb, 256, smem, s>>>(part, splits, T, Cs, Cb, *tail, ad);
+  B200_LAUNCH_CHECK("wgrad_reduce_adam_kernel");
+  return B200LIC_OK;
+}
+
+// ---- fused weight quantiser -> packed tensor-core operand ----------------------------------------------------------------
+// For every element of the packed operand [phase][co][tap][ci] (conv_tc.cu pack_weights_kernel's layout): fetch the
+// source weight, fake-quantise it (nearest: quantizer.py:175-177; AdaRound soft / hard: :437-449 -- the arithmetic of
+// wq_fake_quant_kernel / adaround_fwd_kernel above, bit for bit) and store its bf16 hi / lo split.  mode 1 stores the
+// integer n = code - zero_point instead (exact in bf16, hi slab only): the operand of the two-pass forward.
+__global__ void __launch_bounds__(256)
+    quant_pack_kernel(PackDst g, const float* __restrict__ w, const float* __restrict__ alpha,
+                      const float* __restrict__ delta, const float* __restrict__ zp, int ch, int inner, float top, int soft,
+                      int mode, __nv_bfloat16* __restrict__ bh, __nv_bfloat16* __restrict__ bl, float* __restrict__ w_q) {
+  const int phase = blockIdx.z;
+  int r0 = 0, s0 = 0, KHp = g.KH, KWp = g.KW, rstep = 1;
+  if (g.transposed) {
+    const int st = g.stride, ph = phase / st, pw = phase % st;
+    r0 = (ph + g.pad) % st;
+    s0 = (pw + g.pad) % st;
+    KHp = r0 < g.KH ? (g.KH - r0 + st - 1) / st : 0;
+    KWp = s0 < g.KW ? (g.KW - s0 + st - 1) / st : 0;
+    rstep = st;
+  }
+  const int T = KHp * KWp;
+  const size_t Kmax = (size_t)g.Tmax * g.Cpad;
+  const size_t per_phase = (size_t)g.CoutPad * Kmax;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < per_phase; e += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(e / Kmax);
+    const int k = (int)(e - (size_t)co * Kmax);
+    const int t = k / g.Cpad, ci = k - t * g.Cpad;
+    float val = 0.f;
+    if (co < g.Cout && ci < g.Cin && t < T) {
+      const int i = t / KWp, j = t - i * KWp;
+      const size_t src = (size_t)((long long)co * g.s_co + (long long)ci * g.s_ci + (r0 + i * rstep) * g.KW + (s0 + j * rstep));
+      const int c = (int)((src / inner) % ch);
+      const float d = __ldg(delta + c), z = __ldg(zp + c);
+      const float tq = __fdiv_rn(__ldg(w + src), d);
+      float q;
+      if (alpha == nullptr) {
+        q = __fadd_rn(rintf(tq), z);
+      } else {
+        const float a = __ldg(alpha + src);
+        float up;
+        if (soft) up = fminf(fmaxf(__fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma), 0.f), 1.f);
+        else up = a >= 0.f ? 1.f : 0.f;
+        q = __fadd_rn(__fadd_rn(floorf(tq), up), z);
+      }
+      q = fminf(fmaxf(q, 0.f), top);
+      const float n_ = __fsub_rn(q, z);
+      val = mode ? n_ : __fmul_rn(n_, d);
+      if (w_q) w_q[src] = val;
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(val);
+    bh[(size_t)phase * per_phase + e] = h;
+    if (!mode) bl[(size_t)phase * per_phase + e] = __float2bfloat16_rn(val - __bfloat162float(h));
+  }
+}
+
+int launch_quant_pack(const PackDst& g, const float* w, const float* alpha, const float* delta, const float* zp, int ch,
+                      int inner, int n_levels, int soft, int mode, void* packed, float* w_q, cudaStream_t s) {
+  const size_t per_phase = (size_t)g.CoutPad * g.Tmax * g.Cpad;
+  dim3 grid((unsigned)((per_phase + 255) / 256 > 1184 ? 1184 : (per_phase + 255) / 256), 1, g.phases);
+  __nv_bfloat16* bh = reinterpret_cast<__nv_bfloat16*>(packed);
+  __nv_bfloat16* bl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(packed) + g.b_bytes);
+  quant_pack_kernel<<<grid, 256, 0, s>>>(g, w, alpha, delta, zp, ch, inner, (float)(n_levels - 1), soft, mode, bh, bl, w_q);
+  B200_LAUNCH_CHECK("quant_pack_kernel");
+  return B200LIC_OK;
 }
 
 // ---- integer weights n = code - zero_point (the operand of the two-pass forward, b200lic_conv_fwd_wq) ----------------

@@ -169,6 +169,62 @@ def act_quant(x, n_bits=8, want_codes=False):
     return (out, codes) if want_codes else out
 
 
+def act_quant_stats(x):
+    """Per-channel (min, max) keys of a [N,C,H,W] activation: the first half of `act_quant` (three-launch form)."""
+    x = _c(x.detach(), "activation")
+    N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    keys = torch.empty(2 * Cc, device=x.device, dtype=torch.int32)
+    call("actq_stats_init", _p(keys), Cc)
+    call("actq_stats", _p(x), N, Cc, HW, _p(keys))
+    return keys
+
+
+def act_quant_apply(x, keys, n_bits=8):
+    """The second half of `act_quant`."""
+    x = _c(x.detach(), "activation")
+    N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    out = torch.empty_like(x)
+    call("actq_apply", _p(x), _p(keys), N, Cc, HW, n_bits, _p(out), None)
+    return out
+
+
+def act_quant_apply_stage(x, keys, n_bits, slot, square=False, out=None):
+    """`act_quant_apply` whose result leaves as the staged operand `slot` of the next layer's GEMM (and as fp32 in `out`
+    when given): b200lic_actq_apply_stage."""
+    x = _c(x.detach(), "activation")
+    N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    hi, lo, cpad = slot
+    call("actq_apply_stage", _p(x), _p(keys), N, Cc, HW, n_bits, int(bool(square)), hi, lo, cpad, _p(out))
+
+
+# Deferred activation quantisation (evaluation only; switched on by evaluate.GraphedForward / evaluate.evaluate): a
+# QuantModule whose output goes to exactly one consumer -- the next QuantModule of the same nn.Sequential -- returns its
+# RAW output tagged with the per-channel statistics, and the consumer quantises it while staging its own GEMM operand
+# (one pass instead of apply + NHWC split).  Any other reader calls `resolve_actq` first.
+DEFER_ACTQ = False
+
+
+class defer_actq:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global DEFER_ACTQ
+        self.prev, DEFER_ACTQ = DEFER_ACTQ, self.on
+
+    def __exit__(self, *a):
+        global DEFER_ACTQ
+        DEFER_ACTQ = self.prev
+
+
+def resolve_actq(x):
+    """Materialise a deferred activation quantisation (no-op for ordinary tensors)."""
+    pend = getattr(x, "_b200_actq", None)
+    if pend is None:
+        return x
+    return act_quant_apply(x, pend[0], pend[1])
+
+
 def fixed_point(x, a_l=8, a_r=8):
     x = _c(x, "activation")
     out = torch.empty_like(x)
@@ -619,6 +675,121 @@ def conv_wq(x, w_int, w_scale, bias=None, stride=1, padding=0, output_padding=0,
             return None
         raise
     return y
+
+
+# ------------------------------------------------------------------------------------------------ prepared operands
+def fwd_op(transposed):
+    return _lib.OP_DECONV_FWD if transposed else _lib.OP_CONV_FWD
+
+
+def wgrad_op(transposed):
+    return _lib.OP_DECONV_WGRAD if transposed else _lib.OP_CONV_WGRAD
+
+
+def packed_weight_bytes(d, transposed):
+    """Bytes of the packed tensor-core weight operand of this layer; 0 = no prepared-operand path (folded-tap layer, SIMT)."""
+    return int(_lib.lib().b200lic_conv_packed_weight_bytes(C.byref(d), fwd_op(transposed)))
+
+
+def new_packed(d, transposed, device):
+    n = packed_weight_bytes(d, transposed)
+    return None if n == 0 else torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def pack_weights(w, d, transposed, out=None):
+    """fp32 weight -> packed split-bf16 operand (b200lic_conv_pack_weights)."""
+    w = _c(w, "weight")
+    out = new_packed(d, transposed, w.device) if out is None else out
+    if out is None:
+        return None
+    call("conv_pack_weights", C.byref(d), fwd_op(transposed), _p(w), _p(out), out.numel())
+    return out
+
+
+def quant_pack_weights(w, alpha, delta, zp, axis, n_levels, soft, d, transposed, integer_mode=False, out=None, w_q=None):
+    """Weight quantiser (nearest when alpha is None, else AdaRound soft / hard) fused with the packing."""
+    w = _c(w, "weight")
+    outer, ch, inner = channel_view(w.shape, axis)
+    out = new_packed(d, transposed, w.device) if out is None else out
+    if out is None:
+        return None
+    call("quant_pack_weights", C.byref(d), fwd_op(transposed), _p(w), _p(None if alpha is None else _c(alpha)),
+         _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))), outer, ch, inner, int(n_levels), int(bool(soft)),
+         int(bool(integer_mode)), _p(out), out.numel(), _p(w_q))
+    return out
+
+
+def conv_fwd_packed(x, packed, d, transposed, bias=None, w_scale=None, gdn_x=None, want_norm=False, ws=None, y=None):
+    """Forward with a prepared weight operand; x=None: the activation operand is already staged in `ws`.
+    Returns y, or (y, norm) with want_norm."""
+    if ws is None:
+        ws = _workspace(d, fwd_op(transposed), packed.device)
+    wsb, nws = ws
+    if y is None:
+        y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=packed.device, dtype=torch.float32)
+    norm = torch.empty_like(y) if want_norm else None
+    call("conv_fwd_packed", C.byref(d), fwd_op(transposed), _p(None if x is None else _c(x, "input")), _p(packed),
+         _p(_c(w_scale)), _p(_c(bias)), _p(gdn_x), _p(norm), _p(y), _p(wsb), nws)
+    return (y, norm) if want_norm else y
+
+
+def _slot(name, d, op, ws):
+    wsb, nws = ws
+    if wsb is None:
+        return None
+    hi, lo, cpad = C.c_void_p(), C.c_void_p(), C.c_int()
+    rc = getattr(_lib.lib(), "b200lic_" + name)(C.byref(d), op, _p(wsb), nws, C.byref(hi), C.byref(lo), C.byref(cpad))
+    if rc != 0 or not hi.value:
+        return None
+    return hi, lo, cpad.value
+
+
+def conv_x_slot(d, transposed, ws):
+    """(hi, lo, cpad) of the staged activation operand inside a forward workspace, or None."""
+    return _slot("conv_x_slot", d, fwd_op(transposed), ws)
+
+
+def conv_dy_slot(d, transposed, ws):
+    """(hi, lo, cpad) of the staged dY operand inside a weight-gradient workspace, or None."""
+    return _slot("conv_dy_slot", d, wgrad_op(transposed), ws)
+
+
+def stage_mix_sched(q, fp, idx_table, rows, prob, seed_base, units, unit, sched, slot, square=False, out=None):
+    """gather_mix_sched whose result is written as the staged (split-bf16 NHWC) activation operand `slot`."""
+    q, fp = _c(q), _c(fp)
+    Cc, HW = q.shape[1], q[0, 0].numel()
+    hi, lo, cpad = slot
+    call("stage_mix_sched", _p(q), _p(fp), _p(idx_table), 0 if idx_table is None else idx_table.size(0), int(rows), Cc, HW,
+         float(prob), int(seed_base) & 0xFFFFFFFFFFFFFFFF, int(units), int(unit), _p(sched), int(bool(square)), hi, lo,
+         cpad, _p(out))
+
+
+def lp_loss_stage_sched(pred, tgt_cache, idx_table, units, unit, sched, p, scale, grad_scale, act, slope, loss, slot,
+                        d_pred=None):
+    """lp_loss value + gradient with the gradient written as the staged dY operand `slot` of the weight gradient."""
+    pred, tgt_cache = _c(pred), _c(tgt_cache)
+    rows, Cc, HW = pred.shape[0], pred.shape[1], pred[0, 0].numel()
+    hi, lo, cpad = slot
+    call("lp_loss_stage_sched", _p(pred), _p(tgt_cache), _p(idx_table), 0 if idx_table is None else idx_table.size(0),
+         rows, Cc, HW, int(units), int(unit), _p(sched), float(p), float(scale), float(grad_scale), int(act), float(slope),
+         _p(loss), hi, lo, cpad, _p(d_pred))
+
+
+def conv_wgrad_prepared(d, transposed, x_slot, dy, dw, ws):
+    """Weight gradient from a pre-staged x (and, with dy=None, a pre-staged dY in `ws`)."""
+    wsb, nws = ws
+    call("conv_wgrad_prepared", C.byref(d), int(transposed), x_slot[0], x_slot[1], x_slot[2], _p(dy), _p(dw), _p(wsb), nws)
+
+
+def conv_wgrad_adam_sched(d, transposed, x_slot, dy, ws, w, alpha, delta, zp, exp_avg, exp_avg_sq, axis, n_levels, sched,
+                          beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, reg_weight=0.0, reg_loss=None, dw_out=None):
+    """Weight gradient with the AdaRound backward + Adam step fused behind its split-K reduction."""
+    outer, ch, inner = channel_view(w.shape, axis)
+    wsb, nws = ws
+    call("conv_wgrad_adam_sched", C.byref(d), int(transposed), x_slot[0], x_slot[1], x_slot[2], _p(dy), _p(wsb), nws,
+         _p(_c(w)), _p(_c(alpha)), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))), _p(exp_avg), _p(exp_avg_sq), outer,
+         ch, inner, int(n_levels), _p(sched), beta1, beta2, eps, float(grad_scale), float(reg_weight), _p(reg_loss),
+         _p(dw_out))
 
 
 def conv2d(x, w, bias=None, stride=1, padding=0, dilation=1, groups=1, act=ACT_NONE, slope=0.01, fixed_pt=0):  # noqa

@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..codec.layers import GDN, f_gdn      # noqa: F401  (f_gdn is re-exported like the reference module)
-from .quantizer import StraightThrough, UniformAffineQuantizer
+from .quantizer import AdaRoundQuantizer, StraightThrough, UniformAffineQuantizer
 
 
 class QuantModule(nn.Module):
@@ -71,12 +71,119 @@ class QuantModule(nn.Module):
     def extra_repr(self):
         return self._repr
 
+    # -- prepared weight operand (evaluation) ------------------------------------------------------------------------
+    # The reference re-quantises every weight on every forward (quant_layer.py:113-115).  Without a gradient the weight is
+    # a constant of the layer, so its tensor-core operand -- quantiser + packing in one kernel
+    # (b200lic_quant_pack_weights); for GDN: quantise gamma, re-parametrise, pack -- is built once and reused until
+    # anything it depends on changes (quantiser object, its state, alpha / delta / weight versions).
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_prep", None)                 # device scratch, not part of the pickled QuantModel (main2.py:288)
+        state.pop("_defer_to", None)             # wiring hint of QuantModel (re-derived by link_sequential_consumers)
+        return state
+
+    def _prep_key(self):
+        q = self.weight_quantizer
+
+        def ver(t):
+            return None if t is None else (t.data_ptr(), t._version)
+        bias = self.bias if self.use_weight_quant else self.org_bias
+        return (self.use_weight_quant, id(q), getattr(q, "inited", None), getattr(q, "n_levels", None),
+                getattr(q, "soft_targets", None), ver(self.weight), ver(self.org_weight), ver(getattr(q, "alpha", None)),
+                ver(getattr(q, "delta", None)), ver(getattr(q, "zero_point", None)), ver(bias), ops.DEFAULT_ENGINE)
+
+    def _prepared(self, d):
+        """(packed weight operand, w_scale or None, bias) for descriptor `d`, or None when this call has to take the
+        general path (quantiser not initialised yet, layer without a packed operand)."""
+        q = self.weight_quantizer
+        if self.use_weight_quant and (not isinstance(q, (UniformAffineQuantizer, AdaRoundQuantizer))
+                                      or getattr(q, "_leaf", None) is not None or getattr(q, "soft_targets", False)
+                                      or (hasattr(q, "inited") and not q.inited) or q.delta is None):
+            return None
+        key = self._prep_key()
+        slots = self.__dict__.setdefault("_prep", {})          # one operand per quant state: FP and quantised forwards
+        ent = slots.get(self.use_weight_quant)                 # alternate while the calibration caches are built
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        if torch.cuda.is_current_stream_capturing():
+            return None                # operands are built eagerly (a host read decides the integer form); general path
+        dev = self.weight.device
+        if ops.packed_weight_bytes(d, self.if_tconv) == 0:
+            val = None
+        elif self.is_gdn:
+            gamma = q(self.weight).detach() if self.use_weight_quant else self.org_weight
+            beta = self.bias if self.use_weight_quant else self.org_bias
+            g_eff = self.fwd_kwargs["gamma_reparam"](gamma).detach()
+            b_eff = self.fwd_kwargs["beta_reparam"](beta).detach()
+            val = (ops.pack_weights(g_eff.reshape(g_eff.shape[0], g_eff.shape[1], 1, 1), d, False), None, b_eff)
+        elif not self.use_weight_quant:
+            val = (ops.pack_weights(self.org_weight, d, self.if_tconv), None, self.org_bias)
+        else:
+            axis = q.axis if hasattr(q, "axis") else q.channel_axis(self.weight)
+            alpha = q.alpha.detach() if hasattr(q, "alpha") else None
+            out_axis = 1 if self.if_tconv else 0
+            # two-pass integer form: n = code - zero_point must be exact in bf16 (|n| <= 256) and the scale must sit on
+            # the output channels; a searched range that excludes 0 puts zero_point outside [0, levels-1] (ADVICE r1)
+            integer = (q.n_levels <= 256 and axis in (None, out_axis) and
+                       bool(((q.zero_point >= 0) & (q.zero_point <= q.n_levels - 1)).all()))
+            packed = ops.quant_pack_weights(self.weight.detach(), alpha, q.delta, q.zero_point, axis, q.n_levels, False,
+                                            d, self.if_tconv, integer_mode=integer)
+            scale = None
+            if integer:
+                cout = self.weight.shape[out_axis]
+                scale = q.delta.reshape(-1)
+                scale = (scale.expand(cout) if scale.numel() == 1 else scale).contiguous()
+            val = (packed, scale, self.bias)
+        slots[self.use_weight_quant] = (key, val)
+        return val
+
+    def _forward_prepared(self, input, act, slope):
+        if self.is_gdn:
+            d = ops.gdn_desc(input.shape, self.fwd_kwargs["inverse"])
+        else:
+            kw = self.fwd_kwargs
+            if ops._sq(kw["dilation"], "dilation") != 1 or kw["groups"] != 1:
+                return None
+            d = ops.conv_desc(input.shape, self.weight.shape, kw["stride"], kw["padding"], self.if_tconv,
+                              kw.get("output_padding", 0), act=act, slope=slope)
+        if d.engine == ops.ENGINE_SIMT:
+            return None
+        ws = ops._workspace(d, ops.fwd_op(self.if_tconv), input.device)
+        if ws[0] is None:                        # shape the tensor-core path rejects: the general path picks the engine
+            return None
+        prep = self._prepared(d)
+        if prep is None:
+            return None
+        packed, scale, bias = prep
+        x = ops._c(input, "input")
+        pend = getattr(input, "_b200_actq", None)
+        if pend is not None:
+            # the producer deferred its activation quantiser to us: quantise while staging our own operand
+            slot = ops.conv_x_slot(d, self.if_tconv, ws)
+            if slot is None:
+                x, pend = ops.act_quant_apply(x, pend[0], pend[1]), None
+            else:
+                xq = torch.empty_like(x) if self.is_gdn else None           # GDN's epilogue reads the quantised x itself
+                ops.act_quant_apply_stage(x, pend[0], pend[1], slot, square=self.is_gdn, out=xq)
+                if self.is_gdn:
+                    out = ops.conv_fwd_packed(None, packed, d, False, bias=bias, gdn_x=xq, ws=ws)
+                    return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
+                return ops.conv_fwd_packed(None, packed, d, self.if_tconv, bias=bias, w_scale=scale, ws=ws)
+        if self.is_gdn:
+            out = ops.conv_fwd_packed(x, packed, d, False, bias=bias, gdn_x=x, ws=ws)
+            return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
+        return ops.conv_fwd_packed(x, packed, d, self.if_tconv, bias=bias, w_scale=scale, ws=ws)
+
     def forward(self, input: torch.Tensor):
         act, slope = ops._act_id(self.activation_function)
         if self.is_ps:
             return ops.pixel_shuffle(input, self.fwd_kwargs, act, slope)
         out = None
-        if self.use_weight_quant and not self.is_gdn and not torch.is_grad_enabled():
+        if not torch.is_grad_enabled():
+            out = self._forward_prepared(input, act, slope)
+        if out is None:
+            input = ops.resolve_actq(input)      # general path: a deferred activation quantisation is materialised
+        if out is None and self.use_weight_quant and not self.is_gdn and not torch.is_grad_enabled():
             # hard-quantised weight, no gradient wanted (evaluation): integer weights + per-channel scale in the conv
             # epilogue, two tensor-core passes instead of three (b200lic_conv_fwd_wq); same value up to fp32 rounding
             iw = getattr(self.weight_quantizer, "int_weights", lambda _w: None)(self.weight)
@@ -102,8 +209,22 @@ class QuantModule(nn.Module):
         if self.disable_act_quant:
             return out
         if self.use_act_quant and self.trained:
+            nxt = self.__dict__.get("_defer_to")
+            if (ops.DEFER_ACTQ and nxt is not None and not torch.is_grad_enabled() and out.dim() == 4
+                    and not nxt._forward_hooks and not nxt._forward_pre_hooks and not self._forward_hooks):
+                # evaluation inside an nn.Sequential: the only reader is the next QuantModule, which applies the
+                # quantiser while staging its operand (ops.DEFER_ACTQ); the statistics are taken here
+                bits = self.act_quantizer.n_bits if self.act_quantizer.act_bits_follow_n_bits else 8
+                out = out.detach()
+                out._b200_actq = (ops.act_quant_stats(out), bits)
+                return out
             out = self.act_quantizer(out, True)
         return out
+
+    def invalidate_prepared(self):
+        """Drop the cached weight operand.  Version counters catch in-place torch ops on weight / alpha / delta; writes
+        through `.data` or by a kernel (the AdaRound loop) do not bump them, so the AdaRound loop calls this when it hardens a unit."""
+        self.__dict__.pop("_prep", None)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         self.use_weight_quant = weight_quant

@@ -7,6 +7,20 @@ from .quant_block import specials, BaseQuantBlock
 from .quant_layer import QuantModule, StraightThrough
 
 
+def link_sequential_consumers(model: nn.Module):
+    """Inside an nn.Sequential the output of child i is read by child i+1 only.  Where both are QuantModules (identity
+    StraightThrough placeholders in between are skipped) the producer learns its consumer (`_defer_to`), which lets the
+    evaluation forward defer the dynamic activation quantiser into the consumer's operand staging (ops.DEFER_ACTQ).
+    Host-side wiring only; no effect unless that switch is on."""
+    for seq in model.modules():
+        if not isinstance(seq, nn.Sequential):
+            continue
+        kids = [m for m in seq.children() if not isinstance(m, StraightThrough)]
+        for a, b in zip(kids, kids[1:]):
+            if isinstance(a, QuantModule) and isinstance(b, QuantModule) and not b.is_ps:
+                a.__dict__["_defer_to"] = b
+
+
 class QuantModel(nn.Module):
     def __init__(self, model: nn.Module, weight_quant_params: dict = {}, act_quant_params: dict = {}, is_fusing=True,
                  is_cheng=False):
@@ -14,6 +28,7 @@ class QuantModel(nn.Module):
         # BN folding (reference fold_bn.py) is a no-op for the LIC graphs: they contain no BatchNorm.
         self.model = model
         self.quant_module_refactor(self.model, weight_quant_params, act_quant_params, is_cheng)
+        link_sequential_consumers(self.model)
 
     def quant_module_refactor(self, module: nn.Module, weight_quant_params: dict = {}, act_quant_params: dict = {},
                               is_cheng=False):

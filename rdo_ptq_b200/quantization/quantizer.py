@@ -109,6 +109,8 @@ class UniformAffineQuantizer(nn.Module):
         integer-weight forward does not apply (not initialised, more than 256 levels: |n| must be exact in bf16)."""
         if not self.inited or self.n_levels > 256 or x.dim() != 4 or self.delta is None:
             return None
+        if not _zp_in_grid(self):
+            return None
         return _int_weights(x, self.delta, self.zero_point, self.channel_axis(x), self.n_levels, self.tconv, None)
 
     def init_quantization_scale(self, x: torch.Tensor, channel_wise: bool = False):
@@ -131,6 +133,20 @@ class UniformAffineQuantizer(nn.Module):
     def extra_repr(self):
         return (f'bit={self.n_bits}, scale_method={self.scale_method}, symmetric={self.sym}, '
                 f'channel_wise={self.channel_wise}, leaf_param={self.leaf_param}')
+
+
+def _zp_in_grid(q):
+    """n = code - zero_point is exact in bf16 only for |n| <= 256, i.e. 0 <= zero_point <= levels - 1.  'max' ranges
+    always contain 0; the searched ranges ('mse' / 'l1' / 'l2') need not (reference quantizer.py:300-370), and a
+    single-signed channel then gets a zero point far outside the grid.  One device read per (delta, zero_point) pair."""
+    key = (q.zero_point.data_ptr(), q.zero_point._version, q.n_levels)
+    cached = q.__dict__.get("_zp_ok")
+    if cached is None or cached[0] != key:
+        if torch.cuda.is_current_stream_capturing():
+            return False                  # no host read inside a graph capture: take the always-valid three-pass form
+        ok = bool(((q.zero_point >= 0) & (q.zero_point <= q.n_levels - 1)).all())
+        q.__dict__["_zp_ok"] = cached = (key, ok)
+    return cached[1]
 
 
 def _int_weights(x, delta, zp, axis, n_levels, tconv, alpha):
@@ -214,6 +230,8 @@ class AdaRoundQuantizer(nn.Module):
     def int_weights(self, x):
         """See UniformAffineQuantizer.int_weights; only the hardened quantiser has integer weights."""
         if self.soft_targets or self._leaf is not None or self.n_levels > 256 or x.dim() != 4:
+            return None
+        if not _zp_in_grid(self):
             return None
         return _int_weights(x, self.delta, self.zero_point, self.axis, self.n_levels, getattr(self, "tconv", False),
                             self.alpha.detach())

@@ -8,6 +8,7 @@ One iteration of the reference loop (layer_opt.py:287-309 / block_opt.py:287-311
 No `.item()`/`float()` syncs inside the loop; the loss is read back only every `log_every` iterations.
 """
 import logging
+import os
 from typing import List, Optional
 
 import torch
@@ -106,6 +107,46 @@ class CoderTask:
         pass
 
 
+FUSED_DEFAULT = os.environ.get("B200LIC_FUSED", "1") != "0"
+
+
+class FusedLayer:
+    """Static buffers of the FUSED iteration of a conv / transposed-conv unit (prepared operands, include/b200lic.h):
+    stage_mix (pick + QDrop -> staged activation operand) -> quant_pack (AdaRound soft weight -> packed weight operand)
+    -> GEMM -> loss_stage (loss + gradient -> staged dY operand) -> wgrad with the STE / regulariser / Adam tail fused
+    behind its split-K reduction.  Seven launches; no fp32 batch, soft weight, dL/dout or dL/dWq tensor is written.
+    Not applicable (-> None from `build`): blocks, GDN, PixelShuffle, the folded-tap 3-channel layers, the SIMT engine."""
+
+    def __init__(self):
+        self.d = self.tr = self.packed = self.ws_f = self.ws_w = self.x_slot = self.dy_slot = self.y = self.dw = None
+
+    @staticmethod
+    def build(m, in_shape, batch, world):
+        if not isinstance(m, QuantModule) or m.is_gdn or m.is_ps or m.org_weight is None or m.se_module is not None:
+            return None
+        kw = m.fwd_kwargs
+        if ops._sq(kw["dilation"], "dilation") != 1 or kw["groups"] != 1 or ops.DEFAULT_ENGINE == ops.ENGINE_SIMT:
+            return None
+        f = FusedLayer()
+        act, slope = ops._act_id(m.activation_function)
+        f.tr = m.if_tconv
+        f.d = ops.conv_desc((batch,) + tuple(in_shape), m.weight.shape, kw["stride"], kw["padding"], f.tr,
+                            kw.get("output_padding", 0), act=act, slope=slope)
+        dev = m.weight.device
+        f.packed = ops.new_packed(f.d, f.tr, dev)
+        if f.packed is None:
+            return None
+        f.ws_f = ops._workspace(f.d, ops.fwd_op(f.tr), dev)
+        f.ws_w = ops._workspace(f.d, ops.wgrad_op(f.tr), dev)
+        f.x_slot = ops.conv_x_slot(f.d, f.tr, f.ws_f)
+        f.dy_slot = ops.conv_dy_slot(f.d, f.tr, f.ws_w)
+        if f.x_slot is None or f.dy_slot is None:
+            return None
+        f.y = torch.empty((f.d.N, f.d.Cout, f.d.Ho, f.d.Wo), device=dev, dtype=torch.float32)
+        f.dw = torch.empty_like(m.weight.data) if world > 1 else None
+        return f
+
+
 class UnitTrainer:
     """State of one reconstruction problem: the QuantModules whose alpha is trained, Adam moments, schedules."""
 
@@ -147,6 +188,38 @@ class UnitTrainer:
         dev = self.mods[0].weight.device if self.mods else None
         self.loss_buf = torch.zeros(3, device=dev)      # [rec, task, round] accumulated since the last read
         self.last = {}
+        self.fused = FUSED_DEFAULT                      # A/B switch: the fused iteration where it applies
+        self._fused_plan = False                        # False = not built yet; None = not applicable
+
+    # -- the fused iteration (single conv / transposed-conv unit, reference-default loss) --------------------------------
+    def fused_plan(self, in_shape, batch):
+        if self._fused_plan is False:
+            ok = (self.fused and self.rd_task is None and not self.learn_delta and self.task_p is not None and
+                  float(self.task_p) == float(self.p) and len(self.mods) == 1 and self.mods[0] is self.unit)
+            self._fused_plan = FusedLayer.build(self.unit, in_shape, batch, self.world) if ok else None
+        return self._fused_plan
+
+    def fused_compute(self, f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base):
+        """One fused iteration up to (world == 1: and including) the Adam step.  Returns the list of dL/dWq tensors for
+        `step_update` (empty when the tail ran fused)."""
+        m = self.unit
+        q = m.weight_quantizer
+        ops.stage_mix_sched(q_in, fp_in, idx_table, f.d.N, prob, seed_base, units, unit, sched, f.x_slot)
+        ops.quant_pack_weights(m.weight.data, q.alpha.data, q.delta, q.zero_point, q.axis, q.n_levels, True, f.d, f.tr,
+                               out=f.packed)
+        ops.conv_fwd_packed(None, f.packed, f.d, f.tr, bias=m.bias, ws=f.ws_f, y=f.y)
+        denom = f.y.numel() // f.y.shape[1]
+        ops.lp_loss_stage_sched(f.y, tgt_cache, idx_table, units, unit, sched, self.p, 1.0 / denom, 2.0 / denom, f.d.act,
+                                f.d.act_slope, self.loss_buf[0:1], f.dy_slot)
+        self._same = True
+        if self.world > 1:
+            ops.conv_wgrad_prepared(f.d, f.tr, f.x_slot, None, f.dw, f.ws_w)
+            self._flat = f.dw.view(-1)
+            return [f.dw]
+        ops.conv_wgrad_adam_sched(f.d, f.tr, f.x_slot, None, f.ws_w, m.weight.data, q.alpha.data, q.delta, q.zero_point,
+                                  self.exp_avg[0], self.exp_avg_sq[0], q.axis, q.n_levels, sched, reg_weight=self.weight,
+                                  reg_loss=self.loss_buf[2:3])
+        return []
 
     # -- one iteration ---------------------------------------------------------------------------------------
     def step(self, cur_inp: torch.Tensor, tgt: torch.Tensor, trace: Optional[dict] = None, sched=None, idx=None):
@@ -217,6 +290,8 @@ class UnitTrainer:
             self.count += 1
             b = self.temp_decay(self.count)
             reg_b = 0.0 if self.count < self.loss_start else float(b)
+        if not grads:                                # the fused tail already applied this iteration's Adam step
+            return
         if self.world > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
         for i, m in enumerate(self.mods):
@@ -264,6 +339,7 @@ class UnitTrainer:
         self._frozen = []
         for m in self.mods:
             m.weight_quantizer.soft_targets = False
+            m.invalidate_prepared()             # alpha was written by kernels: any operand cached before is stale
         marks = ([self.unit] if isinstance(self.unit, QuantModule) else
                  [m for _, m in self.unit.named_modules() if isinstance(m, (QuantModule, BaseQuantBlock))])
         for m in marks:
@@ -323,7 +399,13 @@ def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_siz
     tick = (trainer.iters, trainer.loss_start / trainer.iters if trainer.iters else 0.0, trainer.temp_decay.start_b,
             trainer.temp_decay.end_b, trainer.lr)
 
+    fused = trainer.fused_plan(q_in.shape[1:], batch_size) if table.size(1) == batch_size else None
+
     def body():
+        if fused is not None:
+            grads = trainer.fused_compute(fused, q_in, fp_in, cached_outs, table, 1, 0, sched, input_prob, seed_base)
+            trainer.step_update(grads, sched=sched)
+            return
         cur_inp = ops.gather_mix_sched(q_in, fp_in, table, batch_size, input_prob, seed_base, 1, 0, sched)
         tgt = ops.gather_mix_sched(cached_outs, cached_outs, table, batch_size, 1.0, seed_base, 1, 0, sched)
         trainer.step(cur_inp, tgt, sched=sched)

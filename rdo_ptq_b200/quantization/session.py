@@ -300,6 +300,16 @@ class CalibrationSession:
     def _compute(self, j, name):
         """pick + QDrop -> soft weights -> forward -> loss -> wgrad; leaves the unit's dL/dWq in self._grads[name]."""
         U, bs = len(self.units), self.batch_size
+        t = self.trainers[name]
+        src = self._stage[name] if self.host else self.caches[name]
+        fused = t.fused_plan(src[0].shape[1:], bs)
+        if fused is not None:
+            # prepared-operand iteration: pick + QDrop -> staged operand, quantiser -> packed weight, GEMM, loss -> staged
+            # dY, wgrad (+ Adam tail at world size 1); host / streaming modes hold the batch rows already (identity pick)
+            table = None if self.host else self._perm_dev
+            self._grads[name] = t.fused_compute(fused, src[0], src[1], src[2], table, U, j, self.sched, self.input_prob,
+                                                self.seed_base)
+            return
         if self.host:
             qi, fi, tgt = self._stage[name]
             cur = ops.gather_mix_sched(qi, fi, None, bs, self.input_prob, self.seed_base, U, j, self.sched)

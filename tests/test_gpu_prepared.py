@@ -1,0 +1,297 @@
+"""GPU: the prepared-operand entry points (include/b200lic.h, "Prepared operands") against the un-fused kernels they
+replace.  Every comparison is BIT-EXACT (`torch.equal`): the fused kernels restate the same arithmetic in the same
+order, they only skip the round trips through HBM -- so all parity results of the un-fused path carry over."""
+import ctypes as C
+
+import pytest
+import torch
+
+from rdo_ptq_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(dev):
+    from rdo_ptq_b200 import ops as _ops
+    return _ops
+
+
+def _layer(ops, dev, transposed, N=2, Cin=64, Cout=96, H=20, W=24, k=5, st=2, act=0, seed=0):
+    g = torch.Generator().manual_seed(1005 + seed)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    wshape = (Cin, Cout, k, k) if transposed else (Cout, Cin, k, k)
+    w = (torch.randn(wshape, generator=g) * 0.05).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    d = ops.conv_desc(x.shape, w.shape, st, k // 2, transposed, st - 1 if transposed else 0, act=act, slope=0.01)
+    return x, w, b, d
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("mode", ["nearest", "soft", "hard", "integer"])
+def test_quant_pack_equals_quantiser_then_pack(ops, dev, transposed, mode):
+    x, w, b, d = _layer(ops, dev, transposed)
+    axis = 1 if transposed else 0
+    delta, zp = ops.wq_init_minmax(w, axis, 8)
+    alpha = ops.adaround_init_alpha(w, delta, axis) + torch.randn_like(w)
+    if mode == "nearest":
+        ref_w = ops.wq_fake_quant(w, delta, zp, axis, 256)
+        packed = ops.quant_pack_weights(w, None, delta, zp, axis, 256, False, d, transposed)
+    elif mode == "integer":
+        ref_w = ops.wq_int_weights(w, delta, zp, axis, 256, alpha)
+        packed = ops.quant_pack_weights(w, alpha, delta, zp, axis, 256, False, d, transposed, integer_mode=True)
+    else:
+        ref_w = ops.adaround_fwd(w, alpha, delta, zp, axis, 256, mode == "soft")
+        w_q = torch.empty_like(w)
+        packed = ops.quant_pack_weights(w, alpha, delta, zp, axis, 256, mode == "soft", d, transposed, w_q=w_q)
+        assert torch.equal(w_q, ref_w)
+    ref = ops.pack_weights(ref_w, d, transposed)
+    n = packed.numel() // 2 if mode == "integer" else packed.numel()      # integer mode: hi slab only
+    assert torch.equal(packed[:n], ref[:n])
+    # and the forward through the prepared operand equals the plain forward on the quantised weight
+    if mode == "integer":
+        scale = delta.reshape(-1).contiguous()
+        y = ops.conv_fwd_packed(x, packed, d, transposed, bias=b, w_scale=scale)
+        y_ref = ops.conv_wq(x, ref_w, scale, b, stride=d.stride, padding=d.pad, output_padding=d.stride - 1 if transposed
+                            else 0, transposed=transposed)
+    else:
+        y = ops.conv_fwd_packed(x, packed, d, transposed, bias=b)
+        y_ref = ops.deconv2d_raw(x, ref_w, b, d) if transposed else ops.conv2d_raw(x, ref_w, b, d)
+    assert torch.equal(y, y_ref)
+
+
+def test_gdn_forward_with_prepared_gamma(ops, dev):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 64, 16, 24, generator=g).to(dev)
+    gam = (torch.rand(64, 64, generator=g) * 0.01 + 0.1 * torch.eye(64)).to(dev)
+    bet = (1 + torch.rand(64, generator=g)).to(dev)
+    for inverse in (False, True):
+        d = ops.gdn_desc(x.shape, inverse)
+        y_ref, n_ref = ops.conv2d_raw(x, gam.view(64, 64, 1, 1), bet, d, gdn_x=x, want_norm=True)
+        packed = ops.pack_weights(gam.view(64, 64, 1, 1), d, False)
+        y, n = ops.conv_fwd_packed(x, packed, d, False, bias=bet, gdn_x=x, want_norm=True)
+        assert torch.equal(y, y_ref) and torch.equal(n, n_ref)
+
+
+@pytest.mark.parametrize("transposed,Cin", [(False, 64), (True, 64), (False, 96)])
+@pytest.mark.parametrize("prob", [0.5, 1.0])
+def test_stage_mix_equals_gather_mix_then_split(ops, dev, transposed, Cin, prob):
+    """pick + QDrop straight into the staged operand == gather_mix_sched -> fp32 batch -> NHWC split (forward and
+    weight gradient consume the staged operand; 96 channels: the forward pads to 96, the wgrad engine to 128)."""
+    x, w, b, d = _layer(ops, dev, transposed, N=4, Cin=Cin)
+    g = torch.Generator().manual_seed(3)
+    pool_q = torch.randn(6, *x.shape[1:], generator=g).to(dev)
+    pool_f = torch.randn(6, *x.shape[1:], generator=g).to(dev)
+    table = torch.stack([torch.randperm(6, generator=g)[:4] for _ in range(5)]).to(dev)
+    sched = ops.new_sched(dev)
+    for _ in range(3):
+        ops.sched_tick(sched, 100, 0.2, 20, 2)
+    cur = ops.gather_mix_sched(pool_q, pool_f, table, 4, prob, 12345, 7, 2, sched)
+    y_ref, fwd_ws = (ops.deconv2d_raw if transposed else ops.conv2d_raw)(cur, w, b, d, want_ws=True)
+    ws = ops._workspace(d, ops.fwd_op(transposed), dev)
+    slot = ops.conv_x_slot(d, transposed, ws)
+    assert slot is not None and slot[2] == (Cin + 31) // 32 * 32
+    out = torch.empty_like(cur)
+    ops.stage_mix_sched(pool_q, pool_f, table, 4, prob, 12345, 7, 2, sched, slot, out=out)
+    assert torch.equal(out, cur)
+    packed = ops.pack_weights(w, d, transposed)
+    y = ops.conv_fwd_packed(None, packed, d, transposed, bias=b, ws=ws)
+    assert torch.equal(y, y_ref)
+    # weight gradient from the staged x (channel pitch = the forward's padding) == the plain weight gradient
+    dy = torch.randn(y.shape, generator=g).to(dev)
+    dw_ref = torch.empty_like(w)
+    ops._wgrad(d, transposed, cur, dy, dw_ref, (None, 0))
+    ws_w = ops._workspace(d, ops.wgrad_op(transposed), dev)
+    dw = torch.empty_like(w)
+    ops.conv_wgrad_prepared(d, transposed, slot, dy, dw, ws_w)
+    assert torch.equal(dw, dw_ref)
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("act", [0, 2])
+def test_loss_stage_and_fused_tail_equal_the_unfused_chain(ops, dev, transposed, act):
+    """loss + gradient -> staged dY -> wgrad -> (fused) STE / regulariser / Adam, against
+    lp_loss_fwd_bwd_sched -> act_bwd -> conv_wgrad -> adaround_bwd_adam_sched."""
+    x, w, b, d = _layer(ops, dev, transposed, N=4, act=act)
+    axis = 1 if transposed else 0
+    g = torch.Generator().manual_seed(11)
+    delta, zp = ops.wq_init_minmax(w, axis, 4)
+    alpha0 = ops.adaround_init_alpha(w, delta, axis) + torch.randn(w.shape, generator=g).to(dev)
+    sched = ops.new_sched(dev)
+    for _ in range(30):                                         # past the warm-up: the regulariser is on
+        ops.sched_tick(sched, 100, 0.2, 20, 2)
+    wq = ops.adaround_fwd(w, alpha0, delta, zp, axis, 16, True)
+    y, fwd_ws = (ops.deconv2d_raw if transposed else ops.conv2d_raw)(x, wq, b, d, want_ws=True)
+    tgt_pool = torch.randn(6, *y.shape[1:], generator=g).to(dev)
+    table = torch.stack([torch.randperm(6, generator=g)[:4] for _ in range(5)]).to(dev)
+    denom = y.numel() // y.shape[1]
+    # un-fused chain
+    loss_ref, dy = ops.lp_loss_fwd_bwd(y, tgt_pool, 2.0, 1.0 / denom, 2.0 / denom, pick=(table, 3, 1, sched))
+    if act:
+        dy = ops.act_bwd(y, dy, act, 0.01)
+    dw_ref = torch.empty_like(w)
+    ops._wgrad(d, transposed, x, dy, dw_ref, (None, 0))
+    a_ref, m_ref, v_ref = alpha0.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    reg_ref = torch.zeros(1, device=dev)
+    ops.adaround_bwd_adam_sched(w, a_ref, delta, zp, dw_ref, m_ref, v_ref, axis, 16, sched, reg_weight=0.01,
+                                reg_loss=reg_ref)
+    # fused chain
+    ws_f = ops._workspace(d, ops.fwd_op(transposed), dev)
+    x_slot = ops.conv_x_slot(d, transposed, ws_f)
+    ops.stage_mix_sched(x, x, None, 4, 1.0, 0, 1, 0, None, x_slot)
+    ws_w = ops._workspace(d, ops.wgrad_op(transposed), dev)
+    dy_slot = ops.conv_dy_slot(d, transposed, ws_w)
+    assert dy_slot is not None
+    loss = torch.zeros(1, device=dev)
+    d_pred = torch.empty_like(y)
+    ops.lp_loss_stage_sched(y, tgt_pool, table, 3, 1, sched, 2.0, 1.0 / denom, 2.0 / denom, act, 0.01, loss, dy_slot,
+                            d_pred=d_pred)
+    assert torch.equal(d_pred, dy)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())        # fp32 atomics: order of the partial sums
+    a, m, v = alpha0.clone(), torch.zeros_like(w), torch.zeros_like(w)
+    reg = torch.zeros(1, device=dev)
+    dw = torch.empty_like(w)
+    ops.conv_wgrad_adam_sched(d, transposed, x_slot, None, ws_w, w, a, delta, zp, m, v, axis, 16, sched, reg_weight=0.01,
+                              reg_loss=reg, dw_out=dw)
+    assert torch.equal(dw, dw_ref)
+    assert torch.equal(a, a_ref) and torch.equal(m, m_ref) and torch.equal(v, v_ref)
+    assert not torch.equal(a, alpha0)
+    assert abs(reg.item() - reg_ref.item()) <= 1e-5 * abs(reg_ref.item())
+
+
+def test_folded_tap_and_simt_layers_have_no_prepared_path(ops, dev):
+    x, w, b, d = _layer(ops, dev, False, Cin=3, Cout=32)                       # g_a.0-like: folded taps
+    assert ops.packed_weight_bytes(d, False) == 0 and ops.new_packed(d, False, dev) is None
+    ws = ops._workspace(d, ops.fwd_op(False), dev)
+    assert ops.conv_x_slot(d, False, ws) is None
+    x, w, b, d = _layer(ops, dev, False)
+    d.engine = ops.ENGINE_SIMT
+    assert ops.packed_weight_bytes(d, False) == 0
+
+
+def _session(dev, fused, host_caches=False):
+    from rdo_ptq_b200 import codec, quantization as Q
+    from rdo_ptq_b200.quantization import recon
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+    torch.manual_seed(1005)
+    m = codec.ARCHS["mbt2018-mean"](N=64, M=64).eval()
+    synth.init_weights(m, gain=1.2)
+    m.to(dev)
+    q = Q.QuantModel(m, dict(n_bits=4, channel_wise=True, scale_method="max"),
+                     dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)).eval()
+    cali = synth.calibration_patches(4, 64).to(dev)
+    old = recon.FUSED_DEFAULT
+    recon.FUSED_DEFAULT = fused
+    try:
+        s = CalibrationSession(q, cali.cpu() if host_caches == "stream" else cali, batch_size=2, iters=40, warmup=0.1,
+                               host_caches=host_caches, n_streams=1)
+    finally:
+        recon.FUSED_DEFAULT = old
+    return s, q
+
+
+@pytest.mark.parametrize("host_caches", [False, "stream"])
+def test_fused_calibration_iteration_is_bit_identical(dev, host_caches):
+    """The whole session, fused against un-fused, 8 sweeps (eager + graph replays, past the warm-up): alpha and the Adam
+    moments of every unit bit for bit; the fused plan is in use where it applies (12 of the 20 units of this codec)."""
+    sa, qa = _session(dev, True, host_caches)
+    sb, qb = _session(dev, False, host_caches)
+    for _ in range(8):
+        sa.sweep()
+        sb.sweep()
+    torch.cuda.synchronize()
+    n_fused = sum(1 for t in sa.trainers.values() if t._fused_plan not in (False, None))
+    print(f"fused units: {n_fused} of {len(sa.trainers)}")
+    assert n_fused >= 9 and all(t._fused_plan in (False, None) for t in sb.trainers.values())
+    for n in sa.trainers:
+        ta, tb = sa.trainers[n], sb.trainers[n]
+        for ma, mb in zip(ta.mods, tb.mods):
+            assert torch.equal(ma.weight_quantizer.alpha.data, mb.weight_quantizer.alpha.data), n
+        for a, b in zip(ta.exp_avg + ta.exp_avg_sq, tb.exp_avg + tb.exp_avg_sq):
+            assert torch.equal(a, b), n
+    la, lb = sa.losses(), sb.losses()
+    for n in la:
+        assert la[n]["rec"] == pytest.approx(lb[n]["rec"], rel=1e-4, abs=1e-9), n
+        assert la[n]["round"] == pytest.approx(lb[n]["round"], rel=1e-4, abs=1e-9), n
+
+
+def test_evaluation_forward_reuses_the_prepared_weights(dev):
+    """QuantModule keeps the packed weight operand while nothing it depends on changes: the second forward launches no
+    weight kernel, results equal the first forward bit for bit, and a change of alpha rebuilds the operand."""
+    from rdo_ptq_b200 import _lib, codec, quantization as Q
+    torch.manual_seed(1005)
+    m = codec.ARCHS["mbt2018-mean"](N=64, M=64).eval()
+    synth.init_weights(m, gain=1.2)
+    m.to(dev)
+    q = Q.QuantModel(m, dict(n_bits=8, channel_wise=True, scale_method="max"),
+                     dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)).eval()
+    x = synth.synthetic_image(64, 96).to(dev)
+    q.set_quant_state(True, False)
+    with torch.no_grad():
+        q(x)                                                      # initialises the ranges (general path)
+        n0 = _lib.launch_count()
+        a = q(x)["x_hat"].clone()                                 # builds the prepared operands
+        n1 = _lib.launch_count()
+        b = q(x)["x_hat"].clone()                                 # reuses them
+        n2 = _lib.launch_count()
+    assert torch.equal(a, b)
+    mods = [mm for mm in q.modules() if isinstance(mm, Q.QuantModule) and mm.org_weight is not None]
+    n_prep = sum(1 for mm in mods if mm.__dict__.get("_prep", {}).get(True, (None, None))[1] is not None)
+    assert n_prep >= 14
+    assert (n2 - n1) <= (n1 - n0) - n_prep                        # at least one weight kernel per prepared layer is gone
+    # against the un-prepared path (gradient enabled => general path): same values up to the two-pass / three-pass split
+    q2 = q.model.g_a[2]
+    xin = torch.randn(1, 64, 16, 24, device=dev)
+    with torch.no_grad():
+        y_prep = q2(xin)
+    y_gen = q2(xin.requires_grad_(True)).detach()
+    assert ((y_prep - y_gen).norm() / y_gen.norm()).item() < 1e-5
+    # AdaRound: hard weights are cached, a changed alpha invalidates the cache
+    q2.weight_quantizer = Q.AdaRoundQuantizer(q2.weight_quantizer, q2.org_weight.data, round_mode="learned_hard_sigmoid")
+    with torch.no_grad():
+        y1 = q2(xin.detach()).clone()
+        q2.weight_quantizer.alpha.neg_()                  # in-place op on the Parameter: its version counter moves
+        y2 = q2(xin.detach()).clone()
+        q2.weight_quantizer.alpha.data.neg_()             # write through .data (like a kernel): invisible to the counter
+        q2.invalidate_prepared()
+        y3 = q2(xin.detach()).clone()
+    assert not torch.equal(y1, y2) and torch.equal(y1, y3)
+    assert "_prep" in q2.__dict__ and "_prep" not in q2.__getstate__()          # device scratch is not pickled
+
+
+@pytest.mark.parametrize("arch,kw", [("mbt2018-mean", dict(N=64, M=64)), ("bmshj2018-hyperprior", dict(N=64, M=64))])
+def test_deferred_activation_quantiser_is_bit_identical(dev, arch, kw):
+    """W8A8 evaluation forward with the dynamic activation quantiser of every QuantModule inside an nn.Sequential deferred
+    into its consumer's operand staging (ops.DEFER_ACTQ: statistics at the producer, actq_apply_stage at the consumer)
+    against the plain form (stats + apply at the producer, NHWC split at the consumer): same codes, so every output
+    tensor is bit-identical; fewer launches."""
+    from rdo_ptq_b200 import _lib, codec, ops, quantization as Q
+    torch.manual_seed(1005)
+    m = codec.ARCHS[arch](**kw).eval()
+    synth.init_weights(m, gain=1.2)
+    m.to(dev)
+    q = Q.QuantModel(m, dict(n_bits=8, channel_wise=True, scale_method="max"),
+                     dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)).eval()
+    x = synth.synthetic_image(128, 192).to(dev)
+    q.set_quant_state(True, False)
+    with torch.no_grad():
+        q(x)
+        for mm in q.modules():
+            if hasattr(mm, "trained"):
+                mm.trained = True
+        q.set_quant_state(True, True)
+        q.model.g_s[-1].set_quant_state(True, False)
+        q(x)                                                       # prepared weight operands exist from here on
+        n0 = _lib.launch_count()
+        plain = q(x)
+        n1 = _lib.launch_count()
+        with ops.defer_actq():
+            deferred = q(x)
+        n2 = _lib.launch_count()
+    linked = sum(1 for mm in q.modules() if isinstance(mm, Q.QuantModule) and "_defer_to" in mm.__dict__)
+    assert linked >= 14
+    assert torch.equal(plain["x_hat"], deferred["x_hat"])
+    assert torch.equal(plain["likelihoods"]["y"], deferred["likelihoods"]["y"])
+    assert torch.equal(plain["likelihoods"]["z"], deferred["likelihoods"]["z"])
+    assert getattr(deferred["x_hat"], "_b200_actq", None) is None          # nothing pending leaves the model
+    assert (n2 - n1) < (n1 - n0)
