@@ -62,6 +62,10 @@ B200LIC_API int b200lic_device_check(void);
 /* Debug aid: with B200LIC_TC_DEBUG=3 in the environment the tensor-core conv kernel records a %globaltimer timeline
  * (ns) of CTA 0's first work item; this copies up to 128 stamps of the last launch to `out` (synchronises). */
 B200LIC_API int b200lic_debug_timeline(unsigned long long* out, int n);
+/* Scheduling knobs (A/B measurements, tests).  "streamk": 1 = stream-K scheduling of the conv engine where it pays
+ * (default), 0 = whole work items only, 2 = wherever the shape is eligible.  Results are identical up to fp32 summation
+ * order of the K ranges. */
+B200LIC_API int b200lic_set_option(const char* name, int value);
 /* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
 B200LIC_API unsigned long long b200lic_launch_count(void);
 
@@ -414,11 +418,16 @@ B200LIC_API int b200lic_stage_mix_sched(const float* q, const float* fp, const l
 /* b200lic_lp_loss_fwd_bwd_sched whose gradient leaves as the staged dY operand of the weight-gradient GEMM; d_pred (may
  * be NULL) additionally receives it as fp32 NCHW.  idx_table == NULL: tgt_cache is the target batch itself.  `act` is
  * the activation fused into the layer that produced `pred`: its derivative (b200lic_act_bwd, on the activation output)
- * is applied to the gradient, which is then the one the weight gradient needs. */
+ * is applied to the gradient, which is then the one the weight gradient needs.  For a GDN unit (f_gdn, TO quant_layer.py:142-154)
+ * pass its input gdn_x and the pre-(r)sqrt accumulator gdn_norm (both [rows,C,HW]; NULL otherwise): the gradient is then
+ * carried on to the accumulator, d_norm = dy * x * d(norm^-+1/2)/dnorm (b200lic_gdn_bwd_prep), the dY operand of gamma's
+ * weight gradient.  With gdn_x given, pred may be NULL: the unit's output x * norm^-+1/2 is then recomputed on the fly (the
+ * forward only has to produce the accumulator: a plain 1x1 convolution of x*x with bias beta). */
 B200LIC_API int b200lic_lp_loss_stage_sched(const float* pred, const float* tgt_cache, const long long* idx_table,
                                 int table_rows, int rows, int C, int HW, int units, int unit,
                                 const b200lic_calib_sched* sched, float p, float scale, float grad_scale, int act,
-                                float act_slope, float* loss, void* dy_hi, void* dy_lo, int cpad, float* d_pred,
+                                float act_slope, const float* gdn_x, const float* gdn_norm, int gdn_inverse,
+                                float* loss, void* dy_hi, void* dy_lo, int cpad, float* d_pred,
                                 b200lic_stream_t stream);
 /* b200lic_conv_wgrad_staged for an x operand staged with channel pitch x_cpad (the cpad b200lic_conv_x_slot reports:
  * any multiple of 32 >= Cin); dy == NULL: dY is already staged in the slot b200lic_conv_dy_slot reports. */

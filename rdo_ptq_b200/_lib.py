@@ -90,7 +90,7 @@ SIGNATURES = {
     "quant_pack_weights": [_D, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _P],
     "conv_fwd_packed": [_D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ],
     "stage_mix_sched": [_P, _P, _P, _I, _I, _I, _I, _F, _ULL, _I, _I, _P, _I, _P, _P, _I, _P],
-    "lp_loss_stage_sched": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _I, _F, _P, _P, _P, _I, _P],
+    "lp_loss_stage_sched": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _F, _I, _F, _P, _P, _I, _P, _P, _P, _I, _P],
     "conv_wgrad_prepared": [_D, _I, _P, _P, _I, _P, _P, _P, _SZ],
     "conv_wgrad_adam_sched": [_D, _I, _P, _P, _I, _P, _P, _SZ, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F,
                               _F, _F, _P, _P],
@@ -102,6 +102,7 @@ SIGNATURES = {
 PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
          "launch_count": (C.c_ulonglong, []), "factorized_table_floats": (C.c_int, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
          "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+         "set_option": (C.c_int, [C.c_char_p, C.c_int]),
          "conv_staged_view": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p)]),
          "conv_packed_weight_bytes": (C.c_size_t, [_D, C.c_int]),

@@ -60,10 +60,21 @@ int num_sms() {
 
 }  // namespace b200lic
 
-namespace b200lic { int tc2_debug_timeline(unsigned long long* out, int n); }
+namespace b200lic {
+int tc2_debug_timeline(unsigned long long* out, int n);
+void tc2_set_streamk_mode(int v);
+}
 extern "C" {
+int b200lic_set_option(const char* name, int value) {
+  if (name && strcmp(name, "streamk") == 0) {
+    b200lic::tc2_set_streamk_mode(value);
+    return B200LIC_OK;
+  }
+  b200lic::set_error("set_option: unknown option '%s'", name ? name : "(null)");
+  return B200LIC_ERR_ARG;
+}
 int b200lic_debug_timeline(unsigned long long* out, int n) { return b200lic::tc2_debug_timeline(out, n); }
-int b200lic_version(void) { return 100; }
+int b200lic_version(void) { return 200; }
 const char* b200lic_last_error_string(void) { return b200lic::g_err; }
 int b200lic_device_check(void) { return b200lic::check_arch(); }
 unsigned long long b200lic_launch_count(void) { return b200lic::g_launches.load(); }

@@ -200,6 +200,51 @@ struct Tc2Geom {
   int chunk;                  // epilogue chunk width in channels (16 or 32)
   int epi_warps;              // 4, or 8 (two warps per TMEM lane quarter) when the epilogue outweighs the K loop
   int dbg_mode;               // 0 normal; 1 = skip the MMAs; 2 = skip the TMA loads (bottleneck experiments only)
+  int sk;                     // stream-K: every CTA takes one contiguous range of (item, K block) units (see SegIter)
+  int sk_len;                 // units per CTA
+  long long sk_total;         // items x K blocks per item
+};
+
+// Work of one CTA.  Default: whole items, strided over the grid.  Stream-K (g.sk): the K loops of all items are laid end to
+// end and every CTA takes sk_len consecutive K blocks of that line, so 128 equal items load 148 SMs evenly (each
+// item's K range is then shared by two or three CTAs) and a layer with a handful of pixel tiles spreads ITS K loop over
+// the chip instead of shrinking the tile width.  A CTA's first segment may be the inner / tail part of an item that
+// started in an earlier CTA: it dumps that partial accumulator to scratch and signals; the CTA holding the HEAD of an
+// item owns its epilogue and adds the partials of the CTAs after it (which computed them first thing, so nobody waits on
+// work that waits on them).
+struct SegIter {
+  int sk, step, total_items, nkb, w;
+  long long pos, end;
+  __device__ __forceinline__ void init(const Tc2Geom& g, int total_items_, int nkb_) {
+    sk = g.sk;
+    step = (int)gridDim.x;
+    total_items = total_items_;
+    nkb = nkb_;
+    w = (int)blockIdx.x;
+    pos = (long long)blockIdx.x * g.sk_len;
+    end = pos + g.sk_len;
+    if (end > g.sk_total) end = g.sk_total;
+  }
+  // kb_hi = -1: the item's whole K range
+  __device__ __forceinline__ bool next(int& item, int& kb_lo, int& kb_hi) {
+    if (!sk) {
+      if (w >= total_items) return false;
+      item = w;
+      kb_lo = 0;
+      kb_hi = -1;
+      w += step;
+      return true;
+    }
+    if (pos >= end) return false;
+    item = (int)(pos / nkb);
+    kb_lo = (int)(pos - (long long)item * nkb);
+    const long long rem = end - pos;
+    const int room = nkb - kb_lo;
+    const int take = rem < (long long)room ? (int)rem : room;
+    kb_hi = kb_lo + take;
+    pos += take;
+    return true;
+  }
 };
 
 constexpr int kT2Threads = 320;        // TMA warp, MMA warp, up to 8 epilogue warps (launched: 64 + 32 * epi_warps)
@@ -237,7 +282,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
                            const __grid_constant__ CUtensorMap map_n, Tc2Geom g, const float* __restrict__ bias,
                            const float* __restrict__ w_scale, const float* __restrict__ gdn_x,
-                           float* __restrict__ norm_out, float* __restrict__ y, unsigned long long* __restrict__ dbg) {
+                           float* __restrict__ norm_out, float* __restrict__ y, unsigned long long* __restrict__ dbg,
+                           float* __restrict__ sk_part, unsigned* __restrict__ sk_cnt) {
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -298,7 +344,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bh)) : "memory");
       int s = 0;
       uint32_t sphase = 0;
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      SegIter it;
+      it.init(g, total_items, g.KH * g.KW * cblocks);
+      int w, kb_lo, kb_hi;
+      while (it.next(w, kb_lo, kb_hi)) {
         const int rest = w / g.phases, phase = (w + rest) % g.phases;   // rotate: a CTA's items cycle through the phases
         const int n_tile = rest % g.n_tiles, mg = rest / g.n_tiles;
         const PhaseGeom q = phase_geom(g, phase);
@@ -307,6 +356,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
         if (mg * g.MT >= m_tiles) continue;
         const int num_kb = q.KHp * q.KWp * cblocks;
+        const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
         int wb[2], hb[2], nb[2];
         for (int t = 0; t < g.MT; ++t) {
           int mt = mg * g.MT + t;
@@ -317,7 +367,13 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           nb[t] = tn * g.BI;
         }
         int cb = 0, i = 0, j = 0;          // channel block, tap row, tap column of K block kb (no divisions in the loop)
-        for (int kb = 0; kb < num_kb; ++kb) {
+        if (kb_lo > 0) {
+          const int t0 = kb_lo / cblocks;
+          cb = kb_lo - t0 * cblocks;
+          i = t0 / q.KWp;
+          j = t0 - i * q.KWp;
+        }
+        for (int kb = kb_lo; kb < kb_end; ++kb) {
           mbar_wait(empty_bar + 8u * s, sphase ^ 1u);
           const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t fb = full_bar + 8u * s;
@@ -371,7 +427,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       const uint64_t b_desc0 = make_kmajor_sw64_desc(smem_base + (uint32_t)g.MT * 2u * kA2Bytes);
       const uint64_t b_lo_off = (uint64_t)(b_tile_bytes >> 4);
       const int variant = g.w_exact ? 6 + (g.MT - 1) : (g.MT - 1) * 3 + (g.chains - 1);
-      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      SegIter it;
+      it.init(g, total_items, g.KH * g.KW * cblocks);
+      int w, kb_lo, kb_hi;
+      while (it.next(w, kb_lo, kb_hi)) {
         const int rest = w / g.phases, phase = (w + rest) % g.phases;   // rotate: a CTA's items cycle through the phases
         const int mg = rest / g.n_tiles;
         const PhaseGeom q = phase_geom(g, phase);
@@ -381,6 +440,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         if (mg * g.MT >= m_tiles) continue;
         const int num_kb = q.KHp * q.KWp * cblocks;
         if (num_kb == 0) continue;                       // nothing to accumulate: the epilogue writes bias only
+        const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
         // the epilogue must have drained this accumulator set (first use of a set passes immediately)
         mbar_wait(tempty_bar + 8u * set, set_phase[set] ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -388,14 +448,14 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         uint32_t accs[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) accs[i] = acc0 + (uint32_t)(i * g.BN);    // tile i = mt * chains + chain
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo; kb < kb_end; ++kb) {
           mbar_wait(full_bar + 8u * s, sphase);
           if (trace && w == 0 && kb == 0) dbg[100] = gtime();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (g.dbg_mode != 1) {
             const uint64_t sd = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
             const uint64_t a0 = a_desc0 + sd, b0 = b_desc0 + sd;
-            const bool first = kb == 0;
+            const bool first = kb == kb_lo;
             switch (variant) {               // uniform branch; each arm is straight-line code
               case 6: issue_kblock<1, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
               case 7: issue_kblock<2, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
@@ -445,7 +505,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     uint32_t xk_issued = 0, xk_used = 0;    // GDN x chunks requested / consumed (slot = k % NX, parity = (k / NX) & 1)
     const uint32_t NX = (uint32_t)(g.x_slots > 0 ? g.x_slots : 1);
     int bias_base = -1;                     // n-tile whose bias currently sits in sBias
-    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+    const size_t sk_slot = (size_t)g.MT * 128 * g.BN;        // floats of one CTA's partial-accumulator slot
+    SegIter it;
+    it.init(g, total_items, g.KH * g.KW * cblocks);
+    int w, kb_lo, kb_hi;
+    while (it.next(w, kb_lo, kb_hi)) {
       const int rest = w / g.phases, phase = (w + rest) % g.phases;
       const int n_tile = rest % g.n_tiles, mg = rest / g.n_tiles;
       const PhaseGeom q = phase_geom(g, phase);
@@ -454,11 +518,42 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
       if (mg * g.MT >= m_tiles) continue;
       const int num_kb = q.KHp * q.KWp * cblocks;
+      const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
       const int co_base = n_tile * g.BN;
       const int n_chunks = g.BN / CH;
       // chunks of this item, in processing order: (tile t, chunk c); count only valid tiles
       int vt = 0;
       for (int t = 0; t < g.MT; ++t) vt += (mg * g.MT + t < m_tiles) ? 1 : 0;
+      if (g.sk && kb_lo > 0) {
+        // ---- stream-K contributor: this CTA holds an inner / tail part of item w; its owner is an earlier CTA --------
+        mbar_wait_backoff(tfull_bar + 8u * set, set_phase[set]);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc_c = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * set_cols);
+        float* slot = sk_part + (size_t)blockIdx.x * sk_slot;
+        for (int t = 0; t < vt; ++t) {
+          for (int c = grp * 16; c < g.BN; c += h_step) {
+            uint32_t v[16];
+            tmem_ld16(acc_c + (uint32_t)(t * g.chains * g.BN + c), v);
+            tmem_wait_ld16(v);
+            float4* dst = reinterpret_cast<float4*>(slot + ((size_t)t * 128 + m) * g.BN + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+          }
+        }
+        __threadfence();
+        epi_bar(1, epi_threads);
+        if (et == 0) atomicAdd(sk_cnt + w, 1u);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8u * set);
+        set_phase[set] ^= 1u;
+        if (g.acc_sets == 2) set ^= 1;
+        continue;
+      }
+      // stream-K owner of an item whose K range continues in the next n_contrib CTAs
+      const int n_contrib = (g.sk && kb_end < num_kb) ? (num_kb - kb_end + g.sk_len - 1) / g.sk_len : 0;
       const uint32_t item_chunks = (uint32_t)(vt * n_chunks);
       auto chunk_coords = [&](uint32_t ci, int& b0, int& a0, int& n0, int& c0) {
         const int t = (int)ci / n_chunks;
@@ -505,6 +600,16 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       if (tr) dbg[1] = gtime();
+      if (n_contrib > 0) {                    // the contributors' partial accumulators are complete and visible
+        if (et == 0) {
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sk_cnt + w) : "memory");
+            if (seen < (unsigned)n_contrib) __nanosleep(64);
+          } while (seen < (unsigned)n_contrib);
+        }
+        epi_bar(3, epi_threads);
+      }
       const uint32_t acc0 = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(set * set_cols);
       for (uint32_t ci = 0; ci < item_chunks; ++ci) {
         int b0, a0, n0, c0;
@@ -565,6 +670,18 @@ __global__ void __launch_bounds__(kT2Threads, 1)
               tmem_wait_ld16(u);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+            for (int k = 1; k <= n_contrib; ++k) {       // stream-K: the later K ranges of this item, in CTA order
+              const float4* src = reinterpret_cast<const float4*>(sk_part + (size_t)(blockIdx.x + k) * sk_slot +
+                                                                  ((size_t)t * 128 + m) * g.BN + c0 + h);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 u = __ldcg(src + j);
+                v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + u.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + u.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + u.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + u.w);
+              }
             }
           } else {
 #pragma unroll
@@ -704,7 +821,9 @@ struct Tc2Plan {
   bool ok = false;
   int Cpad, CoutPad, Tmax, phases, BN, n_tiles, BW, BH, BI, MT, m_tiles, m_groups, stages, acc_sets, tmem_cols;
   int tma_out, epi_smem, x_slots, chunk, chains, epi_warps;
-  size_t x_bytes, b_bytes, total_bytes, smem_bytes;
+  int sk, sk_len, sk_grid;
+  long long sk_total;
+  size_t x_bytes, b_bytes, total_bytes, smem_bytes, sk_bytes, sk_cnt_bytes;
 };
 
 // Layout of the packed weight operand: [phase][CoutPad][Tmax * Cpad] bf16, hi slab then lo slab (b_bytes each).  It
@@ -728,6 +847,18 @@ bool tc2_weight_layout(int Cin, int Cout, int KH, int KW, int stride, int transp
   *b_bytes = ((size_t)*phases * *CoutPad * *Tmax * *Cpad * 2 + 1023) / 1024 * 1024;
   return true;
 }
+
+// Stream-K policy: 1 = where it pays (default), 0 = off, 2 = wherever eligible.  B200LIC_TC_STREAMK in the environment or
+// b200lic_set_option("streamk", v) (tests compare the two schedules in one process).
+static int g_streamk_mode = -1;
+int tc2_streamk_mode() {
+  if (g_streamk_mode < 0) {
+    const char* e = getenv("B200LIC_TC_STREAMK");
+    g_streamk_mode = e ? atoi(e) : 1;
+  }
+  return g_streamk_mode;
+}
+void tc2_set_streamk_mode(int v) { g_streamk_mode = v; }
 
 // written tensor [N,Cout,Ho,Wo]; gathered tensor [N,Cin,H,W]
 static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
@@ -782,6 +913,10 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   // fill the stage, the same bytes of all active CTAs at the L2 rate); pick the divisor of the padded channel count
   // that minimises waves x cost.
   const int sms = num_sms();
+  const int nkb_sk = KH * KW * (p.Cpad / 32);
+  const bool sk_ok = false;   // (tried: letting the tile-width model assume stream-K everywhere -- a one-tile layer then
+                              // spreads its K loop over 75 CTAs and the item's owner sums 74 partial tiles serially:
+                              // h_a.4 55 -> 718 us.  Stream-K is used for load balance only, see below.)
   {
     double best = 1e300;
     p.BN = bn_max;
@@ -797,8 +932,13 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
         continue;
       }
       const long long items = (long long)p.m_tiles * (p.CoutPad / bn) * p.phases;
-      const long long waves = (items + sms - 1) / sms;
-      const double active = (double)(items < sms ? items : sms);
+      double waves = (double)((items + sms - 1) / sms);
+      double active = (double)(items < sms ? items : sms);
+      if (sk_ok) {                      // stream-K spreads K blocks, not items: fractional waves, (almost) every SM busy
+        const long long units = items * nkb_sk;
+        active = (double)(units < sms ? units : sms);
+        waves = (double)((units + sms - 1) / sms) / (double)nkb_sk;
+      }
       // constants measured on B200 with scripts/bn_sweep.py / tc_timeline.py (profiles/README.md r1d)
       const double t_mma = 6.0 * 62.0 * bn / 192.0;                       // ns per K block: 6 MMAs, 62 ns each at N = 192
       const double bytes = 2.0 * kA2Bytes + 128.0 * bn;
@@ -806,7 +946,7 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
       const double t_l2 = active * bytes / 12000.0;                       // ~12 TB/s of L2 -> shared memory chip-wide
       double t = t_mma > t_fill ? t_mma : t_fill;
       if (t_l2 > t) t = t_l2;
-      const double cost = (double)waves * (t + 2.0);                      // +2 ns: ties go to the wider tile
+      const double cost = waves * (t + 2.0);                              // +2 ns: ties go to the wider tile
       if (cost < best) {
         best = cost;
         p.BN = bn;
@@ -843,6 +983,39 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   p.acc_sets = (2 * p.MT * p.chains * p.BN <= 512) ? 2 : 1;
   p.tmem_cols = pow2_ceil2(p.acc_sets * p.MT * p.chains * p.BN);
   if (p.tmem_cols < 32) p.tmem_cols = 32;
+  // Stream-K (see SegIter): plain convolutions whose items all have the same K loop, for LOAD BALANCE only: 128 items of
+  // two pixel tiles on 148 SMs leave 13.5 % of the machine idle.  The stream-K form runs ONE pixel tile per item (the
+  // accumulator sets are then double-buffered, so dumping a partial tile overlaps the next K range) and is taken when it
+  // saves >= 8 % of the K blocks on the busiest SM while no item is cut into more than three ranges (the owner adds the
+  // other ranges' partial tiles serially).
+  p.sk = 0;
+  p.sk_len = 0;
+  p.sk_total = 0;
+  p.sk_grid = 0;
+  p.sk_bytes = p.sk_cnt_bytes = 0;
+  {
+    const int sk_env = tc2_streamk_mode();
+    const int nkb = KH * KW * (p.Cpad / 32);
+    const long long items1 = (long long)p.phases * p.n_tiles * p.m_tiles;           // one pixel tile per item
+    if (sk_env > 0 && !transposed && !gdn_mode && p.chains == 1 && nkb >= 8 && 2 * p.BN <= 512) {
+      const long long total = items1 * nkb;
+      const int grid = (int)(total < sms ? total : sms);
+      const long long len = (total + grid - 1) / grid;
+      const long long items_now = (long long)p.phases * p.n_tiles * p.m_groups;
+      const long long whole = ((items_now + sms - 1) / sms) * nkb * p.MT;            // busiest SM today, in 1-tile K blocks
+      if ((sk_env == 2 || (double)whole >= 1.08 * (double)len) && 2 * len >= nkb) {
+        p.sk = 1;
+        p.MT = 1;
+        p.m_groups = p.m_tiles;
+        p.acc_sets = 2;
+        p.tmem_cols = pow2_ceil2(2 * p.BN);
+        if (p.tmem_cols < 32) p.tmem_cols = 32;
+        p.sk_len = (int)len;
+        p.sk_total = total;
+        p.sk_grid = (int)((total + len - 1) / len);
+      }
+    }
+  }
   // conv-type outputs with 16-byte aligned rows leave by TMA store
   p.tma_out = (!transposed && (Wo % 4) == 0) ? 1 : 0;
   p.epi_smem = p.tma_out;
@@ -887,6 +1060,11 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
       return p;                                   // never: both follow the same rules (keeps them from drifting apart)
   }
   p.total_bytes = 2 * p.x_bytes + 2 * p.b_bytes + 1024;
+  if (p.sk) {
+    p.sk_bytes = ((size_t)p.sk_grid * p.MT * 128 * p.BN * sizeof(float) + 1023) / 1024 * 1024;
+    p.sk_cnt_bytes = ((size_t)p.phases * p.n_tiles * p.m_groups * sizeof(unsigned) + 1023) / 1024 * 1024;
+    p.total_bytes += p.sk_bytes + p.sk_cnt_bytes;
+  }
   p.ok = true;
   return p;
 }
@@ -1033,7 +1211,7 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
             p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, w_scale ? 1 : p.chains, w_scale ? 1 : 0, act, slope, gdn_mode, fixed_point,
-            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode};
+            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode, p.sk, p.sk_len, p.sk_total};
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc2_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1052,9 +1230,20 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   }
   const long long items = (long long)p.phases * p.n_tiles * p.m_groups;
   const int sms = num_sms();
-  const int grid = (int)(items < sms ? items : sms);
+  int grid = (int)(items < sms ? items : sms);
+  float* sk_part = nullptr;
+  unsigned* sk_cnt = nullptr;
+  if (p.sk) {
+    grid = p.sk_grid;
+    sk_part = reinterpret_cast<float*>(ws + 2 * p.x_bytes + 2 * p.b_bytes);
+    sk_cnt = reinterpret_cast<unsigned*>(ws + 2 * p.x_bytes + 2 * p.b_bytes + p.sk_bytes);
+    if (cudaMemsetAsync(sk_cnt, 0, (size_t)items * sizeof(unsigned), s) != cudaSuccess) {
+      set_error("%s: cannot reset the stream-K counters", name);
+      return B200LIC_ERR_CUDA;
+    }
+  }
   tc2_gather_gemm_kernel<<<grid, 64 + 32 * p.epi_warps, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
-                                                                norm_out, y, dbg);
+                                                                norm_out, y, dbg, sk_part, sk_cnt);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

@@ -293,12 +293,88 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   }
 }
 
-// dW[cs][cb][tap] = sum over splits of part[split][tap][cs][cb]; fixed summation order (deterministic).
+// dW[cs][cb][tap] = sum over splits of part[split][tap][cs][cb]; fixed summation order (deterministic): slab z goes
+// to accumulator z % 4 (a trailing group of fewer than four slabs to accumulator 0), result (a0 + a1) + (a2 + a3).
+// The slabs are L2-resident and the kernel is bound by load latency, so every thread takes four consecutive elements
+// (one 16-byte load per slab) and issues the loads of eight slabs before the first add.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int splits, int T, int Cs, int Cb,
                                                             float* __restrict__ dw) {
   const size_t per = (size_t)T * Cs * Cb;
+  auto store = [&](size_t i, float acc) {
+    const int cb = (int)(i % Cb);
+    const size_t r = i / Cb;
+    const int cs = (int)(r % Cs), t = (int)(r / Cs);
+    dw[((size_t)cs * Cb + cb) * T + t] = acc;
+  };
+  if (splits > 32 && (per & 3) == 0 && (((uintptr_t)part) & 15) == 0) {
+    // Many slabs of a small weight (GDN's 192 x 192 gamma: 147 slabs): one WARP per group of four elements, lane l sums
+    // the slabs z = l, l + 32, ... in increasing order, the lanes are combined by a fixed butterfly (xor 16, 8, 4, 2, 1).
+    // A thread per element would leave a few dozen CTAs walking 147 dependent loads each.
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i4 < (per >> 2); i4 += warps) {
+      const float* p = part + (i4 << 2);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int z = lane; z < splits; z += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)z * per));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+      }
+      if (lane == 0) {
+        const size_t i = i4 << 2;
+        store(i, a.x);
+        store(i + 1, a.y);
+        store(i + 2, a.z);
+        store(i + 3, a.w);
+      }
+    }
+    return;
+  }
+  if ((per & 3) == 0 && (((uintptr_t)part) & 15) == 0) {
+    for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < (per >> 2); i4 += (size_t)gridDim.x * blockDim.x) {
+      const float* p = part + (i4 << 2);
+      float4 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int z = 0;
+      for (; z + 7 < splits; z += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(p + (size_t)(z + k) * per));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a[k & 3].x += v[k].x; a[k & 3].y += v[k].y; a[k & 3].z += v[k].z; a[k & 3].w += v[k].w;
+        }
+      }
+      for (; z + 3 < splits; z += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(p + (size_t)(z + k) * per));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[k].x += v[k].x; a[k].y += v[k].y; a[k].z += v[k].z; a[k].w += v[k].w;
+        }
+      }
+      for (; z < splits; ++z) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)z * per));
+        a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+      }
+      const size_t i = i4 << 2;
+      store(i, (a[0].x + a[1].x) + (a[2].x + a[3].x));
+      store(i + 1, (a[0].y + a[1].y) + (a[2].y + a[3].y));
+      store(i + 2, (a[0].z + a[1].z) + (a[2].z + a[3].z));
+      store(i + 3, (a[0].w + a[1].w) + (a[2].w + a[3].w));
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four loads in flight; the order of additions is fixed
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int z = 0;
     for (; z + 3 < splits; z += 4) {
       a0 += __ldg(part + (size_t)z * per + i);
@@ -307,11 +383,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
       a3 += __ldg(part + (size_t)(z + 3) * per + i);
     }
     for (; z < splits; ++z) a0 += __ldg(part + (size_t)z * per + i);
-    const float acc = (a0 + a1) + (a2 + a3);
-    const int cb = (int)(i % Cb);
-    const size_t r = i / Cb;
-    const int cs = (int)(r % Cs), t = (int)(r / Cs);
-    dw[((size_t)cs * Cb + cb) * T + t] = acc;
+    store(i, (a0 + a1) + (a2 + a3));
   }
 }
 
@@ -347,8 +419,12 @@ static WgPlan make_wg_plan(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb
   p.units = (TT + kBoxesA - 1) / kBoxesA;
   p.ktiles = ((Ws + p.BW - 1) / p.BW) * ((Hs + p.BH - 1) / p.BH) * ((N + p.BI - 1) / p.BI);
   const int ctas = p.units * p.n_tiles;
-  // split-K so that the grid fills two rounds of the SMs without spilling into a third, nearly empty one
-  int want = (2 * num_sms()) / ctas;
+  // split-K so that the grid fills the SMs: ONE round when that already uses >= 95 % of them (few CTAs per split set,
+  // e.g. GDN's single 192 x 192 tile: every extra split is another 147 KB slab for the reduction to read), else two
+  // rounds without spilling into a third, nearly empty one
+  const int sms_ = num_sms();
+  int want = (2 * sms_) / ctas;
+  if (sms_ / ctas >= 1 && (double)((sms_ / ctas) * ctas) >= 0.95 * sms_) want = sms_ / ctas;
   int max_splits = (p.ktiles + 3) / 4;            // >= 4 pixel tiles per split
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
@@ -458,9 +534,13 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
   dim3 grid(p.units, p.n_tiles, p.splits);
   tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mb, ms, g, part);
   B200_LAUNCH_CHECK(name);
-  if (tail != nullptr) return launch_wgrad_reduce_adam(part, p.splits, KH * KW, Cs, Cb, tail, s);
+  if (tail != nullptr) return launch_wgrad_reduce_adam(part, p.splits, KH * KW, Cs, Cb, tail, s);   // (any split count:
+  // the fused tail always sums in the serial order; with > 32 slabs it differs from wgrad_reduce_kernel's butterfly in the
+  // last bits only)
   const size_t per = (size_t)KH * KW * Cs * Cb;
-  wgrad_reduce_kernel<<<grid_for(per, 256), 256, 0, s>>>(part, p.splits, KH * KW, Cs, Cb, dw);
+  // one thread (splits <= 32) or one warp (more slabs) per four elements
+  const size_t red_threads = ((per + 3) / 4) * (p.splits > 32 ? 32 : 1);
+  wgrad_reduce_kernel<<<grid_for(red_threads, 256), 256, 0, s>>>(part, p.splits, KH * KW, Cs, Cb, dw);
   B200_LAUNCH_CHECK("wgrad_reduce_kernel");
   return B200LIC_OK;
 }

@@ -82,48 +82,73 @@ __global__ void __launch_bounds__(256)
   const size_t row = (size_t)C * HW;
   const size_t src_row = (idx ? (size_t)idx[b] : (size_t)b) * row, dst_row = (size_t)b * row;
   const bool vec2 = (HW & 1) == 0;
+  if (vec2) {
+    // all 16 loads of the thread (8 channel rows x {q, fp}) are issued before the first use; one hash word serves both
+    // pixels of a pair (element index even => same group of four)
+    const int p = p0 + 2 * lane;
+    float2 qv[8], fv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int cl = warp + 8 * j, c = c0 + cl, p = p0 + 2 * lane;
-    float v0 = 0.f, v1 = 0.f;
-    if (c < C && p < HW) {
-      const size_t e = (size_t)c * HW + p;
-      const bool has1 = p + 1 < HW;
-      float q0, q1 = 0.f, f0 = 0.f, f1 = 0.f;
-      if (vec2) {
-        const float2 qv = __ldg(reinterpret_cast<const float2*>(q + src_row + e));
-        q0 = qv.x;
-        q1 = qv.y;
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + warp + 8 * j;
+      qv[j] = (c < C && p < HW) ? __ldg(reinterpret_cast<const float2*>(q + src_row + (size_t)c * HW + p)) : make_float2(0.f, 0.f);
+    }
+    if (!all_q) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + warp + 8 * j;
+        fv[j] = (c < C && p < HW) ? __ldg(reinterpret_cast<const float2*>(fp + src_row + (size_t)c * HW + p)) : make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cl = warp + 8 * j, c = c0 + cl;
+      float v0 = qv[j].x, v1 = qv[j].y;
+      if (c < C && p < HW) {
+        const size_t e = (size_t)c * HW + p;
         if (!all_q) {
-          const float2 fv = __ldg(reinterpret_cast<const float2*>(fp + src_row + e));
-          f0 = fv.x;
-          f1 = fv.y;
+          const size_t i = dst_row + e;
+          const unsigned long long word = mix64p(seed ^ mix64p((unsigned long long)(i >> 2)));
+          const unsigned sh = 16u * (unsigned)(i & 3);
+          if (!((unsigned)((word >> sh) & 0xFFFFu) < thresh)) v0 = fv[j].x;
+          if (!((unsigned)((word >> (sh + 16u)) & 0xFFFFu) < thresh)) v1 = fv[j].y;
         }
-      } else {
-        q0 = __ldg(q + src_row + e);
-        if (has1) q1 = __ldg(q + src_row + e + 1);
+        if (out != nullptr) *reinterpret_cast<float2*>(out + dst_row + e) = make_float2(v0, v1);
+      }
+      if (square) {
+        v0 *= v0;
+        v1 *= v1;
+      }
+      t[cl][2 * lane] = v0;
+      t[cl][2 * lane + 1] = v1;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cl = warp + 8 * j, c = c0 + cl, p = p0 + 2 * lane;
+      float v0 = 0.f, v1 = 0.f;
+      if (c < C && p < HW) {
+        const size_t e = (size_t)c * HW + p;
+        const bool has1 = p + 1 < HW;
+        const float q0 = __ldg(q + src_row + e), q1 = has1 ? __ldg(q + src_row + e + 1) : 0.f;
+        float f0 = 0.f, f1 = 0.f;
         if (!all_q) {
           f0 = __ldg(fp + src_row + e);
           if (has1) f1 = __ldg(fp + src_row + e + 1);
         }
-      }
-      v0 = (all_q || qdrop_keep_at(seed, dst_row + e, thresh)) ? q0 : f0;
-      if (has1) v1 = (all_q || qdrop_keep_at(seed, dst_row + e + 1, thresh)) ? q1 : f1;
-      if (out != nullptr) {
-        if (vec2) {
-          *reinterpret_cast<float2*>(out + dst_row + e) = make_float2(v0, v1);
-        } else {
+        v0 = (all_q || qdrop_keep_at(seed, dst_row + e, thresh)) ? q0 : f0;
+        if (has1) v1 = (all_q || qdrop_keep_at(seed, dst_row + e + 1, thresh)) ? q1 : f1;
+        if (out != nullptr) {
           out[dst_row + e] = v0;
           if (has1) out[dst_row + e + 1] = v1;
         }
       }
+      if (square) {
+        v0 *= v0;
+        v1 *= v1;
+      }
+      t[cl][2 * lane] = v0;
+      t[cl][2 * lane + 1] = v1;
     }
-    if (square) {
-      v0 *= v0;
-      v1 *= v1;
-    }
-    t[cl][2 * lane] = v0;
-    t[cl][2 * lane + 1] = v1;
   }
   __syncthreads();
   if (c0 + 2 * lane >= cpad) return;
@@ -143,9 +168,15 @@ __global__ void __launch_bounds__(256)
 // loss += scale * sum |pred - tgt|^p over the batch, with the gradient grad_scale * p |d|^(p-1) sign(d) leaving as the
 // split-bf16 NHWC operand [rows, HW, cpad] of the weight-gradient GEMM (and optionally as fp32 NCHW for a dgrad).
 // tgt row b = tgt_cache[idx[b]] (the pick of the device schedule) or tgt_cache[b].
-__global__ void __launch_bounds__(256)
+// GDN instantiation: `pred` is a GDN unit's output -- given, or (pred == nullptr) recomputed as x * norm^-+1/2 exactly as
+// the conv engine's GDN epilogue computes it -- and the gradient is carried on to the norm accumulator,
+// d_norm = dy * x * d(norm^-+1/2)/dnorm (b200lic_gdn_bwd_prep's arithmetic), the dY operand of gamma's weight gradient.
+// Loads are issued four channel rows at a time before their first use (registers: 4 CTAs of 256 threads per SM).
+template <bool GDN>
+__global__ void __launch_bounds__(256, 4)
     loss_stage_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, PickSched ps, int C, int HW, int cpad,
-                      float p, float scale, float grad_scale, int act, float slope, float* __restrict__ loss,
+                      float p, float scale, float grad_scale, int act, float slope, const float* __restrict__ gdn_x,
+                      const float* __restrict__ gdn_norm, int gdn_inverse, float* __restrict__ loss,
                       __nv_bfloat16* __restrict__ gh, __nv_bfloat16* __restrict__ gl, float* __restrict__ d_pred) {
   __shared__ float t[64][65];
   __shared__ float red[32];
@@ -180,39 +211,84 @@ __global__ void __launch_bounds__(256)
     }
     return a > 0.f ? g : g * neg;
   };
+  auto gdn_y = [&](float x, float nrm) -> float { return gdn_inverse ? x * sqrtf(nrm) : x * rsqrtf(nrm); };
+  auto dnorm = [&](float g, float x, float nrm) -> float {
+    const float r = rsqrtf(nrm);
+    return gdn_inverse ? g * x * 0.5f * r : g * x * (-0.5f) * r * r * r;
+  };
+  if (vec2) {
+    const int px = p0 + 2 * lane;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int cl = warp + 8 * j, c = c0 + cl, px = p0 + 2 * lane;
-    float g0 = 0.f, g1 = 0.f;
-    if (c < C && px < HW) {
-      const size_t e = (size_t)c * HW + px;
-      const bool has1 = px + 1 < HW;
-      float a0, a1 = 0.f, b0, b1 = 0.f;
-      if (vec2) {
-        const float2 av = __ldg(reinterpret_cast<const float2*>(pred + pred_row + e));
-        const float2 bv = __ldg(reinterpret_cast<const float2*>(tgt + tgt_row + e));
-        a0 = av.x; a1 = av.y; b0 = bv.x; b1 = bv.y;
-      } else {
-        a0 = __ldg(pred + pred_row + e);
-        b0 = __ldg(tgt + tgt_row + e);
-        if (has1) {
-          a1 = __ldg(pred + pred_row + e + 1);
-          b1 = __ldg(tgt + tgt_row + e + 1);
+    for (int half = 0; half < 2; ++half) {
+      float2 av[4], bv[4], xv[4], nv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + warp + 8 * (4 * half + j);
+        const bool ok = c < C && px < HW;
+        const size_t e = pred_row + (size_t)c * HW + px;
+        bv[j] = ok ? __ldg(reinterpret_cast<const float2*>(tgt + tgt_row + (size_t)c * HW + px)) : make_float2(0.f, 0.f);
+        if (GDN) {
+          xv[j] = ok ? __ldg(reinterpret_cast<const float2*>(gdn_x + e)) : make_float2(0.f, 0.f);
+          nv[j] = ok ? __ldg(reinterpret_cast<const float2*>(gdn_norm + e)) : make_float2(1.f, 1.f);
         }
+        if (!GDN || pred != nullptr)
+          av[j] = ok ? __ldg(reinterpret_cast<const float2*>(pred + e)) : make_float2(0.f, 0.f);
       }
-      g0 = one(a0, b0);
-      if (has1) g1 = one(a1, b1);
-      if (d_pred != nullptr) {
-        if (vec2) {
-          *reinterpret_cast<float2*>(d_pred + pred_row + e) = make_float2(g0, g1);
-        } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cl = warp + 8 * (4 * half + j), c = c0 + cl;
+        float g0 = 0.f, g1 = 0.f;
+        if (c < C && px < HW) {
+          float a0, a1;
+          if (GDN && pred == nullptr) {
+            a0 = gdn_y(xv[j].x, nv[j].x);
+            a1 = gdn_y(xv[j].y, nv[j].y);
+          } else {
+            a0 = av[j].x;
+            a1 = av[j].y;
+          }
+          g0 = one(a0, bv[j].x);
+          g1 = one(a1, bv[j].y);
+          if (GDN) {
+            g0 = dnorm(g0, xv[j].x, nv[j].x);
+            g1 = dnorm(g1, xv[j].y, nv[j].y);
+          }
+          if (d_pred != nullptr)
+            *reinterpret_cast<float2*>(d_pred + pred_row + (size_t)c * HW + px) = make_float2(g0, g1);
+        }
+        t[cl][2 * lane] = g0;
+        t[cl][2 * lane + 1] = g1;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cl = warp + 8 * j, c = c0 + cl, px = p0 + 2 * lane;
+      float g0 = 0.f, g1 = 0.f;
+      if (c < C && px < HW) {
+        const size_t e = (size_t)c * HW + px;
+        const bool has1 = px + 1 < HW;
+        const float a0 = (GDN && pred == nullptr) ? gdn_y(__ldg(gdn_x + pred_row + e), __ldg(gdn_norm + pred_row + e))
+                                                  : __ldg(pred + pred_row + e);
+        g0 = one(a0, __ldg(tgt + tgt_row + e));
+        if (has1) {
+          const float a1 = (GDN && pred == nullptr)
+                               ? gdn_y(__ldg(gdn_x + pred_row + e + 1), __ldg(gdn_norm + pred_row + e + 1))
+                               : __ldg(pred + pred_row + e + 1);
+          g1 = one(a1, __ldg(tgt + tgt_row + e + 1));
+        }
+        if (GDN) {
+          g0 = dnorm(g0, __ldg(gdn_x + pred_row + e), __ldg(gdn_norm + pred_row + e));
+          if (has1) g1 = dnorm(g1, __ldg(gdn_x + pred_row + e + 1), __ldg(gdn_norm + pred_row + e + 1));
+        }
+        if (d_pred != nullptr) {
           d_pred[pred_row + e] = g0;
           if (has1) d_pred[pred_row + e + 1] = g1;
         }
       }
+      t[cl][2 * lane] = g0;
+      t[cl][2 * lane + 1] = g1;
     }
-    t[cl][2 * lane] = g0;
-    t[cl][2 * lane + 1] = g1;
   }
   if (loss != nullptr) {                         // block_sum synchronises: the tile is complete afterwards
     const float tot = block_sum(acc, red);
@@ -371,23 +447,31 @@ int b200lic_stage_mix_sched(const float* q, const float* fp, const long long* id
 
 int b200lic_lp_loss_stage_sched(const float* pred, const float* tgt_cache, const long long* idx_table, int table_rows,
                                 int rows, int C, int HW, int units, int unit, const b200lic_calib_sched* sched, float p,
-                                float scale, float grad_scale, int act, float act_slope, float* loss, void* dy_hi,
-                                void* dy_lo, int cpad, float* d_pred, b200lic_stream_t stream) {
+                                float scale, float grad_scale, int act, float act_slope, const float* gdn_x,
+                                const float* gdn_norm, int gdn_inverse, float* loss, void* dy_hi, void* dy_lo, int cpad,
+                                float* d_pred, b200lic_stream_t stream) {
   B200_ARCH_GATE();
-  B200_REQUIRE(pred && tgt_cache && dy_hi && dy_lo, "lp_loss_stage_sched: null pointer");
+  B200_REQUIRE((pred || gdn_x) && tgt_cache && dy_hi && dy_lo, "lp_loss_stage_sched: null pointer");
   B200_REQUIRE(p >= 1.f, "lp_loss_stage_sched: p=%f < 1", p);
   B200_REQUIRE(rows >= 1 && rows <= 65535 && C >= 1 && HW >= 1 && cpad >= C && (cpad % 32) == 0,
                "lp_loss_stage_sched: bad shape (rows=%d C=%d HW=%d cpad=%d)", rows, C, HW, cpad);
   B200_REQUIRE(!idx_table || (sched && table_rows >= 1 && units >= 1 && unit >= 0 && unit < units),
                "lp_loss_stage_sched: bad pick arguments");
-  B200_REQUIRE(((((uintptr_t)pred) | ((uintptr_t)tgt_cache) | ((uintptr_t)d_pred)) & 7) == 0,
-               "lp_loss_stage_sched: 8-byte alignment");
+  B200_REQUIRE(((((uintptr_t)pred) | ((uintptr_t)tgt_cache) | ((uintptr_t)d_pred) | ((uintptr_t)gdn_x) |
+                 ((uintptr_t)gdn_norm)) & 7) == 0, "lp_loss_stage_sched: 8-byte alignment");
+  B200_REQUIRE((gdn_x == nullptr) == (gdn_norm == nullptr), "lp_loss_stage_sched: gdn_x and gdn_norm go together");
   PickSched ps{idx_table, table_rows, units, unit, sched};
   dim3 grid((unsigned)(((cpad + 63) / 64) * ((HW + 63) / 64)), 1, (unsigned)rows);
-  loss_stage_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale, act,
-                                                          act_slope, loss,
-                                                          reinterpret_cast<__nv_bfloat16*>(dy_hi),
-                                                          reinterpret_cast<__nv_bfloat16*>(dy_lo), d_pred);
+  if (gdn_x != nullptr)
+    loss_stage_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale,
+                                                                 act, act_slope, gdn_x, gdn_norm, gdn_inverse, loss,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dy_hi),
+                                                                 reinterpret_cast<__nv_bfloat16*>(dy_lo), d_pred);
+  else
+    loss_stage_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale,
+                                                                  act, act_slope, nullptr, nullptr, 0, loss,
+                                                                  reinterpret_cast<__nv_bfloat16*>(dy_hi),
+                                                                  reinterpret_cast<__nv_bfloat16*>(dy_lo), d_pred);
   B200_LAUNCH_CHECK("loss_stage_kernel");
   return B200LIC_OK;
 }

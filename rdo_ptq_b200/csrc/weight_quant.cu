@@ -6,6 +6,7 @@
 //   :281-298 range -> (delta, zero_point); :175-177 fake-quant; :437-452 AdaRound forward;
 //   :454-466 alpha init; layer_opt.py:160-165 rounding regulariser; torch.optim.Adam.
 #include <initializer_list>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "prepared.cuh"
@@ -391,40 +392,115 @@ __global__ void __launch_bounds__(256)
     ad.inv_sqrt_bc2 = __ldg(&t.sched->inv_sqrt_bc2);
     reg_b = __ldg(&t.sched->reg_b);
   }
-  for (int e = threadIdx.x; e < kTailCb * T; e += blockDim.x) {
-    const int tap = e / kTailCb, cbl = e - tap * kTailCb;
-    float acc = 0.f;
-    if (cbl < ncb) {
-      const float* p = part + ((size_t)tap * Cs + cs) * Cb + cb0 + cbl;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int z = 0;
-      for (; z + 3 < splits; z += 4) {
-        a0 += __ldg(p + (size_t)z * per);
-        a1 += __ldg(p + (size_t)(z + 1) * per);
-        a2 += __ldg(p + (size_t)(z + 2) * per);
-        a3 += __ldg(p + (size_t)(z + 3) * per);
+  // Phase 1: one item = 4 consecutive cb of one tap (a float4 of every slab).  All the slabs' loads of an item are
+  // issued before the first add (groups of 8 independent 16-byte loads), so a thread pays two or three L2 round trips
+  // instead of one per split; the additions keep wgrad_reduce_kernel's order: lane z%4 accumulates slab z, then
+  // (a0 + a1) + (a2 + a3).
+  const bool vec = (Cb & 3) == 0 && (((uintptr_t)part) & 15) == 0;
+  if (vec) {
+    for (int e = threadIdx.x; e < (kTailCb / 4) * T; e += blockDim.x) {
+      const int tap = e / (kTailCb / 4), c4 = (e - tap * (kTailCb / 4)) * 4;
+      float4 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < ncb) {                               // ncb is a multiple of 4 here
+        const float* p = part + ((size_t)tap * Cs + cs) * Cb + cb0 + c4;
+        int z = 0;
+        for (; z + 7 < splits; z += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(p + (size_t)(z + k) * per));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a[k & 3].x += v[k].x; a[k & 3].y += v[k].y; a[k & 3].z += v[k].z; a[k & 3].w += v[k].w;
+          }
+        }
+        for (; z + 3 < splits; z += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(p + (size_t)(z + k) * per));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            a[k].x += v[k].x; a[k].y += v[k].y; a[k].z += v[k].z; a[k].w += v[k].w;
+          }
+        }
+        {
+          float4 v[3];
+          const int rem = splits - z;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            v[k] = k < rem ? __ldg(reinterpret_cast<const float4*>(p + (size_t)(z + k) * per)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < rem) { a[0].x += v[k].x; a[0].y += v[k].y; a[0].z += v[k].z; a[0].w += v[k].w; }
+        }
       }
-      for (; z < splits; ++z) a0 += __ldg(p + (size_t)z * per);
-      acc = (a0 + a1) + (a2 + a3);
+      tile[(c4 + 0) * T + tap] = (a[0].x + a[1].x) + (a[2].x + a[3].x);
+      tile[(c4 + 1) * T + tap] = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+      tile[(c4 + 2) * T + tap] = (a[0].z + a[1].z) + (a[2].z + a[3].z);
+      tile[(c4 + 3) * T + tap] = (a[0].w + a[1].w) + (a[2].w + a[3].w);
     }
-    tile[cbl * T + tap] = acc;
+  } else {
+    for (int e = threadIdx.x; e < kTailCb * T; e += blockDim.x) {
+      const int tap = e / kTailCb, cbl = e - tap * kTailCb;
+      float acc = 0.f;
+      if (cbl < ncb) {
+        const float* p = part + ((size_t)tap * Cs + cs) * Cb + cb0 + cbl;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int z = 0;
+        for (; z + 3 < splits; z += 4) {
+          a0 += __ldg(p + (size_t)z * per);
+          a1 += __ldg(p + (size_t)(z + 1) * per);
+          a2 += __ldg(p + (size_t)(z + 2) * per);
+          a3 += __ldg(p + (size_t)(z + 3) * per);
+        }
+        for (; z < splits; ++z) a0 += __ldg(p + (size_t)z * per);
+        acc = (a0 + a1) + (a2 + a3);
+      }
+      tile[cbl * T + tap] = acc;
+    }
   }
   __syncthreads();
+  // Phase 2: the CTA's ncb * T weights are contiguous in weight order and start 16-byte aligned (cb0 % 32 == 0): four per
+  // thread, one 16-byte load / store per array, so the whole CTA is a single pass.  Channel index in 32-bit arithmetic.
   float reg_acc = 0.f;
-  const size_t base = ((size_t)cs * Cb + cb0) * T;
-  for (int e = threadIdx.x; e < ncb * T; e += blockDim.x) {
-    const size_t i = base + e;
-    const int c = (int)((i / t.inner) % t.ch);
+  const unsigned base = (unsigned)(((size_t)cs * Cb + cb0) * T);
+  const unsigned uinner = (unsigned)t.inner, uch = (unsigned)t.ch;
+  auto elem = [&](unsigned i, float dwq, float w_, float a, float& mi, float& vi, float& an) {
+    const unsigned c = (i / uinner) % uch;
     const float d = __ldg(t.delta + c), z = __ldg(t.zp + c);
-    const float dwq = tile[e];
-    if (t.dw_out) t.dw_out[i] = dwq;
-    const float a = t.alpha[i];
-    const float g = adaround_grad(__ldg(t.w + i), a, d, z, t.top, dwq, t.grad_scale, t.reg_weight, reg_b, reg_acc);
-    float mi = t.m[i], vi = t.v[i], an;
+    const float g = adaround_grad(w_, a, d, z, t.top, dwq, t.grad_scale, t.reg_weight, reg_b, reg_acc);
     adam_step(a, g, ad, mi, vi, an);
-    t.m[i] = mi;
-    t.v[i] = vi;
-    t.alpha[i] = an;
+  };
+  const int n_el = ncb * T;
+  if (vec && (n_el & 3) == 0 && ((((uintptr_t)t.w) | ((uintptr_t)t.alpha) | ((uintptr_t)t.m) | ((uintptr_t)t.v) |
+                                   ((uintptr_t)t.dw_out)) & 15) == 0) {
+    for (int e = threadIdx.x * 4; e < n_el; e += blockDim.x * 4) {
+      const unsigned i = base + (unsigned)e;
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(t.w + i));
+      const float4 av = *reinterpret_cast<const float4*>(t.alpha + i);
+      float4 mv = *reinterpret_cast<const float4*>(t.m + i), vv = *reinterpret_cast<const float4*>(t.v + i), an;
+      const float4 gq = make_float4(tile[e], tile[e + 1], tile[e + 2], tile[e + 3]);
+      if (t.dw_out) *reinterpret_cast<float4*>(t.dw_out + i) = gq;
+      elem(i, gq.x, wv.x, av.x, mv.x, vv.x, an.x);
+      elem(i + 1, gq.y, wv.y, av.y, mv.y, vv.y, an.y);
+      elem(i + 2, gq.z, wv.z, av.z, mv.z, vv.z, an.z);
+      elem(i + 3, gq.w, wv.w, av.w, mv.w, vv.w, an.w);
+      *reinterpret_cast<float4*>(t.m + i) = mv;
+      *reinterpret_cast<float4*>(t.v + i) = vv;
+      *reinterpret_cast<float4*>(t.alpha + i) = an;
+    }
+  } else {
+    for (int e = threadIdx.x; e < n_el; e += blockDim.x) {
+      const unsigned i = base + (unsigned)e;
+      const float dwq = tile[e];
+      if (t.dw_out) t.dw_out[i] = dwq;
+      float mi = t.m[i], vi = t.v[i], an;
+      elem(i, dwq, __ldg(t.w + i), t.alpha[i], mi, vi, an);
+      t.m[i] = mi;
+      t.v[i] = vi;
+      t.alpha[i] = an;
+    }
   }
   if (t.reg_loss != nullptr && reg_b > 0.f) {
     const float tot = block_sum(reg_acc, red);
@@ -499,12 +575,112 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same, one CTA per (output channel, 32 input channels) with that slice staged in shared memory: the source is read in
+// its own order (conv: one contiguous 32*KH*KW run; transposed conv: 32 runs of KH*KW) and the packed rows [tap][ci] are
+// written in 64-byte runs -- the element-wise kernel above walks the PACKED index and so reads w / alpha with a stride
+// of KH*KW floats (one useful word per 32-byte sector).
+__global__ void __launch_bounds__(256)
+    quant_pack_tile_kernel(PackDst g, const float* __restrict__ w, const float* __restrict__ alpha,
+                           const float* __restrict__ delta, const float* __restrict__ zp, int ch, int inner, float top,
+                           int soft, int mode, __nv_bfloat16* __restrict__ bh, __nv_bfloat16* __restrict__ bl,
+                           float* __restrict__ w_q) {
+  extern __shared__ float wt[];                     // [KH*KW][32]: one output channel x 32 input channels
+  const int co = blockIdx.x, ci0 = blockIdx.y * 32;
+  const int KK = g.KH * g.KW;
+  const int nci = min(32, g.Cin - ci0);             // <= 0 for a chunk of pure padding channels
+  const unsigned uinner = (unsigned)inner, uch = (unsigned)ch;
+  for (int e = threadIdx.x; e < nci * KK; e += blockDim.x) {
+    const int cl = e / KK, rs = e - cl * KK;
+    const unsigned src = (unsigned)((long long)co * g.s_co + (long long)(ci0 + cl) * g.s_ci + rs);
+    const unsigned c = (src / uinner) % uch;
+    const float d = __ldg(delta + c), z = __ldg(zp + c);
+    const float tq = __fdiv_rn(__ldg(w + src), d);
+    float q;
+    if (alpha == nullptr) {
+      q = __fadd_rn(rintf(tq), z);
+    } else {
+      const float a = __ldg(alpha + src);
+      float up;
+      if (soft) up = fminf(fmaxf(__fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma), 0.f), 1.f);
+      else up = a >= 0.f ? 1.f : 0.f;
+      q = __fadd_rn(__fadd_rn(floorf(tq), up), z);
+    }
+    q = fminf(fmaxf(q, 0.f), top);
+    const float n_ = __fsub_rn(q, z);
+    const float val = mode ? n_ : __fmul_rn(n_, d);
+    if (w_q) w_q[src] = val;
+    wt[rs * 32 + cl] = val;
+  }
+  __syncthreads();
+  const size_t Kmax = (size_t)g.Tmax * g.Cpad;
+  const size_t per_phase = (size_t)g.CoutPad * Kmax;
+  // items: (phase, tap slot t < Tmax, pair of input channels): 64-byte runs of the packed row
+  for (int it = threadIdx.x; it < g.phases * g.Tmax * 16; it += blockDim.x) {
+    const int c2 = (it & 15) * 2, t = (it >> 4) % g.Tmax, phase = (it >> 4) / g.Tmax;
+    int r0 = 0, s0 = 0, KHp = g.KH, KWp = g.KW, rstep = 1;
+    if (g.transposed) {
+      const int st = g.stride, ph = phase / st, pw = phase % st;
+      r0 = (ph + g.pad) % st;
+      s0 = (pw + g.pad) % st;
+      KHp = r0 < g.KH ? (g.KH - r0 + st - 1) / st : 0;
+      KWp = s0 < g.KW ? (g.KW - s0 + st - 1) / st : 0;
+      rstep = st;
+    }
+    float v0 = 0.f, v1 = 0.f;
+    if (t < KHp * KWp) {
+      const int i = t / KWp, j = t - i * KWp;
+      const int rs = (r0 + i * rstep) * g.KW + (s0 + j * rstep);
+      if (c2 < nci) v0 = wt[rs * 32 + c2];
+      if (c2 + 1 < nci) v1 = wt[rs * 32 + c2 + 1];
+    }
+    const size_t o = (size_t)phase * per_phase + (size_t)co * Kmax + (size_t)t * g.Cpad + ci0 + c2;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+    __nv_bfloat162 hv;
+    hv.x = h0;
+    hv.y = h1;
+    *reinterpret_cast<__nv_bfloat162*>(bh + o) = hv;
+    if (!mode) {
+      __nv_bfloat162 lv;
+      lv.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      lv.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      *reinterpret_cast<__nv_bfloat162*>(bl + o) = lv;
+    }
+  }
+}
+
+// zero rows of the padded output channels (co >= Cout) of a packed operand
+__global__ void __launch_bounds__(256) pack_pad_rows_kernel(PackDst g, int mode, __nv_bfloat16* __restrict__ bh,
+                                                             __nv_bfloat16* __restrict__ bl) {
+  const size_t Kmax = (size_t)g.Tmax * g.Cpad;
+  const size_t per_phase = (size_t)g.CoutPad * Kmax, pad = (size_t)(g.CoutPad - g.Cout) * Kmax;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < pad * g.phases; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t phase = e / pad, r = e - phase * pad;
+    const size_t o = phase * per_phase + (size_t)g.Cout * Kmax + r;
+    bh[o] = __float2bfloat16_rn(0.f);
+    if (!mode) bl[o] = __float2bfloat16_rn(0.f);
+  }
+}
+
 int launch_quant_pack(const PackDst& g, const float* w, const float* alpha, const float* delta, const float* zp, int ch,
                       int inner, int n_levels, int soft, int mode, void* packed, float* w_q, cudaStream_t s) {
   const size_t per_phase = (size_t)g.CoutPad * g.Tmax * g.Cpad;
-  dim3 grid((unsigned)((per_phase + 255) / 256 > 1184 ? 1184 : (per_phase + 255) / 256), 1, g.phases);
   __nv_bfloat16* bh = reinterpret_cast<__nv_bfloat16*>(packed);
   __nv_bfloat16* bl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(packed) + g.b_bytes);
+  const size_t tile_bytes = (size_t)32 * g.KH * g.KW * sizeof(float);
+  static const bool elementwise_only = getenv("B200LIC_QPACK_ELEMENTWISE") != nullptr;     // A/B experiments
+  if (tile_bytes <= 40 * 1024 && g.Cpad / 32 <= 65535 && !elementwise_only) {
+    dim3 tgrid((unsigned)g.Cout, (unsigned)(g.Cpad / 32), 1);
+    quant_pack_tile_kernel<<<tgrid, 256, tile_bytes, s>>>(g, w, alpha, delta, zp, ch, inner, (float)(n_levels - 1), soft,
+                                                          mode, bh, bl, w_q);
+    B200_LAUNCH_CHECK("quant_pack_tile_kernel");
+    if (g.CoutPad > g.Cout) {
+      const size_t pad = (size_t)(g.CoutPad - g.Cout) * g.Tmax * g.Cpad * g.phases;
+      pack_pad_rows_kernel<<<grid_for(pad, 256), 256, 0, s>>>(g, mode, bh, bl);
+      B200_LAUNCH_CHECK("pack_pad_rows_kernel");
+    }
+    return B200LIC_OK;
+  }
+  dim3 grid((unsigned)((per_phase + 255) / 256 > 1184 ? 1184 : (per_phase + 255) / 256), 1, g.phases);
   quant_pack_kernel<<<grid, 256, 0, s>>>(g, w, alpha, delta, zp, ch, inner, (float)(n_levels - 1), soft, mode, bh, bl, w_q);
   B200_LAUNCH_CHECK("quant_pack_kernel");
   return B200LIC_OK;

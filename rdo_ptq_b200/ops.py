@@ -202,6 +202,9 @@ def act_quant_apply_stage(x, keys, n_bits, slot, square=False, out=None):
 # RAW output tagged with the per-channel statistics, and the consumer quantises it while staging its own GEMM operand
 # (one pass instead of apply + NHWC split).  Any other reader calls `resolve_actq` first.
 DEFER_ACTQ = False
+# below this size the one-launch cluster kernel (b200lic_actq_fused) + the consumer's own split is cheaper than statistics
+# + apply_stage: deferring trades a pass over the tensor for one more launch
+DEFER_ACTQ_MIN_BYTES = 4 * 1000 * 1000
 
 
 class defer_actq:
@@ -719,15 +722,17 @@ def quant_pack_weights(w, alpha, delta, zp, axis, n_levels, soft, d, transposed,
     return out
 
 
-def conv_fwd_packed(x, packed, d, transposed, bias=None, w_scale=None, gdn_x=None, want_norm=False, ws=None, y=None):
+def conv_fwd_packed(x, packed, d, transposed, bias=None, w_scale=None, gdn_x=None, want_norm=False, ws=None, y=None,
+                    norm=None):
     """Forward with a prepared weight operand; x=None: the activation operand is already staged in `ws`.
-    Returns y, or (y, norm) with want_norm."""
+    Returns y, or (y, norm) with want_norm (`norm`: caller-owned buffer for it)."""
     if ws is None:
         ws = _workspace(d, fwd_op(transposed), packed.device)
     wsb, nws = ws
     if y is None:
         y = torch.empty((d.N, d.Cout, d.Ho, d.Wo), device=packed.device, dtype=torch.float32)
-    norm = torch.empty_like(y) if want_norm else None
+    if want_norm and norm is None:
+        norm = torch.empty_like(y)
     call("conv_fwd_packed", C.byref(d), fwd_op(transposed), _p(None if x is None else _c(x, "input")), _p(packed),
          _p(_c(w_scale)), _p(_c(bias)), _p(gdn_x), _p(norm), _p(y), _p(wsb), nws)
     return (y, norm) if want_norm else y
@@ -765,14 +770,18 @@ def stage_mix_sched(q, fp, idx_table, rows, prob, seed_base, units, unit, sched,
 
 
 def lp_loss_stage_sched(pred, tgt_cache, idx_table, units, unit, sched, p, scale, grad_scale, act, slope, loss, slot,
-                        d_pred=None):
-    """lp_loss value + gradient with the gradient written as the staged dY operand `slot` of the weight gradient."""
-    pred, tgt_cache = _c(pred), _c(tgt_cache)
-    rows, Cc, HW = pred.shape[0], pred.shape[1], pred[0, 0].numel()
+                        d_pred=None, gdn=None):
+    """lp_loss value + gradient with the gradient written as the staged dY operand `slot` of the weight gradient.
+    gdn = (x, norm, inverse): `pred` is a GDN unit's output; the gradient is carried on to the norm accumulator."""
+    tgt_cache = _c(tgt_cache)
+    gx, gn, ginv = (None, None, 0) if gdn is None else (_c(gdn[0]), _c(gdn[1]), int(bool(gdn[2])))
+    pred = None if pred is None else _c(pred)          # None (GDN only): y = x * norm^-+1/2 is recomputed in the kernel
+    shp = (pred if pred is not None else gx).shape
+    rows, Cc, HW = shp[0], shp[1], shp[2] * shp[3]
     hi, lo, cpad = slot
     call("lp_loss_stage_sched", _p(pred), _p(tgt_cache), _p(idx_table), 0 if idx_table is None else idx_table.size(0),
          rows, Cc, HW, int(units), int(unit), _p(sched), float(p), float(scale), float(grad_scale), int(act), float(slope),
-         _p(loss), hi, lo, cpad, _p(d_pred))
+         _p(gx), _p(gn), ginv, _p(loss), hi, lo, cpad, _p(d_pred))
 
 
 def conv_wgrad_prepared(d, transposed, x_slot, dy, dw, ws):
@@ -808,9 +817,9 @@ def conv_transpose2d(x, w, bias=None, stride=1, padding=0, output_padding=0, gro
 
 
 # ------------------------------------------------------------------------------------------------ GDN
-def gdn_reparam(p, bound, pedestal):
+def gdn_reparam(p, bound, pedestal, out=None):
     p = _c(p)
-    out = torch.empty_like(p)
+    out = torch.empty_like(p) if out is None else out
     call("gdn_reparam_fwd", _p(p), p.numel(), bound, pedestal, _p(out))
     return out
 
@@ -830,6 +839,14 @@ class _ReparamFn(torch.autograd.Function):
         dp = torch.empty_like(p)
         call("gdn_reparam_bwd", _p(p), _p(g), p.numel(), ctx.bound, _p(dp))
         return dp, None, None
+
+
+def gdn_reparam_bwd(p, g, bound, out=None):
+    """LowerBound-gated backward of `gdn_reparam` (b200lic_gdn_reparam_bwd)."""
+    p, g = _c(p), _c(g)
+    out = torch.empty_like(p) if out is None else out
+    call("gdn_reparam_bwd", _p(p), _p(g), p.numel(), float(bound), _p(out))
+    return out
 
 
 def gdn_desc(x_shape, inverse, want_norm=False):

@@ -211,7 +211,7 @@ class QuantModule(nn.Module):
         if self.use_act_quant and self.trained:
             nxt = self.__dict__.get("_defer_to")
             if (ops.DEFER_ACTQ and nxt is not None and not torch.is_grad_enabled() and out.dim() == 4
-                    and not nxt._forward_hooks and not nxt._forward_pre_hooks and not self._forward_hooks):
+                    and 4 * out.numel() >= ops.DEFER_ACTQ_MIN_BYTES and not nxt._forward_hooks and not nxt._forward_pre_hooks and not self._forward_hooks):
                 # evaluation inside an nn.Sequential: the only reader is the next QuantModule, which applies the
                 # quantiser while staging its operand (ops.DEFER_ACTQ); the statistics are taken here
                 bits = self.act_quantizer.n_bits if self.act_quantizer.act_bits_follow_n_bits else 8

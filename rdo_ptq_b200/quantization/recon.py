@@ -147,6 +147,45 @@ class FusedLayer:
         return f
 
 
+class FusedGdn:
+    """Static buffers of the fused iteration of a GDN / IGDN unit (f_gdn, quant_layer.py:142-154):
+    stage_mix (pick + QDrop -> the fp32 batch x for the epilogue AND the staged x*x operand) -> AdaRound soft gamma ->
+    re-parametrise -> pack -> GEMM (the accumulator norm = beta + gamma . x*x only) -> loss_stage with the GDN forward tail
+    and backward folded in (y = x * norm^-+1/2 recomputed, dL/dy -> dL/dnorm -> staged dY operand; y, dL/dy and dL/dnorm
+    are never written) -> wgrad of gamma on the staged x*x -> re-parametrisation backward -> STE / regulariser / Adam."""
+
+    @staticmethod
+    def build(m, in_shape, batch, world):
+        if not isinstance(m, QuantModule) or not m.is_gdn or ops.DEFAULT_ENGINE == ops.ENGINE_SIMT:
+            return None
+        if ops._act_id(m.activation_function)[0] != ops.ACT_NONE:
+            return None
+        f = FusedGdn()
+        f.inverse = bool(m.fwd_kwargs["inverse"])
+        f.d = ops.gdn_desc((batch,) + tuple(in_shape), f.inverse)
+        f.d.gdn_mode = 0        # calibration only needs the accumulator norm = beta + gamma . x^2: a plain 1x1 conv of x*x
+        Cc = in_shape[0]
+        f.dw = ops.ConvDesc(f.d.N, Cc, f.d.H, f.d.W, Cc, f.d.H, f.d.W, 1, 1, 1, 0, ops.ACT_NONE, 0.0, f.d.engine, 1, 0, 0)
+        dev = m.weight.device
+        f.packed = ops.new_packed(f.d, False, dev)
+        if f.packed is None:
+            return None
+        f.ws_f = ops._workspace(f.d, ops.fwd_op(False), dev)
+        f.ws_w = ops._workspace(f.dw, ops.wgrad_op(False), dev)
+        f.x_slot = ops.conv_x_slot(f.d, False, f.ws_f)
+        f.dy_slot = ops.conv_dy_slot(f.dw, False, f.ws_w)
+        if f.x_slot is None or f.dy_slot is None:
+            return None
+        shape = (batch,) + tuple(in_shape)
+        f.x = torch.empty(shape, device=dev, dtype=torch.float32)
+        f.norm = torch.empty_like(f.x)
+        f.leaf = torch.empty_like(m.weight.data)
+        f.g_eff, f.dgamma, f.dleaf = torch.empty_like(f.leaf), torch.empty_like(f.leaf), torch.empty_like(f.leaf)
+        f.b_eff = torch.empty_like(m.bias.data)
+        f.gr, f.br = m.fwd_kwargs["gamma_reparam"], m.fwd_kwargs["beta_reparam"]
+        return f
+
+
 class UnitTrainer:
     """State of one reconstruction problem: the QuantModules whose alpha is trained, Adam moments, schedules."""
 
@@ -196,12 +235,42 @@ class UnitTrainer:
         if self._fused_plan is False:
             ok = (self.fused and self.rd_task is None and not self.learn_delta and self.task_p is not None and
                   float(self.task_p) == float(self.p) and len(self.mods) == 1 and self.mods[0] is self.unit)
-            self._fused_plan = FusedLayer.build(self.unit, in_shape, batch, self.world) if ok else None
+            self._fused_plan = None
+            if ok:
+                self._fused_plan = (FusedGdn.build(self.unit, in_shape, batch, self.world) if self.unit.is_gdn else
+                                    FusedLayer.build(self.unit, in_shape, batch, self.world))
         return self._fused_plan
+
+    def _fused_gdn(self, f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base):
+        m = self.unit
+        q = m.weight_quantizer
+        C_ = f.leaf.shape[0]
+        ops.stage_mix_sched(q_in, fp_in, idx_table, f.d.N, prob, seed_base, units, unit, sched, f.x_slot, square=True,
+                            out=f.x)
+        ops.adaround_fwd(m.weight.data, q.alpha.data, q.delta, q.zero_point, q.axis, q.n_levels, True, out=f.leaf)
+        ops.gdn_reparam(f.leaf, f.gr.bound_value, f.gr.pedestal_value, out=f.g_eff)
+        ops.gdn_reparam(m.bias.data, f.br.bound_value, f.br.pedestal_value, out=f.b_eff)
+        ops.pack_weights(f.g_eff.view(C_, C_, 1, 1), f.d, False, out=f.packed)
+        ops.conv_fwd_packed(None, f.packed, f.d, False, bias=f.b_eff, ws=f.ws_f, y=f.norm)
+        denom = f.norm.numel() // f.norm.shape[1]
+        ops.lp_loss_stage_sched(None, tgt_cache, idx_table, units, unit, sched, self.p, 1.0 / denom, 2.0 / denom,
+                                ops.ACT_NONE, 0.0, self.loss_buf[0:1], f.dy_slot, gdn=(f.x, f.norm, f.inverse))
+        ops.conv_wgrad_prepared(f.dw, False, f.x_slot, None, f.dgamma.view(C_, C_, 1, 1), f.ws_w)
+        ops.gdn_reparam_bwd(f.leaf, f.dgamma, f.gr.bound_value, out=f.dleaf)
+        self._same = True
+        if self.world > 1:
+            self._flat = f.dleaf.view(-1)
+            return [f.dleaf]
+        ops.adaround_bwd_adam_sched(m.weight.data, q.alpha.data, q.delta, q.zero_point, f.dleaf, self.exp_avg[0],
+                                    self.exp_avg_sq[0], q.axis, q.n_levels, sched, reg_weight=self.weight,
+                                    reg_loss=self.loss_buf[2:3])
+        return []
 
     def fused_compute(self, f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base):
         """One fused iteration up to (world == 1: and including) the Adam step.  Returns the list of dL/dWq tensors for
         `step_update` (empty when the tail ran fused)."""
+        if isinstance(f, FusedGdn):
+            return self._fused_gdn(f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base)
         m = self.unit
         q = m.weight_quantizer
         ops.stage_mix_sched(q_in, fp_in, idx_table, f.d.N, prob, seed_base, units, unit, sched, f.x_slot)

@@ -29,8 +29,9 @@ def _layer(ops, dev, transposed, N=2, Cin=64, Cout=96, H=20, W=24, k=5, st=2, ac
 
 @pytest.mark.parametrize("transposed", [False, True])
 @pytest.mark.parametrize("mode", ["nearest", "soft", "hard", "integer"])
-def test_quant_pack_equals_quantiser_then_pack(ops, dev, transposed, mode):
-    x, w, b, d = _layer(ops, dev, transposed)
+@pytest.mark.parametrize("Cout", [96, 40])              # 40: output channels padded to 48 in the packed operand
+def test_quant_pack_equals_quantiser_then_pack(ops, dev, transposed, mode, Cout):
+    x, w, b, d = _layer(ops, dev, transposed, Cout=Cout)
     axis = 1 if transposed else 0
     delta, zp = ops.wq_init_minmax(w, axis, 8)
     alpha = ops.adaround_init_alpha(w, delta, axis) + torch.randn_like(w)
@@ -282,16 +283,62 @@ def test_deferred_activation_quantiser_is_bit_identical(dev, arch, kw):
         q.set_quant_state(True, True)
         q.model.g_s[-1].set_quant_state(True, False)
         q(x)                                                       # prepared weight operands exist from here on
-        n0 = _lib.launch_count()
         plain = q(x)
-        n1 = _lib.launch_count()
-        with ops.defer_actq():
-            deferred = q(x)
-        n2 = _lib.launch_count()
+        old, ops.DEFER_ACTQ_MIN_BYTES = ops.DEFER_ACTQ_MIN_BYTES, 0        # defer every eligible layer of this small model
+        try:
+            n1 = _lib.launch_count()
+            with ops.defer_actq():
+                deferred = q(x)
+            n2 = _lib.launch_count()
+            q(x)
+            n3 = _lib.launch_count()
+        finally:
+            ops.DEFER_ACTQ_MIN_BYTES = old
+    assert n2 - n1 != n3 - n2                                              # the deferred form really ran
     linked = sum(1 for mm in q.modules() if isinstance(mm, Q.QuantModule) and "_defer_to" in mm.__dict__)
     assert linked >= 14
     assert torch.equal(plain["x_hat"], deferred["x_hat"])
     assert torch.equal(plain["likelihoods"]["y"], deferred["likelihoods"]["y"])
     assert torch.equal(plain["likelihoods"]["z"], deferred["likelihoods"]["z"])
     assert getattr(deferred["x_hat"], "_b200_actq", None) is None          # nothing pending leaves the model
-    assert (n2 - n1) < (n1 - n0)
+
+
+@pytest.mark.parametrize("shape", [
+    # (N, Cin, H, W, Cout, k, stride): 128 equal items (the g_a.2 class), a handful of pixel tiles (h_a.2 class), a
+    # ragged shape, and the integer-weight form
+    (8, 192, 64, 64, 192, 5, 2), (8, 192, 16, 16, 192, 5, 2), (2, 96, 30, 44, 160, 3, 1), (8, 320, 16, 16, 192, 3, 1)])
+def test_stream_k_schedule_matches_whole_item_schedule(ops, dev, shape):
+    """Stream-K scheduling of the conv engine (K ranges of the items laid end to end, partial accumulators summed by the
+    item's owner) against whole-item scheduling: same MMAs, the K blocks of an output element are summed in a different
+    grouping, so results agree to fp32 rounding (1e-6 relative), for the three-pass and the integer two-pass form."""
+    from rdo_ptq_b200 import _lib
+    N, Cin, H, W, Cout, k, st = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * 0.05).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    d = ops.conv_desc(x.shape, w.shape, st, k // 2, act=2, slope=0.01)
+    delta, zp = ops.wq_init_minmax(w, 0, 8)
+    n_int = ops.wq_int_weights(w, delta, zp, 0, 256)
+    outs = {}
+    try:
+        for mode in (0, 2):
+            assert _lib.lib().b200lic_set_option(b"streamk", mode) == 0
+            y = ops.conv2d_raw(x, w, b, d)
+            y_int = ops.conv_wq(x, n_int, delta.reshape(-1).contiguous(), b, stride=st, padding=k // 2, act=2, slope=0.01)
+            torch.cuda.synchronize()
+            outs[mode] = (y, y_int)
+    finally:
+        _lib.lib().b200lic_set_option(b"streamk", 1)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.double(), w.double(), b.double(), st, k // 2), 0.01)
+    wq = (n_int * delta).double()
+    ref_int = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(x.double(), wq, b.double(), st, k // 2), 0.01)
+    errs = {}
+    for mode in (0, 2):
+        errs[mode] = (((outs[mode][0].double() - ref).norm() / ref.norm()).item(),
+                      ((outs[mode][1].double() - ref_int).norm() / ref_int.norm()).item())
+    between = [((a - c).norm() / a.norm()).item() for a, c in zip(outs[0], outs[2])]
+    print(f"{shape}: vs fp64 whole-item {errs[0]}, stream-K {errs[2]}; between the schedules {between}")
+    for mode in (0, 2):
+        assert errs[mode][0] < 2e-5 and errs[mode][1] < 2e-5               # both well inside the 1e-4 per-layer bar
+    assert max(between) < 4e-5
