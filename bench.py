@@ -144,10 +144,10 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries the one JSON line; NCCL's own log (communicator / rank lines the driver counts) goes to stderr
+        # NCCL's own log (communicator / rank lines the driver counts) is left on; the JSON line is printed LAST, after
+        # the process group is gone, so it stays the final line of stdout
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.call("actq_stats_init", ops._p(torch.empty(2, dtype=torch.int32, device=dev)), 1, stream=None)  # arch gate early
     pk = peaks()
@@ -339,9 +339,14 @@ def run_cuda(args):
                 "gflop_per_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e9,
                 "tflops_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e12 / (seq["ms_per_step"] / 1e3)}
         line.update(fwd)
-        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if world > 1:
+            time.sleep(1.0)                    # let the other ranks' teardown messages drain first
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 def hbm_rooflines(ops, dev, flush, pk):

@@ -444,6 +444,23 @@ B200LIC_API int b200lic_conv_wgrad_adam_sched(const b200lic_conv_desc* d, int tr
                                   float beta1, float beta2, float eps, float grad_scale, float reg_weight,
                                   float* reg_loss, float* dw_out, b200lic_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU tail of the AdaRound iteration over NVLink peer memory (the only exchange step of the path is
+ * the sum of dL/dWq over the data-parallel ranks).  Replaces ncclAllReduce(dL/dWq) + b200lic_adaround_bwd_adam_sched on
+ * every rank: rank r sums the ranks' gradients of ITS shard [shard_lo, shard_hi) out of their memory (peer loads, fixed
+ * rank order), applies STE masks / regulariser / Adam with its shard of the moments, and stores the new alpha into every
+ * rank's alpha buffer (peer stores).  grad_ptrs / alpha_ptrs / flag_ptrs are DEVICE arrays of `world` peer pointers into
+ * symmetric allocations the host set up (CUDA IPC / torch symmetric memory; the library maps nothing itself): each rank's
+ * local gradient, alpha, and a zero-initialised block of 2*world 32-bit flags; `state` = two zero-initialised local
+ * words.  Every rank must launch the call in the same order.  Shards must be 4-element aligned.  alpha is bit-identical
+ * on all ranks by construction; the kernel completes on a rank only after every rank's alpha stores have landed there. */
+B200LIC_API int b200lic_xgpu_reduce_adam_sched(const float* const* grad_ptrs, float* const* alpha_ptrs,
+                                   unsigned* const* flag_ptrs, unsigned* state, int rank, int world, size_t shard_lo,
+                                   size_t shard_hi, const float* w, const float* delta, const float* zero_point,
+                                   float* exp_avg, float* exp_avg_sq, int outer, int ch, int inner, int n_levels,
+                                   const b200lic_calib_sched* sched, float beta1, float beta2, float eps,
+                                   float grad_scale, float reg_weight, float* reg_loss, b200lic_stream_t stream);
+
 /* out = a * sigmoid(b) + c   (AttentionBlock tail) */
 B200LIC_API int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out,
                       b200lic_stream_t stream);

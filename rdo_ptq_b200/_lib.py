@@ -94,6 +94,8 @@ SIGNATURES = {
     "conv_wgrad_prepared": [_D, _I, _P, _P, _I, _P, _P, _P, _SZ],
     "conv_wgrad_adam_sched": [_D, _I, _P, _P, _I, _P, _P, _SZ, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F,
                               _F, _F, _P, _P],
+    "xgpu_reduce_adam_sched": [_P, _P, _P, _P, _I, _I, _SZ, _SZ, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F, _F, _F,
+                               _P],
     "attn_gate": [_P, _P, _P, _SZ, _P],
     "abs": [_P, _SZ, _P],
     "pixel_shuffle": [_P, _I, _I, _I, _I, _I, _I, _F, _P],

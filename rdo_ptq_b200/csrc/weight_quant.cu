@@ -521,6 +521,113 @@ int launch_wgrad_reduce_adam(const float* part, int splits, int T, int Cs, int C
   return B200LIC_OK;
 }
 
+// ---- multi-GPU tail: cross-GPU gradient reduction + Adam over NVLink peer memory, one kernel ------------------------------
+// Data-parallel calibration all-reduces dL/dWq and then applies the same Adam step on every rank.  Here the
+// optimiser state is sharded instead: rank r owns elements [lo, hi) of the layer.  It sums the ranks' local gradients of
+// its shard straight out of their memory (peer loads over NVLink / NVSwitch, fixed rank order), applies the STE masks,
+// the regulariser and Adam with its shard of m / v, and stores the new alpha into EVERY rank's alpha buffer (peer
+// stores): the traffic of a ring all-reduce, but no collective launch, no second pass for Adam, 1/N of the Adam work per
+// rank, and alpha is bit-identical everywhere by construction (each element is computed once).
+// Two cross-GPU barriers on flags in the symmetric buffers: A (entry) -- every rank's gradient buffer is complete (the
+// kernels that wrote it precede this one in stream order); B (exit, last CTA only) -- every rank's alpha stores have
+// landed here before the kernel completes, so stream order protects the next reader of alpha.
+struct XgpuArgs {
+  const float* const* grad_ptrs;    // [world] peer pointers: each rank's local dL/dWq of this layer
+  float* const* alpha_ptrs;         // [world] peer pointers: each rank's alpha of this layer
+  unsigned* const* flag_ptrs;       // [world] peer pointers: each rank's flag block, 2 * world words (A row, B row)
+  unsigned* state;                  // local: [0] epoch, [1] CTAs finished
+  int rank, world;
+  size_t lo, hi;                    // this rank's shard
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until every rank's flag in `row` of MY flag block has reached `epoch`; gives up after ~4 s (a peer died) rather
+// than hanging the GPU
+__device__ __forceinline__ void xgpu_wait(const unsigned* my_flags, int row, int world, unsigned epoch) {
+  for (int p = 0; p < world; ++p) {
+    long long spins = 0;
+    while ((int)(ld_acquire_sys(my_flags + row * world + p) - epoch) < 0) {
+      __nanosleep(100);
+      if (++spins > 40000000LL) return;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    xgpu_reduce_adam_kernel(XgpuArgs x, const float* __restrict__ w, const float* __restrict__ delta,
+                            const float* __restrict__ zp, float* __restrict__ m, float* __restrict__ v, int ch, int inner,
+                            float top, const b200lic_calib_sched* __restrict__ sched, AdamArgs ad, float grad_scale,
+                            float reg_weight, float* __restrict__ reg_loss) {
+  __shared__ float red[32];
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(x.state) + 1u;
+  // ---- barrier A: tell everyone my gradient is ready, wait until everyone's is
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0)
+      for (int p = 0; p < x.world; ++p) st_release_sys(x.flag_ptrs[p] + x.rank, epoch);
+    xgpu_wait(x.flag_ptrs[x.rank], 0, x.world, epoch);
+  }
+  __syncthreads();
+  ad.lr_over_bc1 = __ldg(&sched->lr_over_bc1);
+  ad.inv_sqrt_bc2 = __ldg(&sched->inv_sqrt_bc2);
+  const float reg_b = __ldg(&sched->reg_b);
+  float reg_acc = 0.f;
+  const unsigned uinner = (unsigned)inner, uch = (unsigned)ch;
+  const size_t n4 = (x.hi - x.lo) >> 2;                       // shards are multiples of four elements, 16-byte aligned
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = x.lo + (k << 2);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < x.world; ++p) {                        // fixed rank order; volatile: peer memory, never cached here
+      float4 t;
+      asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "l"(x.grad_ptrs[p] + i)
+                   : "memory");
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + i));
+    const float4 av = *reinterpret_cast<const float4*>(x.alpha_ptrs[x.rank] + i);
+    float4 mv = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i), an;
+    auto elem = [&](unsigned e, float dwq, float w_, float a, float& mi, float& vi, float& out) {
+      const unsigned c = (e / uinner) % uch;
+      const float d = __ldg(delta + c), z = __ldg(zp + c);
+      const float gg = adaround_grad(w_, a, d, z, top, dwq, grad_scale, reg_weight, reg_b, reg_acc);
+      adam_step(a, gg, ad, mi, vi, out);
+    };
+    elem((unsigned)i, g.x, wv.x, av.x, mv.x, vv.x, an.x);
+    elem((unsigned)i + 1, g.y, wv.y, av.y, mv.y, vv.y, an.y);
+    elem((unsigned)i + 2, g.z, wv.z, av.z, mv.z, vv.z, an.z);
+    elem((unsigned)i + 3, g.w, wv.w, av.w, mv.w, vv.w, an.w);
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    for (int p = 0; p < x.world; ++p) *reinterpret_cast<float4*>(x.alpha_ptrs[p] + i) = an;
+  }
+  if (reg_loss != nullptr && reg_b > 0.f) {
+    const float tot = block_sum(reg_acc, red);
+    if (threadIdx.x == 0) atomicAdd(reg_loss, reg_weight * tot * (float)x.world);   // this rank's shard, scaled up
+  }
+  // ---- barrier B: last CTA of the grid signals "my alpha stores are done" and waits for everyone's
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(x.state + 1, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < x.world; ++p) st_release_sys(x.flag_ptrs[p] + x.world + x.rank, epoch);
+      xgpu_wait(x.flag_ptrs[x.rank], 1, x.world, epoch);
+      x.state[1] = 0u;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned*>(x.state) = epoch;
+    }
+  }
+}
+
 // ---- fused weight quantiser -> packed tensor-core operand ----------------------------------------------------------------
 // For every element of the packed operand [phase][co][tap][ci] (conv_tc.cu pack_weights_kernel's layout): fetch the
 // source weight, fake-quantise it (nearest: quantizer.py:175-177; AdaRound soft / hard: :437-449 -- the arithmetic of
@@ -926,6 +1033,30 @@ int b200lic_adaround_bwd_adam_sched(const float* w, float* alpha, const float* d
         w, alpha, delta, zero_point, d_wq, exp_avg, exp_avg_sq, n, ch, inner, (float)(n_levels - 1), ad, grad_scale,
         reg_weight, 0.f, reg_loss, nullptr, sched);
   B200_LAUNCH_CHECK("adaround_bwd_adam_kernel(sched)");
+  return B200LIC_OK;
+}
+
+int b200lic_xgpu_reduce_adam_sched(const float* const* grad_ptrs, float* const* alpha_ptrs, unsigned* const* flag_ptrs,
+                                   unsigned* state, int rank, int world, size_t shard_lo, size_t shard_hi, const float* w,
+                                   const float* delta, const float* zero_point, float* exp_avg, float* exp_avg_sq,
+                                   int outer, int ch, int inner, int n_levels, const b200lic_calib_sched* sched,
+                                   float beta1, float beta2, float eps, float grad_scale, float reg_weight,
+                                   float* reg_loss, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(grad_ptrs && alpha_ptrs && flag_ptrs && state && w && delta && zero_point && exp_avg && exp_avg_sq && sched,
+               "xgpu_reduce_adam_sched: null pointer");
+  B200_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, "xgpu_reduce_adam_sched: rank %d of %d", rank, world);
+  const size_t n = (size_t)outer * ch * inner;
+  B200_REQUIRE(shard_lo <= shard_hi && shard_hi <= n && (shard_lo & 3) == 0 && ((shard_hi - shard_lo) & 3) == 0,
+               "xgpu_reduce_adam_sched: shard [%zu, %zu) must be 4-element aligned inside %zu", shard_lo, shard_hi, n);
+  XgpuArgs x{grad_ptrs, alpha_ptrs, flag_ptrs, state, rank, world, shard_lo, shard_hi};
+  AdamArgs ad{0.f, 0.f, beta1, beta2, eps};
+  const size_t n4 = (shard_hi - shard_lo) >> 2;
+  int grid = grid_for(n4 ? n4 : 1, 256, 4);
+  xgpu_reduce_adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, w, delta, zero_point, exp_avg, exp_avg_sq, ch, inner,
+                                                               (float)(n_levels - 1), sched, ad, grad_scale, reg_weight,
+                                                               reg_loss);
+  B200_LAUNCH_CHECK("xgpu_reduce_adam_kernel");
   return B200LIC_OK;
 }
 

@@ -42,3 +42,36 @@ def reduce_metrics(psnr_sum: float, bpp_sum: float, count: int, device="cpu"):
         dist.all_reduce(acc)
     p, b, c = acc.tolist()
     return p / max(c, 1), b / max(c, 1), int(c)
+
+
+class PeerLayer:
+    """Symmetric (peer-mapped) buffers of one layer for the fused multi-GPU tail (b200lic_xgpu_reduce_adam_sched):
+    every rank allocates [gradient | alpha | flags] through torch's symmetric-memory allocator, the rendezvous exchanges
+    the CUDA IPC handles, and the kernel receives device arrays of the ranks' pointers.  Plumbing only: allocation,
+    handle exchange and pointer tables; the reduction, the Adam step and the barriers are in the kernel."""
+
+    def __init__(self, alpha: torch.nn.Parameter, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        n = alpha.numel()
+        if n % 4 != 0:
+            raise ValueError("layer size must be a multiple of four elements")
+        dev = alpha.device
+        flag_words = 64 * ((2 * self.world + 63) // 64)
+        self.buf = symm.empty(2 * n + flag_words, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.grad = self.buf[:n]
+        self.alpha = self.buf[n:2 * n]
+        self.alpha.copy_(alpha.data.reshape(-1))
+        alpha.data = self.alpha.view(alpha.shape)             # the Parameter now lives in peer-mapped memory
+        self.grad_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.alpha_ptrs = torch.tensor([p + 4 * n for p in ptrs], dtype=torch.int64, device=dev)
+        self.flag_ptrs = torch.tensor([p + 8 * n for p in ptrs], dtype=torch.int64, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int32, device=dev)
+        per = (n // 4 + self.world - 1) // self.world * 4
+        self.lo, self.hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                                    # every rank's buffers are zeroed before anyone signals

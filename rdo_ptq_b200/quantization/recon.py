@@ -108,6 +108,8 @@ class CoderTask:
 
 
 FUSED_DEFAULT = os.environ.get("B200LIC_FUSED", "1") != "0"
+# multi-GPU tail: the fused peer-memory kernel (1) or ncclAllReduce + Adam (0)
+XGPU_DEFAULT = os.environ.get("B200LIC_XGPU", "1") != "0"
 
 
 class FusedLayer:
@@ -145,6 +147,10 @@ class FusedLayer:
         f.y = torch.empty((f.d.N, f.d.Cout, f.d.Ho, f.d.Wo), device=dev, dtype=torch.float32)
         f.dw = torch.empty_like(m.weight.data) if world > 1 else None
         return f
+
+    def use_peer(self, peer, weight):
+        """N > 1 with the peer-memory tail: the weight gradient is written straight into the symmetric buffer."""
+        self.dw = peer.grad.view(weight.shape)
 
 
 class FusedGdn:
@@ -229,6 +235,14 @@ class UnitTrainer:
         self.last = {}
         self.fused = FUSED_DEFAULT                      # A/B switch: the fused iteration where it applies
         self._fused_plan = False                        # False = not built yet; None = not applicable
+        # N > 1: gradients are summed and alpha is updated by ONE kernel over NVLink peer memory
+        # (b200lic_xgpu_reduce_adam_sched) instead of ncclAllReduce + Adam; alpha moves into peer-mapped buffers.  Every
+        # rank takes the same decision (same shapes, same environment).
+        self.peer = None
+        if self.world > 1 and XGPU_DEFAULT and not learn_delta and self.mods and \
+                all(m.weight.numel() % 4 == 0 for m in self.mods):
+            from .. import dist as _dist
+            self.peer = [_dist.PeerLayer(m.weight_quantizer.alpha, process_group) for m in self.mods]
 
     # -- the fused iteration (single conv / transposed-conv unit, reference-default loss) --------------------------------
     def fused_plan(self, in_shape, batch):
@@ -239,6 +253,11 @@ class UnitTrainer:
             if ok:
                 self._fused_plan = (FusedGdn.build(self.unit, in_shape, batch, self.world) if self.unit.is_gdn else
                                     FusedLayer.build(self.unit, in_shape, batch, self.world))
+                if self._fused_plan is not None and self.peer is not None:
+                    if isinstance(self._fused_plan, FusedGdn):
+                        self._fused_plan.dleaf = self.peer[0].grad.view(self._fused_plan.leaf.shape)
+                    else:
+                        self._fused_plan.use_peer(self.peer[0], self.unit.weight.data)
         return self._fused_plan
 
     def _fused_gdn(self, f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base):
@@ -361,6 +380,15 @@ class UnitTrainer:
             reg_b = 0.0 if self.count < self.loss_start else float(b)
         if not grads:                                # the fused tail already applied this iteration's Adam step
             return
+        if self.peer is not None and sched is not None:
+            for i, m in enumerate(self.mods):
+                q, pl = m.weight_quantizer, self.peer[i]
+                if grads[i].data_ptr() != pl.grad.data_ptr():
+                    pl.grad.copy_(grads[i].reshape(-1))       # autograd-tape units: stage the gradient for the peers
+                ops.xgpu_reduce_adam_sched(pl, m.weight.data, q.delta, q.zero_point, self.exp_avg[i], self.exp_avg_sq[i],
+                                           q.axis, q.n_levels, sched, grad_scale=1.0 / self.world, reg_weight=self.weight,
+                                           reg_loss=self.loss_buf[2:3])
+            return
         if self.world > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
         for i, m in enumerate(self.mods):
@@ -416,6 +444,11 @@ class UnitTrainer:
             m.trained = True
         if self.rd_task is not None:
             self.rd_task.close()
+        if self.peer is not None:           # alpha leaves the peer-mapped buffers (they die with the trainer)
+            for m in self.mods:
+                a = m.weight_quantizer.alpha
+                a.data = a.data.clone()
+            self.peer = None
 
 
 def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_size: int, input_prob: float,

@@ -26,9 +26,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(dev, cali, batch, process_group=None):
-    """10 graph-replayed AdaRound iterations on three units (conv, GDN, transposed conv); returns their alphas."""
-    from rdo_ptq_b200 import codec, synth, quantization as Q
+def _run(dev, cali, batch, process_group=None, xgpu=True):
+    """10 graph-replayed AdaRound iterations on three units (conv, GDN, transposed conv); returns their alphas.
+    xgpu: the multi-GPU tail runs as the fused peer-memory kernel (True) or as ncclAllReduce + Adam (False)."""
+    from rdo_ptq_b200 import codec, ops, synth, quantization as Q
+    from rdo_ptq_b200.quantization import recon
+    recon.XGPU_DEFAULT = xgpu
+    calls, real = [0], ops.xgpu_reduce_adam_sched
+
+    def counted(*a, **k):
+        calls[0] += 1
+        return real(*a, **k)
+    ops.xgpu_reduce_adam_sched = counted
     torch.manual_seed(1005)
     m = codec.ARCHS["mbt2018-mean"](N=16, M=24).eval()
     synth.init_weights(m, gain=1.2)
@@ -48,6 +57,9 @@ def _run(dev, cali, batch, process_group=None):
                                warmup=0.2, input_prob=1.0, asym=True, act_quant=False, opt_mode="mse", args=Args(),
                                unit_id=uid, process_group=process_group)
         out[path] = layer.weight_quantizer.alpha.data.clone()
+    ops.xgpu_reduce_adam_sched = real
+    # eager warm-up iterations + the captured one, per unit -- or never, on the NCCL path / a single rank
+    assert (calls[0] >= 3 * len(PATHS)) == bool(xgpu and process_group is not False and torch.distributed.is_initialized())
     return out
 
 
@@ -59,14 +71,17 @@ def _worker(rank, world, port, q):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     pool = synth.calibration_patches(8, 64)
-    alphas = _run(dev, pool[rank::world].contiguous().to(dev), 8 // world)
+    nccl = _run(dev, pool[rank::world].contiguous().to(dev), 8 // world, xgpu=False)
+    alphas = _run(dev, pool[rank::world].contiguous().to(dev), 8 // world, xgpu=True)
     same = True
     for path, a in alphas.items():
         parts = [torch.empty_like(a) for _ in range(world)]
-        dist.all_gather(parts, a)
+        dist.all_gather(parts, a.contiguous())
         same &= all(torch.equal(parts[0], p) for p in parts[1:])
+    # the peer-memory tail against ncclAllReduce + Adam: at two ranks the sum a + b has one order, so bit for bit
+    same_as_nccl = all(torch.equal(alphas[k], nccl[k]) for k in alphas)
     if rank == 0:
-        q.put((same, {k: v.cpu() for k, v in alphas.items()}))
+        q.put((same, same_as_nccl, {k: v.cpu() for k, v in alphas.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,10 +97,11 @@ def test_two_ranks_keep_alpha_bit_identical_and_match_one_rank():
     q, port = ctx.Queue(), _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    same, got = q.get(timeout=600)
+    same, same_as_nccl, got = q.get(timeout=600)
     [p.join(timeout=120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    assert same, "alpha differs between the ranks after 10 all-reduced steps"
+    assert same, "alpha differs between the ranks after 10 steps"
+    assert same_as_nccl, "the peer-memory tail and ncclAllReduce + Adam disagree"
     for path in PATHS:
         d = (got[path] - ref[path]).abs()
         moved = (ref[path] - got[path]).abs().max().item()
