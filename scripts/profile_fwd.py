@@ -67,13 +67,18 @@ def main():
                 first = False
             with torch.no_grad():
                 if args.eager:
-                    qnn(x)
-                    torch.cuda.synchronize()
-                    n0 = _lib.launch_count()
-                    for _ in range(args.reps):
-                        out = qnn(x)
-                        E.total_bits(out)
-                    torch.cuda.synchronize()
+                    from rdo_ptq_b200 import ops
+                    with ops.defer_actq():                  # what evaluate.GraphedForward captures
+                        qnn(x)
+                        qnn(x)
+                        torch.cuda.synchronize()
+                        n0 = _lib.launch_count()
+                        torch.cuda.profiler.start()         # ncu --profile-from-start off: the steady-state forward only
+                        for _ in range(args.reps):
+                            out = qnn(x)
+                            E.total_bits(out)
+                        torch.cuda.synchronize()
+                        torch.cuda.profiler.stop()
                     print(json.dumps({"arch": arch, "hw": hw, "launches_per_fwd": (_lib.launch_count() - n0) / args.reps}))
                     continue
                 gf = E.GraphedForward(qnn)
