@@ -401,6 +401,20 @@ B200LIC_API int b200lic_quant_pack_weights(const b200lic_conv_desc* d, int op, c
 B200LIC_API int b200lic_conv_fwd_packed(const b200lic_conv_desc* d, int op, const float* x, const void* packed_w,
                             const float* w_scale, const float* bias, const float* gdn_x, float* norm_out, float* y,
                             void* workspace, size_t workspace_bytes, b200lic_stream_t stream);
+/* GDN / IGDN forward in one kernel over the raw fp32 NCHW tensor (replaces compressai.layers.GDN.forward as wrapped by
+ * TO quant_layer.py:57-78; evaluation path): y = xq * rsqrt(beta + gamma . xq^2) (inverse: * sqrt), gamma given as the
+ * prepared operand of b200lic_conv_pack_weights for the 1x1 descriptor, beta[C] the reparametrised bias.  minmax != NULL:
+ * x is the un-quantised output of the previous layer and minmax its b200lic_actq_stats result -- xq is the n_bits dynamic
+ * quantiser of x (n_bits <= 8; bit-identical to b200lic_actq_apply), applied on chip; minmax == NULL: xq = x.  HBM traffic
+ * 8 B/element.
+ * b200lic_gdn_fused_ok: 1 when the shape is eligible (HW % 4 == 0, C <= 256); otherwise B200LIC_ERR_UNSUPPORTED. */
+B200LIC_API int b200lic_gdn_fused_ok(int C, int HW);
+/* Test hook: counts, into *mismatches_dev (device, caller-zeroed), the pairs for which the kernel's FMA division differs
+ * from the correctly rounded one over n pseudo-random (value, range) pairs and every code / levels table. */
+B200LIC_API int b200lic_selftest_fast_div(unsigned long long n, unsigned long long seed, unsigned long long* mismatches_dev,
+                              b200lic_stream_t stream);
+B200LIC_API int b200lic_gdn_fwd_fused(const float* x, const float* minmax, int n_bits, const void* packed_gamma,
+                          const float* beta, int N, int C, int HW, int inverse, float* y, b200lic_stream_t stream);
 /* Where a forward workspace expects the staged activation operand ([N,H,W,cpad] bf16 hi and lo; x*x for in_square),
  * and where a weight-gradient workspace (B200LIC_OP_CONV_WGRAD / _DECONV_WGRAD) expects the staged dY
  * ([N,Ho,Wo,cpad]).  NULL / 0 when the shape stages differently. */

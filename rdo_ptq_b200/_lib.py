@@ -96,6 +96,8 @@ SIGNATURES = {
                               _F, _F, _P, _P],
     "xgpu_reduce_adam_sched": [_P, _P, _P, _P, _I, _I, _SZ, _SZ, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F, _F, _F,
                                _P],
+    "gdn_fwd_fused": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "selftest_fast_div": [_ULL, _ULL, _P],
     "attn_gate": [_P, _P, _P, _SZ, _P],
     "abs": [_P, _SZ, _P],
     "pixel_shuffle": [_P, _I, _I, _I, _I, _I, _I, _F, _P],
@@ -105,6 +107,7 @@ PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "devic
          "launch_count": (C.c_ulonglong, []), "factorized_table_floats": (C.c_int, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
          "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
          "set_option": (C.c_int, [C.c_char_p, C.c_int]),
+         "gdn_fused_ok": (C.c_int, [C.c_int, C.c_int]),
          "conv_staged_view": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p)]),
          "conv_packed_weight_bytes": (C.c_size_t, [_D, C.c_int]),

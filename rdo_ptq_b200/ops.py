@@ -738,6 +738,25 @@ def conv_fwd_packed(x, packed, d, transposed, bias=None, w_scale=None, gdn_x=Non
     return (y, norm) if want_norm else y
 
 
+GDN_FUSED = True           # evaluation GDN / IGDN through b200lic_gdn_fwd_fused when the shape allows (tests flip it for A/B)
+
+
+def gdn_fused_ok(C_, HW):
+    return GDN_FUSED and bool(_lib.lib().b200lic_gdn_fused_ok(int(C_), int(HW)))
+
+
+def gdn_fwd_fused(x, packed, beta, inverse, pending=None, y=None):
+    """GDN / IGDN forward in one kernel over the raw NCHW tensor: b200lic_gdn_fwd_fused.  `pending` = (minmax keys,
+    n_bits) of a deferred activation quantiser on x (applied on chip), or None."""
+    x = _c(x.detach(), "input")
+    N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+    if y is None:
+        y = torch.empty_like(x)
+    keys, bits = pending if pending is not None else (None, 8)
+    call("gdn_fwd_fused", _p(x), _p(keys), int(bits), _p(packed), _p(_c(beta)), N, Cc, HW, int(bool(inverse)), _p(y))
+    return y
+
+
 def _slot(name, d, op, ws):
     wsb, nws = ws
     if wsb is None:

@@ -157,6 +157,10 @@ class QuantModule(nn.Module):
         packed, scale, bias = prep
         x = ops._c(input, "input")
         pend = getattr(input, "_b200_actq", None)
+        if self.is_gdn and (pend is None or pend[1] <= 8) and ops.gdn_fused_ok(x.shape[1], x.shape[2] * x.shape[3]):
+            # one kernel over the raw tensor: quantiser (if deferred to us), square, GEMM and epilogue on chip
+            out = ops.gdn_fwd_fused(x, packed, bias, self.fwd_kwargs["inverse"], pending=pend)
+            return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
         if pend is not None:
             # the producer deferred its activation quantiser to us: quantise while staging our own operand
             slot = ops.conv_x_slot(d, self.if_tconv, ws)

@@ -74,6 +74,55 @@ def test_gdn_forward_with_prepared_gamma(ops, dev):
         assert torch.equal(y, y_ref) and torch.equal(n, n_ref)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 16, 24), (1, 192, 64, 96), (3, 192, 30, 22), (1, 128, 200, 130), (2, 80, 12, 20),
+                                   (1, 256, 40, 36), (148, 192, 16, 16)])
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("deferred", [False, True])
+def test_gdn_one_kernel_forward(ops, dev, shape, inverse, deferred):
+    """b200lic_gdn_fwd_fused (operand squared / split / quantised on chip, MN-major tcgen05 operand) against the staged
+    conv-engine form: fp64 GDN as the yardstick for both, and the two against each other at fp32 rounding level.
+    Ragged pixel tails (HW % 128 != 0), several images, channel counts that pad to 32, more tiles than SMs."""
+    N, Cc, H, W = shape
+    g = torch.Generator().manual_seed(11 + Cc + H)
+    x = (torch.randn(N, Cc, H, W, generator=g) * 2).to(dev)
+    gam = (torch.rand(Cc, Cc, generator=g) * 0.02 + 0.1 * torch.eye(Cc)).to(dev)
+    bet = (1 + torch.rand(Cc, generator=g)).to(dev)
+    d = ops.gdn_desc(x.shape, inverse)
+    packed = ops.pack_weights(gam.view(Cc, Cc, 1, 1), d, False)
+    assert ops.gdn_fused_ok(Cc, H * W)
+    if deferred:
+        keys = ops.act_quant_stats(x)
+        xq = ops.act_quant_apply(x, keys, 8)
+        y = ops.gdn_fwd_fused(x, packed, bet, inverse, pending=(keys, 8))
+    else:
+        xq = x
+        y = ops.gdn_fwd_fused(x, packed, bet, inverse)
+    y_ref = ops.conv_fwd_packed(xq, packed, d, False, bias=bet, gdn_x=xq)
+    x64 = xq.double()
+    nrm = torch.einsum("ok,nkhw->nohw", gam.double(), x64 * x64) + bet.double().view(1, -1, 1, 1)
+    y64 = x64 * (nrm.sqrt() if inverse else nrm.rsqrt())
+    scale = y64.abs().max().item()
+    e_new = (y.double() - y64).abs().max().item() / scale
+    e_old = (y_ref.double() - y64).abs().max().item() / scale
+    assert e_new < 5e-6 and e_new < 2 * e_old + 2e-7, (e_new, e_old)
+    assert (y - y_ref).abs().max().item() / scale < 5e-6      # one flipped 8-bit code would be ~4e-3
+
+
+def test_gdn_one_kernel_division_is_correctly_rounded(ops, dev):
+    """The on-chip quantiser divides with an FMA sequence on a precomputed reciprocal; it must round like the IEEE
+    division of b200lic_actq_apply for the codes to stay bit-identical: 2^28 pseudo-random (value, range) pairs and the
+    exhaustive code / levels tables of 2..16 bit."""
+    from rdo_ptq_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.call("selftest_fast_div", 1 << 28, 1005, bad.data_ptr())
+    assert int(bad.item()) == 0
+
+
+def test_gdn_one_kernel_rejects_what_it_cannot_tile(ops, dev):
+    assert not ops.gdn_fused_ok(192, 30 * 31 + 1)      # HW % 4 != 0: TMA row pitch
+    assert not ops.gdn_fused_ok(320, 64 * 64)          # accumulator wider than 256 TMEM columns
+
+
 @pytest.mark.parametrize("transposed,Cin", [(False, 64), (True, 64), (False, 96)])
 @pytest.mark.parametrize("prob", [0.5, 1.0])
 def test_stage_mix_equals_gather_mix_then_split(ops, dev, transposed, Cin, prob):
