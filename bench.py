@@ -384,8 +384,15 @@ def hbm_rooflines(ops, dev, flush, pk):
     bet = torch.ones(192).to(dev)
     dg = ops.gdn_desc(a.shape, False)
     xa = a.abs() + 0.1
-    add("K3 GDN forward (8 B/elem: x in, y out)", lambda: ops.conv2d_raw(xa, gam.view(192, 192, 1, 1), bet, dg, gdn_x=xa),
+    pk_g = ops.pack_weights(gam.view(192, 192, 1, 1), dg, False)
+    yg = torch.empty_like(xa)
+    keys = ops.act_quant_stats(xa)
+    add("K3 GDN forward, one kernel (8 B/elem: x in, y out)", lambda: ops.gdn_fwd_fused(xa, pk_g, bet, False, y=yg),
         8.0 * a.numel(), "[8,192,128,128]")
+    add("K3+K8 GDN forward with the deferred A8 quantiser of its input applied on chip (8 B/elem)",
+        lambda: ops.gdn_fwd_fused(xa, pk_g, bet, False, pending=(keys, 8), y=yg), 8.0 * a.numel(), "[8,192,128,128]")
+    add("K3 GDN forward, round-1 form: staged x^2 operand + conv engine (8 B/elem algorithmic)",
+        lambda: ops.conv2d_raw(xa, gam.view(192, 192, 1, 1), bet, dg, gdn_x=xa), 8.0 * a.numel(), "[8,192,128,128]")
     add("K3 GDN forward + norm for backward (12 B/elem)",
         lambda: ops.conv2d_raw(xa, gam.view(192, 192, 1, 1), bet, dg, gdn_x=xa, want_norm=True), 12.0 * a.numel(),
         "[8,192,128,128]")

@@ -415,6 +415,35 @@ B200LIC_API int b200lic_selftest_fast_div(unsigned long long n, unsigned long lo
                               b200lic_stream_t stream);
 B200LIC_API int b200lic_gdn_fwd_fused(const float* x, const float* minmax, int n_bits, const void* packed_gamma,
                           const float* beta, int N, int C, int HW, int inverse, float* y, b200lic_stream_t stream);
+/* ---- Entropy coding of the latents -------------------------------------------------------------
+ * What the reference reaches through compressai 1.2.4 (`update()`, `compress()`, `decompress()`; task-oriented-PTQ/
+ * models/nic_cvt.py:426-570, light-uniform-PTQ/models/tinylic.py:236-367).
+ * b200lic_pmf_to_quantized_cdf: HOST pointers, runs on the host (table build, parameter-sized).  Row r of pmf
+ * [rows, max_length] (pmf_length[r] live entries) followed by tail_mass[r] becomes the 16-bit CDF row r of cdf_out
+ * [rows, max_length + 2] (pmf_length[r] + 2 live entries, zero padded), every symbol keeping a non-zero width
+ * (compressai ops.cpp pmf_to_quantized_cdf + EntropyModel._pmf_to_cdf). */
+B200LIC_API int b200lic_pmf_to_quantized_cdf(const float* pmf, const float* tail_mass, const int* pmf_length, int rows,
+                                 int max_length, int* cdf_out);
+/* symbols = round_half_even(x - means) (means: NULL, [C] with means_per_channel != 0, or like x) and the table row of
+ * every element: the channel (scales == NULL: EntropyBottleneck) or GaussianConditional.build_indexes(scales) over the
+ * ascending scale_table[levels] with the lower bound scale_bound.  x is [*, C, HW]-shaped, n elements. */
+B200LIC_API int b200lic_rans_symbols(const float* x, const float* means, int means_per_channel, const float* scales,
+                         const float* scale_table, int levels, float scale_bound, int C, int HW, size_t n, int* symbols,
+                         int* indexes, b200lic_stream_t stream);
+/* Chunked rANS (ryg rans64 as compressai's rans_interface.cpp drives it: 16-bit CDFs, 32-bit words, 4-bit bypass digits
+ * behind the last CDF entry): chunk c = symbols [c*chunk, (c+1)*chunk) is one complete stream.  _sizes writes the word
+ * count of every chunk; the caller prefix-sums them into chunk_off[n_chunks + 1]; _write stores stream c at
+ * out_words[chunk_off[c] .. chunk_off[c+1]); _decode is the inverse.  cdf [rows, cdf_stride], cdf_len, offset as
+ * produced by b200lic_pmf_to_quantized_cdf / the models' update(). */
+B200LIC_API int b200lic_rans_encode_sizes(const int* symbols, const int* indexes, unsigned n, unsigned chunk, const int* cdf,
+                              const int* cdf_len, const int* offset, int cdf_stride, unsigned* chunk_words,
+                              b200lic_stream_t stream);
+B200LIC_API int b200lic_rans_encode_write(const int* symbols, const int* indexes, unsigned n, unsigned chunk, const int* cdf,
+                              const int* cdf_len, const int* offset, int cdf_stride, const unsigned* chunk_off,
+                              unsigned* out_words, b200lic_stream_t stream);
+B200LIC_API int b200lic_rans_decode(const unsigned* words, const unsigned* chunk_off, unsigned n, unsigned chunk,
+                        const int* indexes, const int* cdf, const int* cdf_len, const int* offset, int cdf_stride,
+                        int* symbols, b200lic_stream_t stream);
 /* Where a forward workspace expects the staged activation operand ([N,H,W,cpad] bf16 hi and lo; x*x for in_square),
  * and where a weight-gradient workspace (B200LIC_OP_CONV_WGRAD / _DECONV_WGRAD) expects the staged dY
  * ([N,Ho,Wo,cpad]).  NULL / 0 when the shape stages differently. */

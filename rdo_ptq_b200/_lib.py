@@ -98,6 +98,10 @@ SIGNATURES = {
                                _P],
     "gdn_fwd_fused": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "selftest_fast_div": [_ULL, _ULL, _P],
+    "rans_symbols": [_P, _P, _I, _P, _P, _I, _F, _I, _I, _SZ, _P, _P],
+    "rans_encode_sizes": [_P, _P, C.c_uint, C.c_uint, _P, _P, _P, _I, _P],
+    "rans_encode_write": [_P, _P, C.c_uint, C.c_uint, _P, _P, _P, _I, _P, _P],
+    "rans_decode": [_P, _P, C.c_uint, C.c_uint, _P, _P, _P, _P, _I, _P],
     "attn_gate": [_P, _P, _P, _SZ, _P],
     "abs": [_P, _SZ, _P],
     "pixel_shuffle": [_P, _I, _I, _I, _I, _I, _I, _F, _P],
@@ -108,6 +112,7 @@ PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "devic
          "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
          "set_option": (C.c_int, [C.c_char_p, C.c_int]),
          "gdn_fused_ok": (C.c_int, [C.c_int, C.c_int]),
+         "pmf_to_quantized_cdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
          "conv_staged_view": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p)]),
          "conv_packed_weight_bytes": (C.c_size_t, [_D, C.c_int]),

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import coding
 from .layers import LowerBound
 
 
@@ -41,6 +42,7 @@ class EntropyBottleneck(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_prior_cache"] = None     # derived from the parameters; rebuilt on first use after un-pickling
+        state.pop("_tables", None)       # coding tables: rebuilt by update()
         return state
 
     def _prior(self):
@@ -85,6 +87,39 @@ class EntropyBottleneck(nn.Module):
         self.last_bits = bits
         return z_hat, lik
 
+    # -- real entropy coding (compressai EntropyBottleneck.update / compress / decompress) -------------
+    def update(self, force=False):
+        """Build the quantised CDF of every channel from its quantiles (compressai EntropyBottleneck.update)."""
+        if getattr(self, "_tables", None) is not None and not force:
+            return False
+        pmf, tail, length, offset = coding.bottleneck_pmf(self)
+        cdf = coding.quantized_cdf_rows(pmf, tail, length)
+        self._tables = coding.Tables(cdf, length + 2, offset, self.quantiles.device)
+        return True
+
+    def _coding_tables(self):
+        if getattr(self, "_tables", None) is None:
+            raise RuntimeError("EntropyBottleneck: call update() before compress() / decompress()")
+        if self._tables.cdf.device != self.quantiles.device:
+            self._tables = coding.Tables(*self._tables.host, self.quantiles.device)
+        return self._tables
+
+    def compress(self, x, chunk=coding.DEFAULT_CHUNK):
+        """[B,C,H,W] -> one string per image: symbols = round(x - median), table row = channel."""
+        t = self._coding_tables()
+        med = self._get_medians().detach().reshape(-1)
+        sym, idx = coding.symbols_and_indexes(x, means=med)
+        return [coding.encode(sym[b], idx[b], t, chunk) for b in range(x.shape[0])]
+
+    def decompress(self, strings, size):
+        t = self._coding_tables()
+        dev = self.quantiles.device
+        H, W = int(size[0]), int(size[1])
+        idx = torch.arange(self.channels, dtype=torch.int32, device=dev).view(-1, 1, 1).expand(-1, H, W).contiguous()
+        med = self._get_medians().detach().reshape(1, -1, 1, 1)
+        out = torch.stack([coding.decode(s, idx, t) for s in strings])
+        return out.to(torch.float32) + med
+
     def loss(self):
         """aux loss |logits(quantiles) - target| (quant_model.py:72-79).  Parameter-sized (C x 3) host-side helper,
         not a data-path op; evaluated with plain tensor ops."""
@@ -104,6 +139,46 @@ class GaussianConditional(nn.Module):
         self.lower_bound_scale = LowerBound(scale_bound)
         self.last_bits = None
         self.ste_round = False           # see EntropyBottleneck.ste_round
+        self.tail_mass = float(tail_mass)
+        self.scale_table = None if scale_table is None else torch.as_tensor(scale_table, dtype=torch.float32)
+        self._tables = None
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_tables"] = None
+        return state
+
+    # -- real entropy coding (compressai GaussianConditional.update_scale_table / build_indexes / compress / decompress) ----
+    def update_scale_table(self, scale_table, force=False):
+        if self._tables is not None and not force:
+            return False
+        self.scale_table = torch.as_tensor(scale_table, dtype=torch.float32)
+        pmf, tail, length, offset = coding.gaussian_pmf(self.scale_table, self.tail_mass)
+        cdf = coding.quantized_cdf_rows(pmf, tail, length)
+        self._tables = coding.Tables(cdf, length + 2, offset, "cpu")
+        return True
+
+    def _coding_tables(self, device):
+        if self._tables is None:
+            raise RuntimeError("GaussianConditional: call update_scale_table() before compress() / decompress()")
+        if self._tables.cdf.device != torch.device(device):
+            self._tables = coding.Tables(*self._tables.host, device)
+            self.scale_table = self.scale_table.to(device)
+        return self._tables
+
+    def build_indexes(self, scales):
+        self._coding_tables(scales.device)
+        return coding.symbols_and_indexes(scales, scales=scales, scale_table=self.scale_table, bound=self.scale_bound)[1]
+
+    def compress(self, inputs, indexes, means=None, chunk=coding.DEFAULT_CHUNK):
+        t = self._coding_tables(inputs.device)
+        sym, _ = coding.symbols_and_indexes(inputs, means=means)
+        return [coding.encode(sym[b], indexes[b], t, chunk) for b in range(inputs.shape[0])]
+
+    def decompress(self, strings, indexes, means=None):
+        t = self._coding_tables(indexes.device)
+        out = torch.stack([coding.decode(s, indexes[b], t) for b, s in enumerate(strings)]).to(torch.float32)
+        return out if means is None else out + means
 
     def quantize(self, inputs, mode, means=None):
         if mode != "dequantize":

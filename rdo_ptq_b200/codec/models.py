@@ -34,6 +34,36 @@ class ScaleHyperprior(nn.Module):
         y_hat, y_lik = self.gaussian_conditional(y, scales)
         return {"x_hat": self.g_s(y_hat), "likelihoods": {"y": y_lik, "z": z_lik}}
 
+    # -- real entropy coding (compressai CompressionModel.update / ScaleHyperprior.compress / decompress) ----------------
+    def update(self, scale_table=None, force=False):
+        from .coding import get_scale_table
+        a = self.gaussian_conditional.update_scale_table(get_scale_table() if scale_table is None else scale_table, force)
+        b = self.entropy_bottleneck.update(force)
+        return a or b
+
+    def _scales_means(self, params):
+        return params, None
+
+    @torch.no_grad()
+    def compress(self, x):
+        """{"strings": [y_strings, z_strings], "shape": z spatial size}; one string per image and latent."""
+        y = self.g_a(x)
+        z = self.h_a(self._hyper_in(y))
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.shape[-2:])
+        scales, means = self._scales_means(self.h_s(z_hat))
+        indexes = self.gaussian_conditional.build_indexes(scales)
+        y_strings = self.gaussian_conditional.compress(y, indexes, means=means)
+        return {"strings": [y_strings, z_strings], "shape": tuple(z.shape[-2:])}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        scales, means = self._scales_means(self.h_s(z_hat))
+        indexes = self.gaussian_conditional.build_indexes(scales)
+        y_hat = self.gaussian_conditional.decompress(strings[0], indexes, means=means)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
+
     # -- tail of the forward from the output of one sub-network (R + lambda*D task criterion of the calibration) -------
     def _hyper_in(self, y):
         return ops.abs_fn(y)
@@ -83,6 +113,9 @@ class MeanScaleHyperprior(ScaleHyperprior):
     def _hyper_in(self, y):
         return y
 
+    def _scales_means(self, params):
+        return params.chunk(2, 1)
+
     def _gauss(self, y, params):
         scales, means = params.chunk(2, 1)
         return self.gaussian_conditional(y, scales, means=means, training=False)
@@ -113,6 +146,14 @@ class Cheng2020Attention(nn.Module):
                                                 Conv2d(M * 8 // 3, M * 6 // 3, 1))
         self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
         self.gaussian_conditional = GaussianConditional(None)
+
+    def compress(self, x):
+        raise NotImplementedError("cheng2020-attn: y is coded under the masked 5x5 context model, whose decoder is serial "
+                                  "in raster order (compressai runs it on the CPU); the chunked rANS coder covers the "
+                                  "hyperprior families (bmshj2018-hyperprior, mbt2018-mean) -- DESIGN.md section 8")
+
+    def decompress(self, strings, shape):
+        raise NotImplementedError("cheng2020-attn: see compress()")
 
     def forward(self, x):
         y = self.g_a(x)
