@@ -455,6 +455,8 @@ def forward_legs(args, build, E, synth, dev, rank, world, barrier, maxr):
                                  "note": "config 5: evaluate.evaluate over 41 2K images, round-robin over the ranks, "
                                          "per-image PSNR + bpp read back, one 3-number all-reduce; wall clock, max "
                                          "over ranks"}
+    if not args.skip_extra and rank == 0:
+        out["entropy_coding"] = coding_leg(qnn3, E, synth, dev)
     del qnn3, gf
     torch.cuda.empty_cache()
     if not args.skip_extra:
@@ -475,6 +477,87 @@ def forward_legs(args, build, E, synth, dev, rank, world, barrier, maxr):
                 PUAQ.act_bits_follow_n_bits = False
         torch.cuda.empty_cache()
     return out
+
+
+def coding_leg(qnn, E, synth, dev, reps=5):
+    """Next row N2: real strings of the W8A8 codec's latents.  compress() = analysis transforms + symbol/index kernel +
+    chunked rANS encode (sizes pass, prefix sum, write pass, D2H of the strings); decompress() = H2D + decode + synthesis.
+    Wall clock (the strings cross the PCIe bus by definition).  `coder_msym_s`: the rANS kernels alone, strings on the device.
+    `cpu_port_msym_s`: the oracle's sequential restatement (pure Python, 1 core) on a 20k-symbol sample of the same latents
+    -- compressai's C++ coder is not installed here, so no faster CPU arm exists to time."""
+    from rdo_ptq_b200.codec import coding
+    from oracle import rans as R
+    res = {}
+    model = qnn.model
+    model.update()
+    with torch.no_grad():
+        for tag, (h, w_) in (("768x512", (512, 768)), ("2k", (1365, 2048))):
+            xp = E.pad(synth.synthetic_image(h, w_, seed=1005).to(dev), 256)
+            out = model.compress(xp)
+            rec = model.decompress(out["strings"], out["shape"])
+            fwd = qnn(xp)
+            exact = bool(torch.equal(rec["x_hat"], fwd["x_hat"].clamp(0, 1)))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = model.compress(xp)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(reps):
+                model.decompress(out["strings"], out["shape"])
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            est = sum(float((-torch.log2(l)).sum()) for l in fwd["likelihoods"].values()) / (h * w_)
+            # the coder alone on the y latents
+            y = model.g_a(xp)
+            z_hat = model.entropy_bottleneck.decompress(out["strings"][1], out["shape"])
+            scales, means = model._scales_means(model.h_s(z_hat))
+            gc = model.gaussian_conditional
+            idx = gc.build_indexes(scales)
+            sym, _ = coding.symbols_and_indexes(y, means=means)
+            t = gc._coding_tables(dev)
+            n = sym.numel()
+            chunk = coding.DEFAULT_CHUNK
+            n_chunks = (n + chunk - 1) // chunk
+            sizes = torch.empty(n_chunks, dtype=torch.int32, device=dev)
+            offs = torch.zeros(n_chunks + 1, dtype=torch.int32, device=dev)
+            sy, ix = sym.reshape(-1), idx.reshape(-1)
+            args_t = (E.ops._p(t.cdf), E.ops._p(t.cdf_length), E.ops._p(t.offset), t.stride)
+            E.ops.call("rans_encode_sizes", E.ops._p(sy), E.ops._p(ix), n, chunk, *args_t, E.ops._p(sizes))
+            torch.cumsum(sizes, 0, out=offs[1:])
+            words = torch.empty(int(offs[-1].item()), dtype=torch.int32, device=dev)
+            dec = torch.empty(n, dtype=torch.int32, device=dev)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(reps):
+                E.ops.call("rans_encode_sizes", E.ops._p(sy), E.ops._p(ix), n, chunk, *args_t, E.ops._p(sizes))
+                E.ops.call("rans_encode_write", E.ops._p(sy), E.ops._p(ix), n, chunk, *args_t, E.ops._p(offs), E.ops._p(words))
+            ev[1].record()
+            for _ in range(reps):
+                E.ops.call("rans_decode", E.ops._p(words), E.ops._p(offs), n, chunk, E.ops._p(ix), *args_t, E.ops._p(dec))
+            ev[2].record()
+            torch.cuda.synchronize()
+            res[tag] = {"round_trip_exact": exact and bool(torch.equal(dec, sy)),
+                        "file_bpp": 8 * coding.string_bytes(out["strings"]) / (h * w_), "estimated_bpp": est,
+                        "compress_ms": (t1 - t0) / reps * 1e3, "decompress_ms": (t2 - t1) / reps * 1e3,
+                        "compress_mpx_s": h * w_ / 1e6 / ((t1 - t0) / reps), "decompress_mpx_s": h * w_ / 1e6 / ((t2 - t1) / reps),
+                        "y_symbols": n, "chunks": n_chunks,
+                        "coder_encode_msym_s": n / 1e6 / (ev[0].elapsed_time(ev[1]) / reps / 1e3),
+                        "coder_decode_msym_s": n / 1e6 / (ev[1].elapsed_time(ev[2]) / reps / 1e3)}
+            if tag == "768x512":
+                cdf, cdf_len, off = t.host
+                s_np, i_np = sy[:20000].cpu().numpy(), ix[:20000].cpu().numpy()
+                t0 = time.perf_counter()
+                wds = R.rans64_encode(s_np, i_np, cdf, cdf_len, off)
+                t1 = time.perf_counter()
+                R.rans64_decode(wds, len(s_np), i_np, cdf, cdf_len, off)
+                t2 = time.perf_counter()
+                res["cpu_port_msym_s"] = {"encode": len(s_np) / 1e6 / (t1 - t0), "decode": len(s_np) / 1e6 / (t2 - t1),
+                                          "cores": 1, "kind": "port",
+                                          "sample": "first 20000 y symbols of the 768x512 image, pure-Python restatement"}
+    res["note"] = ("mbt2018-mean N=192 M=320 W8A8; strings = header + chunk table + one rans64 stream per 2048 symbols; "
+                   "file_bpp counts every byte of every string")
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------------- CPU arms

@@ -57,10 +57,23 @@ struct RansEnc {
     ++count;
     x >>= 32;
   }
+  // Rans64EncPut, scale_bits = 16.  x / freq is the chain every symbol waits for, and a 64-bit integer division is a
+  // ~100-instruction subroutine here; `rd` = 1.0 / freq is computed off the chain (eight symbols at a time), the quotient
+  // estimate floor(x * rd) is within one of the true quotient (x < 2^47 * freq after the renormalisation, so the estimate
+  // errs by < 2^-4), and the remainder settles it exactly.
   template <bool WRITE>
-  __device__ __forceinline__ void put(unsigned start, unsigned freq) {          // Rans64EncPut, scale_bits = 16
-    if (x >= ((kRansL >> kPrecision) << 32) * (uint64_t)freq) emit<WRITE>();
-    x = ((x / freq) << kPrecision) + (x % freq) + start;
+  __device__ __forceinline__ void put(unsigned start, unsigned freq, double rd) {
+    if (x >= ((uint64_t)freq << 47)) emit<WRITE>();
+    uint64_t q = __double2ull_rz(__ull2double_rz(x) * rd);
+    long long r = (long long)(x - q * freq);
+    if (r < 0) {
+      --q;
+      r += freq;
+    } else if (r >= (long long)freq) {
+      ++q;
+      r -= freq;
+    }
+    x = (q << kPrecision) + (uint64_t)r + start;
   }
   template <bool WRITE>
   __device__ __forceinline__ void put_bits(unsigned val) {                      // Rans64EncPutBits, 4 bits
@@ -82,28 +95,56 @@ __global__ void __launch_bounds__(32)
   e.x = kRansL;
   e.ptr = WRITE ? out + chunk_off[c + 1] : nullptr;
   e.count = 0;
-  for (unsigned i = hi; i-- > lo;) {
-    const int k = idx[i];
-    const int* row = cdf + (size_t)k * stride;
-    const int max_value = cdf_len[k] - 2;
-    int value = sym[i] - offset[k];
-    unsigned raw = 0;
-    if (value < 0) {
-      raw = (unsigned)(-2 * (long long)value - 1);
-      value = max_value;
-    } else if (value >= max_value) {
-      raw = 2u * (unsigned)(value - max_value);
-      value = max_value;
+  // Only the state update depends on the previous symbol; every table look-up depends on (symbol, index) alone.  Eight
+  // symbols are resolved to (start, freq, escape) with their loads in flight together, then pushed through the state one
+  // after the other: the chain per symbol is the 64-bit division, not four dependent global loads.
+  constexpr int kBatch = 8;
+  for (unsigned top = hi; top > lo;) {
+    const unsigned cnt = min((unsigned)kBatch, top - lo);
+    int k[kBatch], value[kBatch], max_value[kBatch];
+    unsigned raw[kBatch], start[kBatch], freq[kBatch];
+    double rd[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const unsigned i = top - 1 - (j < (int)cnt ? j : 0);
+      k[j] = idx[i];
+      value[j] = sym[i];
     }
-    if (value == max_value) {
-      // forward order: symbol, digit count (base-15 unary-ish prefix), digits low to high; coded back to front
-      int n_bypass = 0;
-      while (n_bypass < 8 && (raw >> (n_bypass * kBypassBits)) != 0) ++n_bypass;
-      for (int j = n_bypass - 1; j >= 0; --j) e.put_bits<WRITE>((raw >> (j * kBypassBits)) & kMaxBypass);
-      e.put_bits<WRITE>((unsigned)n_bypass);                        // n_bypass <= 8 < 15: a single prefix digit
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      max_value[j] = cdf_len[k[j]] - 2;
+      value[j] -= offset[k[j]];
     }
-    const unsigned start = (unsigned)row[value];
-    e.put<WRITE>(start, (unsigned)row[value + 1] - start);
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      raw[j] = 0;
+      if (value[j] < 0) {
+        raw[j] = (unsigned)(-2 * (long long)value[j] - 1);
+        value[j] = max_value[j];
+      } else if (value[j] >= max_value[j]) {
+        raw[j] = 2u * (unsigned)(value[j] - max_value[j]);
+        value[j] = max_value[j];
+      }
+      const int* row = cdf + (size_t)k[j] * stride;
+      start[j] = (unsigned)row[value[j]];
+      freq[j] = (unsigned)row[value[j] + 1] - start[j];
+      rd[j] = 1.0 / (double)freq[j];
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      if (j < (int)cnt) {
+        if (value[j] == max_value[j]) {
+          // forward order: symbol, digit count, digits low to high; coded back to front.  raw has 32 bits: at most 8
+          // digits, so the count is a single prefix digit (< 15)
+          int n_bypass = 0;
+          while (n_bypass < 8 && (raw[j] >> (n_bypass * kBypassBits)) != 0) ++n_bypass;
+          for (int d = n_bypass - 1; d >= 0; --d) e.put_bits<WRITE>((raw[j] >> (d * kBypassBits)) & kMaxBypass);
+          e.put_bits<WRITE>((unsigned)n_bypass);
+        }
+        e.put<WRITE>(start[j], freq[j], rd[j]);
+      }
+    }
+    top -= cnt;
   }
   // Rans64EncFlush: low word first in memory
   if (WRITE) {
