@@ -415,6 +415,17 @@ B200LIC_API int b200lic_selftest_fast_div(unsigned long long n, unsigned long lo
                               b200lic_stream_t stream);
 B200LIC_API int b200lic_gdn_fwd_fused(const float* x, const float* minmax, int n_bits, const void* packed_gamma,
                           const float* beta, int N, int C, int HW, int inverse, float* y, b200lic_stream_t stream);
+/* The two data movements of the folded-tap layers (3 -> N analysis conv, N -> 3 synthesis transposed conv; the engine
+ * folds their taps into the channel axis) as entry points, so the fused AdaRound iteration can run those layers as 1x1
+ * problems on prepared operands.  b200lic_im2col_stage: out[n, (ho,wo), (c,r,s)] = x[n, c, ho*stride - pad + r,
+ * wo*stride - pad + s] written as the split-bf16 NHWC operand (cpad channels, zero padded) -- the activation operand of
+ * the folded conv forward / its weight gradient, or (applied to dL/dy) the dY operand of the folded transposed conv's
+ * weight gradient.  b200lic_col2im: y = act(bias + scatter-add of col [N, Cout*KH*KW, H, W]) -- the tail of the folded
+ * transposed conv forward (autograd of F.conv2d / F.conv_transpose2d, TO layer_opt.py:298-307). */
+B200LIC_API int b200lic_im2col_stage(const float* x, int N, int C, int H, int W, int KH, int KW, int stride, int pad,
+                         int Ho, int Wo, void* x_hi, void* x_lo, int cpad, b200lic_stream_t stream);
+B200LIC_API int b200lic_col2im(const float* col, const float* bias, int N, int Cout, int H, int W, int KH, int KW, int stride,
+                   int pad, int Ho, int Wo, int act, float slope, int fixed_point, float* y, b200lic_stream_t stream);
 /* ---- Entropy coding of the latents -------------------------------------------------------------
  * What the reference reaches through compressai 1.2.4 (`update()`, `compress()`, `decompress()`; task-oriented-PTQ/
  * models/nic_cvt.py:426-570, light-uniform-PTQ/models/tinylic.py:236-367).

@@ -98,6 +98,8 @@ SIGNATURES = {
                                _P],
     "gdn_fwd_fused": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "selftest_fast_div": [_ULL, _ULL, _P],
+    "im2col_stage": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I],
+    "col2im": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "rans_symbols": [_P, _P, _I, _P, _P, _I, _F, _I, _I, _SZ, _P, _P],
     "rans_encode_sizes": [_P, _P, C.c_uint, C.c_uint, _P, _P, _P, _I, _P],
     "rans_encode_write": [_P, _P, C.c_uint, C.c_uint, _P, _P, _P, _I, _P, _P],

@@ -269,3 +269,37 @@ int smallc_deconv_wgrad(const b200lic_conv_desc* d, const float* x, const float*
 }
 
 }  // namespace b200lic
+
+using namespace b200lic;
+
+extern "C" {
+
+// The two data movements of the folded-tap layers as entry points of their own, so that the fused AdaRound iteration can
+// run those layers as 1x1 problems on prepared operands (recon.py FusedFolded): im2col straight into a staged operand
+// slot, and the col2im gather that finishes a folded transposed convolution.
+int b200lic_im2col_stage(const float* x, int N, int C, int H, int W, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                         void* x_hi, void* x_lo, int cpad, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(x && x_hi && x_lo && N > 0 && N <= 65535 && C > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && stride > 0 &&
+                   Ho > 0 && Wo > 0,
+               "im2col_stage: bad arguments");
+  B200_REQUIRE(cpad % 32 == 0 && cpad <= kFoldMaxK && C * KH * KW <= cpad, "im2col_stage: cpad=%d for %d folded channels",
+               cpad, C * KH * KW);
+  return stage_im2col(x, N, C, H, W, KH, KW, stride, pad, Ho, Wo, cpad, x_hi, x_lo, as_stream(stream));
+}
+
+int b200lic_col2im(const float* col, const float* bias, int N, int Cout, int H, int W, int KH, int KW, int stride, int pad,
+                   int Ho, int Wo, int act, float slope, int fixed_point, float* y, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(col && y && N > 0 && Cout > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && Ho > 0 && Wo > 0,
+               "col2im: bad arguments");
+  B200_REQUIRE(stride >= 1 && stride <= kMaxSt, "col2im: stride %d outside [1,%d]", stride, kMaxSt);
+  const int Ab = (Ho + stride - 1) / stride, Bb = (Wo + stride - 1) / stride;
+  const size_t n_blocks = (size_t)N * Cout * Ab * Bb;
+  col2im_kernel<<<grid_for(n_blocks, 256, 8), 256, 0, as_stream(stream)>>>(col, bias, Cout, H, W, KH, KW, stride, pad, Ho,
+                                                                         Wo, Ab, Bb, n_blocks, act, slope, fixed_point, y);
+  B200_LAUNCH_CHECK("col2im_kernel");
+  return B200LIC_OK;
+}
+
+}  // extern "C"

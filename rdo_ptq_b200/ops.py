@@ -738,6 +738,23 @@ def conv_fwd_packed(x, packed, d, transposed, bias=None, w_scale=None, gdn_x=Non
     return (y, norm) if want_norm else y
 
 
+def im2col_stage(x, kh, kw, stride, pad, ho, wo, slot):
+    """im2col of x [N,C,H,W] written as the staged split-bf16 operand `slot` (b200lic_im2col_stage)."""
+    x = _c(x, "input")
+    N, Cc, H, W = x.shape
+    call("im2col_stage", _p(x), N, Cc, H, W, kh, kw, stride, pad, ho, wo, slot[0], slot[1], slot[2])
+
+
+def col2im(col, bias, cout, kh, kw, stride, pad, ho, wo, act=ACT_NONE, slope=0.0, y=None):
+    """Tail of the folded transposed conv: y [N,cout,ho,wo] = act(bias + scatter-add of col [N,cout*kh*kw,H,W])."""
+    N, _, H, W = col.shape
+    if y is None:
+        y = torch.empty((N, cout, ho, wo), device=col.device, dtype=torch.float32)
+    call("col2im", _p(col), _p(None if bias is None else _c(bias)), N, cout, H, W, kh, kw, stride, pad, ho, wo, int(act),
+         float(slope), 0, _p(y))
+    return y
+
+
 GDN_FUSED = True           # evaluation GDN / IGDN through b200lic_gdn_fwd_fused when the shape allows (tests flip it for A/B)
 
 

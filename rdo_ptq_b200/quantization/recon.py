@@ -110,6 +110,8 @@ class CoderTask:
 FUSED_DEFAULT = os.environ.get("B200LIC_FUSED", "1") != "0"
 # multi-GPU tail: the fused peer-memory kernel (1) or ncclAllReduce + Adam (0)
 XGPU_DEFAULT = os.environ.get("B200LIC_XGPU", "1") != "0"
+# the folded-tap 3-channel layers through the fused chain as 1x1 problems (FusedFolded); A/B switch like FUSED_DEFAULT
+FOLDED_DEFAULT = os.environ.get("B200LIC_FUSED_FOLDED", "1") != "0"
 
 
 class FusedLayer:
@@ -117,7 +119,8 @@ class FusedLayer:
     stage_mix (pick + QDrop -> staged activation operand) -> quant_pack (AdaRound soft weight -> packed weight operand)
     -> GEMM -> loss_stage (loss + gradient -> staged dY operand) -> wgrad with the STE / regulariser / Adam tail fused
     behind its split-K reduction.  Seven launches; no fp32 batch, soft weight, dL/dout or dL/dWq tensor is written.
-    Not applicable (-> None from `build`): blocks, GDN, PixelShuffle, the folded-tap 3-channel layers, the SIMT engine."""
+    Not applicable (-> None from `build`): blocks, PixelShuffle, the SIMT engine; GDN units take `FusedGdn`, the folded-tap
+    3-channel layers `FusedFolded`."""
 
     def __init__(self):
         self.d = self.tr = self.packed = self.ws_f = self.ws_w = self.x_slot = self.dy_slot = self.y = self.dw = None
@@ -151,6 +154,68 @@ class FusedLayer:
     def use_peer(self, peer, weight):
         """N > 1 with the peer-memory tail: the weight gradient is written straight into the symmetric buffer."""
         self.dw = peer.grad.view(weight.shape)
+
+
+class FusedFolded:
+    """Fused iteration of the two folded-tap layers (3 -> N analysis conv, N -> 3 synthesis transposed conv): the engine
+    runs them as 1x1 problems over an im2col'ed operand (conv_tc_smallc.cu), so they take the prepared-operand chain of
+    `FusedLayer` on the 1x1 descriptor `d1`:
+      conv : pick + QDrop (3-channel batch) -> im2col_stage (the staged activation operand, K = Cin*k*k channels; the SAME
+             buffer is the weight gradient's operand -- the un-fused path builds it twice) -> quant_pack -> GEMM ->
+             loss_stage -> wgrad + STE / regulariser / Adam
+      tconv: stage_mix -> quant_pack -> GEMM (col = x . W'') -> col2im (+ bias) -> loss on the 3-channel output ->
+             im2col_stage of dL/dy as the staged dY operand -> wgrad + tail (the staged x is reused; the un-fused path
+             splits it a second time)."""
+
+    @staticmethod
+    def build(m, in_shape, batch, world):
+        if not isinstance(m, QuantModule) or m.is_gdn or m.is_ps or m.org_weight is None or m.se_module is not None:
+            return None
+        kw = m.fwd_kwargs
+        if ops._sq(kw["dilation"], "dilation") != 1 or kw["groups"] != 1 or ops.DEFAULT_ENGINE == ops.ENGINE_SIMT:
+            return None
+        act, slope = ops._act_id(m.activation_function)
+        f = FusedFolded()
+        f.tr = m.if_tconv
+        f.full = ops.conv_desc((batch,) + tuple(in_shape), m.weight.shape, kw["stride"], kw["padding"], f.tr,
+                               kw.get("output_padding", 0), act=act, slope=slope)
+        g = f.full
+        kk = g.KH * g.KW
+        if kk <= 1 or g.stride > 4:
+            return None
+        dev = m.weight.device
+        if not f.tr:
+            K = g.Cin * kk
+            if K > 128:
+                return None
+            f.d1 = ops.conv_desc((batch, K, g.Ho, g.Wo), (g.Cout, K, 1, 1), 1, 0, False, act=act, slope=slope)
+        else:
+            K = g.Cout * kk
+            if K > 128 or act != ops.ACT_NONE:
+                return None
+            f.d1 = ops.conv_desc((batch, g.Cin, g.H, g.W), (g.Cin, K, 1, 1), 1, 0, True)
+            f.col = torch.empty((batch, K, g.H, g.W), device=dev, dtype=torch.float32)
+        f.packed = ops.new_packed(f.d1, f.tr, dev)
+        if f.packed is None:
+            return None
+        f.ws_f = ops._workspace(f.d1, ops.fwd_op(f.tr), dev)
+        f.ws_w = ops._workspace(f.d1, ops.wgrad_op(f.tr), dev)
+        f.x_slot = ops.conv_x_slot(f.d1, f.tr, f.ws_f)
+        f.dy_slot = ops.conv_dy_slot(f.d1, f.tr, f.ws_w)
+        if f.x_slot is None or f.dy_slot is None or (not f.tr and f.x_slot[2] < K) or (f.tr and f.dy_slot[2] < K):
+            return None
+        f.xb = None if f.tr else torch.empty((batch,) + tuple(in_shape), device=dev, dtype=torch.float32)
+        f.y = torch.empty((g.N, g.Cout, g.Ho, g.Wo), device=dev, dtype=torch.float32)
+        f.dw = torch.empty_like(m.weight.data) if world > 1 else None
+        return f
+
+    def use_peer(self, peer, weight):
+        self.dw = peer.grad.view(weight.shape)
+
+    def d1_wshape(self, m):
+        """The weight (gradient) seen through the 1x1 descriptor: same memory, taps folded into a channel axis."""
+        w = m.weight.shape
+        return (w[0], w[1] * w[2] * w[3], 1, 1)
 
 
 class FusedGdn:
@@ -253,6 +318,8 @@ class UnitTrainer:
             if ok:
                 self._fused_plan = (FusedGdn.build(self.unit, in_shape, batch, self.world) if self.unit.is_gdn else
                                     FusedLayer.build(self.unit, in_shape, batch, self.world))
+                if self._fused_plan is None and not self.unit.is_gdn and FOLDED_DEFAULT:
+                    self._fused_plan = FusedFolded.build(self.unit, in_shape, batch, self.world)
                 if self._fused_plan is not None and self.peer is not None:
                     if isinstance(self._fused_plan, FusedGdn):
                         self._fused_plan.dleaf = self.peer[0].grad.view(self._fused_plan.leaf.shape)
@@ -285,11 +352,47 @@ class UnitTrainer:
                                     reg_loss=self.loss_buf[2:3])
         return []
 
+    def _fused_folded(self, f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base):
+        m = self.unit
+        q = m.weight_quantizer
+        g = f.full
+        if not f.tr:
+            ops.gather_mix_sched(q_in, fp_in, idx_table, g.N, prob, seed_base, units, unit, sched, out=f.xb)
+            ops.im2col_stage(f.xb, g.KH, g.KW, g.stride, g.pad, g.Ho, g.Wo, f.x_slot)
+        else:
+            ops.stage_mix_sched(q_in, fp_in, idx_table, g.N, prob, seed_base, units, unit, sched, f.x_slot)
+        ops.quant_pack_weights(m.weight.data, q.alpha.data, q.delta, q.zero_point, q.axis, q.n_levels, True, f.d1, f.tr,
+                               out=f.packed)
+        denom = f.y.numel() // f.y.shape[1]
+        if not f.tr:
+            ops.conv_fwd_packed(None, f.packed, f.d1, False, bias=m.bias, ws=f.ws_f, y=f.y)
+            ops.lp_loss_stage_sched(f.y, tgt_cache, idx_table, units, unit, sched, self.p, 1.0 / denom, 2.0 / denom,
+                                    g.act, g.act_slope, self.loss_buf[0:1], f.dy_slot)
+        else:
+            ops.conv_fwd_packed(None, f.packed, f.d1, True, ws=f.ws_f, y=f.col)
+            ops.col2im(f.col, m.bias, g.Cout, g.KH, g.KW, g.stride, g.pad, g.Ho, g.Wo, y=f.y)
+            _, d_y = ops.lp_loss_fwd_bwd(f.y, tgt_cache, self.p, scale=1.0 / denom, grad_scale=2.0 / denom,
+                                         loss=self.loss_buf[0:1],
+                                         pick=None if idx_table is None else (idx_table, units, unit, sched))
+            # dL/dcol = im2col(dL/dy) over the conv geometry whose output grid is the transposed conv's input grid
+            ops.im2col_stage(d_y, g.KH, g.KW, g.stride, g.pad, g.H, g.W, f.dy_slot)
+        self._same = True
+        if self.world > 1:
+            ops.conv_wgrad_prepared(f.d1, f.tr, f.x_slot, None, f.dw.view(f.d1_wshape(m)), f.ws_w)
+            self._flat = f.dw.view(-1)
+            return [f.dw]
+        ops.conv_wgrad_adam_sched(f.d1, f.tr, f.x_slot, None, f.ws_w, m.weight.data, q.alpha.data, q.delta, q.zero_point,
+                                  self.exp_avg[0], self.exp_avg_sq[0], q.axis, q.n_levels, sched, reg_weight=self.weight,
+                                  reg_loss=self.loss_buf[2:3])
+        return []
+
     def fused_compute(self, f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base):
         """One fused iteration up to (world == 1: and including) the Adam step.  Returns the list of dL/dWq tensors for
         `step_update` (empty when the tail ran fused)."""
         if isinstance(f, FusedGdn):
             return self._fused_gdn(f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base)
+        if isinstance(f, FusedFolded):
+            return self._fused_folded(f, q_in, fp_in, tgt_cache, idx_table, units, unit, sched, prob, seed_base)
         m = self.unit
         q = m.weight_quantizer
         ops.stage_mix_sched(q_in, fp_in, idx_table, f.d.N, prob, seed_base, units, unit, sched, f.x_slot)
