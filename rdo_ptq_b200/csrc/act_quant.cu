@@ -6,6 +6,7 @@
 // light-uniform-PTQ/quant_int/quantizer.py:120-128 -- static Q(a_l).(a_r) fixed point.
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "quant_math.cuh"
 
 namespace b200lic {
 
@@ -78,6 +79,14 @@ __device__ __forceinline__ float actq_one(float v, float m, float r, float L, fl
   const float q = rintf(__fmul_rn(t, L));
   if (code) *code = q;
   return __fadd_rn(__fmul_rn(__fdiv_rn(q, L), r), m);
+}
+
+// actq_one with both divisions by the FMA sequence (ry = RN(1/r), Ly = RN(1/L)); bit-identical results
+__device__ __forceinline__ float actq_one_fast(float v, float m, float r, float ry, float L, float Ly) {
+  float t = div_rn(__fsub_rn(v, m), r, ry);
+  t = fminf(fmaxf(t, -1.f), 1.f);
+  const float q = rintf(__fmul_rn(t, L));
+  return __fadd_rn(__fmul_rn(div_rn(q, L, Ly), r), m);
 }
 
 __global__ void __launch_bounds__(256) actq_apply_kernel(const float* __restrict__ x, const unsigned* __restrict__ keys,
@@ -266,28 +275,48 @@ __global__ void __launch_bounds__(256)
                             int square, __nv_bfloat16* __restrict__ xh, __nv_bfloat16* __restrict__ xl,
                             float* __restrict__ out) {
   __shared__ float t[64][65];
+  __shared__ float s_m[64], s_r[64], s_ry[64];
   const int cblk = (cpad + 63) >> 6;
   const int n = blockIdx.z, c0 = (int)(blockIdx.x % cblk) * 64, p0 = (int)(blockIdx.x / cblk) * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t img = (size_t)n * C * HW;
   const bool vec2 = (HW & 1) == 0;
+  // per-channel (min, range, RN(1/range)) once per CTA: the two divisions of actq_one become FMA sequences on a
+  // precomputed reciprocal (quant_math.cuh: same correctly rounded quotient, a third of the instructions)
+  if (threadIdx.x < 64) {
+    const int c = c0 + threadIdx.x;
+    float m = 0.f, r = 1.f;
+    if (c < C) {
+      m = key2f(keys[2 * c]);
+      r = fmaxf(__fsub_rn(key2f(keys[2 * c + 1]), m), 1e-6f);
+    }
+    s_m[threadIdx.x] = m;
+    s_r[threadIdx.x] = r;
+    s_ry[threadIdx.x] = div_rn_ok(r) ? __frcp_rn(r) : 0.f;
+  }
+  __syncthreads();
+  const float Ly = div_rn_ok(L) ? __frcp_rn(L) : 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int cl = warp + 8 * j, c = c0 + cl, p = p0 + 2 * lane;
     float v0 = 0.f, v1 = 0.f;
     if (c < C && p < HW) {
-      const float m = key2f(keys[2 * c]);
-      const float r = fmaxf(__fsub_rn(key2f(keys[2 * c + 1]), m), 1e-6f);
+      const float m = s_m[cl], r = s_r[cl], ry = s_ry[cl];
+      const bool fast = ry != 0.f && Ly != 0.f;                  // uniform over the warp (one channel per warp and j)
       const size_t e = img + (size_t)c * HW + p;
       const bool has1 = p + 1 < HW;
       if (vec2) {
         const float2 v = __ldg(reinterpret_cast<const float2*>(x + e));
-        v0 = actq_one(v.x, m, r, L, nullptr);
-        v1 = actq_one(v.y, m, r, L, nullptr);
+        v0 = fast ? actq_one_fast(v.x, m, r, ry, L, Ly) : actq_one(v.x, m, r, L, nullptr);
+        v1 = fast ? actq_one_fast(v.y, m, r, ry, L, Ly) : actq_one(v.y, m, r, L, nullptr);
         if (out) *reinterpret_cast<float2*>(out + e) = make_float2(v0, v1);
       } else {
-        v0 = actq_one(__ldg(x + e), m, r, L, nullptr);
-        if (has1) v1 = actq_one(__ldg(x + e + 1), m, r, L, nullptr);
+        const float a0 = __ldg(x + e);
+        v0 = fast ? actq_one_fast(a0, m, r, ry, L, Ly) : actq_one(a0, m, r, L, nullptr);
+        if (has1) {
+          const float a1 = __ldg(x + e + 1);
+          v1 = fast ? actq_one_fast(a1, m, r, ry, L, Ly) : actq_one(a1, m, r, L, nullptr);
+        }
         if (out) {
           out[e] = v0;
           if (has1) out[e + 1] = v1;

@@ -149,6 +149,92 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same gather with the geometry known at compile time (the synthesis tail of every codec here is k = 5 or 3,
+// stride 2): the tap -> (output phase, input offset) arithmetic folds into constants and the 25 loads of a thread are
+// issued back to back.  Same summation order as the generic kernel (taps in (r, s) order), so results are bit-identical.
+template <int K, int ST, int PAD>
+__global__ void __launch_bounds__(256)
+    col2im_fixed_kernel(const float* __restrict__ col, const float* __restrict__ bias, int Cout, int H, int W, int Ho,
+                        int Wo, int Ab, int Bb, size_t n_blocks, int act, float slope, int fixed_point,
+                        float* __restrict__ y) {
+  constexpr int KK = K * K;
+  constexpr int pad = PAD;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_blocks; t += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(t % Bb);
+    const size_t t1 = t / Bb;
+    const int a = (int)(t1 % Ab);
+    const size_t t2 = t1 / Ab;
+    const int co = (int)(t2 % Cout);
+    const size_t n = t2 / Cout;
+    const float* cn = col + (n * Cout + co) * (size_t)KK * H * W;
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+    float v[K][K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int i = ((r - pad) % ST + ST) % ST;
+      const int h = a - (r - pad - i) / ST;
+#pragma unroll
+      for (int s_ = 0; s_ < K; ++s_) {
+        const int j = ((s_ - pad) % ST + ST) % ST;
+        const int w = b - (s_ - pad - j) / ST;
+        const bool in = h >= 0 && h < H && w >= 0 && w < W;
+        v[r][s_] = in ? __ldg(cn + ((size_t)(r * K + s_) * H + h) * W + w) : 0.f;
+      }
+    }
+    float acc[ST][ST];
+#pragma unroll
+    for (int i = 0; i < ST; ++i)
+#pragma unroll
+      for (int j = 0; j < ST; ++j) acc[i][j] = bv;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int i = ((r - pad) % ST + ST) % ST;
+      const int h = a - (r - pad - i) / ST;
+#pragma unroll
+      for (int s_ = 0; s_ < K; ++s_) {
+        const int j = ((s_ - pad) % ST + ST) % ST;
+        const int w = b - (s_ - pad - j) / ST;
+        const bool in = h >= 0 && h < H && w >= 0 && w < W;      // out-of-range taps are skipped, not added as zeros
+#pragma unroll
+        for (int ii = 0; ii < ST; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < ST; ++jj)
+            if (ii == i && jj == j && in) acc[ii][jj] += v[r][s_];
+      }
+    }
+    float* yn = y + (n * Cout + co) * (size_t)Ho * Wo;
+#pragma unroll
+    for (int i = 0; i < ST; ++i) {
+      const int ho = ST * a + i;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int j = 0; j < ST; ++j) {
+        const int wo = ST * b + j;
+        if (wo >= Wo) continue;
+        float o = apply_act(acc[i][j], act, slope);
+        if (fixed_point) o = rintf(fminf(fmaxf(o, -128.f), 128.f) * 256.f) * (1.f / 256.f);
+        yn[(size_t)ho * Wo + wo] = o;
+      }
+    }
+  }
+}
+
+static void launch_col2im(const float* col, const float* bias, int N, int Cout, int H, int W, int KH, int KW, int st, int pad,
+                          int Ho, int Wo, int act, float slope, int fixed_point, float* y, cudaStream_t s) {
+  const int Ab = (Ho + st - 1) / st, Bb = (Wo + st - 1) / st;
+  const size_t n_blocks = (size_t)N * Cout * Ab * Bb;
+  const int grid = grid_for(n_blocks, 256, 8);
+  if (KH == 5 && KW == 5 && st == 2 && pad == 2)
+    col2im_fixed_kernel<5, 2, 2><<<grid, 256, 0, s>>>(col, bias, Cout, H, W, Ho, Wo, Ab, Bb, n_blocks, act, slope,
+                                                   fixed_point, y);
+  else if (KH == 3 && KW == 3 && st == 2 && pad == 1)
+    col2im_fixed_kernel<3, 2, 1><<<grid, 256, 0, s>>>(col, bias, Cout, H, W, Ho, Wo, Ab, Bb, n_blocks, act, slope,
+                                                   fixed_point, y);
+  else
+    col2im_kernel<<<grid, 256, 0, s>>>(col, bias, Cout, H, W, KH, KW, st, pad, Ho, Wo, Ab, Bb, n_blocks, act, slope,
+                                       fixed_point, y);
+}
+
 // ---- eligibility -------------------------------------------------------------------------------------------------
 static inline bool fold_conv(const b200lic_conv_desc* d) {      // fold taps into the INPUT channel axis
   const int KK = d->KH * d->KW;
@@ -234,11 +320,8 @@ int smallc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w
   int rc = tc2_launch(d->N, d->Cin, d->H, d->W, Cc, d->H, d->W, 1, 1, 1, 0, 0, 1LL, (long long)Cc, B200LIC_ACT_NONE, 0.f, 0,
                       0, 0, x, w, nullptr, nullptr, nullptr, col, base, inner, s, "deconv_fwd(tc, folded taps)");
   if (rc != B200LIC_OK) return rc;
-  const int Ab = (d->Ho + d->stride - 1) / d->stride, Bb = (d->Wo + d->stride - 1) / d->stride;
-  const size_t n_blocks = (size_t)d->N * d->Cout * Ab * Bb;
-  col2im_kernel<<<grid_for(n_blocks, 256, 8), 256, 0, s>>>(col, bias, d->Cout, d->H, d->W, d->KH, d->KW, d->stride, d->pad,
-                                                           d->Ho, d->Wo, Ab, Bb, n_blocks, d->act, d->act_slope,
-                                                           d->fixed_point, y);
+  launch_col2im(col, bias, d->N, d->Cout, d->H, d->W, d->KH, d->KW, d->stride, d->pad, d->Ho, d->Wo, d->act, d->act_slope,
+                d->fixed_point, y, s);
   B200_LAUNCH_CHECK("col2im_kernel");
   return B200LIC_OK;
 }
@@ -294,10 +377,7 @@ int b200lic_col2im(const float* col, const float* bias, int N, int Cout, int H, 
   B200_REQUIRE(col && y && N > 0 && Cout > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && Ho > 0 && Wo > 0,
                "col2im: bad arguments");
   B200_REQUIRE(stride >= 1 && stride <= kMaxSt, "col2im: stride %d outside [1,%d]", stride, kMaxSt);
-  const int Ab = (Ho + stride - 1) / stride, Bb = (Wo + stride - 1) / stride;
-  const size_t n_blocks = (size_t)N * Cout * Ab * Bb;
-  col2im_kernel<<<grid_for(n_blocks, 256, 8), 256, 0, as_stream(stream)>>>(col, bias, Cout, H, W, KH, KW, stride, pad, Ho,
-                                                                         Wo, Ab, Bb, n_blocks, act, slope, fixed_point, y);
+  launch_col2im(col, bias, N, Cout, H, W, KH, KW, stride, pad, Ho, Wo, act, slope, fixed_point, y, as_stream(stream));
   B200_LAUNCH_CHECK("col2im_kernel");
   return B200LIC_OK;
 }

@@ -29,6 +29,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "quant_math.cuh"
 
 namespace b200lic {
 
@@ -137,19 +138,6 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
-// a / b correctly rounded, given y = RN(1 / b): two residual corrections (Markstein).  Requires that the significand of
-// b is not all ones and that a / b neither overflows nor matters when it underflows (the quantiser clamps and rounds it).
-__device__ __forceinline__ float div_rn(float a, float b, float y) {
-  float q = __fmul_rn(a, y);
-  float r = __fmaf_rn(-b, q, a);
-  q = __fmaf_rn(r, y, q);
-  r = __fmaf_rn(-b, q, a);
-  return __fmaf_rn(r, y, q);
-}
-__device__ __forceinline__ bool div_rn_ok(float b) {
-  const uint32_t u = __float_as_uint(b);
-  return (u & 0x7fffffu) != 0x7fffffu && b >= 1e-30f && b <= 1e30f;
-}
 // act_quant.cu's actq_one, restated with explicit round-to-nearest intrinsics (never contracted into FMAs): the codes
 // this kernel produces are the codes b200lic_actq_apply produces, bit for bit.
 //   code = rint(clamp((v - m) / r, -1, 1) * L): the division by the FMA sequence (FAST) or __fdiv_rn; rint by adding
@@ -177,6 +165,12 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
 __device__ __forceinline__ float rsqrt_fast(float v) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// MUFU.SQRT alone (IGDN): sqrtf() is the IEEE-rounded sequence with a slow-path call; the norm is a normal positive number
+__device__ __forceinline__ float sqrt_fast(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -488,7 +482,7 @@ __global__ void __launch_bounds__(kGdThreads, 1)
         }
         if (g.inverse) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) xv[j] *= sqrtf(nrm[j]);
+          for (int j = 0; j < 16; ++j) xv[j] *= sqrt_fast(nrm[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) xv[j] *= rsqrt_fast(nrm[j]);

@@ -738,6 +738,15 @@ def conv_fwd_packed(x, packed, d, transposed, bias=None, w_scale=None, gdn_x=Non
     return (y, norm) if want_norm else y
 
 
+def folded_deconv_desc(d):
+    """The 1x1 transposed-conv descriptor a folded-tap transposed conv (few output channels: Cout*k*k <= 128) runs as --
+    col[n, (co,r,s), h, w] = sum_ci x[n,ci,h,w] * w[ci,co,r,s], finished by `col2im` -- or None (conv_tc_smallc.cu)."""
+    kk = d.KH * d.KW
+    if kk <= 1 or d.Cout * kk > 128 or d.stride > 4 or d.in_square or d.gdn_mode or d.engine == ENGINE_SIMT:
+        return None
+    return ConvDesc(d.N, d.Cin, d.H, d.W, d.Cout * kk, d.H, d.W, 1, 1, 1, 0, ACT_NONE, 0.0, d.engine, 0, 0, 0)
+
+
 def im2col_stage(x, kh, kw, stride, pad, ho, wo, slot):
     """im2col of x [N,C,H,W] written as the staged split-bf16 operand `slot` (b200lic_im2col_stage)."""
     x = _c(x, "input")

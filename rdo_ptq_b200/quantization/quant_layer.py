@@ -92,9 +92,11 @@ class QuantModule(nn.Module):
                 getattr(q, "soft_targets", None), ver(self.weight), ver(self.org_weight), ver(getattr(q, "alpha", None)),
                 ver(getattr(q, "delta", None)), ver(getattr(q, "zero_point", None)), ver(bias), ops.DEFAULT_ENGINE)
 
-    def _prepared(self, d):
+    def _prepared(self, d, fold=1):
         """(packed weight operand, w_scale or None, bias) for descriptor `d`, or None when this call has to take the
-        general path (quantiser not initialised yet, layer without a packed operand)."""
+        general path (quantiser not initialised yet, layer without a packed operand).  fold = k*k when `d` is the 1x1
+        form of a folded-tap transposed conv (ops.folded_deconv_desc): same weight memory, taps folded into the output
+        channel axis."""
         q = self.weight_quantizer
         if self.use_weight_quant and (not isinstance(q, (UniformAffineQuantizer, AdaRoundQuantizer))
                                       or getattr(q, "_leaf", None) is not None or getattr(q, "soft_targets", False)
@@ -117,7 +119,8 @@ class QuantModule(nn.Module):
             b_eff = self.fwd_kwargs["beta_reparam"](beta).detach()
             val = (ops.pack_weights(g_eff.reshape(g_eff.shape[0], g_eff.shape[1], 1, 1), d, False), None, b_eff)
         elif not self.use_weight_quant:
-            val = (ops.pack_weights(self.org_weight, d, self.if_tconv), None, self.org_bias)
+            w = self.org_weight if fold == 1 else self.org_weight.reshape(self.org_weight.shape[0], -1, 1, 1)
+            val = (ops.pack_weights(w, d, self.if_tconv), None, self.org_bias)
         else:
             axis = q.axis if hasattr(q, "axis") else q.channel_axis(self.weight)
             alpha = q.alpha.detach() if hasattr(q, "alpha") else None
@@ -133,6 +136,8 @@ class QuantModule(nn.Module):
                 cout = self.weight.shape[out_axis]
                 scale = q.delta.reshape(-1)
                 scale = (scale.expand(cout) if scale.numel() == 1 else scale).contiguous()
+                if fold != 1:
+                    scale = scale.repeat_interleave(fold).contiguous()
             val = (packed, scale, self.bias)
         slots[self.use_weight_quant] = (key, val)
         return val
@@ -148,6 +153,9 @@ class QuantModule(nn.Module):
                               kw.get("output_padding", 0), act=act, slope=slope)
         if d.engine == ops.ENGINE_SIMT:
             return None
+        d1 = ops.folded_deconv_desc(d) if (self.if_tconv and not self.is_gdn) else None
+        if d1 is not None:
+            return self._forward_folded_deconv(input, d, d1, act, slope)
         ws = ops._workspace(d, ops.fwd_op(self.if_tconv), input.device)
         if ws[0] is None:                        # shape the tensor-core path rejects: the general path picks the engine
             return None
@@ -177,6 +185,28 @@ class QuantModule(nn.Module):
             out = ops.conv_fwd_packed(x, packed, d, False, bias=bias, gdn_x=x, ws=ws)
             return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
         return ops.conv_fwd_packed(x, packed, d, self.if_tconv, bias=bias, w_scale=scale, ws=ws)
+
+    def _forward_folded_deconv(self, input, d, d1, act, slope):
+        """N -> 3 synthesis layer without a gradient: the 1x1 GEMM on prepared operands (a deferred quantiser of the input is
+        applied while staging it) + the col2im gather with bias / activation."""
+        ws = ops._workspace(d1, ops.fwd_op(True), input.device)
+        if ws[0] is None:
+            return None
+        prep = self._prepared(d1, fold=d.KH * d.KW)
+        if prep is None:
+            return None
+        packed, scale, bias = prep
+        x = ops._c(input, "input")
+        pend = getattr(input, "_b200_actq", None)
+        if pend is not None:
+            slot = ops.conv_x_slot(d1, True, ws)
+            if slot is None:
+                x, pend = ops.act_quant_apply(x, pend[0], pend[1]), None
+            else:
+                ops.act_quant_apply_stage(x, pend[0], pend[1], slot)
+                x = None
+        col = ops.conv_fwd_packed(x, packed, d1, True, w_scale=scale, ws=ws)
+        return ops.col2im(col, bias, d.Cout, d.KH, d.KW, d.stride, d.pad, d.Ho, d.Wo, act, slope)
 
     def forward(self, input: torch.Tensor):
         act, slope = ops._act_id(self.activation_function)
