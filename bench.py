@@ -144,10 +144,8 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log (communicator / rank lines the driver counts) is left on; the JSON line is printed LAST, after
-        # the process group is gone, so it stays the final line of stdout
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # NCCL_DEBUG / NCCL_DEBUG_FILE are left exactly as the caller set them (the driver counts ranks from NCCL's own
+        # log); the JSON line is printed LAST, after the process group is gone, so it stays the final line of stdout
         dist.init_process_group("nccl", device_id=dev)
     _lib.call("actq_stats_init", ops._p(torch.empty(2, dtype=torch.int32, device=dev)), 1, stream=None)  # arch gate early
     pk = peaks()
