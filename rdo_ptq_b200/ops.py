@@ -612,8 +612,11 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             _wgrad(ctx.d, False, x, dy, dw, ctx.fwd_ws)
+        # bias gradient (never needed by the AdaRound loop, which freezes everything but alpha; kept so that autograd use
+        # of the op outside that loop is complete): a [Cout] reduction of dL/d(pre-activation)
+        db = dy.sum((0, 2, 3)) if ctx.needs_input_grad[2] else None
         ctx.fwd_ws = (None, 0)
-        return dx, dw, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 class _DeconvFn(torch.autograd.Function):
@@ -642,8 +645,9 @@ class _DeconvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)
             _wgrad(ctx.d, True, x, dy, dw, ctx.fwd_ws)
+        db = dy.sum((0, 2, 3)) if ctx.needs_input_grad[2] else None
         ctx.fwd_ws = (None, 0)
-        return dx, dw, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 def wq_int_weights(w, delta, zp, axis, n_levels, alpha=None):

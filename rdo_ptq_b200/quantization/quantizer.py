@@ -26,8 +26,11 @@ def round_ste(x: torch.Tensor):
 
 
 def lp_loss(pred, tgt, p=2.0, reduction='none'):
-    """reference quantizer.py:71-79, value only (the fused loop uses ops.lp_loss_fwd_bwd for value+grad)."""
+    """reference quantizer.py:71-79.  Differentiable w.r.t. `pred` when it requires a gradient (one K11 pass gives value
+    and gradient); the fused loop calls ops.lp_loss_fwd_bwd directly."""
     denom = pred.numel() // pred.shape[1] if reduction == 'none' else pred.numel()
+    if torch.is_grad_enabled() and pred.requires_grad:
+        return ops.lp_loss_fn(pred, tgt.detach(), p=p, scale=1.0 / denom).reshape(())
     loss, _ = ops.lp_loss_fwd_bwd(pred.detach(), tgt.detach(), p=p, scale=1.0 / denom, want_grad=False)
     return loss.reshape(())
 

@@ -566,6 +566,7 @@ def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_siz
     With an explicit `plan` (tests replaying the oracle's draws) every iteration is issued eagerly."""
     q_in, fp_in = cached_inps[0], (cached_inps[1] if len(cached_inps) > 1 else cached_inps[0])
     n = q_in.size(0)
+    batch_size = min(batch_size, n)      # the reference's randperm(n)[:batch_size] just truncates (layer_opt.py:289)
     losses, since = [], 0
 
     def log(it):
@@ -597,8 +598,14 @@ def run_reconstruction(trainer: UnitTrainer, cached_inps, cached_outs, batch_siz
     seed = DrawPlan().seed
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed * 1000003 + unit_id * 100003)
-    rows = min(trainer.iters, 4096)
-    table = torch.stack([torch.randperm(n, generator=gen, device=dev)[:batch_size] for _ in range(rows)])
+    # one fresh random subset per iteration, like the reference's randperm inside the loop (no wrap-around): up to 4096
+    # rows drawn one randperm at a time, longer runs in one shot (argsort of uniform keys = a uniform random permutation)
+    rows = max(trainer.iters, 1)
+    if rows <= 4096:
+        table = torch.stack([torch.randperm(n, generator=gen, device=dev)[:batch_size] for _ in range(rows)])
+    else:
+        table = torch.cat([torch.rand(min(8192, rows - r0), n, generator=gen, device=dev).argsort(dim=1)[:, :batch_size]
+                           for r0 in range(0, rows, 8192)]).contiguous()
     seed_base = (seed * 2654435761 + unit_id * 40503) & 0xFFFFFFFFFFFF
     sched = ops.new_sched(dev)
     tick = (trainer.iters, trainer.loss_start / trainer.iters if trainer.iters else 0.0, trainer.temp_decay.start_b,

@@ -149,7 +149,15 @@ class CalibrationSession:
         self.it = 0
         g = torch.Generator().manual_seed(seed)
         # pre-drawn batch picks (randperm rows), resident on the device: no host RNG inside the timed loop
-        self._perm = torch.stack([torch.randperm(self.n_samples, generator=g)[:batch_size] for _ in range(PERM_ROWS)])
+        # (row k = (step - 1) * units + unit; PERM_ROWS rows, or one per (step, unit) of the whole run when that is more,
+        # capped at 2^19 rows, so the picks of a full-length calibration do not repeat)
+        rows = min(max(PERM_ROWS, iters * len(self.units)), 1 << 19)
+        if rows <= PERM_ROWS:
+            self._perm = torch.stack([torch.randperm(self.n_samples, generator=g)[:batch_size] for _ in range(rows)])
+        else:
+            self._perm = torch.cat([torch.rand(min(1 << 15, rows - r0), self.n_samples, generator=g).argsort(dim=1)[:, :batch_size]
+                                    for r0 in range(0, rows, 1 << 15)]).contiguous()
+        self._perm_rows = rows
         self._perm_dev = self._perm.to(dev)
         self.seed_base = (seed * 2654435761) & 0xFFFFFFFFFFFF
         # device-resident schedule shared by all units (they advance in lock step)
@@ -267,7 +275,7 @@ class CalibrationSession:
 
     def _stream_step(self, main):
         """Copy this iteration's batch of images host->device (copy stream) and replay the two streaming forwards."""
-        idx = self._perm[self.it % PERM_ROWS].tolist()
+        idx = self._perm[self.it % self._perm_rows].tolist()
         with torch.cuda.stream(self._copy_stream):
             if self._img_used is not None:
                 self._copy_stream.wait_event(self._img_used)
@@ -337,7 +345,7 @@ class CalibrationSession:
         """Host-cache mode: copy this iteration's batch rows of (quant_in, fp_in, fp_out) from pinned host memory into
         the unit's staging buffers on the copy stream (one cudaMemcpyAsync per row; no host-side gather)."""
         k = self.it * len(self.units) + j
-        idx = self._perm[k % PERM_ROWS].tolist()
+        idx = self._perm[k % self._perm_rows].tolist()
         with torch.cuda.stream(self._copy_stream):
             if self._consumed[name] is not None:
                 self._copy_stream.wait_event(self._consumed[name])      # previous sweep's graph has read the staging

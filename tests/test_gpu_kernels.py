@@ -280,6 +280,13 @@ def test_lp_loss_and_reductions(ops, dev, golden_q):
         loss, grad = ops.lp_loss_fwd_bwd(g["a"].to(dev), g["b"].to(dev), p, scale=1.0 / denom)
         assert abs(loss.item() - g["loss"].item()) < 1e-5 * abs(g["loss"].item())
         assert torch.allclose(grad.cpu(), a.grad, rtol=1e-5, atol=1e-7)
+        # the reference-named entry point is differentiable like the reference's
+        from rdo_ptq_b200.quantization.quantizer import lp_loss as product_lp_loss
+        ad = g["a"].to(dev).requires_grad_(True)
+        val = product_lp_loss(ad, g["b"].to(dev), p)
+        val.backward()
+        assert abs(val.item() - g["loss"].item()) < 1e-5 * abs(g["loss"].item())
+        assert torch.allclose(ad.grad.cpu(), a.grad, rtol=1e-5, atol=1e-7)
     gen = torch.Generator().manual_seed(2)
     a, b = torch.rand(1, 3, 512, 768, generator=gen) * 1.2 - 0.1, torch.rand(1, 3, 512, 768, generator=gen)
     s = ops.sq_err_sum(a.to(dev), b.to(dev)).cpu().double()
@@ -318,7 +325,8 @@ def test_conv_fwd_bwd(ops, dev, case, engine_bar):
         pre = F.conv2d(x, w, b, stride=st, padding=pd)
         ref = F.leaky_relu(pre, slope) if act == ops.ACT_LEAKY_RELU else (F.relu(pre) if act == ops.ACT_RELU else pre)
         xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().to(dev).requires_grad_(True)
-        out = ops.conv2d(xd, wd, b.to(dev), st, pd, act=act, slope=slope)
+        bd = b.to(dev).requires_grad_(True)
+        out = ops.conv2d(xd, wd, bd, st, pd, act=act, slope=slope)
         assert rel_err(out, ref) < engine_bar, (case, act)
         dy = torch.randn(ref.shape, generator=gen)
         # the activation derivative is discontinuous at 0: use the GPU's own sign pattern so that an output within one
@@ -328,6 +336,7 @@ def test_conv_fwd_bwd(ops, dev, case, engine_bar):
         gx, gw = torch.autograd.grad(pre, (x, w), dy_eff)
         out.backward(dy.to(dev))
         assert rel_err(xd.grad, gx) < engine_bar and rel_err(wd.grad, gw) < engine_bar, (case, act)
+        assert rel_err(bd.grad, dy_eff.sum((0, 2, 3))) < 1e-5, (case, act)          # bias gradient
 
 
 DECONV_CASES = [  # N, Cin, H, W, Cout, k, stride, pad, out_pad
@@ -347,13 +356,15 @@ def test_deconv_fwd_bwd(ops, dev, case, engine_bar):
     pre = F.conv_transpose2d(x, w, b, stride=st, padding=pd, output_padding=op)
     ref = F.leaky_relu(pre, 0.01)
     xd, wd = x.detach().to(dev).requires_grad_(True), w.detach().to(dev).requires_grad_(True)
-    out = ops.conv_transpose2d(xd, wd, b.to(dev), st, pd, op, act=ops.ACT_LEAKY_RELU, slope=0.01)
+    bd = b.to(dev).requires_grad_(True)
+    out = ops.conv_transpose2d(xd, wd, bd, st, pd, op, act=ops.ACT_LEAKY_RELU, slope=0.01)
     assert out.shape == ref.shape and rel_err(out, ref) < engine_bar, case
     dy = torch.randn(ref.shape, generator=gen)
     dy_eff = torch.where(out.detach().cpu() > 0, dy, dy * 0.01)        # GPU's own sign pattern (see test_conv_fwd_bwd)
     gx, gw = torch.autograd.grad(pre, (x, w), dy_eff)
     out.backward(dy.to(dev))
     assert rel_err(xd.grad, gx) < engine_bar and rel_err(wd.grad, gw) < engine_bar, case
+    assert rel_err(bd.grad, dy_eff.sum((0, 2, 3))) < 1e-5, case
 
 
 def test_conv_rejects_bad_arguments(ops, dev):
