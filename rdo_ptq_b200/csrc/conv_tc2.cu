@@ -848,6 +848,12 @@ bool tc2_weight_layout(int Cin, int Cout, int KH, int KW, int stride, int transp
   return true;
 }
 
+bool gemm1x1_eligible(int KH, int KW, int stride, int pad, int Cpad, int CoutPad, int n_out_tiles, int gdn_mode,
+                      int fixed_point, int w_exact, int H, int W, int Ho, int Wo);
+int gemm1x1_launch(long long M, int HW, int Cpad, int Cout, int CoutPad, void* xh, size_t x_bytes, void* bh, size_t b_bytes,
+                   int w_exact, const float* w_scale, const float* bias, int act, float slope, float* y, cudaStream_t s,
+                   const char* name);
+
 // Stream-K policy: 1 = where it pays (default), 0 = off, 2 = wherever eligible.  B200LIC_TC_STREAMK in the environment or
 // b200lic_set_option("streamk", v) (tests compare the two schedules in one process).
 static int g_streamk_mode = -1;
@@ -1154,6 +1160,12 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
                          bh, bl, s);
     if (rc != B200LIC_OK) return rc;
   }
+
+  // 1b. 1x1 layers with a short contraction: weights resident in shared memory, register epilogue (gemm1x1_tc.cu)
+  if (!has_norm && gemm1x1_eligible(KH, KW, stride, pad, p.Cpad, p.CoutPad, p.n_tiles, gdn_mode, fixed_point, w_scale ? 1 : 0,
+                                    H, W, Ho, Wo))
+    return gemm1x1_launch((long long)N * H * W, H * W, p.Cpad, Cout, p.CoutPad, xh, p.x_bytes, bh, p.b_bytes,
+                          w_scale ? 1 : 0, w_scale, bias, act, slope, y, s, name);
 
   // 2. tensor maps
   CUtensorMap mah, mal, mbh, mbl, my, mx, mn;

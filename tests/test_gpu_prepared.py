@@ -392,3 +392,45 @@ def test_stream_k_schedule_matches_whole_item_schedule(ops, dev, shape):
     for mode in (0, 2):
         assert errs[mode][0] < 2e-5 and errs[mode][1] < 2e-5               # both well inside the 1e-4 per-layer bar
     assert max(between) < 4e-5
+
+
+@pytest.mark.parametrize("case", [
+    # N, Cin, H, W, Cout, transposed, act, integer
+    (2, 75, 24, 40, 192, False, 2, False),      # folded 3 -> N analysis conv (K = 75 -> 96)
+    (1, 192, 33, 21, 75, True, 0, False),       # folded N -> 3 synthesis layer: col = x . W'' (ragged pixel tail)
+    (2, 192, 16, 16, 192, False, 0, False),     # GDN norm GEMM of the calibration
+    (1, 64, 20, 12, 40, False, 1, True),        # integer two-pass form, Cout padded to 48
+    (3, 256, 9, 7, 256, False, 0, False),       # widest eligible shape
+])
+def test_short_k_1x1_engine_matches_the_generic_engine(ops, dev, case):
+    """gemm1x1_tc.cu (weights resident in shared memory, register epilogue) against conv_tc2.cu on the same staged
+    operands: same products in the same order, so the outputs are bit-identical; and both against fp64."""
+    from rdo_ptq_b200 import _lib
+    N, Cin, H, W, Cout, tr, act, integer = case
+    g = torch.Generator().manual_seed(5 + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    wshape = (Cin, Cout, 1, 1) if tr else (Cout, Cin, 1, 1)
+    w = (torch.randn(wshape, generator=g) * 0.1)
+    if integer:
+        w = torch.randint(-128, 128, wshape, generator=g).float()
+    w = w.to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    scale = (torch.rand(Cout, generator=g) * 0.01 + 0.001).to(dev) if integer else None
+    d = ops.conv_desc(x.shape, w.shape, 1, 0, tr, 0, act=act, slope=0.01)
+    packed = ops.pack_weights(w, d, tr)
+    outs = []
+    for mode in (1, 0):
+        assert _lib.lib().b200lic_set_option(b"gemm1x1", mode) == 0
+        try:
+            n0 = _lib.launch_count()
+            outs.append(ops.conv_fwd_packed(x, packed, d, tr, bias=b, w_scale=scale))
+        finally:
+            _lib.lib().b200lic_set_option(b"gemm1x1", 1)
+    assert torch.equal(outs[0], outs[1])
+    w2 = w.view(Cin, Cout).t() if tr else w.view(Cout, Cin)
+    ref = torch.einsum("ok,nkhw->nohw", w2.double(), x.double())
+    if integer:
+        ref = ref * scale.double().view(1, -1, 1, 1)
+    ref = ref + b.double().view(1, -1, 1, 1)
+    ref = torch.relu(ref) if act == 1 else (torch.where(ref > 0, ref, ref * 0.01) if act == 2 else ref)
+    assert (outs[0].double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
