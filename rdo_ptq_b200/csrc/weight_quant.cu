@@ -692,38 +692,30 @@ __global__ void __launch_bounds__(256)
                            int soft, int mode, __nv_bfloat16* __restrict__ bh, __nv_bfloat16* __restrict__ bl,
                            float* __restrict__ w_q) {
   extern __shared__ float wt[];                     // [KH*KW][32]: one output channel x 32 input channels
+  // Index arithmetic once per CTA instead of once per element (the first version spent 200 instructions per weight, most
+  // of them integer divisions by run-time KH*KW / inner / Tmax): the quantisation channel, delta and zero point of each
+  // of the 32 input channels (a (co, ci) filter never straddles a channel of the quantiser: `inner` is a multiple of
+  // KH*KW), and the source tap of every (phase, tap slot) of the packed rows.
+  __shared__ float s_d[32], s_z[32];
+  __shared__ unsigned s_src[32];
+  __shared__ short s_rs[4 * 64];                    // [phase][t] -> r*KW + s, or -1 (phases <= 4... checked by the launcher)
   const int co = blockIdx.x, ci0 = blockIdx.y * 32;
   const int KK = g.KH * g.KW;
   const int nci = min(32, g.Cin - ci0);             // <= 0 for a chunk of pure padding channels
-  const unsigned uinner = (unsigned)inner, uch = (unsigned)ch;
-  for (int e = threadIdx.x; e < nci * KK; e += blockDim.x) {
-    const int cl = e / KK, rs = e - cl * KK;
-    const unsigned src = (unsigned)((long long)co * g.s_co + (long long)(ci0 + cl) * g.s_ci + rs);
-    const unsigned c = (src / uinner) % uch;
-    const float d = __ldg(delta + c), z = __ldg(zp + c);
-    const float tq = __fdiv_rn(__ldg(w + src), d);
-    float q;
-    if (alpha == nullptr) {
-      q = __fadd_rn(rintf(tq), z);
-    } else {
-      const float a = __ldg(alpha + src);
-      float up;
-      if (soft) up = fminf(fmaxf(__fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma), 0.f), 1.f);
-      else up = a >= 0.f ? 1.f : 0.f;
-      q = __fadd_rn(__fadd_rn(floorf(tq), up), z);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 32) {
+    const int cl = threadIdx.x;
+    if (cl < nci) {
+      const unsigned src = (unsigned)((long long)co * g.s_co + (long long)(ci0 + cl) * g.s_ci);
+      const unsigned c = (src / (unsigned)inner) % (unsigned)ch;
+      s_src[cl] = src;
+      s_d[cl] = __ldg(delta + c);
+      s_z[cl] = __ldg(zp + c);
     }
-    q = fminf(fmaxf(q, 0.f), top);
-    const float n_ = __fsub_rn(q, z);
-    const float val = mode ? n_ : __fmul_rn(n_, d);
-    if (w_q) w_q[src] = val;
-    wt[rs * 32 + cl] = val;
   }
-  __syncthreads();
-  const size_t Kmax = (size_t)g.Tmax * g.Cpad;
-  const size_t per_phase = (size_t)g.CoutPad * Kmax;
-  // items: (phase, tap slot t < Tmax, pair of input channels): 64-byte runs of the packed row
-  for (int it = threadIdx.x; it < g.phases * g.Tmax * 16; it += blockDim.x) {
-    const int c2 = (it & 15) * 2, t = (it >> 4) % g.Tmax, phase = (it >> 4) / g.Tmax;
+  const int slots = g.phases * g.Tmax;
+  for (int i = threadIdx.x; i < slots; i += blockDim.x) {
+    const int phase = i / g.Tmax, t = i - phase * g.Tmax;
     int r0 = 0, s0 = 0, KHp = g.KH, KWp = g.KW, rstep = 1;
     if (g.transposed) {
       const int st = g.stride, ph = phase / st, pw = phase % st;
@@ -733,13 +725,52 @@ __global__ void __launch_bounds__(256)
       KWp = s0 < g.KW ? (g.KW - s0 + st - 1) / st : 0;
       rstep = st;
     }
-    float v0 = 0.f, v1 = 0.f;
+    short rs = -1;
     if (t < KHp * KWp) {
-      const int i = t / KWp, j = t - i * KWp;
-      const int rs = (r0 + i * rstep) * g.KW + (s0 + j * rstep);
+      const int ii = t / KWp, jj = t - ii * KWp;
+      rs = (short)((r0 + ii * rstep) * g.KW + (s0 + jj * rstep));
+    }
+    s_rs[i] = rs;
+  }
+  __syncthreads();
+  for (int cl = warp; cl < nci; cl += 8) {          // one input channel per warp and round, lanes along the taps
+    const float d = s_d[cl], z = s_z[cl];
+    const unsigned base = s_src[cl];
+    for (int rs = lane; rs < KK; rs += 32) {
+      const unsigned src = base + (unsigned)rs;
+      const float tq = __fdiv_rn(__ldg(w + src), d);
+      float q;
+      if (alpha == nullptr) {
+        q = __fadd_rn(rintf(tq), z);
+      } else {
+        const float a = __ldg(alpha + src);
+        float up;
+        if (soft) up = fminf(fmaxf(__fadd_rn(__fmul_rn(sigmoidf_(a), kStretch), kGamma), 0.f), 1.f);
+        else up = a >= 0.f ? 1.f : 0.f;
+        q = __fadd_rn(__fadd_rn(floorf(tq), up), z);
+      }
+      q = fminf(fmaxf(q, 0.f), top);
+      const float n_ = __fsub_rn(q, z);
+      const float val = mode ? n_ : __fmul_rn(n_, d);
+      if (w_q) w_q[src] = val;
+      wt[rs * 32 + cl] = val;
+    }
+  }
+  __syncthreads();
+  const size_t Kmax = (size_t)g.Tmax * g.Cpad;
+  const size_t per_phase = (size_t)g.CoutPad * Kmax;
+  // items: (slot = phase * Tmax + t, pair of input channels): 64-byte runs of the packed row
+  for (int it = threadIdx.x; it < slots * 16; it += blockDim.x) {
+    const int c2 = (it & 15) * 2, slot = it >> 4;
+    const int rs = s_rs[slot];
+    float v0 = 0.f, v1 = 0.f;
+    if (rs >= 0) {
       if (c2 < nci) v0 = wt[rs * 32 + c2];
       if (c2 + 1 < nci) v1 = wt[rs * 32 + c2 + 1];
     }
+    // slot = phase * Tmax + t and per_phase = CoutPad * Tmax * Cpad: phase * per_phase + t * Cpad without a division
+    const int phase = g.phases == 1 ? 0 : slot / g.Tmax;
+    const int t = slot - phase * g.Tmax;
     const size_t o = (size_t)phase * per_phase + (size_t)co * Kmax + (size_t)t * g.Cpad + ci0 + c2;
     const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
     __nv_bfloat162 hv;
@@ -775,7 +806,8 @@ int launch_quant_pack(const PackDst& g, const float* w, const float* alpha, cons
   __nv_bfloat16* bl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(packed) + g.b_bytes);
   const size_t tile_bytes = (size_t)32 * g.KH * g.KW * sizeof(float);
   static const bool elementwise_only = getenv("B200LIC_QPACK_ELEMENTWISE") != nullptr;     // A/B experiments
-  if (tile_bytes <= 40 * 1024 && g.Cpad / 32 <= 65535 && !elementwise_only) {
+  if (tile_bytes <= 40 * 1024 && g.Cpad / 32 <= 65535 && g.phases * g.Tmax <= 256 && (inner % (g.KH * g.KW)) == 0 &&
+      !elementwise_only) {
     dim3 tgrid((unsigned)g.Cout, (unsigned)(g.Cpad / 32), 1);
     quant_pack_tile_kernel<<<tgrid, 256, tile_bytes, s>>>(g, w, alpha, delta, zp, ch, inner, (float)(n_levels - 1), soft,
                                                           mode, bh, bl, w_q);
