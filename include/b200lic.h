@@ -513,7 +513,7 @@ B200LIC_API int b200lic_xgpu_reduce_adam_sched(const float* const* grad_ptrs, fl
                                    size_t shard_hi, const float* w, const float* delta, const float* zero_point,
                                    float* exp_avg, float* exp_avg_sq, int outer, int ch, int inner, int n_levels,
                                    const b200lic_calib_sched* sched, float beta1, float beta2, float eps,
-                                   float grad_scale, float reg_weight, float* reg_loss, b200lic_stream_t stream);
+                                   float grad_scale, float reg_weight, float* reg_loss, int exit_barrier, b200lic_stream_t stream);
 
 /* out = a * sigmoid(b) + c   (AttentionBlock tail) */
 B200LIC_API int b200lic_attn_gate(const float* a, const float* b, const float* c, size_t n, float* out,

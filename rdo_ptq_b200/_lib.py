@@ -95,7 +95,7 @@ SIGNATURES = {
     "conv_wgrad_adam_sched": [_D, _I, _P, _P, _I, _P, _P, _SZ, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F,
                               _F, _F, _P, _P],
     "xgpu_reduce_adam_sched": [_P, _P, _P, _P, _I, _I, _SZ, _SZ, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _F, _F, _F, _F,
-                               _P],
+                               _P, _I],
     "gdn_fwd_fused": [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "selftest_fast_div": [_ULL, _ULL, _P],
     "im2col_stage": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I],

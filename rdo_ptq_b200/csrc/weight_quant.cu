@@ -531,6 +531,9 @@ int launch_wgrad_reduce_adam(const float* part, int splits, int T, int Cs, int C
 // Two cross-GPU barriers on flags in the symmetric buffers: A (entry) -- every rank's gradient buffer is complete (the
 // kernels that wrote it precede this one in stream order); B (exit, last CTA only) -- every rank's alpha stores have
 // landed here before the kernel completes, so stream order protects the next reader of alpha.
+// exit_barrier = 0 drops B: valid when, on every rank, another call of this kernel (any layer: its barrier A is a
+// system-scope release / acquire over all ranks, cumulative over the stores fenced here) precedes in stream order the
+// next reader of this layer's alpha and the next writer of its gradient buffer -- a sequential sweep over >= 2 units.
 struct XgpuArgs {
   const float* const* grad_ptrs;    // [world] peer pointers: each rank's local dL/dWq of this layer
   float* const* alpha_ptrs;         // [world] peer pointers: each rank's alpha of this layer
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(256)
     xgpu_reduce_adam_kernel(XgpuArgs x, const float* __restrict__ w, const float* __restrict__ delta,
                             const float* __restrict__ zp, float* __restrict__ m, float* __restrict__ v, int ch, int inner,
                             float top, const b200lic_calib_sched* __restrict__ sched, AdamArgs ad, float grad_scale,
-                            float reg_weight, float* __restrict__ reg_loss) {
+                            float reg_weight, float* __restrict__ reg_loss, int exit_barrier) {
   __shared__ float red[32];
   const unsigned epoch = *reinterpret_cast<volatile unsigned*>(x.state) + 1u;
   // ---- barrier A: tell everyone my gradient is ready, wait until everyone's is
@@ -619,8 +622,10 @@ __global__ void __launch_bounds__(256)
     const unsigned done = atomicAdd(x.state + 1, 1u);
     if (done == gridDim.x - 1) {
       __threadfence_system();
-      for (int p = 0; p < x.world; ++p) st_release_sys(x.flag_ptrs[p] + x.world + x.rank, epoch);
-      xgpu_wait(x.flag_ptrs[x.rank], 1, x.world, epoch);
+      if (exit_barrier) {
+        for (int p = 0; p < x.world; ++p) st_release_sys(x.flag_ptrs[p] + x.world + x.rank, epoch);
+        xgpu_wait(x.flag_ptrs[x.rank], 1, x.world, epoch);
+      }
       x.state[1] = 0u;
       __threadfence();
       *reinterpret_cast<volatile unsigned*>(x.state) = epoch;
@@ -1073,7 +1078,7 @@ int b200lic_xgpu_reduce_adam_sched(const float* const* grad_ptrs, float* const* 
                                    const float* delta, const float* zero_point, float* exp_avg, float* exp_avg_sq,
                                    int outer, int ch, int inner, int n_levels, const b200lic_calib_sched* sched,
                                    float beta1, float beta2, float eps, float grad_scale, float reg_weight,
-                                   float* reg_loss, b200lic_stream_t stream) {
+                                   float* reg_loss, int exit_barrier, b200lic_stream_t stream) {
   B200_ARCH_GATE();
   B200_REQUIRE(grad_ptrs && alpha_ptrs && flag_ptrs && state && w && delta && zero_point && exp_avg && exp_avg_sq && sched,
                "xgpu_reduce_adam_sched: null pointer");
@@ -1087,7 +1092,7 @@ int b200lic_xgpu_reduce_adam_sched(const float* const* grad_ptrs, float* const* 
   int grid = grid_for(n4 ? n4 : 1, 256, 4);
   xgpu_reduce_adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, w, delta, zero_point, exp_avg, exp_avg_sq, ch, inner,
                                                                (float)(n_levels - 1), sched, ad, grad_scale, reg_weight,
-                                                               reg_loss);
+                                                               reg_loss, exit_barrier);
   B200_LAUNCH_CHECK("xgpu_reduce_adam_kernel");
   return B200LIC_OK;
 }

@@ -1034,14 +1034,15 @@ def adaround_bwd_adam_sched(w, alpha, delta, zp, d_wq, exp_avg, exp_avg_sq, axis
 
 
 def xgpu_reduce_adam_sched(peer, w, delta, zp, exp_avg, exp_avg_sq, axis, n_levels, sched, beta1=0.9, beta2=0.999,
-                           eps=1e-8, grad_scale=1.0, reg_weight=0.0, reg_loss=None):
+                           eps=1e-8, grad_scale=1.0, reg_weight=0.0, reg_loss=None, exit_barrier=True):
     """Multi-GPU tail over NVLink peer memory (dist.PeerLayer): shard-wise sum of the ranks' gradients + STE masks +
-    regulariser + Adam + broadcast of the new alpha, one kernel, no collective launch."""
+    regulariser + Adam + broadcast of the new alpha, one kernel, no collective launch.  exit_barrier=False: the caller
+    guarantees that another call (any layer) precedes the next use of this layer's alpha / gradient buffer on every rank."""
     outer, ch, inner = channel_view(w.shape, axis)
     call("xgpu_reduce_adam_sched", _p(peer.grad_ptrs), _p(peer.alpha_ptrs), _p(peer.flag_ptrs), _p(peer.state), peer.rank,
          peer.world, peer.lo, peer.hi, _p(_c(w)), _p(_c(delta.reshape(-1))), _p(_c(zp.reshape(-1))), _p(exp_avg),
          _p(exp_avg_sq), outer, ch, inner, int(n_levels), _p(sched), beta1, beta2, eps, float(grad_scale),
-         float(reg_weight), _p(reg_loss))
+         float(reg_weight), _p(reg_loss), int(bool(exit_barrier)))
 
 
 def gather_mix_sched(q, fp, idx_table, rows, prob, seed_base, units, unit, sched, out=None):

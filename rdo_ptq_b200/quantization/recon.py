@@ -304,6 +304,9 @@ class UnitTrainer:
         # (b200lic_xgpu_reduce_adam_sched) instead of ncclAllReduce + Adam; alpha moves into peer-mapped buffers.  Every
         # rank takes the same decision (same shapes, same environment).
         self.peer = None
+        # the kernel's exit barrier (peers' alpha stores have landed); a sequential multi-unit session turns it off: the
+        # next unit's entry barrier orders the same stores before this unit runs again (b200lic_xgpu_reduce_adam_sched)
+        self.peer_exit_barrier = True
         if self.world > 1 and XGPU_DEFAULT and not learn_delta and self.mods and \
                 all(m.weight.numel() % 4 == 0 for m in self.mods):
             from .. import dist as _dist
@@ -490,7 +493,7 @@ class UnitTrainer:
                     pl.grad.copy_(grads[i].reshape(-1))       # autograd-tape units: stage the gradient for the peers
                 ops.xgpu_reduce_adam_sched(pl, m.weight.data, q.delta, q.zero_point, self.exp_avg[i], self.exp_avg_sq[i],
                                            q.axis, q.n_levels, sched, grad_scale=1.0 / self.world, reg_weight=self.weight,
-                                           reg_loss=self.loss_buf[2:3])
+                                           reg_loss=self.loss_buf[2:3], exit_barrier=self.peer_exit_barrier)
             return
         if self.world > 1:
             dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.pg)
@@ -548,6 +551,9 @@ class UnitTrainer:
         if self.rd_task is not None:
             self.rd_task.close()
         if self.peer is not None:           # alpha leaves the peer-mapped buffers (they die with the trainer)
+            if not self.peer_exit_barrier:  # the last updates' peer stores: complete on every rank before alpha is read
+                torch.cuda.synchronize()
+                dist.barrier(self.pg)
             for m in self.mods:
                 a = m.weight_quantizer.alpha
                 a.data = a.data.clone()

@@ -170,6 +170,15 @@ class CalibrationSession:
         # multi-GPU: the all-reduce + Adam tail of each unit runs on ONE side stream (same collective order on every
         # rank) under the compute of the following units
         self._side = torch.cuda.Stream(device=dev) if (self.world > 1 and graph and overlap_update) else None
+        # Sequential multi-GPU sweep (one stream, tails in line): the peer-memory tail of unit k needs no exit barrier --
+        # the entry barrier of unit k+1's tail, which every rank reaches before unit k runs again, is a system-scope
+        # release / acquire over all ranks that covers unit k's alpha stores (b200lic_xgpu_reduce_adam_sched).  One
+        # cross-GPU barrier per unit instead of two.
+        self._peer_deferred = (self.world > 1 and self._side is None and max(1, n_streams if graph else 1) == 1 and
+                               len(self.units) >= 2 and all(t.peer is not None for t in self.trainers.values()))
+        if self._peer_deferred:
+            for t in self.trainers.values():
+                t.peer_exit_barrier = False
         # Units are independent problems, and most of them (hyperprior layers, 32x32 / 16x16 stages) launch
         # 1-64 CTAs: their graphs are spread over `n_streams` streams (longest-processing-time-first by a cost estimate)
         # so the small units fill the SMs the large ones leave idle.  Each stream owns its graph memory pool.
@@ -386,6 +395,8 @@ class CalibrationSession:
 
     def sweep(self, only=None):
         """One AdaRound iteration (fwd + loss + bwd(alpha) + Adam [+ all-reduce]) on every unit."""
+        if only is not None and self._peer_deferred:
+            raise ValueError("sweep(only=...) with the deferred peer barrier: the tails of ALL units order each other")
         main = torch.cuda.current_stream()
         ops.sched_tick(self.sched, *self._tick)
         graphed = self.use_graph and self.it >= self.graph_warmup

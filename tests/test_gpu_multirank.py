@@ -108,3 +108,64 @@ def test_two_ranks_keep_alpha_bit_identical_and_match_one_rank():
         print(f"{path}: max |alpha(2x4) - alpha(1x8)| = {moved:.2e}, mean {d.mean().item():.2e}")
         # Adam divides by sqrt(v): an element whose gradient is float noise can step the other way; all others agree
         assert d.mean().item() < 2e-5 and (d > 1e-3).float().mean().item() < 1e-3, path
+
+
+def _run_session(dev, cali, batch, xgpu):
+    """Six sweeps (eager + graph replays) of a SEQUENTIAL whole-model session: with the peer-memory tail the session
+    drops the kernel's exit barrier (the next unit's entry barrier orders the alpha stores); returns every unit's alpha."""
+    from rdo_ptq_b200 import codec, synth, quantization as Q
+    from rdo_ptq_b200.quantization import recon
+    from rdo_ptq_b200.quantization.session import CalibrationSession
+    recon.XGPU_DEFAULT = xgpu
+    torch.manual_seed(1005)
+    m = codec.ARCHS["mbt2018-mean"](N=16, M=24).eval()
+    synth.init_weights(m, gain=1.2)
+    m.to(dev)
+    q = Q.QuantModel(m, WQ, AQ).eval()
+    s = CalibrationSession(q, cali, batch_size=batch, iters=40, warmup=0.1, n_streams=1, overlap_update=False)
+    deferred = s._peer_deferred
+    for _ in range(6):
+        s.sweep()
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    out = {n: t.mods[0].weight_quantizer.alpha.data.clone() for n, t in s.trainers.items()}
+    s.finish()
+    return out, deferred
+
+
+def _session_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from rdo_ptq_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pool = synth.calibration_patches(8, 64)
+    shard = pool[rank::world].contiguous().to(dev)
+    nccl, d0 = _run_session(dev, shard, 8 // world, xgpu=False)
+    peer, d1 = _run_session(dev, shard, 8 // world, xgpu=True)
+    same = True
+    for n, a in peer.items():
+        parts = [torch.empty_like(a) for _ in range(world)]
+        dist.all_gather(parts, a.contiguous())
+        same &= all(torch.equal(parts[0], p) for p in parts[1:])
+    same_as_nccl = all(torch.equal(peer[k], nccl[k]) for k in peer)
+    if rank == 0:
+        q.put((same, same_as_nccl, d0, d1, len(peer)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sequential_session_with_deferred_peer_barrier_matches_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_session_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    same, same_as_nccl, d0, d1, n_units = q.get(timeout=600)
+    [p.join(timeout=120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert n_units == 20 and d1 and not d0          # the deferred form was in use with the peer tail only
+    assert same, "alpha differs between the ranks"
+    assert same_as_nccl, "the peer-memory tail with the deferred exit barrier and ncclAllReduce + Adam disagree"
