@@ -2,6 +2,7 @@
 #include <atomic>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200lic {
@@ -61,6 +62,14 @@ int num_sms() {
 }  // namespace b200lic
 
 namespace b200lic {
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B200LIC_PDL");
+    on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
 int tc2_debug_timeline(unsigned long long* out, int n);
 void tc2_set_streamk_mode(int v);
 void gemm1x1_set_mode(int v);

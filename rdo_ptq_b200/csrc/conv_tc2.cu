@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                            const float* __restrict__ w_scale, const float* __restrict__ gdn_x,
                            float* __restrict__ norm_out, float* __restrict__ y, unsigned long long* __restrict__ dbg,
                            float* __restrict__ sk_part, unsigned* __restrict__ sk_cnt) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1254,7 +1255,7 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
       return B200LIC_ERR_CUDA;
     }
   }
-  tc2_gather_gemm_kernel<<<grid, 64 + 32 * p.epi_warps, p.smem_bytes, s>>>(mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
+  launch_pdl(tc2_gather_gemm_kernel, dim3(grid), dim3(64 + 32 * p.epi_warps), p.smem_bytes, s, mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
                                                                 norm_out, y, dbg, sk_part, sk_cnt);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;

@@ -122,6 +122,7 @@ struct WgGeom {
 __global__ void __launch_bounds__(kWgThreads, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_s, WgGeom g,
                     float* __restrict__ part) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace wg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 // (one 16-byte load per slab) and issues the loads of eight slabs before the first add.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int splits, int T, int Cs, int Cb,
                                                             float* __restrict__ dw) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   const size_t per = (size_t)T * Cs * Cb;
   auto store = [&](size_t i, float acc) {
     const int cb = (int)(i % Cb);
@@ -532,7 +534,7 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
     attr_set = true;
   }
   dim3 grid(p.units, p.n_tiles, p.splits);
-  tc_wgrad_kernel<<<grid, kWgThreads, p.smem_bytes, s>>>(mb, ms, g, part);
+  launch_pdl(tc_wgrad_kernel, grid, dim3(kWgThreads), p.smem_bytes, s, mb, ms, g, part);
   B200_LAUNCH_CHECK(name);
   if (tail != nullptr) return launch_wgrad_reduce_adam(part, p.splits, KH * KW, Cs, Cb, tail, s);   // (any split count:
   // the fused tail always sums in the serial order; with > 32 slabs it differs from wgrad_reduce_kernel's butterfly in the
@@ -540,7 +542,7 @@ int tc_wgrad_ex(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb, int KH, i
   const size_t per = (size_t)KH * KW * Cs * Cb;
   // one thread (splits <= 32) or one warp (more slabs) per four elements
   const size_t red_threads = ((per + 3) / 4) * (p.splits > 32 ? 32 : 1);
-  wgrad_reduce_kernel<<<grid_for(red_threads, 256), 256, 0, s>>>(part, p.splits, KH * KW, Cs, Cb, dw);
+  launch_pdl(wgrad_reduce_kernel, dim3(grid_for(red_threads, 256)), dim3(256), 0, s, part, p.splits, KH * KW, Cs, Cb, dw);
   B200_LAUNCH_CHECK("wgrad_reduce_kernel");
   return B200LIC_OK;
 }

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kGdThreads, 1)
     gdn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, GdnGeom g,
                      const float* __restrict__ x, const unsigned* __restrict__ keys, const float* __restrict__ beta,
                      float* __restrict__ y) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace gd;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -626,7 +627,7 @@ int b200lic_gdn_fwd_fused(const float* x, const float* minmax, int n_bits, const
   }
   const int sms = num_sms();
   const int grid = g.n_tiles < sms ? g.n_tiles : sms;
-  gdn_fused_kernel<<<grid, kGdThreads, smem, as_stream(stream)>>>(mx, mb, g, x, reinterpret_cast<const unsigned*>(minmax),
+  launch_pdl(gdn_fused_kernel, dim3(grid), dim3(kGdThreads), smem, as_stream(stream), mx, mb, g, x, reinterpret_cast<const unsigned*>(minmax),
                                                                   beta, y);
   B200_LAUNCH_CHECK("gdn_fused_kernel");
   return B200LIC_OK;

@@ -115,6 +115,7 @@ struct Gemm1x1Geom {
 __global__ void __launch_bounds__(kG1Threads, 1)
     gemm1x1_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Gemm1x1Geom g,
                    const float* __restrict__ bias, const float* __restrict__ w_scale, float* __restrict__ y) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace g1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -368,7 +369,7 @@ int gemm1x1_launch(long long M, int HW, int Cpad, int Cout, int CoutPad, void* x
   }
   const int sms = num_sms();
   const int grid = g.n_tiles < sms ? g.n_tiles : sms;
-  gemm1x1_kernel<<<grid, kG1Threads, smem, s>>>(ma, mb, g, bias, w_scale, y);
+  launch_pdl(gemm1x1_kernel, dim3(grid), dim3(kG1Threads), smem, s, ma, mb, g, bias, w_scale, y);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256)
     stage_mix_kernel(const float* __restrict__ q, const float* __restrict__ fp, PickSched ps, int C, int HW, int cpad,
                      float prob, unsigned long long seed, int square, __nv_bfloat16* __restrict__ xh,
                      __nv_bfloat16* __restrict__ xl, float* __restrict__ out) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   __shared__ float t[64][65];
   const long long* idx = nullptr;
   if (ps.sched != nullptr) {
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256, 4)
                       float p, float scale, float grad_scale, int act, float slope, const float* __restrict__ gdn_x,
                       const float* __restrict__ gdn_norm, int gdn_inverse, float* __restrict__ loss,
                       __nv_bfloat16* __restrict__ gh, __nv_bfloat16* __restrict__ gl, float* __restrict__ d_pred) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   __shared__ float t[64][65];
   __shared__ float red[32];
   const long long* idx = nullptr;
@@ -438,7 +440,7 @@ int b200lic_stage_mix_sched(const float* q, const float* fp, const long long* id
   B200_REQUIRE(((((uintptr_t)q) | ((uintptr_t)fp) | ((uintptr_t)out)) & 7) == 0, "stage_mix_sched: 8-byte alignment");
   PickSched ps{idx_table, table_rows, units, unit, sched};
   dim3 grid((unsigned)(((cpad + 63) / 64) * ((HW + 63) / 64)), 1, (unsigned)rows);
-  stage_mix_kernel<<<grid, 256, 0, as_stream(stream)>>>(q, fp, ps, C, HW, cpad, prob, seed_base & 0xFFFFFFFFFFFFull, square,
+  launch_pdl(stage_mix_kernel, grid, dim3(256), 0, as_stream(stream), q, fp, ps, C, HW, cpad, prob, seed_base & 0xFFFFFFFFFFFFull, square,
                                                          reinterpret_cast<__nv_bfloat16*>(x_hi),
                                                          reinterpret_cast<__nv_bfloat16*>(x_lo), out);
   B200_LAUNCH_CHECK("stage_mix_kernel");
@@ -463,12 +465,12 @@ int b200lic_lp_loss_stage_sched(const float* pred, const float* tgt_cache, const
   PickSched ps{idx_table, table_rows, units, unit, sched};
   dim3 grid((unsigned)(((cpad + 63) / 64) * ((HW + 63) / 64)), 1, (unsigned)rows);
   if (gdn_x != nullptr)
-    loss_stage_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale,
+    launch_pdl(loss_stage_kernel<true>, grid, dim3(256), 0, as_stream(stream), pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale,
                                                                  act, act_slope, gdn_x, gdn_norm, gdn_inverse, loss,
                                                                  reinterpret_cast<__nv_bfloat16*>(dy_hi),
                                                                  reinterpret_cast<__nv_bfloat16*>(dy_lo), d_pred);
   else
-    loss_stage_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale,
+    launch_pdl(loss_stage_kernel<false>, grid, dim3(256), 0, as_stream(stream), pred, tgt_cache, ps, C, HW, cpad, p, scale, grad_scale,
                                                                   act, act_slope, nullptr, nullptr, 0, loss,
                                                                   reinterpret_cast<__nv_bfloat16*>(dy_hi),
                                                                   reinterpret_cast<__nv_bfloat16*>(dy_lo), d_pred);

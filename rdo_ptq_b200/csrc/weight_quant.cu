@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(256)
 constexpr int kTailCb = 32;
 __global__ void __launch_bounds__(256)
     wgrad_reduce_adam_kernel(const float* __restrict__ part, int splits, int T, int Cs, int Cb, WgTail t, AdamArgs ad) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   extern __shared__ float tile[];                 // [kTailCb][T]
   __shared__ float red[32];
   const int cbb = (Cb + kTailCb - 1) / kTailCb;
@@ -516,7 +517,7 @@ int launch_wgrad_reduce_adam(const float* part, int splits, int T, int Cs, int C
     set_error("wgrad_reduce_adam: %d taps exceed the tile", T);
     return B200LIC_ERR_UNSUPPORTED;
   }
-  wgrad_reduce_adam_kernel<<<Cs * cbb, 256, smem, s>>>(part, splits, T, Cs, Cb, *tail, ad);
+  launch_pdl(wgrad_reduce_adam_kernel, dim3(Cs * cbb), dim3(256), smem, s, part, splits, T, Cs, Cb, *tail, ad);
   B200_LAUNCH_CHECK("wgrad_reduce_adam_kernel");
   return B200LIC_OK;
 }
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(256)
                            const float* __restrict__ delta, const float* __restrict__ zp, int ch, int inner, float top,
                            int soft, int mode, __nv_bfloat16* __restrict__ bh, __nv_bfloat16* __restrict__ bl,
                            float* __restrict__ w_q) {
+  pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   extern __shared__ float wt[];                     // [KH*KW][32]: one output channel x 32 input channels
   // Index arithmetic once per CTA instead of once per element (the first version spent 200 instructions per weight, most
   // of them integer divisions by run-time KH*KW / inner / Tmax): the quantisation channel, delta and zero point of each
@@ -814,7 +816,7 @@ int launch_quant_pack(const PackDst& g, const float* w, const float* alpha, cons
   if (tile_bytes <= 40 * 1024 && g.Cpad / 32 <= 65535 && g.phases * g.Tmax <= 256 && (inner % (g.KH * g.KW)) == 0 &&
       !elementwise_only) {
     dim3 tgrid((unsigned)g.Cout, (unsigned)(g.Cpad / 32), 1);
-    quant_pack_tile_kernel<<<tgrid, 256, tile_bytes, s>>>(g, w, alpha, delta, zp, ch, inner, (float)(n_levels - 1), soft,
+    launch_pdl(quant_pack_tile_kernel, tgrid, dim3(256), tile_bytes, s, g, w, alpha, delta, zp, ch, inner, (float)(n_levels - 1), soft,
                                                           mode, bh, bl, w_q);
     B200_LAUNCH_CHECK("quant_pack_tile_kernel");
     if (g.CoutPad > g.Cout) {
