@@ -335,7 +335,9 @@ def run_cuda(args):
                 "clocks": clocks, "roofline": roof, "roofline_hbm": hbm_rows, "cpu_baseline": cpu, "parity": parity,
                 "torch_eager_gpu": eager, "config3_cheng2020_calib": cheng,
                 "gflop_per_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e9,
-                "tflops_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e12 / (seq["ms_per_step"] / 1e3)}
+                "tflops_step": 2 * 2 * sum(macs.values()) * PER_GPU_BATCH / 1e12 / (seq["ms_per_step"] / 1e3),
+                # layers that asked for the tensor-core engine and ran on the exact-fp32 SIMT engine instead (must be 0)
+                "simt_fallbacks": _lib.simt_fallback_count()}
         line.update(fwd)
     if world > 1:
         dist.barrier()

@@ -68,6 +68,9 @@ B200LIC_API int b200lic_debug_timeline(unsigned long long* out, int n);
 B200LIC_API int b200lic_set_option(const char* name, int value);
 /* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
 B200LIC_API unsigned long long b200lic_launch_count(void);
+/* Calls that asked for B200LIC_ENGINE_AUTO and ran on the exact-fp32 SIMT engine because the tcgen05 engine rejected the
+ * shape (the first one of a process is also reported on stderr; B200LIC_QUIET=1 silences the message). */
+B200LIC_API unsigned long long b200lic_simt_fallback_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K7  per-channel weight range + fake-quant.

@@ -110,7 +110,7 @@ SIGNATURES = {
     "pixel_unshuffle": [_P, _I, _I, _I, _I, _I, _P],
 }
 PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "device_check": (C.c_int, []),
-         "launch_count": (C.c_ulonglong, []), "factorized_table_floats": (C.c_int, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
+         "launch_count": (C.c_ulonglong, []), "simt_fallback_count": (C.c_ulonglong, []), "factorized_table_floats": (C.c_int, []), "conv_workspace_bytes": (C.c_size_t, [_D, C.c_int]),
          "debug_timeline": (C.c_int, [C.c_void_p, C.c_int]),
          "set_option": (C.c_int, [C.c_char_p, C.c_int]),
          "gdn_fused_ok": (C.c_int, [C.c_int, C.c_int]),
@@ -159,3 +159,8 @@ def call(name, *args, stream=None):
 
 def launch_count():
     return int(lib().b200lic_launch_count())
+
+
+def simt_fallback_count():
+    """Calls that ran on the exact-fp32 SIMT engine because the tensor-core engine rejected the shape (ENGINE_AUTO)."""
+    return int(lib().b200lic_simt_fallback_count())

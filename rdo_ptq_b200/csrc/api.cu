@@ -62,6 +62,20 @@ int num_sms() {
 }  // namespace b200lic
 
 namespace b200lic {
+static std::atomic<unsigned long long> g_simt_fallbacks{0};
+void note_simt_fallback(const char* op) {
+  if (g_simt_fallbacks.fetch_add(1, std::memory_order_relaxed) == 0 && !getenv("B200LIC_QUIET")) {
+    char name[48];
+    size_t n = 0;
+    while (op[n] && op[n] != '(' && n + 1 < sizeof(name)) {
+      name[n] = op[n];
+      ++n;
+    }
+    name[n] = 0;
+    fprintf(stderr, "libb200lic: %s -> exact-fp32 SIMT engine under B200LIC_ENGINE_AUTO (%s); first occurrence, further ones "
+                    "are only counted (b200lic_simt_fallback_count)\n", name, g_err);
+  }
+}
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -92,4 +106,5 @@ int b200lic_version(void) { return 200; }
 const char* b200lic_last_error_string(void) { return b200lic::g_err; }
 int b200lic_device_check(void) { return b200lic::check_arch(); }
 unsigned long long b200lic_launch_count(void) { return b200lic::g_launches.load(); }
+unsigned long long b200lic_simt_fallback_count(void) { return b200lic::g_simt_fallbacks.load(); }
 }

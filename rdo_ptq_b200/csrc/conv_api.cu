@@ -38,11 +38,17 @@ size_t tc_deconv_wgrad_ws(const b200lic_conv_desc*);
 using namespace b200lic;
 
 // AUTO: tensor cores when eligible, else SIMT.  TC: tensor cores or an error.  SIMT: exact-fp32 engine.
+// The AUTO -> SIMT fallback is counted (b200lic_simt_fallback_count) and the first one of a process is reported on
+// stderr with the reason the tensor-core engine gave: a layer that silently runs 20x slower is a performance bug.
+namespace b200lic {
+void note_simt_fallback(const char* op);
+}
 #define DISPATCH(tc_call, simt_call)                                     \
   do {                                                                   \
     if (d->engine != B200LIC_ENGINE_SIMT) {                              \
       int _rc = (tc_call);                                               \
       if (_rc != B200LIC_ERR_UNSUPPORTED || d->engine == B200LIC_ENGINE_TC) return _rc; \
+      ::b200lic::note_simt_fallback(#tc_call);                           \
     }                                                                    \
     return (simt_call);                                                  \
   } while (0)
