@@ -521,7 +521,11 @@ def test_entropy_kernels_full_size_properties(ops, dev):
     mu = torch.randn(1, 320, 96, 128, generator=gen).to(dev)
     yh, lik, bits = ops.gaussian_lik(y, sc, mu)
     assert torch.equal(yh, torch.round(y - mu) + mu)
-    assert abs(bits.item() - (-torch.log2(lik.double()).sum().item())) < 1e-5 * lik.numel()
+    # bits is an fp32 sum of ~4e7 built from per-CTA partial sums with atomicAdd (ulp 4 at that magnitude, order not fixed):
+    # relative 1e-5 -- the absolute bound used before (1e-5 * numel = 39) sat inside that rounding noise and failed about
+    # one run in ten
+    ref_bits = -torch.log2(lik.double()).sum().item()
+    assert abs(bits.item() - ref_bits) < 1e-5 * abs(ref_bits)
     tot = torch.zeros_like(lik[..., :8, :8])                  # sum over the integer grid on a patch
     for k in range(-60, 61):
         _, l, _ = ops.gaussian_lik((mu + k)[..., :8, :8].contiguous(), sc[..., :8, :8].contiguous(),
