@@ -4,6 +4,7 @@ The Lu2022 Swin blocks of that file (QuantNIC/QuantMlp/QuantWindowAttention/...)
 (SURVEY.md section 2 row 3).  Residual add, LeakyReLU and the block-level dynamic activation quantiser run as
 libb200lic kernels (`add_act`, K8).
 """
+import torch
 import torch.nn as nn
 
 from .. import ops
@@ -29,11 +30,29 @@ class BaseQuantBlock(nn.Module):
             if isinstance(m, QuantModule):
                 m.set_quant_state(weight_quant, act_quant)
 
-    def _aq(self, t):
-        return self.act_quantizer(t, True) if (self.use_act_quant and self.trained) else t
+    def _aq(self, t, consumer=None):
+        """Block-level dynamic activation quantiser.  `consumer`: the QuantModule that is the ONLY reader of the result --
+        in an evaluation forward the quantiser is then deferred into that module's operand staging (ops.DEFER_ACTQ: the
+        statistics are taken here, the codes are applied while the consumer stages its operand; same values)."""
+        if not (self.use_act_quant and self.trained):
+            return t
+        if (consumer is not None and ops.DEFER_ACTQ and not torch.is_grad_enabled() and t.dim() == 4
+                and 4 * t.numel() >= ops.DEFER_ACTQ_MIN_BYTES and not consumer._forward_hooks
+                and not consumer._forward_pre_hooks):
+            bits = self.act_quantizer.n_bits if self.act_quantizer.act_bits_follow_n_bits else 8
+            t = t.detach()
+            t._b200_actq = (ops.act_quant_stats(t), bits)
+            return t
+        return self.act_quantizer(t, True)
 
     def _lrelu(self, t):
         return ops.add_act_fn(t, None, ops.ACT_LEAKY_RELU, float(self.leaky_relu.negative_slope))
+
+    def _conv_lrelu(self, conv, x):
+        """LeakyReLU(conv(x)): without a gradient the activation rides in the convolution's epilogue."""
+        if torch.is_grad_enabled() or conv._forward_hooks:
+            return self._lrelu(conv(x))
+        return conv(x, act_override=(ops.ACT_LEAKY_RELU, float(self.leaky_relu.negative_slope)))
 
 
 class QuantRBWS(BaseQuantBlock):
@@ -49,7 +68,7 @@ class QuantRBWS(BaseQuantBlock):
                      if basic_block.skip is not None else None)
 
     def forward(self, x):
-        out = self._aq(self._lrelu(self.conv1(x)))
+        out = self._aq(self._conv_lrelu(self.conv1, x), consumer=self.conv2)
         out = self.gdn(self.conv2(out))
         out = ops.add_act_fn(out, self.skip(x) if self.skip is not None else x)
         return self._aq(out)
@@ -70,7 +89,7 @@ class QuantRBU(BaseQuantBlock):
                                       basic_block.upsample[1])
 
     def forward(self, x):
-        out = self._aq(self._lrelu(self.subpel_conv(x)))
+        out = self._aq(self._lrelu(self.subpel_conv(x)), consumer=self.conv)
         out = self.igdn(self.conv(out))
         return self._aq(ops.add_act_fn(out, self.upsample(x)))
 
@@ -87,8 +106,8 @@ class QuantRB(BaseQuantBlock):
                      if basic_block.skip is not None else None)
 
     def forward(self, x):
-        out = self._aq(self._lrelu(self.conv1(x)))
-        out = self._aq(self._lrelu(self.conv2(out)))
+        out = self._aq(self._conv_lrelu(self.conv1, x), consumer=self.conv2)
+        out = self._aq(self._conv_lrelu(self.conv2, out))
         out = ops.add_act_fn(out, self.skip(x) if self.skip is not None else x)
         return self._aq(out)
 

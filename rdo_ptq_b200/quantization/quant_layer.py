@@ -208,8 +208,10 @@ class QuantModule(nn.Module):
         col = ops.conv_fwd_packed(x, packed, d1, True, w_scale=scale, ws=ws)
         return ops.col2im(col, bias, d.Cout, d.KH, d.KW, d.stride, d.pad, d.Ho, d.Wo, act, slope)
 
-    def forward(self, input: torch.Tensor):
-        act, slope = ops._act_id(self.activation_function)
+    def forward(self, input: torch.Tensor, act_override=None):
+        """act_override = (act id, slope): an activation the CALLER applies right after this module (the hand-written
+        Cheng2020 blocks, quant_block.py) folded into this module's epilogue; same values, one launch less."""
+        act, slope = act_override if act_override is not None else ops._act_id(self.activation_function)
         if self.is_ps:
             return ops.pixel_shuffle(input, self.fwd_kwargs, act, slope)
         out = None

@@ -3,7 +3,7 @@ import torch.nn as nn
 
 from ..codec.layers import GDN
 from ..codec.entropy_models import EntropyBottleneck
-from .quant_block import specials, BaseQuantBlock
+from .quant_block import specials, BaseQuantBlock, QuantRBWS, QuantRBU
 from .quant_layer import QuantModule, StraightThrough
 
 
@@ -19,6 +19,12 @@ def link_sequential_consumers(model: nn.Module):
         for a, b in zip(kids, kids[1:]):
             if isinstance(a, QuantModule) and isinstance(b, QuantModule) and not b.is_ps:
                 a.__dict__["_defer_to"] = b
+    # the same inside the hand-written Cheng2020 blocks: conv -> (I)GDN with nothing else reading the conv's output
+    for m in model.modules():
+        if isinstance(m, QuantRBWS):
+            m.conv2.__dict__["_defer_to"] = m.gdn
+        elif isinstance(m, QuantRBU):
+            m.conv.__dict__["_defer_to"] = m.igdn
 
 
 class QuantModel(nn.Module):
