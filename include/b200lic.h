@@ -64,7 +64,9 @@ B200LIC_API int b200lic_device_check(void);
 B200LIC_API int b200lic_debug_timeline(unsigned long long* out, int n);
 /* Scheduling knobs (A/B measurements, tests).  "streamk": 1 = stream-K scheduling of the conv engine where it pays
  * (default), 0 = whole work items only, 2 = wherever the shape is eligible.  Results are identical up to fp32 summation
- * order of the K ranges. */
+ * order of the K ranges.  "pair": CTA-pair form of the conv engine (clusters of two CTAs, tcgen05 cta_group::2, M = 256 per
+ * MMA, each CTA staging half of the weight tile): 1 = where the plan expects it to pay (default), 0 = off, 2 = wherever
+ * eligible.  "gemm1x1": 0 = the generic engine also runs the short-K 1x1 layers. */
 B200LIC_API int b200lic_set_option(const char* name, int value);
 /* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
 B200LIC_API unsigned long long b200lic_launch_count(void);

@@ -86,12 +86,17 @@ bool pdl_enabled() {
 }
 int tc2_debug_timeline(unsigned long long* out, int n);
 void tc2_set_streamk_mode(int v);
+void tc2_set_pair_mode(int v);
 void gemm1x1_set_mode(int v);
 }
 extern "C" {
 int b200lic_set_option(const char* name, int value) {
   if (name && strcmp(name, "streamk") == 0) {
     b200lic::tc2_set_streamk_mode(value);
+    return B200LIC_OK;
+  }
+  if (name && strcmp(name, "pair") == 0) {
+    b200lic::tc2_set_pair_mode(value);
     return B200LIC_OK;
   }
   if (name && strcmp(name, "gemm1x1") == 0) {      // 0: the generic engine also runs the short-K 1x1 layers (A/B, tests)

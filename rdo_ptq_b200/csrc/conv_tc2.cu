@@ -73,6 +73,39 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// cta_group::2 forms (CTA pair, see Tc2Geom::pair): the data lands in the executing CTA's shared memory, the
+// complete_tx goes to an mbarrier of either CTA of the pair (a shared::cluster address -- the leader's full barrier).
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {   // shared::cta -> shared::cluster of `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -96,6 +129,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// CTA pair: M = 256 (128 rows from each CTA's A tile), B = the two CTAs' N/2-row halves; issued by the leader only.
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair when the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
   asm volatile(
@@ -158,7 +207,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
 //   acc[mt * CHAINS + chain]: TMEM address of each accumulator tile
 //   EXACT: the weight operand is exactly representable in bf16 (integer codes minus zero point, |n| <= 256), so its
 //          lo slice is zero and the hi*lo pass is skipped: two passes per product instead of three.
-template <int MT, int CHAINS, bool EXACT = false>
+template <int MT, int CHAINS, bool EXACT = false, bool PAIR = false>
 __device__ __forceinline__ void issue_kblock(uint64_t a0, uint64_t b0, uint64_t b_lo_off, const uint32_t* acc,
                                              uint32_t idesc, bool first) {
   constexpr uint64_t kALo = (128 * 64) >> 4, kATile = (2 * 128 * 64) >> 4;
@@ -173,7 +222,8 @@ __device__ __forceinline__ void issue_kblock(uint64_t a0, uint64_t b0, uint64_t 
         const uint64_t ad = a0 + (uint64_t)mt * kATile + (pass == 2 ? kALo : 0) + o;
         const uint64_t bd = b0 + (pass == 1 ? b_lo_off : 0) + o;
         const uint32_t accum = (first && k == 0 && pass < CHAINS) ? 0u : 1u;
-        umma_bf16(acc[mt * CHAINS + (pass % CHAINS)], ad, bd, idesc, accum);
+        if (PAIR) umma_bf16_2cta(acc[mt * CHAINS + (pass % CHAINS)], ad, bd, idesc, accum);
+        else umma_bf16(acc[mt * CHAINS + (pass % CHAINS)], ad, bd, idesc, accum);
       }
     }
   }
@@ -203,6 +253,8 @@ struct Tc2Geom {
   int sk;                     // stream-K: every CTA takes one contiguous range of (item, K block) units (see SegIter)
   int sk_len;                 // units per CTA
   long long sk_total;         // items x K blocks per item
+  int pair;                   // CTA pair (cluster of 2, tcgen05 cta_group::2): one work item = MT pixel tiles per CTA, M = 256
+                              // per MMA, each CTA stages its own A tiles and HALF of the weight tile
 };
 
 // Work of one CTA.  Default: whole items, strided over the grid.  Stream-K (g.sk): the K loops of all items are laid end to
@@ -217,11 +269,12 @@ struct SegIter {
   long long pos, end;
   __device__ __forceinline__ void init(const Tc2Geom& g, int total_items_, int nkb_) {
     sk = g.sk;
-    step = (int)gridDim.x;
+    const int np = g.pair ? 2 : 1;              // both CTAs of a pair walk the same items
+    step = (int)gridDim.x / np;
     total_items = total_items_;
     nkb = nkb_;
-    w = (int)blockIdx.x;
-    pos = (long long)blockIdx.x * g.sk_len;
+    w = (int)blockIdx.x / np;
+    pos = (long long)w * g.sk_len;
     end = pos + g.sk_len;
     if (end > g.sk_total) end = g.sk_total;
   }
@@ -276,6 +329,9 @@ __device__ __forceinline__ PhaseGeom phase_geom(const Tc2Geom& g, int phase) {
   return q;
 }
 
+// PAIR: the CTA-pair form (Tc2Geom::pair), a separate instantiation -- a kernel that contains cta_group::2 instructions
+// can only be launched in clusters of an even size.
+template <bool PAIR>
 __global__ void __launch_bounds__(kT2Threads, 1)
     tc2_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                            const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
@@ -291,7 +347,9 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- shared memory carve-up -------------------------------------------------------------------------------------
-  const uint32_t b_tile_bytes = (uint32_t)g.BN * 64u;
+  const int np = PAIR ? 2 : 1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // 0 = leader: issues the MMAs, owns the full barriers
+  const uint32_t b_tile_bytes = (uint32_t)(g.BN / np) * 64u;     // a CTA of a pair stages its half of the weight tile
   const uint32_t stage_bytes = (uint32_t)g.MT * 2u * kA2Bytes + 2u * b_tile_bytes;
   const uint32_t stage_area = (uint32_t)g.stages * stage_bytes;
   const uint32_t sY = smem_base + stage_area;                    // [2] output staging
@@ -316,19 +374,27 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8u * s, 1);
-      mbar_init(tempty_bar + 8u * s, (uint32_t)g.epi_warps);
+      mbar_init(tempty_bar + 8u * s, (uint32_t)(g.epi_warps * np));   // pair: both CTAs' epilogues report to the leader
     }
     for (int s = 0; s < g.x_slots; ++s) mbar_init(xfull_bar + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
-                 "r"((uint32_t)g.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {     // one warp of EACH CTA of the pair: the same columns are allocated in both tensor memories
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                   "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr),
+                   "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_gen;
   const bool trace = dbg != nullptr && blockIdx.x == 0;     // B200LIC_TC_DEBUG=3: timeline of CTA 0's first item (ns)
@@ -355,12 +421,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const int tiles_w = (q.Pb + g.BW - 1) / g.BW, tiles_h = (q.Pa + g.BH - 1) / g.BH;
         const int tiles_n = (g.N + g.BI - 1) / g.BI;
         const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
-        if (mg * g.MT >= m_tiles) continue;
+        if (mg * np * g.MT >= m_tiles) continue;
         const int num_kb = q.KHp * q.KWp * cblocks;
         const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
         int wb[2], hb[2], nb[2];
         for (int t = 0; t < g.MT; ++t) {
-          int mt = mg * g.MT + t;
+          int mt = (mg * np + (int)rank) * g.MT + t;
           if (mt >= m_tiles) mt = m_tiles - 1;      // odd tail: reload the last tile, the epilogue skips it
           const int tw = mt % tiles_w, th = (mt / tiles_w) % tiles_h, tn = mt / (tiles_w * tiles_h);
           wb[t] = tw * g.BW * q.in_step + q.base_w;
@@ -378,6 +444,33 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           mbar_wait(empty_bar + 8u * s, sphase ^ 1u);
           const uint32_t st_base = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t fb = full_bar + 8u * s;
+          if (PAIR) {
+            // Both CTAs fill their own stage; every byte reports to the LEADER's full barrier (its MMA thread consumes
+            // the stage of both), which expects the bytes of the pair.  The peer's loads can only run ahead of the
+            // leader's expect_tx within one phase: its empty barrier is released by the leader's multicast commit.
+            const uint32_t fbl = mapa_u32(fb, 0);
+            const uint32_t my_bytes = g.w_exact ? stage_bytes - b_tile_bytes : stage_bytes;
+            if (rank == 0) mbar_expect_tx(fb, 2u * my_bytes);
+            for (int mt = 0; mt < g.MT; ++mt) {
+              const int cw = wb[mt] + j * q.tap_step, ch = hb[mt] + i * q.tap_step;
+              tma_load_5d_2cta(st_base + (uint32_t)(2 * mt) * kA2Bytes, &map_ah, fbl, cb * 32, cw, ch, nb[mt], 0);
+            }
+            const uint32_t bb = st_base + (uint32_t)g.MT * 2u * kA2Bytes;
+            const int brow = n_tile * g.BN + (int)rank * (g.BN >> 1);     // this CTA's half of the output channels
+            tma_load_4d_2cta(bb, g.w_exact ? &map_bl : &map_bh, fbl, kb * 32, brow, phase, 0);
+            if (++s == g.stages) {
+              s = 0;
+              sphase ^= 1u;
+            }
+            if (++cb == cblocks) {
+              cb = 0;
+              if (++j == q.KWp) {
+                j = 0;
+                ++i;
+              }
+            }
+            continue;
+          }
           if (g.dbg_mode == 2) {
             mbar_arrive(fb);
             if (++s == g.stages) {
@@ -415,10 +508,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====================================================================================
-    if (elect_one()) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((128u >> 4) << 24);
+    // ===== MMA issuer (one thread; in a CTA pair the leader's) ========================================================
+    if (rank == 0 && elect_one()) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128 (256 over a CTA pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) |
+                             ((PAIR ? (256u >> 4) : (128u >> 4)) << 24);
       int s = 0;
       uint32_t sphase = 0;
       int set = 0;
@@ -427,7 +521,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       const uint64_t a_desc0 = make_kmajor_sw64_desc(smem_base);
       const uint64_t b_desc0 = make_kmajor_sw64_desc(smem_base + (uint32_t)g.MT * 2u * kA2Bytes);
       const uint64_t b_lo_off = (uint64_t)(b_tile_bytes >> 4);
-      const int variant = g.w_exact ? 6 + (g.MT - 1) : (g.MT - 1) * 3 + (g.chains - 1);
+      const int variant = PAIR ? (g.w_exact ? 10 + (g.MT - 1) : 8 + (g.MT - 1))
+                                 : (g.w_exact ? 6 + (g.MT - 1) : (g.MT - 1) * 3 + (g.chains - 1));
       SegIter it;
       it.init(g, total_items, g.KH * g.KW * cblocks);
       int w, kb_lo, kb_hi;
@@ -438,7 +533,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const int tiles_w = (q.Pb + g.BW - 1) / g.BW, tiles_h = (q.Pa + g.BH - 1) / g.BH;
         const int tiles_n = (g.N + g.BI - 1) / g.BI;
         const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
-        if (mg * g.MT >= m_tiles) continue;
+        if (mg * np * g.MT >= m_tiles) continue;
         const int num_kb = q.KHp * q.KWp * cblocks;
         if (num_kb == 0) continue;                       // nothing to accumulate: the epilogue writes bias only
         const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
@@ -457,24 +552,35 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             const uint64_t sd = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
             const uint64_t a0 = a_desc0 + sd, b0 = b_desc0 + sd;
             const bool first = kb == kb_lo;
-            switch (variant) {               // uniform branch; each arm is straight-line code
-              case 6: issue_kblock<1, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
-              case 7: issue_kblock<2, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
-              case 0: issue_kblock<1, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
-              case 1: issue_kblock<1, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
-              case 2: issue_kblock<1, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
-              case 3: issue_kblock<2, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
-              case 4: issue_kblock<2, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
-              default: issue_kblock<2, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
+            if constexpr (PAIR) {
+              switch (variant) {
+                case 8: issue_kblock<1, 1, false, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 9: issue_kblock<2, 1, false, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 10: issue_kblock<1, 1, true, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+                default: issue_kblock<2, 1, true, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+              }
+            } else {
+              switch (variant) {             // uniform branch; each arm is straight-line code
+                case 6: issue_kblock<1, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 7: issue_kblock<2, 1, true>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 0: issue_kblock<1, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 1: issue_kblock<1, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 2: issue_kblock<1, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 3: issue_kblock<2, 1>(a0, b0, b_lo_off, accs, idesc, first); break;
+                case 4: issue_kblock<2, 2>(a0, b0, b_lo_off, accs, idesc, first); break;
+                default: issue_kblock<2, 3>(a0, b0, b_lo_off, accs, idesc, first); break;
+              }
             }
           }
-          umma_commit(empty_bar + 8u * s);        // frees the smem stage when these MMAs retire
+          if (PAIR) umma_commit_2cta(empty_bar + 8u * s);   // ... in both CTAs
+          else umma_commit(empty_bar + 8u * s);   // frees the smem stage when these MMAs retire
           if (++s == g.stages) {
             s = 0;
             sphase ^= 1u;
           }
         }
-        umma_commit(tfull_bar + 8u * set);        // accumulators of this item complete
+        if (PAIR) umma_commit_2cta(tfull_bar + 8u * set);
+        else umma_commit(tfull_bar + 8u * set);   // accumulators of this item complete
         if (trace && w == 0) dbg[101] = gtime();
         set_phase[set] ^= 1u;
         if (g.acc_sets == 2) set ^= 1;
@@ -517,14 +623,15 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       const int tiles_w = (q.Pb + g.BW - 1) / g.BW, tiles_h = (q.Pa + g.BH - 1) / g.BH;
       const int tiles_n = (g.N + g.BI - 1) / g.BI;
       const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
-      if (mg * g.MT >= m_tiles) continue;
+      if (mg * np * g.MT >= m_tiles) continue;
+      const int mt_base = (mg * np + (int)rank) * g.MT;      // first pixel tile of this CTA in the item
       const int num_kb = q.KHp * q.KWp * cblocks;
       const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
       const int co_base = n_tile * g.BN;
       const int n_chunks = g.BN / CH;
       // chunks of this item, in processing order: (tile t, chunk c); count only valid tiles
       int vt = 0;
-      for (int t = 0; t < g.MT; ++t) vt += (mg * g.MT + t < m_tiles) ? 1 : 0;
+      for (int t = 0; t < g.MT; ++t) vt += (mt_base + t < m_tiles) ? 1 : 0;
       if (g.sk && kb_lo > 0) {
         // ---- stream-K contributor: this CTA holds an inner / tail part of item w; its owner is an earlier CTA --------
         mbar_wait_backoff(tfull_bar + 8u * set, set_phase[set]);
@@ -548,7 +655,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         if (et == 0) atomicAdd(sk_cnt + w, 1u);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8u * set);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar + 8u * set, 0));
+          else mbar_arrive(tempty_bar + 8u * set);
+        }
         set_phase[set] ^= 1u;
         if (g.acc_sets == 2) set ^= 1;
         continue;
@@ -559,7 +669,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       auto chunk_coords = [&](uint32_t ci, int& b0, int& a0, int& n0, int& c0) {
         const int t = (int)ci / n_chunks;
         c0 = ((int)ci - t * n_chunks) * CH;
-        const int mt = mg * g.MT + t;
+        const int mt = mt_base + t;
         const int tw = mt % tiles_w, th = (mt / tiles_w) % tiles_h, tn = mt / (tiles_w * tiles_h);
         b0 = tw * g.BW;
         a0 = th * g.BH;
@@ -606,8 +716,8 @@ __global__ void __launch_bounds__(kT2Threads, 1)
           unsigned seen;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sk_cnt + w) : "memory");
-            if (seen < (unsigned)n_contrib) __nanosleep(64);
-          } while (seen < (unsigned)n_contrib);
+            if (seen < (unsigned)(n_contrib * np)) __nanosleep(64);
+          } while (seen < (unsigned)(n_contrib * np));
         }
         epi_bar(3, epi_threads);
       }
@@ -673,7 +783,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
               for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             }
             for (int k = 1; k <= n_contrib; ++k) {       // stream-K: the later K ranges of this item, in CTA order
-              const float4* src = reinterpret_cast<const float4*>(sk_part + (size_t)(blockIdx.x + k) * sk_slot +
+              const float4* src = reinterpret_cast<const float4*>(sk_part + (size_t)(blockIdx.x + k * np) * sk_slot +
                                                                   ((size_t)t * 128 + m) * g.BN + c0 + h);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -785,7 +895,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         // this warp has read everything it needs from the accumulator set: hand it back to the MMA issuer
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8u * set);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar + 8u * set, 0));
+          else mbar_arrive(tempty_bar + 8u * set);
+        }
         set_phase[set] ^= 1u;
         if (g.acc_sets == 2) set ^= 1;
       }
@@ -794,9 +907,14 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();     // neither CTA leaves (or frees tensor memory) while its peer still works on the pair
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                   : "memory");
   }
 }
 
@@ -823,6 +941,7 @@ struct Tc2Plan {
   int Cpad, CoutPad, Tmax, phases, BN, n_tiles, BW, BH, BI, MT, m_tiles, m_groups, stages, acc_sets, tmem_cols;
   int tma_out, epi_smem, x_slots, chunk, chains, epi_warps;
   int sk, sk_len, sk_grid;
+  int pair;
   long long sk_total;
   size_t x_bytes, b_bytes, total_bytes, smem_bytes, sk_bytes, sk_cnt_bytes;
 };
@@ -866,6 +985,18 @@ int tc2_streamk_mode() {
   return g_streamk_mode;
 }
 void tc2_set_streamk_mode(int v) { g_streamk_mode = v; }
+
+// CTA-pair policy: 0 = off, 1 = where the plan below expects it to pay (default), 2 = wherever eligible.
+// B200LIC_TC_PAIR in the environment or b200lic_set_option("pair", v).
+static int g_pair_mode = -1;
+int tc2_pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("B200LIC_TC_PAIR");
+    g_pair_mode = e ? atoi(e) : 1;
+  }
+  return g_pair_mode;
+}
+void tc2_set_pair_mode(int v) { g_pair_mode = v; }
 
 // written tensor [N,Cout,Ho,Wo]; gathered tensor [N,Cin,H,W]
 static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
@@ -1023,10 +1154,66 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
       }
     }
   }
+  // CTA pair (cta_group::2): two CTAs of a cluster run one M = 256 MMA per step, each staging its own 128-pixel A tile
+  // and HALF of the weight tile.  At N = 192 a single CTA reads 10 KB of operands per 96-cycle MMA on top of the TMA fill
+  // of the stages -- more than the 128 B/clk of one SM's shared memory (profiles/README.md r1d/r2: 63 ns per MMA against
+  // a 49 ns floor with the loads switched off); a pair reads 7 KB per MMA per SM and fills 30 % less.  One pixel tile
+  // per CTA with double-buffered accumulators, stream-K over the pairs for load balance (74 pairs).
+  p.pair = 0;
+  {
+    const int pm = tc2_pair_mode();
+    const int nkb = KH * KW * (p.Cpad / 32);
+    const int clusters = sms / 2;
+    const long long pitems = (long long)p.phases * p.n_tiles * ((p.m_tiles + 1) / 2);
+    const bool eligible = !gdn_mode && p.BN % 32 == 0 && 2 * p.BN <= 512 && p.m_tiles >= 2 && clusters >= 1;
+    // Worth it when the K loop dominates and the pairs do not add a wave.  Time of the busiest SM in units of one pixel
+    // tile's K loop: a single CTA runs it at ~63 ns per MMA (N = 192), a pair at ~52 ns (A/B on one box, profiles/README.md
+    // r2: g_a.2 @[8,192,128,128] 155 -> 125 us, 2K forward 503 -> 537 Mpx/s).
+    const long long tiles = (long long)p.phases * p.n_tiles * p.m_tiles;
+    const long long items_now = (long long)p.phases * p.n_tiles * p.m_groups;
+    double t_single = (double)((items_now + sms - 1) / sms) * p.MT * 63.0;
+    if (p.sk) t_single = ((double)tiles / sms > 1.0 / 3.0 ? (double)tiles / sms : 1.0 / 3.0) * 63.0;
+    const double t_pair = (double)((pitems + clusters - 1) / clusters) * 52.0;
+    const bool pays = p.BN >= 64 && nkb >= 16 && t_pair < 0.97 * t_single;
+    if (pm > 0 && eligible && (pm == 2 || pays)) {
+      p.pair = 1;
+      p.MT = 1;
+      p.chains = 1;
+      p.m_groups = (p.m_tiles + 1) / 2;
+      p.acc_sets = 2;
+      p.tmem_cols = pow2_ceil2(2 * p.BN);
+      if (p.tmem_cols < 32) p.tmem_cols = 32;
+      p.sk = 0;
+      p.sk_len = 0;
+      p.sk_total = 0;
+      p.sk_grid = 0;
+      // Stream-K over the pairs works (B200LIC_TC_PAIR_SK=1; tests run it) but measured slower than whole items: g_a.2
+      // @[8,192,128,128] 144 vs 125 us, sequential sweep 3.42 vs 3.39 ms -- off by default.
+      const int sk_env = tc2_streamk_mode();
+      static int pair_sk = -1;
+      if (pair_sk < 0) {
+        const char* e = getenv("B200LIC_TC_PAIR_SK");
+        pair_sk = e ? atoi(e) : 0;
+      }
+      if (sk_env > 0 && (pair_sk > 0 || sk_env == 2) && !transposed && nkb >= 8) {
+        const long long total = pitems * nkb;
+        const int grid = (int)(total < clusters ? total : clusters);
+        const long long len = (total + grid - 1) / grid;
+        const long long whole = ((pitems + clusters - 1) / clusters) * nkb;
+        if ((sk_env == 2 || (double)whole >= 1.08 * (double)len) && 2 * len >= nkb) {
+          p.sk = 1;
+          p.sk_len = (int)len;
+          p.sk_total = total;
+          p.sk_grid = (int)((total + len - 1) / len);      // clusters
+        }
+      }
+    }
+  }
+  const int np = p.pair ? 2 : 1;
   // conv-type outputs with 16-byte aligned rows leave by TMA store
   p.tma_out = (!transposed && (Wo % 4) == 0) ? 1 : 0;
   p.epi_smem = p.tma_out;
-  const size_t stage = (size_t)p.MT * 2 * kA2Bytes + 2 * (size_t)p.BN * 64;
+  const size_t stage = (size_t)p.MT * 2 * kA2Bytes + 2 * (size_t)(p.BN / np) * 64;
   p.chunk = (p.BN % 32 == 0) ? 32 : 16;
   const size_t ctile = (size_t)p.chunk * 512;
   size_t epi = p.tma_out ? (size_t)(2 + ((gdn_mode && has_norm) ? 2 : 0)) * ctile : 0;
@@ -1068,7 +1255,7 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   }
   p.total_bytes = 2 * p.x_bytes + 2 * p.b_bytes + 1024;
   if (p.sk) {
-    p.sk_bytes = ((size_t)p.sk_grid * p.MT * 128 * p.BN * sizeof(float) + 1023) / 1024 * 1024;
+    p.sk_bytes = ((size_t)p.sk_grid * np * p.MT * 128 * p.BN * sizeof(float) + 1023) / 1024 * 1024;
     p.sk_cnt_bytes = ((size_t)p.phases * p.n_tiles * p.m_groups * sizeof(unsigned) + 1023) / 1024 * 1024;
     p.total_bytes += p.sk_bytes + p.sk_cnt_bytes;
   }
@@ -1184,13 +1371,13 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
     const cuuint64_t Kmax = (cuuint64_t)p.Tmax * p.Cpad;
     cuuint64_t bdims[4] = {Kmax, (cuuint64_t)p.CoutPad, (cuuint64_t)p.phases, 2};
     cuuint64_t bstrides[3] = {Kmax * 2, Kmax * 2 * (cuuint64_t)p.CoutPad, (cuuint64_t)p.b_bytes};
-    cuuint32_t bbox[4] = {32, (cuuint32_t)p.BN, 1, 2};
+    cuuint32_t bbox[4] = {32, (cuuint32_t)(p.BN / (p.pair ? 2 : 1)), 1, 2};   // a CTA of a pair loads half of the tile
     cuuint32_t bestr[4] = {1, 1, 1, 1};
     if (!tc_encode_map_ex(&mbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bh, 4, bdims, bstrides, bbox, bestr))
       return B200LIC_ERR_CUDA;
     mbl = mbh;
     if (w_scale) {                              // hi slab only
-      cuuint32_t bbox1[4] = {32, (cuuint32_t)p.BN, 1, 1};
+      cuuint32_t bbox1[4] = {32, (cuuint32_t)(p.BN / (p.pair ? 2 : 1)), 1, 1};
       if (!tc_encode_map_ex(&mbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bh, 4, bdims, bstrides, bbox1, bestr))
         return B200LIC_ERR_CUDA;
     }
@@ -1224,10 +1411,12 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
             p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, w_scale ? 1 : p.chains, w_scale ? 1 : 0, act, slope, gdn_mode, fixed_point,
-            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode, p.sk, p.sk_len, p.sk_total};
+            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode, p.sk, p.sk_len, p.sk_total, p.pair};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc2_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc2_gather_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc2_gather_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_error("%s: cannot raise dynamic shared memory: %s", name, cudaGetErrorString(e));
       return B200LIC_ERR_CUDA;
@@ -1244,10 +1433,11 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   const long long items = (long long)p.phases * p.n_tiles * p.m_groups;
   const int sms = num_sms();
   int grid = (int)(items < sms ? items : sms);
+  if (p.pair) grid = 2 * (int)(items < sms / 2 ? items : sms / 2);
   float* sk_part = nullptr;
   unsigned* sk_cnt = nullptr;
   if (p.sk) {
-    grid = p.sk_grid;
+    grid = p.sk_grid * (p.pair ? 2 : 1);
     sk_part = reinterpret_cast<float*>(ws + 2 * p.x_bytes + 2 * p.b_bytes);
     sk_cnt = reinterpret_cast<unsigned*>(ws + 2 * p.x_bytes + 2 * p.b_bytes + p.sk_bytes);
     if (cudaMemsetAsync(sk_cnt, 0, (size_t)items * sizeof(unsigned), s) != cudaSuccess) {
@@ -1255,8 +1445,12 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
       return B200LIC_ERR_CUDA;
     }
   }
-  launch_pdl(tc2_gather_gemm_kernel, dim3(grid), dim3(64 + 32 * p.epi_warps), p.smem_bytes, s, mah, mal, mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x,
-                                                                norm_out, y, dbg, sk_part, sk_cnt);
+  if (p.pair)
+    launch_pdl_cluster(tc2_gather_gemm_kernel<true>, dim3(grid), dim3(64 + 32 * p.epi_warps), p.smem_bytes, s, 2, mah, mal,
+                       mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x, norm_out, y, dbg, sk_part, sk_cnt);
+  else
+    launch_pdl(tc2_gather_gemm_kernel<false>, dim3(grid), dim3(64 + 32 * p.epi_warps), p.smem_bytes, s, mah, mal, mbh, mbl,
+               my, mx, mn, g, bias, w_scale, gdn_x, norm_out, y, dbg, sk_part, sk_cnt);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

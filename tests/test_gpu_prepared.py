@@ -397,6 +397,58 @@ def test_stream_k_schedule_matches_whole_item_schedule(ops, dev, shape):
     assert max(between) < 4e-5
 
 
+@pytest.mark.parametrize("shape", [
+    # (N, Cin, H, W, Cout, k, stride, transposed): the g_a.2 class (many pixel tiles), an odd tile count (the last pair has
+    # one tile only), a ragged shape, a transposed conv with ragged phases, a 32-channel tile, few tiles x wide Cout
+    (8, 192, 64, 64, 192, 5, 2, False), (1, 64, 24, 16, 96, 3, 1, False), (2, 96, 30, 44, 160, 3, 1, False),
+    (1, 64, 9, 13, 96, 5, 2, True), (1, 32, 16, 16, 32, 3, 1, False), (8, 480, 16, 16, 640, 3, 1, False),
+    (8, 192, 32, 32, 192, 5, 2, True)])
+def test_cta_pair_form_matches_the_single_cta_form(ops, dev, shape):
+    """The CTA-pair form of the conv engine (clusters of two CTAs, tcgen05 cta_group::2: M = 256 per MMA, each CTA staging
+    its own pixel tile and half of the weight tile) against the single-CTA form: every output element is accumulated from
+    the same products in the same K order, so whole-item schedules agree bit for bit; with stream-K forced on both sides
+    (the K ranges are cut differently) to fp32 rounding.  Three-pass and integer two-pass forms, both against fp64."""
+    from rdo_ptq_b200 import _lib
+    N, Cin, H, W, Cout, k, st, tr = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn((Cin, Cout, k, k) if tr else (Cout, Cin, k, k), generator=g) * 0.05).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    ax = 1 if tr else 0
+    delta, zp = ops.wq_init_minmax(w, ax, 8)
+    n_int = ops.wq_int_weights(w, delta, zp, ax, 256)
+    F = torch.nn.functional
+    if tr:
+        ref = F.conv_transpose2d(x.double(), w.double(), b.double(), st, k // 2, st - 1)
+        ref_int = F.conv_transpose2d(x.double(), (n_int * delta).double(), b.double(), st, k // 2, st - 1)
+    else:
+        ref = F.conv2d(x.double(), w.double(), b.double(), st, k // 2)
+        ref_int = F.conv2d(x.double(), (n_int * delta).double(), b.double(), st, k // 2)
+    outs = {}
+    try:
+        for sk in (0, 2):
+            for pair in (0, 2):
+                assert _lib.lib().b200lic_set_option(b"streamk", sk) == 0
+                assert _lib.lib().b200lic_set_option(b"pair", pair) == 0
+                d = ops.conv_desc(x.shape, w.shape, st, k // 2, tr, st - 1 if tr else 0)
+                y = ops.deconv2d_raw(x, w, b, d) if tr else ops.conv2d_raw(x, w, b, d)
+                y_int = ops.conv_wq(x, n_int, delta.reshape(-1).contiguous(), b, stride=st, padding=k // 2,
+                                    output_padding=st - 1 if tr else 0, transposed=tr)
+                torch.cuda.synchronize()
+                outs[(sk, pair)] = (y, y_int)
+    finally:
+        _lib.lib().b200lic_set_option(b"streamk", 1)
+        _lib.lib().b200lic_set_option(b"pair", 1)
+    for key, (y, y_int) in outs.items():
+        assert ((y.double() - ref).norm() / ref.norm()).item() < 2e-5, key
+        if y_int is not None:
+            assert ((y_int.double() - ref_int).norm() / ref_int.norm()).item() < 2e-5, key
+    assert torch.equal(outs[(0, 0)][0], outs[(0, 2)][0])                   # whole items: same accumulation chains
+    if outs[(0, 0)][1] is not None:
+        assert torch.equal(outs[(0, 0)][1], outs[(0, 2)][1])
+    assert ((outs[(2, 0)][0] - outs[(2, 2)][0]).norm() / outs[(2, 0)][0].norm()).item() < 4e-5
+
+
 @pytest.mark.parametrize("case", [
     # N, Cin, H, W, Cout, transposed, act, integer
     (2, 75, 24, 40, 192, False, 2, False),      # folded 3 -> N analysis conv (K = 75 -> 96)
