@@ -243,6 +243,10 @@ typedef struct {
   int in_square;            /* forward/wgrad: use x*x instead of x (GDN's 1x1 conv on x^2) */
   int gdn_mode;             /* forward: 0 plain; 1 out = gdn_x * rsqrt(acc); 2 out = gdn_x * sqrt(acc) */
   int fixed_point;          /* forward: apply LU Q8.8 round(clamp(v,-128,128)*256)/256 to the output */
+  int k_taps;               /* b200lic_conv_fwd_packed, plain conv: contract only the first k_taps filter taps in raster
+                               order (0 = all).  The caller asserts that the remaining taps of the packed weight are zero --
+                               compressai's MaskedConv2d, mask 'A': 12 of 5x5 (TO quant_model.py:45-48 wraps it as a dense
+                               conv).  Every other entry point ignores the field (same value, dense contraction). */
 } b200lic_conv_desc;
 
 /* Scratch bytes the tensor-core engine needs for `op` on this shape (operand staging: NHWC split-bf16 activations and

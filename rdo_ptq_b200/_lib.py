@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
                 ("Cout", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int),
                 ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
                 ("act", C.c_int), ("act_slope", C.c_float), ("engine", C.c_int),
-                ("in_square", C.c_int), ("gdn_mode", C.c_int), ("fixed_point", C.c_int)]
+                ("in_square", C.c_int), ("gdn_mode", C.c_int), ("fixed_point", C.c_int), ("k_taps", C.c_int)]
 
 
 _P, _I, _F, _LL, _SZ, _ULL, _DBL = (C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_ulonglong,

@@ -253,6 +253,7 @@ struct Tc2Geom {
   int sk;                     // stream-K: every CTA takes one contiguous range of (item, K block) units (see SegIter)
   int sk_len;                 // units per CTA
   long long sk_total;         // items x K blocks per item
+  int k_taps;                 // plain conv: contract the first k_taps taps only (0 = all): masked context convolution
   int pair;                   // CTA pair (cluster of 2, tcgen05 cta_group::2): one work item = MT pixel tiles per CTA, M = 256
                               // per MMA, each CTA stages its own A tiles and HALF of the weight tile
 };
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const int tiles_n = (g.N + g.BI - 1) / g.BI;
         const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
         if (mg * np * g.MT >= m_tiles) continue;
-        const int num_kb = q.KHp * q.KWp * cblocks;
+        const int num_kb = (g.k_taps > 0 ? g.k_taps : q.KHp * q.KWp) * cblocks;
         const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
         int wb[2], hb[2], nb[2];
         for (int t = 0; t < g.MT; ++t) {
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
         const int tiles_n = (g.N + g.BI - 1) / g.BI;
         const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
         if (mg * np * g.MT >= m_tiles) continue;
-        const int num_kb = q.KHp * q.KWp * cblocks;
+        const int num_kb = (g.k_taps > 0 ? g.k_taps : q.KHp * q.KWp) * cblocks;
         if (num_kb == 0) continue;                       // nothing to accumulate: the epilogue writes bias only
         const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
         // the epilogue must have drained this accumulator set (first use of a set passes immediately)
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       const int m_tiles = (q.Pa > 0 && q.Pb > 0) ? tiles_w * tiles_h * tiles_n : 0;
       if (mg * np * g.MT >= m_tiles) continue;
       const int mt_base = (mg * np + (int)rank) * g.MT;      // first pixel tile of this CTA in the item
-      const int num_kb = q.KHp * q.KWp * cblocks;
+      const int num_kb = (g.k_taps > 0 ? g.k_taps : q.KHp * q.KWp) * cblocks;
       const int kb_end = kb_hi < 0 ? num_kb : kb_hi;
       const int co_base = n_tile * g.BN;
       const int n_chunks = g.BN / CH;
@@ -998,6 +999,11 @@ int tc2_pair_mode() {
 }
 void tc2_set_pair_mode(int v) { g_pair_mode = v; }
 
+// b200lic_conv_desc::k_taps of the NEXT tc2_launch_ex call of this thread (the launchers share one long positional
+// signature; the tap limit is consumed and cleared by the launch it applies to).
+static thread_local int g_next_taps = 0;
+void tc2_limit_taps_once(int taps) { g_next_taps = taps; }
+
 // written tensor [N,Cout,Ho,Wo]; gathered tensor [N,Cin,H,W]
 static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
                           int transposed, int gdn_mode, int has_norm) {
@@ -1312,7 +1318,10 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
     return B200LIC_ERR_ARG;
   }
   const int has_norm = (gdn_mode && norm_out) ? 1 : 0;
+  const int k_taps = (g_next_taps > 0 && g_next_taps < KH * KW && !transposed && !gdn_mode) ? g_next_taps : 0;
+  g_next_taps = 0;
   Tc2Plan p = make_plan2(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed, gdn_mode, has_norm);
+  if (p.ok && k_taps) p.sk = 0;      // the stream-K line was laid out for the full K loop; whole items (one tile each)
   if (!p.ok) {
     set_error("%s: shape not eligible for the tcgen05 engine", name);
     return B200LIC_ERR_UNSUPPORTED;
@@ -1411,7 +1420,7 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   }
   Tc2Geom g{N, H, W, p.Cpad, Cout, Ho, Wo, KH, KW, stride, pad, transposed, p.BW, p.BH, p.BI, p.BN, p.n_tiles,
             p.MT, p.m_groups, p.phases, p.stages, p.acc_sets, p.tmem_cols, w_scale ? 1 : p.chains, w_scale ? 1 : 0, act, slope, gdn_mode, fixed_point,
-            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode, p.sk, p.sk_len, p.sk_total, p.pair};
+            p.tma_out, has_norm, p.epi_smem, p.x_slots, p.chunk, p.epi_warps, dbg_mode, p.sk, p.sk_len, p.sk_total, k_taps, p.pair};
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc2_gather_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -19,6 +19,7 @@ size_t smallc_conv_fwd_ws(const b200lic_conv_desc* d);
 size_t smallc_deconv_fwd_ws(const b200lic_conv_desc* d);
 int tc_pack_weights(const float* w, int Cout, int Cin, int KH, int KW, int stride, int pad, int transposed, int CoutPad,
                     int Cpad, int Tmax, int phases, long long s_co, long long s_ci, void* bh, void* bl, cudaStream_t s);
+void tc2_limit_taps_once(int taps);
 int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
                   int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
                   int fixed_point, const float* x, const float* w, const void* packed_w, const float* w_scale,
@@ -398,6 +399,7 @@ int b200lic_conv_fwd_packed(const b200lic_conv_desc* d, int op, const float* x, 
                          (long long)d->KH * d->KW, (long long)d->Cout * d->KH * d->KW, d->act, d->act_slope, 0, 0,
                          d->fixed_point, x, nullptr, packed_w, w_scale, bias, nullptr, nullptr, y, workspace,
                          workspace_bytes, as_stream(stream), "deconv_fwd_packed(tc)");
+  if (d->k_taps > 0 && d->k_taps < d->KH * d->KW && !d->gdn_mode) tc2_limit_taps_once(d->k_taps);
   return tc2_launch_ex(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride, d->pad, 0,
                        (long long)d->Cin * d->KH * d->KW, (long long)d->KH * d->KW, d->act, d->act_slope, d->in_square,
                        d->gdn_mode, d->fixed_point, x, nullptr, packed_w, w_scale, bias, gdn_x, norm_out, y, workspace,

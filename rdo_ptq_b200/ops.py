@@ -505,7 +505,7 @@ def _sq(v, what):
 
 
 def conv_desc(x_shape, w_shape, stride, padding, transposed=False, output_padding=0, act=ACT_NONE, slope=0.01,
-              engine=None, in_square=0, gdn_mode=0, fixed_pt=0):
+              engine=None, in_square=0, gdn_mode=0, fixed_pt=0, k_taps=0):
     N, Cin, H, W = x_shape
     st, pd = _sq(stride, "stride"), _sq(padding, "padding")
     KH, KW = w_shape[2], w_shape[3]
@@ -521,7 +521,7 @@ def conv_desc(x_shape, w_shape, stride, padding, transposed=False, output_paddin
         Cout = w_shape[0]
         Ho, Wo = (H + 2 * pd - KH) // st + 1, (W + 2 * pd - KW) // st + 1
     return ConvDesc(N, Cin, H, W, Cout, Ho, Wo, KH, KW, st, pd, act, slope,
-                    DEFAULT_ENGINE if engine is None else engine, in_square, gdn_mode, fixed_pt)
+                    DEFAULT_ENGINE if engine is None else engine, in_square, gdn_mode, fixed_pt, k_taps)
 
 
 def _act_id(module):

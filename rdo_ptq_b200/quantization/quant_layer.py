@@ -4,6 +4,7 @@ Same constructor, attributes and state machine as the reference (quant_layer.py:
 libb200lic kernels: weight quantiser (K7/K6) -> implicit-GEMM conv / transposed conv / fused GDN (K1/K2/K3) with the
 absorbed activation applied in the conv epilogue -> dynamic activation quantiser (K8).
 """
+import os
 from typing import Union
 
 import torch
@@ -12,6 +13,23 @@ import torch.nn as nn
 from .. import ops
 from ..codec.layers import GDN, f_gdn      # noqa: F401  (f_gdn is re-exported like the reference module)
 from .quantizer import AdaRoundQuantizer, StraightThrough, UniformAffineQuantizer
+
+
+# Masked context convolution (compressai MaskedConv2d; the wrap drops the mask, quant_model.py:45-48): at
+# evaluation the taps behind the mask are contracted only when they hold something.  B200LIC_MASKED_TAPS=0: always dense.
+MASKED_TAPS = os.environ.get("B200LIC_MASKED_TAPS", "1") != "0"
+
+
+def _live_tap_prefix(mask):
+    """Length L of the raster-order prefix of live taps when `mask` [Cout,Cin,KH,KW] is the same 1...10...0 pattern for
+    every channel pair (mask 'A' of a 5x5 kernel: 12; mask 'B': 13), else 0."""
+    if mask is None or mask.dim() != 4:
+        return 0
+    flat = mask.reshape(mask.shape[0] * mask.shape[1], -1)
+    L = int(flat[0].sum().item())
+    pattern = torch.zeros_like(flat[0])
+    pattern[:L] = 1
+    return L if 0 < L < flat.shape[1] and bool((flat == pattern).all()) else 0
 
 
 class QuantModule(nn.Module):
@@ -33,6 +51,7 @@ class QuantModule(nn.Module):
             self.fwd_kwargs = dict(stride=org_module.stride, padding=org_module.padding,
                                    dilation=org_module.dilation, groups=org_module.groups)
             self.fwd_func = ops.conv2d
+            self.mask_live_taps = _live_tap_prefix(getattr(org_module, "mask", None))
         elif isinstance(org_module, GDN):
             self.fwd_kwargs = dict(inverse=org_module.inverse, gamma_reparam=org_module.gamma_reparam,
                                    beta_reparam=org_module.beta_reparam)
@@ -66,6 +85,7 @@ class QuantModule(nn.Module):
         self.ignore_reconstruction = False
         self.se_module = se_module
         self.trained = False
+        self.last_k_taps = 0
         self._repr = org_module.extra_repr()
 
     def extra_repr(self):
@@ -139,6 +159,16 @@ class QuantModule(nn.Module):
                 if fold != 1:
                     scale = scale.repeat_interleave(fold).contiguous()
             val = (packed, scale, self.bias)
+        if val is not None:
+            # masked context convolution: when every tap behind the mask is exactly zero in the weight this operand was
+            # built from (always, unless AdaRound un-masked one: alpha of a masked tap is trainable), the
+            # engine contracts the live prefix only (b200lic_conv_desc::k_taps)
+            k_taps, L = 0, getattr(self, "mask_live_taps", 0)
+            if MASKED_TAPS and L and not self.is_gdn and not self.if_tconv and fold == 1:
+                w_eff = self.weight_quantizer(self.weight).detach() if self.use_weight_quant else self.org_weight
+                if bool((w_eff.reshape(w_eff.shape[0], w_eff.shape[1], -1)[:, :, L:] == 0).all()):
+                    k_taps = L
+            val = val + (k_taps,)
         slots[self.use_weight_quant] = (key, val)
         return val
 
@@ -162,7 +192,9 @@ class QuantModule(nn.Module):
         prep = self._prepared(d)
         if prep is None:
             return None
-        packed, scale, bias = prep
+        packed, scale, bias, k_taps = prep
+        d.k_taps = k_taps
+        self.last_k_taps = k_taps                # what the last prepared forward contracted (0 = all taps; tests)
         x = ops._c(input, "input")
         pend = getattr(input, "_b200_actq", None)
         if self.is_gdn and (pend is None or pend[1] <= 8) and ops.gdn_fused_ok(x.shape[1], x.shape[2] * x.shape[3]):
@@ -195,7 +227,7 @@ class QuantModule(nn.Module):
         prep = self._prepared(d1, fold=d.KH * d.KW)
         if prep is None:
             return None
-        packed, scale, bias = prep
+        packed, scale, bias, _ = prep
         x = ops._c(input, "input")
         pend = getattr(input, "_b200_actq", None)
         if pend is not None:

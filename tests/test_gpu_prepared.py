@@ -449,6 +449,70 @@ def test_cta_pair_form_matches_the_single_cta_form(ops, dev, shape):
     assert ((outs[(2, 0)][0] - outs[(2, 2)][0]).norm() / outs[(2, 0)][0].norm()).item() < 4e-5
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 24, 40, 128, 12), (2, 96, 17, 23, 192, 12), (1, 32, 16, 16, 64, 13)])
+def test_masked_context_conv_contracts_the_live_taps_only(ops, dev, shape):
+    """b200lic_conv_desc::k_taps: the 5x5 context convolution behind compressai's causal mask (mask 'A': the first 12
+    taps in raster order, 'B': 13) on a weight whose masked taps are zero -- the truncated K loop adds exact zeros less,
+    so the output is bit-identical to the dense contraction; on a weight with something behind the mask it equals the
+    convolution with that part removed (the caller's assertion is what makes the two the same)."""
+    N, Cin, H, W, Cout, L = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, 5, 5, generator=g) * 0.05).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    w_masked = w.clone()
+    w_masked.view(Cout, Cin, 25)[:, :, L:] = 0
+    d = ops.conv_desc(x.shape, w.shape, 1, 2)
+    dk = ops.conv_desc(x.shape, w.shape, 1, 2, k_taps=L)
+    dense = ops.conv_fwd_packed(x, ops.pack_weights(w_masked, d, False), d, False, bias=b)
+    live = ops.conv_fwd_packed(x, ops.pack_weights(w_masked, dk, False), dk, False, bias=b)
+    assert torch.equal(dense, live)
+    ref = torch.nn.functional.conv2d(x.double(), w_masked.double(), b.double(), 1, 2)
+    assert ((live.double() - ref).norm() / ref.norm()).item() < 2e-5
+    trunc = ops.conv_fwd_packed(x, ops.pack_weights(w, dk, False), dk, False, bias=b)     # something behind the mask
+    assert torch.equal(trunc, live)
+
+
+def test_quantised_cheng2020_context_model_runs_on_the_live_taps(dev):
+    """The wrapped MaskedConv2d of Cheng2020 (TO quant_model.py:45-48 wraps it as a dense conv): the evaluation forward
+    contracts 12 of its 25 taps when the quantised weight is zero behind the mask, all 25 after a masked tap has been
+    set (AdaRound may un-mask one); outputs equal the dense form bit for bit."""
+    from rdo_ptq_b200 import codec, quantization as Q, synth
+    from rdo_ptq_b200.quantization import quant_layer as QL
+    torch.manual_seed(1005)
+    m = codec.ARCHS["cheng2020-attn"](N=32).eval()
+    synth.init_weights(m, gain=0.6)
+    m.to(dev)
+    x = synth.synthetic_image(64, 128).to(dev)
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    with torch.no_grad():
+        m(x)                                              # bakes the mask into weight.data
+        qnn = Q.QuantModel(m, wq, aq, is_cheng=True).eval()
+        qnn.set_quant_state(True, False)
+        ctx = qnn.model.context_prediction
+        assert isinstance(ctx, Q.QuantModule) and ctx.mask_live_taps == 12
+        qnn(x)                                            # first quantised forward initialises the weight quantisers
+        out = qnn(x)                                      # ... the second runs on prepared operands
+        assert ctx.last_k_taps == 12
+        QL.MASKED_TAPS = False
+        try:
+            for mod in qnn.modules():
+                if isinstance(mod, Q.QuantModule):
+                    mod.invalidate_prepared()
+            dense = qnn(x)
+            assert ctx.last_k_taps == 0
+        finally:
+            QL.MASKED_TAPS = True
+        assert torch.equal(out["x_hat"], dense["x_hat"])
+        assert torch.equal(out["likelihoods"]["y"], dense["likelihoods"]["y"])
+        # a masked tap that holds something (what a trained alpha can do): dense contraction again
+        ctx.weight.data[:, :, 4, 4] = ctx.weight.data[:, :, 0, 0]
+        ctx.invalidate_prepared()
+        qnn(x)
+        assert ctx.last_k_taps == 0
+
+
 @pytest.mark.parametrize("case", [
     # N, Cin, H, W, Cout, transposed, act, integer
     (2, 75, 24, 40, 192, False, 2, False),      # folded 3 -> N analysis conv (K = 75 -> 96)
