@@ -118,9 +118,13 @@ class QuantModule(nn.Module):
         form of a folded-tap transposed conv (ops.folded_deconv_desc): same weight memory, taps folded into the output
         channel axis."""
         q = self.weight_quantizer
-        if self.use_weight_quant and (not isinstance(q, (UniformAffineQuantizer, AdaRoundQuantizer))
-                                      or getattr(q, "_leaf", None) is not None or getattr(q, "soft_targets", False)
-                                      or (hasattr(q, "inited") and not q.inited) or q.delta is None):
+        # a stand-in quantiser that returns a constant weight (the streaming session's nearest-rounded weights,
+        # session._FixedWeight): `fixed_weight` = (dequantised weight, (n_int, scale) or None)
+        fixed = getattr(q, "fixed_weight", None) if self.use_weight_quant else None
+        if self.use_weight_quant and fixed is None and (
+                not isinstance(q, (UniformAffineQuantizer, AdaRoundQuantizer))
+                or getattr(q, "_leaf", None) is not None or getattr(q, "soft_targets", False)
+                or (hasattr(q, "inited") and not q.inited) or q.delta is None):
             return None
         key = self._prep_key()
         slots = self.__dict__.setdefault("_prep", {})          # one operand per quant state: FP and quantised forwards
@@ -141,6 +145,18 @@ class QuantModule(nn.Module):
         elif not self.use_weight_quant:
             w = self.org_weight if fold == 1 else self.org_weight.reshape(self.org_weight.shape[0], -1, 1, 1)
             val = (ops.pack_weights(w, d, self.if_tconv), None, self.org_bias)
+        elif fixed is not None:
+            # same operands as the general path builds per call (ops.conv_wq on the integer weights, or the dequantised
+            # weight when there is no integer form), packed once
+            w, iw = fixed
+            scale = None
+            if iw is not None:
+                w, scale = iw
+                if fold != 1:
+                    scale = scale.repeat_interleave(fold).contiguous()
+            if fold != 1:
+                w = w.reshape(w.shape[0], -1, 1, 1)
+            val = (ops.pack_weights(w, d, self.if_tconv), scale, self.bias)
         else:
             axis = q.axis if hasattr(q, "axis") else q.channel_axis(self.weight)
             alpha = q.alpha.detach() if hasattr(q, "alpha") else None

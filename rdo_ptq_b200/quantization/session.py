@@ -101,6 +101,7 @@ class _FixedWeight(torch.nn.Module):
     def __init__(self, w, iw=None):
         super().__init__()
         self.w, self.iw = w, iw
+        self.fixed_weight = (w, iw)       # QuantModule._prepared packs it once (quant_layer.py)
 
     def forward(self, _x):
         return self.w
@@ -236,7 +237,9 @@ class CalibrationSession:
                 with torch.no_grad():
                     q = m.weight_quantizer
                     iw = None if m.is_gdn else getattr(q, "int_weights", lambda _w: None)(m.weight)
-                    self._fixed_w[m] = (q(m.weight).detach().clone(), iw)
+                    # ONE stand-in object per module for the whole session: QuantModule caches the packed operand of a
+                    # constant weight per quantiser object, so the captured forwards reuse it (no per-step packing)
+                    self._fixed_w[m] = _FixedWeight(q(m.weight).detach().clone(), iw)
         return self._stream_forward()
 
     @torch.no_grad()
@@ -269,9 +272,9 @@ class CalibrationSession:
         qnn.set_quant_state(False, False)
         run(1, 2)
         swapped = []
-        for m, w in self._fixed_w.items():                  # nearest-rounded weights, whatever quantiser is installed
+        for m, fq in self._fixed_w.items():                 # nearest-rounded weights, whatever quantiser is installed
             swapped.append((m, m.weight_quantizer))
-            m.weight_quantizer = _FixedWeight(*w)
+            m.weight_quantizer = fq
         qnn.set_quant_state(True, False)
         with torch.cuda.stream(fork):
             run(0, None)
