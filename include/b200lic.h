@@ -228,6 +228,24 @@ B200LIC_API int b200lic_sq_err_sum(const float* a, const float* b, size_t n, flo
 /* out[0] += sum -log2(lik) */
 B200LIC_API int b200lic_bits_sum(const float* lik, size_t n, float* out, b200lic_stream_t stream);
 
+/* MS-SSIM, the third number the reference's entry points report next to PSNR and bpp.
+ * replaces: pytorch_msssim.ms_ssim(a, b, data_range=1.) at TO losses/losses.py:26,31,49-52, LU quantize.py:13,89,
+ * quant.py:86, single_test.py:59-60, dataset_test.py:60-61 (third-party package, pytorch_msssim==1.0.0).
+ * One level: x, y are [planes, H, W] fp32 (planes = N*C); win11 = the normalised 11-tap Gaussian (sigma 1.5);
+ * sums[2*p] += sum of the ssim map of plane p, sums[2*p+1] += sum of its cs map (VALID region (H-10) x (W-10)); the caller
+ * zeroes `sums`.  c1 = (0.01 L)^2, c2 = (0.03 L)^2. */
+B200LIC_API int b200lic_ssim_level(const float* x, const float* y, const float* win11, int planes, int H, int W, float c1,
+                       float c2, double* sums, b200lic_stream_t stream);
+/* 2x2 mean with stride 2 and zero padding pad_h / pad_w in {0,1} counted in the mean (avg_pool2d(kernel_size=2,
+ * padding=size % 2) between the levels): out is [planes, (H+2*pad_h-2)/2+1, (W+2*pad_w-2)/2+1]. */
+B200LIC_API int b200lic_avg_pool2(const float* x, int planes, int H, int W, int pad_h, int pad_w, float* out,
+                      b200lic_stream_t stream);
+/* per_plane[p] = prod_l relu(v_l[p])^w_l, v_l = cs mean of level l < levels-1, ssim mean of the last level
+ * (sums: [levels][planes][2], inv_count[l] = 1 / pixels of level l's maps), weights (0.0448, 0.2856, 0.3001, 0.2363,
+ * 0.1333); mean[0] = mean over planes. */
+B200LIC_API int b200lic_msssim_combine(const double* sums, const double* inv_count, int levels, int planes, float* per_plane,
+                           float* mean, b200lic_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1/K2/K4/K5  convolutions as implicit GEMM.
  * replaces: F.conv2d TO quant_layer.py:28,123 / LU quant_layer.py:27,128; F.conv_transpose2d

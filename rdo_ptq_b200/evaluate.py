@@ -1,9 +1,9 @@
 """Evaluation entry of the hot path: drop-in for task-oriented-PTQ/test_datasets.py (:21-33 PSNR/bpp, :45-73
-pad/crop, :76-117 Test_kodak) and losses/losses.py (:15-28 RateDistortionLoss, MSE metric), on libb200lic
-reductions (K11).  MS-SSIM is outside the hot path (BASELINE north_star names rate + lambda*MSE).
+pad/crop, :76-117 Test_kodak), losses/losses.py (:15-35 RateDistortionLoss, :38-84 Metrics) and the PSNR / MS-SSIM /
+bpp report of light-uniform-PTQ/quantize.py:58-92, on libb200lic reductions (K11) and the MS-SSIM kernels (msssim.cu).
 
 Images are independent, so `evaluate` shards them round-robin over the ranks of the default process group and
-all-reduces (sum psnr, sum bpp, count): the only collective evaluation needs.
+all-reduces (sum psnr, sum bpp, [sum ms-ssim,] count): the only collective evaluation needs.
 """
 import math
 
@@ -40,6 +40,11 @@ def compute_psnr(a, b, clamp=False):
     """-10 log10(mean((a-b)^2)) (test_datasets.py:21-23); `clamp` folds the reference's `rec.clamp_(0,1)` (:98)."""
     s = squared_error_sums(a, b)
     return -10 * math.log10(float(s[1 if clamp else 0]) / a.numel())
+
+
+def compute_msssim(a, b):
+    """pytorch_msssim.ms_ssim(a, b, data_range=1.).item() (LU quantize.py:55-56, dataset_test.py:60-61)."""
+    return float(ops.ms_ssim(a, b, data_range=1.0))
 
 
 def total_bits(out_net):
@@ -94,11 +99,12 @@ class GraphedForward:
 
 
 @torch.no_grad()
-def evaluate(model, images, p=256, shard=True, graph=True):
+def evaluate(model, images, p=256, shard=True, graph=True, ms_ssim=False):
     """Test_kodak (test_datasets.py:76-117) over a list of [1,3,h,w] CUDA tensors.
-    Returns dict(psnr, bpp, count, per_image=[(psnr, bpp), ...] for this rank's images)."""
+    Returns dict(psnr, bpp, count, per_image=[(psnr, bpp), ...] for this rank's images); with `ms_ssim` (the third
+    number of LU quantize.py:58-92 / TO Metrics) also ms_ssim and per_image_ms_ssim."""
     rank, world = (dist.get_rank(), dist.get_world_size()) if (shard and dist.is_initialized()) else (0, 1)
-    per = []
+    per, per_ms = [], []
     fwd = GraphedForward(model) if graph else None
     for i, x in enumerate(images):
         if i % world != rank:
@@ -109,30 +115,46 @@ def evaluate(model, images, p=256, shard=True, graph=True):
             n_, _, hh, ww = out["x_hat"].shape
             rec = crop(out["x_hat"], (h, w))
             per.append((compute_psnr(rec, x, clamp=True), float(bits) / (n_ * hh * ww)))
-            continue
-        with ops.defer_actq():
-            out = model.forward(pad(x, p))
-        rec = crop(out["x_hat"], (h, w))
-        per.append((compute_psnr(rec, x, clamp=True), compute_bpp(out)))
-    acc = torch.tensor([sum(v[0] for v in per), sum(v[1] for v in per), float(len(per))], dtype=torch.float64,
-                       device=images[0].device)
+        else:
+            with ops.defer_actq():
+                out = model.forward(pad(x, p))
+            rec = crop(out["x_hat"], (h, w))
+            per.append((compute_psnr(rec, x, clamp=True), compute_bpp(out)))
+        if ms_ssim:
+            per_ms.append(compute_msssim(rec.clamp(0, 1), x))      # the reconstruction is clamped first (:98)
+    acc = torch.tensor([sum(v[0] for v in per), sum(v[1] for v in per), float(len(per)), sum(per_ms)],
+                       dtype=torch.float64, device=images[0].device)
     if world > 1:
         dist.all_reduce(acc)
-    psnr_sum, bpp_sum, cnt = acc.tolist()
-    return dict(psnr=psnr_sum / max(cnt, 1), bpp=bpp_sum / max(cnt, 1), count=int(cnt), per_image=per)
+    psnr_sum, bpp_sum, cnt, ms_sum = acc.tolist()
+    res = dict(psnr=psnr_sum / max(cnt, 1), bpp=bpp_sum / max(cnt, 1), count=int(cnt), per_image=per)
+    if ms_ssim:
+        res.update(ms_ssim=ms_sum / max(cnt, 1), per_image_ms_ssim=per_ms)
+    return res
 
 
 class RateDistortionLoss(nn.Module):
-    """losses/losses.py:8-35 with metric='mse': bpp_loss + lmbda * 255^2 * mse (value only: PTQ never back-props it)."""
+    """losses/losses.py:8-35: bpp_loss + lmbda * 255^2 * mse (metric='mse') or bpp_loss + lmbda * (1 - MS-SSIM)
+    (metric='ms-ssim'); values only: PTQ never back-props it.  `ms_ssim_loss` is reported for both metrics like the
+    reference whenever the image is large enough for five levels (sides > 160 px; the reference raises below that)."""
 
     def __init__(self, lmbda=1e-2, metric='mse'):
         super().__init__()
-        if metric != 'mse':
-            raise NotImplementedError("MS-SSIM is outside the hot path")
+        if metric not in ('mse', 'ms-ssim'):
+            raise ValueError(f"metric {metric!r}")
         self.lmbda, self.metric = lmbda, metric
 
     def forward(self, output, target):
         N, _, H, W = target.size()
         bpp = float(total_bits(output)) / (N * H * W)
         mse = float(squared_error_sums(output["x_hat"], target)[0]) / target.numel()
-        return {"bpp_loss": bpp, "mse_loss": mse, "loss": self.lmbda * 255 ** 2 * mse + bpp}
+        out = {"bpp_loss": bpp, "mse_loss": mse}
+        if min(H, W) > 160:
+            out["ms_ssim_loss"] = 1.0 - compute_msssim(output["x_hat"], target)
+        if self.metric == 'mse':
+            out["loss"] = self.lmbda * 255 ** 2 * mse + bpp
+        else:
+            if "ms_ssim_loss" not in out:
+                raise ValueError("metric='ms-ssim' needs image sides > 160 px")
+            out["loss"] = self.lmbda * out["ms_ssim_loss"] + bpp
+        return out

@@ -492,6 +492,47 @@ def bits_sum(lik):
     return out
 
 
+_SSIM_WIN = {}
+
+
+def ms_ssim(x, y, data_range=1.0, size_average=True):
+    """pytorch_msssim.ms_ssim(x, y, data_range) of two [N,C,H,W] tensors (reference call sites: include/b200lic.h,
+    "MS-SSIM"): five levels of b200lic_ssim_level with b200lic_avg_pool2 between them, b200lic_msssim_combine.
+    Returns a device scalar (size_average) or the per-image means [N]."""
+    x, y = _c(x, "x"), _c(y, "y")
+    if x.shape != y.shape or x.dim() != 4:
+        raise ValueError(f"ms_ssim: shapes {tuple(x.shape)} / {tuple(y.shape)}")
+    N, Cc, H, W = x.shape
+    if min(H, W) <= (11 - 1) * 2 ** 4:
+        raise ValueError("ms_ssim: image side must exceed 160 px (four 2x downsamplings, 11-tap window)")
+    dev = x.device
+    win = _SSIM_WIN.get(dev)
+    if win is None:
+        c = torch.arange(11, dtype=torch.float32) - 5
+        g = torch.exp(-(c ** 2) / (2 * 1.5 ** 2))
+        win = _SSIM_WIN[dev] = (g / g.sum()).to(dev)
+    planes, levels = N * Cc, 5
+    sums = torch.zeros(levels, planes, 2, device=dev, dtype=torch.float64)
+    inv = []
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    for lvl in range(levels):
+        call("ssim_level", _p(x), _p(y), _p(win), planes, H, W, c1, c2, _p(sums[lvl]))
+        inv.append(1.0 / ((H - 10) * (W - 10)))
+        if lvl < levels - 1:
+            ph, pw = H % 2, W % 2
+            Ho, Wo = (H + 2 * ph - 2) // 2 + 1, (W + 2 * pw - 2) // 2 + 1
+            xn = torch.empty(N, Cc, Ho, Wo, device=dev, dtype=torch.float32)
+            yn = torch.empty_like(xn)
+            call("avg_pool2", _p(x), planes, H, W, ph, pw, _p(xn))
+            call("avg_pool2", _p(y), planes, H, W, ph, pw, _p(yn))
+            x, y, H, W = xn, yn, Ho, Wo
+    inv_t = torch.tensor(inv, dtype=torch.float64).to(dev)
+    per_plane = torch.empty(planes, device=dev, dtype=torch.float32)
+    mean = torch.empty(1, device=dev, dtype=torch.float32)
+    call("msssim_combine", _p(sums), _p(inv_t), levels, planes, _p(per_plane), _p(mean))
+    return mean[0] if size_average else per_plane.view(N, Cc).mean(1)
+
+
 # ------------------------------------------------------------------------------------------------ convolutions
 def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)

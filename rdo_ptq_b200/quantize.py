@@ -62,17 +62,21 @@ def quantize_int8(args, model=None, images=None, device="cuda"):
         images = synth.synthetic_images(args.n_test, h, w)
     images = [t.to(device) for t in images]
     report = {}
+    # PSNR, MS-SSIM, bpp like validate_model (quantize.py:58-92); MS-SSIM needs sides > 160 px (five levels)
+    ms = all(min(t.shape[-2:]) > 160 for t in images)
+    keys = ('psnr', 'ms_ssim', 'bpp') if ms else ('psnr', 'bpp')
+    fmt = '{}: psnr= {:.2f}; ms-ssim={:.4f}; bpp= {:.3f}' if ms else '{}: psnr= {:.2f}; bpp= {:.3f}'
     if args.test_before_calibration:
-        report['fp32'] = E.evaluate(model, images, p=64, shard=False)
-        logging.info('Full-precision model: psnr= {:.2f}; bpp= {:.3f}'.format(report['fp32']['psnr'], report['fp32']['bpp']))
+        report['fp32'] = E.evaluate(model, images, p=64, shard=False, ms_ssim=ms)
+        logging.info(fmt.format('Full-precision model', *[report['fp32'][k] for k in keys]))
     wq_params = {'n_bits': args.n_bits_w, 'channel_wise': True, 'symmetric': False, 'scale_method': args.init}
     aq_params = {'channel_wise': False, 'symmetric': False, 'scale_method': 'max', 'leaf_param': True}
     qnn = QuantModel(model=model, weight_quant_params=wq_params, act_quant_params=aq_params)
     qnn.to(device).eval()
     qnn = generator(qnn, args, images[0])
     qnn.set_quant_state(weight_quant=True, act_quant=True)
-    report['int8'] = E.evaluate(qnn, images, p=64, shard=False)
-    logging.info('INT8: psnr= {:.2f}; bpp= {:.3f}'.format(report['int8']['psnr'], report['int8']['bpp']))
+    report['int8'] = E.evaluate(qnn, images, p=64, shard=False, ms_ssim=ms)
+    logging.info(fmt.format('INT8', *[report['int8'][k] for k in keys]))
     if args.save:
         torch.save(qnn.state_dict(), args.save)
     return qnn, report

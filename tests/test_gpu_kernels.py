@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import quantizers as oq, codec as ocodec
+from rdo_ptq_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -611,3 +612,60 @@ def test_fused_activation_quant_is_bit_identical_to_the_three_launch_path(ops, d
         assert torch.equal(ops.act_quant(x2, 8), y3)
     finally:
         ops.ACTQ_FUSED = True
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 177, 200), (2, 3, 192, 161), (1, 3, 512, 768), (3, 1, 161, 163)])
+def test_ms_ssim_matches_the_oracle(ops, dev, shape):
+    """b200lic_ssim_level / _avg_pool2 / _msssim_combine against oracle/msssim.py (restatement of pytorch_msssim 1.0.0):
+    the pooled images bit for bit (a 4-term mean), every level's ssim / cs means within 2e-6, MS-SSIM within 1e-5; odd
+    and even sides (both pooling paddings), ragged 32 x 16 tiles, per-image values, identical images -> 1."""
+    from oracle import msssim as om
+    N, Cc, H, W = shape
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.rand(N, Cc, H, W, generator=g)
+    x = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(x, (2, 2, 2, 2), mode="reflect"), 5, 1)   # some structure
+    y = (x + 0.05 * torch.randn(x.shape, generator=g)).clamp(0, 1)
+    xd, yd = x.to(dev), y.to(dev)
+    # one level
+    win = om.gauss_1d().to(dev)
+    sums = torch.zeros(N * Cc, 2, dtype=torch.float64, device=dev)
+    ops.call("ssim_level", xd.data_ptr(), yd.data_ptr(), win.data_ptr(), N * Cc, H, W, 0.01 ** 2, 0.03 ** 2,
+              sums.data_ptr())
+    ss_ref, cs_ref = om.ssim_level(x, y)
+    got = (sums / ((H - 10) * (W - 10))).cpu().view(N, Cc, 2)
+    assert (got[..., 0] - ss_ref.double()).abs().max().item() < 2e-6
+    assert (got[..., 1] - cs_ref.double()).abs().max().item() < 2e-6
+    # pooling
+    ph, pw = H % 2, W % 2
+    ref_p = om.downsample(x)
+    out_p = torch.empty(ref_p.shape, device=dev)
+    ops.call("avg_pool2", xd.data_ptr(), N * Cc, H, W, ph, pw, out_p.data_ptr())
+    assert (out_p.cpu() - ref_p).abs().max().item() < 1e-7
+    # the whole metric
+    v, v_ref = ops.ms_ssim(xd, yd).item(), om.ms_ssim(x, y).item()
+    assert abs(v - v_ref) < 1e-5, (v, v_ref)
+    per, per_ref = ops.ms_ssim(xd, yd, size_average=False).cpu(), om.ms_ssim(x, y, size_average=False)
+    assert (per - per_ref).abs().max().item() < 1e-5
+    assert abs(ops.ms_ssim(xd, xd).item() - 1.0) < 1e-6
+    with pytest.raises(ValueError):
+        ops.ms_ssim(xd[:, :, :160].contiguous(), yd[:, :, :160].contiguous())
+
+
+def test_evaluate_reports_ms_ssim_like_the_lu_entry_point(dev):
+    """evaluate(..., ms_ssim=True) and RateDistortionLoss(metric='ms-ssim') on a quantised Balle2018 model (LU
+    quantize.py:58-92 reports psnr / ms-ssim / bpp): the metric of the product's own reconstruction equals the oracle's
+    MS-SSIM of the same tensors."""
+    from oracle import msssim as om
+    from rdo_ptq_b200 import quantize as QZ, evaluate as E
+    args = QZ.parse_args(["--N", "32", "--M", "48", "--hw", "192x256", "--n_test", "2"])
+    qnn, report = QZ.quantize_int8(args, device=dev)
+    assert set(("psnr", "ms_ssim", "bpp")) <= set(report["int8"]) and 0.0 < report["int8"]["ms_ssim"] <= 1.0
+    assert len(report["int8"]["per_image_ms_ssim"]) == 2
+    x = synth.synthetic_images(1, 192, 256)[0].to(dev)
+    with torch.no_grad():
+        out = qnn(E.pad(x, 64))
+    rec = E.crop(out["x_hat"], (192, 256)).clamp(0, 1)
+    assert abs(E.compute_msssim(rec, x) - om.ms_ssim(rec.cpu(), x.cpu()).item()) < 1e-5
+    rd = E.RateDistortionLoss(lmbda=8.73, metric='ms-ssim')(out, E.pad(x, 64))
+    ref_ms = 1.0 - om.ms_ssim(out["x_hat"].cpu(), E.pad(x, 64).cpu()).item()
+    assert abs(rd["ms_ssim_loss"] - ref_ms) < 1e-5 and abs(rd["loss"] - (8.73 * rd["ms_ssim_loss"] + rd["bpp_loss"])) < 1e-6

@@ -2,6 +2,8 @@
 fixture for these pieces ("parity unpinned")."""
 import math
 
+import pytest
+
 import numpy as np
 import torch
 from scipy import special
@@ -163,3 +165,70 @@ def test_oracle_rate_gradients_match_finite_differences():
         d[idx] = eps
         fd = (bits_at(zh + d) - bits_at(zh - d)) / (2 * eps)
         assert abs(fd.item() - z.grad[idx].item()) < 1e-5 * max(1.0, abs(fd.item()))
+
+
+def _ms_ssim_direct_f64(x, y, data_range=1.0):
+    """Independent evaluation of the published MS-SSIM definition in float64: the full 11x11 window (outer product of
+    the 1-D Gaussian) applied through unfold, explicit 2x2 pooling loops -- no code shared with oracle/msssim.py."""
+    from oracle.msssim import WEIGHTS
+    x, y = x.double(), y.double()
+    c = torch.arange(11, dtype=torch.float64) - 5
+    g = torch.exp(-(c ** 2) / (2 * 1.5 ** 2))
+    g = g / g.sum()
+    w2 = torch.outer(g, g).reshape(1, 121, 1)
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+
+    def filt(t):                                    # [N,C,H,W] -> [N,C,(H-10)*(W-10)]
+        n, ch, h, w = t.shape
+        cols = torch.nn.functional.unfold(t.reshape(n * ch, 1, h, w), 11)       # [n*ch, 121, L]
+        return (cols * w2).sum(1).reshape(n, ch, -1)
+
+    def pool(t):
+        n, ch, h, w = t.shape
+        ph, pw = h % 2, w % 2
+        tp = torch.zeros(n, ch, h + 2 * ph, w + 2 * pw, dtype=t.dtype)
+        tp[:, :, ph:ph + h, pw:pw + w] = t
+        ho, wo = (h + 2 * ph - 2) // 2 + 1, (w + 2 * pw - 2) // 2 + 1
+        tp = tp[:, :, :2 * ho, :2 * wo]
+        return 0.25 * (tp[:, :, 0::2, 0::2] + tp[:, :, 0::2, 1::2] + tp[:, :, 1::2, 0::2] + tp[:, :, 1::2, 1::2])
+
+    vals = []
+    for lvl in range(5):
+        m1, m2 = filt(x), filt(y)
+        s1, s2, s12 = filt(x * x) - m1 * m1, filt(y * y) - m2 * m2, filt(x * y) - m1 * m2
+        cs = (2 * s12 + c2) / (s1 + s2 + c2)
+        ss = (2 * m1 * m2 + c1) / (m1 * m1 + m2 * m2 + c1) * cs
+        if lvl < 4:
+            vals.append(cs.mean(-1).clamp(min=0))
+            x, y = pool(x), pool(y)
+        else:
+            vals.append(ss.mean(-1).clamp(min=0))
+    wts = torch.tensor(WEIGHTS, dtype=torch.float64).view(-1, 1, 1)
+    return torch.prod(torch.stack(vals) ** wts, dim=0).mean().item()
+
+
+def test_ms_ssim_oracle_closed_forms_and_direct_evaluation():
+    """oracle/msssim.py (restatement of pytorch_msssim 1.0.0, dependency absent): identical images give exactly 1, more
+    noise gives less, the value agrees with an independent float64 evaluation of the definition (odd and even sides:
+    both pooling paddings), and the pooling matches avg_pool2d's zero-padded, pad-counted mean."""
+    from oracle import msssim
+    g = torch.Generator().manual_seed(3)
+    x = synth.synthetic_images(1, 177, 200)[0]
+    assert abs(msssim.ms_ssim(x, x).item() - 1.0) < 1e-6
+    prev = 1.0
+    for sigma in (0.01, 0.05, 0.2):
+        y = (x + sigma * torch.randn(x.shape, generator=g)).clamp(0, 1)
+        v = msssim.ms_ssim(x, y).item()
+        assert 0.0 < v < prev
+        assert abs(v - _ms_ssim_direct_f64(x, y)) < 2e-5
+        prev = v
+    x2 = torch.rand(2, 3, 192, 161, generator=g)
+    y2 = (x2 + 0.1 * torch.randn(x2.shape, generator=g)).clamp(0, 1)
+    assert abs(msssim.ms_ssim(x2, y2).item() - _ms_ssim_direct_f64(x2, y2)) < 2e-5
+    per = msssim.ms_ssim(x2, y2, size_average=False)
+    assert per.shape == (2,) and abs(per.mean().item() - msssim.ms_ssim(x2, y2).item()) < 1e-6
+    with pytest.raises(ValueError):
+        msssim.ms_ssim(x2[:, :, :160], y2[:, :, :160])
+    t = torch.arange(15.0).reshape(1, 1, 3, 5)
+    d = msssim.downsample(t)
+    assert d.shape == (1, 1, 2, 3) and d[0, 0, 0, 0].item() == 0.0 and d[0, 0, 1, 1].item() == (6 + 7 + 11 + 12) / 4
