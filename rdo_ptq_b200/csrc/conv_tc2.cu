@@ -1172,15 +1172,11 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
     const int clusters = sms / 2;
     const long long pitems = (long long)p.phases * p.n_tiles * ((p.m_tiles + 1) / 2);
     const bool eligible = !gdn_mode && p.BN % 32 == 0 && 2 * p.BN <= 512 && p.m_tiles >= 2 && clusters >= 1;
-    // Worth it when the K loop dominates and the pairs do not add a wave.  Time of the busiest SM in units of one pixel
-    // tile's K loop: a single CTA runs it at ~63 ns per MMA (N = 192), a pair at ~52 ns (A/B on one box, profiles/README.md
-    // r2: g_a.2 @[8,192,128,128] 155 -> 125 us, 2K forward 503 -> 537 Mpx/s).
-    const long long tiles = (long long)p.phases * p.n_tiles * p.m_tiles;
-    const long long items_now = (long long)p.phases * p.n_tiles * p.m_groups;
-    double t_single = (double)((items_now + sms - 1) / sms) * p.MT * 63.0;
-    if (p.sk) t_single = ((double)tiles / sms > 1.0 / 3.0 ? (double)tiles / sms : 1.0 / 3.0) * 63.0;
-    const double t_pair = (double)((pitems + clusters - 1) / clusters) * 52.0;
-    const bool pays = p.BN >= 64 && nkb >= 16 && t_pair < 0.97 * t_single;
+    // Taken wherever the shape is eligible and has a K loop to speak of: a model of the busiest SM (pairs where 52 ns per
+    // MMA against 63 beats the extra wave of 74 pairs, stream-K kept for the few-tile layers) measured slightly WORSE than
+    // pairs everywhere -- sequential sweep 3.318 vs 3.309 ms, W8A8 forward 307 vs 318 Mpx/s (768x512) and 536 vs 544
+    // (2K), streaming e2e 30.5 k vs 30.9 k imgs/s (profiles/r2_ab_pair_policy_*.json).
+    const bool pays = nkb >= 4;
     if (pm > 0 && eligible && (pm == 2 || pays)) {
       p.pair = 1;
       p.MT = 1;

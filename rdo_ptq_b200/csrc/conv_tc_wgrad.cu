@@ -13,6 +13,7 @@
 // Replaces cuDNN wgrad under autograd of F.conv2d / F.conv_transpose2d (TO layer_opt.py:298-307).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "prepared.cuh"
 
@@ -421,12 +422,20 @@ static WgPlan make_wg_plan(int N, int Cs, int Hs, int Ws, int Cb, int Hb, int Wb
   p.units = (TT + kBoxesA - 1) / kBoxesA;
   p.ktiles = ((Ws + p.BW - 1) / p.BW) * ((Hs + p.BH - 1) / p.BH) * ((N + p.BI - 1) / p.BI);
   const int ctas = p.units * p.n_tiles;
-  // split-K so that the grid fills the SMs: ONE round when that already uses >= 95 % of them (few CTAs per split set,
-  // e.g. GDN's single 192 x 192 tile: every extra split is another 147 KB slab for the reduction to read), else two
-  // rounds without spilling into a third, nearly empty one
+  // split-K so that the grid fills the SMs: ONE round of CTAs when that uses >= 75 % of them, else two rounds without
+  // spilling into a third, nearly empty one.  Every split pays a prologue (tensor-memory allocation, barriers) and an
+  // epilogue (two 128 x 192 accumulators to its slab) and adds a slab for the reduction to read, so one round of longer
+  // K ranges beats two rounds well below a full machine: threshold 0.95 -> 0.75 (19 (tap, block) units x 7 splits = 133
+  // CTAs instead of 285) took the sequential sweep 3.36 -> 3.32 ms and the overlapped one 2.76 -> 2.67 ms (A/B on one box,
+  // profiles/r2_ab_wgrad_rounds_*.json; 0.65 and "always one round" measure the same).
   const int sms_ = num_sms();
   int want = (2 * sms_) / ctas;
-  if (sms_ / ctas >= 1 && (double)((sms_ / ctas) * ctas) >= 0.95 * sms_) want = sms_ / ctas;
+  static double one_round_frac = -1.0;
+  if (one_round_frac < 0.0) {
+    const char* e = getenv("B200LIC_WG_ONE_ROUND");           // experiments: SM fill from which one round is preferred
+    one_round_frac = e ? atof(e) : 0.75;
+  }
+  if (sms_ / ctas >= 1 && (double)((sms_ / ctas) * ctas) >= one_round_frac * sms_) want = sms_ / ctas;
   int max_splits = (p.ktiles + 3) / 4;            // >= 4 pixel tiles per split
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
