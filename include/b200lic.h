@@ -68,6 +68,15 @@ B200LIC_API int b200lic_debug_timeline(unsigned long long* out, int n);
  * MMA, each CTA staging half of the weight tile): 1 = where the plan expects it to pay (default), 0 = off, 2 = wherever
  * eligible.  "gemm1x1": 0 = the generic engine also runs the short-K 1x1 layers. */
 B200LIC_API int b200lic_set_option(const char* name, int value);
+/* Activation statistics from the producer's epilogue (K8 fused into K1/K2, north_star (1): "... and the next layer's
+ * activation quantizer").  b200lic_conv_stats_once(minmax): the NEXT conv / transposed-conv forward this thread launches
+ * on the tcgen05 engine (any of the forward entry points; not gdn_mode, Cout <= 640) also merges the per-channel
+ * (min, max) of its output -- after bias / activation / Q8.8, the values it stores -- into `minmax` (the key layout of
+ * b200lic_actq_stats; initialise it with b200lic_actq_stats_init): the same keys, bit for bit, without the extra pass over
+ * the tensor.  b200lic_conv_stats_pending() returns 1 and disarms when no launch has consumed the request (engine or
+ * shape without the fused statistics: the caller runs b200lic_actq_stats), 0 when the keys are being written. */
+B200LIC_API int b200lic_conv_stats_once(float* minmax);
+B200LIC_API int b200lic_conv_stats_pending(void);
 /* number of kernel launches issued by this library in this process (bench.py `gpu_launches`). */
 B200LIC_API unsigned long long b200lic_launch_count(void);
 /* Calls that asked for B200LIC_ENGINE_AUTO and ran on the exact-fp32 SIMT engine because the tcgen05 engine rejected the

@@ -296,6 +296,17 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   const float Ly = div_rn_ok(L) ? __frcp_rn(L) : 0.f;
+  // All eight 8-byte loads of a thread are issued before the first one is used: with one load in flight per thread the
+  // kernel ran at 55 % of the HBM rate (2048 threads x 8 B = 16 KB in flight per SM against ~35 KB that the latency needs).
+  float2 raw[8];
+  if (vec2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + warp + 8 * j, p = p0 + 2 * lane;
+      raw[j] = (c < C && p < HW) ? __ldg(reinterpret_cast<const float2*>(x + img + (size_t)c * HW + p))
+                                 : make_float2(0.f, 0.f);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int cl = warp + 8 * j, c = c0 + cl, p = p0 + 2 * lane;
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(256)
       const size_t e = img + (size_t)c * HW + p;
       const bool has1 = p + 1 < HW;
       if (vec2) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(x + e));
+        const float2 v = raw[j];
         v0 = fast ? actq_one_fast(v.x, m, r, ry, L, Ly) : actq_one(v.x, m, r, L, nullptr);
         v1 = fast ? actq_one_fast(v.y, m, r, ry, L, Ly) : actq_one(v.y, m, r, L, nullptr);
         if (out) *reinterpret_cast<float2*>(out + e) = make_float2(v0, v1);

@@ -87,6 +87,8 @@ bool pdl_enabled() {
 int tc2_debug_timeline(unsigned long long* out, int n);
 void tc2_set_streamk_mode(int v);
 void tc2_set_pair_mode(int v);
+void tc2_stats_once(unsigned* keys);
+unsigned* tc2_stats_peek();
 void gemm1x1_set_mode(int v);
 }
 extern "C" {
@@ -105,6 +107,15 @@ int b200lic_set_option(const char* name, int value) {
   }
   b200lic::set_error("set_option: unknown option '%s'", name ? name : "(null)");
   return B200LIC_ERR_ARG;
+}
+int b200lic_conv_stats_once(float* minmax) {
+  b200lic::tc2_stats_once(reinterpret_cast<unsigned*>(minmax));
+  return B200LIC_OK;
+}
+int b200lic_conv_stats_pending(void) {
+  const int pending = b200lic::tc2_stats_peek() != nullptr ? 1 : 0;
+  b200lic::tc2_stats_once(nullptr);
+  return pending;
 }
 int b200lic_debug_timeline(unsigned long long* out, int n) { return b200lic::tc2_debug_timeline(out, n); }
 int b200lic_version(void) { return 200; }

@@ -303,6 +303,7 @@ struct SegIter {
 
 constexpr int kT2Threads = 320;        // TMA warp, MMA warp, up to 8 epilogue warps (launched: 64 + 32 * epi_warps)
 constexpr int kA2Bytes = 128 * 64;        // 128 pixel rows x 32 bf16
+constexpr int kStatCh = 640;              // output channels the fused activation statistics cover (shared-memory table)
 
 struct PhaseGeom {
   int ph, pw, KHp, KWp, Pa, Pb, in_step, tap_step, base_h, base_w, out_step;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kT2Threads, 1)
                            const __grid_constant__ CUtensorMap map_n, Tc2Geom g, const float* __restrict__ bias,
                            const float* __restrict__ w_scale, const float* __restrict__ gdn_x,
                            float* __restrict__ norm_out, float* __restrict__ y, unsigned long long* __restrict__ dbg,
-                           float* __restrict__ sk_part, unsigned* __restrict__ sk_cnt) {
+                           float* __restrict__ sk_part, unsigned* __restrict__ sk_cnt, unsigned* __restrict__ stats) {
   pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace v2;
   extern __shared__ uint8_t smem_raw[];
@@ -360,6 +361,10 @@ __global__ void __launch_bounds__(kT2Threads, 1)
   const uint32_t bars = sN + ((g.epi_smem && g.has_norm) ? 2u * ctile : 0u);
   const uint32_t sBias = bars + 512u;                                                // [BN] bias of the current n-tile
   const uint32_t sScale = sBias + 1024u;                                             // [BN] weight scale (w_exact)
+  // [kStatCh] min keys, [kStatCh] max keys of the output channels this CTA has written (stats != nullptr): the dynamic
+  // activation quantiser of the NEXT layer needs per-channel (min, max) of this output (quantizer.py:99-121); taken here
+  // from the values in registers they cost a few warp reductions per chunk instead of another pass over the tensor
+  const uint32_t sStat = sScale + 1024u;
   const uint32_t full_bar = bars, empty_bar = bars + 8u * g.stages;
   const uint32_t tfull_bar = empty_bar + 8u * g.stages;          // [2] accumulator set complete
   const uint32_t tempty_bar = tfull_bar + 16u;                   // [2] accumulator set drained (one arrival per epilogue warp)
@@ -379,6 +384,12 @@ __global__ void __launch_bounds__(kT2Threads, 1)
     }
     for (int s = 0; s < g.x_slots; ++s) mbar_init(xfull_bar + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (stats != nullptr) {
+    for (int i = threadIdx.x; i < kStatCh; i += blockDim.x) {
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(sStat + (uint32_t)i * 4u), "r"(0xffffffffu) : "memory");
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(sStat + (uint32_t)(kStatCh + i) * 4u), "r"(0u) : "memory");
+    }
   }
   if (warp == 1) {
     if (PAIR) {     // one warp of EACH CTA of the pair: the same columns are allocated in both tensor memories
@@ -857,6 +868,27 @@ __global__ void __launch_bounds__(kT2Threads, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = rintf(fminf(fmaxf(r[j], -128.f), 128.f) * 256.f) * (1.f / 256.f);
           }
+          if (stats != nullptr) {
+            // per-channel min / max of what this warp is about to store: ordered-integer keys (f2key), one integer warp
+            // reduction each, lane j keeps channel j's pair and merges it into the CTA's shared table
+            const int lim = g.Cout - (co_base + c0 + h);
+            unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const unsigned k = f2key(r[j]);
+              const unsigned rmin = __reduce_min_sync(0xffffffffu, valid ? k : 0xffffffffu);
+              const unsigned rmax = __reduce_max_sync(0xffffffffu, valid ? k : 0u);
+              if (lane == j) {
+                kmn = rmin;
+                kmx = rmax;
+              }
+            }
+            if (lane < 16 && lane < lim) {
+              const uint32_t ch = (uint32_t)(co_base + c0 + h + lane);
+              asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(sStat + ch * 4u), "r"(kmn) : "memory");
+              asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(sStat + ((uint32_t)kStatCh + ch) * 4u), "r"(kmx) : "memory");
+            }
+          }
           if (trh) dbg[112 + (h >> 4) * 4] = gtime();
           if (g.tma_out) {
             const uint32_t ya = sY + buf * tile_bytes + so0;
@@ -905,6 +937,16 @@ __global__ void __launch_bounds__(kT2Threads, 1)
       }
     }
     if (g.tma_out && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    if (stats != nullptr) {               // this CTA's table -> the global keys (b200lic_actq_stats layout: min, max per channel)
+      epi_bar(3, epi_threads);
+      for (int ch = et; ch < g.Cout && ch < kStatCh; ch += epi_threads) {
+        unsigned a, b;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(sStat + (uint32_t)ch * 4u));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(sStat + (uint32_t)(kStatCh + ch) * 4u));
+        if (a != 0xffffffffu) atomicMin(stats + 2 * ch, a);
+        if (b != 0u) atomicMax(stats + 2 * ch + 1, b);
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -972,8 +1014,8 @@ bool tc2_weight_layout(int Cin, int Cout, int KH, int KW, int stride, int transp
 bool gemm1x1_eligible(int KH, int KW, int stride, int pad, int Cpad, int CoutPad, int n_out_tiles, int gdn_mode,
                       int fixed_point, int w_exact, int H, int W, int Ho, int Wo);
 int gemm1x1_launch(long long M, int HW, int Cpad, int Cout, int CoutPad, void* xh, size_t x_bytes, void* bh, size_t b_bytes,
-                   int w_exact, const float* w_scale, const float* bias, int act, float slope, float* y, cudaStream_t s,
-                   const char* name);
+                   int w_exact, const float* w_scale, const float* bias, int act, float slope, float* y, unsigned* stats,
+                   cudaStream_t s, const char* name);
 
 // Stream-K policy: 1 = where it pays (default), 0 = off, 2 = wherever eligible.  B200LIC_TC_STREAMK in the environment or
 // b200lic_set_option("streamk", v) (tests compare the two schedules in one process).
@@ -1003,6 +1045,12 @@ void tc2_set_pair_mode(int v) { g_pair_mode = v; }
 // signature; the tap limit is consumed and cleared by the launch it applies to).
 static thread_local int g_next_taps = 0;
 void tc2_limit_taps_once(int taps) { g_next_taps = taps; }
+// Same mechanism for the fused activation statistics: the NEXT conv-engine forward of this thread also merges the
+// per-channel (min, max) keys of its output into `keys` (b200lic_actq_stats layout, initialised by the caller).  The
+// launch that honours it clears it; b200lic_conv_stats_pending() tells the caller whether anyone did.
+static thread_local unsigned* g_next_stats = nullptr;
+void tc2_stats_once(unsigned* keys) { g_next_stats = keys; }
+unsigned* tc2_stats_peek() { return g_next_stats; }
 
 // written tensor [N,Cout,Ho,Wo]; gathered tensor [N,Cin,H,W]
 static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride,
@@ -1219,7 +1267,8 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
   p.chunk = (p.BN % 32 == 0) ? 32 : 16;
   const size_t ctile = (size_t)p.chunk * 512;
   size_t epi = p.tma_out ? (size_t)(2 + ((gdn_mode && has_norm) ? 2 : 0)) * ctile : 0;
-  const size_t avail = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 2048 /*bias, weight scale*/;
+  const size_t avail = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/ - 2048 /*bias, weight scale*/ -
+                       2 * kStatCh * 4 /*activation statistics*/;
   p.x_slots = 0;
   if (gdn_mode && p.tma_out) {
     // GDN is bound by the x / y / norm streams, not by its short K loop: two operand stages, and every remaining
@@ -1245,7 +1294,7 @@ static Tc2Plan make_plan2(int N, int Cin, int H, int W, int Cout, int Ho, int Wo
     const char* e_ew = getenv("B200LIC_TC_EPI");             // experiments only
     if (e_ew && (atoi(e_ew) == 4 || atoi(e_ew) == 8)) p.epi_warps = atoi(e_ew);
   }
-  p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 2048;
+  p.smem_bytes = (size_t)p.stages * stage + epi + 1024 + 512 + 2048 + 2 * kStatCh * 4;
   p.x_bytes = ((size_t)N * H * W * p.Cpad * 2 + 1023) / 1024 * 1024;
   p.b_bytes = ((size_t)p.phases * p.CoutPad * p.Tmax * p.Cpad * 2 + 1023) / 1024 * 1024;
   {
@@ -1316,6 +1365,8 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   const int has_norm = (gdn_mode && norm_out) ? 1 : 0;
   const int k_taps = (g_next_taps > 0 && g_next_taps < KH * KW && !transposed && !gdn_mode) ? g_next_taps : 0;
   g_next_taps = 0;
+  unsigned* stats = (!gdn_mode && Cout <= kStatCh) ? g_next_stats : nullptr;     // else left pending: the caller runs the pass
+  if (stats) g_next_stats = nullptr;
   Tc2Plan p = make_plan2(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed, gdn_mode, has_norm);
   if (p.ok && k_taps) p.sk = 0;      // the stream-K line was laid out for the full K loop; whole items (one tile each)
   if (!p.ok) {
@@ -1358,7 +1409,7 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   if (!has_norm && gemm1x1_eligible(KH, KW, stride, pad, p.Cpad, p.CoutPad, p.n_tiles, gdn_mode, fixed_point, w_scale ? 1 : 0,
                                     H, W, Ho, Wo))
     return gemm1x1_launch((long long)N * H * W, H * W, p.Cpad, Cout, p.CoutPad, xh, p.x_bytes, bh, p.b_bytes,
-                          w_scale ? 1 : 0, w_scale, bias, act, slope, y, s, name);
+                          w_scale ? 1 : 0, w_scale, bias, act, slope, y, stats, s, name);
 
   // 2. tensor maps
   CUtensorMap mah, mal, mbh, mbl, my, mx, mn;
@@ -1452,10 +1503,10 @@ int tc2_launch_ex(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH
   }
   if (p.pair)
     launch_pdl_cluster(tc2_gather_gemm_kernel<true>, dim3(grid), dim3(64 + 32 * p.epi_warps), p.smem_bytes, s, 2, mah, mal,
-                       mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x, norm_out, y, dbg, sk_part, sk_cnt);
+                       mbh, mbl, my, mx, mn, g, bias, w_scale, gdn_x, norm_out, y, dbg, sk_part, sk_cnt, stats);
   else
     launch_pdl(tc2_gather_gemm_kernel<false>, dim3(grid), dim3(64 + 32 * p.epi_warps), p.smem_bytes, s, mah, mal, mbh, mbl,
-               my, mx, mn, g, bias, w_scale, gdn_x, norm_out, y, dbg, sk_part, sk_cnt);
+               my, mx, mn, g, bias, w_scale, gdn_x, norm_out, y, dbg, sk_part, sk_cnt, stats);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

@@ -17,6 +17,8 @@
 
 namespace b200lic {
 
+void tc2_stats_once(unsigned* keys);
+unsigned* tc2_stats_peek();
 int tc2_launch(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,
                int transposed, long long s_co, long long s_ci, int act, float slope, int in_square, int gdn_mode,
                int fixed_point, const float* x, const float* w, const float* bias, const float* gdn_x, float* norm_out,
@@ -317,8 +319,12 @@ int smallc_deconv_fwd(const b200lic_conv_desc* d, const float* x, const float* w
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   float* col = reinterpret_cast<float*>(base + inner);
   // W''[(co,r,s), ci] = w[ci, co, r, s]: written-channel stride 1, gathered-channel stride Cout*KH*KW
+  // (the GEMM writes `col`, not the layer output: a pending b200lic_conv_stats_once request stays pending)
+  unsigned* pending_stats = tc2_stats_peek();
+  tc2_stats_once(nullptr);
   int rc = tc2_launch(d->N, d->Cin, d->H, d->W, Cc, d->H, d->W, 1, 1, 1, 0, 0, 1LL, (long long)Cc, B200LIC_ACT_NONE, 0.f, 0,
                       0, 0, x, w, nullptr, nullptr, nullptr, col, base, inner, s, "deconv_fwd(tc, folded taps)");
+  tc2_stats_once(pending_stats);
   if (rc != B200LIC_OK) return rc;
   launch_col2im(col, bias, d->N, d->Cout, d->H, d->W, d->KH, d->KW, d->stride, d->pad, d->Ho, d->Wo, d->act, d->act_slope,
                 d->fixed_point, y, s);

@@ -114,7 +114,8 @@ struct Gemm1x1Geom {
 
 __global__ void __launch_bounds__(kG1Threads, 1)
     gemm1x1_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Gemm1x1Geom g,
-                   const float* __restrict__ bias, const float* __restrict__ w_scale, float* __restrict__ y) {
+                   const float* __restrict__ bias, const float* __restrict__ w_scale, float* __restrict__ y,
+                   unsigned* __restrict__ stats) {
   pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace g1;
   extern __shared__ uint8_t smem_raw[];
@@ -129,7 +130,10 @@ __global__ void __launch_bounds__(kG1Threads, 1)
   const uint32_t par = a_ring + (uint32_t)g.SA * kG1AStage;
   float* s_bias = reinterpret_cast<float*>(smem_gen + (par - smem_base));
   float* s_scale = s_bias + 256;
-  const uint32_t bars = par + 2048u;
+  // [256] min keys, [256] max keys of the output channels (stats != nullptr): per-channel statistics for the next
+  // layer's dynamic activation quantiser, taken from the registers of the epilogue (see conv_tc2.cu)
+  unsigned* s_stat = reinterpret_cast<unsigned*>(s_scale + 256);
+  const uint32_t bars = par + 4096u;
   const uint32_t a_full = bars, a_empty = a_full + 8u * kG1MaxSA, b_full = a_empty + 8u * kG1MaxSA;
   const uint32_t t_full = b_full + 8u, t_empty = t_full + 16u;
   const uint32_t tmem_ptr_addr = t_empty + 16u;
@@ -150,6 +154,8 @@ __global__ void __launch_bounds__(kG1Threads, 1)
   for (int c = threadIdx.x; c < 256; c += kG1Threads) {
     s_bias[c] = (bias && c < g.Cout) ? __ldg(bias + c) : 0.f;
     s_scale[c] = (w_scale && c < g.Cout) ? __ldg(w_scale + c) : 1.f;
+    s_stat[c] = 0xffffffffu;
+    s_stat[256 + c] = 0u;
   }
   if (warp == 1) {
     const uint32_t cols = 2u * (uint32_t)g.acc_cols;
@@ -267,6 +273,23 @@ __global__ void __launch_bounds__(kG1Threads, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
         }
+        if (stats != nullptr) {
+          unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const unsigned k = f2key(r[j]);
+            const unsigned rmin = __reduce_min_sync(0xffffffffu, valid ? k : 0xffffffffu);
+            const unsigned rmax = __reduce_max_sync(0xffffffffu, valid ? k : 0u);
+            if (lane == j) {
+              kmn = rmin;
+              kmx = rmax;
+            }
+          }
+          if (lane < 16 && c0 + lane < g.Cout) {
+            atomicMin(s_stat + c0 + lane, kmn);
+            atomicMax(s_stat + 256 + c0 + lane, kmx);
+          }
+        }
         float* yc = yp + (size_t)c0 * g.HW;
         if (full) {
 #pragma unroll
@@ -285,6 +308,12 @@ __global__ void __launch_bounds__(kG1Threads, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (stats != nullptr) {
+    for (int c = threadIdx.x; c < g.Cout; c += kG1Threads) {
+      if (s_stat[c] != 0xffffffffu) atomicMin(stats + 2 * c, s_stat[c]);
+      if (s_stat[256 + c] != 0u) atomicMax(stats + 2 * c + 1, s_stat[256 + c]);
+    }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t cols = 2u * (uint32_t)g.acc_cols;
@@ -305,7 +334,7 @@ static bool gemm1x1_enabled() {
 }
 
 static size_t gemm1x1_smem(int nkb, int BN, int w_exact, int SA) {
-  return 1024 + (size_t)nkb * (w_exact ? 1 : 2) * BN * 64 + (size_t)SA * kG1AStage + 2048 + 512;
+  return 1024 + (size_t)nkb * (w_exact ? 1 : 2) * BN * 64 + (size_t)SA * kG1AStage + 4096 + 512;
 }
 
 // Eligibility of a planned tc2 launch: 1x1, stride 1, no padding, plain epilogue, the whole weight operand and at least
@@ -321,8 +350,8 @@ bool gemm1x1_eligible(int KH, int KW, int stride, int pad, int Cpad, int CoutPad
 // xh / xl: staged activation operand [M][Cpad] bf16 (lo slab x_bytes behind the hi slab); bh: packed weights
 // [CoutPad][Cpad] hi, lo slab b_bytes behind it.
 int gemm1x1_launch(long long M, int HW, int Cpad, int Cout, int CoutPad, void* xh, size_t x_bytes, void* bh, size_t b_bytes,
-                   int w_exact, const float* w_scale, const float* bias, int act, float slope, float* y, cudaStream_t s,
-                   const char* name) {
+                   int w_exact, const float* w_scale, const float* bias, int act, float slope, float* y, unsigned* stats,
+                   cudaStream_t s, const char* name) {
   Gemm1x1Geom g{};
   g.M = M;
   g.HW = HW;
@@ -369,7 +398,7 @@ int gemm1x1_launch(long long M, int HW, int Cpad, int Cout, int CoutPad, void* x
   }
   const int sms = num_sms();
   const int grid = g.n_tiles < sms ? g.n_tiles : sms;
-  launch_pdl(gemm1x1_kernel, dim3(grid), dim3(kG1Threads), smem, s, ma, mb, g, bias, w_scale, y);
+  launch_pdl(gemm1x1_kernel, dim3(grid), dim3(kG1Threads), smem, s, ma, mb, g, bias, w_scale, y, stats);
   B200_LAUNCH_CHECK(name);
   return B200LIC_OK;
 }

@@ -179,6 +179,23 @@ def act_quant_stats(x):
     return keys
 
 
+# Statistics from the producer's epilogue (b200lic_conv_stats_once): FUSE_ACTQ_STATS=False runs the separate pass (A/B).
+FUSE_ACTQ_STATS = os.environ.get("B200LIC_FUSE_ACTQ_STATS", "1") != "0"
+
+
+def conv_stats_arm(channels, device):
+    """Fresh (min, max) keys for `channels` output channels and a request that the next conv-engine forward fills them."""
+    keys = torch.empty(2 * channels, device=device, dtype=torch.int32)
+    call("actq_stats_init", _p(keys), channels)
+    _lib.lib().b200lic_conv_stats_once(_p(keys))
+    return keys
+
+
+def conv_stats_taken():
+    """True when a launch consumed the request of `conv_stats_arm` (its keys are valid once that launch completes)."""
+    return _lib.lib().b200lic_conv_stats_pending() == 0
+
+
 def act_quant_apply(x, keys, n_bits=8):
     """The second half of `act_quant`."""
     x = _c(x.detach(), "activation")

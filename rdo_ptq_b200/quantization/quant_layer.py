@@ -100,6 +100,7 @@ class QuantModule(nn.Module):
         state = self.__dict__.copy()
         state.pop("_prep", None)                 # device scratch, not part of the pickled QuantModel (main2.py:288)
         state.pop("_defer_to", None)             # wiring hint of QuantModel (re-derived by link_sequential_consumers)
+        state.pop("_stat_keys", None)
         return state
 
     def _prep_key(self):
@@ -188,7 +189,29 @@ class QuantModule(nn.Module):
         slots[self.use_weight_quant] = (key, val)
         return val
 
-    def _forward_prepared(self, input, act, slope):
+    def _stats_wanted(self):
+        """The conditions of the deferred activation quantiser that are known BEFORE the layer runs: when they hold, the
+        convolution's epilogue takes the per-channel statistics of its own output (ops.conv_stats_arm)."""
+        nxt = self.__dict__.get("_defer_to")
+        return (ops.FUSE_ACTQ_STATS and ops.DEFER_ACTQ and not self.is_gdn and not self.is_ps
+                and not self.disable_act_quant and self.use_act_quant and self.trained and nxt is not None
+                and not torch.is_grad_enabled() and not nxt._forward_hooks and not nxt._forward_pre_hooks
+                and not self._forward_hooks)
+
+    def _arm_stats(self, fuse, d=None, input=None):
+        """Right before the launch of this module's convolution (nothing else may run on the engine in between).  Only
+        for outputs the deferred quantiser will actually take (ops.DEFER_ACTQ_MIN_BYTES): smaller ones go through the
+        one-launch cluster quantiser, which takes its own statistics."""
+        if not fuse:
+            return
+        if d is None:
+            kw = self.fwd_kwargs
+            d = ops.conv_desc(input.shape, self.weight.shape, kw["stride"], kw["padding"], self.if_tconv,
+                              kw.get("output_padding", 0))
+        if 4 * d.N * d.Cout * d.Ho * d.Wo >= ops.DEFER_ACTQ_MIN_BYTES:
+            self._stat_keys = ops.conv_stats_arm(d.Cout, self.weight.device)
+
+    def _forward_prepared(self, input, act, slope, fuse=False):
         if self.is_gdn:
             d = ops.gdn_desc(input.shape, self.fwd_kwargs["inverse"])
         else:
@@ -228,10 +251,12 @@ class QuantModule(nn.Module):
                 if self.is_gdn:
                     out = ops.conv_fwd_packed(None, packed, d, False, bias=bias, gdn_x=xq, ws=ws)
                     return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
+                self._arm_stats(fuse, d)
                 return ops.conv_fwd_packed(None, packed, d, self.if_tconv, bias=bias, w_scale=scale, ws=ws)
         if self.is_gdn:
             out = ops.conv_fwd_packed(x, packed, d, False, bias=bias, gdn_x=x, ws=ws)
             return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
+        self._arm_stats(fuse, d)
         return ops.conv_fwd_packed(x, packed, d, self.if_tconv, bias=bias, w_scale=scale, ws=ws)
 
     def _forward_folded_deconv(self, input, d, d1, act, slope):
@@ -263,17 +288,25 @@ class QuantModule(nn.Module):
         if self.is_ps:
             return ops.pixel_shuffle(input, self.fwd_kwargs, act, slope)
         out = None
+        fuse = self._stats_wanted()
+        self._stat_keys = None
         if not torch.is_grad_enabled():
-            out = self._forward_prepared(input, act, slope)
+            out = self._forward_prepared(input, act, slope, fuse)
         if out is None:
             input = ops.resolve_actq(input)      # general path: a deferred activation quantisation is materialised
+            # (transposed convs may run as a folded GEMM + col2im there: its GEMM output is not the layer output)
+            fuse = fuse and not self.if_tconv
         if out is None and self.use_weight_quant and not self.is_gdn and not torch.is_grad_enabled():
             # hard-quantised weight, no gradient wanted (evaluation): integer weights + per-channel scale in the conv
             # epilogue, two tensor-core passes instead of three (b200lic_conv_fwd_wq); same value up to fp32 rounding
             iw = getattr(self.weight_quantizer, "int_weights", lambda _w: None)(self.weight)
             if iw is not None:
+                self._arm_stats(fuse, input=input)
                 out = ops.conv_wq(input, iw[0], iw[1], self.bias, transposed=self.if_tconv, act=act, slope=slope,
                                   **self.fwd_kwargs)
+                if out is None and self._stat_keys is not None:
+                    ops.conv_stats_taken()       # no launch happened: disarm
+                    self._stat_keys = None
         if out is not None:
             weight = bias = None
         elif self.use_weight_quant:
@@ -287,7 +320,13 @@ class QuantModule(nn.Module):
             if act != ops.ACT_NONE:
                 out = ops.add_act_fn(out, None, act, slope)
         else:
+            if self._stat_keys is None:
+                self._arm_stats(fuse, input=input)
             out = self.fwd_func(input, weight, bias, act=act, slope=slope, **self.fwd_kwargs)
+        keys = None
+        if self._stat_keys is not None:          # armed: did a tensor-core launch take the statistics?
+            keys = self._stat_keys if ops.conv_stats_taken() else None
+            self._stat_keys = None
         if self.se_module is not None:
             raise NotImplementedError("se_module is never set on the LIC hot path")
         if self.disable_act_quant:
@@ -300,7 +339,7 @@ class QuantModule(nn.Module):
                 # quantiser while staging its operand (ops.DEFER_ACTQ); the statistics are taken here
                 bits = self.act_quantizer.n_bits if self.act_quantizer.act_bits_follow_n_bits else 8
                 out = out.detach()
-                out._b200_actq = (ops.act_quant_stats(out), bits)
+                out._b200_actq = (keys if keys is not None else ops.act_quant_stats(out), bits)
                 return out
             out = self.act_quantizer(out, True)
         return out

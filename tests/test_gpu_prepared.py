@@ -449,6 +449,53 @@ def test_cta_pair_form_matches_the_single_cta_form(ops, dev, shape):
     assert ((outs[(2, 0)][0] - outs[(2, 2)][0]).norm() / outs[(2, 0)][0].norm()).item() < 4e-5
 
 
+@pytest.mark.parametrize("case", [
+    # N, Cin, H, W, Cout, k, stride, transposed, act: generic engine (pairs / single CTA), ragged tiles, padded channel
+    # count, transposed conv (strided phase stores), 1x1 short-K engine, folded 3 -> N conv, stream-K owner
+    (2, 96, 30, 44, 160, 3, 1, False, 2), (1, 64, 24, 16, 40, 3, 1, False, 0), (1, 64, 9, 13, 96, 5, 2, True, 1),
+    (2, 192, 16, 16, 192, 1, 1, False, 2), (1, 3, 64, 96, 128, 5, 2, False, 0), (8, 192, 32, 32, 192, 5, 2, False, 0)])
+@pytest.mark.parametrize("pair", [0, 2])
+def test_activation_statistics_from_the_conv_epilogue(ops, dev, case, pair):
+    """b200lic_conv_stats_once: the per-channel (min, max) keys the convolution's epilogue merges from its registers equal
+    the keys of b200lic_actq_stats over the stored output, bit for bit (min / max are exact), on every path that honours
+    the request; an engine that does not (SIMT) leaves it pending."""
+    from rdo_ptq_b200 import _lib
+    N, Cin, H, W, Cout, k, st, tr, act = case
+    g = torch.Generator().manual_seed(21 + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn((Cin, Cout, k, k) if tr else (Cout, Cin, k, k), generator=g) * 0.05).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    ax = 1 if tr else 0
+    delta, zp = ops.wq_init_minmax(w, ax, 8)
+    n_int = ops.wq_int_weights(w, delta, zp, ax, 256)
+    try:
+        assert _lib.lib().b200lic_set_option(b"pair", pair) == 0
+        for sk in (1, 2):
+            assert _lib.lib().b200lic_set_option(b"streamk", sk) == 0
+            d = ops.conv_desc(x.shape, w.shape, st, k // 2, tr, st - 1 if tr else 0, act=act, slope=0.01)
+            keys = ops.conv_stats_arm(Cout, dev)
+            y = ops.deconv2d_raw(x, w, b, d) if tr else ops.conv2d_raw(x, w, b, d)
+            folded_deconv = tr and not ops.conv_stats_taken() if tr else False
+            if not tr:
+                assert ops.conv_stats_taken()
+            if not folded_deconv:
+                assert torch.equal(keys, ops.act_quant_stats(y)), (sk, "three-pass")
+            keys = ops.conv_stats_arm(Cout, dev)
+            y_int = ops.conv_wq(x, n_int, delta.reshape(-1).contiguous(), b, stride=st, padding=k // 2,
+                                output_padding=st - 1 if tr else 0, transposed=tr, act=act, slope=0.01)
+            taken = ops.conv_stats_taken()
+            if y_int is not None and taken:
+                assert torch.equal(keys, ops.act_quant_stats(y_int)), (sk, "integer")
+        d = ops.conv_desc(x.shape, w.shape, st, k // 2, tr, st - 1 if tr else 0, engine=ops.ENGINE_SIMT)
+        keys = ops.conv_stats_arm(Cout, dev)
+        (ops.deconv2d_raw if tr else ops.conv2d_raw)(x, w, b, d)
+        assert not ops.conv_stats_taken()                      # the exact-fp32 engine has no fused statistics
+        assert _lib.lib().b200lic_conv_stats_pending() == 0    # ... and the request is disarmed
+    finally:
+        _lib.lib().b200lic_set_option(b"streamk", 1)
+        _lib.lib().b200lic_set_option(b"pair", 1)
+
+
 @pytest.mark.parametrize("shape", [(1, 64, 24, 40, 128, 12), (2, 96, 17, 23, 192, 12), (1, 32, 16, 16, 64, 13)])
 def test_masked_context_conv_contracts_the_live_taps_only(ops, dev, shape):
     """b200lic_conv_desc::k_taps: the 5x5 context convolution behind compressai's causal mask (mask 'A': the first 12
