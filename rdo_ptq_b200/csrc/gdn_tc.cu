@@ -38,6 +38,9 @@ bool tc_encode_map_ex(CUtensorMap* m, CUtensorMapDataType dt, CUtensorMapSwizzle
 bool tc2_weight_layout(int Cin, int Cout, int KH, int KW, int stride, int transposed, int* Cpad, int* CoutPad, int* Tmax,
                        int* phases, size_t* b_bytes);
 
+void tc2_stats_once(unsigned* keys);
+unsigned* tc2_stats_peek();
+
 namespace gd {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -199,7 +202,7 @@ struct GdnGeom {
 __global__ void __launch_bounds__(kGdThreads, 1)
     gdn_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, GdnGeom g,
                      const float* __restrict__ x, const unsigned* __restrict__ keys, const float* __restrict__ beta,
-                     float* __restrict__ y) {
+                     float* __restrict__ y, unsigned* __restrict__ stats) {
   pdl_wait();                 // programmatic dependent launch (common.cuh): predecessor complete, memory visible
   using namespace gd;
   extern __shared__ uint8_t smem_raw[];
@@ -217,7 +220,10 @@ __global__ void __launch_bounds__(kGdThreads, 1)
   float4* s_par = reinterpret_cast<float4*>(smem_gen + (par - smem_base));    // per channel: beta, min, range, RN(1/range)
   float* s_lut = reinterpret_cast<float*>(s_par + 256);                        // code / L
   const uint32_t par_a = par, lut_a = par + 4096u;                             // the same, as shared-window addresses
-  const uint32_t bars = par + 5u * 256u * 4u;
+  // [256] min keys, [256] max keys of the OUTPUT channels (stats != nullptr): statistics for the dynamic quantiser of the
+  // layer after this one, taken from the epilogue's registers (b200lic_conv_stats_once, see conv_tc2.cu)
+  unsigned* s_stat = reinterpret_cast<unsigned*>(s_lut + 256);
+  const uint32_t bars = par + 7u * 256u * 4u;
   const uint32_t x_full = bars, x_empty = x_full + 8u * kGdMaxSX;
   const uint32_t a_full = x_empty + 8u * kGdMaxSX, ab_empty = a_full + 8u * kGdMaxSA, b_full = ab_empty + 8u * kGdMaxSA;
   const uint32_t t_full = b_full + 8u * kGdMaxSA, t_empty = t_full + 16u;
@@ -253,6 +259,8 @@ __global__ void __launch_bounds__(kGdThreads, 1)
     }
     s_par[c] = make_float4(in ? __ldg(beta + c) : 1.f, m, r, div_rn_ok(r) ? __frcp_rn(r) : 0.f);
     s_lut[c] = (float)c <= L ? __fdiv_rn((float)c, L) : 0.f;
+    s_stat[c] = 0xffffffffu;
+    s_stat[256 + c] = 0u;
   }
   if (warp == 1) {
     const uint32_t cols = 2u * (uint32_t)g.acc_cols;
@@ -488,6 +496,23 @@ __global__ void __launch_bounds__(kGdThreads, 1)
 #pragma unroll
           for (int j = 0; j < 16; ++j) xv[j] *= rsqrt_fast(nrm[j]);
         }
+        if (stats != nullptr) {
+          unsigned kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const unsigned k = f2key(xv[j]);
+            const unsigned rmin = __reduce_min_sync(0xffffffffu, valid ? k : 0xffffffffu);
+            const unsigned rmax = __reduce_max_sync(0xffffffffu, valid ? k : 0u);
+            if (lane == j) {
+              kmn = rmin;
+              kmx = rmax;
+            }
+          }
+          if (lane < 16 && c0 + lane < g.C) {
+            atomicMin(s_stat + c0 + lane, kmn);
+            atomicMax(s_stat + 256 + c0 + lane, kmx);
+          }
+        }
         float* yp = y + base + (size_t)c0 * g.HW;
         if (full) {
 #pragma unroll
@@ -507,6 +532,12 @@ __global__ void __launch_bounds__(kGdThreads, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (stats != nullptr) {
+    for (int c = threadIdx.x; c < g.C; c += kGdThreads) {
+      if (s_stat[c] != 0xffffffffu) atomicMin(stats + 2 * c, s_stat[c]);
+      if (s_stat[256 + c] != 0u) atomicMax(stats + 2 * c + 1, s_stat[256 + c]);
+    }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t cols = 2u * (uint32_t)g.acc_cols;
@@ -587,7 +618,7 @@ int b200lic_gdn_fwd_fused(const float* x, const float* minmax, int n_bits, const
   // two A/B stages are enough (a K block's six MMAs are much shorter than its conversion); the rest of the shared
   // memory goes to the X ring, which hides the HBM latency
   g.SA = 2;
-  fixed = 1024 + (size_t)g.SA * (kGdAStage + b_stage) + q_bytes + 5 * 256 * 4 + 512;
+  fixed = 1024 + (size_t)g.SA * (kGdAStage + b_stage) + q_bytes + 7 * 256 * 4 + 512;
   int sx = fixed < 227 * 1024 ? (int)((227 * 1024 - fixed) / kGdXStage) : 0;
   g.SX = sx > kGdMaxSX ? kGdMaxSX : sx;
   if (g.SX < 3) {
@@ -627,8 +658,10 @@ int b200lic_gdn_fwd_fused(const float* x, const float* minmax, int n_bits, const
   }
   const int sms = num_sms();
   const int grid = g.n_tiles < sms ? g.n_tiles : sms;
+  unsigned* stats = tc2_stats_peek();            // a pending b200lic_conv_stats_once request: this launch honours it
+  if (stats) tc2_stats_once(nullptr);
   launch_pdl(gdn_fused_kernel, dim3(grid), dim3(kGdThreads), smem, as_stream(stream), mx, mb, g, x, reinterpret_cast<const unsigned*>(minmax),
-                                                                  beta, y);
+                                                                  beta, y, stats);
   B200_LAUNCH_CHECK("gdn_fused_kernel");
   return B200LIC_OK;
 }

@@ -193,7 +193,7 @@ class QuantModule(nn.Module):
         """The conditions of the deferred activation quantiser that are known BEFORE the layer runs: when they hold, the
         convolution's epilogue takes the per-channel statistics of its own output (ops.conv_stats_arm)."""
         nxt = self.__dict__.get("_defer_to")
-        return (ops.FUSE_ACTQ_STATS and ops.DEFER_ACTQ and not self.is_gdn and not self.is_ps
+        return (ops.FUSE_ACTQ_STATS and ops.DEFER_ACTQ and not self.is_ps
                 and not self.disable_act_quant and self.use_act_quant and self.trained and nxt is not None
                 and not torch.is_grad_enabled() and not nxt._forward_hooks and not nxt._forward_pre_hooks
                 and not self._forward_hooks)
@@ -238,6 +238,7 @@ class QuantModule(nn.Module):
         pend = getattr(input, "_b200_actq", None)
         if self.is_gdn and (pend is None or pend[1] <= 8) and ops.gdn_fused_ok(x.shape[1], x.shape[2] * x.shape[3]):
             # one kernel over the raw tensor: quantiser (if deferred to us), square, GEMM and epilogue on chip
+            self._arm_stats(fuse and act == ops.ACT_NONE, d)
             out = ops.gdn_fwd_fused(x, packed, bias, self.fwd_kwargs["inverse"], pending=pend)
             return ops.add_act(out, None, act, slope) if act != ops.ACT_NONE else out
         if pend is not None:
@@ -295,7 +296,7 @@ class QuantModule(nn.Module):
         if out is None:
             input = ops.resolve_actq(input)      # general path: a deferred activation quantisation is materialised
             # (transposed convs may run as a folded GEMM + col2im there: its GEMM output is not the layer output)
-            fuse = fuse and not self.if_tconv
+            fuse = fuse and not self.if_tconv and not self.is_gdn
         if out is None and self.use_weight_quant and not self.is_gdn and not torch.is_grad_enabled():
             # hard-quantised weight, no gradient wanted (evaluation): integer weights + per-channel scale in the conv
             # epilogue, two tensor-core passes instead of three (b200lic_conv_fwd_wq); same value up to fp32 rounding

@@ -254,7 +254,11 @@ class CalibrationSession:
                 clone = isinstance(m, BaseQuantBlock)
 
                 def hook(_m, inp, out, n=n, clone=clone):
-                    store[n][slot_in] = inp[0].detach().clone() if clone else inp[0].detach()
+                    # the first unit's input IS the image buffer, which the copy stream refills for the next step as soon
+                    # as this forward has run (self._img_used) -- possibly while that unit's iteration still reads it:
+                    # the unit gets its own copy (6 MB device-to-device at the benchmark's size)
+                    own = clone or inp[0].data_ptr() == self._img.data_ptr()
+                    store[n][slot_in] = inp[0].detach().clone() if own else inp[0].detach()
                     if slot_out is not None:
                         store[n][slot_out] = out.detach().clone() if clone else out.detach()
                 hooks.append(m.register_forward_hook(hook))

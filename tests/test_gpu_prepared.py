@@ -496,6 +496,26 @@ def test_activation_statistics_from_the_conv_epilogue(ops, dev, case, pair):
         _lib.lib().b200lic_set_option(b"pair", 1)
 
 
+@pytest.mark.parametrize("shape", [(1, 192, 64, 96), (3, 80, 30, 22), (2, 256, 40, 36)])
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("deferred", [False, True])
+def test_activation_statistics_from_the_gdn_epilogue(ops, dev, shape, inverse, deferred):
+    """The one-kernel GDN honours b200lic_conv_stats_once too: keys of its output == b200lic_actq_stats(y), bit for bit
+    (ragged pixel tails, padded channel counts, with and without the deferred input quantiser)."""
+    N, Cc, H, W = shape
+    g = torch.Generator().manual_seed(5 + Cc)
+    x = (torch.randn(N, Cc, H, W, generator=g) * 2).to(dev)
+    gam = (torch.rand(Cc, Cc, generator=g) * 0.02 + 0.1 * torch.eye(Cc)).to(dev)
+    bet = (1 + torch.rand(Cc, generator=g)).to(dev)
+    d = ops.gdn_desc(x.shape, inverse)
+    packed = ops.pack_weights(gam.view(Cc, Cc, 1, 1), d, False)
+    pend = (ops.act_quant_stats(x), 8) if deferred else None
+    keys = ops.conv_stats_arm(Cc, dev)
+    y = ops.gdn_fwd_fused(x, packed, bet, inverse, pending=pend)
+    assert ops.conv_stats_taken()
+    assert torch.equal(keys, ops.act_quant_stats(y))
+
+
 @pytest.mark.parametrize("shape", [(1, 64, 24, 40, 128, 12), (2, 96, 17, 23, 192, 12), (1, 32, 16, 16, 64, 13)])
 def test_masked_context_conv_contracts_the_live_taps_only(ops, dev, shape):
     """b200lic_conv_desc::k_taps: the 5x5 context convolution behind compressai's causal mask (mask 'A': the first 12
