@@ -228,8 +228,9 @@ def run_cuda(args):
     w_soft = ops.adaround_fwd(u.weight.data, wq_.alpha.data, wq_.delta, wq_.zero_point, wq_.axis, wq_.n_levels, True)
     op_ms = graph_time_ms(lambda: ops.conv2d_raw(q_in, w_soft, u.bias.data, d), flush)
     alg_bytes = 2.0 * 2 * q_in.numel() + 2.0 * 2 * u.weight.numel() + 4.0 * y_buf.numel()
-    roof = {"bound": "tensor", "kernel": "tc2_gather_gemm_kernel: conv_fwd g_a.2 192->192 5x5 s2 @[8,192,128,128] on "
-                                         "prepared operands (the forward GEMM of the fused AdaRound iteration)",
+    roof = {"bound": "tensor", "kernel": "tc2_gather_gemm_kernel<pair>: conv_fwd g_a.2 192->192 5x5 s2 @[8,192,128,128] on "
+                                         "prepared operands (the forward GEMM of the fused AdaRound iteration; CTA-pair "
+                                         "form, tcgen05 cta_group::2, M = 256 per MMA)",
             "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"],
             "peak_sustained": pk["tf_sustained"], "frac_of_sustained": ach / pk["tf_sustained"],
             "traffic": ncu_traffic("tc2_gather_gemm_kernel g_a.2"), "algorithmic_bytes": alg_bytes,
@@ -238,7 +239,8 @@ def run_cuda(args):
             "note": "kernel timed in isolation: graph replay, L2 flushed, flush subtracted; `peak` = measured BURST bf16 "
                     "figure; 3 bf16 MMA passes per product (fp32-accurate split) bound frac at 1/3; algorithmic bytes = "
                     "split-bf16 x (4 B/elem) + packed weights (4 B/elem) + fp32 y; `traffic` = dram bytes of this kernel "
-                    "from the committed ncu --set full capture; `unfused_op_*` = round 1's op (NHWC split + pack + GEMM)"}
+                    "from the committed ncu --set full capture (profiles/r2p_ncu_full_pair_raw.csv: tensor pipe 67 % of elapsed / "
+                    "81 % of active cycles, cold cache); `unfused_op_*` = round 1's op (NHWC split + pack + GEMM)"}
     del sess
     torch.cuda.empty_cache()
 
