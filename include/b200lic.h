@@ -282,6 +282,12 @@ typedef struct {
 enum { B200LIC_OP_CONV_FWD = 0, B200LIC_OP_DECONV_FWD = 1, B200LIC_OP_CONV_DGRAD = 2, B200LIC_OP_DECONV_DGRAD = 3,
        B200LIC_OP_CONV_WGRAD = 4, B200LIC_OP_DECONV_WGRAD = 5 };
 B200LIC_API size_t b200lic_conv_workspace_bytes(const b200lic_conv_desc* d, int op);
+/* How the generic tcgen05 engine would run a forward problem (host-side planning only, no device work; tests and tuning
+ * scripts): info[0] eligible, [1] output-channel tile BN, [2] channel tiles, [3] pixel tiles per CTA and work item,
+ * [4] pixel tiles of the largest phase, [5] work items, [6] CTA-pair form, [7] stream-K, [8] grid in CTAs, [9] shared-memory
+ * stages, [10] epilogue warps, [11] tensor-memory columns.  Folded-tap and short-K 1x1 layers take other kernels (the plan
+ * describes the generic engine only). */
+B200LIC_API int b200lic_conv_plan_info(const b200lic_conv_desc* d, int op, int* info);
 
 /* y = act(conv2d(x, w) + bias).  gdn_x (may be NULL unless gdn_mode) is [N,Cout,Ho,Wo]; norm_out (may be NULL)
  * receives the pre-(r)sqrt accumulator in gdn_mode. */

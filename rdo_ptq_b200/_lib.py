@@ -122,6 +122,7 @@ PLAIN = {"version": (C.c_int, []), "last_error_string": (C.c_char_p, []), "devic
                                         C.POINTER(C.c_void_p)]),
          "conv_packed_weight_bytes": (C.c_size_t, [_D, C.c_int]),
          "conv_stats_once": (C.c_int, [C.c_void_p]), "conv_stats_pending": (C.c_int, []),
+         "conv_plan_info": (C.c_int, [_D, C.c_int, C.POINTER(C.c_int)]),
          "conv_x_slot": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_int)]),
          "conv_dy_slot": (C.c_int, [_D, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

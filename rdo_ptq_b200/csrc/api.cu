@@ -89,6 +89,8 @@ void tc2_set_streamk_mode(int v);
 void tc2_set_pair_mode(int v);
 void tc2_stats_once(unsigned* keys);
 unsigned* tc2_stats_peek();
+void tc2_plan_info(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int transposed,
+                   int gdn_mode, int* info);
 void gemm1x1_set_mode(int v);
 }
 extern "C" {
@@ -107,6 +109,15 @@ int b200lic_set_option(const char* name, int value) {
   }
   b200lic::set_error("set_option: unknown option '%s'", name ? name : "(null)");
   return B200LIC_ERR_ARG;
+}
+int b200lic_conv_plan_info(const b200lic_conv_desc* d, int op, int* info) {
+  if (!d || !info || (op != B200LIC_OP_CONV_FWD && op != B200LIC_OP_DECONV_FWD)) {
+    b200lic::set_error("conv_plan_info: needs a descriptor, a forward op and 12 ints");
+    return B200LIC_ERR_ARG;
+  }
+  b200lic::tc2_plan_info(d->N, d->Cin, d->H, d->W, d->Cout, d->Ho, d->Wo, d->KH, d->KW, d->stride,
+                         op == B200LIC_OP_DECONV_FWD ? 1 : 0, d->gdn_mode, info);
+  return B200LIC_OK;
 }
 int b200lic_conv_stats_once(float* minmax) {
   b200lic::tc2_stats_once(reinterpret_cast<unsigned*>(minmax));

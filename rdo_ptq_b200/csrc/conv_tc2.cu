@@ -1320,6 +1320,23 @@ size_t tc2_workspace_bytes(int N, int Cin, int H, int W, int Cout, int Ho, int W
   return p.ok ? p.total_bytes : 0;
 }
 
+// The plan of the generic engine for a forward problem, for tests and tuning scripts (b200lic_conv_plan_info).
+// info: [0] eligible, [1] BN, [2] n_tiles, [3] MT, [4] pixel tiles of the largest phase, [5] work items, [6] pair,
+// [7] stream-K, [8] grid (CTAs), [9] shared-memory stages, [10] epilogue warps, [11] tensor-memory columns
+void tc2_plan_info(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int transposed,
+                   int gdn_mode, int* info) {
+  Tc2Plan p = make_plan2(N, Cin, H, W, Cout, Ho, Wo, KH, KW, stride, transposed, gdn_mode, 0);
+  for (int i = 0; i < 12; ++i) info[i] = 0;
+  if (!p.ok) return;
+  const long long items = (long long)p.phases * p.n_tiles * p.m_groups;
+  const int sms = num_sms();
+  int grid = (int)(items < sms ? items : sms);
+  if (p.pair) grid = 2 * (int)(items < sms / 2 ? items : sms / 2);
+  if (p.sk) grid = p.sk_grid * (p.pair ? 2 : 1);
+  const int v[12] = {1, p.BN, p.n_tiles, p.MT, p.m_tiles, (int)items, p.pair, p.sk, grid, p.stages, p.epi_warps, p.tmem_cols};
+  for (int i = 0; i < 12; ++i) info[i] = v[i];
+}
+
 // Generic launcher.  (N,Cin,H,W) gathered tensor, (Cout,Ho,Wo) written tensor, weight strides of the written /
 // gathered channel axes.
 int tc2_launch_wq(int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int KH, int KW, int stride, int pad,

@@ -183,6 +183,17 @@ def act_quant_stats(x):
 FUSE_ACTQ_STATS = os.environ.get("B200LIC_FUSE_ACTQ_STATS", "1") != "0"
 
 
+def conv_plan_info(d, transposed=False):
+    """Host-side plan of the generic conv engine for descriptor `d` (b200lic_conv_plan_info) as a dict."""
+    info = (C.c_int * 12)()
+    rc = _lib.lib().b200lic_conv_plan_info(C.byref(d), fwd_op(transposed), info)
+    if rc != 0:
+        raise _lib.B200LicError("conv_plan_info", rc, _lib.lib().b200lic_last_error_string().decode())
+    keys = ("eligible", "BN", "n_tiles", "MT", "m_tiles", "items", "pair", "stream_k", "grid", "stages", "epi_warps",
+            "tmem_cols")
+    return dict(zip(keys, list(info)))
+
+
 def conv_stats_arm(channels, device):
     """Fresh (min, max) keys for `channels` output channels and a request that the next conv-engine forward fills them."""
     keys = torch.empty(2 * channels, device=device, dtype=torch.int32)

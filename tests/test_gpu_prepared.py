@@ -449,6 +449,41 @@ def test_cta_pair_form_matches_the_single_cta_form(ops, dev, shape):
     assert ((outs[(2, 0)][0] - outs[(2, 2)][0]).norm() / outs[(2, 0)][0].norm()).item() < 4e-5
 
 
+@pytest.mark.parametrize("shape", [
+    # (N, Cin, H, W, Cout, k, stride, transposed) with an ODD number of pixel tiles at the widest channel tile: the peer
+    # CTA of the last pair has nothing to write (3 tiles; 5 tiles; 9 + ragged phases of a transposed conv)
+    (1, 64, 24, 16, 96, 3, 1, False), (1, 96, 40, 16, 128, 3, 1, False), (1, 64, 17, 24, 64, 5, 2, True)])
+def test_cta_pair_form_with_an_odd_tile_count(ops, dev, shape, monkeypatch):
+    """The widest output-channel tile is forced (B200LIC_TC_BN, an experiments knob: the cost model would give these few-
+    pixel shapes 16-channel tiles, which the pair form does not take), so that the pair form meets an odd pixel-tile count:
+    the last pair's second CTA loads a duplicate tile, joins the M = 256 MMAs and stores nothing."""
+    from rdo_ptq_b200 import _lib
+    monkeypatch.setenv("B200LIC_TC_BN", "256")
+    N, Cin, H, W, Cout, k, st, tr = shape
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn((Cin, Cout, k, k) if tr else (Cout, Cin, k, k), generator=g) * 0.05).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    F = torch.nn.functional
+    ref = (F.conv_transpose2d(x.double(), w.double(), b.double(), st, k // 2, st - 1) if tr
+           else F.conv2d(x.double(), w.double(), b.double(), st, k // 2))
+    outs = {}
+    try:
+        for pair in (0, 2):
+            assert _lib.lib().b200lic_set_option(b"pair", pair) == 0
+            d = ops.conv_desc(x.shape, w.shape, st, k // 2, tr, st - 1 if tr else 0)
+            info = ops.conv_plan_info(d, tr)
+            assert info["pair"] == (1 if pair else 0) and info["BN"] == Cout
+            if not tr:
+                assert info["m_tiles"] % 2 == 1
+            outs[pair] = ops.deconv2d_raw(x, w, b, d) if tr else ops.conv2d_raw(x, w, b, d)
+            torch.cuda.synchronize()
+    finally:
+        _lib.lib().b200lic_set_option(b"pair", 1)
+    assert ((outs[2].double() - ref).norm() / ref.norm()).item() < 2e-5
+    assert torch.equal(outs[0], outs[2])
+
+
 @pytest.mark.parametrize("case", [
     # N, Cin, H, W, Cout, k, stride, transposed, act: generic engine (pairs / single CTA), ragged tiles, padded channel
     # count, transposed conv (strided phase stores), 1x1 short-K engine, folded 3 -> N conv, stream-K owner

@@ -140,3 +140,44 @@ def test_bench_reference_arm_json_contract(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "1")                       # other ranks exit without work or output
     bench.run_reference(argparse.Namespace(steps=1, warmup=0))
     assert capsys.readouterr().out == ""
+
+
+def test_conv_engine_plan_pairs_and_options():
+    """b200lic_conv_plan_info (host-side planning, no device): the CTA-pair form is taken for every eligible shape (output-
+    channel tile a multiple of 32, at least two pixel tiles, not GDN), its grid is an even number of CTAs of at most the
+    SM count, one pixel tile per CTA with double-buffered accumulators; options "pair" / "streamk" switch the forms."""
+    from rdo_ptq_b200 import _lib, ops
+    L = _lib.lib()
+
+    def plan(shape, w, st, tr=False, gdn=False):
+        d = ops.gdn_desc(shape, False) if gdn else ops.conv_desc(shape, w, st, w[2] // 2, tr, st - 1 if tr else 0)
+        return ops.conv_plan_info(d, tr)
+
+    try:
+        p = plan((8, 192, 128, 128), (192, 192, 5, 5), 2)                    # g_a.2 of the benchmark
+        assert p["eligible"] and p["pair"] == 1 and p["BN"] == 192 and p["MT"] == 1 and p["stream_k"] == 0
+        assert p["m_tiles"] == 256 and p["items"] == 128 and p["grid"] == 148 and p["tmem_cols"] == 512
+        p2k = plan((1, 192, 768, 1024), (192, 192, 5, 5), 2)
+        assert p2k["pair"] == 1 and p2k["items"] == 768 and p2k["grid"] == 148
+        pt = plan((8, 192, 32, 32), (192, 192, 5, 5), 2, tr=True)           # four sub-pixel phases x 64 tiles
+        assert pt["pair"] == 1 and pt["items"] == 4 * 32 and pt["grid"] % 2 == 0
+        narrow = plan((1, 64, 24, 16), (96, 64, 3, 3), 1)                    # few pixels: the cost model spreads the
+        assert narrow["pair"] == 0 and narrow["BN"] == 16 and narrow["n_tiles"] == 6     # K loop over 16-channel tiles
+        os.environ["B200LIC_TC_BN"] = "256"                                  # (experiments knob: widest tile)
+        odd = plan((1, 64, 24, 16), (96, 64, 3, 3), 1)                       # 3 pixel tiles: the last pair has one
+        del os.environ["B200LIC_TC_BN"]
+        assert odd["pair"] == 1 and odd["BN"] == 96 and odd["m_tiles"] == 3 and odd["items"] == 2 and odd["grid"] == 4
+        small = plan((2, 16, 64, 64), (16, 16, 5, 5), 2)                     # 16-channel tile: single CTA
+        assert small["pair"] == 0 and small["grid"] == small["items"]
+        assert plan((8, 192, 128, 128), None, 1, gdn=True)["pair"] == 0      # GDN's K loop is six blocks
+        assert L.b200lic_set_option(b"pair", 0) == 0
+        single = plan((8, 192, 128, 128), (192, 192, 5, 5), 2)
+        assert single["pair"] == 0 and single["grid"] <= 148 and single["m_tiles"] == 256
+        assert L.b200lic_set_option(b"pair", 2) == 0 and L.b200lic_set_option(b"streamk", 2) == 0
+        sk = plan((8, 192, 128, 128), (192, 192, 5, 5), 2)                   # stream-K over the pairs (tests only)
+        assert sk["pair"] == 1 and sk["stream_k"] == 1 and sk["grid"] == 148
+        assert L.b200lic_set_option(b"nonsense", 1) != 0
+    finally:
+        os.environ.pop("B200LIC_TC_BN", None)
+        L.b200lic_set_option(b"pair", 1)
+        L.b200lic_set_option(b"streamk", 1)
