@@ -86,6 +86,40 @@ __device__ __forceinline__ float key2f(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Warp-wide fp32 min / max in one instruction (CREDUX.MIN/MAX.F32, sm_100a); NaN inputs are ignored like fminf / fmaxf.
+__device__ __forceinline__ float warp_redux_min_f32(float v) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float warp_redux_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+// Per-channel (min, max) of 16 channel values per lane over the lanes of a warp (one pixel per lane): lane j < 16 returns
+// the ordered-integer keys (f2key) of channel j.  `valid`: this lane's pixel exists (ragged tiles).
+__device__ __forceinline__ void warp_channel_minmax16(const float (&r)[16], bool valid, int lane, unsigned& kmn,
+                                                      unsigned& kmx) {
+  const bool allv = __all_sync(0xffffffffu, valid);
+  float fmn = INFINITY, fmx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float lo = r[j], hi = r[j];
+    if (!allv) {
+      lo = valid ? lo : INFINITY;
+      hi = valid ? hi : -INFINITY;
+    }
+    const float a = warp_redux_min_f32(lo), b = warp_redux_max_f32(hi);
+    if (lane == j) {
+      fmn = a;
+      fmx = b;
+    }
+  }
+  kmn = f2key(fmn);      // an all-invalid warp yields key(+inf) / key(-inf): neutral against any finite value
+  kmx = f2key(fmx);
+}
+
 // ---- programmatic dependent launch ----------------------------------------------------------------------------------
 // The kernels of the calibration sweep / evaluation forward are launched through launch_pdl(): such a kernel may be
 // scheduled as soon as the CTAs of its predecessor in the stream have exited (the implicit trigger), without waiting

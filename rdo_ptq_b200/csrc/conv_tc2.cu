@@ -869,20 +869,11 @@ __global__ void __launch_bounds__(kT2Threads, 1)
             for (int j = 0; j < 16; ++j) r[j] = rintf(fminf(fmaxf(r[j], -128.f), 128.f) * 256.f) * (1.f / 256.f);
           }
           if (stats != nullptr) {
-            // per-channel min / max of what this warp is about to store: ordered-integer keys (f2key), one integer warp
-            // reduction each, lane j keeps channel j's pair and merges it into the CTA's shared table
+            // per-channel min / max of what this warp is about to store: one fp32 warp reduction each (CREDUX), lane j keeps
+            // channel j's pair as ordered-integer keys (f2key) and merges it into the CTA's shared table
             const int lim = g.Cout - (co_base + c0 + h);
-            unsigned kmn = 0xffffffffu, kmx = 0u;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const unsigned k = f2key(r[j]);
-              const unsigned rmin = __reduce_min_sync(0xffffffffu, valid ? k : 0xffffffffu);
-              const unsigned rmax = __reduce_max_sync(0xffffffffu, valid ? k : 0u);
-              if (lane == j) {
-                kmn = rmin;
-                kmx = rmax;
-              }
-            }
+            unsigned kmn, kmx;
+            warp_channel_minmax16(r, valid, lane, kmn, kmx);
             if (lane < 16 && lane < lim) {
               const uint32_t ch = (uint32_t)(co_base + c0 + h + lane);
               asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(sStat + ch * 4u), "r"(kmn) : "memory");

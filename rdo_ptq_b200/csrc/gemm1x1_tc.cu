@@ -274,17 +274,8 @@ __global__ void __launch_bounds__(kG1Threads, 1)
           for (int j = 0; j < 16; ++j) r[j] = r[j] > 0.f ? r[j] : r[j] * slope;
         }
         if (stats != nullptr) {
-          unsigned kmn = 0xffffffffu, kmx = 0u;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const unsigned k = f2key(r[j]);
-            const unsigned rmin = __reduce_min_sync(0xffffffffu, valid ? k : 0xffffffffu);
-            const unsigned rmax = __reduce_max_sync(0xffffffffu, valid ? k : 0u);
-            if (lane == j) {
-              kmn = rmin;
-              kmx = rmax;
-            }
-          }
+          unsigned kmn, kmx;
+          warp_channel_minmax16(r, valid, lane, kmn, kmx);
           if (lane < 16 && c0 + lane < g.Cout) {
             atomicMin(s_stat + c0 + lane, kmn);
             atomicMax(s_stat + 256 + c0 + lane, kmx);
