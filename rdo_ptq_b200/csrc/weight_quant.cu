@@ -13,7 +13,7 @@
 
 namespace b200lic {
 
-constexpr float kZeta = 1.1f, kGamma = -0.1f;
+constexpr float kGamma = -0.1f;   // AdaRound's rectified sigmoid stretches (0, 1) to (gamma, zeta) = (-0.1, 1.1)
 constexpr float kStretch = 1.2f;  // fl32(zeta - gamma) = fl32(1.2000000000000002)
 
 // ---- K7a: one CTA per quantisation channel; tensor viewed as [outer, ch, inner] ---------------------
