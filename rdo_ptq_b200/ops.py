@@ -232,7 +232,8 @@ def act_quant_apply_stage(x, keys, n_bits, slot, square=False, out=None):
 DEFER_ACTQ = False
 # below this size the one-launch cluster kernel (b200lic_actq_fused) + the consumer's own split is cheaper than statistics
 # + apply_stage: deferring trades a pass over the tensor for one more launch
-DEFER_ACTQ_MIN_BYTES = 4 * 1000 * 1000
+# (B200LIC_DEFER_MIN_BYTES for A/B runs: 1 MB and 0.25 MB measure within 1 % of the default at 768x512 and 2K)
+DEFER_ACTQ_MIN_BYTES = int(os.environ.get("B200LIC_DEFER_MIN_BYTES", 4 * 1000 * 1000))
 
 
 class defer_actq:
