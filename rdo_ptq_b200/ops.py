@@ -198,7 +198,7 @@ def conv_stats_arm(channels, device):
     """Fresh (min, max) keys for `channels` output channels and a request that the next conv-engine forward fills them."""
     keys = torch.empty(2 * channels, device=device, dtype=torch.int32)
     call("actq_stats_init", _p(keys), channels)
-    _lib.lib().b200lic_conv_stats_once(_p(keys))
+    _lib.lib().b200lic_conv_stats_once(_p(keys))      # replaces a request an aborted caller may have left behind
     return keys
 
 
