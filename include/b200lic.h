@@ -237,6 +237,25 @@ B200LIC_API int b200lic_sq_err_sum(const float* a, const float* b, size_t n, flo
 /* out[0] += sum -log2(lik) */
 B200LIC_API int b200lic_bits_sum(const float* lik, size_t n, float* out, b200lic_stream_t stream);
 
+/* Token-major pieces of the Linear / LayerNorm wrappers (TO quantization/quant_layer.py:38-49,117-121; the Swin blocks of
+ * quant_block.py:330-641 are built from them).  F.linear over [rows, Cin] tokens is the 1x1 convolution of
+ * `rows` one-pixel images: describe it as b200lic_conv_desc{N=rows, Cin, H=W=1, Cout, Ho=Wo=1, KH=KW=1, stride 1, pad 0},
+ * stage the operand with b200lic_stage_tokens into the slot b200lic_conv_x_slot reports (fp32 rows -> split-bf16 rows,
+ * channels padded to cpad) and run b200lic_conv_fwd_packed with x = NULL: the output [rows, Cout, 1, 1] is the token
+ * matrix [rows, Cout]. */
+B200LIC_API int b200lic_stage_tokens(const float* x, size_t rows, int C, int cpad, void* x_hi, void* x_lo,
+                         b200lic_stream_t stream);
+/* F.layer_norm(x, (C,), gamma, beta, eps) over the last axis of x [rows, C] (gamma / beta may be NULL). */
+B200LIC_API int b200lic_layernorm_fwd(const float* x, const float* gamma, const float* beta, size_t rows, int C, float eps,
+                          float* y, b200lic_stream_t stream);
+/* ActQuantizer (TO quantizer.py:81-121) of a token-major tensor: per LAST-axis channel over all rows (the reference's 3-D
+ * branch, `x_clone[:,:,i]`), dynamic (min, max), n_bits levels; same arithmetic as b200lic_actq_apply.  minmax: 2*C words of
+ * scratch for the keys. */
+B200LIC_API int b200lic_actq_tokens(const float* x, size_t rows, int C, int n_bits, float* minmax, float* out,
+                        b200lic_stream_t stream);
+/* nn.GELU() in its exact (erf) form. */
+B200LIC_API int b200lic_gelu_fwd(const float* x, size_t n, float* y, b200lic_stream_t stream);
+
 /* MS-SSIM, the third number the reference's entry points report next to PSNR and bpp.
  * replaces: pytorch_msssim.ms_ssim(a, b, data_range=1.) at TO losses/losses.py:26,31,49-52, LU quantize.py:13,89,
  * quant.py:86, single_test.py:59-60, dataset_test.py:60-61 (third-party package, pytorch_msssim==1.0.0).

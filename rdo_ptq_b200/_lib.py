@@ -66,6 +66,10 @@ SIGNATURES = {
     "lp_loss_fwd_bwd_sched": [_P, _P, _P, _I, _SZ, _SZ, _I, _I, _P, _F, _F, _F, _P, _P],
     "sq_err_sum": [_P, _P, _SZ, _P],
     "bits_sum": [_P, _SZ, _P],
+    "stage_tokens": [_P, _SZ, _I, _I, _P, _P],
+    "layernorm_fwd": [_P, _P, _P, _SZ, _I, _F, _P],
+    "gelu_fwd": [_P, _SZ, _P],
+    "actq_tokens": [_P, _SZ, _I, _I, _P, _P],
     "ssim_level": [_P, _P, _P, _I, _I, _I, _F, _F, _P],
     "avg_pool2": [_P, _I, _I, _I, _I, _I, _P],
     "msssim_combine": [_P, _P, _I, _I, _P, _P],

@@ -186,3 +186,29 @@ class AttentionBlock(nn.Module):
 
     def forward(self, x):
         return ops.attn_gate(self.conv_a(x), self.conv_b(x), x)
+
+
+class GELU(nn.Module):
+    """nn.GELU() (exact form) on b200lic_gelu_fwd."""
+
+    def forward(self, x):
+        return ops.gelu(x)
+
+
+class Mlp(nn.Module):
+    """task-oriented-PTQ/models/layers.py:35-52 (the feed-forward half of a Swin block): fc1 -> GELU -> fc2 over token
+    tensors [..., C]; dropout is the identity at evaluation.  The Linear layers run on the tcgen05 conv engine
+    (ops.linear).  Forward only: see SURVEY 8(f) N4."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, x):
+        x = ops.linear(x, self.fc1.weight, self.fc1.bias)
+        x = self.act(x)
+        return ops.linear(x, self.fc2.weight, self.fc2.bias)

@@ -521,6 +521,59 @@ def bits_sum(lik):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ token-major ops
+def linear(x, w, bias=None, packed=None):
+    """F.linear(x, w, bias) for x [..., Cin], w [Cout, Cin] on the tcgen05 conv engine: the tokens are `rows` one-pixel
+    images, the token matrix is already the engine's NHWC operand (include/b200lic.h, "Token-major pieces").  `packed`:
+    a prepared weight operand of `linear_desc(rows, Cin, Cout)` (pack_weights of w.view(Cout, Cin, 1, 1))."""
+    x = _c(x, "input")
+    Cout, Cin = w.shape
+    if x.shape[-1] != Cin:
+        raise ValueError(f"linear: weight {tuple(w.shape)} does not match input features {x.shape[-1]}")
+    rows = x.numel() // Cin
+    d = linear_desc(rows, Cin, Cout)
+    ws = _workspace(d, _lib.OP_CONV_FWD, x.device)
+    slot = None if ws[0] is None else conv_x_slot(d, False, ws)
+    if slot is None:
+        raise _lib.B200LicError("linear", -4, f"no tensor-core plan for {rows} x {Cin} -> {Cout}")
+    hi, lo, cpad = slot
+    call("stage_tokens", _p(x), rows, Cin, cpad, hi, lo)
+    if packed is None:
+        packed = pack_weights(_c(w, "weight").view(Cout, Cin, 1, 1), d, False)
+    y = conv_fwd_packed(None, packed, d, False, bias=bias, ws=ws)
+    return y.view(*x.shape[:-1], Cout)
+
+
+def linear_desc(rows, Cin, Cout):
+    return conv_desc((rows, Cin, 1, 1), (Cout, Cin, 1, 1), 1, 0)
+
+
+def layer_norm(x, weight=None, bias=None, eps=1e-5):
+    """F.layer_norm over the last axis (b200lic_layernorm_fwd)."""
+    x = _c(x, "input")
+    Cc = x.shape[-1]
+    y = torch.empty_like(x)
+    call("layernorm_fwd", _p(x), _p(_c(weight)), _p(_c(bias)), x.numel() // Cc, Cc, float(eps), _p(y))
+    return y
+
+
+def act_quant_tokens(x, n_bits=8):
+    """ActQuantizer of a [..., C] token tensor: per last-axis channel over everything else (quantizer.py:81-121, 3-D branch)."""
+    x = _c(x.detach(), "activation")
+    Cc = x.shape[-1]
+    keys = torch.empty(2 * Cc, device=x.device, dtype=torch.int32)
+    out = torch.empty_like(x)
+    call("actq_tokens", _p(x), x.numel() // Cc, Cc, int(n_bits), _p(keys), _p(out))
+    return out
+
+
+def gelu(x):
+    x = _c(x, "input")
+    y = torch.empty_like(x)
+    call("gelu_fwd", _p(x), x.numel(), _p(y))
+    return y
+
+
 _SSIM_WIN = {}
 
 

@@ -1,14 +1,14 @@
 """B200 drop-in for the Cheng2020 part of task-oriented-PTQ/quantization/quant_block.py (:77-102, :219-328, :645-657).
 
-The Lu2022 Swin blocks of that file (QuantNIC/QuantMlp/QuantWindowAttention/...) are outside the hot path
-(SURVEY.md section 2 row 3).  Residual add, LeakyReLU and the block-level dynamic activation quantiser run as
+Of the Lu2022 Swin blocks of that file only QuantMlp (:330-350) is carried, forward only; window
+attention and the RSTB wrappers around it are not built.  Residual add, LeakyReLU and the block-level dynamic activation quantiser run as
 libb200lic kernels (`add_act`, K8).
 """
 import torch
 import torch.nn as nn
 
 from .. import ops
-from ..codec.layers import ResidualBlockWithStride, ResidualBlockUpsample, ResidualBlock, subpel_conv3x3
+from ..codec.layers import ResidualBlockWithStride, ResidualBlockUpsample, ResidualBlock, subpel_conv3x3, Mlp
 from .quant_layer import QuantModule
 from .quantizer import StraightThrough, UniformAffineQuantizer, ActQuantizer
 
@@ -125,6 +125,23 @@ class QuantSC(BaseQuantBlock):
     def forward(self, x):
         out = self.subpel_conv[1](self.subpel_conv[0](x))
         return ops.add_act_fn(out, None, ops.ACT_LEAKY_RELU, 0.01)
+
+
+class QuantMlp(BaseQuantBlock):
+    """quant_block.py:330-350: fc1 (its own activation quantiser disabled) -> act -> [A8] -> fc2.  Values only."""
+
+    def __init__(self, basic_block: Mlp, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.fc1 = QuantModule(basic_block.fc1, weight_quant_params, act_quant_params, disable_act_quant=True)
+        self.act = basic_block.act
+        self.fc2 = QuantModule(basic_block.fc2, weight_quant_params, act_quant_params)
+
+    def forward(self, x):
+        x = self.fc1(x)
+        x = ops.gelu(x) if isinstance(self.act, nn.GELU) or type(self.act).__name__ == "GELU" else self.act(x)
+        if self.use_act_quant and self.trained:
+            x = ActQuantizer(x)
+        return self.fc2(x)
 
 
 specials = {

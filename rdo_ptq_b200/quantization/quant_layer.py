@@ -38,6 +38,7 @@ class QuantModule(nn.Module):
                  se_module=None):
         super().__init__()
         self.if_layer_norm = False
+        self.is_linear = False
         self.if_tconv = False
         self.is_ps = False
         self.is_gdn = False
@@ -61,9 +62,19 @@ class QuantModule(nn.Module):
             self.fwd_kwargs = org_module.upscale_factor
             self.fwd_func = ops.pixel_shuffle
             self.is_ps = True
-        elif isinstance(org_module, (nn.Linear, nn.LayerNorm)):
-            raise NotImplementedError("Linear/LayerNorm wrappers belong to the Lu2022 Swin codec, which is outside the "
-                                      "B200 hot path (SURVEY.md 8(f) N4)")
+        elif isinstance(org_module, nn.Linear):
+            # quant_layer.py:38-41; forward only (evaluation): the Swin blocks that train through these wrappers
+            # (quant_block.py:330-641) are not built, SURVEY 8(f) N4
+            self.fwd_kwargs = dict()
+            self.fwd_func = ops.linear
+            self.is_linear = True
+        elif isinstance(org_module, nn.LayerNorm):
+            # quant_layer.py:43-48: gamma goes through the weight quantiser (a 1-D weight: one range for the tensor)
+            self.fwd_kwargs = dict(normalized_shape=org_module.normalized_shape, eps=org_module.eps)
+            self.fwd_func = ops.layer_norm
+            self.if_layer_norm = True
+            if len(org_module.normalized_shape) != 1:
+                raise NotImplementedError("LayerNorm over more than the last axis")
         else:
             raise ValueError('Not supported modules: {}'.format(org_module))
 
@@ -288,6 +299,8 @@ class QuantModule(nn.Module):
         act, slope = act_override if act_override is not None else ops._act_id(self.activation_function)
         if self.is_ps:
             return ops.pixel_shuffle(input, self.fwd_kwargs, act, slope)
+        if self.is_linear or self.if_layer_norm:
+            return self._forward_tokens(input)
         out = None
         fuse = self._stats_wanted()
         self._stat_keys = None
@@ -342,6 +355,35 @@ class QuantModule(nn.Module):
                 out = out.detach()
                 out._b200_actq = (keys if keys is not None else ops.act_quant_stats(out), bits)
                 return out
+            out = self.act_quantizer(out, True)
+        return out
+
+    def _forward_tokens(self, input):
+        """nn.Linear / nn.LayerNorm over token tensors (quant_layer.py:113-134 with fwd_func = F.linear / F.layer_norm):
+        the GEMM of a Linear runs on the tcgen05 conv engine (ops.linear), LayerNorm and the token-major activation
+        quantiser are one kernel each.  Values only: the reference trains alpha of these layers inside QuantRSTB block
+        reconstruction, which is not built."""
+        if torch.is_grad_enabled() and (input.requires_grad or any(
+                p.requires_grad for p in self.weight_quantizer.parameters())):
+            raise NotImplementedError("Linear / LayerNorm wrappers are forward-only (SURVEY.md 8(f) N4)")
+        if self.use_weight_quant:
+            weight, bias = self.weight_quantizer(self.weight).detach(), self.bias
+        else:
+            weight, bias = self.org_weight, self.org_bias
+        if self.is_linear:
+            out = ops.linear(input.detach(), weight, bias)
+        else:
+            out = ops.layer_norm(input.detach(), weight, bias, self.fwd_kwargs["eps"])
+        af = self.activation_function                  # an activation QuantModel absorbed from the nn.Sequential (:51-56)
+        if isinstance(af, nn.GELU) or type(af).__name__ == "GELU":
+            out = ops.gelu(out)
+        elif not isinstance(af, StraightThrough):
+            act, slope = ops._act_id(af)
+            if act != ops.ACT_NONE:
+                out = ops.add_act(out, None, act, slope)
+        if self.disable_act_quant:
+            return out
+        if self.use_act_quant and self.trained:
             out = self.act_quantizer(out, True)
         return out
 

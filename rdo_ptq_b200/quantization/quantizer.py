@@ -37,7 +37,10 @@ def lp_loss(pred, tgt, p=2.0, reduction='none'):
 
 def ActQuantizer(x: torch.Tensor, n_bits: int = 8):
     """reference quantizer.py:99-121: dynamic per-channel fake-quant, detached.  The reference hard-wires 8 bit
-    (`Handle_Parameter(b_w=8)`); `n_bits` is the additive knob BASELINE config 4 (W10A10) needs."""
+    (`Handle_Parameter(b_w=8)`); `n_bits` is the additive knob BASELINE config 4 (W10A10) needs.
+    4-D: per channel of axis 1; 3-D (token tensors of the Swin blocks, quantizer.py:107-109): per channel of the LAST axis."""
+    if x.dim() == 3:
+        return ops.act_quant_tokens(x, n_bits)
     return ops.act_quant(x, n_bits)
 
 
