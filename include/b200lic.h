@@ -253,6 +253,16 @@ B200LIC_API int b200lic_layernorm_fwd(const float* x, const float* gamma, const 
  * scratch for the keys. */
 B200LIC_API int b200lic_actq_tokens(const float* x, size_t rows, int C, int n_bits, float* minmax, float* out,
                         b200lic_stream_t stream);
+/* Window attention core of the Swin blocks (TO models/layers.py:137-166; quantised form quant_block.py:383-418), in two
+ * halves because the reference's ActQuantizer sits between them.  qkv: [B_, N, 3C] (q | k | v, each nH heads of C/nH);
+ * bias: [nH, N, N] relative-position bias already gathered; mask: [nW, N, N] shift mask or NULL (window b uses row
+ * b % nW).  N <= 64 tokens per window, head dimension <= 32 (B200LIC_ERR_UNSUPPORTED beyond).
+ *   P[b,h,i,j]   = softmax_j((q_i * scale) . k_j + bias[h,i,j] + mask[b % nW,i,j])        -> P [B_, nH, N, N]
+ *   out[b,i,h*hd+d] = sum_j P[b,h,i,j] * v[j,d]   (= (attn @ v).transpose(1, 2).reshape(B_, N, C))  -> out [B_, N, C] */
+B200LIC_API int b200lic_window_attn_softmax(const float* qkv, const float* bias, const float* mask, int B_, int N, int C, int nH,
+                                int nW, float scale, float* P, b200lic_stream_t stream);
+B200LIC_API int b200lic_window_attn_apply(const float* P, const float* qkv, int B_, int N, int C, int nH, float* out,
+                              b200lic_stream_t stream);
 /* nn.GELU() in its exact (erf) form. */
 B200LIC_API int b200lic_gelu_fwd(const float* x, size_t n, float* y, b200lic_stream_t stream);
 

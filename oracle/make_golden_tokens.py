@@ -1,7 +1,8 @@
 """Golden vectors for the token-major wrappers: outputs of the REFERENCE's own code, imported unmodified
 from /root/reference through oracle/_ref_shim.py -- `QuantModule` over nn.Linear and nn.LayerNorm
 (task-oriented-PTQ/quantization/quant_layer.py:38-49,105-134), `ActQuantizer` on 3-D tensors (quantizer.py:81-121), and the
-`Mlp` of models/layers.py:35-52 wrapped as `QuantMlp` (quant_block.py:330-350).  TEST INFRASTRUCTURE ONLY; runs only where
+`Mlp` of models/layers.py:35-52 wrapped as `QuantMlp` (quant_block.py:330-350), the attention core of `WindowAttention`
+(models/layers.py:137-166) and an `RSTB` wrapped as `QuantRSTB` (quant_block.py:601-641).  TEST INFRASTRUCTURE ONLY; runs only where
 /root/reference exists.  Writes tests/golden/tokens_ref.pt (committed):
 
     python -m oracle.make_golden_tokens
@@ -65,6 +66,45 @@ def token_vectors():
         qmlp.set_quant_state(True, True)
         rec["wa"] = qmlp(x).clone()
         G["mlp_w8"] = rec
+        # window attention core, from the reference's WindowAttention (models/layers.py:137-166) on shifted windows
+        att = r_layers.WindowAttention(32, (4, 4), 4).eval()
+        att.relative_position_bias_table.copy_(0.5 * torch.randn(att.relative_position_bias_table.shape, generator=g))
+        blk = r_layers.SwinTransformerBlock(32, (8, 12), 4, window_size=4, shift_size=2)
+        xw = torch.randn(2 * 6, 16, 32, generator=g)
+        qkv = att.qkv(xw)
+        B_, N, C = xw.shape
+        q, k, v = qkv.reshape(B_, N, 3, 4, C // 4).permute(2, 0, 3, 1, 4)
+        a_ = (q * att.scale) @ k.transpose(-2, -1)
+        bias = att.relative_position_bias_table[att.relative_position_index.view(-1)].view(N, N, -1).permute(2, 0, 1)
+        a_ = a_ + bias.unsqueeze(0)
+        a_ = (a_.view(B_ // 6, 6, 4, N, N) + blk.attn_mask.unsqueeze(1).unsqueeze(0)).view(-1, 4, N, N).softmax(-1)
+        G["attn_core"] = {"qkv": qkv.clone(), "bias": bias.contiguous().clone(), "mask": blk.attn_mask.clone(),
+                          "scale": att.scale, "attn": a_.clone(), "out": (a_ @ v).transpose(1, 2).reshape(B_, N, C).clone(),
+                          "x": xw.clone(), "state": {k_: v_.clone() for k_, v_ in att.state_dict().items()},
+                          "module_out": att(xw, mask=blk.attn_mask).clone()}
+        # QuantRSTB (quant_block.py:601-641) over an RSTB with one plain and one shifted block
+        rstb = r_layers.RSTB(dim=32, input_resolution=(8, 8), depth=2, num_heads=4, window_size=4, mlp_ratio=2.).eval()
+        for n_, p_ in rstb.named_parameters():
+            if "relative_position_bias_table" in n_:
+                p_.copy_(0.5 * torch.randn(p_.shape, generator=g))
+            elif n_.endswith("norm1.weight") or n_.endswith("norm2.weight"):
+                p_.copy_(1 + 0.2 * torch.randn(p_.shape, generator=g))
+            elif n_.endswith("bias"):
+                p_.copy_(0.1 * torch.randn(p_.shape, generator=g))
+            else:
+                p_.copy_(0.15 * torch.randn(p_.shape, generator=g))
+        xm = torch.randn(2, 32, 8, 8, generator=g)
+        qr = r_qb.QuantRSTB(copy.deepcopy(rstb), WQ8, AQ8).eval()
+        rec = {"x": xm.clone(), "state": {k_: v_.clone() for k_, v_ in rstb.state_dict().items()},
+               "fp_module": rstb(xm, (8, 8)).clone(), "fp": qr(xm, (8, 8)).clone()}
+        qr.set_quant_state(True, False)
+        rec["w"] = qr(xm, (8, 8)).clone()
+        for m in qr.modules():
+            if hasattr(m, "trained"):
+                m.trained = True
+        qr.set_quant_state(True, True)
+        rec["wa"] = qr(xm, (8, 8)).clone()
+        G["rstb_w8"] = rec
     return G
 
 

@@ -69,6 +69,8 @@ SIGNATURES = {
     "stage_tokens": [_P, _SZ, _I, _I, _P, _P],
     "layernorm_fwd": [_P, _P, _P, _SZ, _I, _F, _P],
     "gelu_fwd": [_P, _SZ, _P],
+    "window_attn_softmax": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "window_attn_apply": [_P, _P, _I, _I, _I, _I, _P],
     "actq_tokens": [_P, _SZ, _I, _I, _P, _P],
     "ssim_level": [_P, _P, _P, _I, _I, _I, _F, _F, _P],
     "avg_pool2": [_P, _I, _I, _I, _I, _I, _P],

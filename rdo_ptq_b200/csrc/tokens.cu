@@ -108,6 +108,69 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- window attention core (TO models/layers.py:137-166, quant_block.py:383-418) -----------------------------------------
+// qkv [B_, N, 3C] (the output of the qkv Linear: q | k | v, each [nH, hd] per token).  One CTA per (window b, head h).
+// P[b,h,i,j] = softmax_j( (q_i * scale) . k_j + bias[h,i,j] + mask[b % nW, i, j] )
+// out[b, i, h*hd + d] = sum_j P[b,h,i,j] * v[j,d]        (= (attn @ v).transpose(1, 2).reshape(B_, N, C))
+// The two halves are separate kernels because the reference quantises P (dynamic, per head over ALL windows) in between.
+constexpr int kAttnMaxN = 64, kAttnMaxD = 32;
+
+__global__ void __launch_bounds__(256)
+    window_attn_softmax_kernel(const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,
+                               int N, int C, int nH, int nW, float scale, float* __restrict__ P) {
+  __shared__ float qs[kAttnMaxN][kAttnMaxD + 1], ks[kAttnMaxN][kAttnMaxD + 1], S[kAttnMaxN][kAttnMaxN + 1];
+  const int b = blockIdx.x / nH, h = blockIdx.x % nH, hd = C / nH;
+  const float* base = qkv + (size_t)b * N * 3 * C + (size_t)h * hd;
+  for (int e = threadIdx.x; e < N * hd; e += blockDim.x) {
+    const int i = e / hd, d = e - i * hd;
+    qs[i][d] = __ldg(base + (size_t)i * 3 * C + d) * scale;
+    ks[i][d] = __ldg(base + (size_t)i * 3 * C + C + d);
+  }
+  __syncthreads();
+  const float* bh = bias + (size_t)h * N * N;
+  const float* mw = mask ? mask + (size_t)(b % nW) * N * N : nullptr;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int i = e / N, j = e - i * N;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc = fmaf(qs[i][d], ks[j][d], acc);
+    acc += __ldg(bh + e);
+    if (mw) acc += __ldg(mw + e);
+    S[i][j] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* Pb = P + ((size_t)b * nH + h) * N * N;
+  for (int i = warp; i < N; i += nwarps) {
+    const float a0 = lane < N ? S[i][lane] : -INFINITY, a1 = lane + 32 < N ? S[i][lane + 32] : -INFINITY;
+    const float mx = warp_max(fmaxf(a0, a1));
+    const float e0 = lane < N ? expf(a0 - mx) : 0.f, e1 = lane + 32 < N ? expf(a1 - mx) : 0.f;
+    const float sum = warp_sum(e0 + e1);
+    if (lane < N) Pb[(size_t)i * N + lane] = e0 / sum;
+    if (lane + 32 < N) Pb[(size_t)i * N + lane + 32] = e1 / sum;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    window_attn_apply_kernel(const float* __restrict__ P, const float* __restrict__ qkv, int N, int C, int nH,
+                             float* __restrict__ out) {
+  __shared__ float Ps[kAttnMaxN][kAttnMaxN + 1], vs[kAttnMaxN][kAttnMaxD + 1];
+  const int b = blockIdx.x / nH, h = blockIdx.x % nH, hd = C / nH;
+  const float* Pb = P + ((size_t)b * nH + h) * N * N;
+  const float* vbase = qkv + (size_t)b * N * 3 * C + 2 * (size_t)C + (size_t)h * hd;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) Ps[e / N][e % N] = __ldg(Pb + e);
+  for (int e = threadIdx.x; e < N * hd; e += blockDim.x) {
+    const int j = e / hd, d = e - j * hd;
+    vs[j][d] = __ldg(vbase + (size_t)j * 3 * C + d);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * hd; e += blockDim.x) {
+    const int i = e / hd, d = e - i * hd;
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) acc = fmaf(Ps[i][j], vs[j][d], acc);
+    out[((size_t)b * N + i) * C + (size_t)h * hd + d] = acc;
+  }
+}
+
 }  // namespace b200lic
 
 using namespace b200lic;
@@ -149,6 +212,40 @@ int b200lic_actq_tokens(const float* x, size_t rows, int C, int n_bits, float* m
   const size_t n = rows * (size_t)C;
   actq_tokens_apply_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, keys, n, C, (float)((1 << n_bits) - 1), out);
   B200_LAUNCH_CHECK("actq_tokens_apply_kernel");
+  return B200LIC_OK;
+}
+
+static int window_attn_check(const char* name, int B_, int N, int C, int nH) {
+  B200_REQUIRE(B_ > 0 && N > 0 && C > 0 && nH > 0 && C % nH == 0, "%s: bad shape", name);
+  if (N > kAttnMaxN || C / nH > kAttnMaxD) {
+    set_error("%s: window of %d tokens x head dimension %d exceeds %d x %d", name, N, C / nH, kAttnMaxN, kAttnMaxD);
+    return B200LIC_ERR_UNSUPPORTED;
+  }
+  B200_REQUIRE((long long)B_ * nH < 2147483647LL, "%s: too many windows", name);
+  return B200LIC_OK;
+}
+
+int b200lic_window_attn_softmax(const float* qkv, const float* bias, const float* mask, int B_, int N, int C, int nH, int nW,
+                                float scale, float* P, b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(qkv && bias && P, "window_attn_softmax: null pointer");
+  int rc = window_attn_check("window_attn_softmax", B_, N, C, nH);
+  if (rc != B200LIC_OK) return rc;
+  B200_REQUIRE(!mask || (nW > 0 && B_ % nW == 0), "window_attn_softmax: %d windows do not tile a batch of %d", nW, B_);
+  window_attn_softmax_kernel<<<(unsigned)(B_ * nH), 256, 0, as_stream(stream)>>>(qkv, bias, mask, N, C, nH, mask ? nW : 1,
+                                                                                 scale, P);
+  B200_LAUNCH_CHECK("window_attn_softmax_kernel");
+  return B200LIC_OK;
+}
+
+int b200lic_window_attn_apply(const float* P, const float* qkv, int B_, int N, int C, int nH, float* out,
+                              b200lic_stream_t stream) {
+  B200_ARCH_GATE();
+  B200_REQUIRE(P && qkv && out, "window_attn_apply: null pointer");
+  int rc = window_attn_check("window_attn_apply", B_, N, C, nH);
+  if (rc != B200LIC_OK) return rc;
+  window_attn_apply_kernel<<<(unsigned)(B_ * nH), 256, 0, as_stream(stream)>>>(P, qkv, N, C, nH, out);
+  B200_LAUNCH_CHECK("window_attn_apply_kernel");
   return B200LIC_OK;
 }
 

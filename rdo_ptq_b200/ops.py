@@ -567,6 +567,27 @@ def act_quant_tokens(x, n_bits=8):
     return out
 
 
+def window_attn_softmax(qkv, bias, mask, num_heads, scale):
+    """softmax((q * scale) @ k^T + bias [+ mask]) of window attention: qkv [B_, N, 3C] -> P [B_, nH, N, N]."""
+    qkv, bias = _c(qkv, "qkv"), _c(bias, "bias")
+    B_, N, C3 = qkv.shape
+    Cc = C3 // 3
+    P = torch.empty(B_, num_heads, N, N, device=qkv.device, dtype=torch.float32)
+    nW = 1 if mask is None else mask.shape[0]
+    call("window_attn_softmax", _p(qkv), _p(bias), _p(_c(mask)), B_, N, Cc, num_heads, nW, float(scale), _p(P))
+    return P
+
+
+def window_attn_apply(P, qkv):
+    """(P @ v).transpose(1, 2).reshape(B_, N, C) with v taken from qkv [B_, N, 3C]."""
+    P, qkv = _c(P, "attn"), _c(qkv, "qkv")
+    B_, nH, N, _ = P.shape
+    Cc = qkv.shape[2] // 3
+    out = torch.empty(B_, N, Cc, device=qkv.device, dtype=torch.float32)
+    call("window_attn_apply", _p(P), _p(qkv), B_, N, Cc, nH, _p(out))
+    return out
+
+
 def gelu(x):
     x = _c(x, "input")
     y = torch.empty_like(x)

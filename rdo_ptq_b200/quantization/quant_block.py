@@ -1,7 +1,8 @@
 """B200 drop-in for the Cheng2020 part of task-oriented-PTQ/quantization/quant_block.py (:77-102, :219-328, :645-657).
 
-Of the Lu2022 Swin blocks of that file only QuantMlp (:330-350) is carried, forward only; window
-attention and the RSTB wrappers around it are not built.  Residual add, LeakyReLU and the block-level dynamic activation quantiser run as
+The Lu2022 Swin blocks of that file (QuantMlp :330-350, QuantWindowAttention :353-423, QuantSwinTransformerBlock :426-553,
+QuantBasicLayer :556-598, QuantRSTB :601-641) are carried FORWARD ONLY: block reconstruction through
+them, and the NIC / TinyLIC graphs that use them, are not built.  Residual add, LeakyReLU and the block-level dynamic activation quantiser run as
 libb200lic kernels (`add_act`, K8).
 """
 import torch
@@ -9,6 +10,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..codec.layers import ResidualBlockWithStride, ResidualBlockUpsample, ResidualBlock, subpel_conv3x3, Mlp
+from ..codec import swin
 from .quant_layer import QuantModule
 from .quantizer import StraightThrough, UniformAffineQuantizer, ActQuantizer
 
@@ -144,7 +146,88 @@ class QuantMlp(BaseQuantBlock):
         return self.fc2(x)
 
 
+class QuantWindowAttention(BaseQuantBlock):
+    """quant_block.py:353-423: qkv and proj as QuantModules; the dynamic quantiser sits on the attention matrix (per head,
+    4-D) and on the attention output (per channel, 3-D) once the block is trained."""
+
+    def __init__(self, basic_block: swin.WindowAttention, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.dim, self.window_size, self.num_heads = basic_block.dim, basic_block.window_size, basic_block.num_heads
+        self.scale = basic_block.scale
+        self.qkv = QuantModule(basic_block.qkv, weight_quant_params, act_quant_params)
+        self.proj = QuantModule(basic_block.proj, weight_quant_params, act_quant_params)
+        self.relative_position_bias_table = basic_block.relative_position_bias_table
+        self.relative_position_index = basic_block.relative_position_index
+
+    def forward(self, x, mask=None):
+        qkv = self.qkv(x)
+        bias = swin.gathered_bias(self.relative_position_bias_table, self.relative_position_index, x.shape[1])
+        attn = ops.window_attn_softmax(qkv, bias, mask, self.num_heads, self.scale)
+        quantise = self.use_act_quant and self.trained
+        if quantise:
+            attn = ActQuantizer(attn)
+        out = ops.window_attn_apply(attn, qkv)
+        if quantise:
+            out = ActQuantizer(out)
+        return self.proj(out)
+
+
+class QuantSwinTransformerBlock(BaseQuantBlock):
+    """quant_block.py:426-553: LayerNorms as QuantModules, quantised attention and Mlp, block output quantised when
+    trained."""
+
+    def __init__(self, basic_block: swin.SwinTransformerBlock, weight_quant_params: dict = {},
+                 act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.geom = basic_block            # window / shift geometry and the cached mask (no parameters of its own are used)
+        self.norm1 = QuantModule(basic_block.norm1, weight_quant_params, act_quant_params)
+        self.attn = QuantWindowAttention(basic_block.attn, weight_quant_params, act_quant_params)
+        self.norm2 = QuantModule(basic_block.norm2, weight_quant_params, act_quant_params)
+        self.mlp = QuantMlp(basic_block.mlp, weight_quant_params, act_quant_params)
+
+    def forward(self, x, x_size):
+        y = self.geom.attend(self.attn, self.norm1(x), x_size)
+        x = ops.add_act(x, y.contiguous())
+        x = ops.add_act(x, self.mlp(self.norm2(x)))
+        if self.use_act_quant and self.trained:
+            x = ActQuantizer(x)
+        return x
+
+
+class QuantBasicLayer(BaseQuantBlock):
+    """quant_block.py:556-598."""
+
+    def __init__(self, basic_block: swin.BasicLayer, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.blocks = nn.ModuleList([QuantSwinTransformerBlock(b, weight_quant_params, act_quant_params)
+                                     for b in basic_block.blocks])
+
+    def forward(self, x, x_size):
+        for blk in self.blocks:
+            x = blk(x, x_size)
+        return x
+
+
+class QuantRSTB(BaseQuantBlock):
+    """quant_block.py:601-641: tokens through the quantised BasicLayer, back to a feature map, plus the input; the sum is
+    quantised (4-D, per channel) when the block is trained."""
+
+    def __init__(self, basic_block: swin.RSTB, weight_quant_params: dict = {}, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.dim, self.input_resolution = basic_block.dim, basic_block.input_resolution
+        self.residual_group = QuantBasicLayer(basic_block.residual_group, weight_quant_params, act_quant_params)
+        self.patch_embed, self.patch_unembed = swin.PatchEmbed(), swin.PatchUnEmbed()
+
+    def forward(self, x, x_size):
+        y = self.patch_unembed(self.residual_group(self.patch_embed(x), x_size), x_size)
+        out = ops.add_act(y, x)
+        if self.use_act_quant and self.trained:
+            out = ActQuantizer(out)
+        return out
+
+
 specials = {
+    swin.RSTB: QuantRSTB,
     ResidualBlockWithStride: QuantRBWS,
     ResidualBlockUpsample: QuantRBU,
     ResidualBlock: QuantRB,
