@@ -181,3 +181,43 @@ def test_conv_engine_plan_pairs_and_options():
         os.environ.pop("B200LIC_TC_BN", None)
         L.b200lic_set_option(b"pair", 1)
         L.b200lic_set_option(b"streamk", 1)
+
+
+def test_quant_model_rewrites_swin_blocks_like_the_reference():
+    """QuantModel's graph rewrite (quant_model.py:23-66) over a model that holds convolutions and an RSTB: the RSTB becomes
+    a QuantRSTB (specials), its Linear / LayerNorm children QuantModules, with the same module tree as the reference's own
+    QuantModel builds from its own RSTB (imported through the shim when /root/reference is present).  Construction only."""
+    import torch.nn as nn
+    from rdo_ptq_b200 import codec, quantization as Q
+
+    def tiny(rstb_cls, conv=nn.Conv2d):
+        class Net(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.g_a0 = conv(3, 32, 5, stride=2, padding=2)
+                self.g_a1 = rstb_cls(dim=32, input_resolution=(8, 8), depth=2, num_heads=4, window_size=4, mlp_ratio=2.)
+                self.g_a2 = conv(32, 32, 3, stride=2, padding=1)
+        return Net()
+
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    q = Q.QuantModel(tiny(codec.RSTB), wq, aq)
+    assert isinstance(q.model.g_a1, Q.QuantRSTB) and isinstance(q.model.g_a0, Q.QuantModule)
+    blk = q.model.g_a1.residual_group.blocks[1]
+    assert isinstance(blk, Q.QuantSwinTransformerBlock) and blk.geom.shift_size == 2 and blk.geom.attn_mask is not None
+    assert isinstance(blk.attn.qkv, Q.QuantModule) and blk.attn.qkv.is_linear and blk.norm1.if_layer_norm
+    assert blk.mlp.fc1.disable_act_quant and not blk.mlp.fc2.disable_act_quant
+
+    def tree(model, QM, QB):
+        return [(n.replace(".geom", "@"), type(m).__name__) for n, m in model.named_modules()
+                if isinstance(m, (QM, QB)) and ".geom." not in n]
+
+    mine = tree(q, Q.QuantModule, Q.BaseQuantBlock)
+    assert len([t for t in mine if t[1] == "QuantModule"]) == 2 + 12
+    from oracle import _ref_shim as S
+    if S.available():
+        TO = S.import_task_oriented()
+        from quantization import quant_layer as r_ql, quant_block as r_qb
+        from models import layers as r_layers
+        r = TO.QuantModel(tiny(r_layers.RSTB), wq, aq)
+        assert tree(r, r_ql.QuantModule, r_qb.BaseQuantBlock) == mine
