@@ -256,7 +256,7 @@ B200LIC_API int b200lic_actq_tokens(const float* x, size_t rows, int C, int n_bi
 /* Window attention core of the Swin blocks (TO models/layers.py:137-166; quantised form quant_block.py:383-418), in two
  * halves because the reference's ActQuantizer sits between them.  qkv: [B_, N, 3C] (q | k | v, each nH heads of C/nH);
  * bias: [nH, N, N] relative-position bias already gathered; mask: [nW, N, N] shift mask or NULL (window b uses row
- * b % nW).  N <= 64 tokens per window, head dimension <= 32 (B200LIC_ERR_UNSUPPORTED beyond).
+ * b % nW).  N <= 64 tokens per window, head dimension <= 48 (B200LIC_ERR_UNSUPPORTED beyond).
  *   P[b,h,i,j]   = softmax_j((q_i * scale) . k_j + bias[h,i,j] + mask[b % nW,i,j])        -> P [B_, nH, N, N]
  *   out[b,i,h*hd+d] = sum_j P[b,h,i,j] * v[j,d]   (= (attn @ v).transpose(1, 2).reshape(B_, N, C))  -> out [B_, N, C] */
 B200LIC_API int b200lic_window_attn_softmax(const float* qkv, const float* bias, const float* mask, int B_, int N, int C, int nH,

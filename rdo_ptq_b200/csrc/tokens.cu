@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256)
 // P[b,h,i,j] = softmax_j( (q_i * scale) . k_j + bias[h,i,j] + mask[b % nW, i, j] )
 // out[b, i, h*hd + d] = sum_j P[b,h,i,j] * v[j,d]        (= (attn @ v).transpose(1, 2).reshape(B_, N, C))
 // The two halves are separate kernels because the reference quantises P (dynamic, per head over ALL windows) in between.
-constexpr int kAttnMaxN = 64, kAttnMaxD = 32;
+constexpr int kAttnMaxN = 64, kAttnMaxD = 48;   // Lu2022: 8 x 8 windows, head dimension 12 ... 48 (192 channels on 4 heads)
 
 __global__ void __launch_bounds__(256)
     window_attn_softmax_kernel(const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ mask,

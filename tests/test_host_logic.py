@@ -221,3 +221,36 @@ def test_quant_model_rewrites_swin_blocks_like_the_reference():
         from models import layers as r_layers
         r = TO.QuantModel(tiny(r_layers.RSTB), wq, aq)
         assert tree(r, r_ql.QuantModule, r_qb.BaseQuantBlock) == mine
+
+
+def test_lu2022_graph_and_its_rewrite_match_the_reference():
+    """codec.NIC (the Lu2022 graph, nic_cvt.py:21-330): same state-dict keys and shapes as the reference's own NIC, and
+    QuantModel rewrites it into the same tree of QuantModules / QuantRSTBs (imported through the shim).  Construction only:
+    the composed forward has not been run on hardware (see the header of rdo_ptq_b200/codec/nic.py)."""
+    import warnings
+    from rdo_ptq_b200 import codec, quantization as Q
+    from oracle import _ref_shim as S
+    cfg = dict(height=128, width=128, in_chans=3, embed_dim=32, latent_dim=48, window_size=4, mlp_ratio=2., qkv_bias=True,
+               qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, use_checkpoint=False)
+    wq = dict(n_bits=8, channel_wise=True, scale_method="max")
+    aq = dict(n_bits=8, channel_wise=True, scale_method="max", leaf_param=False)
+    m = codec.NIC(cfg)
+    assert m.g_a1.residual_group.blocks[1].shift_size == 2 and m.h_a1.residual_group.blocks[0].window_size == 2
+    q = Q.QuantModel(codec.NIC(cfg), wq, aq)
+    mine = [(n, type(mod).__name__) for n, mod in q.named_modules()
+            if isinstance(mod, (Q.QuantModule, Q.BaseQuantBlock)) and ".geom." not in n]
+    assert sum(1 for _, t in mine if t == "QuantRSTB") == 12
+    if not S.available():
+        return
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        TO = S.import_task_oriented()
+        from quantization import quant_layer as r_ql, quant_block as r_qb
+        from models import nic_cvt as r_nic
+        r = r_nic.NIC(cfg)
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == \
+               {k: tuple(v.shape) for k, v in r.state_dict().items()}
+        rq = TO.QuantModel(r_nic.NIC(cfg), wq, aq)
+        ref = [(n, type(mod).__name__) for n, mod in rq.named_modules()
+               if isinstance(mod, (r_ql.QuantModule, r_qb.BaseQuantBlock))]
+        assert mine == ref
